@@ -1,0 +1,902 @@
+/* oracle/tahoe_oracle.c -- TEST INFRASTRUCTURE ONLY (see tahoe_oracle.h).
+ *
+ * Plain-C restatement of the reference algorithm for the Hex8 hot path.
+ * Every function cites the reference file:line (relative to /root/reference)
+ * it follows, including loop / summation order where the reference fixes one.
+ * Written for clarity, not speed: this is the checker, never the product.
+ */
+#include "tahoe_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SQRT23 0.81649658092772603273 /* sqrt(2/3), J2SimoC0HardeningT.cpp:11 */
+static const double kYieldTol = 1.0e-10; /* J2SimoC0HardeningT.cpp:12 */
+
+/* ------------------------------------------------------------------ */
+/* small dense helpers (column-major 3x3: A[i+3j])                     */
+/* ------------------------------------------------------------------ */
+static double det3(const double* A)
+{
+    return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[3] * (A[1] * A[8] - A[2] * A[7]) + A[6] * (A[1] * A[5] - A[2] * A[4]);
+}
+static void inv3(const double* A, double det, double* B)
+{
+    double r = 1.0 / det;
+    B[0] = (A[4] * A[8] - A[5] * A[7]) * r;
+    B[1] = -(A[1] * A[8] - A[2] * A[7]) * r;
+    B[2] = (A[1] * A[5] - A[2] * A[4]) * r;
+    B[3] = -(A[3] * A[8] - A[5] * A[6]) * r;
+    B[4] = (A[0] * A[8] - A[2] * A[6]) * r;
+    B[5] = -(A[0] * A[5] - A[2] * A[3]) * r;
+    B[6] = (A[3] * A[7] - A[4] * A[6]) * r;
+    B[7] = -(A[0] * A[7] - A[1] * A[6]) * r;
+    B[8] = (A[0] * A[4] - A[1] * A[3]) * r;
+}
+static void mul3(const double* A, const double* B, double* C) /* C = A B */
+{
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) {
+            double s = 0.0;
+            for (int k = 0; k < 3; k++) s += A[i + 3 * k] * B[k + 3 * j];
+            C[i + 3 * j] = s;
+        }
+}
+/* symmetric (11,22,33,23,13,12) <-> full */
+static const int VI[6] = {0, 1, 2, 1, 0, 0};
+static const int VJ[6] = {0, 1, 2, 2, 2, 1};
+static void sym_to_mat(const double* s, double* A)
+{
+    A[0] = s[0]; A[4] = s[1]; A[8] = s[2];
+    A[5] = A[7] = s[3]; A[2] = A[6] = s[4]; A[1] = A[3] = s[5];
+}
+static double sym_det(const double* s)
+{
+    double A[9];
+    sym_to_mat(s, A);
+    return det3(A);
+}
+static double sym_trace(const double* s) { return s[0] + s[1] + s[2]; }
+static void sym_dev(double* s)
+{
+    double p = sym_trace(s) / 3.0;
+    s[0] -= p; s[1] -= p; s[2] -= p;
+}
+static double sym_scalar_product(const double* s) /* dSymMatrixT::ScalarProduct: s:s */
+{
+    return s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + 2.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
+}
+/* B = Q A Q^T with A symmetric (dSymMatrixT::MultQBQT) */
+static void sym_QAQT(const double* Q, const double* a, double* b)
+{
+    double A[9], T[9], R[9];
+    sym_to_mat(a, A);
+    mul3(Q, A, T);
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) {
+            double s = 0.0;
+            for (int k = 0; k < 3; k++) s += T[i + 3 * k] * Q[j + 3 * k];
+            R[i + 3 * j] = s;
+        }
+    for (int I = 0; I < 6; I++) b[I] = R[VI[I] + 3 * VJ[I]];
+}
+/* b = F F^T, FSSolidMatT::Compute_b (FSSolidMatT.cpp:402-434) */
+static void compute_b(const double* f, double* a)
+{
+    a[0] = f[0] * f[0] + f[3] * f[3] + f[6] * f[6];
+    a[1] = f[1] * f[1] + f[4] * f[4] + f[7] * f[7];
+    a[2] = f[2] * f[2] + f[5] * f[5] + f[8] * f[8];
+    a[3] = f[1] * f[2] + f[4] * f[5] + f[7] * f[8];
+    a[4] = f[0] * f[2] + f[3] * f[5] + f[6] * f[8];
+    a[5] = f[0] * f[1] + f[3] * f[4] + f[6] * f[7];
+}
+
+/* ------------------------------------------------------------------ */
+/* materials                                                           */
+/* ------------------------------------------------------------------ */
+/* IsotropicT::Set_E_nu (materials/primitives/IsotropicT.cpp:32-45) */
+void orc_material_from_E_nu(orc_material_t* m, int kind, double E, double nu, double density)
+{
+    memset(m, 0, sizeof(*m));
+    m->kind = kind;
+    m->mu = 0.5 * E / (1.0 + nu);
+    m->lambda = 2.0 * m->mu * nu / (1.0 - 2.0 * nu);
+    m->kappa = m->lambda + 2.0 / 3.0 * m->mu;
+    m->density = density;
+}
+
+/* IsotropicT::ComputeModuli (IsotropicT.cpp:153-169): reduced-index C, row-major/symmetric here */
+static void hooke_moduli(const orc_material_t* m, double C[6][6])
+{
+    memset(C, 0, 36 * sizeof(double));
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) C[i][j] = m->lambda;
+        C[i][i] = m->lambda + 2.0 * m->mu;
+        C[i + 3][i + 3] = m->mu;
+    }
+}
+/* HookeanMatT::HookeanStress (Hookean/HookeanMatT.cpp:103-108) -> dSymMatrixT::A_ijkl_B_kl
+ * (dSymMatrixT.cpp:856-887): explicit factor 2 on the shear columns */
+static void hooke_stress(const orc_material_t* m, const double* e, double* s)
+{
+    double C[6][6];
+    hooke_moduli(m, C);
+    for (int I = 0; I < 6; I++)
+        s[I] = C[I][0] * e[0] + C[I][1] * e[1] + C[I][2] * e[2] + 2.0 * (C[I][3] * e[3] + C[I][4] * e[4] + C[I][5] * e[5]);
+}
+
+/* FDKStV / FDHookeanMatT::s_ij (Hookean/FDHookeanMatT.cpp:39-55):
+ * E = (F^T F - 1)/2 (FSSolidMatT::Compute_E, FSSolidMatT.cpp:472-505), S = C:E, sigma = F S F^T / J */
+static void fdkstv_stress(const orc_material_t* m, const double* F, double* sig)
+{
+    const double* f = F;
+    double e[6], S[6];
+    e[0] = (f[0] * f[0] + f[1] * f[1] + f[2] * f[2] - 1.0) * 0.5;
+    e[1] = (f[3] * f[3] + f[4] * f[4] + f[5] * f[5] - 1.0) * 0.5;
+    e[2] = (f[6] * f[6] + f[7] * f[7] + f[8] * f[8] - 1.0) * 0.5;
+    e[3] = (f[3] * f[6] + f[4] * f[7] + f[5] * f[8]) * 0.5;
+    e[4] = (f[0] * f[6] + f[1] * f[7] + f[2] * f[8]) * 0.5;
+    e[5] = (f[0] * f[3] + f[1] * f[4] + f[2] * f[5]) * 0.5;
+    hooke_stress(m, e, S);
+    sym_QAQT(F, S, sig);
+    double J = det3(F);
+    for (int I = 0; I < 6; I++) sig[I] /= J;
+}
+/* FDHookeanMatT::c_ijkl (FDHookeanMatT.cpp:30-37) + TensorTransformT::FFFFC_3D
+ * (primitives/TensorTransformT.cpp:102-153): c_ijkl = F_iI F_jJ F_kK F_lL C_IJKL / J */
+static void fdkstv_moduli(const orc_material_t* m, const double* F, double c[6][6])
+{
+    double C[6][6];
+    hooke_moduli(m, C);
+    /* full 4th-order tensor from the reduced form (minor symmetries) */
+    static const int V[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
+    double J = det3(F);
+    for (int A = 0; A < 6; A++)
+        for (int B = 0; B < 6; B++) {
+            int i = VI[A], j = VJ[A], k = VI[B], l = VJ[B];
+            double s = 0.0;
+            for (int I = 0; I < 3; I++)
+                for (int Jj = 0; Jj < 3; Jj++)
+                    for (int K = 0; K < 3; K++)
+                        for (int L = 0; L < 3; L++)
+                            s += F[i + 3 * I] * F[j + 3 * Jj] * F[k + 3 * K] * F[l + 3 * L] * C[V[I][Jj]][V[K][L]];
+            c[A][B] = s / J;
+        }
+}
+
+/* SimoIso3D::dU, ddU (materials/Simo/SimoIso3D.h:93-101) */
+static double simo_dU(const orc_material_t* m, double J) { return 0.5 * m->kappa * (J - 1.0 / J); }
+static double simo_ddU(const orc_material_t* m, double J) { return 0.5 * m->kappa * (1.0 + 1.0 / (J * J)); }
+
+/* SimoIso3D::ComputeCauchy (SimoIso3D.cpp:127-136) */
+static void simo_cauchy(const orc_material_t* m, double J, const double* b_bar, double* sig)
+{
+    for (int I = 0; I < 6; I++) sig[I] = m->mu / J * b_bar[I];
+    sym_dev(sig);
+    double p = simo_dU(m, J);
+    sig[0] += p; sig[1] += p; sig[2] += p;
+}
+/* SimoIso3D::ComputeModuli (SimoIso3D.cpp:102-125) with the fixed forms of
+ * TakeParameterList :74-97 (ReducedIndexI / ReducedIndexDeviatoric, dMatrixT.cpp:328-385) */
+static void simo_moduli(const orc_material_t* m, double J, const double* b_bar, double c[6][6])
+{
+    double du = simo_dU(m, J), ddu = simo_ddU(m, J);
+    double mu_bar = m->mu * sym_trace(b_bar) / (J * 3.0);
+    double s[6];
+    for (int I = 0; I < 6; I++) s[I] = m->mu * b_bar[I];
+    sym_dev(s);
+    static const double one[6] = {1, 1, 1, 0, 0, 0};
+    for (int A = 0; A < 6; A++)
+        for (int B = 0; B < 6; B++) {
+            double IxI = one[A] * one[B];
+            double I4 = (A == B) ? (A < 3 ? 1.0 : 0.5) : 0.0;
+            double Dev = I4 - IxI / 3.0;
+            double symo = 0.5 * (s[A] * one[B] + one[A] * s[B]); /* Outer + dMatrixT::Symmetrize */
+            c[A][B] = (du + J * ddu) * IxI - 2.0 * du * I4 + 2.0 * mu_bar * Dev - 4.0 / (J * 3.0) * symo;
+        }
+}
+/* SimoIso3D::s_ij (SimoIso3D.cpp:36-53) */
+static int simo_eval(const orc_material_t* m, const double* F, double* sig, double c[6][6])
+{
+    double b[6], b_bar[6];
+    compute_b(F, b);
+    double J = sym_det(b);
+    if (J <= 0.0) return ORC_BAD_JACOBIAN;
+    J = sqrt(J);
+    double sc = pow(J, -2.0 / 3.0);
+    for (int I = 0; I < 6; I++) b_bar[I] = sc * b[I];
+    if (sig) simo_cauchy(m, J, b_bar, sig);
+    if (c) simo_moduli(m, J, b_bar, c);
+    return ORC_OK;
+}
+
+/* J2 hardening K(alpha), K'(alpha) (J2_C0HardeningT.h:68-69; C1functions/LinearT.h:71,
+ * LinearExponentialT.cpp:48-57) */
+static double j2_K(const orc_material_t* m, double a)
+{
+    if (m->hard_kind == ORC_HARD_LINEAR) return m->hard[0] * a + m->hard[1];
+    return m->hard[0] + m->hard[1] * a + m->hard[2] * (1.0 - exp(-a / m->hard[3]));
+}
+static double j2_dK(const orc_material_t* m, double a)
+{
+    if (m->hard_kind == ORC_HARD_LINEAR) return m->hard[0];
+    return m->hard[1] + m->hard[2] * exp(-a / m->hard[3]) / m->hard[3];
+}
+enum { kalpha = 0, kstressnorm = 1, kdgamma = 2, kftrial = 3, kmu_bar = 4, kmu_bar_bar = 5, kDetF_tot = 6, kHeatIncr = 7 };
+
+/* J2Simo3D::s_ij / c_ijkl (plasticity_J2/J2Simo3D.cpp:41-105) with
+ * J2SimoC0HardeningT::{TrialElasticState :42-88, PlasticLoading :91-144, StressCorrection :148-253,
+ * ModuliCorrection :260-309, InitIntermediate :409-426}.  dH = 0 (J2_C0HardeningT.h:50-51). */
+static int j2_eval(const orc_material_t* m, const double* F, const double* Flast, orc_j2_ip_t* ips, int ip,
+                   int* alloc, int iteration, double* sig, double c[6][6])
+{
+    orc_j2_ip_t* st = &ips[ip];
+    double mu = m->mu;
+    double Flinv[9], frel[9];
+    inv3(Flast, det3(Flast), Flinv);
+    mul3(F, Flinv, frel); /* J2Simo3D::ComputeGradients :253-261 */
+    double J = det3(F);
+    double b_tr[6], beta_tr[6], trace_beta_tr = 0.0;
+
+    /* TrialElasticState */
+    for (int pass = 0; pass < 2; pass++) {
+        if (*alloc) {
+            if (st->flag == ORC_J2_NOTINIT) { /* InitIntermediate */
+                double frinv[9], Fn[9];
+                inv3(frel, det3(frel), frinv);
+                mul3(frinv, F, Fn);
+                compute_b(Fn, st->b_bar);
+                double sc = pow(sym_det(st->b_bar), -1.0 / 3.0);
+                for (int I = 0; I < 6; I++) { st->b_bar[I] *= sc; st->beta_bar[I] = 0.0; }
+                st->flag = ORC_J2_ELASTIC;
+            }
+            double fbar[9], sc = pow(det3(frel), -1.0 / 3.0);
+            for (int i = 0; i < 9; i++) fbar[i] = sc * frel[i];
+            sym_QAQT(fbar, st->b_bar, b_tr);
+            sym_QAQT(fbar, st->beta_bar, beta_tr);
+            trace_beta_tr = sym_trace(beta_tr);
+            beta_tr[0] -= trace_beta_tr / 3.0; beta_tr[1] -= trace_beta_tr / 3.0; beta_tr[2] -= trace_beta_tr / 3.0;
+            st->internal[kDetF_tot] = J;
+            memcpy(st->b_bar_trial, b_tr, sizeof b_tr);
+            memcpy(st->beta_bar_trial, beta_tr, sizeof beta_tr);
+        } else {
+            compute_b(F, b_tr);
+            double sc = pow(J, -2.0 / 3.0);
+            for (int I = 0; I < 6; I++) { b_tr[I] *= sc; beta_tr[I] = 0.0; }
+            trace_beta_tr = 0.0;
+        }
+        if (pass == 1 || !sig) break;
+
+        /* s_ij: elastic stress then return map */
+        simo_cauchy(m, J, b_tr, sig);
+        if (!(iteration > -1)) break; /* 1st iteration is elastic, J2Simo3D.cpp:83-84 */
+
+        /* PlasticLoading */
+        double rel[6];
+        memcpy(rel, b_tr, sizeof rel);
+        sym_dev(rel);
+        for (int I = 0; I < 6; I++) rel[I] = mu * rel[I] - beta_tr[I];
+        if (!*alloc) {
+            double f = sqrt(sym_scalar_product(rel)) - SQRT23 * j2_K(m, 0.0);
+            if (!(f > kYieldTol)) break;
+            /* AllocateElement :312-333: all 8 IPs, flags = kNotInit, data = 0 */
+            *alloc = 1;
+            for (int q = 0; q < 8; q++) { memset(&ips[q], 0, sizeof(orc_j2_ip_t)); ips[q].flag = ORC_J2_NOTINIT; }
+            continue; /* redo trial state on the allocated element, then PlasticLoading again */
+        }
+        break;
+    }
+    if (sig && iteration > -1 && *alloc) {
+        /* PlasticLoading on an allocated element :101-143 */
+        double rel[6];
+        memcpy(rel, b_tr, sizeof rel);
+        sym_dev(rel);
+        for (int I = 0; I < 6; I++) rel[I] = mu * rel[I] - beta_tr[I];
+        double* in = st->internal;
+        in[kstressnorm] = sqrt(sym_scalar_product(rel));
+        in[kftrial] = in[kstressnorm] - SQRT23 * j2_K(m, in[kalpha]);
+        in[kmu_bar] = mu * sym_trace(b_tr) / 3.0;
+        in[kmu_bar_bar] = in[kmu_bar] - trace_beta_tr / 3.0;
+        in[kHeatIncr] = 0.0;
+        for (int I = 0; I < 6; I++) st->unit_norm[I] = rel[I] / in[kstressnorm];
+        if (in[kftrial] > kYieldTol) {
+            st->flag = ORC_J2_PLASTIC;
+            /* StressCorrection :148-253 */
+            double alpha = in[kalpha], mbb = in[kmu_bar_bar], dgamma;
+            if (m->hard_kind == ORC_HARD_LINEAR)
+                dgamma = in[kftrial] / (2.0 * mbb) / (1.0 + (j2_dK(m, alpha) / 3.0 / mbb));
+            else {
+                double x_tr = in[kftrial] + SQRT23 * j2_K(m, alpha);
+                double f_hat = -in[kftrial];
+                double k = 2.0 * mbb;
+                dgamma = 0.0;
+                int count = 0, max_iteration = 15;
+                while (fabs(f_hat) > kYieldTol && ++count <= max_iteration) {
+                    double df_hat = 2.0 * j2_dK(m, alpha + SQRT23 * dgamma) / 3.0 + k;
+                    if (df_hat < 1.0e-12) return ORC_J2_LOCAL_FAIL;
+                    dgamma -= f_hat / df_hat;
+                    f_hat = SQRT23 * j2_K(m, alpha + SQRT23 * dgamma) - x_tr + k * dgamma;
+                }
+                if (count == max_iteration) return ORC_J2_LOCAL_FAIL;
+            }
+            in[kdgamma] = dgamma;
+            for (int I = 0; I < 6; I++) sig[I] += -2.0 * mbb * dgamma / in[kDetF_tot] * st->unit_norm[I];
+            in[kHeatIncr] = 0.9 * dgamma * j2_K(m, alpha + SQRT23 * dgamma) / in[kDetF_tot];
+        } else {
+            st->flag = ORC_J2_ELASTIC; /* StressCorrection is not reached: dgamma keeps its old value */
+        }
+    }
+    if (c) {
+        simo_moduli(m, J, b_tr, c);
+        if (*alloc && st->flag == ORC_J2_PLASTIC) { /* ModuliCorrection :260-309 */
+            const double* in = st->internal;
+            const double* n = st->unit_norm;
+            double stressnorm = in[kstressnorm], dgamma = in[kdgamma], alpha = in[kalpha];
+            double mb = in[kmu_bar], mbb = in[kmu_bar_bar];
+            double f0 = 2.0 * mb * dgamma / stressnorm;
+            double d0 = 1.0 + j2_dK(m, alpha) / 3.0 / mbb;
+            double f1 = 1.0 / d0 - f0;
+            double d1 = 2.0 * mbb * f1 - (4.0 / 3.0) * dgamma * (1.0 / d0 - 1.0);
+            double d2 = 2.0 * stressnorm * f1;
+            double N[9], NN[9], nn2[6];
+            sym_to_mat(n, N);
+            mul3(N, N, NN);
+            for (int I = 0; I < 6; I++) nn2[I] = NN[VI[I] + 3 * VJ[I]];
+            sym_dev(nn2);
+            static const double one[6] = {1, 1, 1, 0, 0, 0};
+            for (int A = 0; A < 6; A++)
+                for (int B = 0; B < 6; B++) {
+                    double I4 = (A == B) ? (A < 3 ? 1.0 : 0.5) : 0.0;
+                    double Dev = I4 - one[A] * one[B] / 3.0;
+                    double corr = -2.0 * mbb * f0 * Dev + f0 * (4.0 / 3.0) * stressnorm * 0.5 * (n[A] * one[B] + one[A] * n[B]) -
+                                  d1 * n[A] * n[B] - d2 * n[A] * nn2[B];
+                    c[A][B] += corr / in[kDetF_tot];
+                }
+        }
+    }
+    return ORC_OK;
+}
+/* J2SimoC0HardeningT::Update (J2SimoC0HardeningT.cpp:341-384), called from J2Simo3D::UpdateHistory
+ * for allocated elements only */
+void orc_j2_update(const orc_material_t* m, orc_j2_ip_t* j2)
+{
+    for (int ip = 0; ip < 8; ip++) {
+        orc_j2_ip_t* st = &j2[ip];
+        memcpy(st->b_bar, st->b_bar_trial, sizeof st->b_bar);
+        memcpy(st->beta_bar, st->beta_bar_trial, sizeof st->beta_bar);
+        if (st->flag == ORC_J2_PLASTIC) {
+            st->flag = ORC_J2_ELASTIC;
+            double dgamma = st->internal[kdgamma], mbb = st->internal[kmu_bar_bar];
+            double k = 2.0 * mbb * dgamma / m->mu;
+            st->internal[kalpha] += SQRT23 * dgamma;
+            for (int I = 0; I < 6; I++) st->b_bar[I] += -k * st->unit_norm[I];
+        }
+    }
+}
+/* J2SimoC0HardeningT::Reset (:387-407) */
+void orc_j2_reset(orc_j2_ip_t* j2)
+{
+    for (int ip = 0; ip < 8; ip++) { j2[ip].flag = ORC_J2_ELASTIC; j2[ip].internal[kdgamma] = 0.0; }
+}
+
+/* ------------------------------------------------------------------ */
+/* geometry                                                            */
+/* ------------------------------------------------------------------ */
+/* HexahedronT.cpp:23-25 vertex signs; :421-430 N and dN/dxi; SetLocalShape :1492-1669
+ * (8 points: g = 1/sqrt3, points in node order, weights 1) */
+static const double RA[8] = {-1, 1, 1, -1, -1, 1, 1, -1};
+static const double SA[8] = {-1, -1, 1, 1, -1, -1, 1, 1};
+static const double TA[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+void orc_hex8_parent(double Na[8][8], double DNa[8][3][8], double w[8])
+{
+    double g = 1.0 / sqrt(3.0);
+    for (int ip = 0; ip < 8; ip++) {
+        double r = g * RA[ip], s = g * SA[ip], t = g * TA[ip];
+        w[ip] = 1.0;
+        for (int a = 0; a < 8; a++) {
+            double tr = 1.0 + RA[a] * r, ts = 1.0 + SA[a] * s, tt = 1.0 + TA[a] * t;
+            Na[ip][a] = 0.125 * tr * ts * tt;
+            DNa[ip][0][a] = 0.125 * RA[a] * ts * tt;
+            DNa[ip][1][a] = 0.125 * tr * SA[a] * tt;
+            DNa[ip][2][a] = 0.125 * tr * ts * TA[a];
+        }
+    }
+}
+/* ParentDomainT::Jacobian (toolbox/src/geometry/ParentDomainT.cpp:99-189, node loop a=0..7) and
+ * ComputeDNa (:426-510): J_ij = sum_a X_a,i dN_a/dxi_j ; dN/dX = J^-T dN/dxi */
+int orc_hex8_shape(const double X[8][3], double dNdX[8][3][8], double det[8])
+{
+    double Na[8][8], DNa[8][3][8], w[8];
+    orc_hex8_parent(Na, DNa, w);
+    for (int ip = 0; ip < 8; ip++) {
+        double Jm[9] = {0}, Ji[9];
+        for (int a = 0; a < 8; a++)
+            for (int j = 0; j < 3; j++)
+                for (int i = 0; i < 3; i++) Jm[i + 3 * j] += X[a][i] * DNa[ip][j][a];
+        det[ip] = det3(Jm);
+        if (det[ip] <= 0.0) return ORC_BAD_JACOBIAN;
+        inv3(Jm, det[ip], Ji);
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++)
+                dNdX[ip][i][a] = Ji[0 + 3 * i] * DNa[ip][0][a] + Ji[1 + 3 * i] * DNa[ip][1][a] + Ji[2 + 3 * i] * DNa[ip][2][a];
+    }
+    return ORC_OK;
+}
+/* ShapeFunctionT::GradU (ShapeFunctionT.h:384-388): G_ij = sum_a u_a,i dN_a/dX_j (column-major) */
+static void grad_u(const double u[8][3], double dN[3][8], double* G)
+{
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) {
+            double s = 0.0;
+            for (int a = 0; a < 8; a++) s += u[a][i] * dN[j][a];
+            G[i + 3 * j] = s;
+        }
+}
+/* f += scale * B^T sigma with Set_B of SolidElementT.cpp:854-920 */
+static void add_BT_sigma(double scale, double dN[3][8], const double* s, double* fe)
+{
+    for (int a = 0; a < 8; a++) {
+        double nx = dN[0][a], ny = dN[1][a], nz = dN[2][a];
+        fe[3 * a + 0] += scale * (nx * s[0] + nz * s[4] + ny * s[5]);
+        fe[3 * a + 1] += scale * (ny * s[1] + nz * s[3] + nx * s[5]);
+        fe[3 * a + 2] += scale * (nz * s[2] + ny * s[3] + nx * s[4]);
+    }
+}
+/* 6x24 B from dN (Hughes 2.8.21, SolidElementT::Set_B) */
+static void set_B(double dN[3][8], double B[6][24])
+{
+    memset(B, 0, 6 * 24 * sizeof(double));
+    for (int a = 0; a < 8; a++) {
+        double nx = dN[0][a], ny = dN[1][a], nz = dN[2][a];
+        B[0][3 * a + 0] = nx; B[4][3 * a + 0] = nz; B[5][3 * a + 0] = ny;
+        B[1][3 * a + 1] = ny; B[3][3 * a + 1] = nz; B[5][3 * a + 1] = nx;
+        B[2][3 * a + 2] = nz; B[3][3 * a + 2] = ny; B[4][3 * a + 2] = nx;
+    }
+}
+
+/* finite-strain stress / modulus dispatch: FSSolidMatT s_ij, c_ijkl */
+static int fs_material(const orc_material_t* m, const double* F, const double* Fl, orc_j2_ip_t* j2, int ip, int* alloc,
+                       int iteration, double* sig, double c[6][6])
+{
+    switch (m->kind) {
+    case ORC_FDKSTV:
+        if (sig) fdkstv_stress(m, F, sig);
+        if (c) fdkstv_moduli(m, F, c);
+        return ORC_OK;
+    case ORC_SIMO_ISO: return simo_eval(m, F, sig, c);
+    case ORC_J2_SIMO: return j2_eval(m, F, Fl, j2, ip, alloc, iteration, sig, c);
+    }
+    return ORC_BAD_JACOBIAN;
+}
+
+/* K1. SmallStrainT::SetGlobalShape/FormKd (SmallStrainT.cpp:327-401,255-282);
+ * FiniteStrainT::SetGlobalShape (FiniteStrainT.cpp:267-304); TotalLagrangianT::FormKd
+ * (TotalLagrangianT.cpp:107-144); UpdatedLagrangianT::SetGlobalShape/FormKd (:83-91,145-171). */
+int orc_element_force(int form, const orc_material_t* m, const double X[8][3], const double u[8][3],
+                      const double u_last[8][3], orc_j2_ip_t* j2, int* alloc, int iteration, double fe[24])
+{
+    double dN[8][3][8], det[8], dNc[8][3][8], detc[8];
+    static const double zero[8][3] = {{0}};
+    int dummy_alloc = 0;
+    if (!alloc) alloc = &dummy_alloc;
+    if (!u_last) u_last = zero;
+    memset(fe, 0, 24 * sizeof(double));
+    int err = orc_hex8_shape(X, dN, det);
+    if (err) return err;
+    if (form == ORC_UPDATED_LAGRANGIAN) {
+        double x[8][3];
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) x[a][i] = X[a][i] + u[a][i];
+        err = orc_hex8_shape(x, dNc, detc);
+        if (err) return err;
+    }
+    for (int ip = 0; ip < 8; ip++) {
+        double G[9], sig[6];
+        grad_u(u, dN[ip], G);
+        if (form == ORC_SMALL_STRAIN) {
+            double e[6]; /* dSymMatrixT::Symmetrize */
+            e[0] = G[0]; e[1] = G[4]; e[2] = G[8];
+            e[3] = 0.5 * (G[5] + G[7]); e[4] = 0.5 * (G[2] + G[6]); e[5] = 0.5 * (G[1] + G[3]);
+            hooke_stress(m, e, sig);
+            add_BT_sigma(det[ip], dN[ip], sig, fe);
+            continue;
+        }
+        double F[9], Fl[9];
+        memcpy(F, G, sizeof F);
+        F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+        grad_u(u_last, dN[ip], Fl);
+        Fl[0] += 1.0; Fl[4] += 1.0; Fl[8] += 1.0;
+        err = fs_material(m, F, Fl, j2, ip, alloc, iteration, sig, NULL);
+        if (err) return err;
+        if (form == ORC_UPDATED_LAGRANGIAN) {
+            add_BT_sigma(detc[ip], dNc[ip], sig, fe);
+        } else { /* total Lagrangian: P/J = sigma F^-T ; f_a,i += J w det (P/J)_iJ dN_a/dX_J */
+            double J = det3(F);
+            if (J <= 0.0) return ORC_BAD_JACOBIAN;
+            double Fi[9], S[9], P[9];
+            inv3(F, J, Fi);
+            sym_to_mat(sig, S);
+            for (int jj = 0; jj < 3; jj++)
+                for (int i = 0; i < 3; i++) {
+                    double s = 0.0;
+                    for (int k = 0; k < 3; k++) s += S[i + 3 * k] * Fi[jj + 3 * k]; /* MultABT */
+                    P[i + 3 * jj] = s;
+                }
+            double sc = J * det[ip];
+            for (int a = 0; a < 8; a++)
+                for (int i = 0; i < 3; i++)
+                    fe[3 * a + i] += sc * (P[i] * dN[ip][0][a] + P[i + 3] * dN[ip][1][a] + P[i + 6] * dN[ip][2][a]);
+        }
+    }
+    return ORC_OK;
+}
+
+/* K3. SmallStrainT::FormStiffness (SmallStrainT.cpp:285-324); TotalLagrangianT::FormStiffness
+ * (TotalLagrangianT.cpp:40-104); UpdatedLagrangianT::FormStiffness (:94-142);
+ * nMatrixT::MultQTBQ (nMatrixT.h:1406-1500); dMatrixT::Expand (dMatrixT.cpp:690-727). */
+int orc_element_stiffness(int form, const orc_material_t* m, const double X[8][3], const double u[8][3],
+                          const double u_last[8][3], orc_j2_ip_t* j2, int* alloc, int iteration, double Ke[576])
+{
+    double dN[8][3][8], det[8], dNc[8][3][8], detc[8];
+    static const double zero[8][3] = {{0}};
+    int dummy_alloc = 0;
+    if (!alloc) alloc = &dummy_alloc;
+    if (!u_last) u_last = zero;
+    memset(Ke, 0, 576 * sizeof(double));
+    int err = orc_hex8_shape(X, dN, det);
+    if (err) return err;
+    if (form == ORC_UPDATED_LAGRANGIAN) {
+        double x[8][3];
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) x[a][i] = X[a][i] + u[a][i];
+        err = orc_hex8_shape(x, dNc, detc);
+        if (err) return err;
+    }
+    double kg[8][8]; /* stress stiffness */
+    memset(kg, 0, sizeof kg);
+    for (int ip = 0; ip < 8; ip++) {
+        double c[6][6], sig[6], B[6][24], scale;
+        double(*dNx)[8]; /* spatial gradients used for B */
+        double dNp[3][8];
+        if (form == ORC_SMALL_STRAIN) {
+            hooke_moduli(m, c);
+            dNx = dN[ip];
+            scale = det[ip];
+        } else {
+            double F[9], Fl[9];
+            grad_u(u, dN[ip], F);
+            F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+            grad_u(u_last, dN[ip], Fl);
+            Fl[0] += 1.0; Fl[4] += 1.0; Fl[8] += 1.0;
+            err = fs_material(m, F, Fl, j2, ip, alloc, iteration, sig, c);
+            if (err) return err;
+            if (form == ORC_UPDATED_LAGRANGIAN) {
+                dNx = dNc[ip];
+                scale = detc[ip];
+            } else { /* push dN/dX forward with F^-1: dN/dx_i = F^-1_Ji dN/dX_J */
+                double J = det3(F), Fi[9];
+                inv3(F, J, Fi);
+                for (int a = 0; a < 8; a++)
+                    for (int i = 0; i < 3; i++)
+                        dNp[i][a] = Fi[0 + 3 * i] * dN[ip][0][a] + Fi[1 + 3 * i] * dN[ip][1][a] + Fi[2 + 3 * i] * dN[ip][2][a];
+                dNx = dNp;
+                scale = det[ip] * J;
+            }
+            double S[9];
+            sym_to_mat(sig, S);
+            for (int a = 0; a < 8; a++)
+                for (int b = 0; b < 8; b++) {
+                    double s = 0.0;
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++) s += dNx[i][a] * S[i + 3 * j] * dNx[j][b];
+                    kg[a][b] += scale * s;
+                }
+        }
+        set_B(dNx, B);
+        for (int r = 0; r < 24; r++)
+            for (int cc = 0; cc < 24; cc++) {
+                double s = 0.0;
+                for (int I = 0; I < 6; I++) {
+                    double t = 0.0;
+                    for (int Jj = 0; Jj < 6; Jj++) t += c[I][Jj] * B[Jj][cc];
+                    s += B[I][r] * t;
+                }
+                Ke[r + 24 * cc] += scale * s;
+            }
+    }
+    if (form != ORC_SMALL_STRAIN)
+        for (int a = 0; a < 8; a++)
+            for (int b = 0; b < 8; b++)
+                for (int i = 0; i < 3; i++) Ke[(3 * a + i) + 24 * (3 * b + i)] += kg[a][b];
+    return ORC_OK;
+}
+
+/* K4. ContinuumElementT::FormMass kLumpedMass (continuum/common/ContinuumElementT.cpp:767-842) */
+int orc_element_lumped_mass(double density, const double X[8][3], double me[8])
+{
+    double Na[8][8], DNa[8][3][8], w[8], dN[8][3][8], det[8];
+    orc_hex8_parent(Na, DNa, w);
+    int err = orc_hex8_shape(X, dN, det);
+    if (err) return err;
+    double dsum = 0.0, totmas = 0.0, nee[8] = {0};
+    for (int ip = 0; ip < 8; ip++) {
+        double temp1 = density * w[ip] * det[ip];
+        totmas += temp1;
+        for (int a = 0; a < 8; a++) {
+            double temp2 = temp1 * Na[ip][a] * Na[ip][a];
+            dsum += temp2;
+            nee[a] += temp2;
+        }
+    }
+    double diagmass = totmas / dsum;
+    for (int a = 0; a < 8; a++) me[a] = diagmass * nee[a];
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* mesh sweeps: SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295), element order, then
+ * SolverT::AssembleRHS (solvers/SolverT.cpp:446-477) adds in that order                               */
+/* ------------------------------------------------------------------ */
+static void gather(const int32_t* c, const double* A, double out[8][3])
+{
+    for (int a = 0; a < 8; a++)
+        for (int i = 0; i < 3; i++) out[a][i] = A[3 * (int64_t)c[a] + i];
+}
+int orc_internal_force(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X,
+                       const double* u, const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration, double* f,
+                       int64_t* bad_elem)
+{
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], ue[8][3], ul[8][3], fe[24];
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        gather(c, u, ue);
+        if (u_last) gather(c, u_last, ul);
+        int err = orc_element_force(form, m, Xe, ue, u_last ? ul : NULL, j2 ? j2 + 8 * e : NULL, alloc ? alloc + e : NULL,
+                                    iteration, fe);
+        if (err) {
+            if (bad_elem) *bad_elem = e;
+            return err;
+        }
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) f[3 * (int64_t)c[a] + i] += fe[3 * a + i];
+    }
+    return ORC_OK;
+}
+int orc_lumped_mass(double density, int64_t ne, const int32_t* conn, const double* X, double* mass)
+{
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], me[8];
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        int err = orc_element_lumped_mass(density, Xe, me);
+        if (err) return err;
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) mass[3 * (int64_t)c[a] + i] += me[a];
+    }
+    return ORC_OK;
+}
+
+/* a24. FieldT::InitEquations (nodes/FieldT.cpp:635-659) + NodeManagerT::SetEquationNumbers
+ * (nodes/NodeManagerT.cpp:712-767): node-major, dof-minor, prescribed = kPrescribed (-1) */
+int64_t orc_set_equation_numbers(int64_t nn, const uint8_t* bc, int32_t* eqnos)
+{
+    int64_t num_eq = 0;
+    for (int64_t i = 0; i < nn * 3; i++) eqnos[i] = bc[i] ? -1 : (int32_t)(++num_eq);
+    return num_eq;
+}
+
+/* a22. GraphT::MakeGraph(active, add_self=true, upper_only) (toolbox/src/graph/GraphT.cpp:376-488):
+ * every pair of active equations of an element is an edge; MSRBuilderT::GenerateSuperLU
+ * (MSRBuilderT.cpp:216-244) / GenerateMSR (:134-181) sort each row ascending. */
+static int cmp_i32(const void* a, const void* b)
+{
+    int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
+    return (x > y) - (x < y);
+}
+typedef struct { int64_t* ptr; int32_t* col; } rows_t;
+static rows_t build_rows(int64_t ne, const int32_t* conn, int64_t nn, const int32_t* eqnos, int64_t neq, int upper_only)
+{
+    /* node -> elements */
+    int64_t* nptr = calloc(nn + 1, sizeof(int64_t));
+    for (int64_t i = 0; i < ne * 8; i++) nptr[conn[i] + 1]++;
+    for (int64_t n = 0; n < nn; n++) nptr[n + 1] += nptr[n];
+    int64_t* fill = malloc(nn * sizeof(int64_t));
+    memcpy(fill, nptr, nn * sizeof(int64_t));
+    int64_t* nel = malloc(ne * 8 * sizeof(int64_t));
+    for (int64_t e = 0; e < ne; e++)
+        for (int a = 0; a < 8; a++) nel[fill[conn[8 * e + a]]++] = e;
+    rows_t R;
+    R.ptr = calloc(neq + 1, sizeof(int64_t));
+    int64_t cap = 1024, len = 0;
+    R.col = malloc(cap * sizeof(int32_t));
+    int32_t* tmp = malloc(27 * 3 * 8 * sizeof(int32_t));
+    for (int64_t n = 0; n < nn; n++) {
+        /* candidate columns: all active eqs of all nodes of all elements at node n */
+        int nt = 0;
+        for (int64_t k = nptr[n]; k < nptr[n + 1]; k++)
+            for (int a = 0; a < 8; a++)
+                for (int i = 0; i < 3; i++) {
+                    int32_t q = eqnos[3 * (int64_t)conn[8 * nel[k] + a] + i];
+                    if (q > 0) tmp[nt++] = q - 1;
+                }
+        qsort(tmp, nt, sizeof(int32_t), cmp_i32);
+        int nu = 0;
+        for (int k = 0; k < nt; k++)
+            if (nu == 0 || tmp[k] != tmp[nu - 1]) tmp[nu++] = tmp[k];
+        for (int i = 0; i < 3; i++) {
+            int32_t r = eqnos[3 * n + i];
+            if (r <= 0) continue;
+            r -= 1;
+            if (len + nu > cap) { while (len + nu > cap) cap *= 2; R.col = realloc(R.col, cap * sizeof(int32_t)); }
+            int64_t start = len;
+            for (int k = 0; k < nu; k++)
+                if (!upper_only || tmp[k] >= r) R.col[len++] = tmp[k];
+            R.ptr[r + 1] = len - start;
+        }
+    }
+    /* rows were emitted in equation order because numbering is node-major */
+    for (int64_t r = 0; r < neq; r++) R.ptr[r + 1] += R.ptr[r];
+    free(nptr); free(fill); free(nel); free(tmp);
+    return R;
+}
+int64_t orc_csr_structure(int64_t ne, const int32_t* conn, int64_t nn, const int32_t* eqnos, int64_t neq, int upper_only,
+                          int64_t* rowptr, int32_t* colind)
+{
+    rows_t R = build_rows(ne, conn, nn, eqnos, neq, upper_only);
+    int64_t nnz = R.ptr[neq];
+    if (rowptr) memcpy(rowptr, R.ptr, (neq + 1) * sizeof(int64_t));
+    if (colind) memcpy(colind, R.col, nnz * sizeof(int32_t));
+    free(R.ptr); free(R.col);
+    return nnz;
+}
+int64_t orc_msr_structure(int64_t ne, const int32_t* conn, int64_t nn, const int32_t* eqnos, int64_t neq, int upper_only,
+                          int32_t* bindx)
+{
+    rows_t R = build_rows(ne, conn, nn, eqnos, neq, upper_only);
+    int64_t nnz = R.ptr[neq];
+    int64_t total = nnz - neq + neq + 1;
+    if (bindx) {
+        int64_t pos = neq + 1;
+        bindx[0] = (int32_t)pos;
+        for (int64_t r = 0; r < neq; r++) {
+            for (int64_t k = R.ptr[r]; k < R.ptr[r + 1]; k++)
+                if (R.col[k] != r) bindx[pos++] = R.col[k];
+            bindx[r + 1] = (int32_t)pos;
+        }
+    }
+    free(R.ptr); free(R.col);
+    return total;
+}
+
+/* greedy colouring, elements visited in order, smallest colour not used by any
+ * element sharing a node.  No reference counterpart. */
+int orc_greedy_colouring(int64_t ne, const int32_t* conn, int64_t nn, int32_t* colour)
+{
+    uint64_t* used = calloc(nn, sizeof(uint64_t)); /* bitmask of colours present at each node (<= 64 colours) */
+    int ncol = 0;
+    for (int64_t e = 0; e < ne; e++) {
+        uint64_t mask = 0;
+        for (int a = 0; a < 8; a++) mask |= used[conn[8 * e + a]];
+        int c = 0;
+        while (c < 64 && (mask >> c) & 1) c++;
+        if (c >= 64) { free(used); return -1; }
+        colour[e] = c;
+        if (c + 1 > ncol) ncol = c + 1;
+        for (int a = 0; a < 8; a++) used[conn[8 * e + a]] |= (uint64_t)1 << c;
+    }
+    free(used);
+    return ncol;
+}
+
+/* SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154) + MSRMatrixT::Assemble
+ * (MSRMatrixT.cpp:66-216) restated on the full CSR: val[pos(eq_r, eq_c)] += Ke[r][c] in element order */
+int orc_assemble_stiffness(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X,
+                           const double* u, const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration,
+                           const int32_t* eqnos, int64_t neq, const int64_t* rowptr, const int32_t* colind, double* val)
+{
+    (void)neq;
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], ue[8][3], ul[8][3], Ke[576];
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        gather(c, u, ue);
+        if (u_last) gather(c, u_last, ul);
+        int err = orc_element_stiffness(form, m, Xe, ue, u_last ? ul : NULL, j2 ? j2 + 8 * e : NULL,
+                                        alloc ? alloc + e : NULL, iteration, Ke);
+        if (err) return err;
+        int32_t eq[24];
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) eq[3 * a + i] = eqnos[3 * (int64_t)c[a] + i];
+        for (int r = 0; r < 24; r++) {
+            if (eq[r] <= 0) continue;
+            int64_t row = eq[r] - 1;
+            for (int cc = 0; cc < 24; cc++) {
+                if (eq[cc] <= 0) continue;
+                int32_t col = eq[cc] - 1;
+                int64_t lo = rowptr[row], hi = rowptr[row + 1] - 1;
+                while (lo < hi) { int64_t mid = (lo + hi) / 2; if (colind[mid] < col) lo = mid + 1; else hi = mid; }
+                if (colind[lo] != col) return -1;
+                val[lo] += Ke[r + 24 * cc];
+            }
+        }
+    }
+    return ORC_OK;
+}
+
+/* K6. MSRMatrixT::Multx (primitives/globalmatrix/MSRMatrixT.cpp:385-420) on the CSR form */
+void orc_csr_spmv(int64_t n, const int64_t* rowptr, const int32_t* colind, const double* val, const double* x, double* y)
+{
+    for (int64_t r = 0; r < n; r++) {
+        double s = 0.0;
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) s += val[k] * x[colind[k]];
+        y[r] = s;
+    }
+}
+static double dot(int64_t n, const double* a, const double* b) /* nArrayT::Dot (nArrayT.h:988-998) */
+{
+    double s = 0.0;
+    for (int64_t i = 0; i < n; i++) s += a[i] * b[i];
+    return s;
+}
+/* K6-K8: linear CG with Jacobi preconditioner = DiagonalMatrixT::Factorize/BackSubstitute
+ * (DiagonalMatrixT.cpp:267-323: reciprocal, |m| < 1e-12 skipped) applied to r.
+ * Textbook PCG (Aztec-style AZ_cg + AZ_Jacobi, the precedent AztecMatrixT.h:18-75 names). */
+int orc_pcg_jacobi(int64_t n, const int64_t* rowptr, const int32_t* colind, const double* val, const double* b, double* x,
+                   double rtol, double atol, int max_iter, double* final_rnorm)
+{
+    double *r = malloc(n * 8), *z = malloc(n * 8), *p = malloc(n * 8), *q = malloc(n * 8), *dinv = malloc(n * 8);
+    for (int64_t i = 0; i < n; i++) {
+        double d = 0.0;
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++)
+            if (colind[k] == i) d = val[k];
+        dinv[i] = fabs(d) > 1.0e-12 ? 1.0 / d : d;
+    }
+    orc_csr_spmv(n, rowptr, colind, val, x, q);
+    for (int64_t i = 0; i < n; i++) { r[i] = b[i] - q[i]; z[i] = dinv[i] * r[i]; p[i] = z[i]; }
+    double rz = dot(n, r, z), rnorm = sqrt(dot(n, r, r)), r0 = rnorm;
+    int it = 0;
+    while (it < max_iter && rnorm > atol && rnorm > rtol * r0) {
+        orc_csr_spmv(n, rowptr, colind, val, p, q);
+        double alpha = rz / dot(n, p, q);
+        for (int64_t i = 0; i < n; i++) { x[i] += alpha * p[i]; r[i] -= alpha * q[i]; z[i] = dinv[i] * r[i]; }
+        double rz_new = dot(n, r, z);
+        rnorm = sqrt(dot(n, r, r));
+        double beta = rz_new / rz;
+        rz = rz_new;
+        for (int64_t i = 0; i < n; i++) p[i] = z[i] + beta * p[i];
+        it++;
+    }
+    if (final_rnorm) *final_rnorm = rnorm;
+    free(r); free(z); free(p); free(q); free(dinv);
+    return it;
+}
+
+/* a19. nExplicitCD::Predictor (integrators/explicitCD/nExplicitCD.cpp:72-96, constants :214-223)
+ * then ConsistentKBC (:20-69) for kFix / kDsp cards, as FieldT::InitStep orders them (FieldT.cpp:326-387) */
+void orc_cd_predictor(int64_t ndof, double dt, double* d, double* v, double* a, const uint8_t* bc, const double* bcval)
+{
+    double dpred_v = dt, dpred_a = 0.5 * dt * dt, vpred_a = 0.5 * dt;
+    for (int64_t i = 0; i < ndof; i++) {
+        d[i] += dpred_v * v[i] + dpred_a * a[i];
+        v[i] += vpred_a * a[i];
+        a[i] = 0.0;
+        if (bc && bc[i] == 1) { d[i] = 0.0; v[i] = 0.0; a[i] = 0.0; }
+        else if (bc && bc[i] == 2) { d[i] = bcval[i]; a[i] = 0.0; }
+    }
+}
+/* LinearSolver::Solve (solvers/LinearSolver.cpp:37-101): update = M^-1 R (DiagonalMatrixT.cpp:267-323),
+ * FieldT::AssembleUpdate (FieldT.cpp:531-556: prescribed dofs get 0), nExplicitCD::Corrector (:98-139) */
+void orc_cd_corrector(int64_t ndof, double dt, double* v, double* a, const double* R, const double* mass, const uint8_t* bc)
+{
+    double vcorr_a = 0.5 * dt;
+    for (int64_t i = 0; i < ndof; i++) {
+        double upd = 0.0;
+        if (!(bc && bc[i])) {
+            double minv = fabs(mass[i]) > 1.0e-12 ? 1.0 / mass[i] : mass[i];
+            upd = R[i] * minv;
+        }
+        v[i] += vcorr_a * upd;
+        a[i] += upd;
+    }
+}

@@ -1,0 +1,114 @@
+/* oracle/tahoe_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C CPU restatement of Tahoe's Hex8 continuum-solid hot path
+ * (SURVEY.md section 8a).  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may link or call this.
+ * The product (tahoe_b200/) never does.
+ *
+ * Parity status: PINNED against the reference itself -- oracle/_ref/tahoe_dump
+ * (the unmodified reference compiled by oracle/build_ref.mk) writes
+ * full-precision fixtures into tests/golden/ (tests/golden/make_golden.py);
+ * tests/test_oracle_golden.py checks every function below against them.
+ *
+ * Conventions: node order of HexahedronT.cpp:23-25,
+ * 8 integration points at +-1/sqrt(3) in node order with unit weights,
+ * symmetric-tensor order 11,22,33,23,13,12 with tensor shear components,
+ * F stored column-major F[i + 3*j], nodal arrays [node][dof], element
+ * vectors [node a][dof i] -> 3*a+i, element matrices column-major 24x24.
+ */
+#ifndef TAHOE_ORACLE_H
+#define TAHOE_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_SMALL_STRAIN = 0, ORC_TOTAL_LAGRANGIAN = 1, ORC_UPDATED_LAGRANGIAN = 2 };
+enum { ORC_SSKSTV = 0, ORC_FDKSTV = 1, ORC_SIMO_ISO = 2, ORC_J2_SIMO = 3 };
+enum { ORC_OK = 0, ORC_BAD_JACOBIAN = 1, ORC_J2_LOCAL_FAIL = 2 };
+enum { ORC_J2_ELASTIC = 0, ORC_J2_PLASTIC = 1, ORC_J2_NOTINIT = 2 };
+enum { ORC_HARD_LINEAR = 0, ORC_HARD_LINEAR_EXP = 1 };
+
+typedef struct {
+    int    kind;       /* ORC_SSKSTV ... */
+    double mu, lambda, kappa, density;
+    int    hard_kind;  /* J2: hardening function K(alpha) */
+    double hard[4];    /* linear: K = hard[0]*alpha + hard[1];
+                          linear_exponential: K = hard[0] + hard[1]*alpha + hard[2]*(1-exp(-alpha/hard[3])) */
+} orc_material_t;
+
+/* J2 history of one integration point, field order of
+ * J2SimoC0HardeningT::LoadData (J2SimoC0HardeningT.cpp:429-452) */
+typedef struct {
+    double b_bar[6], unit_norm[6], beta_bar[6], b_bar_trial[6], beta_bar_trial[6];
+    double internal[8]; /* alpha, stressnorm, dgamma, ftrial, mu_bar, mu_bar_bar, detF_tot, heat */
+    int    flag;        /* ORC_J2_* */
+} orc_j2_ip_t;
+
+void orc_material_from_E_nu(orc_material_t* m, int kind, double E, double nu, double density);
+
+/* a3: parent-domain tables. Na[ip][a], DNa[ip][d][a], w[ip] */
+void orc_hex8_parent(double Na[8][8], double DNa[8][3][8], double w[8]);
+
+/* a3: dN/dX at the 8 IPs of one element. X[a][d]. returns ORC_BAD_JACOBIAN if any det <= 0 */
+int orc_hex8_shape(const double X[8][3], double dNdX[8][3][8], double det[8]);
+
+/* K1: one element's internal force fe[3*a+i] (the +B^T sigma integral; Tahoe's RHS gets -fe).
+ * u_last and j2 (8 IPs, may be NULL for non-J2), alloc = pointer to the element's
+ * "IsAllocated" flag, iteration = GroupIterationNumber() */
+int orc_element_force(int form, const orc_material_t* m, const double X[8][3], const double u[8][3],
+                      const double u_last[8][3], orc_j2_ip_t* j2, int* alloc, int iteration, double fe[24]);
+
+/* K3: one element's tangent Ke[r + 24*c] (whole matrix) */
+int orc_element_stiffness(int form, const orc_material_t* m, const double X[8][3], const double u[8][3],
+                          const double u_last[8][3], orc_j2_ip_t* j2, int* alloc, int iteration, double Ke[576]);
+
+/* K4: one element's lumped mass me[a] (same on the 3 dofs of node a) */
+int orc_element_lumped_mass(double density, const double X[8][3], double me[8]);
+
+/* J2 history commit / reset over one element (J2SimoC0HardeningT::Update/Reset) */
+void orc_j2_update(const orc_material_t* m, orc_j2_ip_t* j2);
+void orc_j2_reset(orc_j2_ip_t* j2);
+
+/* mesh-level sweeps, element order = serial reference order */
+int orc_internal_force(int form, const orc_material_t* m, int64_t ne, const int32_t* conn /*[ne][8]*/,
+                       const double* X /*[nn][3]*/, const double* u, const double* u_last,
+                       orc_j2_ip_t* j2 /*[ne][8] or NULL*/, int* alloc /*[ne] or NULL*/, int iteration,
+                       double* f /*[nn][3], accumulated into*/, int64_t* bad_elem);
+int orc_lumped_mass(double density, int64_t ne, const int32_t* conn, const double* X, double* mass /*[nn][3] accumulated*/);
+
+/* a24: equation numbers.  bc[nn*3] != 0 marks prescribed dofs.  eqnos 1-based, -1 prescribed. returns n_eq */
+int64_t orc_set_equation_numbers(int64_t nn, const uint8_t* bc, int32_t* eqnos);
+
+/* a22: sparsity of the active equations.  CSR in the form of MSRBuilderT::SetSuperLUData
+ * (rowptr 0-based, colind 0-based sorted, diagonal in place).  Call with colind==NULL to size. */
+int64_t orc_csr_structure(int64_t ne, const int32_t* conn, int64_t nn, const int32_t* eqnos, int64_t neq,
+                          int upper_only, int64_t* rowptr /*[neq+1]*/, int32_t* colind);
+/* MSR structure data of MSRBuilderT::SetMSRData: bindx[0..neq] row starts, then sorted off-diagonal cols */
+int64_t orc_msr_structure(int64_t ne, const int32_t* conn, int64_t nn, const int32_t* eqnos, int64_t neq,
+                          int upper_only, int32_t* bindx);
+
+/* greedy element colouring in element order (no reference counterpart: SURVEY section 0.4) */
+int orc_greedy_colouring(int64_t ne, const int32_t* conn, int64_t nn, int32_t* colour);
+
+/* assemble K (full CSR) and the residual R = fext - fint on the active equations */
+int orc_assemble_stiffness(int form, const orc_material_t* m, int64_t ne, const int32_t* conn,
+                           const double* X, const double* u, const double* u_last, orc_j2_ip_t* j2, int* alloc,
+                           int iteration, const int32_t* eqnos, int64_t neq, const int64_t* rowptr,
+                           const int32_t* colind, double* val);
+
+/* K6: y = A x on CSR (MSRMatrixT::Multx restated on the CSR form) */
+void orc_csr_spmv(int64_t n, const int64_t* rowptr, const int32_t* colind, const double* val, const double* x, double* y);
+
+/* K6-K8: linear Jacobi-PCG.  returns iterations; x is start guess and result */
+int orc_pcg_jacobi(int64_t n, const int64_t* rowptr, const int32_t* colind, const double* val,
+                   const double* b, double* x, double rtol, double atol, int max_iter, double* final_rnorm);
+
+/* a19: central difference.  bc code per dof: 0 free, 1 fixed (kFix), 2 prescribed displacement (kDsp, value in bcval) */
+void orc_cd_predictor(int64_t ndof, double dt, double* d, double* v, double* a, const uint8_t* bc, const double* bcval);
+void orc_cd_corrector(int64_t ndof, double dt, double* v, double* a, const double* R, const double* mass, const uint8_t* bc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
