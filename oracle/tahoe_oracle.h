@@ -26,7 +26,7 @@ extern "C" {
 enum { ORC_SMALL_STRAIN = 0, ORC_TOTAL_LAGRANGIAN = 1, ORC_UPDATED_LAGRANGIAN = 2 };
 enum { ORC_SSKSTV = 0, ORC_FDKSTV = 1, ORC_SIMO_ISO = 2, ORC_J2_SIMO = 3 };
 enum { ORC_OK = 0, ORC_BAD_JACOBIAN = 1, ORC_J2_LOCAL_FAIL = 2 };
-enum { ORC_J2_ELASTIC = 0, ORC_J2_PLASTIC = 1, ORC_J2_NOTINIT = 2 };
+enum { ORC_J2_NOTINIT = -1, ORC_J2_PLASTIC = 0, ORC_J2_ELASTIC = 1 }; /* J2SimoC0HardeningT.h:33-36 */
 enum { ORC_HARD_LINEAR = 0, ORC_HARD_LINEAR_EXP = 1 };
 
 typedef struct {

@@ -1,0 +1,42 @@
+"""Shared helpers for the parity tests: load a golden fixture, derive BC arrays and the equation system."""
+import glob
+import json
+import os
+
+import numpy as np
+
+import tahoe_input as ti
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+STATIC = [n for n in ALL if "static" in n or n.startswith("ref_mat") or n.startswith("ref_beam") or n == "ref_traction_a"]
+EXPLICIT = [n for n in ALL if "explicit" in n]
+WITH_LHS = [n for n in ALL if n.startswith("syn_") and "static" in n]
+
+
+class Case:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.z = z
+        self.desc = json.loads(str(z["desc"]))
+        self.nodesets = {int(k[3:]): z[k] for k in z.files if k.startswith("ns_")}
+        self.X = np.ascontiguousarray(z["ref_coords"])
+        self.conn = np.ascontiguousarray(z["ref_conn"])
+        self.nn, self.ne = self.X.shape[0], self.conn.shape[0]
+        t = self.desc["time"]
+        self.nsteps, self.dt = t["num_steps"], t["time_step"]
+        self.dump_steps = sorted(int(k[6:]) for k in z.files if k.startswith("ref_d_"))
+        # profile_matrix (CCSMatrixT) renumbers equations for bandwidth; others keep node-major numbering
+        self.renumbered = self.desc["solver"].get("matrix") == "profile_matrix"
+
+    def ref(self, key):
+        return self.z["ref_" + key]
+
+    def bc(self, t):
+        return ti.bc_arrays(self.desc, self.nodesets, self.nn, t)
+
+
+def relerr(a, b):
+    s = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / s

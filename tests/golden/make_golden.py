@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the authoring container only (needs /root/reference and oracle/_ref/tahoe_dump, built by
+`make -f oracle/build_ref.mk`).  Two kinds of cases:
+
+* the reference's own regression inputs for the hot path (benchmark_XML level.0 / level.1,
+  SURVEY.md section 8c), run as shipped;
+* synthetic jittered cubes written as TahoeII .geom + XML, so that Jacobians
+  are non-trivial and every formulation x material pair of the hot path is pinned, including the
+  assembled tangent and MSR structure (`SPOOLES_matrix` is MSRMatrixT-derived and does not renumber).
+
+Each fixture holds the case description (JSON), the mesh, node sets, and the reference's in-memory
+arrays at full precision (oracle/ref_dump.cpp).  The fixtures travel; the reference does not.
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(REPO, "tests"))
+import tahoe_input as ti  # noqa: E402
+
+DUMP = os.path.join(REPO, "oracle", "_ref", "tahoe_dump")
+REF = "/root/reference/benchmark_XML"
+
+
+def load_dump(d):
+    out = {}
+    for line in open(os.path.join(d, "manifest.txt")):
+        name, typ, d0, d1 = line.split()
+        a = np.fromfile(os.path.join(d, name + ".bin"), dtype=np.float64 if typ == "f8" else np.int32)
+        out[name] = a.reshape(int(d0), int(d1)) if int(d1) else a
+    return out
+
+
+def run_case(name, xml_path, flags, desc, coords, conn, nodesets):
+    out = tempfile.mkdtemp(prefix="dump_")
+    r = subprocess.run([DUMP, os.path.basename(xml_path), out] + flags, cwd=os.path.dirname(xml_path),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-3000:])
+        raise RuntimeError("tahoe_dump failed for " + name)
+    dump = load_dump(out)
+    shutil.rmtree(out)
+    assert np.array_equal(dump["conn"], conn), "connectivity mismatch vs geom reader"
+    assert np.allclose(dump["coords"], coords, rtol=0, atol=0), "coords mismatch vs geom reader"
+    payload = {"desc": np.array(json.dumps(desc))}
+    for sid, ids in nodesets.items():
+        payload["ns_%d" % sid] = np.asarray(ids, np.int32)
+    for k, v in dump.items():
+        payload["ref_" + k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **payload)
+    print("%-28s %7.1f kB  %s" % (name, os.path.getsize(path) / 1024, " ".join(sorted(dump))))
+
+
+def reference_case(name, rel_xml, flags):
+    """one of the reference's own inputs, run as shipped from a scratch copy of its directory tree"""
+    src_dir = os.path.dirname(os.path.join(REF, rel_xml))
+    work = tempfile.mkdtemp(prefix="ref_")
+    level_dir = os.path.dirname(src_dir)
+    shutil.copytree(level_dir, os.path.join(work, "lvl"), ignore=shutil.ignore_patterns("benchmark", "*.run", "*.out"))
+    xml = os.path.join(work, "lvl", os.path.basename(src_dir), os.path.basename(rel_xml))
+    desc = ti.parse_xml(xml)
+    desc["source"] = "benchmark_XML/" + rel_xml
+    coords, conn, nodesets = ti.read_geom(os.path.normpath(os.path.join(os.path.dirname(xml), desc["geometry_file"])))
+    run_case(name, xml, flags, desc, coords, conn, nodesets)
+    shutil.rmtree(work)
+
+
+def synthetic_case(name, n, desc, flags, jitter=0.1):
+    work = tempfile.mkdtemp(prefix="syn_")
+    dims = n if isinstance(n, tuple) else (n, n, n)
+    coords, conn, nodesets = ti.structured_cube(*dims, jitter=jitter, seed=12345)
+    ti.write_geom(os.path.join(work, "mesh.geom"), coords, conn, nodesets)
+    coords, conn2, nodesets2 = ti.read_geom(os.path.join(work, "mesh.geom"))  # what the reference will read
+    assert np.array_equal(conn, conn2)
+    desc = dict(desc, geometry_file="mesh.geom", source="synthetic %dx%dx%d jitter %g seed 12345" % (*dims, jitter))
+    xml = os.path.join(work, name + ".xml")
+    ti.write_xml(xml, desc)
+    run_case(name, xml, flags, desc, coords, conn, nodesets2)
+    shutil.rmtree(work)
+
+
+RAMP = [(0.0, 0.0), (1.0, 1.0)]
+CLAMP_X0 = [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)]
+NEWTON = {"type": "nonlinear_solver", "abs_tolerance": "1.0e-12", "rel_tolerance": "1.0e-12",
+          "divergence_tolerance": "1.0e+03", "max_iterations": "25", "matrix": "SPOOLES_matrix"}
+EXPLICIT = {"type": "linear_solver", "matrix": "diagonal_matrix"}
+
+
+def main():
+    only = set(sys.argv[1:])
+
+    def want(n):
+        return not only or n in only
+
+    # ---- the reference's own regression inputs ----
+    ref_cases = [
+        ("ref_traction_a", "level.0/3D.elastostatic/traction.a.xml", ["--fint"]),
+        ("ref_beam_newton_totlag", "level.0/3D.elastostatic/beam.Newton.TotLag.xml", ["--fint"]),
+        ("ref_beam_newton", "level.0/3D.elastostatic/beam.Newton.xml", ["--fint"]),
+        ("ref_explicit_1", "level.0/3D.elastodynamic/explicit.1.xml", ["--every", "25", "--fint"]),
+        ("ref_explicit_2", "level.0/3D.elastodynamic/explicit.2.xml", ["--every", "25", "--fint"]),
+        ("ref_mat_1_a", "level.1/material.solid/3D/material.01/mat.1.a.xml", ["--fint"]),
+        ("ref_mat_2_a", "level.1/material.solid/3D/material.02/mat.2.a.xml", ["--fint"]),
+        ("ref_mat_5_a", "level.1/material.solid/3D/material.05/mat.5.a.xml", ["--fint"]),
+        ("ref_mat_09_a", "level.1/material.solid/3D/material.09/mat.09.a.xml", ["--every", "1", "--fint"]),
+    ]
+    for name, rel, flags in ref_cases:
+        if want(name):
+            reference_case(name, rel, flags)
+
+    # ---- synthetic jittered cubes ----
+    kstv = {"type": "small_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25}
+    fdkstv = {"type": "large_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25}
+    simo = {"type": "Simo_isotropic", "density": 1.0, "kappa": 1000.0, "mu": 5.0}
+    simo_soft = {"type": "Simo_isotropic", "density": 1.0, "E": 100.0, "nu": 0.25}
+    j2 = {"type": "Simo_J2", "density": 1.0, "E": 100.0, "nu": 0.25,
+          "hardening": {"type": "linear_function", "a": 0.05, "b": 0.25}}
+    pull_f = [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005}]
+
+    def pull_u(v):
+        return CLAMP_X0 + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": v},
+                           {"nodeset": 2, "dof": 3, "type": "u", "schedule": 1, "value": 0.3 * v}]
+
+    def static(nsteps):
+        return {"num_steps": nsteps, "time_step": 1.0 / nsteps, "schedules": [RAMP]}
+
+    syn = [
+        ("syn_ss_kstv_static", 4, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
+                                   "element": {"type": "small_strain"}, "material": kstv, "solver": NEWTON},
+         ["--fint", "--lhs"]),
+        ("syn_tl_simo_static", 3, {"time": static(2), "integrator": "static", "kbc": pull_u(0.15), "fbc": [],
+                                   "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": NEWTON},
+         ["--every", "1", "--fint", "--lhs"]),
+        ("syn_ul_simo_static", 3, {"time": static(2), "integrator": "static", "kbc": pull_u(0.15), "fbc": [],
+                                   "element": {"type": "updated_lagrangian"}, "material": simo_soft, "solver": NEWTON},
+         ["--every", "1", "--fint", "--lhs"]),
+        ("syn_tl_fdkstv_static", 3, {"time": static(2), "integrator": "static", "kbc": pull_u(0.15), "fbc": [],
+                                     "element": {"type": "total_lagrangian"}, "material": fdkstv, "solver": NEWTON},
+         ["--every", "1", "--fint", "--lhs"]),
+        ("syn_ul_fdkstv_static", 3, {"time": static(2), "integrator": "static", "kbc": pull_u(0.15), "fbc": [],
+                                     "element": {"type": "updated_lagrangian"}, "material": fdkstv, "solver": NEWTON},
+         ["--every", "1", "--fint", "--lhs"]),
+        ("syn_ul_j2_static", 3, {"time": static(4), "integrator": "static", "kbc": pull_u(0.06), "fbc": [],
+                                 "element": {"type": "updated_lagrangian"}, "material": j2, "solver": NEWTON},
+         ["--every", "1", "--fint", "--lhs"]),
+        ("syn_tl_simo_explicit", 4, {"time": {"num_steps": 40, "time_step": 0.5 * 0.25 / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0),
+                                              "schedules": [[(0.0, 1.0)]]},
+                                     "integrator": "central_difference", "kbc": CLAMP_X0,
+                                     "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02},
+                                             {"nodeset": 2, "dof": 3, "schedule": 1, "value": -0.01}],
+                                     "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"},
+                                     "material": simo, "solver": EXPLICIT},
+         ["--every", "10", "--fint"]),
+        ("syn_ul_fdkstv_explicit", 4, {"time": {"num_steps": 40, "time_step": 0.01, "schedules": [[(0.0, 1.0)]]},
+                                       "integrator": "central_difference",
+                                       "kbc": CLAMP_X0 + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.0}],
+                                       "fbc": [{"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.05}],
+                                       "element": {"type": "updated_lagrangian", "mass_type": "lumped_mass"},
+                                       "material": fdkstv, "solver": EXPLICIT},
+         ["--every", "10", "--fint"]),
+    ]
+    for name, n, desc, flags in syn:
+        if want(name):
+            synthetic_case(name, n, desc, flags)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+"""ctypes binding of oracle/tahoe_oracle.c (test infrastructure -- the checker, never the product)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(REPO, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+
+SMALL_STRAIN, TOTAL_LAGRANGIAN, UPDATED_LAGRANGIAN = 0, 1, 2
+SSKSTV, FDKSTV, SIMO_ISO, J2_SIMO = 0, 1, 2, 3
+FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2}
+KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3}
+
+
+class Material(C.Structure):
+    _fields_ = [("kind", C.c_int), ("mu", C.c_double), ("lam", C.c_double), ("kappa", C.c_double),
+                ("density", C.c_double), ("hard_kind", C.c_int), ("hard", C.c_double * 4)]
+
+
+J2_DTYPE = np.dtype([("b_bar", "f8", 6), ("unit_norm", "f8", 6), ("beta_bar", "f8", 6), ("b_bar_trial", "f8", 6),
+                     ("beta_bar_trial", "f8", 6), ("internal", "f8", 8), ("flag", "i4"), ("_pad", "i4")])
+
+
+def build(force=False):
+    src = os.path.join(ORACLE_DIR, "tahoe_oracle.c")
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(ORACLE_DIR, "tahoe_oracle.h")))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-o", LIB_PATH, src, "-lm"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_csr_structure.restype = C.c_int64
+        _lib.orc_msr_structure.restype = C.c_int64
+        _lib.orc_set_equation_numbers.restype = C.c_int64
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def material(desc_mat):
+    """orc_material_t from the XML material description (IsotropicT::TakeParameterList)"""
+    m = Material()
+    kind = KIND_OF[desc_mat["type"]]
+    if "E" in desc_mat:
+        lib().orc_material_from_E_nu(C.byref(m), kind, C.c_double(desc_mat["E"]), C.c_double(desc_mat["nu"]),
+                                     C.c_double(desc_mat["density"]))
+    else:  # IsotropicT::Set_mu_kappa
+        m.kind, m.mu, m.kappa, m.density = kind, desc_mat["mu"], desc_mat["kappa"], desc_mat["density"]
+        m.lam = m.kappa - 2.0 * m.mu / 3.0
+    h = desc_mat.get("hardening")
+    if h:
+        if h["type"] == "linear_function":
+            m.hard_kind = 0
+            m.hard[0], m.hard[1] = h["a"], h["b"]
+        else:
+            m.hard_kind = 1
+            for i, k in enumerate("abcd"):
+                m.hard[i] = h[k]
+    return m
+
+
+def internal_force(form, mat, conn, X, u, u_last=None, j2=None, alloc=None, iteration=0):
+    conn = np.ascontiguousarray(conn, np.int32)
+    f = np.zeros_like(X)
+    bad = C.c_int64(-1)
+    err = lib().orc_internal_force(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(u), _p(u_last),
+                                   _p(j2), _p(alloc), iteration, _p(f), C.byref(bad))
+    return err, f
+
+
+def lumped_mass(density, conn, X):
+    conn = np.ascontiguousarray(conn, np.int32)
+    m = np.zeros_like(X)
+    err = lib().orc_lumped_mass(C.c_double(density), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(m))
+    assert err == 0
+    return m
+
+
+def equation_numbers(bc_code):
+    bc = np.ascontiguousarray(bc_code != 0, np.uint8)
+    eq = np.zeros(bc.shape, np.int32)
+    neq = lib().orc_set_equation_numbers(C.c_int64(bc.shape[0]), _p(bc), _p(eq))
+    return eq, int(neq)
+
+
+def csr_structure(conn, eqnos, neq, upper_only=False):
+    conn = np.ascontiguousarray(conn, np.int32)
+    rowptr = np.zeros(neq + 1, np.int64)
+    args = (C.c_int64(conn.shape[0]), _p(conn), C.c_int64(eqnos.shape[0]), _p(eqnos), C.c_int64(neq), int(upper_only))
+    nnz = lib().orc_csr_structure(*args, _p(rowptr), None)
+    colind = np.zeros(nnz, np.int32)
+    lib().orc_csr_structure(*args, _p(rowptr), _p(colind))
+    return rowptr, colind
+
+
+def msr_structure(conn, eqnos, neq, upper_only):
+    conn = np.ascontiguousarray(conn, np.int32)
+    args = (C.c_int64(conn.shape[0]), _p(conn), C.c_int64(eqnos.shape[0]), _p(eqnos), C.c_int64(neq), int(upper_only))
+    n = lib().orc_msr_structure(*args, None)
+    bindx = np.zeros(n, np.int32)
+    lib().orc_msr_structure(*args, _p(bindx))
+    return bindx
+
+
+def colouring(conn, nn):
+    conn = np.ascontiguousarray(conn, np.int32)
+    col = np.zeros(conn.shape[0], np.int32)
+    ncol = lib().orc_greedy_colouring(C.c_int64(conn.shape[0]), _p(conn), C.c_int64(nn), _p(col))
+    return ncol, col
+
+
+def assemble_stiffness(form, mat, conn, X, u, eqnos, neq, rowptr, colind, u_last=None, j2=None, alloc=None, iteration=0):
+    conn = np.ascontiguousarray(conn, np.int32)
+    val = np.zeros(colind.shape[0])
+    err = lib().orc_assemble_stiffness(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(u), _p(u_last),
+                                       _p(j2), _p(alloc), iteration, _p(eqnos), C.c_int64(neq), _p(rowptr), _p(colind),
+                                       _p(val))
+    return err, val
+
+
+def element_stiffness(form, mat, Xe, ue, ul=None, j2=None, alloc=None, iteration=0):
+    Ke = np.zeros(576)
+    err = lib().orc_element_stiffness(form, C.byref(mat), _p(np.ascontiguousarray(Xe)), _p(np.ascontiguousarray(ue)),
+                                      _p(ul), _p(j2), _p(alloc), iteration, _p(Ke))
+    return err, Ke.reshape(24, 24).T  # column-major -> [r, c]
+
+
+def element_force(form, mat, Xe, ue, ul=None, j2=None, alloc=None, iteration=0):
+    fe = np.zeros(24)
+    err = lib().orc_element_force(form, C.byref(mat), _p(np.ascontiguousarray(Xe)), _p(np.ascontiguousarray(ue)),
+                                  _p(ul), _p(j2), _p(alloc), iteration, _p(fe))
+    return err, fe
+
+
+def spmv(rowptr, colind, val, x):
+    y = np.zeros_like(x)
+    lib().orc_csr_spmv(C.c_int64(x.shape[0]), _p(rowptr), _p(colind), _p(val), _p(x), _p(y))
+    return y
+
+
+def pcg_jacobi(rowptr, colind, val, b, x0=None, rtol=1e-12, atol=0.0, max_iter=10000):
+    x = np.zeros_like(b) if x0 is None else x0.copy()
+    rn = C.c_double(0.0)
+    it = lib().orc_pcg_jacobi(C.c_int64(b.shape[0]), _p(rowptr), _p(colind), _p(val), _p(b), _p(x), C.c_double(rtol),
+                              C.c_double(atol), int(max_iter), C.byref(rn))
+    return x, it, rn.value
+
+
+def cd_predictor(dt, d, v, a, bc, bcval):
+    lib().orc_cd_predictor(C.c_int64(d.size), C.c_double(dt), _p(d), _p(v), _p(a), _p(bc), _p(bcval))
+
+
+def cd_corrector(dt, v, a, R, mass, bc):
+    lib().orc_cd_corrector(C.c_int64(v.size), C.c_double(dt), _p(v), _p(a), _p(R), _p(mass), _p(bc))
+
+
+def j2_update(mat, j2, alloc):
+    for e in np.nonzero(alloc)[0]:
+        lib().orc_j2_update(C.byref(mat), C.c_void_p(j2.ctypes.data + int(e) * 8 * J2_DTYPE.itemsize))
+
+
+def j2_reset(j2, alloc):
+    for e in np.nonzero(alloc)[0]:
+        lib().orc_j2_reset(C.c_void_p(j2.ctypes.data + int(e) * 8 * J2_DTYPE.itemsize))

@@ -1,0 +1,219 @@
+"""Pins oracle/tahoe_oracle.c against the reference itself (fixtures written by tests/golden/make_golden.py
+from oracle/_ref/tahoe_dump, i.e. the unmodified reference run in-process at full precision)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from cases import ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+
+TOL = 1e-10  # north_star: forces / displacements agree to 1e-10 relative
+
+
+def _setup(oracle, name):
+    c = Case(name)
+    form = oracle.FORM_OF[c.desc["element"]["type"]]
+    mat = oracle.material(c.desc["material"])
+    return c, form, mat
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_equation_numbers_bit_exact(oracle, name):
+    """NodeManagerT::SetEquationNumbers: bit-exact unless the matrix type asked for renumbering"""
+    c = Case(name)
+    code, _, _ = c.bc(0.0)
+    eq, neq = oracle.equation_numbers(code)
+    ref = c.ref("eqnos")
+    assert np.array_equal(eq > 0, ref > 0)
+    assert neq == ref.max()
+    if not c.renumbered:
+        assert np.array_equal(eq, ref)
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if "j2" not in n and "09" not in n])
+def test_internal_force_matches_reference(oracle, name):
+    c, form, mat = _setup(oracle, name)
+    d = c.ref("d_%d" % c.dump_steps[-1])
+    err, f = oracle.internal_force(form, mat, c.conn, c.X, d)
+    assert err == 0
+    assert relerr(f, c.ref("fint")) < TOL
+    if not c.renumbered and not c.desc["element"].get("natural_bc") and c.desc["integrator"] == "static":
+        code, _, fext = c.bc(c.nsteps * c.dt)
+        eq, _ = oracle.equation_numbers(code)
+        assert np.abs((fext - f)[eq > 0] - c.ref("rhs")).max() < TOL * max(np.abs(f).max(), 1.0)
+
+
+@pytest.mark.parametrize("name", WITH_LHS)
+def test_msr_structure_bit_exact(oracle, name):
+    """MSRBuilderT::SetMSRData: identical integer array"""
+    c = Case(name)
+    code, _, _ = c.bc(0.0)
+    eq, neq = oracle.equation_numbers(code)
+    sym = "j2" not in name  # J2Simo3D::TangentType is kNonSymmetric -> full rows
+    bindx = oracle.msr_structure(c.conn, eq, neq, upper_only=sym)
+    assert np.array_equal(bindx, c.ref("msr_bindx"))
+    rowptr, colind = oracle.csr_structure(c.conn, eq, neq)
+    # CSR (SuperLU form) holds the same pattern with the diagonal in place
+    assert rowptr[-1] == (2 * (len(bindx) - neq - 1) + neq if sym else len(bindx) - 1)
+    for r in (0, neq // 2, neq - 1):
+        cols = colind[rowptr[r]:rowptr[r + 1]]
+        assert np.all(np.diff(cols) > 0) and r in cols
+
+
+@pytest.mark.parametrize("name", [n for n in WITH_LHS if "j2" not in n])
+def test_tangent_matches_reference(oracle, name):
+    c, form, mat = _setup(oracle, name)
+    code, _, _ = c.bc(0.0)
+    eq, neq = oracle.equation_numbers(code)
+    rowptr, colind = oracle.csr_structure(c.conn, eq, neq)
+    d = c.ref("d_%d" % c.dump_steps[-1])
+    err, val = oracle.assemble_stiffness(form, mat, c.conn, c.X, d, eq, neq, rowptr, colind)
+    assert err == 0
+    A = sp.csr_matrix((val, colind, rowptr), shape=(neq, neq))
+    r, cc, v = c.ref("lhs_r"), c.ref("lhs_c"), c.ref("lhs_v")
+    mine = np.asarray(A[r, cc]).ravel()
+    assert relerr(mine, v) < TOL
+    assert abs(A - A.T).max() < 1e-12 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("name", EXPLICIT)
+def test_explicit_central_difference_matches_reference(oracle, name):
+    """lumped mass + nExplicitCD predictor/corrector + K1 over the whole run"""
+    c, form, mat = _setup(oracle, name)
+    mass = oracle.lumped_mass(mat.density, c.conn, c.X)
+    d, v, a = c.ref("d_0").copy(), c.ref("v_0").copy(), np.zeros_like(c.X)
+    code, val, fext = c.bc(0.0)
+    err, f = oracle.internal_force(form, mat, c.conn, c.X, d)
+    a = np.where(code == 0, (fext - f) / mass, 0.0)  # FEManagerT::InitialCondition
+    assert np.abs(a - c.ref("a_0")).max() < 1e-12 * max(np.abs(a).max(), 1.0)
+    for k in range(1, c.nsteps + 1):
+        code, val, fext = c.bc(k * c.dt)
+        oracle.cd_predictor(c.dt, d, v, a, code, val)
+        err, f = oracle.internal_force(form, mat, c.conn, c.X, d)
+        assert err == 0
+        oracle.cd_corrector(c.dt, v, a, fext - f, mass, code)
+        if k in c.dump_steps:
+            assert relerr(d, c.ref("d_%d" % k)) < TOL
+            assert relerr(v, c.ref("v_%d" % k)) < TOL
+            assert relerr(a, c.ref("a_%d" % k)) < TOL
+
+
+def newton(oracle, c, form, mat, solve):
+    """NLSolver::Solve restated (solvers/NLSolver.cpp:57-263): yields (step, d, iteration_number)"""
+    code, _, _ = c.bc(0.0)
+    eq, neq = oracle.equation_numbers(code)
+    rowptr, colind = oracle.csr_structure(c.conn, eq, neq)
+    act = eq > 0
+    isj2 = mat.kind == oracle.J2_SIMO
+    j2 = np.zeros((c.ne, 8), oracle.J2_DTYPE) if isj2 else None
+    alloc = np.zeros(c.ne, np.int32) if isj2 else None
+    s = c.desc["solver"]
+    atol, rtol = float(s["abs_tolerance"]), float(s["rel_tolerance"])
+    d = c.ref("d_0").copy()  # FEManagerT::InitialCondition state (non-zero only if the load is on at t=0)
+    d_last = d.copy()
+    for k in range(1, c.nsteps + 1):
+        code, val, fext = c.bc(k * c.dt)
+        d[code == 1] = 0.0
+        d[code == 2] = val[code == 2]
+        it = -1
+        err, f = oracle.internal_force(form, mat, c.conn, c.X, d, d_last, j2, alloc, it)
+        assert err == 0
+        R = (fext - f)[act]
+        e0 = e = np.linalg.norm(R)
+        while e0 >= atol and not (it >= 0 and (e / e0 < rtol or e < atol)):
+            assert it < 25
+            err, kv = oracle.assemble_stiffness(form, mat, c.conn, c.X, d, eq, neq, rowptr, colind, d_last, j2, alloc, it)
+            assert err == 0
+            d[act] += solve(rowptr, colind, kv, R)
+            it += 1
+            err, f = oracle.internal_force(form, mat, c.conn, c.X, d, d_last, j2, alloc, it)
+            assert err == 0
+            R = (fext - f)[act]
+            e = np.linalg.norm(R)
+        if isj2:
+            oracle.j2_update(mat, j2, alloc)
+        d_last = d.copy()
+        yield k, d, it, j2, alloc
+
+
+def _direct(rowptr, colind, kv, R):
+    n = len(R)
+    return spla.spsolve(sp.csr_matrix((kv, colind, rowptr), shape=(n, n)).tocsc(), R)
+
+
+@pytest.mark.parametrize("name", [n for n in STATIC if n != "ref_traction_a"])
+def test_static_newton_matches_reference(oracle, name):
+    """displacements, Newton iteration counts and (J2) committed history vs the reference's Newton + direct solve"""
+    c, form, mat = _setup(oracle, name)
+    iters = c.ref("iters")
+    for k, d, it, j2, alloc in newton(oracle, c, form, mat, _direct):
+        if k in c.dump_steps:
+            assert relerr(d, c.ref("d_%d" % k)) < TOL
+        assert it == iters[k - 1]
+    if mat.kind == oracle.J2_SIMO:
+        assert np.array_equal(alloc, c.ref("j2_alloc"))
+        data = c.ref("j2_data").reshape(c.ne, 5 * 48 + 64)
+        flags = c.ref("j2_flags")
+        assert alloc.sum() > 0 and j2["internal"][:, :, 0].max() > 1e-3  # really yielded
+        for e in np.nonzero(alloc)[0]:
+            for i, nm in enumerate(["b_bar", "unit_norm", "beta_bar", "b_bar_trial", "beta_bar_trial"]):
+                assert np.abs(j2[e][nm] - data[e, 48 * i:48 * (i + 1)].reshape(8, 6)).max() < 1e-10
+            assert np.abs(j2[e]["internal"] - data[e, 240:].reshape(8, 8)).max() < 1e-10
+            assert np.array_equal(j2[e]["flag"], flags[e])
+
+
+def test_j2_tangent_is_consistent(oracle):
+    """J2 plastic tangent vs finite differences of the oracle's own stress (the reference's check_LHS idea,
+    SolverT.cpp:863-951); the Newton iteration counts above pin it against the reference as well"""
+    c, form, mat = _setup(oracle, "syn_ul_j2_static")
+    Xe = c.X[c.conn[0]]
+    ul = c.ref("d_2")[c.conn[0]].copy()
+    ue = c.ref("d_3")[c.conn[0]].copy()
+    j2 = np.zeros(8, oracle.J2_DTYPE)
+    alloc = np.zeros(1, np.int32)
+    # build history up to step 2 for this element alone, then linearise about step 3
+    for k in (1, 2):
+        u0 = c.ref("d_%d" % (k - 1))[c.conn[0]].copy()
+        u1 = c.ref("d_%d" % k)[c.conn[0]].copy()
+        err, _ = oracle.element_force(form, mat, Xe, u1, u0, j2, alloc, 1)
+        assert err == 0
+        if alloc[0]:
+            oracle.j2_update(mat, j2.reshape(1, 8), alloc)
+    err, f0 = oracle.element_force(form, mat, Xe, ue, ul, j2.copy(), alloc.copy(), 1)
+    st, al = j2.copy(), alloc.copy()
+    oracle.element_force(form, mat, Xe, ue, ul, st, al, 1)
+    err, K = oracle.element_stiffness(form, mat, Xe, ue, ul, st, al, 1)
+    assert err == 0 and (st["flag"] == 0).any()  # kIsPlastic
+    Kfd = np.zeros((24, 24))
+    h = 1e-7
+    for j in range(24):
+        up, um = ue.copy().ravel(), ue.copy().ravel()
+        up[j] += h
+        um[j] -= h
+        _, fp = oracle.element_force(form, mat, Xe, up.reshape(8, 3), ul, j2.copy(), alloc.copy(), 1)
+        _, fm = oracle.element_force(form, mat, Xe, um.reshape(8, 3), ul, j2.copy(), alloc.copy(), 1)
+        Kfd[:, j] = (fp - fm) / (2 * h)
+    assert np.abs(K - Kfd).max() < 2e-5 * np.abs(K).max()
+
+
+def test_pcg_jacobi_solves_reference_system(oracle):
+    c, form, mat = _setup(oracle, "syn_ss_kstv_static")
+    code, _, fext = c.bc(1.0)
+    eq, neq = oracle.equation_numbers(code)
+    rowptr, colind = oracle.csr_structure(c.conn, eq, neq)
+    err, kv = oracle.assemble_stiffness(form, mat, c.conn, c.X, np.zeros_like(c.X), eq, neq, rowptr, colind)
+    x, it, rn = oracle.pcg_jacobi(rowptr, colind, kv, fext[eq > 0], rtol=1e-14, max_iter=5000)
+    d = np.zeros_like(c.X)
+    d[eq > 0] = x
+    assert 0 < it < 5000
+    assert relerr(d, c.ref("d_1")) < TOL
+
+
+def test_colouring_is_valid_and_8_on_structured(oracle):
+    import tahoe_input as ti
+    X, conn, _ = ti.structured_cube(5, 4, 3)
+    ncol, col = oracle.colouring(conn, X.shape[0])
+    assert ncol == 8
+    for cc in range(ncol):
+        nodes = conn[col == cc].ravel()
+        assert len(np.unique(nodes)) == len(nodes)
