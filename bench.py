@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- explicit central-difference element-updates/s on a structured Hex8 cube (BASELINE.json configs[1] per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n EDGE] [--workload explicit|pcg] [--impl reference]
+
+One "step" = one explicit central-difference step over the whole mesh: total-Lagrangian Neo-Hookean (SimoIso3D) internal
+force over every element (K1), deterministic node gather, M^-1 R, corrector and the next predictor (K5).
+  value   element-updates/s, device-resident (d, v, a stay in HBM), CUDA events on the library's stream, max over ranks
+  e2e     the same step through the host-buffer entry point tb2_explicit_step_host: d, v, a come from pinned host memory
+          and go back every step (what a drop-in does when Tahoe's FieldT stays authoritative)
+  roofline / roofline_fp64   the dominant kernel (K1) against the measured HBM and FP64 peaks, from per-launch CUDA events
+          recorded inside the timed region
+  cpu_baseline   the unmodified reference binary (oracle/_ref/tahoe, built from /root/reference by oracle/build_ref.mk)
+          on a bounded sample of the same workload, one core; falls back to the C oracle port if the binary is absent.
+`--impl reference` times that reference binary alone on all host cores (one serial Tahoe process per core; Tahoe's
+classic element path is single-threaded and no MPI exists on this box).
+N > 1 (torchrun): weak scaling, one EDGE^3 brick per rank, interface-node force sums over NCCL.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "element-updates/s"
+MATERIAL = {"type": "Simo_isotropic", "density": 1.0, "kappa": 1000.0, "mu": 5.0}  # legacy_hex_*.xml
+REF_BIN = os.path.join(REPO, "oracle", "_ref", "tahoe")
+
+
+def stable_dt(n):
+    return 0.5 * (1.0 / n) / np.sqrt((MATERIAL["kappa"] + 4.0 * MATERIAL["mu"] / 3.0) / MATERIAL["density"])
+
+
+def initial_displacement(X):
+    """smooth trilinear field + seeded noise (u = 1e-2 smooth + 1e-4 noise)"""
+    rng = np.random.default_rng(12345)
+    A = rng.standard_normal((3, 3))
+    return 1e-2 * X @ A.T * 0.3 + 1e-4 * (1.0 / 64) * rng.standard_normal(X.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the unmodified reference binary on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------------
+def _write_reference_case(work, n, nsteps):
+    import tahoe_input as ti
+    X, conn, ns = ti.structured_cube(n, jitter=0.1)
+    if not os.path.exists(os.path.join(work, "mesh.geom")):
+        ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
+    desc = {"geometry_file": "mesh.geom",
+            "time": {"num_steps": nsteps, "time_step": float(stable_dt(n)), "schedules": [[(0.0, 1.0)]]},
+            "integrator": "central_difference",
+            "kbc": [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)],
+            "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 1e-3}],
+            "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": MATERIAL,
+            "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}
+    ti.write_xml(os.path.join(work, "run_%d.xml" % nsteps), desc)
+    return conn.shape[0]
+
+
+def _run_reference_batch(work, nsteps, procs):
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([REF_BIN, "-f", "run_%d.xml" % nsteps], cwd=work, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                           env=dict(os.environ, OMP_NUM_THREADS="1")) for _ in range(procs)]
+    rc = [p.wait() for p in ps]
+    if any(rc):
+        raise RuntimeError("reference binary failed: %s" % rc)
+    return time.perf_counter() - t0
+
+
+def reference_rate(n, s_lo, s_hi, procs):
+    """element-updates/s of `procs` concurrent serial reference processes on an n^3 cube, from the wall-clock difference
+    between an s_hi-step and an s_lo-step run (cancels input parsing, set-up and FEManagerT::InitialCondition)"""
+    work = tempfile.mkdtemp(prefix="tb2_ref_")
+    try:
+        ne = _write_reference_case(work, n, s_lo)
+        _write_reference_case(work, n, s_hi)
+        t_lo = _run_reference_batch(work, s_lo, procs)
+        t_hi = _run_reference_batch(work, s_hi, procs)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    dt = max(t_hi - t_lo, 1e-9)
+    return procs * ne * (s_hi - s_lo) / dt, dt, ne
+
+
+def oracle_port_rate(n, steps):
+    """fallback CPU baseline: the plain-C oracle port (kind = "port"), one core"""
+    import oracle_lib as orc
+    import tahoe_input as ti
+    X, conn, ns = ti.structured_cube(n, jitter=0.1)
+    mat = orc.material(MATERIAL)
+    u = initial_displacement(X)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.internal_force(orc.TOTAL_LAGRANGIAN, mat, conn, X, u)
+    return conn.shape[0] * steps / (time.perf_counter() - t0), conn.shape[0]
+
+
+def cpu_baseline(sample_n=40, s_lo=2, s_hi=42):
+    if os.path.exists(REF_BIN):
+        rate, dt, ne = reference_rate(sample_n, s_lo, s_hi, 1)
+        return {"value": rate, "unit": METRIC, "cores": 1, "kind": "reference",
+                "sample": "%d^3=%d-element jittered cube, %d explicit steps of oracle/_ref/tahoe (classic total_lagrangian + Simo_isotropic, "
+                          "lumped mass, central_difference), wall(%d steps) - wall(%d steps) = %.2f s" % (sample_n, ne, s_hi - s_lo, s_hi, s_lo, dt)}
+    rate, ne = oracle_port_rate(24, 4)
+    return {"value": rate, "unit": METRIC, "cores": 1, "kind": "port",
+            "sample": "24^3=%d elements x 4 internal-force sweeps of oracle/tahoe_oracle.c (reference binary absent)" % ne}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 32
+    w, k = max(args.warmup, 1), max(args.steps, 1)
+    k = min(k, 60)
+    if os.path.exists(REF_BIN):
+        rate, dt, ne = reference_rate(n, w, w + k, cores)
+        kind, sample = "reference", ("%d concurrent serial oracle/_ref/tahoe processes (one per host core; no MPI/METIS on this box), each a %d^3=%d-element "
+                                     "jittered cube, %d timed explicit steps (wall(%d) - wall(%d) steps)" % (cores, n, ne, k, w + k, w))
+    else:
+        rate, ne = oracle_port_rate(24, k)
+        dt, cores, kind, sample = ne * k / rate, 1, "port", "oracle/tahoe_oracle.c internal-force sweeps on 24^3 (reference binary absent)"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": METRIC, "n_gpus": args.gpus, "steps": k, "warmup": w,
+            "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.n, args.gpus),
+            "cpu_baseline": {"value": rate, "unit": METRIC, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": rate, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n, gpus):
+    return {"workload": "BASELINE.json configs[1]: %d^3=%d-element structured Hex8 cube per GPU (jitter 0.1 h, seed 12345), total_lagrangian + "
+                        "Simo_isotropic Neo-Hookean (kappa=1000, mu=5, rho=1), 8 integration points, lumped mass, explicit central difference"
+                        % (n, n ** 3),
+            "elements_per_gpu": n ** 3, "partition": "1 brick" if gpus == 1 else "%d bricks, NCCL interface-node force sum" % gpus,
+            "l2": "inputs larger than L2 (per-step working set ~%d MB vs 126 MB L2)" % (n ** 3 * (192 + 32 + 9 * 24) // 10 ** 6)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from tahoe_b200 import capi, mesh as tmesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.lib()
+    n = args.n
+    # ---- mesh: one n^3 brick per rank (weak scaling)
+    if world == 1:
+        X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+        part = None
+    else:
+        gx, gy, gz = tmesh.brick_grid(world)
+        part = tmesh.partition_cube(n * gx, n * gy, n * gz, world, rank, jitter=0.1)
+        X, conn, ns = part["coords"], part["conn"], part["nodesets"]
+    ne_local, nn_local = conn.shape[0], X.shape[0]
+    m = capi.Mesh(X, conn, device=local)
+    if world > 1:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        m.comm_init(rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
+    g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MATERIAL))
+    ex = capi.Explicit(g)
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1  # x = 0 face clamped
+    fext = np.zeros_like(X)
+    if world == 1:
+        fext[ns[2], 0] = 1e-3
+    u0 = initial_displacement(X)
+    ex.set_bc(code, np.zeros_like(X), fext)
+    ex.set_state(u0, np.zeros_like(X), np.zeros_like(X))
+    dt = float(stable_dt(n * (1 if world == 1 else max(tmesh.brick_grid(world)))))
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        m.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident timed region
+    ex.run(dt, args.warmup)
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.profile_begin()
+    ev0.record(stream)
+    ex.run(dt, args.steps)
+    ev1.record(stream)
+    ms_cat, cnt_cat, launches = m.profile_end()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    d, v, a = ex.get_state()
+    if not (np.isfinite(d).all() and np.isfinite(v).all()):
+        raise SystemExit("bench.py: non-finite state after the timed region")
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(ne_local)], device="cuda", dtype=torch.float64)
+    kt = torch.tensor([ms_cat[0] / max(cnt_cat[0], 1), ms_cat[1] / max(cnt_cat[1], 1), ms_cat[6] / max(cnt_cat[6], 1)], device="cuda",
+                      dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ne_total = float(tot.item())
+    value = ne_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers in pinned memory, H2D + D2H of d, v, a inside every step
+    e2e_steps = max(3, min(args.steps, 30))
+    hd, hv, ha = (torch.zeros(X.shape, dtype=torch.float64).pin_memory() for _ in range(3))
+    hd.copy_(torch.from_numpy(d))
+    hv.copy_(torch.from_numpy(v))
+    ha.copy_(torch.from_numpy(a))
+    for _ in range(3):
+        ex.step_host_ptr(dt, hd.data_ptr(), hv.data_ptr(), ha.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        ex.step_host_ptr(dt, hd.data_ptr(), hv.data_ptr(), ha.data_ptr())
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) if world == 1 else 0.0)
+    te = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = ne_total * e2e_steps / (float(te.item()) * 1e-3)
+    if not np.isfinite(hd.numpy()).all():
+        raise SystemExit("bench.py: non-finite state after the e2e region")
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        fp64_peak = capi.measure_fp64_peak(local)
+        k1_ms, k5_ms, comm_ms = (float(x) for x in kt.tolist())
+        # algorithmic bytes (SURVEY.md 8d / DESIGN.md): K1 = 104 B/element (conn 32 + X 24 + u 24 + f 24), K5 = 192 B/node
+        k1_bytes = 104.0 * ne_local
+        k1_flops = args.k1_flop_per_element * ne_local
+        roof = {"bound": "hbm", "kernel": "k_internal_force<TL,SimoIso> (K1)", "achieved": k1_bytes / (k1_ms * 1e-3) * 1e-9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": args.k1_traffic_bytes, "peak_source": hbm_src,
+                "avg_launch_ms": k1_ms, "share_of_step": k1_ms * args.steps / ms,
+                "note": "K1 is FP64-pipe bound (arithmetic intensity ~%.0f flop/B >> machine balance): see roofline_fp64" % (args.k1_flop_per_element / 104.0)}
+        roof64 = {"bound": "fp64", "kernel": roof["kernel"], "achieved": k1_flops / (k1_ms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
+                  "frac": k1_flops / (k1_ms * 1e-3) * 1e-12 / fp64_peak, "flop_per_element": args.k1_flop_per_element,
+                  "peak_source": "measured in this run (tb2_measure_fp64_peak: dependent DFMA chains)"}
+        k5_bytes = (192.0 + 24.0) * nn_local  # d,v,a R+W, fext, minv + fint write
+        roof_k5 = {"bound": "hbm", "kernel": "k_cd_node_update (gather + K5)", "achieved": k5_bytes / (k5_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": k5_bytes / (k5_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": k5_ms, "share_of_step": k5_ms * args.steps / ms,
+                   "note": "algorithmic 216 B/node; the kernel also re-reads the 192 B/element force scratch"}
+        step_bytes = 104.0 * ne_local + 192.0 * nn_local
+        line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(n, world), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(72 * nn_local * world),
+                        "d2h_bytes_per_step": int(72 * nn_local * world), "steps": e2e_steps, "ms_per_step": float(te.item()) / e2e_steps,
+                        "api": "tb2_explicit_step_host (pinned host d,v,a in and out every step)"},
+                "gpu_launches": int(launches), "roofline": roof, "roofline_fp64": roof64, "roofline_k5": roof_k5,
+                "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
+                "interface_exchange_ms": comm_ms if world > 1 else None,
+                "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        ex.close(); g.close(); m.close()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--n", type=int, default=100, help="cube edge in elements per GPU (100 -> 1M elements, configs[1])")
+    ap.add_argument("--impl", default="tahoe_b200", choices=["tahoe_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    # per-element figures of K1 taken from the committed ncu capture (profiles/), see DESIGN.md
+    ap.add_argument("--k1-flop-per-element", type=float, default=K1_FLOP_PER_ELEMENT)
+    ap.add_argument("--k1-traffic-bytes", type=float, default=K1_TRAFFIC_BYTES)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+# FP64 flops per element executed by K1 (DFMA = 2, DADD/DMUL = 1), from the ncu capture in profiles/ (None until measured)
+K1_FLOP_PER_ELEMENT = 6000.0
+K1_TRAFFIC_BYTES = None
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/* tahoe_b200.h -- C ABI of libtahoe_b200.so: the B200 (sm_100a, FP64) implementation of Tahoe's
+ * Hex8 continuum-solid hot path.
+ *
+ * Tahoe has no FFI today: the boundary is three C++ abstract classes.  Every entry point
+ * below names the reference member function (file:line under the Tahoe source tree) whose work it
+ * performs, so that the C++ plugin classes in tahoe_b200/host/ (CudaSolidElementT : ElementBaseT,
+ * CudaCSRMatrixT : GlobalMatrixT, CudaExplicitCD) are thin forwarding shells.  INTEGRATION.md shows the
+ * reference-side registration.
+ *
+ * Conventions (identical to the reference):
+ *   - nodal arrays are [node][dof] doubles (dArray2DT), ndof = nsd = 3;
+ *   - connectivity is [element][8] int32, 0-based, HexahedronT node order (HexahedronT.cpp:23-25);
+ *   - equation numbers are 1-based, <= 0 means prescribed (FieldT.cpp:635-659);
+ *   - symmetric tensors are ordered 11,22,33,23,13,12 (dSymMatrixT);
+ *   - 8 integration points, +-1/sqrt(3), in node order, unit weights (HexahedronT.cpp:1540-1547).
+ *   - all arithmetic is FP64.  There is no CPU fallback: every call fails with TB2_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ *
+ * Pointers named d_* are DEVICE pointers on the mesh's device; pointers named h_* are HOST pointers.
+ * All calls are synchronous with respect to the host unless stated otherwise; one CUDA stream per mesh.
+ * Return value: 0 (TB2_OK) or a tb2_status; the mapping to Tahoe's ExceptionT::CodeT is in tb2_status.
+ */
+#ifndef TAHOE_B200_H
+#define TAHOE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TB2_OK = 0,
+    TB2_ERR_BAD_JACOBIAN = 1, /* ExceptionT::kBadJacobianDet: det J <= 0 (ParentDomainT.cpp:451) or det F <= 0 (TotalLagrangianT.cpp:127) */
+    TB2_ERR_J2_LOCAL = 2,     /* ExceptionT::kGeneralFail: J2 local Newton failed (J2SimoC0HardeningT.cpp:203-204) */
+    TB2_ERR_CUDA = 3,         /* ExceptionT::kGeneralFail: CUDA runtime error / no device */
+    TB2_ERR_ARG = 4,          /* ExceptionT::kBadInputValue */
+    TB2_ERR_SIZE = 5,         /* ExceptionT::kSizeMismatch / kOutOfRange */
+    TB2_ERR_PCG_BREAKDOWN = 6,/* ExceptionT::kGeneralFail: p.Ap <= 0 */
+    TB2_ERR_COMM = 7          /* ExceptionT::kMPIFail */
+} tb2_status;
+
+typedef enum { TB2_SMALL_STRAIN = 0, TB2_TOTAL_LAGRANGIAN = 1, TB2_UPDATED_LAGRANGIAN = 2 } tb2_formulation;
+/* materials: SSKStV (Hookean/KStV/SSKStV.cpp), FDKStV (FDKStV.cpp), SimoIso3D (Simo/SimoIso3D.cpp), J2Simo3D (plasticity_J2/J2Simo3D.cpp) */
+typedef enum { TB2_SSKSTV = 0, TB2_FDKSTV = 1, TB2_SIMO_ISO = 2, TB2_J2_SIMO = 3 } tb2_material_kind;
+typedef enum { TB2_HARD_LINEAR = 0, TB2_HARD_LINEAR_EXP = 1 } tb2_hardening_kind;
+/* kinematic boundary condition codes per dof (KBC_CardT::CodeT subset used by nExplicitCD::ConsistentKBC, nExplicitCD.cpp:20-69) */
+typedef enum { TB2_BC_FREE = 0, TB2_BC_FIX = 1, TB2_BC_DSP = 2 } tb2_bc_code;
+
+typedef struct {
+    int32_t kind;      /* tb2_material_kind */
+    int32_t hard_kind; /* tb2_hardening_kind (J2 only) */
+    double  mu, lambda, kappa, density; /* IsotropicT (materials/primitives/IsotropicT.cpp:32-45) */
+    double  hard[4];   /* linear: K = hard[0]*alpha + hard[1] (C1functions/LinearT.h:71);
+                          linear_exponential: K = hard[0] + hard[1]*alpha + hard[2]*(1 - exp(-alpha/hard[3])) */
+} tb2_material;
+
+typedef struct tb2_mesh      tb2_mesh;      /* device-resident connectivity + reference coordinates (ModelManagerT / ElementBaseT::fConnectivities) */
+typedef struct tb2_group     tb2_group;     /* one continuum-solid element group (SolidElementT subclass + its material + history) */
+typedef struct tb2_equations tb2_equations; /* equation numbers + sparsity (FieldT::fEqnos, MSRBuilderT) */
+typedef struct tb2_matrix    tb2_matrix;    /* device CSR global matrix (GlobalMatrixT subclass; MSRMatrixT semantics) */
+typedef struct tb2_explicit  tb2_explicit;  /* d, v, a, lumped mass, BCs on device: FieldT + nExplicitCD + DiagonalMatrixT */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* tb2_version(void);
+const char* tb2_last_error(void);          /* text of the last CUDA / argument error on this thread */
+int tb2_device_count(int* count);
+/* raw device memory helpers for hosts that do not bring their own allocator (the C++ plugin classes) */
+int tb2_malloc(int device, size_t bytes, void** d_ptr);
+int tb2_free(int device, void* d_ptr);
+int tb2_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes);
+int tb2_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes);
+int tb2_host_register(void* h_ptr, size_t bytes);   /* pin a Tahoe-owned dArrayT for async copies */
+int tb2_host_unregister(void* h_ptr);
+
+/* ---- instrumentation ---------------------------------------------------------------------------
+ * Per-kernel device times measured with CUDA events on the mesh stream, and the number of kernels this library launched.
+ * Categories: 0 element internal force (K1), 1 node gather + central-difference update (K5), 2 predictor, 3 SpMV (K6),
+ * 4 PCG vector kernels (K7/K8), 5 stiffness assembly (K3), 6 interface exchange, 7 other.
+ * tb2_profile_end synchronises the stream; h_ms[8], h_count[8]. */
+int tb2_profile_begin(tb2_mesh* mesh);
+int tb2_profile_end(tb2_mesh* mesh, double* h_ms, int64_t* h_count, int64_t* kernel_launches);
+int tb2_mesh_synchronize(tb2_mesh* mesh);
+/* measured FP64 FMA throughput of the device (dependent-FMA chains, best of 5): the roofline denominator of K1 / K3 */
+int tb2_measure_fp64_peak(int device, double* tflops);
+
+/* ---- mesh (ElementBaseT::DefineElements ElementBaseT.cpp:592-658, ModelManagerT coordinates) --- */
+/* Uploads connectivity (re-laid-out SoA [8][ne_pad]) and reference coordinates, builds the
+ * node->(element,local node) incidence used by the deterministic gather (replaces the serial
+ * scatter of SolverT::AssembleRHS, SolverT.cpp:446-477). */
+int tb2_mesh_create(int device, int64_t num_nodes, int64_t num_elements, const int32_t* h_conn, const double* h_coords,
+                    tb2_mesh** mesh);
+int tb2_mesh_destroy(tb2_mesh* mesh);
+int tb2_mesh_sizes(const tb2_mesh* mesh, int64_t* num_nodes, int64_t* num_elements);
+int tb2_mesh_device(const tb2_mesh* mesh, int* device);
+void* tb2_mesh_stream(const tb2_mesh* mesh); /* cudaStream_t all kernels of this mesh are launched on */
+/* Greedy element colouring in element order (no reference counterpart; pinned to
+ * oracle/tahoe_oracle.c:orc_greedy_colouring).  h_colour[num_elements], returns the colour count. */
+int tb2_mesh_colouring(tb2_mesh* mesh, int32_t* h_colour, int32_t* num_colours);
+
+/* ---- element group (SolidElementT / SmallStrainT / TotalLagrangianT / UpdatedLagrangianT) -------- */
+int tb2_group_create(tb2_mesh* mesh, int formulation, const tb2_material* material, tb2_group** group);
+int tb2_group_destroy(tb2_group* group);
+/* SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295) with FormKd (SmallStrainT.cpp:255-282,
+ * TotalLagrangianT.cpp:107-144, UpdatedLagrangianT.cpp:145-171): d_fint[nn][3] = sum_e B^T sigma
+ * (Tahoe's RHS receives -d_fint).  d_u_last may be NULL unless the material is J2.  iteration is
+ * ElementSupportT::IterationNumber() (-1 on the first RHS of a step: J2Simo3D.cpp:83-84).
+ * Asynchronous on the mesh stream; errors are reported by tb2_group_status. */
+int tb2_form_internal_force(tb2_group* group, const double* d_u, const double* d_u_last, int iteration, double* d_fint);
+/* same through host arrays: the call a host-resident RHSDriver() makes (H2D u, kernels, D2H fint) */
+int tb2_form_internal_force_host(tb2_group* group, const double* h_u, const double* h_u_last, int iteration, double* h_fint);
+/* first failing element (0-based) and code since the last call; resets the flag.  Synchronises. */
+int tb2_group_status(tb2_group* group, int64_t* bad_element);
+/* ContinuumElementT::FormMass kLumpedMass (ContinuumElementT.cpp:767-842) summed to nodes: d_mass[nn][3] */
+int tb2_form_lumped_mass(tb2_group* group, double* d_mass);
+int tb2_form_lumped_mass_host(tb2_group* group, double* h_mass);
+/* J2 history: SolidElementT::CloseStep -> J2Simo3D::UpdateHistory (J2SimoC0HardeningT.cpp:341-384), ResetStep -> ResetHistory (:387-407) */
+int tb2_group_close_step(tb2_group* group);
+int tb2_group_reset_step(tb2_group* group);
+/* J2 history download in the reference's ElementCardT layout (J2SimoC0HardeningT.cpp:429-452):
+ * h_data[ne][5*48+64] doubles, h_flags[ne][8], h_alloc[ne] (restart hand-off, ContinuumElementT.cpp:217-249) */
+int tb2_group_get_history(tb2_group* group, double* h_data, int32_t* h_flags, int32_t* h_alloc);
+int tb2_group_set_history(tb2_group* group, const double* h_data, const int32_t* h_flags, const int32_t* h_alloc);
+
+/* ---- explicit central difference (nExplicitCD.cpp:72-139, DiagonalMatrixT.cpp:267-323, FieldT.cpp:531-556) */
+int tb2_explicit_create(tb2_group* group, tb2_explicit** ex); /* forms and inverts the lumped mass */
+int tb2_explicit_destroy(tb2_explicit* ex);
+int tb2_explicit_set_state(tb2_explicit* ex, const double* h_d, const double* h_v, const double* h_a);
+int tb2_explicit_get_state(tb2_explicit* ex, double* h_d, double* h_v, double* h_a);
+/* h_code[nn][3] tb2_bc_code, h_value[nn][3] prescribed displacement, h_fext[nn][3] nodal forces (FieldT::FormRHS, FieldT.cpp:390-411).
+ * Any pointer may be NULL to keep the current array. */
+int tb2_explicit_set_bc(tb2_explicit* ex, const uint8_t* h_code, const double* h_value, const double* h_fext);
+/* FEManagerT::InitialCondition (FEManagerT.cpp:2034): a = M^-1 (fext - fint(d)) on free dofs */
+int tb2_explicit_initial_condition(tb2_explicit* ex);
+/* nsteps x { Predictor + ConsistentKBC ; fint ; a = M^-1 R ; Corrector }.  h_fext_scale / h_value_scale
+ * (each nsteps long or NULL = 1.0) scale the stored fext / prescribed values at each step (ScheduleT). */
+int tb2_explicit_run(tb2_explicit* ex, double dt, int nsteps, const double* h_fext_scale, const double* h_value_scale);
+/* one step through host arrays: H2D d,v,a ; step ; D2H d,v,a  (what a drop-in does when Tahoe's FieldT stays authoritative) */
+int tb2_explicit_step_host(tb2_explicit* ex, double dt, double* h_d, double* h_v, double* h_a);
+/* device views for cooperating plugins / multi-GPU harness: which = 0 d, 1 v, 2 a, 3 mass, 4 fext, 5 fint */
+double* tb2_explicit_device_array(tb2_explicit* ex, int which);
+
+/* ---- equations + sparsity (NodeManagerT::SetEquationNumbers NodeManagerT.cpp:712-767; GraphT::MakeGraph GraphT.cpp:376-488;
+ *      MSRBuilderT.cpp:134-181,216-244) ---------------------------------------------------------- */
+int tb2_equations_create(tb2_mesh* mesh, const uint8_t* h_bc_code /*[nn][3], nonzero = prescribed*/, tb2_equations** eqs);
+int tb2_equations_destroy(tb2_equations* eqs);
+int tb2_equations_count(const tb2_equations* eqs, int64_t* num_eq);
+int tb2_equations_get(const tb2_equations* eqs, int32_t* h_eqnos /*[nn][3]*/);
+const int32_t* tb2_equations_device(const tb2_equations* eqs);
+
+/* ---- global matrix (GlobalMatrixT.h:24-223; storage semantics of MSRMatrixT, solve = AztecMatrixT-style CG+Jacobi) */
+int tb2_matrix_create(tb2_equations* eqs, tb2_matrix** A); /* GlobalMatrixT::Initialize + MSRBuilderT: CSR structure built on device */
+int tb2_matrix_destroy(tb2_matrix* A);
+int tb2_matrix_nnz(const tb2_matrix* A, int64_t* nnz);
+/* MSRBuilderT::SetSuperLUData form: rowptr[neq+1] (int64), colind[nnz] sorted, diagonal in place */
+int tb2_matrix_get_csr(const tb2_matrix* A, int64_t* h_rowptr, int32_t* h_colind, double* h_val /* may be NULL */);
+/* MSRBuilderT::SetMSRData form (MSRMatrixT.h:21-23): returns length when h_bindx == NULL */
+int tb2_matrix_get_msr(const tb2_matrix* A, int upper_only, int32_t* h_bindx, int64_t* length);
+int tb2_matrix_clear(tb2_matrix* A); /* GlobalMatrixT::Clear */
+/* SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154) + FormStiffness (SmallStrainT.cpp:285-324,
+ * TotalLagrangianT.cpp:40-104, UpdatedLagrangianT.cpp:94-142) + MSRMatrixT::Assemble (MSRMatrixT.cpp:66-216):
+ * A += K(u), colour by colour through the element->slot map (no float atomics). */
+int tb2_form_stiffness(tb2_group* group, tb2_matrix* A, const double* d_u, const double* d_u_last, int iteration);
+int tb2_form_stiffness_host(tb2_group* group, tb2_matrix* A, const double* h_u, const double* h_u_last, int iteration);
+/* MSRMatrixT::Multx (MSRMatrixT.cpp:385-420): y = A x on equation-space vectors [neq] */
+int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y);
+int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y);
+/* GlobalMatrixT::CopyDiagonal */
+int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag);
+/* GlobalMatrixT::Solve -> BackSubstitute (GlobalMatrixT.cpp:77-113): Jacobi-preconditioned CG
+ * (preconditioner = DiagonalMatrixT::Factorize semantics, DiagonalMatrixT.cpp:267-310).
+ * d_x: start guess in, solution out.  Stops when |r| <= atol or |r| <= rtol*|r0| or max_iter. */
+int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
+                   double* final_rnorm);
+int tb2_matrix_pcg_host(tb2_matrix* A, const double* h_b, double* h_x, double rtol, double atol, int max_iter,
+                        int* iterations, double* final_rnorm);
+/* gather / scatter between [nn][3] nodal arrays and [neq] equation vectors (FieldT::AssembleUpdate FieldT.cpp:531-556,
+ * SolverT::AssembleRHS SolverT.cpp:446-477): y_eq = x_node[active] ; x_node[active] += s * y_eq */
+int tb2_equations_gather(const tb2_equations* eqs, const double* d_nodal, double* d_eqvec);
+int tb2_equations_scatter_add(const tb2_equations* eqs, double scale, const double* d_eqvec, double* d_nodal);
+
+/* ---- multi-GPU (replaces CommManagerT::AllGather / CommunicatorT::Sum) ------------ */
+/* One process per GPU.  The harness creates an NCCL unique id on rank 0, distributes it by its own
+ * means, and every rank calls tb2_comm_init on its mesh.  h_interface_nodes are this rank's local node
+ * ids of nodes shared with other ranks, h_interface_slots their positions in the packed global interface
+ * vector (identical on every sharer). */
+int tb2_comm_unique_id(char h_id[128]);
+int tb2_comm_init(tb2_mesh* mesh, int rank, int nranks, const char h_id[128], int64_t num_interface_nodes,
+                  const int32_t* h_interface_nodes, const int32_t* h_interface_slots, int64_t num_global_interface_nodes,
+                  const uint8_t* h_node_owned /*[nn]: 1 if this rank owns the node (dot products count it once)*/);
+int tb2_comm_destroy(tb2_mesh* mesh);
+/* d_nodal[nn][3] += contributions of the other sharers on interface nodes (ncclAllReduce on the packed vector) */
+int tb2_comm_sum_interface(tb2_mesh* mesh, double* d_nodal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,375 @@
+"""ctypes binding of libtahoe_b200.so (include/tahoe_b200.h).
+
+This is the harness-side binding used by tests/, bench.py and __graft_entry__.py; the product's host side is the C++
+plugin layer in tahoe_b200/host/ which calls the same C ABI.  There is no fallback of any kind: if the shared library
+is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libtahoe_b200.so")
+
+SMALL_STRAIN, TOTAL_LAGRANGIAN, UPDATED_LAGRANGIAN = 0, 1, 2
+SSKSTV, FDKSTV, SIMO_ISO, J2_SIMO = 0, 1, 2, 3
+FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2}
+KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3}
+STATUS = {0: "ok", 1: "bad_jacobian", 2: "j2_local", 3: "cuda", 4: "argument", 5: "size", 6: "pcg_breakdown", 7: "comm"}
+J2_BLOCK = 5 * 48 + 64  # doubles per element in the reference's ElementCardT layout
+
+# the exported symbols of include/tahoe_b200.h (checked by tests/test_capi_symbols.py against the header text)
+SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2_memcpy_h2d tb2_memcpy_d2h tb2_host_register
+tb2_host_unregister tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
+tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
+tb2_form_lumped_mass_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
+tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
+tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
+tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_destroy
+tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
+tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
+tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface""".split()
+
+
+class Tb2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("tahoe_b200: %s (%d): %s" % (STATUS.get(code, "?"), code, msg))
+        self.code = code
+
+
+class Material(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("hard_kind", C.c_int32), ("mu", C.c_double), ("lam", C.c_double), ("kappa", C.c_double),
+                ("density", C.c_double), ("hard", C.c_double * 4)]
+
+
+_lib = None
+
+
+def lib():
+    """load the C-ABI library; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libtahoe_b200.so is not built (%s); run __graft_entry__.build() -- there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.tb2_version.restype = C.c_char_p
+        L.tb2_last_error.restype = C.c_char_p
+        L.tb2_mesh_stream.restype = C.c_void_p
+        L.tb2_explicit_device_array.restype = C.c_void_p
+        L.tb2_equations_device.restype = C.c_void_p
+        _lib = L
+    return _lib
+
+
+def _chk(code):
+    if code != 0:
+        raise Tb2Error(code, lib().tb2_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _dp(x):
+    """device pointer from an int, a torch tensor or None"""
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, np.float64)
+
+
+def material(desc_mat):
+    """tb2_material from the XML material description (IsotropicT::TakeParameterList, IsotropicT.cpp:32-45)"""
+    m = Material()
+    m.kind = KIND_OF[desc_mat["type"]]
+    m.density = desc_mat.get("density", 1.0)
+    if "E" in desc_mat:
+        E, nu = desc_mat["E"], desc_mat["nu"]
+        m.mu = 0.5 * E / (1.0 + nu)
+        m.lam = 2.0 * m.mu * nu / (1.0 - 2.0 * nu)
+        m.kappa = m.lam + 2.0 / 3.0 * m.mu
+    else:
+        m.mu, m.kappa = desc_mat["mu"], desc_mat["kappa"]
+        m.lam = m.kappa - 2.0 * m.mu / 3.0
+    h = desc_mat.get("hardening")
+    if h:
+        if h["type"] == "linear_function":
+            m.hard_kind = 0
+            m.hard[0], m.hard[1] = h["a"], h["b"]
+        else:
+            m.hard_kind = 1
+            for i, k in enumerate("abcd"):
+                m.hard[i] = h[k]
+    return m
+
+
+def device_count():
+    n = C.c_int(0)
+    _chk(lib().tb2_device_count(C.byref(n)))
+    return n.value
+
+
+def measure_fp64_peak(device=0):
+    t = C.c_double(0.0)
+    _chk(lib().tb2_measure_fp64_peak(int(device), C.byref(t)))
+    return t.value
+
+
+class _Handle:
+    """Owner of one C handle.  Children (group of a mesh, matrix of an equation set ...) are closed before their parent no
+    matter in which order Python finalises the objects (the cyclic GC gives no order): parent and child reference each other
+    strongly, and whichever is finalised first closes the sub-tree bottom-up."""
+    _destroy = None
+
+    def _init_handle(self, parent=None):
+        self.h = C.c_void_p()
+        self._children = []
+        self._parent = parent
+        if parent is not None:
+            parent._children.append(self)
+
+    def close(self):
+        if not getattr(self, "h", None):
+            return
+        for c in list(self._children):
+            c.close()
+        self._children = []
+        getattr(lib(), self._destroy)(self.h)
+        self.h = C.c_void_p()
+        if self._parent is not None and self in self._parent._children:
+            self._parent._children.remove(self)
+        self._parent = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mesh(_Handle):
+    _destroy = "tb2_mesh_destroy"
+
+    def __init__(self, coords, conn, device=0):
+        coords = _f64(coords)
+        conn = np.ascontiguousarray(conn, np.int32)
+        assert coords.ndim == 2 and coords.shape[1] == 3 and conn.ndim == 2 and conn.shape[1] == 8
+        self.nn, self.ne, self.device = coords.shape[0], conn.shape[0], device
+        self._init_handle()
+        _chk(lib().tb2_mesh_create(device, C.c_int64(self.nn), C.c_int64(self.ne), _p(conn), _p(coords), C.byref(self.h)))
+
+    @property
+    def stream(self):
+        return lib().tb2_mesh_stream(self.h)
+
+    def synchronize(self):
+        _chk(lib().tb2_mesh_synchronize(self.h))
+
+    def profile_begin(self):
+        _chk(lib().tb2_profile_begin(self.h))
+
+    def profile_end(self):
+        """-> (ms[8], count[8], kernel_launches) per category of include/tahoe_b200.h"""
+        ms, cnt, n = np.zeros(8), np.zeros(8, np.int64), C.c_int64(0)
+        _chk(lib().tb2_profile_end(self.h, _p(ms), _p(cnt), C.byref(n)))
+        return ms, cnt, n.value
+
+    def colouring(self):
+        col = np.zeros(self.ne, np.int32)
+        n = C.c_int32(0)
+        _chk(lib().tb2_mesh_colouring(self.h, _p(col), C.byref(n)))
+        return n.value, col
+
+    # ---- multi-GPU
+    def comm_init(self, rank, nranks, uid, if_nodes, if_slots, n_global_interface, owned):
+        if_nodes = np.ascontiguousarray(if_nodes, np.int32)
+        if_slots = np.ascontiguousarray(if_slots, np.int32)
+        owned = np.ascontiguousarray(owned, np.uint8)
+        _chk(lib().tb2_comm_init(self.h, rank, nranks, uid, C.c_int64(len(if_nodes)), _p(if_nodes), _p(if_slots),
+                                 C.c_int64(n_global_interface), _p(owned)))
+
+    def sum_interface(self, d_nodal):
+        _chk(lib().tb2_comm_sum_interface(self.h, _dp(d_nodal)))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _chk(lib().tb2_comm_unique_id(buf))
+    return buf.raw
+
+
+class Group(_Handle):
+    _destroy = "tb2_group_destroy"
+
+    def __init__(self, mesh, form, mat):
+        self.mesh, self.form, self.mat = mesh, form, mat
+        self._init_handle(mesh)
+        _chk(lib().tb2_group_create(mesh.h, int(form), C.byref(mat), C.byref(self.h)))
+
+    def internal_force_host(self, u, u_last=None, iteration=0):
+        u, u_last = _f64(u), _f64(u_last)
+        f = np.zeros((self.mesh.nn, 3))
+        _chk(lib().tb2_form_internal_force_host(self.h, _p(u), _p(u_last), int(iteration), _p(f)))
+        return f
+
+    def internal_force(self, d_u, d_u_last, iteration, d_f):
+        _chk(lib().tb2_form_internal_force(self.h, _dp(d_u), _dp(d_u_last), int(iteration), _dp(d_f)))
+
+    def status(self):
+        bad = C.c_int64(-1)
+        return lib().tb2_group_status(self.h, C.byref(bad)), bad.value
+
+    def lumped_mass_host(self):
+        m = np.zeros((self.mesh.nn, 3))
+        _chk(lib().tb2_form_lumped_mass_host(self.h, _p(m)))
+        return m
+
+    def close_step(self):
+        _chk(lib().tb2_group_close_step(self.h))
+
+    def reset_step(self):
+        _chk(lib().tb2_group_reset_step(self.h))
+
+    def get_history(self):
+        ne = self.mesh.ne
+        data, flags, alloc = np.zeros((ne, J2_BLOCK)), np.zeros((ne, 8), np.int32), np.zeros(ne, np.int32)
+        _chk(lib().tb2_group_get_history(self.h, _p(data), _p(flags), _p(alloc)))
+        return data, flags, alloc
+
+    def set_history(self, data, flags, alloc):
+        data, flags, alloc = _f64(data), np.ascontiguousarray(flags, np.int32), np.ascontiguousarray(alloc, np.int32)
+        _chk(lib().tb2_group_set_history(self.h, _p(data), _p(flags), _p(alloc)))
+
+
+class Explicit(_Handle):
+    _destroy = "tb2_explicit_destroy"
+
+    def __init__(self, group):
+        self.group = group
+        self.nn = group.mesh.nn
+        self._init_handle(group)
+        _chk(lib().tb2_explicit_create(group.h, C.byref(self.h)))
+
+    def set_state(self, d=None, v=None, a=None):
+        _chk(lib().tb2_explicit_set_state(self.h, _p(_f64(d)), _p(_f64(v)), _p(_f64(a))))
+
+    def get_state(self):
+        d, v, a = (np.zeros((self.nn, 3)) for _ in range(3))
+        _chk(lib().tb2_explicit_get_state(self.h, _p(d), _p(v), _p(a)))
+        return d, v, a
+
+    def set_bc(self, code=None, value=None, fext=None):
+        code = None if code is None else np.ascontiguousarray(code, np.uint8)
+        _chk(lib().tb2_explicit_set_bc(self.h, _p(code), _p(_f64(value)), _p(_f64(fext))))
+
+    def initial_condition(self):
+        _chk(lib().tb2_explicit_initial_condition(self.h))
+
+    def run(self, dt, nsteps, fext_scale=None, value_scale=None):
+        fs, vs = _f64(fext_scale), _f64(value_scale)
+        assert fs is None or len(fs) >= nsteps
+        assert vs is None or len(vs) >= nsteps
+        _chk(lib().tb2_explicit_run(self.h, C.c_double(dt), int(nsteps), _p(fs), _p(vs)))
+
+    def step_host(self, dt, d, v, a):
+        """d, v, a: C-contiguous float64 host arrays (ideally pinned), updated in place"""
+        _chk(lib().tb2_explicit_step_host(self.h, C.c_double(dt), C.c_void_p(d.ctypes.data), C.c_void_p(v.ctypes.data),
+                                          C.c_void_p(a.ctypes.data)))
+
+    def step_host_ptr(self, dt, pd, pv, pa):
+        _chk(lib().tb2_explicit_step_host(self.h, C.c_double(dt), C.c_void_p(pd), C.c_void_p(pv), C.c_void_p(pa)))
+
+    def device_array(self, which):
+        return lib().tb2_explicit_device_array(self.h, int(which))
+
+    def mass_host(self):
+        m = np.zeros((self.nn, 3))
+        _chk(lib().tb2_memcpy_d2h(self.group.mesh.device, _p(m), C.c_void_p(self.device_array(3)), C.c_size_t(m.nbytes)))
+        return m
+
+
+class Equations(_Handle):
+    _destroy = "tb2_equations_destroy"
+
+    def __init__(self, mesh, bc_code):
+        self.mesh = mesh
+        bc = np.ascontiguousarray(np.asarray(bc_code) != 0, np.uint8)
+        assert bc.shape == (mesh.nn, 3)
+        self._init_handle(mesh)
+        _chk(lib().tb2_equations_create(mesh.h, _p(bc), C.byref(self.h)))
+        n = C.c_int64(0)
+        _chk(lib().tb2_equations_count(self.h, C.byref(n)))
+        self.neq = n.value
+
+    def eqnos(self):
+        eq = np.zeros((self.mesh.nn, 3), np.int32)
+        _chk(lib().tb2_equations_get(self.h, _p(eq)))
+        return eq
+
+    def gather(self, d_nodal, d_eqvec):
+        _chk(lib().tb2_equations_gather(self.h, _dp(d_nodal), _dp(d_eqvec)))
+
+    def scatter_add(self, scale, d_eqvec, d_nodal):
+        _chk(lib().tb2_equations_scatter_add(self.h, C.c_double(scale), _dp(d_eqvec), _dp(d_nodal)))
+
+
+class Matrix(_Handle):
+    _destroy = "tb2_matrix_destroy"
+
+    def __init__(self, eqs):
+        self.eqs = eqs
+        self.neq = eqs.neq
+        self._init_handle(eqs)
+        _chk(lib().tb2_matrix_create(eqs.h, C.byref(self.h)))
+        n = C.c_int64(0)
+        _chk(lib().tb2_matrix_nnz(self.h, C.byref(n)))
+        self.nnz = n.value
+
+    def csr(self, values=True):
+        rowptr, colind = np.zeros(self.neq + 1, np.int64), np.zeros(self.nnz, np.int32)
+        val = np.zeros(self.nnz) if values else None
+        _chk(lib().tb2_matrix_get_csr(self.h, _p(rowptr), _p(colind), _p(val)))
+        return rowptr, colind, val
+
+    def msr(self, upper_only):
+        n = C.c_int64(0)
+        _chk(lib().tb2_matrix_get_msr(self.h, int(upper_only), None, C.byref(n)))
+        bindx = np.zeros(n.value, np.int32)
+        _chk(lib().tb2_matrix_get_msr(self.h, int(upper_only), _p(bindx), C.byref(n)))
+        return bindx
+
+    def clear(self):
+        _chk(lib().tb2_matrix_clear(self.h))
+
+    def form_stiffness_host(self, group, u, u_last=None, iteration=0):
+        _chk(lib().tb2_form_stiffness_host(group.h, self.h, _p(_f64(u)), _p(_f64(u_last)), int(iteration)))
+
+    def form_stiffness(self, group, d_u, d_u_last=None, iteration=0):
+        _chk(lib().tb2_form_stiffness(group.h, self.h, _dp(d_u), _dp(d_u_last), int(iteration)))
+
+    def multx_host(self, x):
+        x = _f64(x)
+        y = np.zeros_like(x)
+        _chk(lib().tb2_matrix_multx_host(self.h, _p(x), _p(y)))
+        return y
+
+    def multx(self, d_x, d_y):
+        _chk(lib().tb2_matrix_multx(self.h, _dp(d_x), _dp(d_y)))
+
+    def pcg_host(self, b, x0=None, rtol=1e-12, atol=0.0, max_iter=10000):
+        b = _f64(b)
+        x = np.zeros_like(b) if x0 is None else _f64(x0).copy()
+        it, rn = C.c_int(0), C.c_double(0.0)
+        _chk(lib().tb2_matrix_pcg_host(self.h, _p(b), _p(x), C.c_double(rtol), C.c_double(atol), int(max_iter), C.byref(it), C.byref(rn)))
+        return x, it.value, rn.value
+
+    def pcg(self, d_b, d_x, rtol=1e-12, atol=0.0, max_iter=10000):
+        it, rn = C.c_int(0), C.c_double(0.0)
+        _chk(lib().tb2_matrix_pcg(self.h, _dp(d_b), _dp(d_x), C.c_double(rtol), C.c_double(atol), int(max_iter), C.byref(it), C.byref(rn)))
+        return it.value, rn.value

@@ -1,0 +1,190 @@
+// tb2_comm.cu -- multi-GPU exchange: element-partitioned mesh, one process per GPU.
+//
+// The reference exchanges ghost-node field updates point-to-point and sums dot products with MPI_Allreduce
+// (CommManagerT::AllGather CommManagerT.cpp:424-436, SolverT::InnerProduct SolverT.cpp:854-860).  Here every rank owns a
+// set of elements; nodes on partition faces are replicated on every touching rank.  The one exchange per sweep is the sum
+// of partial nodal quantities (internal force, lumped mass, A_loc p) over the sharers, done as ONE ncclAllReduce on the
+// packed global interface vector (every rank contributes zeros for interface nodes it does not touch): every sharer
+// receives bitwise the same sum, so the redundant node updates stay identical on all ranks.
+//
+// NCCL is bound at run time (dlopen libnccl.so.2) so that a single-GPU host needs no NCCL at all and a torch-hosted
+// harness shares the NCCL already loaded in the process.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "tb2_internal.h"
+
+namespace tb2 {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { kNcclSum = 0, kNcclFloat64 = 8 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.lib) return TB2_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("cannot load NCCL: %s", dlerror());
+        return TB2_ERR_COMM;
+    }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+        set_error("NCCL library lacks required symbols");
+        return TB2_ERR_COMM;
+    }
+    g_nccl.lib = h;
+    return TB2_OK;
+}
+static int nccl_fail(int r, const char* what)
+{
+    set_error("NCCL error %d (%s) in %s", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what);
+    return TB2_ERR_COMM;
+}
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int64_t n_if = 0, n_glob = 0;
+    DevBuf<int> nodes, slots;
+    DevBuf<double> packed;          // [n_glob][3]
+    DevBuf<unsigned char> owned;    // [nn]
+    DevBuf<double> scal;            // all-reduce scratch for scalars
+};
+
+__global__ void k_pack(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots, const double* __restrict__ nodal,
+                       double* __restrict__ packed)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_if) return;
+    const int64_t k = t / 3;
+    const int i = (int)(t % 3);
+    packed[3 * (int64_t)slots[k] + i] = nodal[3 * (int64_t)nodes[k] + i];
+}
+__global__ void k_unpack(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots, const double* __restrict__ packed,
+                         double* __restrict__ nodal)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_if) return;
+    const int64_t k = t / 3;
+    const int i = (int)(t % 3);
+    nodal[3 * (int64_t)nodes[k] + i] = packed[3 * (int64_t)slots[k] + i];
+}
+
+bool comm_active(tb2_mesh* m) { return m->comm && m->comm->nranks > 1 && m->comm->n_glob > 0; }
+const unsigned char* comm_owned_mask(tb2_mesh* m) { return m->comm ? m->comm->owned.p : nullptr; }
+
+// in-place sum of n doubles over ranks (PCG scalars); no-op without a communicator
+int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n)
+{
+    if (!m->comm || m->comm->nranks == 1) return TB2_OK;
+    const int r = g_nccl.AllReduce(d_vals, d_vals, (size_t)n, kNcclFloat64, kNcclSum, m->comm->comm, m->stream);
+    return r ? nccl_fail(r, "ncclAllReduce(scalars)") : TB2_OK;
+}
+
+} // namespace tb2
+
+using namespace tb2;
+
+extern "C" {
+
+int tb2_comm_unique_id(char h_id[128])
+{
+    TB2_ARG(h_id);
+    TB2_CHECK(load_nccl());
+    ncclUniqueId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r) return nccl_fail(r, "ncclGetUniqueId");
+    memcpy(h_id, id.internal, 128);
+    return TB2_OK;
+}
+
+int tb2_comm_init(tb2_mesh* m, int rank, int nranks, const char h_id[128], int64_t n_if, const int32_t* h_nodes, const int32_t* h_slots,
+                  int64_t n_glob, const uint8_t* h_owned)
+{
+    TB2_ARG(m && h_id && nranks >= 1 && rank >= 0 && rank < nranks && n_if >= 0 && n_glob >= n_if);
+    TB2_ARG(n_if == 0 || (h_nodes && h_slots));
+    DeviceGuard dg(m->device);
+    TB2_CHECK(load_nccl());
+    if (m->comm) tb2_comm_destroy(m);
+    Comm* c = new Comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->n_if = n_if;
+    c->n_glob = n_glob;
+    ncclUniqueId id;
+    memcpy(id.internal, h_id, 128);
+    int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r) {
+        delete c;
+        return nccl_fail(r, "ncclCommInitRank");
+    }
+    cudaError_t e = c->nodes.alloc(n_if > 0 ? n_if : 1);
+    if (e == cudaSuccess) e = c->slots.alloc(n_if > 0 ? n_if : 1);
+    if (e == cudaSuccess) e = c->packed.alloc(3 * (n_glob > 0 ? n_glob : 1));
+    if (e == cudaSuccess) e = c->owned.alloc(m->nn);
+    if (e == cudaSuccess) e = c->scal.alloc(8);
+    if (e == cudaSuccess && n_if) e = cudaMemcpy(c->nodes.p, h_nodes, n_if * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_if) e = cudaMemcpy(c->slots.p, h_slots, n_if * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (h_owned) e = cudaMemcpy(c->owned.p, h_owned, m->nn, cudaMemcpyHostToDevice);
+        else e = cudaMemset(c->owned.p, 1, m->nn);
+    }
+    if (e != cudaSuccess) {
+        g_nccl.CommDestroy(c->comm);
+        delete c;
+        return cuda_fail(e, "communicator buffers", __FILE__, __LINE__);
+    }
+    m->comm = c;
+    return TB2_OK;
+}
+
+int tb2_comm_destroy(tb2_mesh* m)
+{
+    if (!m || !m->comm) return TB2_OK;
+    DeviceGuard dg(m->device);
+    cudaStreamSynchronize(m->stream);
+    if (m->comm->comm) g_nccl.CommDestroy(m->comm->comm);
+    delete m->comm;
+    m->comm = nullptr;
+    return TB2_OK;
+}
+
+int tb2_comm_sum_interface(tb2_mesh* m, double* d_nodal)
+{
+    TB2_ARG(m && d_nodal);
+    Comm* c = m->comm;
+    if (!c || c->nranks == 1 || c->n_glob == 0) return TB2_OK;
+    DeviceGuard dg(m->device);
+    ProfScope ps(m, kProfComm, 2);
+    TB2_CUDA(cudaMemsetAsync(c->packed.p, 0, 3 * c->n_glob * sizeof(double), m->stream));
+    const int T = 256;
+    if (c->n_if) k_pack<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->nodes.p, c->slots.p, d_nodal, c->packed.p);
+    const int r = g_nccl.AllReduce(c->packed.p, c->packed.p, (size_t)(3 * c->n_glob), kNcclFloat64, kNcclSum, c->comm, m->stream);
+    if (r) return nccl_fail(r, "ncclAllReduce(interface)");
+    if (c->n_if) k_unpack<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->nodes.p, c->slots.p, c->packed.p, d_nodal);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,507 @@
+// tb2_elements.cu -- K1 (internal force), K4 (lumped mass), the deterministic node gather, and the element-group API.
+//
+// K1 replaces SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295).  One thread owns one element and
+// walks its 8 integration points in the reference's order.  Instead of the per-IP 8x3 shape-function table
+// (HexahedronT.cpp:421-430) the kernel works on the trilinear modes of X and u (tb2_math.cuh), which cuts the
+// Jacobian / grad-u / B^T sigma work from 72 to 27-36 FMA each and keeps everything in registers.
+//
+// Finite strain.  With j = dx/dxi = J0 + du/dxi (J0 = dX/dxi):   F = j J0^-1,  det F = det j / det J0, and both
+//   TotalLagrangianT::FormKd  (f_a = sum_ip w detJ0 J (sigma F^-T) dN_a/dX,  TotalLagrangianT.cpp:107-144) and
+//   UpdatedLagrangianT::FormKd (f_a = sum_ip w det j  sigma dN_a/dx,          UpdatedLagrangianT.cpp:145-171)
+// reduce to  f_a = sum_ip w sigma adj(j)^T dN_a/dxi  (adj = det * inverse): the two reference classes are two
+// roundings of the same integral, so one kernel body serves both and needs no reciprocal of det j.
+//
+// Scatter.  Threads write the 24 element values to an SoA scratch fe[24][stride] (coalesced); a node kernel then sums
+// each node's <= 8 contributions in ascending element order -- the order of the reference's serial assembly
+// (SolverT::AssembleRHS, SolverT.cpp:446-477) -- so there are no float atomics and reruns are bit-reproducible.
+#include "tb2_internal.h"
+
+namespace tb2 {
+
+struct ElemArgs {
+    int64_t ne, stride;
+    const int* conn;  // [8][stride]
+    const double* X;  // [nn][3]
+    const double* u;  // [nn][3]
+    const double* ul; // [nn][3] (J2) or null
+    double* fe;       // [24][stride]
+    MatConst mat;
+    J2Hist hist;
+    int iteration;
+    unsigned long long* status; // [0] = max error code, [1] = min failing element
+};
+
+TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
+{
+    atomicMax(p.status, (unsigned long long)err);
+    atomicMin(p.status + 1, (unsigned long long)e);
+}
+
+template <int FORM, int MAT>
+__global__ void __launch_bounds__(128) k_internal_force(const ElemArgs p)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= p.ne) return;
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+
+    Modes cX, cU, cL, A;
+    load_modes(p.X, n, cX);
+    load_modes(p.u, n, cU);
+    if (MAT == kJ2Simo) load_modes(p.ul, n, cL);
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) A.m[k][i] = 0.0;
+
+    int alloc = 0, err = kErrNone;
+    if (MAT == kJ2Simo) alloc = p.hist.alloc[e];
+
+#pragma unroll 1
+    for (int ip = 0; ip < 8; ip++) {
+        double s0, s1, s2;
+        ip_signs(ip, s0, s1, s2);
+        double J0[3][3], H[3][3], J0a[3][3], G[3][3], S[3][3];
+        mode_gradient(cX, s0, s1, s2, J0);
+        mode_gradient(cU, s0, s1, s2, H);
+        const double det0 = adj3(J0, J0a);
+        if (det0 <= 0.0) err = kErrBadJacobian; // ParentDomainT::ComputeDNa, ParentDomainT.cpp:451
+        const double rdet0 = 1.0 / det0;
+        double sig[6];
+        if (FORM == kSmallStrain) {
+            // SmallStrainT::SetGlobalShape (SmallStrainT.cpp:327-401): eps = sym(grad_X u), grad_X u = H J0^-1
+            double g[3][3], eps[6];
+            mul3(H, J0a, g);
+            eps[0] = g[0][0] * rdet0;
+            eps[1] = g[1][1] * rdet0;
+            eps[2] = g[2][2] * rdet0;
+            eps[3] = 0.5 * (g[1][2] + g[2][1]) * rdet0;
+            eps[4] = 0.5 * (g[0][2] + g[2][0]) * rdet0;
+            eps[5] = 0.5 * (g[0][1] + g[1][0]) * rdet0;
+            hooke_stress(p.mat, eps, sig);
+            sym_to_mat(sig, S);
+            mul3_abt(S, J0a, G); // G = w detJ0 sigma J0^-T
+        } else {
+            double j[3][3], ja[3][3], F[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) j[i][k] = J0[i][k] + H[i][k];
+            const double detj = adj3(j, ja);
+            if (detj <= 0.0) err = kErrBadJacobian; // TotalLagrangianT.cpp:127-128 / current-configuration ComputeDNa
+            mul3(j, J0a, F);
+            scale3(F, rdet0);
+            const double J = detj * rdet0;
+            if (MAT == kFDKStV)
+                fdkstv_stress(p.mat, F, J, sig);
+            else if (MAT == kSimoIso) {
+                double b_bar[6];
+                simo_bbar(F, J, b_bar);
+                simo_cauchy(p.mat, J, b_bar, sig);
+            } else if (MAT == kJ2Simo) {
+                double Hl[3][3], Fl[3][3], c[6][6];
+                mode_gradient(cL, s0, s1, s2, Hl);
+                mul3(Hl, J0a, Fl);
+                scale3(Fl, rdet0);
+                Fl[0][0] += 1.0; Fl[1][1] += 1.0; Fl[2][2] += 1.0; // FiniteStrainT::SetGlobalShape, FiniteStrainT.cpp:267-304
+                const int e2 = j2_eval<false>(p.mat, p.hist, e, ip, alloc, p.iteration, F, Fl, J, sig, c);
+                if (e2) err = e2 > err ? e2 : err;
+            }
+            sym_to_mat(sig, S);
+            mul3_abt(S, ja, G); // G = w det(j) sigma j^-T
+        }
+        mode_accumulate(A, s0, s1, s2, G);
+    }
+    if (err) report(p, err, e);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double f[8];
+        modes_to_nodes(A, i, f);
+#pragma unroll
+        for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
+    }
+}
+
+// K4: ContinuumElementT::FormMass, kLumpedMass branch (ContinuumElementT.cpp:767-842).  me[a] -> fe[a][stride]
+__global__ void __launch_bounds__(128) k_lumped_mass(int64_t ne, int64_t stride, const int* __restrict__ conn,
+                                                    const double* __restrict__ X, double density, double* __restrict__ fe,
+                                                    unsigned long long* status)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(conn + a * stride + e);
+    Modes cX;
+    load_modes(X, n, cX);
+    const double RA[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, SA[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, TA[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+    double nee[8], dsum = 0.0, totmas = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) nee[a] = 0.0;
+#pragma unroll
+    for (int ip = 0; ip < 8; ip++) {
+        double J0[3][3];
+        mode_gradient(cX, RA[ip], SA[ip], TA[ip], J0);
+        const double det0 = det3(J0);
+        if (det0 <= 0.0) {
+            atomicMax(status, (unsigned long long)kErrBadJacobian);
+            atomicMin(status + 1, (unsigned long long)e);
+        }
+        const double temp1 = density * det0; // weight = 1
+        totmas += temp1;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const double Na = 0.125 * (1.0 + RA[a] * RA[ip] * TB2_G) * (1.0 + SA[a] * SA[ip] * TB2_G) * (1.0 + TA[a] * TA[ip] * TB2_G);
+            const double temp2 = temp1 * Na * Na;
+            dsum += temp2;
+            nee[a] += temp2;
+        }
+    }
+    const double diagmass = totmas / dsum;
+#pragma unroll
+    for (int a = 0; a < 8; a++) fe[(int64_t)a * stride + e] = diagmass * nee[a];
+}
+
+// node gather: out[n][i] = sum over incident (e,a), ascending e, of fe[rows(a,i)][e].
+// PER_DOF: rows = 3a+i (forces); else rows = a for all three dofs (lumped mass: same value on the 3 dofs of a node)
+template <bool PER_DOF>
+__global__ void __launch_bounds__(256) k_node_gather(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                    const double* __restrict__ fe, int64_t stride, double* __restrict__ out)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nn) return;
+    const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    for (int k = k0; k < k1; k++) {
+        const int ent = __ldg(inc + k);
+        const int64_t e = ent >> 3;
+        const int a = ent & 7;
+        if (PER_DOF) {
+            f0 += __ldg(fe + (int64_t)(3 * a) * stride + e);
+            f1 += __ldg(fe + (int64_t)(3 * a + 1) * stride + e);
+            f2 += __ldg(fe + (int64_t)(3 * a + 2) * stride + e);
+        } else {
+            const double m = __ldg(fe + (int64_t)a * stride + e);
+            f0 += m; f1 += m; f2 += m;
+        }
+    }
+    out[3 * n] = f0;
+    out[3 * n + 1] = f1;
+    out[3 * n + 2] = f2;
+}
+
+__global__ void k_j2_close_step(int64_t ne, J2Hist h, double mu)
+{
+    // J2SimoC0HardeningT::Update (J2SimoC0HardeningT.cpp:341-384), allocated elements only; one thread per (e, ip)
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t e = t % h.stride;
+    const int ip = (int)(t / h.stride);
+    if (ip >= 8 || e >= ne || !h.alloc[e]) return;
+    double bt[6], bbt[6];
+    hist_load6(h, e, ip, kHBBarTrial, bt);
+    hist_load6(h, e, ip, kHBetaBarTrial, bbt);
+    int& flag = h.flag[(int64_t)ip * h.stride + e];
+    if (flag == kJ2Plastic) {
+        flag = kJ2Elastic;
+        const double dgamma = hist(h, e, ip, kHInternal + kDGamma), mbb = hist(h, e, ip, kHInternal + kMuBarBar);
+        const double k = 2.0 * mbb * dgamma / mu;
+        hist(h, e, ip, kHInternal + kAlpha) += TB2_SQRT23 * dgamma;
+        double n[6];
+        hist_load6(h, e, ip, kHUnitNorm, n);
+#pragma unroll
+        for (int I = 0; I < 6; I++) bt[I] += -k * n[I];
+    }
+    hist_store6(h, e, ip, kHBBar, bt);
+    hist_store6(h, e, ip, kHBetaBar, bbt);
+}
+__global__ void k_j2_reset_step(int64_t ne, J2Hist h)
+{
+    // J2SimoC0HardeningT::Reset (:387-407)
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t e = t % h.stride;
+    const int ip = (int)(t / h.stride);
+    if (ip >= 8 || e >= ne || !h.alloc[e]) return;
+    h.flag[(int64_t)ip * h.stride + e] = kJ2Elastic;
+    hist(h, e, ip, kHInternal + kDGamma) = 0.0;
+}
+
+typedef void (*force_kernel_t)(const ElemArgs);
+static force_kernel_t pick_force_kernel(int form, int mat)
+{
+    switch (form * 4 + mat) {
+    case kSmallStrain * 4 + kSSKStV: return k_internal_force<kSmallStrain, kSSKStV>;
+    case kTotalLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV>;
+    case kTotalLagrangian * 4 + kSimoIso: return k_internal_force<kTotalLagrangian, kSimoIso>;
+    case kTotalLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo>;
+    // UpdatedLagrangianT shares the finite-strain body (see file header)
+    case kUpdatedLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV>;
+    case kUpdatedLagrangian * 4 + kSimoIso: return k_internal_force<kTotalLagrangian, kSimoIso>;
+    case kUpdatedLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo>;
+    }
+    return nullptr;
+}
+
+J2Hist group_hist(tb2_group* g)
+{
+    J2Hist h;
+    h.data = g->hist.p;
+    h.flag = g->hist_flag.p;
+    h.alloc = g->hist_alloc.p;
+    h.stride = g->mesh->stride;
+    return h;
+}
+
+// element sweep only: fe scratch <- element forces (used by the fused explicit path too)
+int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration)
+{
+    tb2_mesh* m = g->mesh;
+    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind);
+    if (!k) {
+        set_error("formulation %d does not support material %d", g->form, g->mat.kind);
+        return TB2_ERR_ARG;
+    }
+    if (g->mat.kind == TB2_J2_SIMO && !d_ul) {
+        set_error("J2Simo3D needs the last converged displacement (u_last)");
+        return TB2_ERR_ARG;
+    }
+    ElemArgs p;
+    p.ne = m->ne;
+    p.stride = m->stride;
+    p.conn = m->conn.p;
+    p.X = m->X.p;
+    p.u = d_u;
+    p.ul = d_ul;
+    p.fe = m->fe.p;
+    p.mat = g->mc;
+    p.hist = group_hist(g);
+    p.iteration = iteration;
+    p.status = g->status.p;
+    const int T = 128;
+    {
+        ProfScope ps(m, kProfForce);
+        k<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(p);
+    }
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof)
+{
+    const int T = 256;
+    const unsigned nb = (unsigned)((m->nn + T - 1) / T);
+    ProfScope ps(m, kProfNodeUpdate);
+    if (per_dof) k_node_gather<true><<<nb, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, d_out);
+    else k_node_gather<false><<<nb, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, d_out);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+int ensure_stage(tb2_mesh* m, int which)
+{
+    DevBuf<double>& b = which == 0 ? m->stage_a : (which == 1 ? m->stage_b : m->stage_c);
+    if (!b.p) TB2_CUDA(b.alloc(3 * m->nn));
+    return TB2_OK;
+}
+
+} // namespace tb2
+
+using namespace tb2;
+
+extern "C" {
+
+int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_group** out)
+{
+    TB2_ARG(mesh && mat && out);
+    TB2_ARG(form >= 0 && form <= 2 && mat->kind >= 0 && mat->kind <= 3);
+    if ((form == TB2_SMALL_STRAIN) != (mat->kind == TB2_SSKSTV)) {
+        // SSSolidMatT materials go with SmallStrainT, FSSolidMatT materials with FiniteStrainT (MaterialListT checks)
+        set_error("material %d is not valid for formulation %d", mat->kind, form);
+        return TB2_ERR_ARG;
+    }
+    DeviceGuard dg(mesh->device);
+    tb2_group* g = new tb2_group;
+    g->mesh = mesh;
+    g->form = form;
+    g->mat = *mat;
+    g->mc.mu = mat->mu;
+    g->mc.lambda = mat->lambda;
+    g->mc.kappa = mat->kappa;
+    g->mc.hard_kind = mat->hard_kind;
+    for (int i = 0; i < 4; i++) g->mc.hard[i] = mat->hard[i];
+    cudaError_t e = g->status.alloc(2);
+    if (e == cudaSuccess && mat->kind == TB2_J2_SIMO) {
+        e = g->hist.alloc((size_t)kHNumDouble * 8 * mesh->stride);
+        if (e == cudaSuccess) e = g->hist_flag.alloc(8 * mesh->stride);
+        if (e == cudaSuccess) e = g->hist_alloc.alloc(mesh->stride);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->hist.p, 0, g->hist.n * sizeof(double), mesh->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->hist_flag.p, 0, g->hist_flag.n * sizeof(int), mesh->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->hist_alloc.p, 0, g->hist_alloc.n * sizeof(int), mesh->stream);
+    }
+    const unsigned long long init[2] = {0ull, ~0ull};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->status.p, init, sizeof init, cudaMemcpyHostToDevice, mesh->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mesh->stream);
+    if (e != cudaSuccess) {
+        delete g;
+        return cuda_fail(e, "group allocation", __FILE__, __LINE__);
+    }
+    *out = g;
+    return TB2_OK;
+}
+
+int tb2_group_destroy(tb2_group* g)
+{
+    if (!g) return TB2_OK;
+    DeviceGuard dg(g->mesh->device);
+    cudaStreamSynchronize(g->mesh->stream);
+    delete g;
+    return TB2_OK;
+}
+
+int tb2_form_internal_force(tb2_group* g, const double* d_u, const double* d_ul, int iteration, double* d_f)
+{
+    TB2_ARG(g && d_u && d_f);
+    DeviceGuard dg(g->mesh->device);
+    TB2_CHECK(launch_element_forces(g, d_u, d_ul, iteration));
+    return launch_node_gather(g->mesh, d_f, true);
+}
+
+int tb2_group_status(tb2_group* g, int64_t* bad_element)
+{
+    TB2_ARG(g);
+    DeviceGuard dg(g->mesh->device);
+    unsigned long long st[2];
+    TB2_CUDA(cudaMemcpyAsync(st, g->status.p, sizeof st, cudaMemcpyDeviceToHost, g->mesh->stream));
+    TB2_CUDA(cudaStreamSynchronize(g->mesh->stream));
+    if (bad_element) *bad_element = st[0] ? (int64_t)st[1] : -1;
+    if (st[0]) {
+        const unsigned long long init[2] = {0ull, ~0ull};
+        TB2_CUDA(cudaMemcpyAsync(g->status.p, init, sizeof init, cudaMemcpyHostToDevice, g->mesh->stream));
+        TB2_CUDA(cudaStreamSynchronize(g->mesh->stream));
+        set_error(st[0] == kErrBadJacobian ? "non-positive Jacobian determinant in element %lld" : "J2 local iteration failed in element %lld",
+                  (long long)st[1]);
+    }
+    return st[0] == kErrBadJacobian ? TB2_ERR_BAD_JACOBIAN : (st[0] == kErrJ2Local ? TB2_ERR_J2_LOCAL : TB2_OK);
+}
+
+int tb2_form_internal_force_host(tb2_group* g, const double* h_u, const double* h_ul, int iteration, double* h_f)
+{
+    TB2_ARG(g && h_u && h_f);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    TB2_CHECK(ensure_stage(m, 0));
+    TB2_CHECK(ensure_stage(m, 1));
+    TB2_CUDA(cudaMemcpyAsync(m->stage_a.p, h_u, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_ul) {
+        TB2_CHECK(ensure_stage(m, 2));
+        TB2_CUDA(cudaMemcpyAsync(m->stage_c.p, h_ul, bytes, cudaMemcpyHostToDevice, m->stream));
+    }
+    TB2_CHECK(tb2_form_internal_force(g, m->stage_a.p, h_ul ? m->stage_c.p : nullptr, iteration, m->stage_b.p));
+    TB2_CUDA(cudaMemcpyAsync(h_f, m->stage_b.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    return tb2_group_status(g, nullptr);
+}
+
+int tb2_form_lumped_mass(tb2_group* g, double* d_mass)
+{
+    TB2_ARG(g && d_mass);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    const int T = 128;
+    ProfScope ps(m, kProfOther);
+    k_lumped_mass<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(m->ne, m->stride, m->conn.p, m->X.p, g->mat.density, m->fe.p,
+                                                                       g->status.p);
+    TB2_CUDA(cudaGetLastError());
+    return launch_node_gather(m, d_mass, false);
+}
+
+int tb2_form_lumped_mass_host(tb2_group* g, double* h_mass)
+{
+    TB2_ARG(g && h_mass);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CHECK(ensure_stage(m, 1));
+    TB2_CHECK(tb2_form_lumped_mass(g, m->stage_b.p));
+    TB2_CUDA(cudaMemcpyAsync(h_mass, m->stage_b.p, 3 * m->nn * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    return tb2_group_status(g, nullptr);
+}
+
+int tb2_group_close_step(tb2_group* g)
+{
+    TB2_ARG(g);
+    if (g->mat.kind != TB2_J2_SIMO) return TB2_OK;
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    const int T = 256;
+    k_j2_close_step<<<(unsigned)((8 * m->stride + T - 1) / T), T, 0, m->stream>>>(m->ne, group_hist(g), g->mat.mu);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+int tb2_group_reset_step(tb2_group* g)
+{
+    TB2_ARG(g);
+    if (g->mat.kind != TB2_J2_SIMO) return TB2_OK;
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    const int T = 256;
+    k_j2_reset_step<<<(unsigned)((8 * m->stride + T - 1) / T), T, 0, m->stream>>>(m->ne, group_hist(g));
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+// layout conversion between the device SoA history and the reference's per-element block
+// [b_bar 8x6 | unit_norm 8x6 | beta_bar 8x6 | b_bar_trial 8x6 | beta_bar_trial 8x6 | internal 8x8] (J2SimoC0HardeningT.cpp:429-452)
+int tb2_group_get_history(tb2_group* g, double* h_data, int32_t* h_flags, int32_t* h_alloc)
+{
+    TB2_ARG(g && g->mat.kind == TB2_J2_SIMO);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    const int64_t S = m->stride, ne = m->ne;
+    if (h_data) {
+        std::vector<double> raw((size_t)kHNumDouble * 8 * S);
+        TB2_CUDA(cudaMemcpy(raw.data(), g->hist.p, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t e = 0; e < ne; e++) {
+            double* out = h_data + e * (5 * 48 + 64);
+            for (int blk = 0; blk < 5; blk++)
+                for (int ip = 0; ip < 8; ip++)
+                    for (int I = 0; I < 6; I++) out[blk * 48 + ip * 6 + I] = raw[((size_t)(blk * 6 + I) * 8 + ip) * S + e];
+            for (int ip = 0; ip < 8; ip++)
+                for (int k = 0; k < 8; k++) out[240 + ip * 8 + k] = raw[((size_t)(kHInternal + k) * 8 + ip) * S + e];
+        }
+    }
+    if (h_flags) {
+        std::vector<int> raw((size_t)8 * S);
+        TB2_CUDA(cudaMemcpy(raw.data(), g->hist_flag.p, raw.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int64_t e = 0; e < ne; e++)
+            for (int ip = 0; ip < 8; ip++) h_flags[e * 8 + ip] = raw[(size_t)ip * S + e];
+    }
+    if (h_alloc) TB2_CUDA(cudaMemcpy(h_alloc, g->hist_alloc.p, ne * sizeof(int), cudaMemcpyDeviceToHost));
+    return TB2_OK;
+}
+int tb2_group_set_history(tb2_group* g, const double* h_data, const int32_t* h_flags, const int32_t* h_alloc)
+{
+    TB2_ARG(g && g->mat.kind == TB2_J2_SIMO && h_data && h_flags && h_alloc);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    const int64_t S = m->stride, ne = m->ne;
+    std::vector<double> raw((size_t)kHNumDouble * 8 * S, 0.0);
+    std::vector<int> rawf((size_t)8 * S, 0);
+    for (int64_t e = 0; e < ne; e++) {
+        const double* in = h_data + e * (5 * 48 + 64);
+        for (int blk = 0; blk < 5; blk++)
+            for (int ip = 0; ip < 8; ip++)
+                for (int I = 0; I < 6; I++) raw[((size_t)(blk * 6 + I) * 8 + ip) * S + e] = in[blk * 48 + ip * 6 + I];
+        for (int ip = 0; ip < 8; ip++) {
+            for (int k = 0; k < 8; k++) raw[((size_t)(kHInternal + k) * 8 + ip) * S + e] = in[240 + ip * 8 + k];
+            rawf[(size_t)ip * S + e] = h_flags[e * 8 + ip];
+        }
+    }
+    TB2_CUDA(cudaMemcpy(g->hist.p, raw.data(), raw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TB2_CUDA(cudaMemcpy(g->hist_flag.p, rawf.data(), rawf.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TB2_CUDA(cudaMemcpy(g->hist_alloc.p, h_alloc, ne * sizeof(int), cudaMemcpyHostToDevice));
+    return TB2_OK;
+}
+
+} // extern "C"

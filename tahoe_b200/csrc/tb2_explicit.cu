@@ -1,0 +1,294 @@
+// tb2_explicit.cu -- K5: explicit central-difference update on device-resident fields.
+//
+// Reference order of one step:
+//   FieldT::InitStep -> nExplicitCD::Predictor (nExplicitCD.cpp:72-96): d += dt v + dt^2/2 a ; v += dt/2 a ; a = 0,
+//                       then ConsistentKBC on prescribed dofs (nExplicitCD.cpp:20-69)
+//   LinearSolver::Solve (LinearSolver.cpp:37-101): R = fext - fint(d) ; update = M^-1 R (DiagonalMatrixT.cpp:267-323)
+//   FieldT::AssembleUpdate (FieldT.cpp:531-556: prescribed dofs get 0) ; nExplicitCD::Corrector (:98-139): v += dt/2 upd ; a += upd
+// On the device this is two launches per step: the element sweep (K1) and one node kernel that gathers the element
+// forces, forms R, applies M^-1, the corrector and -- when another step follows -- the next step's predictor, so d, v, a
+// are read and written once per step (192 B/node/step).
+#include "tb2_internal.h"
+
+namespace tb2 {
+
+int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration);
+int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
+bool comm_active(tb2_mesh* m);
+
+// predictor + ConsistentKBC, one thread per dof
+__global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, double* __restrict__ d, double* __restrict__ v,
+                                                     double* __restrict__ a, const unsigned char* __restrict__ code,
+                                                     const double* __restrict__ bcval, double value_scale)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ndof) return;
+    const unsigned char c = code[i];
+    double di = d[i], vi = v[i];
+    const double ai = a[i];
+    di += dt * vi + 0.5 * dt * dt * ai;
+    vi += 0.5 * dt * ai;
+    if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
+    else if (c == TB2_BC_DSP) di = value_scale * bcval[i];
+    d[i] = di;
+    v[i] = vi;
+    a[i] = 0.0;
+}
+
+// node kernel: gather fint, R = s*fext - fint, upd = minv*R on free dofs, corrector; optionally the next predictor.
+// a_in is the acceleration left by the predictor (0 on every dof), kept as an input for generality (a += upd).
+// GATHER = false: fint already holds the (interface-summed) internal force (multi-GPU path)
+template <bool GATHER, bool NEXT_PREDICTOR>
+__global__ void __launch_bounds__(256) k_cd_node_update(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                       const double* __restrict__ fe, int64_t stride, double dt, double fext_scale,
+                                                       double next_value_scale, const double* __restrict__ fext,
+                                                       const double* __restrict__ minv, const unsigned char* __restrict__ code,
+                                                       const double* __restrict__ bcval, double* __restrict__ d,
+                                                       double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nn) return;
+    double f[3] = {0.0, 0.0, 0.0};
+    if (GATHER) {
+        const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
+        for (int k = k0; k < k1; k++) {
+            const int ent = __ldg(inc + k);
+            const int64_t e = ent >> 3;
+            const int a3 = 3 * (ent & 7);
+            f[0] += __ldg(fe + (int64_t)(a3)*stride + e);
+            f[1] += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
+            f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
+        }
+    } else {
+        f[0] = fint[3 * n];
+        f[1] = fint[3 * n + 1];
+        f[2] = fint[3 * n + 2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int64_t q = 3 * n + i;
+        const unsigned char c = code[q];
+        const double R = fext_scale * fext[q] - f[i];
+        const double upd = c ? 0.0 : R * minv[q];
+        double vi = v[q] + 0.5 * dt * upd;
+        double ai = a[q] + upd;
+        if (GATHER) fint[q] = f[i];
+        if (NEXT_PREDICTOR) {
+            double di = d[q] + dt * vi + 0.5 * dt * dt * ai;
+            vi += 0.5 * dt * ai;
+            ai = 0.0;
+            if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
+            else if (c == TB2_BC_DSP) di = next_value_scale * bcval[q];
+            d[q] = di;
+        }
+        v[q] = vi;
+        a[q] = ai;
+    }
+}
+
+// DiagonalMatrixT::Factorize (DiagonalMatrixT.cpp:267-310): reciprocal, |m| < 1e-12 left as is
+__global__ void k_invert_diagonal(int64_t n, const double* __restrict__ m, double* __restrict__ minv)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = m[i];
+    minv[i] = fabs(x) > 1.0e-12 ? 1.0 / x : x;
+}
+
+// FEManagerT::InitialCondition: a = minv (fext - fint) on free dofs, 0 elsewhere
+__global__ void k_initial_acceleration(int64_t n, const double* __restrict__ fext, const double* __restrict__ fint,
+                                       const double* __restrict__ minv, const unsigned char* __restrict__ code, double* __restrict__ a)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i] = code[i] ? 0.0 : (fext[i] - fint[i]) * minv[i];
+}
+
+} // namespace tb2
+
+using namespace tb2;
+
+static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
+{
+    tb2_group* g = ex->group;
+    tb2_mesh* m = g->mesh;
+    const int64_t ndof = 3 * m->nn;
+    const int T = 256;
+    const unsigned nbn = (unsigned)((m->nn + T - 1) / T), nbd = (unsigned)((ndof + T - 1) / T);
+    if (nsteps <= 0) return TB2_OK;
+    {
+        ProfScope ps(m, kProfPredictor);
+        k_cd_predictor<<<nbd, T, 0, m->stream>>>(ndof, dt, ex->d.p, ex->v.p, ex->a.p, ex->bccode.p, ex->bcval.p, vs ? vs[0] : 1.0);
+    }
+    const bool multi = comm_active(m);
+    for (int s = 0; s < nsteps; s++) {
+        TB2_CHECK(launch_element_forces(g, ex->d.p, nullptr, 0));
+        const double fsc = fs ? fs[s] : 1.0;
+        if (multi) {
+            // partial nodal forces -> sum over the ranks sharing interface nodes -> update from the summed force
+            TB2_CHECK(launch_node_gather(m, ex->fint.p, true));
+            TB2_CHECK(tb2_comm_sum_interface(m, ex->fint.p));
+            ProfScope ps(m, kProfNodeUpdate);
+            if (s + 1 < nsteps)
+                k_cd_node_update<false, true><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                                                                       vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
+                                                                       ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
+            else
+                k_cd_node_update<false, false><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                                                                        ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
+                                                                        ex->v.p, ex->a.p, ex->fint.p);
+        } else if (s + 1 < nsteps) {
+            ProfScope ps(m, kProfNodeUpdate);
+            k_cd_node_update<true, true><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                                                            vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p,
+                                                            ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
+        } else {
+            ProfScope ps(m, kProfNodeUpdate);
+            k_cd_node_update<true, false><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                                                             ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p,
+                                                             ex->a.p, ex->fint.p);
+        }
+    }
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+extern "C" {
+
+int tb2_explicit_create(tb2_group* g, tb2_explicit** out)
+{
+    TB2_ARG(g && out);
+    if (g->mat.kind == TB2_J2_SIMO) {
+        set_error("explicit central difference with J2Simo3D is not supported (needs per-step history commit)");
+        return TB2_ERR_ARG;
+    }
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    tb2_explicit* ex = new tb2_explicit;
+    ex->group = g;
+    const size_t n = 3 * m->nn;
+    cudaError_t e = cudaSuccess;
+    DevBuf<double>* bufs[] = {&ex->d, &ex->v, &ex->a, &ex->mass, &ex->minv, &ex->fext, &ex->fint, &ex->bcval};
+    for (auto* b : bufs) {
+        if (e == cudaSuccess) e = b->alloc(n);
+        if (e == cudaSuccess) e = cudaMemsetAsync(b->p, 0, n * sizeof(double), m->stream);
+    }
+    if (e == cudaSuccess) e = ex->bccode.alloc(n);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ex->bccode.p, 0, n, m->stream);
+    if (e != cudaSuccess) {
+        delete ex;
+        return cuda_fail(e, "explicit state allocation", __FILE__, __LINE__);
+    }
+    int s = tb2_form_lumped_mass(g, ex->mass.p);
+    if (s == TB2_OK) s = tb2_comm_sum_interface(m, ex->mass.p); // interface-node mass is summed once over the sharers
+    if (s == TB2_OK) {
+        k_invert_diagonal<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>((int64_t)n, ex->mass.p, ex->minv.p);
+        s = tb2_group_status(g, nullptr);
+    }
+    if (s != TB2_OK) {
+        delete ex;
+        return s;
+    }
+    *out = ex;
+    return TB2_OK;
+}
+
+int tb2_explicit_destroy(tb2_explicit* ex)
+{
+    if (!ex) return TB2_OK;
+    DeviceGuard dg(ex->group->mesh->device);
+    cudaStreamSynchronize(ex->group->mesh->stream);
+    delete ex;
+    return TB2_OK;
+}
+
+int tb2_explicit_set_state(tb2_explicit* ex, const double* h_d, const double* h_v, const double* h_a)
+{
+    TB2_ARG(ex);
+    tb2_mesh* m = ex->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    if (h_d) TB2_CUDA(cudaMemcpyAsync(ex->d.p, h_d, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_v) TB2_CUDA(cudaMemcpyAsync(ex->v.p, h_v, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_a) TB2_CUDA(cudaMemcpyAsync(ex->a.p, h_a, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
+int tb2_explicit_get_state(tb2_explicit* ex, double* h_d, double* h_v, double* h_a)
+{
+    TB2_ARG(ex);
+    tb2_mesh* m = ex->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    if (h_d) TB2_CUDA(cudaMemcpyAsync(h_d, ex->d.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    if (h_v) TB2_CUDA(cudaMemcpyAsync(h_v, ex->v.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    if (h_a) TB2_CUDA(cudaMemcpyAsync(h_a, ex->a.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
+int tb2_explicit_set_bc(tb2_explicit* ex, const uint8_t* h_code, const double* h_value, const double* h_fext)
+{
+    TB2_ARG(ex);
+    tb2_mesh* m = ex->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t n = 3 * m->nn;
+    if (h_code) TB2_CUDA(cudaMemcpyAsync(ex->bccode.p, h_code, n, cudaMemcpyHostToDevice, m->stream));
+    if (h_value) TB2_CUDA(cudaMemcpyAsync(ex->bcval.p, h_value, n * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    if (h_fext) TB2_CUDA(cudaMemcpyAsync(ex->fext.p, h_fext, n * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
+
+int tb2_explicit_initial_condition(tb2_explicit* ex)
+{
+    TB2_ARG(ex);
+    tb2_group* g = ex->group;
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CHECK(tb2_form_internal_force(g, ex->d.p, nullptr, 0, ex->fint.p));
+    TB2_CHECK(tb2_comm_sum_interface(m, ex->fint.p));
+    const int64_t n = 3 * m->nn;
+    k_initial_acceleration<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(n, ex->fext.p, ex->fint.p, ex->minv.p, ex->bccode.p, ex->a.p);
+    TB2_CUDA(cudaGetLastError());
+    return tb2_group_status(g, nullptr);
+}
+
+int tb2_explicit_run(tb2_explicit* ex, double dt, int nsteps, const double* h_fext_scale, const double* h_value_scale)
+{
+    TB2_ARG(ex && nsteps >= 0);
+    DeviceGuard dg(ex->group->mesh->device);
+    TB2_CHECK(explicit_steps(ex, dt, nsteps, h_fext_scale, h_value_scale));
+    return tb2_group_status(ex->group, nullptr);
+}
+
+int tb2_explicit_step_host(tb2_explicit* ex, double dt, double* h_d, double* h_v, double* h_a)
+{
+    TB2_ARG(ex && h_d && h_v && h_a);
+    tb2_mesh* m = ex->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    TB2_CUDA(cudaMemcpyAsync(ex->d.p, h_d, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(ex->v.p, h_v, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(ex->a.p, h_a, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CHECK(explicit_steps(ex, dt, 1, nullptr, nullptr));
+    TB2_CUDA(cudaMemcpyAsync(h_d, ex->d.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(h_v, ex->v.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(h_a, ex->a.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    return tb2_group_status(ex->group, nullptr);
+}
+
+double* tb2_explicit_device_array(tb2_explicit* ex, int which)
+{
+    if (!ex) return nullptr;
+    switch (which) {
+    case 0: return ex->d.p;
+    case 1: return ex->v.p;
+    case 2: return ex->a.p;
+    case 3: return ex->mass.p;
+    case 4: return ex->fext.p;
+    case 5: return ex->fint.p;
+    }
+    return nullptr;
+}
+
+} // extern "C"

@@ -1,0 +1,170 @@
+// tb2_internal.h -- host-side handle structs shared by the translation units of libtahoe_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/tahoe_b200.h"
+#include "tb2_materials.cuh"
+
+namespace tb2 {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TB2_CUDA(call)                                                    \
+    do {                                                                  \
+        cudaError_t _e = (call);                                          \
+        if (_e != cudaSuccess) return tb2::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+#define TB2_CHECK(call)            \
+    do {                           \
+        int _s = (call);           \
+        if (_s != TB2_OK) return _s; \
+    } while (0)
+#define TB2_ARG(cond)                                         \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            tb2::set_error("bad argument: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+            return TB2_ERR_ARG;                               \
+        }                                                     \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct Comm; // tb2_comm.cu
+
+// per-kernel CUDA-event timing on the mesh stream (bench.py's roofline numbers are measured with these, live, inside the
+// timed region) and a count of our own kernel launches
+enum { kProfForce = 0, kProfNodeUpdate = 1, kProfPredictor = 2, kProfSpmv = 3, kProfPcgVec = 4, kProfStiffness = 5, kProfComm = 6,
+       kProfOther = 7, kProfNumCat = 8 };
+struct ProfRec {
+    int cat;
+    cudaEvent_t a, b;
+};
+
+} // namespace tb2
+
+struct tb2_mesh {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t nn = 0, ne = 0, stride = 0; // stride = ne rounded up to 32 (SoA pitch)
+    tb2::DevBuf<int> conn;              // [8][stride] SoA connectivity
+    tb2::DevBuf<double> X;              // [nn][3]
+    tb2::DevBuf<int> inc_ptr;           // [nn+1] node -> incidence range
+    tb2::DevBuf<int> inc;               // [8*ne] entries e*8+a, ascending in e within a node
+    tb2::DevBuf<double> fe;             // [24][stride] element force scratch
+    tb2::DevBuf<double> stage_a, stage_b, stage_c; // [nn][3] staging for the *_host entry points
+    // colouring (built lazily)
+    int ncolours = 0;
+    std::vector<int32_t> colour_host;   // [ne]
+    tb2::DevBuf<int> colour_elems;      // elements sorted by colour
+    std::vector<int64_t> colour_start;  // [ncolours+1]
+    tb2::Comm* comm = nullptr;
+    bool prof_on = false;
+    std::vector<tb2::ProfRec> prof;
+    uint64_t launches = 0;
+};
+
+namespace tb2 {
+// brackets one or more launches of category cat; counts n kernel launches
+struct ProfScope {
+    tb2_mesh* m;
+    int idx = -1;
+    ProfScope(tb2_mesh* mesh, int cat, int n = 1) : m(mesh)
+    {
+        m->launches += (uint64_t)n;
+        if (!m->prof_on) return;
+        ProfRec r;
+        r.cat = cat;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, m->stream);
+        m->prof.push_back(r);
+        idx = (int)m->prof.size() - 1;
+    }
+    ~ProfScope()
+    {
+        if (idx >= 0) cudaEventRecord(m->prof[idx].b, m->stream);
+    }
+};
+} // namespace tb2
+
+struct tb2_group {
+    tb2_mesh* mesh = nullptr;
+    int form = 0;
+    tb2_material mat{};
+    tb2::MatConst mc{};
+    // J2 history
+    tb2::DevBuf<double> hist;      // [38][8][stride]
+    tb2::DevBuf<double> hist_save; // committed copy for ResetStep is not needed: trial fields are recomputed
+    tb2::DevBuf<int> hist_flag;    // [8][stride]
+    tb2::DevBuf<int> hist_alloc;   // [stride]
+    tb2::DevBuf<unsigned long long> status; // [0] error code, [1] first bad element
+};
+
+struct tb2_equations {
+    tb2_mesh* mesh = nullptr;
+    int64_t neq = 0;
+    tb2::DevBuf<int> eqnos;   // [nn][3], 1-based, -1 prescribed
+    tb2::DevBuf<int> eq_node; // [neq] -> nodal dof index 3*n+i
+};
+
+struct tb2_matrix {
+    tb2_equations* eqs = nullptr;
+    int64_t neq = 0, nnz = 0;
+    tb2::DevBuf<int> adj_ptr;     // [nn+1] node adjacency (sorted neighbour nodes incl. self)
+    tb2::DevBuf<int> adj;         // neighbour node ids
+    tb2::DevBuf<int> adj_coloff;  // per adjacency entry: column offset of the neighbour's first active dof inside the node's rows
+    tb2::DevBuf<int> elem_adjpos; // [64][stride]: position of node b in node a's adjacency list
+    tb2::DevBuf<long long> rowptr; // [neq+1]
+    tb2::DevBuf<int> colind;      // [nnz]
+    tb2::DevBuf<double> val;      // [nnz]
+    tb2::DevBuf<double> dinv, r, z, p, q; // PCG work vectors [neq]
+    tb2::DevBuf<double> scal;     // reduction scalars
+    tb2::DevBuf<double> partial;  // per-block partial sums
+};
+
+struct tb2_explicit {
+    tb2_group* group = nullptr;
+    tb2::DevBuf<double> d, v, a, mass, minv, fext, fint, bcval;
+    tb2::DevBuf<unsigned char> bccode;
+};

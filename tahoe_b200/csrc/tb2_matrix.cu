@@ -1,0 +1,653 @@
+// tb2_matrix.cu -- K9 (equation numbers, sparsity, element->slot map) and K6-K8 (CSR SpMV, Jacobi-PCG).
+//
+// Equation numbering follows NodeManagerT::SetEquationNumbers / FieldT::InitEquations (NodeManagerT.cpp:712-767,
+// FieldT.cpp:635-659): node-major, dof-minor, 1-based, prescribed dofs = -1.  Because the numbering is monotone in the
+// node id, the sorted column list of a row is the concatenation, over the row node's neighbour nodes in ascending node
+// order, of the neighbours' active equations -- which is what GraphT::MakeGraph + MSRBuilderT's per-row sort produce
+// (GraphT.cpp:376-488, MSRBuilderT.cpp:134-181).  The structure is therefore built from a node adjacency (<= 27 entries
+// per node on a structured mesh) instead of from 24x24 equation pairs per element.
+#include <cub/cub.cuh>
+
+#include "tb2_internal.h"
+
+namespace tb2 {
+
+static const int kMaxAdj = 160; // candidate buffer per node: up to 20 incident hexes
+
+// ---- equations ----------------------------------------------------------------------------------------------------
+__global__ void k_active_flags(int64_t ndof, const unsigned char* __restrict__ bc, int* __restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < ndof) flag[i] = bc[i] ? 0 : 1;
+}
+__global__ void k_assign_eqnos(int64_t ndof, const int* __restrict__ flag, const int* __restrict__ incl, int* __restrict__ eqnos,
+                               int* __restrict__ eq_node)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ndof) return;
+    if (flag[i]) {
+        eqnos[i] = incl[i];
+        eq_node[incl[i] - 1] = (int)i;
+    } else
+        eqnos[i] = -1; // FieldT::kPrescribed
+}
+
+// ---- node adjacency -------------------------------------------------------------------------------------------------
+// sorted unique neighbour nodes of node n (incl. n): union of the nodes of its incident elements
+__device__ int collect_neighbours(int64_t n, const int* __restrict__ inc_ptr, const int* __restrict__ inc, const int* __restrict__ conn,
+                                  int64_t stride, int* buf, int& overflow)
+{
+    int cnt = 0;
+    for (int k = inc_ptr[n]; k < inc_ptr[n + 1]; k++) {
+        const int64_t e = inc[k] >> 3;
+        for (int a = 0; a < 8; a++) {
+            const int v = conn[a * stride + e];
+            // sorted insert without duplicates
+            int lo = 0, hi = cnt;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (buf[mid] < v) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < cnt && buf[lo] == v) continue;
+            if (cnt >= kMaxAdj) { overflow = 1; continue; }
+            for (int q = cnt; q > lo; q--) buf[q] = buf[q - 1];
+            buf[lo] = v;
+            cnt++;
+        }
+    }
+    return cnt;
+}
+__global__ void __launch_bounds__(128) k_adj_count(int64_t nn, const int* inc_ptr, const int* inc, const int* conn, int64_t stride,
+                                                  int* __restrict__ count, int* overflow)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nn) return;
+    int buf[kMaxAdj], ov = 0;
+    count[n] = collect_neighbours(n, inc_ptr, inc, conn, stride, buf, ov);
+    if (ov) *overflow = 1;
+}
+// fill adjacency + per-entry column offset; rowlen[n] = number of columns in each row of node n
+__global__ void __launch_bounds__(128) k_adj_fill(int64_t nn, const int* inc_ptr, const int* inc, const int* conn, int64_t stride,
+                                                 const int* __restrict__ adj_ptr, const int* __restrict__ eqnos, int* __restrict__ adj,
+                                                 int* __restrict__ coloff, int* __restrict__ rowlen, long long* __restrict__ node_nnz)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nn) return;
+    int buf[kMaxAdj], ov = 0;
+    const int cnt = collect_neighbours(n, inc_ptr, inc, conn, stride, buf, ov);
+    const int base = adj_ptr[n];
+    int off = 0;
+    for (int k = 0; k < cnt; k++) {
+        const int64_t m = buf[k];
+        adj[base + k] = (int)m;
+        coloff[base + k] = off;
+        off += (eqnos[3 * m] > 0) + (eqnos[3 * m + 1] > 0) + (eqnos[3 * m + 2] > 0);
+    }
+    rowlen[n] = off;
+    const int nact = (eqnos[3 * n] > 0) + (eqnos[3 * n + 1] > 0) + (eqnos[3 * n + 2] > 0);
+    node_nnz[n] = (long long)nact * off;
+}
+__global__ void k_rowptr(int64_t nn, const int* __restrict__ eqnos, const int* __restrict__ rowlen,
+                         const long long* __restrict__ node_start, long long* __restrict__ rowptr, int64_t neq, long long nnz)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n == 0) rowptr[neq] = nnz;
+    if (n >= nn) return;
+    int r = 0;
+    for (int i = 0; i < 3; i++) {
+        const int eq = eqnos[3 * n + i];
+        if (eq > 0) {
+            rowptr[eq - 1] = node_start[n] + (long long)r * rowlen[n];
+            r++;
+        }
+    }
+}
+// one thread per adjacency entry: writes the neighbour's active equations into each active row of the node
+__global__ void k_colind(int64_t nn, int64_t nadj, const int* __restrict__ adj_ptr, const int* __restrict__ adj,
+                         const int* __restrict__ coloff, const int* __restrict__ eqnos, const long long* __restrict__ rowptr,
+                         int* __restrict__ colind)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nadj) return;
+    // owning node by binary search in adj_ptr
+    int64_t lo = 0, hi = nn;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (adj_ptr[mid + 1] <= k) lo = mid + 1;
+        else hi = mid;
+    }
+    const int64_t n = lo, m = adj[k];
+    const int off = coloff[k];
+    for (int i = 0; i < 3; i++) {
+        const int eq = eqnos[3 * n + i];
+        if (eq <= 0) continue;
+        long long p = rowptr[eq - 1] + off;
+        for (int j = 0; j < 3; j++) {
+            const int c = eqnos[3 * m + j];
+            if (c > 0) colind[p++] = c - 1;
+        }
+    }
+}
+// elem_adjpos[(a*8+b)][e] = index into adj[] of (conn[a] -> conn[b])
+__global__ void k_elem_adjpos(int64_t ne, int64_t stride, const int* __restrict__ conn, const int* __restrict__ adj_ptr,
+                              const int* __restrict__ adj, int* __restrict__ pos)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t e = t % stride;
+    const int ab = (int)(t / stride);
+    if (ab >= 64 || e >= ne) return;
+    const int na = conn[(ab >> 3) * stride + e], nb = conn[(ab & 7) * stride + e];
+    int lo = adj_ptr[na], hi = adj_ptr[na + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (adj[mid] < nb) lo = mid + 1;
+        else hi = mid;
+    }
+    pos[(int64_t)ab * stride + e] = lo;
+}
+
+// ---- K6: y = A x, one warp per row (MSRMatrixT::Multx, MSRMatrixT.cpp:385-420) ---------------------------------------
+// optional fused dot: partial[block] = sum over the block's rows of x[row]*y[row] (p.Ap of CG)
+template <bool WITH_DOT>
+__global__ void __launch_bounds__(256) k_spmv(int64_t n, const long long* __restrict__ rowptr, const int* __restrict__ colind,
+                                              const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                              double* __restrict__ partial, const int* __restrict__ done)
+{
+    if (WITH_DOT && done && *done) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
+    double s = 0.0;
+    if (row < n) {
+        const long long k0 = rowptr[row], k1 = rowptr[row + 1];
+        for (long long k = k0 + lane; k < k1; k += 32) s += val[k] * __ldg(x + colind[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[row] = s;
+    }
+    if (WITH_DOT) {
+        __shared__ double sh[8];
+        if (lane == 0) sh[wib] = row < n ? s * x[row] : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+            partial[blockIdx.x] = t;
+        }
+    }
+}
+
+// deterministic two-stage reductions -------------------------------------------------------------------------------
+TB2_DEV double block_sum(double v, double* sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t; // valid in thread 0
+}
+
+// scalars: [0] rz, [1] pAp, [2] rz_new, [3] rr, [4] alpha, [5] beta, [6] r0norm, [7] rnorm
+enum { kRZ = 0, kPAP = 1, kRZNEW = 2, kRR = 3, kALPHA = 4, kBETA = 5, kR0 = 6, kRNORM = 7, kNumScal = 8 };
+// control ints: [0] done, [1] iterations, [2] breakdown
+struct PcgCtl {
+    int done, iters, breakdown, pad;
+};
+
+// sum nparts partials (optionally 2 interleaved streams) with one block
+__global__ void __launch_bounds__(1024) k_reduce_pap(int nparts, const double* __restrict__ partial, double* __restrict__ scal, PcgCtl* ctl)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) v += partial[i];
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) {
+        scal[kPAP] = v;
+        if (!(v > 0.0)) { ctl->breakdown = 1; ctl->done = 1; scal[kALPHA] = 0.0; }
+        else scal[kALPHA] = scal[kRZ] / v;
+    }
+}
+// x += alpha p ; r -= alpha q ; z = dinv r ; partial rz, rr
+__global__ void __launch_bounds__(256) k_pcg_update(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl,
+                                                   const double* __restrict__ p, const double* __restrict__ q,
+                                                   const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+                                                   double* __restrict__ z, double* __restrict__ partial)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    const double alpha = scal[kALPHA];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        z[i] = zi;
+        rz += ri * zi;
+        rr += ri * ri;
+    }
+    rz = block_sum(rz, sh);
+    rr = block_sum(rr, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = rz;
+        partial[2 * blockIdx.x + 1] = rr;
+    }
+}
+__global__ void __launch_bounds__(1024) k_reduce_rz(int nparts, const double* __restrict__ partial, double* __restrict__ scal, PcgCtl* ctl,
+                                                   double rtol, double atol, int max_iter)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) {
+        const double rnorm = sqrt(b);
+        scal[kBETA] = a / scal[kRZ];
+        scal[kRZ] = a;
+        scal[kRNORM] = rnorm;
+        ctl->iters += 1;
+        if (!(rnorm > atol) || !(rnorm > rtol * scal[kR0]) || ctl->iters >= max_iter) ctl->done = 1;
+    }
+}
+// p = z + beta p
+__global__ void __launch_bounds__(256) k_pcg_direction(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl,
+                                                      const double* __restrict__ z, double* __restrict__ p)
+{
+    if (ctl->done) return;
+    const double beta = scal[kBETA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
+}
+// setup: dinv from diagonal (DiagonalMatrixT::Factorize semantics); r = b - q ; z = dinv r ; p = z ; partial rz, rr
+__global__ void k_extract_dinv(int64_t n, const long long* __restrict__ rowptr, const int* __restrict__ colind, const double* __restrict__ val,
+                               double* __restrict__ out, int invert)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long lo = rowptr[i], hi = rowptr[i + 1];
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (colind[mid] < i) lo = mid + 1;
+        else hi = mid;
+    }
+    const double d = (lo < rowptr[i + 1] && colind[lo] == i) ? val[lo] : 0.0;
+    out[i] = invert ? (fabs(d) > 1.0e-12 ? 1.0 / d : d) : d;
+}
+__global__ void __launch_bounds__(256) k_pcg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
+                                                 const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ z,
+                                                 double* __restrict__ p, double* __restrict__ partial)
+{
+    __shared__ double sh[32];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        z[i] = zi;
+        p[i] = zi;
+        rz += ri * zi;
+        rr += ri * ri;
+    }
+    rz = block_sum(rz, sh);
+    rr = block_sum(rr, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = rz;
+        partial[2 * blockIdx.x + 1] = rr;
+    }
+}
+__global__ void __launch_bounds__(1024) k_reduce_init(int nparts, const double* __restrict__ partial, double* __restrict__ scal, PcgCtl* ctl,
+                                                     double rtol, double atol, int max_iter)
+{
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) {
+        const double rnorm = sqrt(b);
+        scal[kRZ] = a;
+        scal[kR0] = rnorm;
+        scal[kRNORM] = rnorm;
+        ctl->iters = 0;
+        ctl->breakdown = 0;
+        ctl->done = (!(rnorm > atol) || !(rnorm > rtol * rnorm) || max_iter <= 0) ? 1 : 0;
+    }
+}
+
+__global__ void k_eq_gather(int64_t neq, const int* __restrict__ eq_node, const double* __restrict__ nodal, double* __restrict__ v)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < neq) v[i] = nodal[eq_node[i]];
+}
+__global__ void k_eq_scatter_add(int64_t neq, const int* __restrict__ eq_node, double s, const double* __restrict__ v, double* __restrict__ nodal)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < neq) nodal[eq_node[i]] += s * v[i];
+}
+
+static const int kReduceBlocks = 148 * 8;
+
+} // namespace tb2
+
+using namespace tb2;
+
+extern "C" {
+
+int tb2_equations_create(tb2_mesh* m, const uint8_t* h_bc, tb2_equations** out)
+{
+    TB2_ARG(m && h_bc && out);
+    DeviceGuard dg(m->device);
+    const int64_t ndof = 3 * m->nn;
+    tb2_equations* q = new tb2_equations;
+    q->mesh = m;
+    DevBuf<unsigned char> bc, tmp;
+    DevBuf<int> flag, incl;
+    auto fail = [&](int s) { delete q; return s; };
+#define Q_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(cuda_fail(_e, #call, __FILE__, __LINE__)); } while (0)
+    Q_CUDA(bc.alloc(ndof));
+    Q_CUDA(flag.alloc(ndof));
+    Q_CUDA(incl.alloc(ndof));
+    Q_CUDA(q->eqnos.alloc(ndof));
+    Q_CUDA(cudaMemcpyAsync(bc.p, h_bc, ndof, cudaMemcpyHostToDevice, m->stream));
+    const int T = 256;
+    const unsigned nb = (unsigned)((ndof + T - 1) / T);
+    k_active_flags<<<nb, T, 0, m->stream>>>(ndof, bc.p, flag.p);
+    size_t tb = 0;
+    Q_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, flag.p, incl.p, (int)ndof, m->stream));
+    Q_CUDA(tmp.alloc(tb));
+    Q_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, flag.p, incl.p, (int)ndof, m->stream));
+    int neq = 0;
+    Q_CUDA(cudaMemcpyAsync(&neq, incl.p + ndof - 1, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    Q_CUDA(cudaStreamSynchronize(m->stream));
+    q->neq = neq;
+    Q_CUDA(q->eq_node.alloc(neq > 0 ? neq : 1));
+    k_assign_eqnos<<<nb, T, 0, m->stream>>>(ndof, flag.p, incl.p, q->eqnos.p, q->eq_node.p);
+    Q_CUDA(cudaGetLastError());
+    Q_CUDA(cudaStreamSynchronize(m->stream));
+#undef Q_CUDA
+    *out = q;
+    return TB2_OK;
+}
+int tb2_equations_destroy(tb2_equations* q)
+{
+    if (!q) return TB2_OK;
+    DeviceGuard dg(q->mesh->device);
+    cudaStreamSynchronize(q->mesh->stream);
+    delete q;
+    return TB2_OK;
+}
+int tb2_equations_count(const tb2_equations* q, int64_t* neq)
+{
+    TB2_ARG(q && neq);
+    *neq = q->neq;
+    return TB2_OK;
+}
+int tb2_equations_get(const tb2_equations* q, int32_t* h_eqnos)
+{
+    TB2_ARG(q && h_eqnos);
+    DeviceGuard dg(q->mesh->device);
+    TB2_CUDA(cudaMemcpy(h_eqnos, q->eqnos.p, 3 * q->mesh->nn * sizeof(int), cudaMemcpyDeviceToHost));
+    return TB2_OK;
+}
+const int32_t* tb2_equations_device(const tb2_equations* q) { return q ? q->eqnos.p : nullptr; }
+
+int tb2_equations_gather(const tb2_equations* q, const double* d_nodal, double* d_eqvec)
+{
+    TB2_ARG(q && d_nodal && d_eqvec);
+    DeviceGuard dg(q->mesh->device);
+    if (q->neq) k_eq_gather<<<(unsigned)((q->neq + 255) / 256), 256, 0, q->mesh->stream>>>(q->neq, q->eq_node.p, d_nodal, d_eqvec);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+int tb2_equations_scatter_add(const tb2_equations* q, double scale, const double* d_eqvec, double* d_nodal)
+{
+    TB2_ARG(q && d_nodal && d_eqvec);
+    DeviceGuard dg(q->mesh->device);
+    if (q->neq) k_eq_scatter_add<<<(unsigned)((q->neq + 255) / 256), 256, 0, q->mesh->stream>>>(q->neq, q->eq_node.p, scale, d_eqvec, d_nodal);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_matrix_create(tb2_equations* q, tb2_matrix** out)
+{
+    TB2_ARG(q && out && q->neq > 0);
+    tb2_mesh* m = q->mesh;
+    DeviceGuard dg(m->device);
+    tb2_matrix* A = new tb2_matrix;
+    A->eqs = q;
+    A->neq = q->neq;
+    const int64_t nn = m->nn, neq = q->neq;
+    auto fail = [&](int s) { delete A; return s; };
+#define A_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(cuda_fail(_e, #call, __FILE__, __LINE__)); } while (0)
+    DevBuf<int> count, rowlen, overflow;
+    DevBuf<long long> node_nnz, node_start;
+    DevBuf<unsigned char> tmp;
+    A_CUDA(count.alloc(nn + 1));
+    A_CUDA(rowlen.alloc(nn));
+    A_CUDA(overflow.alloc(1));
+    A_CUDA(node_nnz.alloc(nn + 1));
+    A_CUDA(node_start.alloc(nn + 1));
+    A_CUDA(A->adj_ptr.alloc(nn + 1));
+    A_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), m->stream));
+    A_CUDA(cudaMemsetAsync(count.p + nn, 0, sizeof(int), m->stream));
+    A_CUDA(cudaMemsetAsync(node_nnz.p + nn, 0, sizeof(long long), m->stream));
+    const int T = 128;
+    const unsigned nbn = (unsigned)((nn + T - 1) / T);
+    k_adj_count<<<nbn, T, 0, m->stream>>>(nn, m->inc_ptr.p, m->inc.p, m->conn.p, m->stride, count.p, overflow.p);
+    size_t tb = 0, tb2 = 0;
+    A_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, count.p, A->adj_ptr.p, (int)(nn + 1), m->stream));
+    A_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, node_nnz.p, node_start.p, (int)(nn + 1), m->stream));
+    A_CUDA(tmp.alloc(tb > tb2 ? tb : tb2));
+    A_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, count.p, A->adj_ptr.p, (int)(nn + 1), m->stream));
+    int nadj = 0, ov = 0;
+    A_CUDA(cudaMemcpyAsync(&nadj, A->adj_ptr.p + nn, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    A_CUDA(cudaMemcpyAsync(&ov, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    A_CUDA(cudaStreamSynchronize(m->stream));
+    if (ov) {
+        set_error("a node has more than %d distinct neighbours", kMaxAdj);
+        return fail(TB2_ERR_SIZE);
+    }
+    A_CUDA(A->adj.alloc(nadj));
+    A_CUDA(A->adj_coloff.alloc(nadj));
+    k_adj_fill<<<nbn, T, 0, m->stream>>>(nn, m->inc_ptr.p, m->inc.p, m->conn.p, m->stride, A->adj_ptr.p, q->eqnos.p, A->adj.p,
+                                         A->adj_coloff.p, rowlen.p, node_nnz.p);
+    A_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, node_nnz.p, node_start.p, (int)(nn + 1), m->stream));
+    long long nnz = 0;
+    A_CUDA(cudaMemcpyAsync(&nnz, node_start.p + nn, sizeof(long long), cudaMemcpyDeviceToHost, m->stream));
+    A_CUDA(cudaStreamSynchronize(m->stream));
+    A->nnz = nnz;
+    A_CUDA(A->rowptr.alloc(neq + 1));
+    A_CUDA(A->colind.alloc(nnz));
+    A_CUDA(A->val.alloc(nnz));
+    A_CUDA(cudaMemsetAsync(A->val.p, 0, nnz * sizeof(double), m->stream));
+    k_rowptr<<<nbn, T, 0, m->stream>>>(nn, q->eqnos.p, rowlen.p, node_start.p, A->rowptr.p, neq, nnz);
+    k_colind<<<(unsigned)((nadj + 255) / 256), 256, 0, m->stream>>>(nn, nadj, A->adj_ptr.p, A->adj.p, A->adj_coloff.p, q->eqnos.p,
+                                                                  A->rowptr.p, A->colind.p);
+    A_CUDA(A->elem_adjpos.alloc(64 * m->stride));
+    k_elem_adjpos<<<(unsigned)((64 * m->stride + 255) / 256), 256, 0, m->stream>>>(m->ne, m->stride, m->conn.p, A->adj_ptr.p, A->adj.p,
+                                                                                 A->elem_adjpos.p);
+    A_CUDA(A->dinv.alloc(neq));
+    A_CUDA(A->r.alloc(neq));
+    A_CUDA(A->z.alloc(neq));
+    A_CUDA(A->p.alloc(neq));
+    A_CUDA(A->q.alloc(neq));
+    A_CUDA(A->scal.alloc(kNumScal + 4)); // + PcgCtl
+    const int64_t spmv_blocks = (neq + 7) / 8;
+    A_CUDA(A->partial.alloc((spmv_blocks > 2 * kReduceBlocks ? spmv_blocks : 2 * kReduceBlocks) + 8));
+    A_CUDA(cudaGetLastError());
+    A_CUDA(cudaStreamSynchronize(m->stream));
+#undef A_CUDA
+    *out = A;
+    return TB2_OK;
+}
+int tb2_matrix_destroy(tb2_matrix* A)
+{
+    if (!A) return TB2_OK;
+    DeviceGuard dg(A->eqs->mesh->device);
+    cudaStreamSynchronize(A->eqs->mesh->stream);
+    delete A;
+    return TB2_OK;
+}
+int tb2_matrix_nnz(const tb2_matrix* A, int64_t* nnz)
+{
+    TB2_ARG(A && nnz);
+    *nnz = A->nnz;
+    return TB2_OK;
+}
+int tb2_matrix_get_csr(const tb2_matrix* A, int64_t* h_rowptr, int32_t* h_colind, double* h_val)
+{
+    TB2_ARG(A);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    if (h_rowptr) TB2_CUDA(cudaMemcpy(h_rowptr, A->rowptr.p, (A->neq + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (h_colind) TB2_CUDA(cudaMemcpy(h_colind, A->colind.p, A->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_val) TB2_CUDA(cudaMemcpy(h_val, A->val.p, A->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    return TB2_OK;
+}
+// MSR index array (MSRMatrixT.h:21-23, MSRBuilderT::SetMSRData): bindx[0..neq] row starts, then off-diagonal columns
+int tb2_matrix_get_msr(const tb2_matrix* A, int upper_only, int32_t* h_bindx, int64_t* length)
+{
+    TB2_ARG(A && length);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    const int64_t neq = A->neq;
+    std::vector<long long> rp(neq + 1);
+    std::vector<int> ci(A->nnz);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    TB2_CUDA(cudaMemcpy(rp.data(), A->rowptr.p, (neq + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
+    TB2_CUDA(cudaMemcpy(ci.data(), A->colind.p, A->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    // export only: a re-indexing of the device structure into the reference's container format
+    int64_t pos = neq + 1;
+    if (h_bindx) h_bindx[0] = (int32_t)pos;
+    for (int64_t r = 0; r < neq; r++) {
+        for (long long k = rp[r]; k < rp[r + 1]; k++)
+            if (ci[k] != r && (!upper_only || ci[k] > r)) {
+                if (h_bindx) h_bindx[pos] = ci[k];
+                pos++;
+            }
+        if (h_bindx) h_bindx[r + 1] = (int32_t)pos;
+    }
+    *length = pos;
+    return TB2_OK;
+}
+int tb2_matrix_clear(tb2_matrix* A)
+{
+    TB2_ARG(A);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaMemsetAsync(A->val.p, 0, A->nnz * sizeof(double), m->stream));
+    return TB2_OK;
+}
+
+int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y)
+{
+    TB2_ARG(A && d_x && d_y);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    ProfScope ps(m, kProfSpmv);
+    k_spmv<false><<<(unsigned)((A->neq + 7) / 8), 256, 0, m->stream>>>(A->neq, A->rowptr.p, A->colind.p, A->val.p, d_x, d_y, nullptr, nullptr);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y)
+{
+    TB2_ARG(A && h_x && h_y);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaMemcpyAsync(A->p.p, h_x, A->neq * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    TB2_CHECK(tb2_matrix_multx(A, A->p.p, A->q.p));
+    TB2_CUDA(cudaMemcpyAsync(h_y, A->q.p, A->neq * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
+int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag)
+{
+    TB2_ARG(A && d_diag);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    k_extract_dinv<<<(unsigned)((A->neq + 255) / 256), 256, 0, m->stream>>>(A->neq, A->rowptr.p, A->colind.p, A->val.p, d_diag, 0);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
+                   double* final_rnorm)
+{
+    TB2_ARG(A && d_b && d_x);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    const int64_t n = A->neq;
+    cudaStream_t st = m->stream;
+    double* scal = A->scal.p;
+    PcgCtl* ctl = (PcgCtl*)(A->scal.p + kNumScal);
+    const unsigned spmv_blocks = (unsigned)((n + 7) / 8);
+    int64_t vb = (n + 255) / 256;
+    const unsigned vec_blocks = (unsigned)(vb < kReduceBlocks ? vb : kReduceBlocks);
+    {
+        ProfScope ps(m, kProfPcgVec, 4);
+        k_extract_dinv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 1);
+        k_spmv<false><<<spmv_blocks, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
+        k_pcg_init<<<vec_blocks, 256, 0, st>>>(n, d_b, A->q.p, A->dinv.p, A->r.p, A->z.p, A->p.p, A->partial.p);
+        k_reduce_init<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, rtol, atol, max_iter);
+    }
+    TB2_CUDA(cudaGetLastError());
+    PcgCtl h{};
+    const int check_every = 16;
+    for (int it = 0; it < max_iter;) {
+        for (int k = 0; k < check_every && it < max_iter; k++, it++) {
+            {
+                ProfScope ps(m, kProfSpmv);
+                k_spmv<true><<<spmv_blocks, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, A->partial.p, &ctl->done);
+            }
+            ProfScope ps(m, kProfPcgVec, 4);
+            k_reduce_pap<<<1, 1024, 0, st>>>((int)spmv_blocks, A->partial.p, scal, ctl);
+            k_pcg_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->p.p, A->q.p, A->dinv.p, d_x, A->r.p, A->z.p, A->partial.p);
+            k_reduce_rz<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, rtol, atol, max_iter);
+            k_pcg_direction<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->z.p, A->p.p);
+        }
+        TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        TB2_CUDA(cudaStreamSynchronize(st));
+        if (h.done) break;
+    }
+    TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    double hs[kNumScal];
+    TB2_CUDA(cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
+    TB2_CUDA(cudaStreamSynchronize(st));
+    if (iterations) *iterations = h.iters;
+    if (final_rnorm) *final_rnorm = hs[kRNORM];
+    if (h.breakdown) {
+        set_error("PCG breakdown: p.Ap = %g <= 0 (matrix not positive definite)", hs[kPAP]);
+        return TB2_ERR_PCG_BREAKDOWN;
+    }
+    return TB2_OK;
+}
+
+int tb2_matrix_pcg_host(tb2_matrix* A, const double* h_b, double* h_x, double rtol, double atol, int max_iter, int* iterations,
+                        double* final_rnorm)
+{
+    TB2_ARG(A && h_b && h_x);
+    tb2_mesh* m = A->eqs->mesh;
+    DeviceGuard dg(m->device);
+    DevBuf<double> b, x;
+    TB2_CUDA(b.alloc(A->neq));
+    TB2_CUDA(x.alloc(A->neq));
+    TB2_CUDA(cudaMemcpyAsync(b.p, h_b, A->neq * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(x.p, h_x, A->neq * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    int s = tb2_matrix_pcg(A, b.p, x.p, rtol, atol, max_iter, iterations, final_rnorm);
+    TB2_CUDA(cudaMemcpyAsync(h_x, x.p, A->neq * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return s;
+}
+
+} // extern "C"

@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/tahoe_b200.h) against
+ (i) the golden fixtures written by the unmodified reference (tests/golden/*.npz) and
+ (ii) the CPU oracle (oracle/tahoe_oracle.c) on seeded synthetic inputs.
+Bar (BASELINE.json north_star): integer structures bit-exact, FP64 fields to 1e-10 relative."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import tahoe_input as ti
+from cases import ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def tb2():
+    from tahoe_b200 import capi
+    capi.lib()
+    assert capi.device_count() >= 1
+    return capi
+
+
+def _group(tb2, c):
+    mesh = tb2.Mesh(c.X, c.conn)
+    mat = tb2.material(c.desc["material"])
+    return mesh, tb2.Group(mesh, tb2.FORM_OF[c.desc["element"]["type"]], mat), mat
+
+
+# ------------------------------------------------------------------ K1 / K4
+@pytest.mark.parametrize("name", [n for n in ALL if "j2" not in n and "09" not in n])
+def test_internal_force_matches_reference(tb2, name):
+    c = Case(name)
+    mesh, grp, _ = _group(tb2, c)
+    d = c.ref("d_%d" % c.dump_steps[-1])
+    f = grp.internal_force_host(d)
+    assert relerr(f, c.ref("fint")) < TOL
+
+
+FORMS = [("small_strain", "small_strain_StVenant"), ("total_lagrangian", "large_strain_StVenant"),
+         ("total_lagrangian", "Simo_isotropic"), ("updated_lagrangian", "large_strain_StVenant"),
+         ("updated_lagrangian", "Simo_isotropic")]
+
+
+def _synthetic(n=(7, 6, 5), amp=2e-2, seed=7):
+    X, conn, ns = ti.structured_cube(*n, jitter=0.2)
+    rng = np.random.default_rng(seed)
+    u = amp * (0.3 * X @ rng.standard_normal((3, 3)) + 0.2 * rng.standard_normal(X.shape) / max(n))
+    return X, conn, ns, u
+
+
+@pytest.mark.parametrize("form,matname", FORMS)
+def test_internal_force_matches_oracle(tb2, oracle, form, matname):
+    X, conn, _, u = _synthetic()
+    desc = {"type": matname, "E": 100.0, "nu": 0.25, "density": 1.3}
+    err, f_ref = oracle.internal_force(oracle.FORM_OF[form], oracle.material(desc), conn, X, u)
+    assert err == 0
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.FORM_OF[form], tb2.material(desc))
+    f = grp.internal_force_host(u)
+    assert relerr(f, f_ref) < TOL
+    # reruns are bit-reproducible (no float atomics)
+    assert np.array_equal(f, grp.internal_force_host(u))
+
+
+def test_lumped_mass_matches_oracle(tb2, oracle):
+    X, conn, _, _ = _synthetic()
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, 0, tb2.material({"type": "small_strain_StVenant", "E": 1.0, "nu": 0.3, "density": 2.5}))
+    m = grp.lumped_mass_host()
+    assert relerr(m, oracle.lumped_mass(2.5, conn, X)) < 1e-13
+    assert abs(m[:, 0].sum() - 2.5) < 1e-12  # total mass of the unit cube
+
+
+def test_bad_jacobian_is_reported(tb2):
+    X, conn, _, u = _synthetic((3, 3, 3))
+    X = X.copy()
+    X[conn[5, 0]] = X[conn[5, 6]] + 0.3  # invert element 5
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, 0, tb2.material({"type": "small_strain_StVenant", "E": 1.0, "nu": 0.3, "density": 1.0}))
+    with pytest.raises(tb2.Tb2Error) as e:
+        grp.internal_force_host(u)
+    assert e.value.code == 1  # TB2_ERR_BAD_JACOBIAN <-> ExceptionT::kBadJacobianDet
+
+
+# ------------------------------------------------------------------ K5 explicit
+@pytest.mark.parametrize("name", EXPLICIT)
+def test_explicit_central_difference_matches_reference(tb2, name):
+    c = Case(name)
+    mesh, grp, mat = _group(tb2, c)
+    ex = tb2.Explicit(grp)
+    code, val, fext = c.bc(0.0)
+    sched_dep = any(k["type"] != "fixed" for k in c.desc["kbc"]) or bool(c.desc["fbc"])
+    ex.set_state(c.ref("d_0"), c.ref("v_0"), np.zeros_like(c.X))
+    ex.set_bc(code, val, fext)
+    ex.initial_condition()
+    _, _, a0 = ex.get_state()
+    assert np.abs(a0 - c.ref("a_0")).max() < 1e-12 * max(np.abs(a0).max(), 1.0)
+    done = 0
+    for k in c.dump_steps:
+        if k == 0:
+            continue
+        if sched_dep:  # time-dependent BCs: refresh arrays every step (what FieldT::InitStep does on the host)
+            for s in range(done + 1, k + 1):
+                code, val, fext = c.bc(s * c.dt)
+                ex.set_bc(code, val, fext)
+                ex.run(c.dt, 1)
+        else:
+            ex.run(c.dt, k - done)
+        done = k
+        d, v, a = ex.get_state()
+        assert relerr(d, c.ref("d_%d" % k)) < TOL
+        assert relerr(v, c.ref("v_%d" % k)) < TOL
+        assert relerr(a, c.ref("a_%d" % k)) < TOL
+
+
+def test_explicit_step_host_equals_resident_run(tb2):
+    X, conn, ns, u = _synthetic((6, 6, 6), amp=5e-3)
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, 1, tb2.material({"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    dt = 1e-4
+    ex = tb2.Explicit(grp)
+    ex.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    ex.set_state(u, np.zeros_like(X), np.zeros_like(X))
+    ex.run(dt, 5)
+    d1, v1, a1 = ex.get_state()
+    d, v, a = u.copy(), np.zeros_like(X), np.zeros_like(X)
+    for _ in range(5):
+        ex.step_host(dt, d, v, a)
+    assert np.array_equal(d, d1) and np.array_equal(v, v1) and np.array_equal(a, a1)
+
+
+# ------------------------------------------------------------------ K9 structure
+@pytest.mark.parametrize("name", ALL)
+def test_equation_numbers_bit_exact(tb2, name):
+    c = Case(name)
+    code, _, _ = c.bc(0.0)
+    mesh = tb2.Mesh(c.X, c.conn)
+    eqs = tb2.Equations(mesh, code)
+    eq, ref = eqs.eqnos(), c.ref("eqnos")
+    assert eqs.neq == ref.max()
+    assert np.array_equal(eq > 0, ref > 0)
+    if not c.renumbered:
+        assert np.array_equal(eq, ref)
+
+
+@pytest.mark.parametrize("name", WITH_LHS)
+def test_msr_structure_bit_exact(tb2, oracle, name):
+    c = Case(name)
+    code, _, _ = c.bc(0.0)
+    mesh = tb2.Mesh(c.X, c.conn)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    sym = "j2" not in name
+    assert np.array_equal(A.msr(upper_only=sym), c.ref("msr_bindx"))
+    rowptr, colind, _ = A.csr(values=False)
+    rp, ci = oracle.csr_structure(c.conn, eqs.eqnos(), eqs.neq)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+
+
+def test_csr_structure_and_colouring_bit_exact_on_cube(tb2, oracle):
+    X, conn, ns = ti.structured_cube(9, 7, 8, jitter=0.1)
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    code[ns[4], 1] = 1
+    mesh = tb2.Mesh(X, conn)
+    eqs = tb2.Equations(mesh, code)
+    eq, neq = oracle.equation_numbers(code)
+    assert np.array_equal(eqs.eqnos(), eq) and eqs.neq == neq
+    A = tb2.Matrix(eqs)
+    rowptr, colind, _ = A.csr(values=False)
+    rp, ci = oracle.csr_structure(conn, eq, neq)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+    assert np.array_equal(A.msr(True), oracle.msr_structure(conn, eq, neq, True))
+    ncol, col = mesh.colouring()
+    ncol_ref, col_ref = oracle.colouring(conn, X.shape[0])
+    assert ncol == ncol_ref == 8 and np.array_equal(col, col_ref)
+
+
+def test_colouring_bit_exact_on_shuffled_mesh(tb2, oracle):
+    """element order is what the greedy colouring depends on: permute it"""
+    X, conn, _ = ti.structured_cube(6, 5, 4)
+    perm = np.random.default_rng(3).permutation(conn.shape[0])
+    conn = np.ascontiguousarray(conn[perm])
+    mesh = tb2.Mesh(X, conn)
+    ncol, col = mesh.colouring()
+    ncol_ref, col_ref = oracle.colouring(conn, X.shape[0])
+    assert ncol == ncol_ref and np.array_equal(col, col_ref)
+
+
+# ------------------------------------------------------------------ K3 / K6-K8
+@pytest.mark.parametrize("name", [n for n in WITH_LHS if "j2" not in n])
+def test_tangent_matches_reference(tb2, name):
+    c = Case(name)
+    code, _, _ = c.bc(0.0)
+    mesh, grp, _ = _group(tb2, c)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    d = c.ref("d_%d" % c.dump_steps[-1])
+    A.form_stiffness_host(grp, d)
+    rowptr, colind, val = A.csr()
+    M = sp.csr_matrix((val, colind, rowptr), shape=(eqs.neq, eqs.neq))
+    r, cc, v = c.ref("lhs_r"), c.ref("lhs_c"), c.ref("lhs_v")
+    assert relerr(np.asarray(M[r, cc]).ravel(), v) < TOL
+    assert abs(M - M.T).max() < 1e-12 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("form,matname", FORMS)
+def test_tangent_matches_oracle(tb2, oracle, form, matname):
+    X, conn, ns, u = _synthetic((5, 4, 6))
+    desc = {"type": matname, "E": 100.0, "nu": 0.25, "density": 1.0}
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    code[ns[6], 2] = 1
+    eq, neq = oracle.equation_numbers(code)
+    rp, ci = oracle.csr_structure(conn, eq, neq)
+    err, kv = oracle.assemble_stiffness(oracle.FORM_OF[form], oracle.material(desc), conn, X, u, eq, neq, rp, ci)
+    assert err == 0
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.FORM_OF[form], tb2.material(desc))
+    A = tb2.Matrix(tb2.Equations(mesh, code))
+    A.form_stiffness_host(grp, u)
+    _, _, val = A.csr()
+    assert relerr(val, kv) < TOL
+    val1 = val.copy()
+    A.clear()
+    A.form_stiffness_host(grp, u)
+    assert np.array_equal(A.csr()[2], val1)  # deterministic assembly
+    # K6: SpMV
+    x = np.random.default_rng(1).standard_normal(neq)
+    assert relerr(A.multx_host(x), oracle.spmv(rp, ci, kv, x)) < 1e-12
+
+
+def test_pcg_matches_oracle_and_reference(tb2, oracle):
+    c = Case("syn_ss_kstv_static")
+    code, _, fext = c.bc(1.0)
+    mesh, grp, _ = _group(tb2, c)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    A.form_stiffness_host(grp, np.zeros_like(c.X))
+    b = fext[eqs.eqnos() > 0]
+    x, it, rn = A.pcg_host(b, rtol=1e-14, max_iter=5000)
+    rowptr, colind, val = A.csr()
+    x_ref, it_ref, _ = oracle.pcg_jacobi(rowptr, colind, val, b, rtol=1e-14, max_iter=5000)
+    assert 0 < it < 5000 and abs(it - it_ref) <= 2
+    assert relerr(x, x_ref) < TOL
+    d = np.zeros_like(c.X)
+    d[eqs.eqnos() > 0] = x
+    assert relerr(d, c.ref("d_1")) < TOL
+
+
+def _newton_gpu(tb2, c, linear_solve):
+    """NLSolver::Solve (NLSolver.cpp:57-263) driven through the C ABI"""
+    mesh, grp, mat = _group(tb2, c)
+    code, _, _ = c.bc(0.0)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    act = eqs.eqnos() > 0
+    isj2 = mat.kind == tb2.J2_SIMO
+    s = c.desc["solver"]
+    atol, rtol = float(s["abs_tolerance"]), float(s["rel_tolerance"])
+    d = c.ref("d_0").copy()
+    d_last = d.copy()
+    for k in range(1, c.nsteps + 1):
+        code, val, fext = c.bc(k * c.dt)
+        d[code == 1] = 0.0
+        d[code == 2] = val[code == 2]
+        it = -1
+        R = (fext - grp.internal_force_host(d, d_last if isj2 else None, it))[act]
+        e0 = e = np.linalg.norm(R)
+        while e0 >= atol and not (it >= 0 and (e / e0 < rtol or e < atol)):
+            assert it < 25
+            A.clear()
+            A.form_stiffness_host(grp, d, d_last if isj2 else None, it)
+            d[act] += linear_solve(A, R)
+            it += 1
+            R = (fext - grp.internal_force_host(d, d_last if isj2 else None, it))[act]
+            e = np.linalg.norm(R)
+        grp.close_step()
+        d_last = d.copy()
+        yield k, d, it, grp
+
+
+def _solve_pcg(A, R):
+    x, it, rn = A.pcg_host(R, rtol=1e-13, max_iter=20000)
+    return x
+
+
+def _solve_direct(A, R):
+    rowptr, colind, val = A.csr()
+    return spla.spsolve(sp.csr_matrix((val, colind, rowptr), shape=(A.neq, A.neq)).tocsc(), R)
+
+
+@pytest.mark.parametrize("name", [n for n in STATIC if n != "ref_traction_a" and "j2" not in n and "09" not in n])
+def test_static_newton_pcg_matches_reference(tb2, name):
+    """device K1 + K3 + Jacobi-PCG inside the reference's Newton loop reproduces the reference's displacements"""
+    c = Case(name)
+    iters = c.ref("iters")
+    for k, d, it, _ in _newton_gpu(tb2, c, _solve_pcg):
+        if k in c.dump_steps:
+            assert relerr(d, c.ref("d_%d" % k)) < 1e-9  # PCG to 1e-13 relative residual; Newton contracts the rest
+        assert it == iters[k - 1]
+
+
+@pytest.mark.parametrize("name", [n for n in STATIC if "j2" in n or "09" in n])
+def test_static_newton_j2_matches_reference(tb2, name):
+    """J2Simo3D: non-symmetric tangent -> the assembled device matrix is solved directly (as the reference does with LU);
+    displacements, iteration counts and the committed history must match"""
+    c = Case(name)
+    iters = c.ref("iters")
+    grp = None
+    for k, d, it, grp in _newton_gpu(tb2, c, _solve_direct):
+        if k in c.dump_steps:
+            assert relerr(d, c.ref("d_%d" % k)) < TOL
+        assert it == iters[k - 1]
+    data, flags, alloc = grp.get_history()
+    assert np.array_equal(alloc, c.ref("j2_alloc"))
+    ref = c.ref("j2_data").reshape(c.ne, 5 * 48 + 64)
+    sel = alloc > 0
+    assert sel.sum() > 0
+    assert np.abs(data[sel] - ref[sel]).max() < 1e-10
+    assert np.array_equal(flags[sel], c.ref("j2_flags")[sel])
+
+
+# ------------------------------------------------------------------ size-independent properties at larger sizes
+def test_properties_on_large_mesh(tb2):
+    n = 48
+    X, conn, ns = ti.structured_cube(n, jitter=0.15)
+    mesh = tb2.Mesh(X, conn)
+    mat = tb2.material({"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0})
+    grp = tb2.Group(mesh, 1, mat)
+    # rigid translation + rotation: zero internal force (finite strain is objective)
+    th = 0.3
+    Q = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    u = X @ (Q.T - np.eye(3)) + np.array([0.1, -0.2, 0.3])
+    f = grp.internal_force_host(u)
+    assert np.abs(f).max() < 1e-9 * mat.kappa / n ** 2
+    # any deformation: internal forces are self-equilibrated (sum = 0, moment = 0)
+    rng = np.random.default_rng(0)
+    u = 0.01 * X @ rng.standard_normal((3, 3))
+    f = grp.internal_force_host(u)
+    scale = np.abs(f).sum()
+    assert np.abs(f.sum(axis=0)).max() < 1e-12 * scale
+    x = X + u
+    assert np.abs(np.cross(x, f).sum(axis=0)).max() < 1e-11 * scale
+    # homogeneous deformation -> interior nodes are in equilibrium even on the jittered mesh (patch test)
+    k, j, i = np.meshgrid(np.arange(n + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    interior = ((i > 0) & (i < n) & (j > 0) & (j < n) & (k > 0) & (k < n)).ravel()
+    assert np.abs(f[interior]).max() < 1e-9 * np.abs(f).max()
+    # lumped mass: total mass and positivity
+    m = grp.lumped_mass_host()
+    assert abs(m[:, 0].sum() - 1.0) < 1e-11 and m.min() > 0
+
+
+def test_stiffness_properties_on_large_mesh(tb2):
+    n = 24
+    X, conn, ns = ti.structured_cube(n, jitter=0.15)
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, 0, tb2.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    eqs = tb2.Equations(mesh, code)  # no BCs: K has the 6 rigid-body modes in its null space
+    A = tb2.Matrix(eqs)
+    assert A.nnz == 9 * (3 * (n + 1) - 2) ** 3  # 9 (3 p - 2)^3 for a p^3-node cube
+    u0 = np.zeros_like(X)
+    A.form_stiffness_host(grp, u0)
+    t = np.tile([1.0, 2.0, -0.5], X.shape[0])
+    y = A.multx_host(t)
+    kmax = 100.0 / n
+    assert np.abs(y).max() < 1e-11 * kmax * 10
+    rot = np.cross(np.array([0.2, -0.1, 0.4]), X).ravel()
+    assert np.abs(A.multx_host(rot)).max() < 1e-11 * kmax * 10
+    # K u = fint(u) for the linear element
+    u = 1e-3 * np.random.default_rng(5).standard_normal(X.shape)
+    assert relerr(A.multx_host(u.ravel()).reshape(-1, 3), grp.internal_force_host(u)) < 1e-11
