@@ -38,7 +38,7 @@ REF_BIN = os.path.join(REPO, "oracle", "_ref", "tahoe")
 
 
 def stable_dt(n):
-    return 0.5 * (1.0 / n) / np.sqrt((MATERIAL["kappa"] + 4.0 * MATERIAL["mu"] / 3.0) / MATERIAL["density"])
+    return 0.25 * (1.0 / n) / np.sqrt((MATERIAL["kappa"] + 4.0 * MATERIAL["mu"] / 3.0) / MATERIAL["density"])
 
 
 def initial_displacement(X):

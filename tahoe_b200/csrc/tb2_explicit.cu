@@ -16,6 +16,20 @@ int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, i
 int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
 bool comm_active(tb2_mesh* m);
 
+// nExplicitCD::Predictor (nExplicitCD.cpp:72-96) / Corrector (:98-139) with explicit roundings, so that the stand-alone and
+// the fused kernels produce bit-identical fields
+TB2_DEV void cd_predict(double dt, double& d, double& v, double a)
+{
+    d = __fma_rn(dt, v, d);
+    d = __fma_rn(__dmul_rn(__dmul_rn(0.5, dt), dt), a, d);
+    v = __fma_rn(__dmul_rn(0.5, dt), a, v);
+}
+TB2_DEV void cd_correct(double dt, double& v, double& a, double upd)
+{
+    v = __fma_rn(__dmul_rn(0.5, dt), upd, v);
+    a = __dadd_rn(a, upd);
+}
+
 // predictor + ConsistentKBC, one thread per dof
 __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, double* __restrict__ d, double* __restrict__ v,
                                                      double* __restrict__ a, const unsigned char* __restrict__ code,
@@ -26,8 +40,7 @@ __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, d
     const unsigned char c = code[i];
     double di = d[i], vi = v[i];
     const double ai = a[i];
-    di += dt * vi + 0.5 * dt * dt * ai;
-    vi += 0.5 * dt * ai;
+    cd_predict(dt, di, vi, ai);
     if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
     else if (c == TB2_BC_DSP) di = value_scale * bcval[i];
     d[i] = di;
@@ -68,14 +81,14 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t nn, const int* _
     for (int i = 0; i < 3; i++) {
         const int64_t q = 3 * n + i;
         const unsigned char c = code[q];
-        const double R = fext_scale * fext[q] - f[i];
-        const double upd = c ? 0.0 : R * minv[q];
-        double vi = v[q] + 0.5 * dt * upd;
-        double ai = a[q] + upd;
+        const double R = __dsub_rn(__dmul_rn(fext_scale, fext[q]), f[i]);
+        const double upd = c ? 0.0 : __dmul_rn(R, minv[q]);
+        double vi = v[q], ai = a[q];
+        cd_correct(dt, vi, ai, upd);
         if (GATHER) fint[q] = f[i];
         if (NEXT_PREDICTOR) {
-            double di = d[q] + dt * vi + 0.5 * dt * dt * ai;
-            vi += 0.5 * dt * ai;
+            double di = d[q];
+            cd_predict(dt, di, vi, ai);
             ai = 0.0;
             if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
             else if (c == TB2_BC_DSP) di = next_value_scale * bcval[q];
