@@ -14,6 +14,8 @@
 // Scatter.  Threads write the 24 element values to an SoA scratch fe[24][stride] (coalesced); a node kernel then sums
 // each node's <= 8 contributions in ascending element order -- the order of the reference's serial assembly
 // (SolverT::AssembleRHS, SolverT.cpp:446-477) -- so there are no float atomics and reruns are bit-reproducible.
+#include <cstdlib>
+
 #include "tb2_internal.h"
 
 namespace tb2 {
@@ -37,8 +39,8 @@ TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
     atomicMin(p.status + 1, (unsigned long long)e);
 }
 
-template <int FORM, int MAT>
-__global__ void __launch_bounds__(128) k_internal_force(const ElemArgs p)
+template <int FORM, int MAT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= p.ne) return;
@@ -90,16 +92,25 @@ __global__ void __launch_bounds__(128) k_internal_force(const ElemArgs p)
                 for (int k = 0; k < 3; k++) j[i][k] = J0[i][k] + H[i][k];
             const double detj = adj3(j, ja);
             if (detj <= 0.0) err = kErrBadJacobian; // TotalLagrangianT.cpp:127-128 / current-configuration ComputeDNa
-            mul3(j, J0a, F);
-            scale3(F, rdet0);
+            mul3(j, J0a, F); // = det0 * F
+            if (MAT == kSimoIso) {
+                // SimoIso3D::s_ij on the unscaled F' = det0 F: b = F'F'^T / det0^2, one reciprocal for 1/det0 and 1/J
+                const double rdd = 1.0 / (det0 * detj);
+                const double rd0 = rdd * detj, rJ = det0 * (det0 * rdd), J = detj * rd0;
+                double b[6];
+                sym_fft(F, b);
+                sym_dev(b);
+                const double r = rcbrt(J);
+                const double sc = (p.mat.mu * rJ) * (r * r) * (rd0 * rd0); // (mu/J) J^(-2/3) / det0^2
+                const double pr = 0.5 * p.mat.kappa * (J - rJ);            // U'(J), SimoIso3D.h:93-96
+                sig[0] = sc * b[0] + pr; sig[1] = sc * b[1] + pr; sig[2] = sc * b[2] + pr;
+                sig[3] = sc * b[3]; sig[4] = sc * b[4]; sig[5] = sc * b[5];
+            }
             const double J = detj * rdet0;
+            if (MAT != kSimoIso) scale3(F, rdet0);
             if (MAT == kFDKStV)
                 fdkstv_stress(p.mat, F, J, sig);
-            else if (MAT == kSimoIso) {
-                double b_bar[6];
-                simo_bbar(F, J, b_bar);
-                simo_cauchy(p.mat, J, b_bar, sig);
-            } else if (MAT == kJ2Simo) {
+            else if (MAT == kJ2Simo) {
                 double Hl[3][3], Fl[3][3], c[6][6];
                 mode_gradient(cL, s0, s1, s2, Hl);
                 mul3(Hl, J0a, Fl);
@@ -227,17 +238,25 @@ __global__ void k_j2_reset_step(int64_t ne, J2Hist h)
 }
 
 typedef void (*force_kernel_t)(const ElemArgs);
+static const int kDefaultMinBlocks = 2;
 static force_kernel_t pick_force_kernel(int form, int mat)
 {
-    switch (form * 4 + mat) {
-    case kSmallStrain * 4 + kSSKStV: return k_internal_force<kSmallStrain, kSSKStV>;
-    case kTotalLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV>;
-    case kTotalLagrangian * 4 + kSimoIso: return k_internal_force<kTotalLagrangian, kSimoIso>;
-    case kTotalLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo>;
+    // registers-per-thread cap experiment (TB2_K1_MINBLOCKS=2|3|4 resident CTAs of 128 threads per SM); default from the ncu study
+    static int minb = 0;
+    if (!minb) {
+        const char* s = getenv("TB2_K1_MINBLOCKS");
+        minb = s ? atoi(s) : kDefaultMinBlocks;
+        if (minb < 2 || minb > 4) minb = kDefaultMinBlocks;
+    }
     // UpdatedLagrangianT shares the finite-strain body (see file header)
-    case kUpdatedLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV>;
-    case kUpdatedLagrangian * 4 + kSimoIso: return k_internal_force<kTotalLagrangian, kSimoIso>;
-    case kUpdatedLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo>;
+    if (form == kUpdatedLagrangian) form = kTotalLagrangian;
+    switch (form * 4 + mat) {
+    case kSmallStrain * 4 + kSSKStV: return k_internal_force<kSmallStrain, kSSKStV, 2>;
+    case kTotalLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV, 2>;
+    case kTotalLagrangian * 4 + kSimoIso:
+        return minb == 2 ? k_internal_force<kTotalLagrangian, kSimoIso, 2>
+                         : (minb == 3 ? k_internal_force<kTotalLagrangian, kSimoIso, 3> : k_internal_force<kTotalLagrangian, kSimoIso, 4>);
+    case kTotalLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo, 2>;
     }
     return nullptr;
 }
