@@ -148,6 +148,10 @@ const int32_t* tb2_equations_device(const tb2_equations* eqs);
 
 /* ---- global matrix (GlobalMatrixT.h:24-223; storage semantics of MSRMatrixT, solve = AztecMatrixT-style CG+Jacobi) */
 int tb2_matrix_create(tb2_equations* eqs, tb2_matrix** A); /* GlobalMatrixT::Initialize + MSRBuilderT: CSR structure built on device */
+/* the same matrix type from host CSR arrays (rowptr int64 [neq+1], colind sorted, 0-based): what a host-assembled
+ * MSRMatrixT-derived plugin hands over (GenerateRCV / MSRBuilderT::SetSuperLUData form); values by tb2_matrix_set_values */
+int tb2_matrix_create_csr(int device, int64_t num_eq, const int64_t* h_rowptr, const int32_t* h_colind, tb2_matrix** A);
+int tb2_matrix_set_values(tb2_matrix* A, const double* h_val /*[nnz]*/);
 int tb2_matrix_destroy(tb2_matrix* A);
 int tb2_matrix_nnz(const tb2_matrix* A, int64_t* nnz);
 /* MSRBuilderT::SetSuperLUData form: rowptr[neq+1] (int64), colind[nnz] sorted, diagonal in place */

@@ -238,7 +238,7 @@ __global__ void k_j2_reset_step(int64_t ne, J2Hist h)
 }
 
 typedef void (*force_kernel_t)(const ElemArgs);
-static const int kDefaultMinBlocks = 2;
+static const int kDefaultMinBlocks = 3; // r01b: 168 regs, 3 CTAs/SM: K1 191 us vs 203 (2) and 201 (4) on 1M elements
 static force_kernel_t pick_force_kernel(int form, int mat)
 {
     // registers-per-thread cap experiment (TB2_K1_MINBLOCKS=2|3|4 resident CTAs of 128 threads per SM); default from the ncu study

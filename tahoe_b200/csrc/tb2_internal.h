@@ -149,7 +149,9 @@ struct tb2_equations {
 };
 
 struct tb2_matrix {
-    tb2_equations* eqs = nullptr;
+    tb2_equations* eqs = nullptr; // null for a matrix created from raw CSR arrays (tb2_matrix_create_csr)
+    tb2_mesh* ctx = nullptr;      // device + stream + instrumentation context (the mesh, or a private one)
+    bool owns_ctx = false;
     int64_t neq = 0, nnz = 0;
     tb2::DevBuf<int> adj_ptr;     // [nn+1] node adjacency (sorted neighbour nodes incl. self)
     tb2::DevBuf<int> adj;         // neighbour node ids

@@ -425,6 +425,7 @@ int tb2_matrix_create(tb2_equations* q, tb2_matrix** out)
     DeviceGuard dg(m->device);
     tb2_matrix* A = new tb2_matrix;
     A->eqs = q;
+    A->ctx = m;
     A->neq = q->neq;
     const int64_t nn = m->nn, neq = q->neq;
     auto fail = [&](int s) { delete A; return s; };
@@ -493,9 +494,73 @@ int tb2_matrix_create(tb2_equations* q, tb2_matrix** out)
 int tb2_matrix_destroy(tb2_matrix* A)
 {
     if (!A) return TB2_OK;
-    DeviceGuard dg(A->eqs->mesh->device);
-    cudaStreamSynchronize(A->eqs->mesh->stream);
+    DeviceGuard dg(A->ctx->device);
+    cudaStreamSynchronize(A->ctx->stream);
+    tb2_mesh* ctx = A->owns_ctx ? A->ctx : nullptr;
     delete A;
+    if (ctx) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    }
+    return TB2_OK;
+}
+
+static int alloc_pcg_work(tb2_matrix* A)
+{
+    const int64_t neq = A->neq;
+    TB2_CUDA(A->dinv.alloc(neq));
+    TB2_CUDA(A->r.alloc(neq));
+    TB2_CUDA(A->z.alloc(neq));
+    TB2_CUDA(A->p.alloc(neq));
+    TB2_CUDA(A->q.alloc(neq));
+    TB2_CUDA(A->scal.alloc(kNumScal + 4));
+    const int64_t spmv_blocks = (neq + 7) / 8;
+    TB2_CUDA(A->partial.alloc((spmv_blocks > 2 * kReduceBlocks ? spmv_blocks : 2 * kReduceBlocks) + 8));
+    return TB2_OK;
+}
+
+// a device CSR matrix from host CSR arrays: the path a host-assembled Tahoe matrix (MSRMatrixT-derived plugin) takes
+int tb2_matrix_create_csr(int device, int64_t neq, const int64_t* h_rowptr, const int32_t* h_colind, tb2_matrix** out)
+{
+    TB2_ARG(out && h_rowptr && h_colind && neq > 0);
+    int ndev = 0;
+    TB2_CUDA(cudaGetDeviceCount(&ndev));
+    TB2_ARG(device >= 0 && device < ndev);
+    DeviceGuard dg(device);
+    tb2_mesh* ctx = new tb2_mesh;
+    ctx->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    tb2_matrix* A = new tb2_matrix;
+    A->ctx = ctx;
+    A->owns_ctx = true;
+    A->neq = neq;
+    A->nnz = h_rowptr[neq];
+    int s = TB2_OK;
+    auto chk = [&](cudaError_t err) { if (s == TB2_OK && err != cudaSuccess) s = cuda_fail(err, "tb2_matrix_create_csr", __FILE__, __LINE__); };
+    chk(A->rowptr.alloc(neq + 1));
+    chk(A->colind.alloc(A->nnz));
+    chk(A->val.alloc(A->nnz));
+    if (s == TB2_OK) chk(cudaMemcpy(A->rowptr.p, h_rowptr, (neq + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    if (s == TB2_OK) chk(cudaMemcpy(A->colind.p, h_colind, A->nnz * sizeof(int), cudaMemcpyHostToDevice));
+    if (s == TB2_OK) chk(cudaMemset(A->val.p, 0, A->nnz * sizeof(double)));
+    if (s == TB2_OK) s = alloc_pcg_work(A);
+    if (s != TB2_OK) {
+        tb2_matrix_destroy(A);
+        return s;
+    }
+    *out = A;
+    return TB2_OK;
+}
+int tb2_matrix_set_values(tb2_matrix* A, const double* h_val)
+{
+    TB2_ARG(A && h_val);
+    DeviceGuard dg(A->ctx->device);
+    TB2_CUDA(cudaMemcpyAsync(A->val.p, h_val, A->nnz * sizeof(double), cudaMemcpyHostToDevice, A->ctx->stream));
+    TB2_CUDA(cudaStreamSynchronize(A->ctx->stream));
     return TB2_OK;
 }
 int tb2_matrix_nnz(const tb2_matrix* A, int64_t* nnz)
@@ -507,7 +572,7 @@ int tb2_matrix_nnz(const tb2_matrix* A, int64_t* nnz)
 int tb2_matrix_get_csr(const tb2_matrix* A, int64_t* h_rowptr, int32_t* h_colind, double* h_val)
 {
     TB2_ARG(A);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     if (h_rowptr) TB2_CUDA(cudaMemcpy(h_rowptr, A->rowptr.p, (A->neq + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -519,7 +584,7 @@ int tb2_matrix_get_csr(const tb2_matrix* A, int64_t* h_rowptr, int32_t* h_colind
 int tb2_matrix_get_msr(const tb2_matrix* A, int upper_only, int32_t* h_bindx, int64_t* length)
 {
     TB2_ARG(A && length);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     const int64_t neq = A->neq;
     std::vector<long long> rp(neq + 1);
@@ -544,7 +609,7 @@ int tb2_matrix_get_msr(const tb2_matrix* A, int upper_only, int32_t* h_bindx, in
 int tb2_matrix_clear(tb2_matrix* A)
 {
     TB2_ARG(A);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     TB2_CUDA(cudaMemsetAsync(A->val.p, 0, A->nnz * sizeof(double), m->stream));
     return TB2_OK;
@@ -553,7 +618,7 @@ int tb2_matrix_clear(tb2_matrix* A)
 int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y)
 {
     TB2_ARG(A && d_x && d_y);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     ProfScope ps(m, kProfSpmv);
     k_spmv<false><<<(unsigned)((A->neq + 7) / 8), 256, 0, m->stream>>>(A->neq, A->rowptr.p, A->colind.p, A->val.p, d_x, d_y, nullptr, nullptr);
@@ -563,7 +628,7 @@ int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y)
 int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y)
 {
     TB2_ARG(A && h_x && h_y);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     TB2_CUDA(cudaMemcpyAsync(A->p.p, h_x, A->neq * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     TB2_CHECK(tb2_matrix_multx(A, A->p.p, A->q.p));
@@ -574,7 +639,7 @@ int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y)
 int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag)
 {
     TB2_ARG(A && d_diag);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     k_extract_dinv<<<(unsigned)((A->neq + 255) / 256), 256, 0, m->stream>>>(A->neq, A->rowptr.p, A->colind.p, A->val.p, d_diag, 0);
     TB2_CUDA(cudaGetLastError());
@@ -585,7 +650,7 @@ int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, d
                    double* final_rnorm)
 {
     TB2_ARG(A && d_b && d_x);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     const int64_t n = A->neq;
     cudaStream_t st = m->stream;
@@ -637,7 +702,7 @@ int tb2_matrix_pcg_host(tb2_matrix* A, const double* h_b, double* h_x, double rt
                         double* final_rnorm)
 {
     TB2_ARG(A && h_b && h_x);
-    tb2_mesh* m = A->eqs->mesh;
+    tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     DevBuf<double> b, x;
     TB2_CUDA(b.alloc(A->neq));

@@ -318,7 +318,7 @@ int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const dou
 {
     TB2_ARG(g && A && d_u);
     tb2_mesh* m = g->mesh;
-    TB2_ARG(A->eqs->mesh == m);
+    TB2_ARG(A->eqs && A->eqs->mesh == m);
     DeviceGuard dg(m->device);
     stiff_kernel_t k = pick_stiff_kernel(g->form, g->mat.kind);
     TB2_ARG(k != nullptr);

@@ -1,0 +1,231 @@
+/* CudaSolidElementT.cpp -- see CudaSolidElementT.h */
+#include "CudaSolidElementT.h"
+
+#include "CudaPCGMatrixT.h"
+#include "ElementSupportT.h"
+#include "ExceptionT.h"
+#include "FDKStV.h"
+#include "FEManagerT.h"
+#include "FieldT.h"
+#include "IsotropicT.h"
+#include "J2Simo3D.h"
+#include "MaterialListT.h"
+#include "ParameterListT.h"
+#include "SSKStV.h"
+#include "SimoIso3D.h"
+#include "SolidMaterialT.h"
+#include "eIntegratorT.h"
+#include "iArray2DT.h"
+
+#include <cstring>
+#include <vector>
+
+using namespace Tahoe;
+
+namespace Tahoe {
+const char* kCudaSolidElementNames[3] = {"cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian"};
+
+ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& support)
+{
+	if (name == kCudaSolidElementNames[0]) return new CudaSmallStrainT(support, kCudaSolidElementNames[0], TB2_SMALL_STRAIN);
+	if (name == kCudaSolidElementNames[1]) return new CudaTotalLagrangianT(support, kCudaSolidElementNames[1], TB2_TOTAL_LAGRANGIAN);
+	if (name == kCudaSolidElementNames[2]) return new CudaUpdatedLagrangianT(support, kCudaSolidElementNames[2], TB2_UPDATED_LAGRANGIAN);
+	return NULL;
+}
+} // namespace Tahoe
+
+/* depth-first search of the validated parameter tree for a sub-list by name (J2 hardening function) */
+static const ParameterListT* FindList(const ParameterListT& list, const char* name)
+{
+	if (list.Name() == name) return &list;
+	const ArrayT<ParameterListT>& subs = list.Lists();
+	for (int i = 0; i < subs.Length(); i++) {
+		const ParameterListT* hit = FindList(subs[i], name);
+		if (hit) return hit;
+	}
+	return NULL;
+}
+
+template <class BaseT>
+CudaSolidElementT<BaseT>::CudaSolidElementT(const ElementSupportT& support, const char* name, int formulation):
+	BaseT(support),
+	fFormulation(formulation),
+	fMesh(NULL),
+	fGroup(NULL),
+	fEqs(NULL),
+	fMatrix(NULL),
+	fIsJ2(false)
+{
+	this->SetName(name);
+}
+
+template <class BaseT>
+CudaSolidElementT<BaseT>::~CudaSolidElementT(void)
+{
+	if (fMatrix) tb2_matrix_destroy(fMatrix);
+	if (fEqs) tb2_equations_destroy(fEqs);
+	if (fGroup) tb2_group_destroy(fGroup);
+	if (fMesh) tb2_mesh_destroy(fMesh);
+}
+
+/* status code -> Tahoe exception (include/tahoe_b200.h: tb2_status) */
+template <class BaseT>
+void CudaSolidElementT<BaseT>::Check(int status, const char* caller) const
+{
+	switch (status) {
+	case TB2_OK: return;
+	case TB2_ERR_BAD_JACOBIAN: ExceptionT::BadJacobianDet(caller, "%s", tb2_last_error());
+	case TB2_ERR_ARG: ExceptionT::BadInputValue(caller, "%s", tb2_last_error());
+	case TB2_ERR_SIZE: ExceptionT::SizeMismatch(caller, "%s", tb2_last_error());
+	case TB2_ERR_COMM: ExceptionT::MPIFail(caller, "%s", tb2_last_error());
+	default: ExceptionT::GeneralFail(caller, "%s", tb2_last_error());
+	}
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
+{
+	const char caller[] = "CudaSolidElementT::TakeParameterList";
+
+	/* inherited: connectivity, shape functions, materials, output -- all Tahoe's own */
+	BaseT::TakeParameterList(list);
+
+	/* the device path covers exactly the reference's Hex8 / 8-point / standard-B case */
+	if (this->GeometryCode() != GeometryT::kHexahedron || this->NumElementNodes() != 8 || this->NumIP() != 8 || this->NumSD() != 3)
+		ExceptionT::BadInputValue(caller, "the CUDA element group supports 8-node hexahedra with 8 integration points only");
+	const ParameterT* b_opt = list.Parameter("strain_displacement"); /* SmallStrainT only (SmallStrainT.cpp:38-42): 0 = standard */
+	if (b_opt && int(*b_opt) != 0)
+		ExceptionT::BadInputValue(caller, "strain_displacement must be \"standard\" (B-bar is a different formulation)");
+	if (this->fMaterialList->Length() != 1)
+		ExceptionT::BadInputValue(caller, "exactly one material per CUDA element group");
+
+	/* material constants */
+	ContinuumMaterialT* cmat = (*(this->fMaterialList))[0];
+	tb2_material mat;
+	memset(&mat, 0, sizeof(mat));
+	if (dynamic_cast<SSKStV*>(cmat)) mat.kind = TB2_SSKSTV;
+	else if (dynamic_cast<FDKStV*>(cmat)) mat.kind = TB2_FDKSTV;
+	else if (dynamic_cast<J2Simo3D*>(cmat)) mat.kind = TB2_J2_SIMO; /* before its base SimoIso3D */
+	else if (dynamic_cast<SimoIso3D*>(cmat)) mat.kind = TB2_SIMO_ISO;
+	else ExceptionT::BadInputValue(caller, "material \"%s\" has no device implementation", cmat->Name().Pointer());
+	const IsotropicT* iso = dynamic_cast<const IsotropicT*>(cmat);
+	const SolidMaterialT* smat = dynamic_cast<const SolidMaterialT*>(cmat);
+	if (!iso || !smat) ExceptionT::GeneralFail(caller, "material is not isotropic");
+	mat.mu = iso->Mu();
+	mat.lambda = iso->Lambda();
+	mat.kappa = iso->Kappa();
+	mat.density = const_cast<SolidMaterialT*>(smat)->Density();
+	fIsJ2 = (mat.kind == TB2_J2_SIMO);
+	if (fIsJ2) { /* K(alpha): C1functions/LinearT.h:71, LinearExponentialT.cpp:48-57 */
+		const ParameterListT* lin = FindList(list, "linear_function");
+		const ParameterListT* lexp = FindList(list, "linear_exponential");
+		if (lin) {
+			mat.hard_kind = TB2_HARD_LINEAR;
+			mat.hard[0] = lin->GetParameter("a");
+			mat.hard[1] = lin->GetParameter("b");
+		} else if (lexp) {
+			mat.hard_kind = TB2_HARD_LINEAR_EXP;
+			mat.hard[0] = lexp->GetParameter("a");
+			mat.hard[1] = lexp->GetParameter("b");
+			mat.hard[2] = lexp->GetParameter("c");
+			mat.hard[3] = lexp->GetParameter("d");
+		} else
+			ExceptionT::BadInputValue(caller, "Simo_J2 hardening must be linear_function or linear_exponential");
+	}
+
+	/* connectivity of all blocks, in block order then file order (ElementBaseT.cpp:607-632) */
+	std::vector<int32_t> conn;
+	for (int b = 0; b < this->fConnectivities.Length(); b++) {
+		const iArray2DT& c = *(this->fConnectivities[b]);
+		conn.insert(conn.end(), c.Pointer(), c.Pointer() + c.Length());
+	}
+	const dArray2DT& X = this->ElementSupport().InitialCoordinates();
+	Check(tb2_mesh_create(0, X.MajorDim(), (int64_t)(conn.size() / 8), &conn[0], X.Pointer(), &fMesh), caller);
+	Check(tb2_group_create(fMesh, fFormulation, &mat, &fGroup), caller);
+	fFint.Dimension(X.MajorDim(), 3);
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::RHSDriver(void)
+{
+	const char caller[] = "CudaSolidElementT::RHSDriver";
+
+	/* tractions: O(surface) host work, inherited (ContinuumElementT.cpp:505-665) */
+	ContinuumElementT::RHSDriver();
+
+	/* components dictated by the integrator (SolidElementT.cpp:1197-1215) */
+	double constMa = 0.0, constKd = 0.0;
+	int formMa = this->fIntegrator->FormMa(constMa);
+	int formKd = this->fIntegrator->FormKd(constKd);
+	if (this->fMassType == ContinuumElementT::kNoMass) formMa = 0;
+	if (formMa || (this->fBodySchedule && this->fBody.Magnitude() > kSmall))
+		ExceptionT::GeneralFail(caller, "inertial / body-force residual terms are not on the device path (explicit lumped-mass and static analyses only)");
+	if (!formKd) return;
+
+	const FieldT& field = this->Field();
+	const dArray2DT& disp = field[0];
+	const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
+	int iteration = this->ElementSupport().IterationNumber(this->Group());
+	Check(tb2_form_internal_force_host(fGroup, disp.Pointer(), last, iteration, fFint.Pointer()), caller);
+
+	/* RHS += -constKd * fint on the active equations: one call for the whole group (SolverT::AssembleRHS, SolverT.cpp:446-477) */
+	fFint *= -constKd;
+	this->ElementSupport().AssembleRHS(this->Group(), fFint, field.Equations());
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::LHSDriver(GlobalT::SystemTypeT sys_type)
+{
+	const char caller[] = "CudaSolidElementT::LHSDriver";
+
+	/* mass matrix requested (explicit: once) or a host matrix type: Tahoe's own assembly */
+	double constM = 0.0, constK = 0.0;
+	int formM = this->fIntegrator->FormM(constM);
+	int formK = this->fIntegrator->FormK(constK);
+	const GlobalMatrixT& lhs = this->ElementSupport().FEManager().LHS(this->Group());
+	CudaPCGMatrixT* cuda_lhs = const_cast<CudaPCGMatrixT*>(dynamic_cast<const CudaPCGMatrixT*>(&lhs));
+	if (!cuda_lhs || formM || !formK || fabs(constK) < kSmall) {
+		BaseT::LHSDriver(sys_type);
+		return;
+	}
+
+	/* tractions etc. */
+	ContinuumElementT::LHSDriver(sys_type);
+
+	/* device assembly into the cooperating matrix: K3 straight into its CSR, no element matrices cross the bus */
+	const FieldT& field = this->Field();
+	if (!fEqs) { /* equation numbers exist now: prescribed dofs have eqnos <= 0 (FieldT.cpp:635-659) */
+		const iArray2DT& eq = field.Equations();
+		std::vector<uint8_t> bc(eq.Length());
+		for (int i = 0; i < eq.Length(); i++) bc[i] = eq[i] > 0 ? 0 : 1;
+		Check(tb2_equations_create(fMesh, &bc[0], &fEqs), caller);
+		Check(tb2_matrix_create(fEqs, &fMatrix), caller);
+	}
+	const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
+	int iteration = this->ElementSupport().IterationNumber(this->Group());
+	Check(tb2_matrix_clear(fMatrix), caller);
+	Check(tb2_form_stiffness_host(fGroup, fMatrix, field[0].Pointer(), last, iteration), caller);
+	cuda_lhs->AddDeviceMatrix(fMatrix, constK);
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::CloseStep(void)
+{
+	BaseT::CloseStep();
+	if (fGroup) Check(tb2_group_close_step(fGroup), "CudaSolidElementT::CloseStep");
+}
+
+template <class BaseT>
+GlobalT::RelaxCodeT CudaSolidElementT<BaseT>::ResetStep(void)
+{
+	GlobalT::RelaxCodeT relax = BaseT::ResetStep();
+	if (fGroup) Check(tb2_group_reset_step(fGroup), "CudaSolidElementT::ResetStep");
+	return relax;
+}
+
+/* explicit instantiation */
+namespace Tahoe {
+template class CudaSolidElementT<SmallStrainT>;
+template class CudaSolidElementT<TotalLagrangianT>;
+template class CudaSolidElementT<UpdatedLagrangianT>;
+}

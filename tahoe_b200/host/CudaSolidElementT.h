@@ -1,0 +1,88 @@
+/* CudaSolidElementT.h -- Tahoe element-group plugin that runs the Hex8 continuum-solid element loop on a B200 through
+ * the C ABI of libtahoe_b200.so (include/tahoe_b200.h).
+ *
+ * The class template derives from Tahoe's own SmallStrainT / TotalLagrangianT / UpdatedLagrangianT, so the XML
+ * parameters, material lists, output, mass matrix and restart code are inherited unchanged and an input file differs
+ * from a classic one by the element tag only (<total_lagrangian> -> <cuda_total_lagrangian>).  What is replaced is the
+ * per-element virtual-call loop:
+ *   RHSDriver()  : SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295)  -> tb2_form_internal_force_host
+ *   LHSDriver()  : SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154)  -> tb2_form_stiffness into the
+ *                  device CSR of a cooperating CudaPCGMatrixT; any other matrix type keeps Tahoe's host assembly
+ *   CloseStep()/ResetStep() : J2 history commit / reset on the device.
+ * Results leave through ElementSupportT::AssembleRHS (ElementSupportT.h:43) with the field's equation array, i.e. one
+ * call for the whole group instead of one per element.
+ */
+#ifndef _CUDA_SOLID_ELEMENT_T_H_
+#define _CUDA_SOLID_ELEMENT_T_H_
+
+#include "SmallStrainT.h"
+#include "TotalLagrangianT.h"
+#include "UpdatedLagrangianT.h"
+#include "dArray2DT.h"
+
+#include "tahoe_b200.h"
+
+namespace Tahoe {
+
+class CudaPCGMatrixT;
+
+/** interface the cooperating matrix uses to ask an element group for a device-assembled tangent */
+class CudaStiffnessSourceT
+{
+public:
+	virtual ~CudaStiffnessSourceT(void) {}
+	virtual tb2_mesh* DeviceMesh(void) = 0;
+};
+
+template <class BaseT>
+class CudaSolidElementT: public BaseT, public CudaStiffnessSourceT
+{
+public:
+
+	/** \param name XML tag, \param formulation tb2_formulation */
+	CudaSolidElementT(const ElementSupportT& support, const char* name, int formulation);
+	virtual ~CudaSolidElementT(void);
+
+	/** build the device mesh / element group after Tahoe has read connectivity and materials */
+	virtual void TakeParameterList(const ParameterListT& list);
+
+	/** \name history */
+	/*@{*/
+	virtual void CloseStep(void);
+	virtual GlobalT::RelaxCodeT ResetStep(void);
+	/*@}*/
+
+	virtual tb2_mesh* DeviceMesh(void) { return fMesh; }
+
+protected:
+
+	/** residual: tractions on the host (ContinuumElementT::RHSDriver), element forces on the device */
+	virtual void RHSDriver(void);
+
+	/** tangent: device assembly when the solver's matrix is a CudaPCGMatrixT, else inherited */
+	virtual void LHSDriver(GlobalT::SystemTypeT sys_type);
+
+private:
+
+	void Check(int status, const char* caller) const;
+
+	int fFormulation;
+	tb2_mesh* fMesh;
+	tb2_group* fGroup;
+	tb2_equations* fEqs;   /**< built lazily: equation numbers are set after TakeParameterList */
+	tb2_matrix* fMatrix;   /**< device tangent of this group (structure from the mesh) */
+	bool fIsJ2;
+	dArray2DT fFint;       /**< [nn][3] internal force of the whole group */
+};
+
+typedef CudaSolidElementT<SmallStrainT> CudaSmallStrainT;
+typedef CudaSolidElementT<TotalLagrangianT> CudaTotalLagrangianT;
+typedef CudaSolidElementT<UpdatedLagrangianT> CudaUpdatedLagrangianT;
+
+/** factory used by the one-line registration in ElementListT::NewElement; returns NULL for other names */
+ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& support);
+/** the XML tags handled by NewCudaSolidElement */
+extern const char* kCudaSolidElementNames[3];
+
+} // namespace Tahoe
+#endif

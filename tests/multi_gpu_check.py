@@ -1,0 +1,90 @@
+"""Multi-GPU parity script (run under torchrun, one rank per GPU; launched by tests/test_gpu_multi.py):
+explicit central difference on an element-partitioned cube with NCCL interface-node force sums must reproduce the
+single-GPU run of the whole cube (rank 0 computes it on its own device) to 1e-12, and all sharers of an interface node
+must hold bitwise identical values."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from tahoe_b200 import capi, mesh as tmesh  # noqa: E402
+
+MAT = {"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0}
+
+
+def field(X):
+    return 0.01 * X @ np.array([[0.3, -0.2, 0.1], [0.05, 0.4, -0.3], [0.2, 0.1, -0.25]]) + 1e-3 * np.sin(7.0 * X[:, ::-1])
+
+
+def setup(X, conn, ns, device, comm=None):
+    m = capi.Mesh(X, conn, device=device)
+    if comm:
+        m.comm_init(*comm)
+    g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MAT))
+    ex = capi.Explicit(g)
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 1e-3  # on interface nodes every sharer holds the full nodal load (it is not summed)
+    ex.set_bc(code, np.zeros_like(X), fext)
+    ex.set_state(field(X), np.zeros_like(X), np.zeros_like(X))
+    return m, g, ex
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = (12, 10, 8)
+    dt, nsteps = 2e-4, 25
+    part = tmesh.partition_cube(*dims, world, rank, jitter=0.15)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    m, g, ex = setup(part["coords"], part["conn"], part["nodesets"], local,
+                     (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"]))
+    ex.initial_condition()
+    ex.run(dt, nsteps)
+    d, v, a = ex.get_state()
+    mass = ex.mass_host()
+    nn_glob = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
+    # gather every rank's fields on rank 0 keyed by global node id
+    out = [None] * world
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass})
+    ok = True
+    if rank == 0:
+        X, conn, ns = tmesh.structured_cube(*dims, jitter=0.15)
+        m1, g1, ex1 = setup(X, conn, ns, local)
+        ex1.initial_condition()
+        ex1.run(dt, nsteps)
+        d1, v1, a1 = ex1.get_state()
+        mass1 = ex1.mass_host()
+        seen = {}
+        for r, o in enumerate(out):
+            for nm, ref in (("d", d1), ("v", v1), ("a", a1), ("mass", mass1)):
+                err = np.abs(o[nm] - ref[o["gid"]]).max() / max(np.abs(ref).max(), 1e-300)
+                if not err < 1e-12:
+                    print("rank %d field %s differs from the single-GPU run: %.3e" % (r, nm, err))
+                    ok = False
+            for gid, row in zip(o["gid"], np.hstack([o["d"], o["v"], o["a"]])):
+                if gid in seen and not np.array_equal(seen[gid], row):
+                    print("node %d differs bitwise between sharers" % gid)
+                    ok = False
+                    break
+                seen[gid] = row
+        assert len(seen) == nn_glob
+        print("multi_gpu_check: world=%d %s" % (world, "OK" if ok else "FAILED"))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    ex.close(); g.close(); m.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

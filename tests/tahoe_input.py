@@ -206,7 +206,7 @@ def parse_xml(path):
 def write_xml(path, d):
     t = d["time"]
     L = ['<?xml version="1.0"?>', '<tahoe geometry_file="%s">' % d["geometry_file"],
-         '  <time num_steps="%d" output_inc="0" time_step="%.17g">' % (t["num_steps"], t["time_step"])]
+         '  <time num_steps="%d" output_inc="%d" time_step="%.17g">' % (t["num_steps"], d.get("output_inc", 0), t["time_step"])]
     for s in t["schedules"]:
         L.append("    <schedule_function><piecewise_linear>")
         L += ['      <OrderedPair x="%.17g" y="%.17g"/>' % p for p in s]
@@ -227,7 +227,9 @@ def write_xml(path, d):
     L.append("    </field>\n  </nodes>\n  <element_list>")
     e, m = d["element"], d["material"]
     mass = ' mass_type="%s"' % e["mass_type"] if e.get("mass_type", "automatic") != "automatic" else ""
-    L.append('    <%s field_name="displacement"%s>\n      <hexahedron/>' % (e["type"], mass))
+    L.append('    <%s field_name="displacement"%s>\n      <hexahedron/>' % (e.get("tag", e["type"]), mass))
+    if e.get("nodal_output"):
+        L.append('      <solid_element_nodal_output displacements="1"/>')
     small = e["type"] == "small_strain"
     blk = "small_strain_element_block" if small else "large_strain_element_block"
     mlist = "small_strain_material_3D" if small else "large_strain_material_3D"
@@ -240,10 +242,10 @@ def write_xml(path, d):
     h = m.get("hardening")
     if h:
         L.append("            <%s %s/>" % (h["type"], " ".join('%s="%.17g"' % (k, v) for k, v in h.items() if k != "type")))
-    L.append("          </%s>\n        </%s>\n      </%s>\n    </%s>\n  </element_list>" % (m["type"], mlist, blk, e["type"]))
+    L.append("          </%s>\n        </%s>\n      </%s>\n    </%s>\n  </element_list>" % (m["type"], mlist, blk, e.get("tag", e["type"])))
     s = d["solver"]
-    attrs = " ".join('%s="%s"' % (k, v) for k, v in s.items() if k not in ("type", "matrix"))
-    L.append("  <%s %s><%s/></%s>\n</tahoe>" % (s["type"], attrs, s["matrix"], s["type"]))
+    attrs = " ".join('%s="%s"' % (k, v) for k, v in s.items() if k not in ("type", "matrix", "matrix_attrs"))
+    L.append("  <%s %s><%s %s/></%s>\n</tahoe>" % (s["type"], attrs, s["matrix"], s.get("matrix_attrs", ""), s["type"]))
     with open(path, "w") as f:
         f.write("\n".join(L) + "\n")
 

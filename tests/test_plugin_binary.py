@@ -1,0 +1,131 @@
+"""The drop-in itself: a Tahoe executable built from the UNMODIFIED reference libraries + tahoe_b200/host (plugin classes and
+the registration patch) must, for inputs that differ from classic ones by the element / matrix tag only, reproduce the
+reference executable's nodal output.  The reference's own regression criterion is rel 1e-8 on the 12-digit .run files
+(benchmark_XML/comparator/src/ComparatorT.cpp:27-28); here 1e-9.
+
+CPU part (no GPU): the plugin binary validates the new tags against its parameter tree and then fails loudly because no
+CUDA device exists -- it must not fall back to the host element loop."""
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import tahoe_input as ti
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(REPO, "oracle", "_ref", "tahoe")
+PLUGIN_BIN = os.path.join(REPO, "tahoe_b200", "host", "_build", "tahoe_b200")
+needs_bins = pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(PLUGIN_BIN)),
+                                reason="reference / plugin executables are built in the authoring container (make -C tahoe_b200/host)")
+
+CLAMP = [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)]
+RAMP = [(0.0, 0.0), (1.0, 1.0)]
+
+
+def _cases():
+    kstv = {"type": "small_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25}
+    simo = {"type": "Simo_isotropic", "density": 1.0, "kappa": 1000.0, "mu": 5.0}
+    simo_soft = {"type": "Simo_isotropic", "density": 1.0, "E": 100.0, "nu": 0.25}
+    j2 = {"type": "Simo_J2", "density": 1.0, "E": 100.0, "nu": 0.25, "hardening": {"type": "linear_function", "a": 0.05, "b": 0.25}}
+    newton = {"type": "nonlinear_solver", "abs_tolerance": "1.0e-12", "rel_tolerance": "1.0e-12", "divergence_tolerance": "1.0e+03",
+              "max_iterations": "25", "matrix": "SPOOLES_matrix"}
+    pcg = dict(newton, matrix="CUDA_PCG_matrix", matrix_attrs='rel_tolerance="1.0e-13" max_iterations="20000"')
+    pull = CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.06}, {"nodeset": 2, "dof": 3, "type": "u", "schedule": 1, "value": 0.02}]
+    n = 5
+    dt = 0.25 * (1.0 / n) / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0)
+    return {
+        # explicit dynamics: device K1, Tahoe's own lumped mass / DiagonalMatrixT / nExplicitCD on the host
+        "explicit_tl_simo": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                              "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
+                              "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": simo,
+                              "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        # static Newton: device K1 + device K3 + device PCG against the reference's SPOOLES LU
+        "static_ss_kstv_pcg": ({"time": {"num_steps": 1, "time_step": 1.0, "schedules": [RAMP]}, "integrator": "static", "kbc": CLAMP,
+                                "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005}],
+                                "element": {"type": "small_strain"}, "material": kstv, "solver": newton}, pcg),
+        "static_tl_simo_pcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": newton}, pcg),
+        # J2: device K1 with history, Tahoe's host tangent + SPOOLES (non-symmetric tangent)
+        "static_ul_j2_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                             "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton}, None),
+    }
+
+
+def _write(work, name, desc, cuda, solver_override, n=5):
+    X, conn, ns = ti.structured_cube(n, jitter=0.15)
+    if not os.path.exists(os.path.join(work, "mesh.geom")):
+        ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
+    d = dict(desc, geometry_file="mesh.geom", output_inc=desc["time"]["num_steps"])
+    d["element"] = dict(desc["element"], nodal_output=True)
+    if cuda:
+        d["element"]["tag"] = "cuda_" + desc["element"]["type"]
+        if solver_override:
+            d["solver"] = solver_override
+    path = os.path.join(work, name + (".cuda" if cuda else ".ref") + ".xml")
+    ti.write_xml(path, d)
+    return path
+
+
+def _nodal_output(run_file):
+    """last 'Nodal data' table of a Tahoe text .run file -> array [nn, nvalues]"""
+    text = open(run_file).read()
+    block = text[text.rindex("Nodal data:"):]
+    rows = []
+    for line in block.splitlines():
+        f = line.split()
+        if len(f) >= 5 and re.match(r"^\d+$", f[0]) and re.match(r"^\d+$", f[1]):
+            rows.append([float(x) for x in f[2:]])
+        elif rows and not f:
+            break
+    return np.array(rows)
+
+
+def _run(binary, xml):
+    return subprocess.run([binary, "-f", os.path.basename(xml)], cwd=os.path.dirname(xml), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True, timeout=600)
+
+
+@needs_bins
+def test_plugin_binary_accepts_new_tags_and_fails_loudly_without_gpu():
+    from tahoe_b200 import capi
+    try:
+        if capi.device_count() > 0:
+            pytest.skip("a CUDA device is present")
+    except capi.Tb2Error:
+        pass
+    work = tempfile.mkdtemp(prefix="tb2_plugin_")
+    try:
+        desc, override = _cases()["static_ss_kstv_pcg"]
+        xml = _write(work, "case", desc, True, override, n=2)
+        r = _run(PLUGIN_BIN, xml)
+        assert "cuda_small_strain" not in r.stdout or "unrecognized" not in r.stdout.lower()
+        assert "CUDA error" in r.stdout or "no CUDA" in r.stdout or "cuda" in r.stdout.lower(), r.stdout[-2000:]
+        assert not os.path.exists(os.path.join(work, "case.cuda.io0.run"))  # nothing was computed
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(_cases()))
+def test_plugin_reproduces_reference_output(name):
+    desc, override = _cases()[name]
+    work = tempfile.mkdtemp(prefix="tb2_plugin_")
+    try:
+        ref_xml = _write(work, name, desc, False, None)
+        cuda_xml = _write(work, name, desc, True, override)
+        r0 = _run(REF_BIN, ref_xml)
+        assert r0.returncode == 0, r0.stdout[-2000:]
+        r1 = _run(PLUGIN_BIN, cuda_xml)
+        assert r1.returncode == 0 and "End Execution" in r1.stdout, r1.stdout[-3000:]
+        a = _nodal_output(os.path.join(work, name + ".ref.io0.run"))
+        b = _nodal_output(os.path.join(work, name + ".cuda.io0.run"))
+        assert a.shape == b.shape and a.shape[0] == 6 ** 3
+        assert np.abs(a).max() > 1e-6
+        assert np.abs(a - b).max() < 1e-9 * np.abs(a).max()
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
