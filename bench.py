@@ -193,6 +193,66 @@ def workload_config(n, gpus):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: PCG DOF-iterations/s (configs[2] scaled to one GPU's share)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_pcg(torch, capi, tmesh, local, n, iters, hbm_peak):
+    """small-strain elastic n^3 cube: device assembly (K3) of the CSR tangent, then `iters` Jacobi-PCG iterations (K6-K8)
+    with device-resident vectors.  Returns the "pcg" object of the JSON line."""
+    X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+    m = capi.Mesh(X, conn, device=local)
+    g = capi.Group(m, capi.SMALL_STRAIN, capi.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    t0 = time.perf_counter()
+    eqs = capi.Equations(m, code)
+    A = capi.Matrix(eqs)
+    m.synchronize()
+    t_struct = time.perf_counter() - t0
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    u0 = torch.zeros(X.shape, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    A.form_stiffness(g, u0)  # warm-up (includes the one-off colouring)
+    m.synchronize()
+    A.clear()
+    m.profile_begin()
+    A.form_stiffness(g, u0)
+    ms_cat, cnt_cat, _ = m.profile_end()
+    t_assembly_ms = float(ms_cat[5])
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 1e-3
+    b = torch.from_numpy(fext[eqs.eqnos() > 0]).to(dev)
+    x = torch.zeros_like(b)
+    torch.cuda.synchronize()
+    A.pcg(b, x, rtol=0.0, atol=0.0, max_iter=5)  # warm-up
+    x.zero_()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.profile_begin()
+    e0.record(stream)
+    it, rn = A.pcg(b, x, rtol=0.0, atol=0.0, max_iter=iters)
+    e1.record(stream)
+    ms_cat, cnt_cat, launches = m.profile_end()
+    ms = e0.elapsed_time(e1)
+    if it != iters or not np.isfinite(rn):
+        raise SystemExit("bench.py: PCG ran %d of %d iterations, |r| = %g" % (it, iters, rn))
+    spmv_ms = float(ms_cat[3]) / max(int(cnt_cat[3]), 1)
+    spmv_bytes = 12.0 * A.nnz + 12.0 * A.neq
+    iter_bytes = spmv_bytes + 128.0 * A.neq  # SURVEY.md 8d: unfused PCG iteration
+    out = {"metric": "PCG DOF-iters/s", "value": A.neq * iters / (ms * 1e-3), "unit": "DOF-iters/s", "iterations": iters,
+           "ms_per_iteration": ms / iters, "num_equations": A.neq, "nnz": A.nnz, "gpu_launches": int(launches),
+           "workload": "BASELINE.json configs[2] at one GPU's share: %d^3=%d-element small_strain + SSKStV cube, %d equations, CSR %d nnz "
+                       "assembled on the device (K3), Jacobi-PCG with device-resident vectors" % (n, n ** 3, A.neq, A.nnz),
+           "assembly": {"ms": t_assembly_ms, "elements_per_s": n ** 3 / (t_assembly_ms * 1e-3), "structure_build_s": t_struct},
+           "roofline": {"bound": "hbm", "kernel": "k_spmv<dot> (K6)", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": spmv_bytes / (spmv_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": spmv_ms,
+                        "share_of_iteration": spmv_ms * iters / ms, "traffic": None},
+           "iteration_hbm_frac": iter_bytes * iters / (ms * 1e-3) * 1e-9 / hbm_peak}
+    A.close(); eqs.close(); g.close(); m.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -335,6 +395,8 @@ def run_gpu_arm(args):
                 "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
                 "interface_exchange_ms": comm_ms if world > 1 else None,
                 "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None}
+        if world == 1 and not args.no_pcg:
+            line["pcg"] = run_pcg(torch, capi, tmesh, local, args.pcg_n, args.pcg_iters, hbm_peak)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -350,6 +412,9 @@ def main():
     ap.add_argument("--n", type=int, default=100, help="cube edge in elements per GPU (100 -> 1M elements, configs[1])")
     ap.add_argument("--impl", default="tahoe_b200", choices=["tahoe_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pcg", action="store_true", help="skip the PCG DOF-iters/s leg")
+    ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")
+    ap.add_argument("--pcg-iters", type=int, default=100)
     # per-element figures of K1 taken from the committed ncu capture (profiles/), see DESIGN.md
     ap.add_argument("--k1-flop-per-element", type=float, default=K1_FLOP_PER_ELEMENT)
     ap.add_argument("--k1-traffic-bytes", type=float, default=K1_TRAFFIC_BYTES)
