@@ -315,11 +315,16 @@ def run_gpu_arm(args):
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m.profile_begin()
+    if not args.no_profile:
+        m.profile_begin()
     ev0.record(stream)
     ex.run(dt, args.steps)
     ev1.record(stream)
-    ms_cat, cnt_cat, launches = m.profile_end()
+    if args.no_profile:  # experiment mode: no per-launch events inside the timed region (roofline objects are then meaningless)
+        m.synchronize()
+        ms_cat, cnt_cat, launches = np.ones(8), np.ones(8, np.int64), 0
+    else:
+        ms_cat, cnt_cat, launches = m.profile_end()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
@@ -328,7 +333,8 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: non-finite state after the timed region")
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(ne_local)], device="cuda", dtype=torch.float64)
-    kt = torch.tensor([ms_cat[0] / max(cnt_cat[0], 1), ms_cat[1] / max(cnt_cat[1], 1), ms_cat[6] / max(cnt_cat[6], 1)], device="cuda",
+    # per-STEP device time of each kernel = sum of its launches in the step (the slab pipeline launches K1 / K5 in chunks)
+    kt = torch.tensor([ms_cat[0] / args.steps, ms_cat[1] / args.steps, ms_cat[6] / args.steps], device="cuda",
                       dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,14 +381,14 @@ def run_gpu_arm(args):
         k1_flops = args.k1_flop_per_element * ne_local
         roof = {"bound": "hbm", "kernel": "k_internal_force<TL,SimoIso> (K1)", "achieved": k1_bytes / (k1_ms * 1e-3) * 1e-9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": args.k1_traffic_bytes, "peak_source": hbm_src,
-                "avg_launch_ms": k1_ms, "share_of_step": k1_ms * args.steps / ms,
+                "avg_launch_ms": k1_ms, "launches_per_step": int(cnt_cat[0]) // args.steps, "share_of_step": k1_ms * args.steps / ms,
                 "note": "K1 is FP64-pipe bound (arithmetic intensity ~%.0f flop/B >> machine balance): see roofline_fp64" % (args.k1_flop_per_element / 104.0)}
         roof64 = {"bound": "fp64", "kernel": roof["kernel"], "achieved": k1_flops / (k1_ms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
                   "frac": k1_flops / (k1_ms * 1e-3) * 1e-12 / fp64_peak, "flop_per_element": args.k1_flop_per_element,
                   "peak_source": "measured in this run (tb2_measure_fp64_peak: dependent DFMA chains)"}
         k5_bytes = (192.0 + 24.0) * nn_local  # d,v,a R+W, fext, minv + fint write
         roof_k5 = {"bound": "hbm", "kernel": "k_cd_node_update (gather + K5)", "achieved": k5_bytes / (k5_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": k5_bytes / (k5_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": k5_ms, "share_of_step": k5_ms * args.steps / ms,
+                   "frac": k5_bytes / (k5_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": k5_ms, "launches_per_step": int(cnt_cat[1]) // args.steps, "share_of_step": k5_ms * args.steps / ms,
                    "note": "algorithmic 216 B/node; the kernel also re-reads the 192 B/element force scratch"}
         step_bytes = 104.0 * ne_local + 192.0 * nn_local
         line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -392,6 +398,9 @@ def run_gpu_arm(args):
                         "d2h_bytes_per_step": int(72 * nn_local * world), "steps": e2e_steps, "ms_per_step": float(te.item()) / e2e_steps,
                         "api": "tb2_explicit_step_host (pinned host d,v,a in and out every step)"},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_fp64": roof64, "roofline_k5": roof_k5,
+                "schedule": ("serial" if world > 1 or os.environ.get("TB2_PIPELINE", "1") == "0" else
+                             "slab pipeline: K1 chunks on one stream overlap K5 chunks on a second one, so avg_launch_ms (sum of a kernel's chunk "
+                             "launches per step, measured while the other kernel co-runs) and the shares add up to more than the step"),
                 "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
                 "interface_exchange_ms": comm_ms if world > 1 else None,
                 "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None}
@@ -413,6 +422,7 @@ def main():
     ap.add_argument("--impl", default="tahoe_b200", choices=["tahoe_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the PCG DOF-iters/s leg")
+    ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")
     ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")
     ap.add_argument("--pcg-iters", type=int, default=100)
     # per-element figures of K1 taken from the committed ncu capture (profiles/), see DESIGN.md

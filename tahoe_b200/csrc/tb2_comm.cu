@@ -91,6 +91,28 @@ __global__ void k_unpack(int64_t n_if, const int* __restrict__ nodes, const int*
     nodal[3 * (int64_t)nodes[k] + i] = packed[3 * (int64_t)slots[k] + i];
 }
 
+// equation-space variant: v[neq] holds values of the active dofs only (prescribed dofs contribute / receive nothing)
+__global__ void k_pack_eq(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots, const int* __restrict__ eqnos,
+                          const double* __restrict__ v, double* __restrict__ packed)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_if) return;
+    const int64_t k = t / 3;
+    const int i = (int)(t % 3);
+    const int eq = eqnos[3 * (int64_t)nodes[k] + i];
+    packed[3 * (int64_t)slots[k] + i] = eq > 0 ? v[eq - 1] : 0.0;
+}
+__global__ void k_unpack_eq(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots, const int* __restrict__ eqnos,
+                            const double* __restrict__ packed, double* __restrict__ v)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_if) return;
+    const int64_t k = t / 3;
+    const int i = (int)(t % 3);
+    const int eq = eqnos[3 * (int64_t)nodes[k] + i];
+    if (eq > 0) v[eq - 1] = packed[3 * (int64_t)slots[k] + i];
+}
+
 bool comm_active(tb2_mesh* m) { return m->comm && m->comm->nranks > 1 && m->comm->n_glob > 0; }
 const unsigned char* comm_owned_mask(tb2_mesh* m) { return m->comm ? m->comm->owned.p : nullptr; }
 
@@ -100,6 +122,22 @@ int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n)
     if (!m->comm || m->comm->nranks == 1) return TB2_OK;
     const int r = g_nccl.AllReduce(d_vals, d_vals, (size_t)n, kNcclFloat64, kNcclSum, m->comm->comm, m->stream);
     return r ? nccl_fail(r, "ncclAllReduce(scalars)") : TB2_OK;
+}
+
+// v[neq] += contributions of the other sharers on interface equations (A_loc p, diagonal) -- same packed all-reduce
+int comm_sum_interface_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec)
+{
+    Comm* c = m->comm;
+    if (!c || c->nranks == 1 || c->n_glob == 0) return TB2_OK;
+    ProfScope ps(m, kProfComm, 2);
+    TB2_CUDA(cudaMemsetAsync(c->packed.p, 0, 3 * c->n_glob * sizeof(double), m->stream));
+    const int T = 256;
+    if (c->n_if) k_pack_eq<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, d_eqvec, c->packed.p);
+    const int r = g_nccl.AllReduce(c->packed.p, c->packed.p, (size_t)(3 * c->n_glob), kNcclFloat64, kNcclSum, c->comm, m->stream);
+    if (r) return nccl_fail(r, "ncclAllReduce(interface, eq)");
+    if (c->n_if) k_unpack_eq<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, c->packed.p, d_eqvec);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
 }
 
 } // namespace tb2

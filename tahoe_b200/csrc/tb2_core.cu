@@ -2,6 +2,7 @@
 #include <cub/cub.cuh>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "tb2_internal.h"
@@ -68,6 +69,49 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
         a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
     }
     out[blockIdx.x * (int64_t)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// slab pipeline bookkeeping (tb2_explicit.cu): contiguous element / node index chunks and their dependency ranges
+static void build_pipeline(tb2_mesh* m, const int32_t* h_conn, int sm_count)
+{
+    const int64_t wave = (int64_t)sm_count * 3 * 128; // elements of one resident wave of K1 (3 CTAs of 128 threads per SM)
+    // measured on a 1M-element cube (r01): 4 chunks of ~4.4 waves beat 9 chunks of 2 waves (launch tails) and 3 chunks (too little
+    // overlap): keep chunks near 4-5 waves, at least 4 and at most 32 of them
+    int64_t C = m->ne / (9 * wave / 2);
+    if (C < 4) C = 4;
+    if (C > 32) C = 32;
+    if (const char* s = getenv("TB2_PIPE_CHUNKS")) { // experiment knob
+        const int want = atoi(s);
+        if (want >= 1) C = want;
+    }
+    int64_t chunk = ((m->ne + C - 1) / C + wave - 1) / wave * wave;
+    C = (m->ne + chunk - 1) / chunk;
+    if (C < 3) C = 1;
+    m->pipe_e0.assign(C + 1, 0);
+    m->pipe_n0.assign(C + 1, 0);
+    for (int64_t c = 0; c <= C; c++) {
+        m->pipe_e0[c] = C == 1 ? (c ? m->ne : 0) : (c * chunk < m->ne ? c * chunk : m->ne);
+        m->pipe_n0[c] = m->nn * c / C;
+    }
+    m->pipe_emax_of_nc.assign(C, -1);
+    m->pipe_nmax_of_ec.assign(C, -1);
+    if (C == 1) return;
+    for (int64_t e = 0; e < m->ne; e++) {
+        const int ce = (int)(e / chunk);
+        for (int a = 0; a < 8; a++) {
+            const int64_t n = h_conn[8 * e + a];
+            int nc = (int)(n * C / m->nn);
+            while (nc + 1 < C && m->pipe_n0[nc + 1] <= n) nc++;
+            while (nc > 0 && m->pipe_n0[nc] > n) nc--;
+            if (ce > m->pipe_emax_of_nc[nc]) m->pipe_emax_of_nc[nc] = ce;
+            if (nc > m->pipe_nmax_of_ec[ce]) m->pipe_nmax_of_ec[ce] = nc;
+        }
+    }
+    // both streams run their chunks in index order, so a dependency on "all chunks <= k" is a wait on chunk k: make the maps monotone
+    for (int64_t c = 1; c < C; c++) {
+        if (m->pipe_emax_of_nc[c] < m->pipe_emax_of_nc[c - 1]) m->pipe_emax_of_nc[c] = m->pipe_emax_of_nc[c - 1];
+        if (m->pipe_nmax_of_ec[c] < m->pipe_nmax_of_ec[c - 1]) m->pipe_nmax_of_ec[c] = m->pipe_nmax_of_ec[c - 1];
+    }
 }
 
 } // namespace tb2
@@ -199,6 +243,9 @@ int tb2_mesh_create(int device, int64_t nn, int64_t ne, const int32_t* h_conn, c
         M_CUDA(cudaStreamSynchronize(m->stream));
     }
 #undef M_CUDA
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    build_pipeline(m, h_conn, prop.multiProcessorCount);
     *out = m;
     return TB2_OK;
 }
@@ -211,6 +258,17 @@ int tb2_mesh_destroy(tb2_mesh* m)
     DeviceGuard g(m->device);
     if (m->comm) tb2_comm_destroy(m);
     cudaStreamSynchronize(m->stream);
+    if (m->stream2) {
+        cudaStreamSynchronize(m->stream2);
+        cudaStreamDestroy(m->stream2);
+    }
+    for (auto& r : m->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : m->ev_k1) cudaEventDestroy(e);
+    for (auto e : m->ev_k5) cudaEventDestroy(e);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     cudaStreamDestroy(m->stream);
     delete m;
     return TB2_OK;
@@ -241,11 +299,7 @@ int tb2_profile_begin(tb2_mesh* m)
 {
     TB2_ARG(m);
     DeviceGuard g(m->device);
-    for (auto& r : m->prof) {
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
-    }
-    m->prof.clear();
+    m->prof_used = 0;
     m->prof_on = true;
     m->launches = 0;
     return TB2_OK;
@@ -258,16 +312,15 @@ int tb2_profile_end(tb2_mesh* m, double* h_ms, int64_t* h_count, int64_t* launch
     m->prof_on = false;
     double ms[kProfNumCat] = {0};
     int64_t cnt[kProfNumCat] = {0};
-    for (auto& r : m->prof) {
+    for (size_t i = 0; i < m->prof_used; i++) {
+        const ProfRec& r = m->prof[i];
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
             ms[r.cat] += t;
             cnt[r.cat]++;
         }
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
     }
-    m->prof.clear();
+    m->prof_used = 0;
     for (int c = 0; c < kProfNumCat; c++) {
         if (h_ms) h_ms[c] = ms[c];
         if (h_count) h_count[c] = cnt[c];

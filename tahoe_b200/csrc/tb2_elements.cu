@@ -21,7 +21,7 @@
 namespace tb2 {
 
 struct ElemArgs {
-    int64_t ne, stride;
+    int64_t e_begin, ne, stride; // elements [e_begin, ne)
     const int* conn;  // [8][stride]
     const double* X;  // [nn][3]
     const double* u;  // [nn][3]
@@ -42,7 +42,7 @@ TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
 template <int FORM, int MAT, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
 {
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t e = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= p.ne) return;
     int n[8];
 #pragma unroll
@@ -271,8 +271,16 @@ J2Hist group_hist(tb2_group* g)
     return h;
 }
 
+int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st);
+
 // element sweep only: fe scratch <- element forces (used by the fused explicit path too)
 int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration)
+{
+    return launch_element_forces_range(g, d_u, d_ul, iteration, 0, g->mesh->ne, g->mesh->stream);
+}
+
+// elements [e0, e1) on stream st (the slab pipeline of tb2_explicit.cu launches the sweep in chunks)
+int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st)
 {
     tb2_mesh* m = g->mesh;
     force_kernel_t k = pick_force_kernel(g->form, g->mat.kind);
@@ -285,7 +293,8 @@ int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, i
         return TB2_ERR_ARG;
     }
     ElemArgs p;
-    p.ne = m->ne;
+    p.e_begin = e0;
+    p.ne = e1;
     p.stride = m->stride;
     p.conn = m->conn.p;
     p.X = m->X.p;
@@ -298,8 +307,8 @@ int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, i
     p.status = g->status.p;
     const int T = 128;
     {
-        ProfScope ps(m, kProfForce);
-        k<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(p);
+        ProfScope ps(m, kProfForce, 1, st);
+        k<<<(unsigned)((e1 - e0 + T - 1) / T), T, 0, st>>>(p);
     }
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;

@@ -8,12 +8,15 @@
 // On the device this is two launches per step: the element sweep (K1) and one node kernel that gathers the element
 // forces, forms R, applies M^-1, the corrector and -- when another step follows -- the next step's predictor, so d, v, a
 // are read and written once per step (192 B/node/step).
+#include <cstdlib>
+
 #include "tb2_internal.h"
 
 namespace tb2 {
 
 int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration);
 int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
+int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st);
 bool comm_active(tb2_mesh* m);
 
 // nExplicitCD::Predictor (nExplicitCD.cpp:72-96) / Corrector (:98-139) with explicit roundings, so that the stand-alone and
@@ -52,14 +55,14 @@ __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, d
 // a_in is the acceleration left by the predictor (0 on every dof), kept as an input for generality (a += upd).
 // GATHER = false: fint already holds the (interface-summed) internal force (multi-GPU path)
 template <bool GATHER, bool NEXT_PREDICTOR>
-__global__ void __launch_bounds__(256) k_cd_node_update(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+__global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                                        const double* __restrict__ fe, int64_t stride, double dt, double fext_scale,
                                                        double next_value_scale, const double* __restrict__ fext,
                                                        const double* __restrict__ minv, const unsigned char* __restrict__ code,
                                                        const double* __restrict__ bcval, double* __restrict__ d,
                                                        double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint)
 {
-    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n = n_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= nn) return;
     double f[3] = {0.0, 0.0, 0.0};
     if (GATHER) {
@@ -121,6 +124,78 @@ __global__ void k_initial_acceleration(int64_t n, const double* __restrict__ fex
 
 using namespace tb2;
 
+// Slab pipeline (single GPU).  K1 is FP64-pipe bound and K5 is HBM bound, and K5 of a node chunk only needs K1 of the element
+// chunks touching it, so the two kernels of a step -- and of consecutive steps -- are overlapped: element chunks run in index
+// order on the mesh stream, node chunks in index order on a second stream, ordered by events:
+//   K5(s, nc) waits for K1(s, last element chunk touching nc);   K1(s+1, ec) waits for K5(s, last node chunk touched by ec).
+// The same two conditions cover the write-after-read hazards on d (K5 writes what K1 reads) and on the force scratch.
+// Arithmetic and summation order are those of the serial schedule: results are bitwise identical (tested).
+static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
+{
+    tb2_group* g = ex->group;
+    tb2_mesh* m = g->mesh;
+    const int C = (int)m->pipe_e0.size() - 1;
+    const int64_t ndof = 3 * m->nn;
+    const int T = 256;
+    if (!m->stream2) {
+        TB2_CUDA(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+        m->ev_k1.resize(C);
+        m->ev_k5.resize(C);
+        for (int c = 0; c < C; c++) {
+            TB2_CUDA(cudaEventCreateWithFlags(&m->ev_k1[c], cudaEventDisableTiming));
+            TB2_CUDA(cudaEventCreateWithFlags(&m->ev_k5[c], cudaEventDisableTiming));
+        }
+        TB2_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    {
+        ProfScope ps(m, kProfPredictor);
+        k_cd_predictor<<<(unsigned)((ndof + T - 1) / T), T, 0, m->stream>>>(ndof, dt, ex->d.p, ex->v.p, ex->a.p, ex->bccode.p, ex->bcval.p,
+                                                                           vs ? vs[0] : 1.0);
+    }
+    TB2_CUDA(cudaEventRecord(m->ev_join, m->stream));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_join, 0));
+    for (int s = 0; s < nsteps; s++) {
+        const double fsc = fs ? fs[s] : 1.0;
+        int nc = 0;
+        for (int c = 0; c < C; c++) {
+            if (s > 0 && m->pipe_nmax_of_ec[c] >= 0) TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_k5[m->pipe_nmax_of_ec[c]], 0));
+            TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, m->pipe_e0[c], m->pipe_e0[c + 1], m->stream));
+            TB2_CUDA(cudaEventRecord(m->ev_k1[c], m->stream));
+            for (; nc < C && m->pipe_emax_of_nc[nc] <= c; nc++) {
+                const int64_t n0 = m->pipe_n0[nc], n1 = m->pipe_n0[nc + 1];
+                if (m->pipe_emax_of_nc[nc] >= 0) TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_k1[m->pipe_emax_of_nc[nc]], 0));
+                if (n1 > n0) {
+                    ProfScope ps(m, kProfNodeUpdate, 1, m->stream2);
+                    const unsigned nb = (unsigned)((n1 - n0 + T - 1) / T);
+                    if (s + 1 < nsteps)
+                        k_cd_node_update<true, true><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                                                                              vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
+                                                                              ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
+                    else
+                        k_cd_node_update<true, false><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                                                                               ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
+                                                                               ex->v.p, ex->a.p, ex->fint.p);
+                }
+                TB2_CUDA(cudaEventRecord(m->ev_k5[nc], m->stream2));
+            }
+        }
+    }
+    TB2_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+static bool pipeline_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char* s = getenv("TB2_PIPELINE");
+        on = (s && s[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
 {
     tb2_group* g = ex->group;
@@ -129,6 +204,7 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
     const int T = 256;
     const unsigned nbn = (unsigned)((m->nn + T - 1) / T), nbd = (unsigned)((ndof + T - 1) / T);
     if (nsteps <= 0) return TB2_OK;
+    if (!comm_active(m) && m->pipe_e0.size() > 2 && nsteps > 1 && pipeline_enabled()) return explicit_steps_pipelined(ex, dt, nsteps, fs, vs);
     {
         ProfScope ps(m, kProfPredictor);
         k_cd_predictor<<<nbd, T, 0, m->stream>>>(ndof, dt, ex->d.p, ex->v.p, ex->a.p, ex->bccode.p, ex->bcval.p, vs ? vs[0] : 1.0);
@@ -143,21 +219,21 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
             TB2_CHECK(tb2_comm_sum_interface(m, ex->fint.p));
             ProfScope ps(m, kProfNodeUpdate);
             if (s + 1 < nsteps)
-                k_cd_node_update<false, true><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                k_cd_node_update<false, true><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
                                                                        vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
                                                                        ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
             else
-                k_cd_node_update<false, false><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                k_cd_node_update<false, false><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
                                                                         ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
                                                                         ex->v.p, ex->a.p, ex->fint.p);
         } else if (s + 1 < nsteps) {
             ProfScope ps(m, kProfNodeUpdate);
-            k_cd_node_update<true, true><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+            k_cd_node_update<true, true><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
                                                             vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p,
                                                             ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
         } else {
             ProfScope ps(m, kProfNodeUpdate);
-            k_cd_node_update<true, false><<<nbn, T, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+            k_cd_node_update<true, false><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
                                                              ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p,
                                                              ex->a.p, ex->fint.p);
         }

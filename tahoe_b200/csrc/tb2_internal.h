@@ -99,8 +99,16 @@ struct tb2_mesh {
     tb2::DevBuf<int> colour_elems;      // elements sorted by colour
     std::vector<int64_t> colour_start;  // [ncolours+1]
     tb2::Comm* comm = nullptr;
+    // slab pipeline of the explicit step (tb2_explicit.cu): element chunks [pipe_e0[c], pipe_e0[c+1]), node chunks likewise;
+    // pipe_emax_of_nc[c] = last element chunk touching node chunk c, pipe_nmax_of_ec[c] = last node chunk touched by element chunk c
+    std::vector<int64_t> pipe_e0, pipe_n0;
+    std::vector<int> pipe_emax_of_nc, pipe_nmax_of_ec;
+    cudaStream_t stream2 = nullptr;
+    std::vector<cudaEvent_t> ev_k1, ev_k5;
+    cudaEvent_t ev_join = nullptr;
     bool prof_on = false;
-    std::vector<tb2::ProfRec> prof;
+    std::vector<tb2::ProfRec> prof; // event pool
+    size_t prof_used = 0;
     uint64_t launches = 0;
 };
 
@@ -109,21 +117,25 @@ namespace tb2 {
 struct ProfScope {
     tb2_mesh* m;
     int idx = -1;
-    ProfScope(tb2_mesh* mesh, int cat, int n = 1) : m(mesh)
+    cudaStream_t st;
+    ProfScope(tb2_mesh* mesh, int cat, int n = 1, cudaStream_t stream = nullptr) : m(mesh), st(stream ? stream : mesh->stream)
     {
         m->launches += (uint64_t)n;
         if (!m->prof_on) return;
-        ProfRec r;
-        r.cat = cat;
-        cudaEventCreate(&r.a);
-        cudaEventCreate(&r.b);
-        cudaEventRecord(r.a, m->stream);
-        m->prof.push_back(r);
-        idx = (int)m->prof.size() - 1;
+        if (m->prof_used == m->prof.size()) { // grow the event pool (events are reused across profile_begin/end)
+            ProfRec r;
+            r.cat = cat;
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+            m->prof.push_back(r);
+        }
+        idx = (int)m->prof_used++;
+        m->prof[idx].cat = cat;
+        cudaEventRecord(m->prof[idx].a, st);
     }
     ~ProfScope()
     {
-        if (idx >= 0) cudaEventRecord(m->prof[idx].b, m->stream);
+        if (idx >= 0) cudaEventRecord(m->prof[idx].b, st);
     }
 };
 } // namespace tb2
@@ -157,12 +169,15 @@ struct tb2_matrix {
     tb2::DevBuf<int> adj;         // neighbour node ids
     tb2::DevBuf<int> adj_coloff;  // per adjacency entry: column offset of the neighbour's first active dof inside the node's rows
     tb2::DevBuf<int> elem_adjpos; // [64][stride]: position of node b in node a's adjacency list
+    tb2::DevBuf<int> grp;          // SpMV row groups: first row | (rows-1) << 30
+    int64_t ngroups = 0;
     tb2::DevBuf<long long> rowptr; // [neq+1]
     tb2::DevBuf<int> colind;      // [nnz]
     tb2::DevBuf<double> val;      // [nnz]
     tb2::DevBuf<double> dinv, r, z, p, q; // PCG work vectors [neq]
     tb2::DevBuf<double> scal;     // reduction scalars
     tb2::DevBuf<double> partial;  // per-block partial sums
+    tb2::DevBuf<unsigned char> eq_owned; // multi-GPU: 1 if this rank owns the equation's node (dot products count it once)
 };
 
 struct tb2_explicit {

@@ -147,34 +147,96 @@ __global__ void k_elem_adjpos(int64_t ne, int64_t stride, const int* __restrict_
     pos[(int64_t)ab * stride + e] = lo;
 }
 
-// ---- K6: y = A x, one warp per row (MSRMatrixT::Multx, MSRMatrixT.cpp:385-420) ---------------------------------------
-// optional fused dot: partial[block] = sum over the block's rows of x[row]*y[row] (p.Ap of CG)
+// ---- K6: y = A x (MSRMatrixT::Multx, MSRMatrixT.cpp:385-420) ------------------------------------------------------------
+// One warp per ROW GROUP: the <= 3 rows of a node share their column pattern (equation numbering is node-major), so the warp
+// reads colind and gathers x once and feeds up to three rows: 8 B/nnz values + 4/3 B/nnz indices instead of 12 B/nnz.
+// A matrix without node structure (tb2_matrix_create_csr) uses groups of one row.  Persistent grid: warp w of block b walks
+// groups b*W+w, +gridDim*W, ...; the p.Ap partial of a block is accumulated in that fixed order (deterministic).
+// grp[g] = first row | (rows-1) << 30.
 template <bool WITH_DOT>
-__global__ void __launch_bounds__(256) k_spmv(int64_t n, const long long* __restrict__ rowptr, const int* __restrict__ colind,
-                                              const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
-                                              double* __restrict__ partial, const int* __restrict__ done)
+__global__ void __launch_bounds__(256) k_spmv(int64_t ngroups, const int* __restrict__ grp, const long long* __restrict__ rowptr,
+                                              const int* __restrict__ colind, const double* __restrict__ val, const double* __restrict__ x,
+                                              double* __restrict__ y, double* __restrict__ partial, const int* __restrict__ done)
 {
     if (WITH_DOT && done && *done) return;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + wib;
-    double s = 0.0;
-    if (row < n) {
-        const long long k0 = rowptr[row], k1 = rowptr[row + 1];
-        for (long long k = k0 + lane; k < k1; k += 32) s += val[k] * __ldg(x + colind[k]);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
+    double dot = 0.0;
+    for (int64_t g = blockIdx.x * (int64_t)W + wib; g < ngroups; g += (int64_t)gridDim.x * W) {
+        const unsigned packed = (unsigned)__ldg(grp + g);
+        const int64_t r0 = packed & 0x3fffffffu;
+        const int nr = (int)(packed >> 30) + 1;
+        const long long k0 = __ldg(rowptr + r0);
+        const int len = (int)(__ldg(rowptr + r0 + 1) - k0);
+        const double* v0 = val + k0;
+        const int* c0 = colind + k0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (nr == 3) {
+            for (int k = lane; k < len; k += 32) {
+                const double xv = __ldg(x + __ldcs(c0 + k));
+                s0 += __ldcs(v0 + k) * xv;
+                s1 += __ldcs(v0 + len + k) * xv;
+                s2 += __ldcs(v0 + 2 * len + k) * xv;
+            }
+        } else {
+            for (int k = lane; k < len; k += 32) {
+                const double xv = __ldg(x + __ldcs(c0 + k));
+                s0 += __ldcs(v0 + k) * xv;
+                if (nr > 1) s1 += __ldcs(v0 + len + k) * xv;
+            }
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) y[row] = s;
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            y[r0] = s0;
+            if (nr > 1) y[r0 + 1] = s1;
+            if (nr > 2) y[r0 + 2] = s2;
+            if (WITH_DOT) {
+                dot += s0 * x[r0];
+                if (nr > 1) dot += s1 * x[r0 + 1];
+                if (nr > 2) dot += s2 * x[r0 + 2];
+            }
+        }
     }
     if (WITH_DOT) {
         __shared__ double sh[8];
-        if (lane == 0) sh[wib] = row < n ? s * x[row] : 0.0;
+        if (lane == 0) sh[wib] = dot;
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+            for (int w = 0; w < W; w++) t += sh[w];
             partial[blockIdx.x] = t;
         }
     }
+}
+// row groups of a mesh-derived matrix: one group per node with active dofs (flag/scan/compact); generic: one per row
+__global__ void k_group_flags(int64_t nn, const int* __restrict__ eqnos, int* __restrict__ flag)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n < nn) flag[n] = (eqnos[3 * n] > 0 || eqnos[3 * n + 1] > 0 || eqnos[3 * n + 2] > 0) ? 1 : 0;
+}
+__global__ void k_group_fill(int64_t nn, const int* __restrict__ eqnos, const int* __restrict__ flag, const int* __restrict__ excl,
+                             int* __restrict__ grp)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nn || !flag[n]) return;
+    int first = 0, cnt = 0;
+    for (int i = 0; i < 3; i++) {
+        const int eq = eqnos[3 * n + i];
+        if (eq > 0) {
+            if (!cnt) first = eq - 1;
+            cnt++;
+        }
+    }
+    grp[excl[n]] = (int)((unsigned)first | ((unsigned)(cnt - 1) << 30));
+}
+__global__ void k_group_identity(int64_t n, int* __restrict__ grp)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) grp[i] = (int)i;
 }
 
 // deterministic two-stage reductions -------------------------------------------------------------------------------
@@ -220,7 +282,8 @@ __global__ void __launch_bounds__(1024) k_reduce_pap(int nparts, const double* _
 __global__ void __launch_bounds__(256) k_pcg_update(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl,
                                                    const double* __restrict__ p, const double* __restrict__ q,
                                                    const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-                                                   double* __restrict__ z, double* __restrict__ partial)
+                                                   double* __restrict__ z, double* __restrict__ partial,
+                                                   const unsigned char* __restrict__ w = nullptr)
 {
     if (ctl->done) return;
     __shared__ double sh[32];
@@ -232,8 +295,10 @@ __global__ void __launch_bounds__(256) k_pcg_update(int64_t n, const double* __r
         const double zi = dinv[i] * ri;
         r[i] = ri;
         z[i] = zi;
-        rz += ri * zi;
-        rr += ri * ri;
+        if (!w || w[i]) {
+            rz += ri * zi;
+            rr += ri * ri;
+        }
     }
     rz = block_sum(rz, sh);
     rr = block_sum(rr, sh);
@@ -285,7 +350,8 @@ __global__ void k_extract_dinv(int64_t n, const long long* __restrict__ rowptr, 
 }
 __global__ void __launch_bounds__(256) k_pcg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q,
                                                  const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ z,
-                                                 double* __restrict__ p, double* __restrict__ partial)
+                                                 double* __restrict__ p, double* __restrict__ partial,
+                                                 const unsigned char* __restrict__ w = nullptr)
 {
     __shared__ double sh[32];
     double rz = 0.0, rr = 0.0;
@@ -295,8 +361,10 @@ __global__ void __launch_bounds__(256) k_pcg_init(int64_t n, const double* __res
         r[i] = ri;
         z[i] = zi;
         p[i] = zi;
-        rz += ri * zi;
-        rr += ri * ri;
+        if (!w || w[i]) {
+            rz += ri * zi;
+            rr += ri * ri;
+        }
     }
     rz = block_sum(rz, sh);
     rr = block_sum(rr, sh);
@@ -335,7 +403,81 @@ __global__ void k_eq_scatter_add(int64_t neq, const int* __restrict__ eq_node, d
     if (i < neq) nodal[eq_node[i]] += s * v[i];
 }
 
+// ---- multi-GPU PCG pieces (sub-domain matrices) ------------------------------------------------------------------
+// weighted dot: partial[block] = sum_i w_i a_i b_i (w = 1 on equations whose node this rank owns)
+__global__ void __launch_bounds__(256) k_wdot(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                             const unsigned char* __restrict__ w, double* __restrict__ partial, const PcgCtl* ctl)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (w[i]) s += a[i] * b[i];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// red[k] = sum of the k-th interleaved stream of partials (k < nstreams <= 2)
+__global__ void __launch_bounds__(1024) k_sum_partials(int nparts, int nstreams, const double* __restrict__ partial, double* __restrict__ red,
+                                                      const PcgCtl* ctl)
+{
+    if (ctl && ctl->done) return;
+    __shared__ double sh[32];
+    for (int k = 0; k < nstreams; k++) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) v += partial[nstreams * i + k];
+        v = block_sum(v, sh);
+        if (threadIdx.x == 0) red[k] = v;
+        __syncthreads();
+    }
+}
+__global__ void k_scalars_init(const double* red, double* scal, PcgCtl* ctl, double rtol, double atol, int max_iter)
+{
+    const double rnorm = sqrt(red[1]);
+    scal[kRZ] = red[0];
+    scal[kR0] = rnorm;
+    scal[kRNORM] = rnorm;
+    ctl->iters = 0;
+    ctl->breakdown = 0;
+    ctl->done = (!(rnorm > atol) || !(rnorm > rtol * rnorm) || max_iter <= 0) ? 1 : 0;
+}
+__global__ void k_scalars_alpha(const double* red, double* scal, PcgCtl* ctl)
+{
+    if (ctl->done) return;
+    const double v = red[0];
+    scal[kPAP] = v;
+    if (!(v > 0.0)) { ctl->breakdown = 1; ctl->done = 1; scal[kALPHA] = 0.0; }
+    else scal[kALPHA] = scal[kRZ] / v;
+}
+__global__ void k_scalars_beta(const double* red, double* scal, PcgCtl* ctl, double rtol, double atol, int max_iter)
+{
+    if (ctl->done) return;
+    const double rnorm = sqrt(red[1]);
+    scal[kBETA] = red[0] / scal[kRZ];
+    scal[kRZ] = red[0];
+    scal[kRNORM] = rnorm;
+    ctl->iters += 1;
+    if (!(rnorm > atol) || !(rnorm > rtol * scal[kR0]) || ctl->iters >= max_iter) ctl->done = 1;
+}
+__global__ void k_eq_owned(int64_t neq, const int* __restrict__ eq_node, const unsigned char* __restrict__ node_owned, unsigned char* __restrict__ w)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < neq) w[i] = node_owned[eq_node[i] / 3];
+}
+__global__ void k_invert_diag(int64_t n, double* __restrict__ d)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = d[i];
+    d[i] = fabs(x) > 1.0e-12 ? 1.0 / x : x;
+}
+
+bool comm_active(tb2_mesh* m);
+const unsigned char* comm_owned_mask(tb2_mesh* m);
+int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n);
+int comm_sum_interface_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec);
+
 static const int kReduceBlocks = 148 * 8;
+static const int kSpmvBlocks = 148 * 8; // persistent: 8 CTAs of 256 threads per SM
 
 } // namespace tb2
 
@@ -420,7 +562,7 @@ int tb2_equations_scatter_add(const tb2_equations* q, double scale, const double
 
 int tb2_matrix_create(tb2_equations* q, tb2_matrix** out)
 {
-    TB2_ARG(q && out && q->neq > 0);
+    TB2_ARG(q && out && q->neq > 0 && q->neq < (1LL << 30));
     tb2_mesh* m = q->mesh;
     DeviceGuard dg(m->device);
     tb2_matrix* A = new tb2_matrix;
@@ -483,8 +625,21 @@ int tb2_matrix_create(tb2_equations* q, tb2_matrix** out)
     A_CUDA(A->p.alloc(neq));
     A_CUDA(A->q.alloc(neq));
     A_CUDA(A->scal.alloc(kNumScal + 4)); // + PcgCtl
-    const int64_t spmv_blocks = (neq + 7) / 8;
-    A_CUDA(A->partial.alloc((spmv_blocks > 2 * kReduceBlocks ? spmv_blocks : 2 * kReduceBlocks) + 8));
+    A_CUDA(A->partial.alloc(2 * kReduceBlocks + kSpmvBlocks + 8));
+    {   // row groups: one per node with active dofs
+        DevBuf<int> gflag, gexcl;
+        A_CUDA(gflag.alloc(nn + 1));
+        A_CUDA(gexcl.alloc(nn + 1));
+        A_CUDA(cudaMemsetAsync(gflag.p + nn, 0, sizeof(int), m->stream));
+        k_group_flags<<<(unsigned)((nn + 255) / 256), 256, 0, m->stream>>>(nn, q->eqnos.p, gflag.p);
+        A_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, gflag.p, gexcl.p, (int)(nn + 1), m->stream));
+        int ng = 0;
+        A_CUDA(cudaMemcpyAsync(&ng, gexcl.p + nn, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        A_CUDA(cudaStreamSynchronize(m->stream));
+        A->ngroups = ng;
+        A_CUDA(A->grp.alloc(ng > 0 ? ng : 1));
+        k_group_fill<<<(unsigned)((nn + 255) / 256), 256, 0, m->stream>>>(nn, q->eqnos.p, gflag.p, gexcl.p, A->grp.p);
+    }
     A_CUDA(cudaGetLastError());
     A_CUDA(cudaStreamSynchronize(m->stream));
 #undef A_CUDA
@@ -514,8 +669,14 @@ static int alloc_pcg_work(tb2_matrix* A)
     TB2_CUDA(A->p.alloc(neq));
     TB2_CUDA(A->q.alloc(neq));
     TB2_CUDA(A->scal.alloc(kNumScal + 4));
-    const int64_t spmv_blocks = (neq + 7) / 8;
-    TB2_CUDA(A->partial.alloc((spmv_blocks > 2 * kReduceBlocks ? spmv_blocks : 2 * kReduceBlocks) + 8));
+    TB2_CUDA(A->partial.alloc(2 * kReduceBlocks + kSpmvBlocks + 8));
+    if (!A->grp.p) { // no node structure known: one row per group
+        TB2_ARG(neq < (1LL << 30));
+        TB2_CUDA(A->grp.alloc(neq));
+        A->ngroups = neq;
+        k_group_identity<<<(unsigned)((neq + 255) / 256), 256, 0, A->ctx->stream>>>(neq, A->grp.p);
+        TB2_CUDA(cudaGetLastError());
+    }
     return TB2_OK;
 }
 
@@ -621,7 +782,7 @@ int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y)
     tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     ProfScope ps(m, kProfSpmv);
-    k_spmv<false><<<(unsigned)((A->neq + 7) / 8), 256, 0, m->stream>>>(A->neq, A->rowptr.p, A->colind.p, A->val.p, d_x, d_y, nullptr, nullptr);
+    k_spmv<false><<<kSpmvBlocks, 256, 0, m->stream>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, d_y, nullptr, nullptr);
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
 }
@@ -646,23 +807,94 @@ int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag)
     return TB2_OK;
 }
 
+// Jacobi-PCG on an element-partitioned mesh: every rank holds the sub-domain matrix of its own elements (assembled locally,
+// never exchanged).  Per iteration: q = A_loc p, ONE interface sum of q (the same packed all-reduce as the force sum), dots
+// over owned equations + one all-reduce of 1-2 scalars (SolverT::InnerProduct semantics: each equation counted once).
+// b and x must be consistent on all sharers of an interface node (they are when b comes from interface-summed forces).
+static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
+                           double* final_rnorm)
+{
+    tb2_mesh* m = A->ctx;
+    const int64_t n = A->neq;
+    cudaStream_t st = m->stream;
+    double* scal = A->scal.p;
+    PcgCtl* ctl = (PcgCtl*)(A->scal.p + kNumScal);
+    const int* eqnos = A->eqs->eqnos.p;
+    int64_t vb = (n + 255) / 256;
+    const unsigned vec_blocks = (unsigned)(vb < kReduceBlocks ? vb : kReduceBlocks);
+    const unsigned nb1 = (unsigned)((n + 255) / 256);
+    if (!A->eq_owned.p) {
+        TB2_CUDA(A->eq_owned.alloc(n));
+        k_eq_owned<<<nb1, 256, 0, st>>>(n, A->eqs->eq_node.p, comm_owned_mask(m), A->eq_owned.p);
+    }
+    const unsigned char* w = A->eq_owned.p;
+    double* red = A->partial.p + 2 * kReduceBlocks + kSpmvBlocks; // 8 spare doubles at the end of the partial buffer
+    // Jacobi preconditioner from the ASSEMBLED diagonal
+    k_extract_dinv<<<nb1, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 0);
+    TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->dinv.p));
+    k_invert_diag<<<nb1, 256, 0, st>>>(n, A->dinv.p);
+    k_spmv<false><<<kSpmvBlocks, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
+    TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->q.p));
+    k_pcg_init<<<vec_blocks, 256, 0, st>>>(n, d_b, A->q.p, A->dinv.p, A->r.p, A->z.p, A->p.p, A->partial.p, w);
+    k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 2, A->partial.p, red, nullptr);
+    TB2_CHECK(comm_allreduce_scalars(m, red, 2));
+    k_scalars_init<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter);
+    TB2_CUDA(cudaGetLastError());
+    PcgCtl h{};
+    const int check_every = 8;
+    for (int it = 0; it < max_iter;) {
+        for (int k = 0; k < check_every && it < max_iter; k++, it++) {
+            {
+                ProfScope ps(m, kProfSpmv);
+                k_spmv<false><<<kSpmvBlocks, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, nullptr, nullptr);
+            }
+            TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->q.p));
+            ProfScope ps(m, kProfPcgVec, 8);
+            k_wdot<<<vec_blocks, 256, 0, st>>>(n, A->p.p, A->q.p, w, A->partial.p, ctl);
+            k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 1, A->partial.p, red, ctl);
+            TB2_CHECK(comm_allreduce_scalars(m, red, 1));
+            k_scalars_alpha<<<1, 1, 0, st>>>(red, scal, ctl);
+            k_pcg_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->p.p, A->q.p, A->dinv.p, d_x, A->r.p, A->z.p, A->partial.p, w);
+            k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 2, A->partial.p, red, ctl);
+            TB2_CHECK(comm_allreduce_scalars(m, red, 2));
+            k_scalars_beta<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter);
+            k_pcg_direction<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->z.p, A->p.p);
+        }
+        TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        TB2_CUDA(cudaStreamSynchronize(st));
+        if (h.done) break; // identical on every rank: the flag derives from all-reduced scalars
+    }
+    TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    double hs[kNumScal];
+    TB2_CUDA(cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
+    TB2_CUDA(cudaStreamSynchronize(st));
+    if (iterations) *iterations = h.iters;
+    if (final_rnorm) *final_rnorm = hs[kRNORM];
+    if (h.breakdown) {
+        set_error("PCG breakdown: p.Ap = %g <= 0 (matrix not positive definite)", hs[kPAP]);
+        return TB2_ERR_PCG_BREAKDOWN;
+    }
+    return TB2_OK;
+}
+
 int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
                    double* final_rnorm)
 {
     TB2_ARG(A && d_b && d_x);
     tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
+    if (A->eqs && comm_active(m)) return pcg_distributed(A, d_b, d_x, rtol, atol, max_iter, iterations, final_rnorm);
     const int64_t n = A->neq;
     cudaStream_t st = m->stream;
     double* scal = A->scal.p;
     PcgCtl* ctl = (PcgCtl*)(A->scal.p + kNumScal);
-    const unsigned spmv_blocks = (unsigned)((n + 7) / 8);
+    const unsigned spmv_blocks = kSpmvBlocks;
     int64_t vb = (n + 255) / 256;
     const unsigned vec_blocks = (unsigned)(vb < kReduceBlocks ? vb : kReduceBlocks);
     {
         ProfScope ps(m, kProfPcgVec, 4);
         k_extract_dinv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 1);
-        k_spmv<false><<<spmv_blocks, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
+        k_spmv<false><<<spmv_blocks, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
         k_pcg_init<<<vec_blocks, 256, 0, st>>>(n, d_b, A->q.p, A->dinv.p, A->r.p, A->z.p, A->p.p, A->partial.p);
         k_reduce_init<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, rtol, atol, max_iter);
     }
@@ -673,7 +905,7 @@ int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, d
         for (int k = 0; k < check_every && it < max_iter; k++, it++) {
             {
                 ProfScope ps(m, kProfSpmv);
-                k_spmv<true><<<spmv_blocks, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, A->partial.p, &ctl->done);
+                k_spmv<true><<<spmv_blocks, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, A->partial.p, &ctl->done);
             }
             ProfScope ps(m, kProfPcgVec, 4);
             k_reduce_pap<<<1, 1024, 0, st>>>((int)spmv_blocks, A->partial.p, scal, ctl);

@@ -36,6 +36,26 @@ def setup(X, conn, ns, device, comm=None):
     return m, g, ex
 
 
+def static_pcg(m, X, ns):
+    """small-strain elastic solve K x = f with the sub-domain matrix of this rank (tb2_matrix_pcg picks the distributed path
+    when the mesh has a communicator): x on the local nodes, iteration count"""
+    g = capi.Group(m, capi.SMALL_STRAIN, capi.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    eqs = capi.Equations(m, code)
+    A = capi.Matrix(eqs)
+    A.form_stiffness_host(g, np.zeros_like(X))
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 1e-3   # consistent on all sharers
+    fext[ns[2], 2] = -4e-4
+    act = eqs.eqnos() > 0
+    x, it, rn = A.pcg_host(fext[act], rtol=1e-13, max_iter=20000)
+    d = np.zeros_like(X)
+    d[act] = x
+    A.close(); eqs.close(); g.close()
+    return d, it
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -51,10 +71,11 @@ def main():
     ex.run(dt, nsteps)
     d, v, a = ex.get_state()
     mass = ex.mass_host()
+    xs, its = static_pcg(m, part["coords"], part["nodesets"])
     nn_glob = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
     # gather every rank's fields on rank 0 keyed by global node id
     out = [None] * world
-    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass})
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass, "xs": xs, "its": its})
     ok = True
     if rank == 0:
         X, conn, ns = tmesh.structured_cube(*dims, jitter=0.15)
@@ -63,8 +84,14 @@ def main():
         ex1.run(dt, nsteps)
         d1, v1, a1 = ex1.get_state()
         mass1 = ex1.mass_host()
+        xs1, its1 = static_pcg(m1, X, ns)
+        print("PCG iterations: single GPU %d, partitioned %s" % (its1, [o["its"] for o in out]))
         seen = {}
         for r, o in enumerate(out):
+            err = np.abs(o["xs"] - xs1[o["gid"]]).max() / np.abs(xs1).max()
+            if not err < 1e-9 or abs(o["its"] - its1) > 3:
+                print("rank %d static PCG solution differs from the single-GPU solve: %.3e (its %d vs %d)" % (r, err, o["its"], its1))
+                ok = False
             for nm, ref in (("d", d1), ("v", v1), ("a", a1), ("mass", mass1)):
                 err = np.abs(o[nm] - ref[o["gid"]]).max() / max(np.abs(ref).max(), 1e-300)
                 if not err < 1e-12:
