@@ -42,26 +42,73 @@ def stable_dt(n):
 
 
 def initial_displacement(X):
-    """smooth trilinear field + seeded noise (u = 1e-2 smooth + 1e-4 noise)"""
+    """smooth field + seeded noise (u = 1e-2 smooth + 1e-4 noise).  The smooth part is a 0.3 % homogeneous strain
+    tapered to zero at the clamped x = 0 face (no displacement jump at the boundary condition) and the noise scales with the
+    element size, so the same field is a gentle start at every mesh size."""
     rng = np.random.default_rng(12345)
     A = rng.standard_normal((3, 3))
-    return 1e-2 * X @ A.T * 0.3 + 1e-4 * (1.0 / 64) * rng.standard_normal(X.shape)
+    h = 1.0 / max(round((X.shape[0]) ** (1.0 / 3.0)) - 1, 1)
+    return 1e-2 * 0.3 * X[:, :1] * (X @ A.T) + 1.5e-4 * h * rng.standard_normal(X.shape)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # clocks sampler (B200_PROFILING.md)
 # ---------------------------------------------------------------------------------------------------------------------
 class Clocks:
+    """SM clock + throttle-reason sampler for the timed region.  NVML in a thread (5 ms period: the timed region of a small
+    --steps run is only tens of ms); falls back to the recipe's `nvidia-smi -lms` line when pynvml is unusable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu):
-        self.gpu, self.proc, self.lines = gpu, None, []
+    def __init__(self, gpu, uuid=None):
+        self.gpu, self.uuid, self.proc, self.lines = gpu, uuid, None, []
+        self.nvml, self.handle, self.samples, self.smax, self.bits, self.power = None, None, [], None, 0, []
+        self.stop_flag = threading.Event()
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, self.uuid.encode()):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, h
+            return True
+        except Exception:
+            return False
+
+    def _nvml_loop(self):
+        p, h = self.nvml, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(p.nvmlDeviceGetClockInfo(h, p.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(p.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.bits |= int(p.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.power.append(p.nvmlDeviceGetPowerUsage(h) * 1e-3)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
 
     def start(self):
+        if self._nvml_open():
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -72,6 +119,12 @@ class Clocks:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            reasons = sorted(name for bit, name in self.REASONS if self.bits & bit)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None, "source": "nvml, 5 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +143,8 @@ class Clocks:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 20"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -105,7 +159,7 @@ def _write_reference_case(work, n, nsteps):
             "time": {"num_steps": nsteps, "time_step": float(stable_dt(n)), "schedules": [[(0.0, 1.0)]]},
             "integrator": "central_difference",
             "kbc": [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)],
-            "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 1e-3}],
+            "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02 / (n * n)}],
             "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": MATERIAL,
             "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}
     ti.write_xml(os.path.join(work, "run_%d.xml" % nsteps), desc)
@@ -195,11 +249,22 @@ def workload_config(n, gpus):
 # ---------------------------------------------------------------------------------------------------------------------
 # second half of BASELINE.json's metric: PCG DOF-iterations/s (configs[2] scaled to one GPU's share)
 # ---------------------------------------------------------------------------------------------------------------------
-def run_pcg(torch, capi, tmesh, local, n, iters, hbm_peak):
-    """small-strain elastic n^3 cube: device assembly (K3) of the CSR tangent, then `iters` Jacobi-PCG iterations (K6-K8)
-    with device-resident vectors.  Returns the "pcg" object of the JSON line."""
-    X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
+    """small-strain elastic cube, n^3 elements per GPU: device assembly (K3) of the CSR tangent, then `iters` Jacobi-PCG iterations
+    (K6-K8) with device-resident vectors.  N > 1: every rank holds the sub-domain matrix of its brick; per iteration one packed
+    interface sum of A_loc p and two scalar all-reduces over NCCL.  Returns the "pcg" object of the JSON line (rank 0)."""
+    if world == 1:
+        X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+        part = None
+    else:
+        gx, gy, gz = tmesh.brick_grid(world)
+        part = tmesh.partition_cube(n * gx, n * gy, n * gz, world, rank, jitter=0.1)
+        X, conn, ns = part["coords"], part["conn"], part["nodesets"]
     m = capi.Mesh(X, conn, device=local)
+    if world > 1:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        m.comm_init(rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
     g = capi.Group(m, capi.SMALL_STRAIN, capi.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
     code = np.zeros(X.shape, np.uint8)
     code[ns[1]] = 1
@@ -221,32 +286,50 @@ def run_pcg(torch, capi, tmesh, local, n, iters, hbm_peak):
     t_assembly_ms = float(ms_cat[5])
     fext = np.zeros_like(X)
     fext[ns[2], 0] = 1e-3
-    b = torch.from_numpy(fext[eqs.eqnos() > 0]).to(dev)
+    active = eqs.eqnos() > 0
+    b = torch.from_numpy(fext[active]).to(dev)
     x = torch.zeros_like(b)
+    neq_glob = torch.tensor([float((active & (part["owned"][:, None] > 0)).sum()) if part else float(A.neq), float(A.nnz), float(conn.shape[0])],
+                            device=dev, dtype=torch.float64)
     torch.cuda.synchronize()
     A.pcg(b, x, rtol=0.0, atol=0.0, max_iter=5)  # warm-up
     x.zero_()
+    m.synchronize()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.all_reduce(neq_glob, op=dist.ReduceOp.SUM)
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     m.profile_begin()
     e0.record(stream)
     it, rn = A.pcg(b, x, rtol=0.0, atol=0.0, max_iter=iters)
     e1.record(stream)
     ms_cat, cnt_cat, launches = m.profile_end()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     ms = e0.elapsed_time(e1)
     if it != iters or not np.isfinite(rn):
         raise SystemExit("bench.py: PCG ran %d of %d iterations, |r| = %g" % (it, iters, rn))
-    spmv_ms = float(ms_cat[3]) / max(int(cnt_cat[3]), 1)
-    spmv_bytes = 12.0 * A.nnz + 12.0 * A.neq
-    iter_bytes = spmv_bytes + 128.0 * A.neq  # unfused PCG iteration
-    out = {"metric": "PCG DOF-iters/s", "value": A.neq * iters / (ms * 1e-3), "unit": "DOF-iters/s", "iterations": iters,
-           "ms_per_iteration": ms / iters, "num_equations": A.neq, "nnz": A.nnz, "gpu_launches": int(launches),
-           "workload": "BASELINE.json configs[2] at one GPU's share: %d^3=%d-element small_strain + SSKStV cube, %d equations, CSR %d nnz "
-                       "assembled on the device (K3), Jacobi-PCG with device-resident vectors" % (n, n ** 3, A.neq, A.nnz),
-           "assembly": {"ms": t_assembly_ms, "elements_per_s": n ** 3 / (t_assembly_ms * 1e-3), "structure_build_s": t_struct},
-           "roofline": {"bound": "hbm", "kernel": "k_spmv<dot> (K6)", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9, "peak": hbm_peak,
+    tt = torch.tensor([ms, float(ms_cat[3]) / max(int(cnt_cat[3]), 1), float(ms_cat[6]) / iters, t_assembly_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, spmv_ms, comm_ms, t_assembly_ms = (float(v) for v in tt.tolist())
+    neq_total, nnz_total, ne_total = (float(v) for v in neq_glob.tolist())
+    spmv_bytes = 12.0 * A.nnz + 12.0 * A.neq        # this rank's launch (CSR 12 B/nnz + 12 B/row)
+    iter_bytes = spmv_bytes + 128.0 * A.neq         # unfused PCG iteration
+    out = {"metric": "PCG DOF-iters/s", "value": neq_total * iters / (ms * 1e-3), "unit": "DOF-iters/s", "n_gpus": world, "iterations": iters,
+           "ms_per_iteration": ms / iters, "num_equations": int(neq_total), "nnz": int(nnz_total), "gpu_launches": int(launches),
+           "workload": "BASELINE.json configs[2] at %d^3=%d small_strain + SSKStV elements per GPU (%d GPUs: %d elements, %d equations), CSR "
+                       "assembled on the device (K3)%s, Jacobi-PCG with device-resident vectors"
+                       % (n, n ** 3, world, int(ne_total), int(neq_total), " as sub-domain matrices" if world > 1 else ""),
+           "assembly": {"ms": t_assembly_ms, "elements_per_s": ne_total / (t_assembly_ms * 1e-3), "structure_build_s": t_struct},
+           "roofline": {"bound": "hbm", "kernel": "k_spmv (K6)", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9, "peak": hbm_peak,
                         "unit": "GB/s", "frac": spmv_bytes / (spmv_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": spmv_ms,
-                        "share_of_iteration": spmv_ms * iters / ms, "traffic": None},
+                        "share_of_iteration": spmv_ms * iters / ms, "traffic": PCG_SPMV_TRAFFIC_BYTES_PER_NNZ * A.nnz,
+                        "note": "algorithmic bytes are SURVEY.md 8d's CSR figure (12 B/nnz + 12 B/row); the node-grouped kernel reads "
+                                "colind once per 3 rows, so its DRAM traffic (ncu, profiles/) is below the algorithmic bytes"},
+           "interface_exchange_ms_per_iteration": comm_ms if world > 1 else None,
            "iteration_hbm_frac": iter_bytes * iters / (ms * 1e-3) * 1e-9 / hbm_peak}
     A.close(); eqs.close(); g.close(); m.close()
     return out
@@ -295,7 +378,7 @@ def run_gpu_arm(args):
     code[ns[1]] = 1  # x = 0 face clamped
     fext = np.zeros_like(X)
     if world == 1:
-        fext[ns[2], 0] = 1e-3
+        fext[ns[2], 0] = 0.02 / (n * n)  # nodal share of a 0.02 traction (<< mu) on the x = 1 face: the same load at every mesh size
     u0 = initial_displacement(X)
     ex.set_bc(code, np.zeros_like(X), fext)
     ex.set_state(u0, np.zeros_like(X), np.zeros_like(X))
@@ -310,10 +393,16 @@ def run_gpu_arm(args):
 
     # ---- device-resident timed region
     ex.run(dt, args.warmup)
-    barrier()
-    clocks = Clocks(local)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    if not args.no_profile:
+        m.profile_reserve(args.steps * 16 + 64)
+    clocks = Clocks(local, uuid)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # before the barrier: the sampler's start-up must not skew rank 0 against the others
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if not args.no_profile:
         m.profile_begin()
@@ -376,20 +465,34 @@ def run_gpu_arm(args):
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         fp64_peak = capi.measure_fp64_peak(local)
         k1_ms, k5_ms, comm_ms = (float(x) for x in kt.tolist())
-        # algorithmic bytes (SURVEY.md 8d / DESIGN.md): K1 = 104 B/element (conn 32 + X 24 + u 24 + f 24), K5 = 192 B/node
-        k1_bytes = 104.0 * ne_local
-        k1_flops = args.k1_flop_per_element * ne_local
-        roof = {"bound": "hbm", "kernel": "k_internal_force<TL,SimoIso> (K1)", "achieved": k1_bytes / (k1_ms * 1e-3) * 1e-9, "peak": hbm_peak,
-                "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": args.k1_traffic_bytes, "peak_source": hbm_src,
-                "avg_launch_ms": k1_ms, "launches_per_step": int(cnt_cat[0]) // args.steps, "share_of_step": k1_ms * args.steps / ms,
-                "note": "K1 is FP64-pipe bound (arithmetic intensity ~%.0f flop/B >> machine balance): see roofline_fp64" % (args.k1_flop_per_element / 104.0)}
-        roof64 = {"bound": "fp64", "kernel": roof["kernel"], "achieved": k1_flops / (k1_ms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
-                  "frac": k1_flops / (k1_ms * 1e-3) * 1e-12 / fp64_peak, "flop_per_element": args.k1_flop_per_element,
-                  "peak_source": "measured in this run (tb2_measure_fp64_peak: dependent DFMA chains)"}
-        k5_bytes = (192.0 + 24.0) * nn_local  # d,v,a R+W, fext, minv + fint write
-        roof_k5 = {"bound": "hbm", "kernel": "k_cd_node_update (gather + K5)", "achieved": k5_bytes / (k5_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": k5_bytes / (k5_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": k5_ms, "launches_per_step": int(cnt_cat[1]) // args.steps, "share_of_step": k5_ms * args.steps / ms,
-                   "note": "algorithmic 216 B/node; the kernel also re-reads the 192 B/element force scratch"}
+        # algorithmic bytes (SURVEY.md 8d / DESIGN.md): K1 = 104 B/element (conn 32 + X 24 + u 24 + f 24), K5 = 192 B/node.
+        # Per LAUNCH: one launch of the slab pipeline sweeps ne/launches_per_step elements.
+        k1_lps = max(int(cnt_cat[0]) // args.steps, 1)
+        k5_lps = max(int(cnt_cat[1]) // args.steps, 1)
+        k1_launch_ms = k1_ms / k1_lps
+        k1_bytes = 104.0 * ne_local / k1_lps
+        k1_flops = args.k1_flop_per_element * ne_local / k1_lps
+        k1_insts = args.k1_fp64_inst_per_element * ne_local / k1_lps
+        roof = {"bound": "hbm", "kernel": "k_internal_force<TL,SimoIso> (K1)", "achieved": k1_bytes / (k1_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": k1_bytes / (k1_launch_ms * 1e-3) * 1e-9 / hbm_peak,
+                "traffic": args.k1_traffic_bytes_per_element * ne_local / k1_lps, "peak_source": hbm_src,
+                "avg_launch_ms": k1_launch_ms, "launches_per_step": k1_lps, "elements_per_launch": ne_local / k1_lps,
+                "algorithmic_bytes_per_launch": k1_bytes, "share_of_step": k1_ms * args.steps / ms,
+                "note": "K1 is FP64-pipe bound (arithmetic intensity ~%.0f flop/B >> machine balance): see roofline_fp64; traffic = dram read+write "
+                        "per launch from the ncu --set full capture in profiles/ (per-element figure x elements per launch)" % (args.k1_flop_per_element / 104.0)}
+        roof64 = {"bound": "fp64", "kernel": roof["kernel"], "achieved": k1_flops / (k1_launch_ms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
+                  "frac": k1_flops / (k1_launch_ms * 1e-3) * 1e-12 / fp64_peak, "flop_per_element": args.k1_flop_per_element,
+                  "fp64_inst_per_element": args.k1_fp64_inst_per_element,
+                  "pipe_frac": k1_insts / (k1_launch_ms * 1e-3) * 1e-12 / (0.5 * fp64_peak),
+                  "peak_source": "measured in this run (tb2_measure_fp64_peak: dependent DFMA chains; 1 DFMA = 2 flop)",
+                  "note": "frac counts real flops (DFMA 2, DMUL/DADD 1) against the all-FMA peak; pipe_frac counts FP64 instructions against the pipe's "
+                          "issue rate (peak/2 instructions/s), i.e. what ncu reports as sm__pipe_fp64_cycles_active"}
+        k5_launch_ms = k5_ms / k5_lps
+        k5_bytes = (192.0 + 24.0) * nn_local / k5_lps  # d,v,a R+W, fext, minv + fint write
+        roof_k5 = {"bound": "hbm", "kernel": "k_cd_node_update (gather + K5)", "achieved": k5_bytes / (k5_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": k5_bytes / (k5_launch_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": k5_launch_ms, "launches_per_step": k5_lps,
+                   "share_of_step": k5_ms * args.steps / ms,
+                   "note": "algorithmic 216 B/node; the kernel also re-reads the 192 B/element force scratch (L2-resident in the slab pipeline)"}
         step_bytes = 104.0 * ne_local + 192.0 * nn_local
         line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -398,27 +501,36 @@ def run_gpu_arm(args):
                         "d2h_bytes_per_step": int(72 * nn_local * world), "steps": e2e_steps, "ms_per_step": float(te.item()) / e2e_steps,
                         "api": "tb2_explicit_step_host (pinned host d,v,a in and out every step)"},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_fp64": roof64, "roofline_k5": roof_k5,
-                "schedule": ("serial" if world > 1 or os.environ.get("TB2_PIPELINE", "1") == "0" else
-                             "slab pipeline: K1 chunks on one stream overlap K5 chunks on a second one, so avg_launch_ms (sum of a kernel's chunk "
-                             "launches per step, measured while the other kernel co-runs) and the shares add up to more than the step"),
+                "schedule": ("serial" if os.environ.get("TB2_PIPELINE", "1") == "0" else
+                             "slab pipeline: K1 chunks on one stream overlap K5 chunks on a second one, so avg_launch_ms (measured while the other "
+                             "kernel co-runs) and the shares add up to more than the step"
+                             + ("; N > 1: boundary elements first, packed interface all-reduce on a third stream beside the slab pipeline, "
+                                "interface nodes updated last" if world > 1 else "")),
                 "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
                 "interface_exchange_ms": comm_ms if world > 1 else None,
                 "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None}
-        if world == 1 and not args.no_pcg:
-            line["pcg"] = run_pcg(torch, capi, tmesh, local, args.pcg_n, args.pcg_iters, hbm_peak)
+    ex.close(); g.close(); m.close()
+    hbm_peak_all = 6650.0
+    try:
+        hbm_peak_all = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError, ValueError):
+        pass
+    pcg = None if args.no_pcg else run_pcg(torch, dist, capi, tmesh, local, rank, world, args.pcg_n, args.pcg_iters, hbm_peak_all)
+    if rank == 0:
+        if pcg:
+            line["pcg"] = pcg
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
-        ex.close(); g.close(); m.close()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--n", type=int, default=100, help="cube edge in elements per GPU (100 -> 1M elements, configs[1])")
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--n", "--edge", dest="n", type=int, default=100, help="cube edge in elements per GPU (100 -> 1M elements, configs[1])")
     ap.add_argument("--impl", default="tahoe_b200", choices=["tahoe_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the PCG DOF-iters/s leg")
@@ -427,7 +539,8 @@ def main():
     ap.add_argument("--pcg-iters", type=int, default=100)
     # per-element figures of K1 taken from the committed ncu capture (profiles/), see DESIGN.md
     ap.add_argument("--k1-flop-per-element", type=float, default=K1_FLOP_PER_ELEMENT)
-    ap.add_argument("--k1-traffic-bytes", type=float, default=K1_TRAFFIC_BYTES)
+    ap.add_argument("--k1-fp64-inst-per-element", type=float, default=K1_FP64_INST_PER_ELEMENT)
+    ap.add_argument("--k1-traffic-bytes-per-element", type=float, default=K1_TRAFFIC_BYTES_PER_ELEMENT)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -436,9 +549,13 @@ def main():
         run_gpu_arm(args)
 
 
-# FP64 flops per element executed by K1 (DFMA = 2, DADD/DMUL = 1), from the ncu capture in profiles/ (None until measured)
-K1_FLOP_PER_ELEMENT = 6000.0
-K1_TRAFFIC_BYTES = None
+# Per-element figures of K1 <TL, SimoIso> from the ncu --set full capture profiles/r01c_k1_full (284,160-element slab launch):
+# thread-level DFMA 1280 + DMUL 715 + DADD 450 = 2445 FP64 instructions = 3725 flop; dram read 23.5 MB + write 7.9 MB = 110.5 B/element.
+K1_FLOP_PER_ELEMENT = 3725.0
+K1_FP64_INST_PER_ELEMENT = 2445.0
+K1_TRAFFIC_BYTES_PER_ELEMENT = 110.5
+# k_spmv DRAM read+write per stored non-zero (ncu --set full, profiles/r01c_spmv_full: 2.465 GB for 242,991,882 nnz)
+PCG_SPMV_TRAFFIC_BYTES_PER_NNZ = 10.15
 
 if __name__ == "__main__":
     main()

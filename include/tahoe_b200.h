@@ -76,6 +76,7 @@ int tb2_host_unregister(void* h_ptr);
  * Categories: 0 element internal force (K1), 1 node gather + central-difference update (K5), 2 predictor, 3 SpMV (K6),
  * 4 PCG vector kernels (K7/K8), 5 stiffness assembly (K3), 6 interface exchange, 7 other.
  * tb2_profile_end synchronises the stream; h_ms[8], h_count[8]. */
+int tb2_profile_reserve(tb2_mesh* mesh, int64_t records); /* pre-create the event pairs so that none is created inside a timed region */
 int tb2_profile_begin(tb2_mesh* mesh);
 int tb2_profile_end(tb2_mesh* mesh, double* h_ms, int64_t* h_count, int64_t* kernel_launches);
 int tb2_mesh_synchronize(tb2_mesh* mesh);

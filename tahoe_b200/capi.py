@@ -21,7 +21,7 @@ J2_BLOCK = 5 * 48 + 64  # doubles per element in the reference's ElementCardT la
 
 # the exported symbols of include/tahoe_b200.h (checked by tests/test_capi_symbols.py against the header text)
 SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2_memcpy_h2d tb2_memcpy_d2h tb2_host_register
-tb2_host_unregister tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
+tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
 tb2_form_lumped_mass_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
@@ -170,6 +170,9 @@ class Mesh(_Handle):
 
     def synchronize(self):
         _chk(lib().tb2_mesh_synchronize(self.h))
+
+    def profile_reserve(self, records):
+        _chk(lib().tb2_profile_reserve(self.h, C.c_int64(int(records))))
 
     def profile_begin(self):
         _chk(lib().tb2_profile_begin(self.h))

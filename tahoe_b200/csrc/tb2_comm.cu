@@ -13,6 +13,8 @@
 
 #include <cstring>
 
+#include <cub/cub.cuh>
+
 #include "tb2_internal.h"
 
 namespace tb2 {
@@ -70,7 +72,43 @@ struct Comm {
     DevBuf<double> packed;          // [n_glob][3]
     DevBuf<unsigned char> owned;    // [nn]
     DevBuf<double> scal;            // all-reduce scratch for scalars
+    // overlapped explicit step: node -> slot map, the elements touching interface nodes, a stream for the collective
+    DevBuf<int> node_slot;          // [nn], -1 = private node
+    DevBuf<int> belems;             // [nb]
+    DevBuf<unsigned char> belem_flag; // [ne]
+    int64_t nb = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_reduced = nullptr, ev_done = nullptr;
+    ~Comm()
+    {
+        if (ev_packed) cudaEventDestroy(ev_packed);
+        if (ev_reduced) cudaEventDestroy(ev_reduced);
+        if (ev_done) cudaEventDestroy(ev_done);
+        if (stream) cudaStreamDestroy(stream);
+    }
 };
+
+__global__ void k_fill_int(int64_t n, int v, int* __restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+__global__ void k_node_slots(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots, int* __restrict__ node_slot)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_if) node_slot[nodes[k]] = slots[k];
+}
+// flag[e] = 1 if element e has a node on the partition interface
+__global__ void k_boundary_flags(int64_t ne, int64_t stride, const int* __restrict__ conn, const int* __restrict__ node_slot,
+                                 unsigned char* __restrict__ flag)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int any = 0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) any |= node_slot[conn[a * stride + e]] >= 0;
+    flag[e] = (unsigned char)any;
+}
 
 __global__ void k_pack(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots, const double* __restrict__ nodal,
                        double* __restrict__ packed)
@@ -114,6 +152,35 @@ __global__ void k_unpack_eq(int64_t n_if, const int* __restrict__ nodes, const i
 }
 
 bool comm_active(tb2_mesh* m) { return m->comm && m->comm->nranks > 1 && m->comm->n_glob > 0; }
+
+bool comm_plan(tb2_mesh* m, CommPlan* out)
+{
+    if (!comm_active(m) || !m->comm->stream) return false;
+    Comm* c = m->comm;
+    out->n_if = c->n_if;
+    out->n_glob = c->n_glob;
+    out->nb = c->nb;
+    out->nodes = c->nodes.p;
+    out->slots = c->slots.p;
+    out->node_slot = c->node_slot.p;
+    out->belems = c->belems.p;
+    out->belem_flag = c->belem_flag.p;
+    out->packed = c->packed.p;
+    out->stream = c->stream;
+    out->ev_packed = c->ev_packed;
+    out->ev_reduced = c->ev_reduced;
+    out->ev_done = c->ev_done;
+    return true;
+}
+
+// the packed-vector all-reduce on the communicator's own stream (ordering is the caller's: events in CommPlan)
+int comm_allreduce_packed(tb2_mesh* m)
+{
+    Comm* c = m->comm;
+    ProfScope ps(m, kProfComm, 1, c->stream);
+    const int r = g_nccl.AllReduce(c->packed.p, c->packed.p, (size_t)(3 * c->n_glob), kNcclFloat64, kNcclSum, c->comm, c->stream);
+    return r ? nccl_fail(r, "ncclAllReduce(interface, overlapped)") : TB2_OK;
+}
 const unsigned char* comm_owned_mask(tb2_mesh* m) { return m->comm ? m->comm->owned.p : nullptr; }
 
 // in-place sum of n doubles over ranks (PCG scalars); no-op without a communicator
@@ -188,6 +255,38 @@ int tb2_comm_init(tb2_mesh* m, int rank, int nranks, const char h_id[128], int64
         if (h_owned) e = cudaMemcpy(c->owned.p, h_owned, m->nn, cudaMemcpyHostToDevice);
         else e = cudaMemset(c->owned.p, 1, m->nn);
     }
+    // overlap plan: node -> slot map and the (ascending) list of elements that touch an interface node
+    if (e == cudaSuccess) e = c->node_slot.alloc(m->nn);
+    if (e == cudaSuccess && nranks > 1 && n_glob > 0) {
+        const int T = 256;
+        DevBuf<unsigned char>& flag = c->belem_flag;
+        DevBuf<unsigned char> tmp;
+        DevBuf<int> nsel;
+        k_fill_int<<<(unsigned)((m->nn + T - 1) / T), T, 0, m->stream>>>(m->nn, -1, c->node_slot.p);
+        if (n_if) k_node_slots<<<(unsigned)((n_if + T - 1) / T), T, 0, m->stream>>>(n_if, c->nodes.p, c->slots.p, c->node_slot.p);
+        e = flag.alloc(m->ne);
+        if (e == cudaSuccess) e = nsel.alloc(1);
+        if (e == cudaSuccess) e = c->belems.alloc(m->ne);
+        if (e == cudaSuccess) {
+            k_boundary_flags<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(m->ne, m->stride, m->conn.p, c->node_slot.p, flag.p);
+            size_t bytes = 0;
+            cub::CountingInputIterator<int> ids(0);
+            e = cub::DeviceSelect::Flagged(nullptr, bytes, ids, flag.p, c->belems.p, nsel.p, (int)m->ne, m->stream);
+            if (e == cudaSuccess) e = tmp.alloc(bytes);
+            if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp.p, bytes, ids, flag.p, c->belems.p, nsel.p, (int)m->ne, m->stream);
+            int h_n = 0;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&h_n, nsel.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+            c->nb = h_n;
+        }
+        // the exchange lane outranks the bulk sweeps: its few CTAs (boundary elements, NCCL) must not queue behind a full-GPU grid
+        int prio_lo = 0, prio_hi = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_reduced, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         g_nccl.CommDestroy(c->comm);
         delete c;
@@ -202,6 +301,7 @@ int tb2_comm_destroy(tb2_mesh* m)
     if (!m || !m->comm) return TB2_OK;
     DeviceGuard dg(m->device);
     cudaStreamSynchronize(m->stream);
+    if (m->comm->stream) cudaStreamSynchronize(m->comm->stream);
     if (m->comm->comm) g_nccl.CommDestroy(m->comm->comm);
     delete m->comm;
     m->comm = nullptr;

@@ -295,6 +295,19 @@ int tb2_mesh_synchronize(tb2_mesh* m)
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     return TB2_OK;
 }
+int tb2_profile_reserve(tb2_mesh* m, int64_t records)
+{
+    TB2_ARG(m && records >= 0);
+    DeviceGuard g(m->device);
+    while ((int64_t)m->prof.size() < records) {
+        ProfRec r;
+        r.cat = 0;
+        TB2_CUDA(cudaEventCreate(&r.a));
+        TB2_CUDA(cudaEventCreate(&r.b));
+        m->prof.push_back(r);
+    }
+    return TB2_OK;
+}
 int tb2_profile_begin(tb2_mesh* m)
 {
     TB2_ARG(m);
@@ -318,6 +331,23 @@ int tb2_profile_end(tb2_mesh* m, double* h_ms, int64_t* h_count, int64_t* launch
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
             ms[r.cat] += t;
             cnt[r.cat]++;
+        }
+    }
+    if (const char* path = getenv("TB2_PROF_DUMP")) { // timeline of the last TB2_PROF_DUMP_N (default 200) launches: cat,start_ms,end_ms
+        char fname[1024];
+        snprintf(fname, sizeof fname, path, m->device); // a %d in the path becomes the device ordinal (one file per rank)
+        if (FILE* f = fopen(fname, "w")) {
+            const char* nmax = getenv("TB2_PROF_DUMP_N");
+            const size_t want = nmax ? (size_t)atol(nmax) : 200;
+            const size_t first = m->prof_used > want ? m->prof_used - want : 0;
+            fprintf(f, "cat,start_ms,end_ms\n");
+            for (size_t i = first; i < m->prof_used; i++) {
+                float t0 = 0.f, t1 = 0.f;
+                if (cudaEventElapsedTime(&t0, m->prof[first].a, m->prof[i].a) != cudaSuccess) { cudaGetLastError(); continue; }
+                if (cudaEventElapsedTime(&t1, m->prof[first].a, m->prof[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+                fprintf(f, "%d,%.4f,%.4f\n", m->prof[i].cat, t0, t1);
+            }
+            fclose(f);
         }
     }
     m->prof_used = 0;

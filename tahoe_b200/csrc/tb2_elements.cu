@@ -21,7 +21,9 @@
 namespace tb2 {
 
 struct ElemArgs {
-    int64_t e_begin, ne, stride; // elements [e_begin, ne)
+    int64_t e_begin, ne, stride; // elements [e_begin, ne), or entries [e_begin, ne) of elist
+    const int* elist; // optional element index list (multi-GPU: the elements touching partition-interface nodes)
+    const unsigned char* skip; // optional [ne] flags: elements a range launch leaves to the index-list launch
     const int* conn;  // [8][stride]
     const double* X;  // [nn][3]
     const double* u;  // [nn][3]
@@ -42,8 +44,10 @@ TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
 template <int FORM, int MAT, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
 {
-    const int64_t e = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= p.ne) return;
+    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.ne) return;
+    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
+    if (p.skip && p.skip[e]) return;
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
@@ -271,7 +275,8 @@ J2Hist group_hist(tb2_group* g)
     return h;
 }
 
-int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st);
+int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st,
+                                const int* d_elist = nullptr, const unsigned char* d_skip = nullptr);
 
 // element sweep only: fe scratch <- element forces (used by the fused explicit path too)
 int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration)
@@ -280,7 +285,9 @@ int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, i
 }
 
 // elements [e0, e1) on stream st (the slab pipeline of tb2_explicit.cu launches the sweep in chunks)
-int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st)
+// (with d_elist: entries [e0, e1) of that element index list; with d_skip: flagged elements are left out)
+int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st,
+                                const int* d_elist, const unsigned char* d_skip)
 {
     tb2_mesh* m = g->mesh;
     force_kernel_t k = pick_force_kernel(g->form, g->mat.kind);
@@ -296,6 +303,8 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
     p.e_begin = e0;
     p.ne = e1;
     p.stride = m->stride;
+    p.elist = d_elist;
+    p.skip = d_skip;
     p.conn = m->conn.p;
     p.X = m->X.p;
     p.u = d_u;
@@ -306,6 +315,7 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
     p.iteration = iteration;
     p.status = g->status.p;
     const int T = 128;
+    if (e1 <= e0) return TB2_OK;
     {
         ProfScope ps(m, kProfForce, 1, st);
         k<<<(unsigned)((e1 - e0 + T - 1) / T), T, 0, st>>>(p);

@@ -8,6 +8,7 @@
 // On the device this is two launches per step: the element sweep (K1) and one node kernel that gathers the element
 // forces, forms R, applies M^-1, the corrector and -- when another step follows -- the next step's predictor, so d, v, a
 // are read and written once per step (192 B/node/step).
+#include <chrono>
 #include <cstdlib>
 
 #include "tb2_internal.h"
@@ -16,8 +17,11 @@ namespace tb2 {
 
 int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration);
 int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
-int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st);
+int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st,
+                                const int* d_elist = nullptr, const unsigned char* d_skip = nullptr);
 bool comm_active(tb2_mesh* m);
+bool comm_plan(tb2_mesh* m, CommPlan* out);
+int comm_allreduce_packed(tb2_mesh* m);
 
 // nExplicitCD::Predictor (nExplicitCD.cpp:72-96) / Corrector (:98-139) with explicit roundings, so that the stand-alone and
 // the fused kernels produce bit-identical fields
@@ -54,16 +58,20 @@ __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, d
 // node kernel: gather fint, R = s*fext - fint, upd = minv*R on free dofs, corrector; optionally the next predictor.
 // a_in is the acceleration left by the predictor (0 on every dof), kept as an input for generality (a += upd).
 // GATHER = false: fint already holds the (interface-summed) internal force (multi-GPU path)
+// skip_slot (multi-GPU overlap): nodes with skip_slot[n] >= 0 lie on the partition interface and are updated by
+// k_cd_interface_update once the summed force has arrived
 template <bool GATHER, bool NEXT_PREDICTOR>
 __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                                        const double* __restrict__ fe, int64_t stride, double dt, double fext_scale,
                                                        double next_value_scale, const double* __restrict__ fext,
                                                        const double* __restrict__ minv, const unsigned char* __restrict__ code,
                                                        const double* __restrict__ bcval, double* __restrict__ d,
-                                                       double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint)
+                                                       double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint,
+                                                       const int* __restrict__ skip_slot = nullptr)
 {
     const int64_t n = n_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= nn) return;
+    if (skip_slot && skip_slot[n] >= 0) return;
     double f[3] = {0.0, 0.0, 0.0};
     if (GATHER) {
         const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
@@ -89,6 +97,67 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
         double vi = v[q], ai = a[q];
         cd_correct(dt, vi, ai, upd);
         if (GATHER) fint[q] = f[i];
+        if (NEXT_PREDICTOR) {
+            double di = d[q];
+            cd_predict(dt, di, vi, ai);
+            ai = 0.0;
+            if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
+            else if (c == TB2_BC_DSP) di = next_value_scale * bcval[q];
+            d[q] = di;
+        }
+        v[q] = vi;
+        a[q] = ai;
+    }
+}
+
+// multi-GPU overlap, step 1: the partial internal force of this rank on its interface nodes, summed in the same ascending
+// element order as everywhere else, written straight into the packed global interface vector (zeroed beforehand)
+__global__ void __launch_bounds__(256) k_gather_pack(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
+                                                    const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                    const double* __restrict__ fe, int64_t stride, double* __restrict__ packed)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_if) return;
+    const int64_t n = nodes[k];
+    const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    for (int q = k0; q < k1; q++) {
+        const int ent = __ldg(inc + q);
+        const int64_t e = ent >> 3;
+        const int a3 = 3 * (ent & 7);
+        f0 += __ldg(fe + (int64_t)(a3)*stride + e);
+        f1 += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
+        f2 += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
+    }
+    double* out = packed + 3 * (int64_t)slots[k];
+    out[0] = f0;
+    out[1] = f1;
+    out[2] = f2;
+}
+
+// multi-GPU overlap, step 2: the node update of the interface nodes from the all-reduced force (same arithmetic as
+// k_cd_node_update, so every sharer of a node computes bitwise the same d, v, a)
+template <bool NEXT_PREDICTOR>
+__global__ void __launch_bounds__(256) k_cd_interface_update(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
+                                                            const double* __restrict__ packed, double dt, double fext_scale,
+                                                            double next_value_scale, const double* __restrict__ fext,
+                                                            const double* __restrict__ minv, const unsigned char* __restrict__ code,
+                                                            const double* __restrict__ bcval, double* __restrict__ d,
+                                                            double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_if) return;
+    const int64_t n = nodes[k];
+    const double* f = packed + 3 * (int64_t)slots[k];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int64_t q = 3 * n + i;
+        const unsigned char c = code[q];
+        const double R = __dsub_rn(__dmul_rn(fext_scale, fext[q]), f[i]);
+        const double upd = c ? 0.0 : __dmul_rn(R, minv[q]);
+        double vi = v[q], ai = a[q];
+        cd_correct(dt, vi, ai, upd);
+        fint[q] = f[i];
         if (NEXT_PREDICTOR) {
             double di = d[q];
             cd_predict(dt, di, vi, ai);
@@ -130,15 +199,30 @@ using namespace tb2;
 //   K5(s, nc) waits for K1(s, last element chunk touching nc);   K1(s+1, ec) waits for K5(s, last node chunk touched by ec).
 // The same two conditions cover the write-after-read hazards on d (K5 writes what K1 reads) and on the force scratch.
 // Arithmetic and summation order are those of the serial schedule: results are bitwise identical (tested).
+//
+// Multi-GPU (element-partitioned mesh).  The interface exchange is a third, independent lane beside the same pipeline:
+//   comm stream    K1 over the elements touching interface nodes (index list) -> k_gather_pack of this rank's partial interface
+//                  forces into the packed vector -> ncclAllReduce -> k_cd_interface_update of the interface nodes;
+//   main / second  the slab pipeline, with K1 leaving out the boundary elements and K5 leaving out the interface nodes.
+// Interface nodes are written by the comm lane only and read by the boundary elements only, so the lanes meet in two places:
+// the boundary sweep of step s+1 waits for the last K5 chunk of step s (it reads private nodes too), and the K5 chunks of a
+// step wait for that step's boundary sweep (they gather its element forces and overwrite the d it reads).
 static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
 {
     tb2_group* g = ex->group;
     tb2_mesh* m = g->mesh;
+    CommPlan cp;
+    const bool multi = comm_plan(m, &cp);
+    const int* skip = multi ? cp.node_slot : nullptr;
     const int C = (int)m->pipe_e0.size() - 1;
     const int64_t ndof = 3 * m->nn;
     const int T = 256;
     if (!m->stream2) {
-        TB2_CUDA(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+        // the HBM-bound node kernels outrank the FP64-bound element sweep they run beside (their CTAs are small and short)
+        int prio_lo = 0, prio_hi = 0;
+        TB2_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const char* p2 = getenv("TB2_K5_PRIORITY"); // experiment knob: 1 = run the node lane at elevated priority
+        TB2_CUDA(cudaStreamCreateWithPriority(&m->stream2, cudaStreamNonBlocking, (p2 && p2[0] == '1') ? (prio_hi < prio_lo ? prio_hi + 1 : prio_hi) : prio_lo));
         m->ev_k1.resize(C);
         m->ev_k5.resize(C);
         for (int c = 0; c < C; c++) {
@@ -154,12 +238,42 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
     }
     TB2_CUDA(cudaEventRecord(m->ev_join, m->stream));
     TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_join, 0));
+    const auto t_enqueue0 = std::chrono::steady_clock::now();
     for (int s = 0; s < nsteps; s++) {
         const double fsc = fs ? fs[s] : 1.0;
         int nc = 0;
+        if (multi) {
+            // comm lane of step s (its previous interface update is ahead of it on the same stream)
+            TB2_CUDA(cudaStreamWaitEvent(cp.stream, s > 0 ? m->ev_k5[C - 1] : m->ev_join, 0));
+            TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, 0, cp.nb, cp.stream, cp.belems));
+            {
+                ProfScope ps(m, kProfComm, 2, cp.stream);
+                TB2_CUDA(cudaMemsetAsync(cp.packed, 0, 3 * cp.n_glob * sizeof(double), cp.stream));
+                if (cp.n_if)
+                    k_gather_pack<<<(unsigned)((cp.n_if + T - 1) / T), T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, m->inc_ptr.p, m->inc.p,
+                                                                                        m->fe.p, m->stride, cp.packed);
+            }
+            TB2_CUDA(cudaEventRecord(cp.ev_packed, cp.stream));
+            TB2_CHECK(comm_allreduce_packed(m));
+            if (cp.n_if) {
+                ProfScope ps(m, kProfNodeUpdate, 1, cp.stream);
+                const unsigned nb = (unsigned)((cp.n_if + T - 1) / T);
+                if (s + 1 < nsteps)
+                    k_cd_interface_update<true><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.packed, dt, fsc, vs ? vs[s + 1] : 1.0,
+                                                                        ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p,
+                                                                        ex->a.p, ex->fint.p);
+                else
+                    k_cd_interface_update<false><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.packed, dt, fsc, 1.0, ex->fext.p,
+                                                                         ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p, ex->a.p,
+                                                                         ex->fint.p);
+            }
+            TB2_CUDA(cudaEventRecord(cp.ev_done, cp.stream));
+            TB2_CUDA(cudaStreamWaitEvent(m->stream2, cp.ev_packed, 0)); // K5 chunks of this step follow the boundary sweep
+        }
         for (int c = 0; c < C; c++) {
             if (s > 0 && m->pipe_nmax_of_ec[c] >= 0) TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_k5[m->pipe_nmax_of_ec[c]], 0));
-            TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, m->pipe_e0[c], m->pipe_e0[c + 1], m->stream));
+            TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, m->pipe_e0[c], m->pipe_e0[c + 1], m->stream, nullptr,
+                                                  multi ? cp.belem_flag : nullptr));
             TB2_CUDA(cudaEventRecord(m->ev_k1[c], m->stream));
             for (; nc < C && m->pipe_emax_of_nc[nc] <= c; nc++) {
                 const int64_t n0 = m->pipe_n0[nc], n1 = m->pipe_n0[nc + 1];
@@ -170,19 +284,24 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
                     if (s + 1 < nsteps)
                         k_cd_node_update<true, true><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
                                                                               vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
-                                                                              ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
+                                                                              ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p, skip);
                     else
                         k_cd_node_update<true, false><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
                                                                                ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
-                                                                               ex->v.p, ex->a.p, ex->fint.p);
+                                                                               ex->v.p, ex->a.p, ex->fint.p, skip);
                 }
                 TB2_CUDA(cudaEventRecord(m->ev_k5[nc], m->stream2));
             }
         }
     }
+    if (multi) TB2_CUDA(cudaStreamWaitEvent(m->stream, cp.ev_done, 0));
     TB2_CUDA(cudaEventRecord(m->ev_join, m->stream2));
     TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     TB2_CUDA(cudaGetLastError());
+    if (getenv("TB2_DEBUG_TIMING")) // host enqueue cost of the step loop (is the pipeline launch-bound?)
+        fprintf(stderr, "[tb2] explicit pipeline: %d steps enqueued in %.3f ms (%.1f us/step host)\n", nsteps,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enqueue0).count(),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enqueue0).count() / nsteps);
     return TB2_OK;
 }
 
@@ -204,7 +323,7 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
     const int T = 256;
     const unsigned nbn = (unsigned)((m->nn + T - 1) / T), nbd = (unsigned)((ndof + T - 1) / T);
     if (nsteps <= 0) return TB2_OK;
-    if (!comm_active(m) && m->pipe_e0.size() > 2 && nsteps > 1 && pipeline_enabled()) return explicit_steps_pipelined(ex, dt, nsteps, fs, vs);
+    if (m->pipe_e0.size() > 2 && nsteps > 1 && pipeline_enabled()) return explicit_steps_pipelined(ex, dt, nsteps, fs, vs);
     {
         ProfScope ps(m, kProfPredictor);
         k_cd_predictor<<<nbd, T, 0, m->stream>>>(ndof, dt, ex->d.p, ex->v.p, ex->a.p, ex->bccode.p, ex->bcval.p, vs ? vs[0] : 1.0);

@@ -71,6 +71,18 @@ struct DevBuf {
 };
 
 struct Comm; // tb2_comm.cu
+// what the overlapped multi-GPU explicit step (tb2_explicit.cu) needs from the communicator
+struct CommPlan {
+    int64_t n_if = 0, n_glob = 0, nb = 0;
+    const int* nodes = nullptr;     // [n_if] local ids of the interface nodes
+    const int* slots = nullptr;     // [n_if] their slots in the packed global interface vector
+    const int* node_slot = nullptr; // [nn] slot of a node, -1 for nodes private to this rank
+    const int* belems = nullptr;    // [nb] elements touching an interface node, ascending
+    const unsigned char* belem_flag = nullptr; // [ne] 1 for those elements
+    double* packed = nullptr;       // [n_glob][3]
+    cudaStream_t stream = nullptr;  // the collective runs here, beside the element sweep
+    cudaEvent_t ev_packed = nullptr, ev_reduced = nullptr, ev_done = nullptr;
+};
 
 // per-kernel CUDA-event timing on the mesh stream (bench.py's roofline numbers are measured with these, live, inside the
 // timed region) and a count of our own kernel launches

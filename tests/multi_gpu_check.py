@@ -56,6 +56,48 @@ def static_pcg(m, X, ns):
     return d, it
 
 
+def pipelined_phase(rank, world, local):
+    """64^3 elements per rank -> 3+ slab chunks: the overlapped schedule (boundary elements first, all-reduce beside the slab
+    pipeline, interface nodes updated last) must give bitwise the fields of the serial schedule (single-step calls), and both
+    must match the single-GPU run of the whole mesh"""
+    n, nsteps = 64, 6
+    gx, gy, gz = tmesh.brick_grid(world)
+    dims = (n * gx, n * gy, n * gz)
+    dt = 0.25 / max(dims) / np.sqrt(1000.0 + 20.0 / 3.0)
+    part = tmesh.partition_cube(*dims, world, rank, jitter=0.1)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
+    m, g, ex = setup(part["coords"], part["conn"], part["nodesets"], local, comm)
+    ex.run(dt, nsteps)
+    piped = ex.get_state()
+    ex.set_state(field(part["coords"]), np.zeros_like(part["coords"]), np.zeros_like(part["coords"]))
+    for _ in range(nsteps):
+        ex.run(dt, 1)
+    serial = ex.get_state()
+    ok = all(np.array_equal(a, b) for a, b in zip(piped, serial))
+    if not ok:
+        print("rank %d: overlapped schedule differs bitwise from the serial one: %s"
+              % (rank, [float(np.abs(a - b).max()) for a, b in zip(piped, serial)]))
+    out = [None] * world
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": piped[0], "v": piped[1], "a": piped[2]})
+    ex.close(); g.close(); m.close()
+    if rank == 0:
+        X, conn, ns = tmesh.structured_cube(*dims, jitter=0.1)
+        m1, g1, ex1 = setup(X, conn, ns, local)
+        ex1.run(dt, nsteps)
+        ref = dict(zip("dva", ex1.get_state()))
+        for r, o in enumerate(out):
+            for nm in "dva":
+                err = np.abs(o[nm] - ref[nm][o["gid"]]).max() / max(np.abs(ref[nm]).max(), 1e-300)
+                if not err < 1e-12:
+                    print("pipelined phase: rank %d field %s differs from the single-GPU run: %.3e" % (r, nm, err))
+                    ok = False
+        ex1.close(); g1.close(); m1.close()
+        print("multi_gpu_check: pipelined phase world=%d %s" % (world, "OK" if ok else "FAILED"))
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -105,10 +147,11 @@ def main():
                 seen[gid] = row
         assert len(seen) == nn_glob
         print("multi_gpu_check: world=%d %s" % (world, "OK" if ok else "FAILED"))
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, src=0)
-    dist.barrier()
     ex.close(); g.close(); m.close()
+    ok = pipelined_phase(rank, world, local) and ok
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 
