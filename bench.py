@@ -448,6 +448,12 @@ def run_gpu_arm(args):
     for _ in range(e2e_steps):
         ex.step_host_ptr(dt, hd.data_ptr(), hv.data_ptr(), ha.data_ptr())
     e1.record(stream)
+    if os.environ.get("TB2_PROF_DUMP_E2E"):  # diagnostics only: launch/copy timeline of one more host-buffer step
+        os.environ["TB2_PROF_DUMP"] = os.environ["TB2_PROF_DUMP_E2E"]
+        m.profile_begin()
+        ex.step_host_ptr(dt, hd.data_ptr(), hv.data_ptr(), ha.data_ptr())
+        m.profile_end()
+        del os.environ["TB2_PROF_DUMP"]
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) if world == 1 else 0.0)
     te = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)

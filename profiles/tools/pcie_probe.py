@@ -1,0 +1,28 @@
+import torch, time
+n = 74_181_672 // 8
+h_in = torch.zeros(n, dtype=torch.float64).pin_memory()
+h_out = torch.zeros(n, dtype=torch.float64).pin_memory()
+d_a = torch.zeros(n, dtype=torch.float64, device="cuda")
+d_b = torch.zeros(n, dtype=torch.float64, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def t(fn, reps=10):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+def h2d():
+    with torch.cuda.stream(s1): d_a.copy_(h_in, non_blocking=True)
+def d2h():
+    with torch.cuda.stream(s2): h_out.copy_(d_b, non_blocking=True)
+def both():
+    h2d(); d2h()
+def chunked(k=16):
+    c = n // k
+    for i in range(k):
+        with torch.cuda.stream(s1): d_a[i*c:(i+1)*c].copy_(h_in[i*c:(i+1)*c], non_blocking=True)
+        with torch.cuda.stream(s2): h_out[i*c:(i+1)*c].copy_(d_b[i*c:(i+1)*c], non_blocking=True)
+mb = n * 8 / 1e6
+for name, fn in (("h2d", h2d), ("d2h", d2h), ("both", both), ("chunked16", chunked)):
+    ms = t(fn)
+    print(f"{name}: {ms:.3f} ms  ({mb/ms:.1f} GB/s per direction)")

@@ -115,6 +115,15 @@ def device_count():
     return n.value
 
 
+def host_register(arr):
+    """pin a host array (tb2_host_register): async copies, and kernel-written results in tb2_explicit_step_host"""
+    _chk(lib().tb2_host_register(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)))
+
+
+def host_unregister(arr):
+    _chk(lib().tb2_host_unregister(C.c_void_p(arr.ctypes.data)))
+
+
 def measure_fp64_peak(device=0):
     t = C.c_double(0.0)
     _chk(lib().tb2_measure_fp64_peak(int(device), C.byref(t)))

@@ -114,6 +114,42 @@ static void build_pipeline(tb2_mesh* m, const int32_t* h_conn, int sm_count)
     }
 }
 
+// the same bookkeeping for the host-buffer step: C equal slabs (no wave rounding: the copies, not the kernels, set the pace)
+static void build_host_plan(tb2_mesh* m, const int32_t* h_conn)
+{
+    PipePlan& P = m->hplan;
+    int64_t C = 16;
+    if (const char* s = getenv("TB2_HOST_CHUNKS")) {
+        const int want = atoi(s);
+        if (want >= 1) C = want;
+    }
+    if (m->ne < 64 * C) C = 1;
+    const int64_t chunk = (m->ne + C - 1) / C;
+    P.e0.assign(C + 1, 0);
+    P.n0.assign(C + 1, 0);
+    for (int64_t c = 0; c <= C; c++) {
+        P.e0[c] = c * chunk < m->ne ? c * chunk : m->ne;
+        P.n0[c] = m->nn * c / C;
+    }
+    P.emax_of_nc.assign(C, -1);
+    P.nmax_of_ec.assign(C, -1);
+    for (int64_t e = 0; e < m->ne; e++) {
+        const int ce = (int)(e / chunk);
+        for (int a = 0; a < 8; a++) {
+            const int64_t n = h_conn[8 * e + a];
+            int nc = (int)(n * C / m->nn);
+            while (nc + 1 < C && P.n0[nc + 1] <= n) nc++;
+            while (nc > 0 && P.n0[nc] > n) nc--;
+            if (ce > P.emax_of_nc[nc]) P.emax_of_nc[nc] = ce;
+            if (nc > P.nmax_of_ec[ce]) P.nmax_of_ec[ce] = nc;
+        }
+    }
+    for (int64_t c = 1; c < C; c++) {
+        if (P.emax_of_nc[c] < P.emax_of_nc[c - 1]) P.emax_of_nc[c] = P.emax_of_nc[c - 1];
+        if (P.nmax_of_ec[c] < P.nmax_of_ec[c - 1]) P.nmax_of_ec[c] = P.nmax_of_ec[c - 1];
+    }
+}
+
 } // namespace tb2
 
 using namespace tb2;
@@ -246,6 +282,7 @@ int tb2_mesh_create(int device, int64_t nn, int64_t ne, const int32_t* h_conn, c
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     build_pipeline(m, h_conn, prop.multiProcessorCount);
+    build_host_plan(m, h_conn);
     *out = m;
     return TB2_OK;
 }
@@ -266,6 +303,14 @@ int tb2_mesh_destroy(tb2_mesh* m)
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
+    for (cudaStream_t st : {m->stream_h2d, m->stream_d2h})
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    for (auto* v : {&m->ev_h2d, &m->ev_pred, &m->ev_hk1, &m->ev_hk5})
+        for (auto e : *v) cudaEventDestroy(e);
+    if (m->ev_d2h_done) cudaEventDestroy(m->ev_d2h_done);
     for (auto e : m->ev_k1) cudaEventDestroy(e);
     for (auto e : m->ev_k5) cudaEventDestroy(e);
     if (m->ev_join) cudaEventDestroy(m->ev_join);

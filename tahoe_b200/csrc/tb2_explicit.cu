@@ -40,7 +40,8 @@ TB2_DEV void cd_correct(double dt, double& v, double& a, double upd)
 // predictor + ConsistentKBC, one thread per dof
 __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, double* __restrict__ d, double* __restrict__ v,
                                                      double* __restrict__ a, const unsigned char* __restrict__ code,
-                                                     const double* __restrict__ bcval, double value_scale)
+                                                     const double* __restrict__ bcval, double value_scale,
+                                                     double* __restrict__ host_d = nullptr)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= ndof) return;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, d
     d[i] = di;
     v[i] = vi;
     a[i] = 0.0;
+    if (host_d) host_d[i] = di; // host-buffer step: d is final for this step, it goes straight back over PCIe (mapped pinned memory)
 }
 
 // node kernel: gather fint, R = s*fext - fint, upd = minv*R on free dofs, corrector; optionally the next predictor.
@@ -107,6 +109,54 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
         }
         v[q] = vi;
         a[q] = ai;
+    }
+}
+
+// Host-buffer step: k_cd_node_update<gather, no next predictor> that also writes v and a to the caller's (mapped, pinned) host
+// arrays.  The block's 3 x 256 results are staged in shared memory so that every warp store to host memory is a contiguous
+// 256-byte run (posted PCIe writes; the copy engines stay free for the host -> device direction).
+__global__ void __launch_bounds__(256) k_cd_node_update_hostout(int64_t n_begin, int64_t nn, const int* __restrict__ inc_ptr,
+                                                               const int* __restrict__ inc, const double* __restrict__ fe, int64_t stride,
+                                                               double dt, double fext_scale, const double* __restrict__ fext,
+                                                               const double* __restrict__ minv, const unsigned char* __restrict__ code,
+                                                               double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint,
+                                                               double* __restrict__ host_v, double* __restrict__ host_a)
+{
+    __shared__ double sv[768], sa[768];
+    const int64_t nb0 = n_begin + blockIdx.x * (int64_t)blockDim.x;
+    const int64_t n = nb0 + threadIdx.x;
+    if (n < nn) {
+        double f[3] = {0.0, 0.0, 0.0};
+        const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
+        for (int k = k0; k < k1; k++) {
+            const int ent = __ldg(inc + k);
+            const int64_t e = ent >> 3;
+            const int a3 = 3 * (ent & 7);
+            f[0] += __ldg(fe + (int64_t)(a3)*stride + e);
+            f[1] += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
+            f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int64_t q = 3 * n + i;
+            const unsigned char c = code[q];
+            const double R = __dsub_rn(__dmul_rn(fext_scale, fext[q]), f[i]);
+            const double upd = c ? 0.0 : __dmul_rn(R, minv[q]);
+            double vi = v[q], ai = a[q];
+            cd_correct(dt, vi, ai, upd);
+            fint[q] = f[i];
+            v[q] = vi;
+            a[q] = ai;
+            sv[3 * threadIdx.x + i] = vi;
+            sa[3 * threadIdx.x + i] = ai;
+        }
+    }
+    __syncthreads();
+    const int64_t nb1 = nb0 + blockDim.x < nn ? nb0 + blockDim.x : nn;
+    const int cnt = (int)(3 * (nb1 - nb0));
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        host_v[3 * nb0 + t] = sv[t];
+        host_a[3 * nb0 + t] = sa[t];
     }
 }
 
@@ -305,6 +355,139 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
     return TB2_OK;
 }
 
+static bool pipeline_enabled();
+
+// One step through HOST arrays (Tahoe's FieldT stays authoritative: d, v, a come in and go back every step), as a slab pipeline
+// over four streams so that PCIe runs in both directions at once:
+//   h2d stream   d, v, a of node slab 0, 1, 2, ...                                      (host -> device)
+//   main stream  predictor of a slab as soon as it has landed; K1 of an element slab once the node slabs it touches are predicted
+//   second       K5 (gather, M^-1 R, corrector) of a node slab once the element slabs touching it are done
+//   d2h stream   d of a slab right after its predictor, v and a right after its K5         (device -> host)
+// Same kernels, same arithmetic and summation order as the serial path: bitwise identical fields (tested).
+// device alias of a host pointer when the memory is pinned and mapped (cudaHostAlloc / cudaHostRegister), else null
+static double* mapped_host_alias(double* h)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? (double*)at.devicePointer : nullptr;
+}
+
+static int explicit_step_host_pipelined(tb2_explicit* ex, double dt, double* h_d, double* h_v, double* h_a)
+{
+    tb2_group* g = ex->group;
+    tb2_mesh* m = g->mesh;
+    const PipePlan& P = m->hplan;
+    const int C = P.chunks();
+    const int T = 256;
+    // Opt-in (TB2_HOST_FUSED_D2H=1) for pinned + mapped host arrays: the kernels write the results to the host themselves and the
+    // copy engines only upload.  Measured on the B200 box (profiles/r01c_summary.md): slower than the copy-engine download
+    // (2.7 vs 2.4 ms per 1M-element step) -- 8-byte posted writes from the SMs reach 12-26 GB/s and slow the upload beside them.
+    static const bool fuse_allowed = getenv("TB2_HOST_FUSED_D2H") && getenv("TB2_HOST_FUSED_D2H")[0] == '1';
+    double *md = fuse_allowed ? mapped_host_alias(h_d) : nullptr, *mv = fuse_allowed ? mapped_host_alias(h_v) : nullptr,
+           *ma = fuse_allowed ? mapped_host_alias(h_a) : nullptr;
+    const bool fused = fuse_allowed && md && mv && ma;
+    if (!m->stream2) {
+        TB2_CUDA(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+        const int Cc = (int)m->pipe_e0.size() - 1;
+        m->ev_k1.resize(Cc);
+        m->ev_k5.resize(Cc);
+        for (int c = 0; c < Cc; c++) {
+            TB2_CUDA(cudaEventCreateWithFlags(&m->ev_k1[c], cudaEventDisableTiming));
+            TB2_CUDA(cudaEventCreateWithFlags(&m->ev_k5[c], cudaEventDisableTiming));
+        }
+        TB2_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    if (!m->stream_h2d) {
+        TB2_CUDA(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
+        TB2_CUDA(cudaStreamCreateWithFlags(&m->stream_d2h, cudaStreamNonBlocking));
+        for (auto* v : {&m->ev_h2d, &m->ev_pred, &m->ev_hk1, &m->ev_hk5}) {
+            v->resize(C);
+            for (int c = 0; c < C; c++) TB2_CUDA(cudaEventCreateWithFlags(&(*v)[c], cudaEventDisableTiming));
+        }
+        TB2_CUDA(cudaEventCreateWithFlags(&m->ev_d2h_done, cudaEventDisableTiming));
+    }
+    // everything queued on the mesh stream so far (state uploads, earlier steps) precedes the copies
+    TB2_CUDA(cudaEventRecord(m->ev_join, m->stream));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream_h2d, m->ev_join, 0));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream_d2h, m->ev_join, 0));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_join, 0));
+    for (int nc = 0; nc < C; nc++) {
+        const int64_t o = 3 * P.n0[nc];
+        const size_t bytes = (size_t)(3 * (P.n0[nc + 1] - P.n0[nc])) * sizeof(double);
+        if (bytes) {
+            ProfScope ps(m, kProfOther, 0, m->stream_h2d);
+            TB2_CUDA(cudaMemcpyAsync(ex->d.p + o, h_d + o, bytes, cudaMemcpyHostToDevice, m->stream_h2d));
+            TB2_CUDA(cudaMemcpyAsync(ex->v.p + o, h_v + o, bytes, cudaMemcpyHostToDevice, m->stream_h2d));
+            TB2_CUDA(cudaMemcpyAsync(ex->a.p + o, h_a + o, bytes, cudaMemcpyHostToDevice, m->stream_h2d));
+        }
+        TB2_CUDA(cudaEventRecord(m->ev_h2d[nc], m->stream_h2d));
+    }
+    int np = 0, nc = 0;
+    // predictor + ConsistentKBC of node slabs [np, upto], each as soon as its copy has landed; d of the slab goes straight back
+    auto predict_upto = [&](int upto) -> int {
+        for (; np < C && np <= upto; np++) {
+            const int64_t o = 3 * P.n0[np], cnt = 3 * (P.n0[np + 1] - P.n0[np]);
+            TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_h2d[np], 0));
+            if (cnt) {
+                ProfScope ps(m, kProfPredictor);
+                k_cd_predictor<<<(unsigned)((cnt + T - 1) / T), T, 0, m->stream>>>(cnt, dt, ex->d.p + o, ex->v.p + o, ex->a.p + o, ex->bccode.p + o,
+                                                                                  ex->bcval.p + o, 1.0, fused ? md + o : nullptr);
+            }
+            TB2_CUDA(cudaEventRecord(m->ev_pred[np], m->stream));
+            if (!fused) {
+                TB2_CUDA(cudaStreamWaitEvent(m->stream_d2h, m->ev_pred[np], 0));
+                if (cnt) {
+                    ProfScope ps(m, kProfOther, 0, m->stream_d2h);
+                    TB2_CUDA(cudaMemcpyAsync(h_d + o, ex->d.p + o, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, m->stream_d2h));
+                }
+            }
+        }
+        return TB2_OK;
+    };
+    for (int c = 0; c < C; c++) {
+        TB2_CHECK(predict_upto(P.nmax_of_ec[c])); // the node slabs this element slab reads
+        TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, P.e0[c], P.e0[c + 1], m->stream));
+        TB2_CUDA(cudaEventRecord(m->ev_hk1[c], m->stream));
+        for (; nc < C && P.emax_of_nc[nc] <= c; nc++) {
+            const int64_t n0 = P.n0[nc], n1 = P.n0[nc + 1];
+            const int64_t o = 3 * n0;
+            if (np <= nc) TB2_CHECK(predict_upto(nc)); // a node slab no element of slabs <= c touches
+            TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_pred[nc], 0));
+            if (P.emax_of_nc[nc] >= 0) TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_hk1[P.emax_of_nc[nc]], 0));
+            if (n1 > n0) {
+                ProfScope ps(m, kProfNodeUpdate, 1, m->stream2);
+                const unsigned nb = (unsigned)((n1 - n0 + T - 1) / T);
+                if (fused)
+                    k_cd_node_update_hostout<<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, 1.0, ex->fext.p,
+                                                                      ex->minv.p, ex->bccode.p, ex->v.p, ex->a.p, ex->fint.p, mv, ma);
+                else
+                    k_cd_node_update<true, false><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, 1.0, 1.0,
+                                                                           ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p,
+                                                                           ex->a.p, ex->fint.p);
+            }
+            TB2_CUDA(cudaEventRecord(m->ev_hk5[nc], m->stream2));
+            if (!fused) {
+                TB2_CUDA(cudaStreamWaitEvent(m->stream_d2h, m->ev_hk5[nc], 0));
+                if (n1 > n0) {
+                    const size_t bytes = (size_t)(3 * (n1 - n0)) * sizeof(double);
+                    ProfScope ps(m, kProfOther, 0, m->stream_d2h);
+                    TB2_CUDA(cudaMemcpyAsync(h_v + o, ex->v.p + o, bytes, cudaMemcpyDeviceToHost, m->stream_d2h));
+                    TB2_CUDA(cudaMemcpyAsync(h_a + o, ex->a.p + o, bytes, cudaMemcpyDeviceToHost, m->stream_d2h));
+                }
+            }
+        }
+    }
+    TB2_CUDA(cudaEventRecord(m->ev_d2h_done, m->stream_d2h));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_d2h_done, 0));
+    TB2_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+    TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
 static bool pipeline_enabled()
 {
     static int on = -1;
@@ -475,6 +658,10 @@ int tb2_explicit_step_host(tb2_explicit* ex, double dt, double* h_d, double* h_v
     tb2_mesh* m = ex->group->mesh;
     DeviceGuard dg(m->device);
     const size_t bytes = 3 * m->nn * sizeof(double);
+    if (!comm_active(m) && m->hplan.chunks() > 1 && pipeline_enabled()) {
+        TB2_CHECK(explicit_step_host_pipelined(ex, dt, h_d, h_v, h_a));
+        return tb2_group_status(ex->group, nullptr);
+    }
     TB2_CUDA(cudaMemcpyAsync(ex->d.p, h_d, bytes, cudaMemcpyHostToDevice, m->stream));
     TB2_CUDA(cudaMemcpyAsync(ex->v.p, h_v, bytes, cudaMemcpyHostToDevice, m->stream));
     TB2_CUDA(cudaMemcpyAsync(ex->a.p, h_a, bytes, cudaMemcpyHostToDevice, m->stream));

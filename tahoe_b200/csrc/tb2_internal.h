@@ -95,6 +95,15 @@ struct ProfRec {
 
 } // namespace tb2
 
+namespace tb2 {
+// contiguous element / node index chunks and their dependency ranges (slab pipelines of tb2_explicit.cu)
+struct PipePlan {
+    std::vector<int64_t> e0, n0;            // element chunks [e0[c], e0[c+1]), node chunks likewise
+    std::vector<int> emax_of_nc, nmax_of_ec; // last element chunk touching node chunk c / last node chunk touched by element chunk c
+    int chunks() const { return (int)e0.size() - 1; }
+};
+} // namespace tb2
+
 struct tb2_mesh {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -115,6 +124,12 @@ struct tb2_mesh {
     // pipe_emax_of_nc[c] = last element chunk touching node chunk c, pipe_nmax_of_ec[c] = last node chunk touched by element chunk c
     std::vector<int64_t> pipe_e0, pipe_n0;
     std::vector<int> pipe_emax_of_nc, pipe_nmax_of_ec;
+    // host-buffer step (tb2_explicit_step_host): finer slabs, so that the H2D copy of the later slabs and the D2H copy of the
+    // finished ones overlap (full-duplex PCIe) with the kernels in between
+    tb2::PipePlan hplan;
+    cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_h2d, ev_pred, ev_hk1, ev_hk5;
+    cudaEvent_t ev_d2h_done = nullptr;
     cudaStream_t stream2 = nullptr;
     std::vector<cudaEvent_t> ev_k1, ev_k5;
     cudaEvent_t ev_join = nullptr;

@@ -115,8 +115,12 @@ def test_explicit_central_difference_matches_reference(tb2, name):
         assert relerr(a, c.ref("a_%d" % k)) < TOL
 
 
-def test_explicit_step_host_equals_resident_run(tb2):
-    X, conn, ns, u = _synthetic((6, 6, 6), amp=5e-3)
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("dims", [(6, 6, 6), (24, 20, 17), (40, 40, 40)])
+def test_explicit_step_host_equals_resident_run(tb2, dims, pinned):
+    """host-buffer step (tb2_explicit_step_host; >= 1024 elements: the slab pipeline that overlaps the upload, the kernels and
+    the download; pinned = registered host arrays, which the kernels write directly) against the device-resident run: bitwise"""
+    X, conn, ns, u = _synthetic(dims, amp=5e-3)
     mesh = tb2.Mesh(X, conn)
     grp = tb2.Group(mesh, 1, tb2.material({"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0}))
     code = np.zeros(X.shape, np.uint8)
@@ -128,8 +132,16 @@ def test_explicit_step_host_equals_resident_run(tb2):
     ex.run(dt, 5)
     d1, v1, a1 = ex.get_state()
     d, v, a = u.copy(), np.zeros_like(X), np.zeros_like(X)
-    for _ in range(5):
-        ex.step_host(dt, d, v, a)
+    if pinned:
+        for arr in (d, v, a):
+            tb2.host_register(arr)
+    try:
+        for _ in range(5):
+            ex.step_host(dt, d, v, a)
+    finally:
+        if pinned:
+            for arr in (d, v, a):
+                tb2.host_unregister(arr)
     assert np.array_equal(d, d1) and np.array_equal(v, v1) and np.array_equal(a, a1)
 
 
