@@ -138,6 +138,83 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
     }
 }
 
+// K1, total-Lagrangian SimoIso3D, shared-memory variant.  The 42 read-only mode coefficients of X and x = X + u live in shared
+// memory ([coefficient][thread]: private columns, conflict-free) instead of registers, which brings the kernel from 168-220
+// registers to ~100 and doubles the resident warps that feed the FP64 pipe.  Same arithmetic as k_internal_force except that
+// j = grad(x modes) is formed directly (the modes of x = X + u are summed once per element) instead of J0 + grad(u modes).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const ElemArgs p)
+{
+    __shared__ double sX[21][128], sx[21][128];
+    const int tid = threadIdx.x;
+    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + tid;
+    if (t >= p.ne) return;
+    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
+    if (p.skip && p.skip[e]) return;
+    {
+        int n[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+        Modes cX, cU;
+        load_modes(p.X, n, cX);
+        load_modes(p.u, n, cU);
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                sX[3 * k + i][tid] = cX.m[k][i];
+                sx[3 * k + i][tid] = cX.m[k][i] + cU.m[k][i];
+            }
+    }
+    Modes A;
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) A.m[k][i] = 0.0;
+    int err = kErrNone;
+#pragma unroll 1
+    for (int ip = 0; ip < 8; ip++) {
+        double s0, s1, s2;
+        ip_signs(ip, s0, s1, s2);
+        const double s12 = s1 * s2, s02 = s0 * s2, s01 = s0 * s1;
+        double J0[3][3], j[3][3], J0a[3][3], ja[3][3], F[3][3], G[3][3], S[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            J0[i][0] = sX[0 + i][tid] + s1 * sX[6 + i][tid] + s2 * sX[12 + i][tid] + s12 * sX[18 + i][tid];
+            J0[i][1] = sX[3 + i][tid] + s0 * sX[6 + i][tid] + s2 * sX[15 + i][tid] + s02 * sX[18 + i][tid];
+            J0[i][2] = sX[9 + i][tid] + s0 * sX[12 + i][tid] + s1 * sX[15 + i][tid] + s01 * sX[18 + i][tid];
+            j[i][0] = sx[0 + i][tid] + s1 * sx[6 + i][tid] + s2 * sx[12 + i][tid] + s12 * sx[18 + i][tid];
+            j[i][1] = sx[3 + i][tid] + s0 * sx[6 + i][tid] + s2 * sx[15 + i][tid] + s02 * sx[18 + i][tid];
+            j[i][2] = sx[9 + i][tid] + s0 * sx[12 + i][tid] + s1 * sx[15 + i][tid] + s01 * sx[18 + i][tid];
+        }
+        const double det0 = adj3(J0, J0a);
+        const double detj = adj3(j, ja);
+        if (det0 <= 0.0 || detj <= 0.0) err = kErrBadJacobian; // ParentDomainT.cpp:451 / TotalLagrangianT.cpp:127-128
+        mul3(j, J0a, F); // = det0 * F
+        const double rdd = 1.0 / (det0 * detj);
+        const double rd0 = rdd * detj, rJ = det0 * (det0 * rdd), J = detj * rd0;
+        double b[6], sig[6];
+        sym_fft(F, b);
+        sym_dev(b);
+        const double r = rcbrt(J);
+        const double sc = (p.mat.mu * rJ) * (r * r) * (rd0 * rd0); // (mu/J) J^(-2/3) / det0^2
+        const double pr = 0.5 * p.mat.kappa * (J - rJ);            // U'(J), SimoIso3D.h:93-96
+        sig[0] = sc * b[0] + pr; sig[1] = sc * b[1] + pr; sig[2] = sc * b[2] + pr;
+        sig[3] = sc * b[3]; sig[4] = sc * b[4]; sig[5] = sc * b[5];
+        sym_to_mat(sig, S);
+        mul3_abt(S, ja, G); // G = w det(j) sigma j^-T
+        mode_accumulate(A, s0, s1, s2, G);
+    }
+    if (err) report(p, err, e);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double f[8];
+        modes_to_nodes(A, i, f);
+#pragma unroll
+        for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
+    }
+}
+
 // K4: ContinuumElementT::FormMass, kLumpedMass branch (ContinuumElementT.cpp:767-842).  me[a] -> fe[a][stride]
 __global__ void __launch_bounds__(128) k_lumped_mass(int64_t ne, int64_t stride, const int* __restrict__ conn,
                                                     const double* __restrict__ X, double density, double* __restrict__ fe,
@@ -254,6 +331,13 @@ static force_kernel_t pick_force_kernel(int form, int mat)
     }
     // UpdatedLagrangianT shares the finite-strain body (see file header)
     if (form == kUpdatedLagrangian) form = kTotalLagrangian;
+    static int sm_variant = -1; // TB2_K1_SMEM=<resident CTAs per SM> selects the shared-memory-modes variant (experiment knob)
+    if (sm_variant < 0) {
+        const char* s = getenv("TB2_K1_SMEM");
+        sm_variant = s ? atoi(s) : 0;
+    }
+    if (form == kTotalLagrangian && mat == kSimoIso && sm_variant > 0)
+        return sm_variant <= 3 ? k_internal_force_simo_sm<3> : (sm_variant == 4 ? k_internal_force_simo_sm<4> : k_internal_force_simo_sm<5>);
     switch (form * 4 + mat) {
     case kSmallStrain * 4 + kSSKStV: return k_internal_force<kSmallStrain, kSSKStV, 2>;
     case kTotalLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV, 2>;

@@ -154,9 +154,9 @@ __global__ void k_elem_adjpos(int64_t ne, int64_t stride, const int* __restrict_
 // groups b*W+w, +gridDim*W, ...; the p.Ap partial of a block is accumulated in that fixed order (deterministic).
 // grp[g] = first row | (rows-1) << 30.
 template <bool WITH_DOT>
-__global__ void __launch_bounds__(256) k_spmv(int64_t ngroups, const int* __restrict__ grp, const long long* __restrict__ rowptr,
-                                              const int* __restrict__ colind, const double* __restrict__ val, const double* __restrict__ x,
-                                              double* __restrict__ y, double* __restrict__ partial, const int* __restrict__ done)
+__global__ void __launch_bounds__(256, 6) k_spmv(int64_t ngroups, const int* __restrict__ grp, const long long* __restrict__ rowptr,
+                                                 const int* __restrict__ colind, const double* __restrict__ val, const double* __restrict__ x,
+                                                 double* __restrict__ y, double* __restrict__ partial, const int* __restrict__ done)
 {
     if (WITH_DOT && done && *done) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -170,7 +170,21 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t ngroups, const int* __rest
         const double* v0 = val + k0;
         const int* c0 = colind + k0;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        if (nr == 3) {
+        if (nr == 3 && len <= 96) {
+            // the common case (a Q1 hex node couples to <= 27 nodes = 81 columns): all loads of the row group are issued before
+            // the first use, so one round trip to HBM covers the whole group instead of one per 32 columns
+            const int ka = lane, kb = lane + 32, kc = lane + 64;
+            const bool pa = ka < len, pb = kb < len, pc = kc < len;
+            const int ca = pa ? __ldcs(c0 + ka) : 0, cb = pb ? __ldcs(c0 + kb) : 0, cc = pc ? __ldcs(c0 + kc) : 0;
+            const double a0 = pa ? __ldcs(v0 + ka) : 0.0, a1 = pa ? __ldcs(v0 + len + ka) : 0.0, a2 = pa ? __ldcs(v0 + 2 * len + ka) : 0.0;
+            const double b0 = pb ? __ldcs(v0 + kb) : 0.0, b1 = pb ? __ldcs(v0 + len + kb) : 0.0, b2 = pb ? __ldcs(v0 + 2 * len + kb) : 0.0;
+            const double d0 = pc ? __ldcs(v0 + kc) : 0.0, d1 = pc ? __ldcs(v0 + len + kc) : 0.0, d2 = pc ? __ldcs(v0 + 2 * len + kc) : 0.0;
+            const double xa = pa ? __ldg(x + ca) : 0.0, xb = pb ? __ldg(x + cb) : 0.0, xc = pc ? __ldg(x + cc) : 0.0;
+            // same per-lane summation order as the generic loop below: k = lane, lane + 32, lane + 64
+            s0 = a0 * xa; s1 = a1 * xa; s2 = a2 * xa;
+            s0 += b0 * xb; s1 += b1 * xb; s2 += b2 * xb;
+            s0 += d0 * xc; s1 += d1 * xc; s2 += d2 * xc;
+        } else if (nr == 3) {
             for (int k = lane; k < len; k += 32) {
                 const double xv = __ldg(x + __ldcs(c0 + k));
                 s0 += __ldcs(v0 + k) * xv;
@@ -477,7 +491,27 @@ int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n);
 int comm_sum_interface_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec);
 
 static const int kReduceBlocks = 148 * 8;
-static const int kSpmvBlocks = 148 * 8; // persistent: 8 CTAs of 256 threads per SM
+static const int kSpmvBlocks = 148 * 8; // upper bound of the persistent SpMV grid (sizes the partial-sum buffer)
+// persistent SpMV grid: exactly the CTAs that are resident at once (SM count x occupancy of the kernel), so that no second,
+// thinner wave follows the first (r01c: a fixed 8/SM grid ran as 6 + 2 resident CTAs and averaged 53 % of the warp slots)
+static unsigned spmv_grid()
+{
+    static unsigned blocks = 0;
+    if (!blocks) {
+        int dev = 0, sms = 148, occ = 6, occ_dot = 6, envb = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<false>, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dot, k_spmv<true>, 256, 0);
+        if (occ_dot < occ) occ = occ_dot;
+        if (const char* e = getenv("TB2_SPMV_CTAS_PER_SM")) envb = atoi(e); // experiment knob
+        if (envb > 0) occ = envb;
+        if (occ < 1) occ = 1;
+        blocks = (unsigned)(sms * occ);
+        if (blocks > (unsigned)kSpmvBlocks) blocks = kSpmvBlocks;
+    }
+    return blocks;
+}
 
 } // namespace tb2
 
@@ -782,7 +816,7 @@ int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y)
     tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     ProfScope ps(m, kProfSpmv);
-    k_spmv<false><<<kSpmvBlocks, 256, 0, m->stream>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, d_y, nullptr, nullptr);
+    k_spmv<false><<<spmv_grid(), 256, 0, m->stream>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, d_y, nullptr, nullptr);
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
 }
@@ -833,7 +867,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     k_extract_dinv<<<nb1, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 0);
     TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->dinv.p));
     k_invert_diag<<<nb1, 256, 0, st>>>(n, A->dinv.p);
-    k_spmv<false><<<kSpmvBlocks, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
+    k_spmv<false><<<spmv_grid(), 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
     TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->q.p));
     k_pcg_init<<<vec_blocks, 256, 0, st>>>(n, d_b, A->q.p, A->dinv.p, A->r.p, A->z.p, A->p.p, A->partial.p, w);
     k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 2, A->partial.p, red, nullptr);
@@ -846,7 +880,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
         for (int k = 0; k < check_every && it < max_iter; k++, it++) {
             {
                 ProfScope ps(m, kProfSpmv);
-                k_spmv<false><<<kSpmvBlocks, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, nullptr, nullptr);
+                k_spmv<false><<<spmv_grid(), 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, nullptr, nullptr);
             }
             TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->q.p));
             ProfScope ps(m, kProfPcgVec, 8);
@@ -888,7 +922,7 @@ int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, d
     cudaStream_t st = m->stream;
     double* scal = A->scal.p;
     PcgCtl* ctl = (PcgCtl*)(A->scal.p + kNumScal);
-    const unsigned spmv_blocks = kSpmvBlocks;
+    const unsigned spmv_blocks = spmv_grid();
     int64_t vb = (n + 255) / 256;
     const unsigned vec_blocks = (unsigned)(vb < kReduceBlocks ? vb : kReduceBlocks);
     {
