@@ -295,6 +295,11 @@ int tb2_mesh_destroy(tb2_mesh* m)
     DeviceGuard g(m->device);
     if (m->comm) tb2_comm_destroy(m);
     cudaStreamSynchronize(m->stream);
+    if (m->stream1b) {
+        cudaStreamSynchronize(m->stream1b);
+        cudaStreamDestroy(m->stream1b);
+    }
+    if (m->ev_join1b) cudaEventDestroy(m->ev_join1b);
     if (m->stream2) {
         cudaStreamSynchronize(m->stream2);
         cudaStreamDestroy(m->stream2);

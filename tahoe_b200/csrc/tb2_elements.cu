@@ -41,8 +41,8 @@ TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
     atomicMin(p.status + 1, (unsigned long long)e);
 }
 
-template <int FORM, int MAT, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
+template <int FORM, int MAT>
+TB2_DEV void internal_force_body(const ElemArgs& p)
 {
     const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= p.ne) return;
@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
 #pragma unroll
     for (int k = 0; k < 7; k++)
 #pragma unroll
-        for (int i = 0; i < 3; i++) A.m[k][i] = 0.0;
+        for (int i = 0; i < 3; i++) {
+            A.m[k][i] = 0.0;
+            if (FORM != kSmallStrain) cU.m[k][i] += cX.m[k][i]; // finite strain: modes of x = X + u, so that j = dx/dxi directly
+        }
 
     int alloc = 0, err = kErrNone;
     if (MAT == kJ2Simo) alloc = p.hist.alloc[e];
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
         ip_signs(ip, s0, s1, s2);
         double J0[3][3], H[3][3], J0a[3][3], G[3][3], S[3][3];
         mode_gradient(cX, s0, s1, s2, J0);
-        mode_gradient(cU, s0, s1, s2, H);
+        mode_gradient(cU, s0, s1, s2, H); // small strain: du/dxi; finite strain: j = dx/dxi
         const double det0 = adj3(J0, J0a);
         if (det0 <= 0.0) err = kErrBadJacobian; // ParentDomainT::ComputeDNa, ParentDomainT.cpp:451
         const double rdet0 = 1.0 / det0;
@@ -89,27 +92,41 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
             sym_to_mat(sig, S);
             mul3_abt(S, J0a, G); // G = w detJ0 sigma J0^-T
         } else {
-            double j[3][3], ja[3][3], F[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) j[i][k] = J0[i][k] + H[i][k];
+            double ja[3][3], F[3][3];
+            const double (&j)[3][3] = H;
             const double detj = adj3(j, ja);
             if (detj <= 0.0) err = kErrBadJacobian; // TotalLagrangianT.cpp:127-128 / current-configuration ComputeDNa
-            mul3(j, J0a, F); // = det0 * F
             if (MAT == kSimoIso) {
-                // SimoIso3D::s_ij on the unscaled F' = det0 F: b = F'F'^T / det0^2, one reciprocal for 1/det0 and 1/J
-                const double rdd = 1.0 / (det0 * detj);
-                const double rd0 = rdd * detj, rJ = det0 * (det0 * rdd), J = detj * rd0;
-                double b[6];
-                sym_fft(F, b);
-                sym_dev(b);
-                const double r = rcbrt(J);
-                const double sc = (p.mat.mu * rJ) * (r * r) * (rd0 * rd0); // (mu/J) J^(-2/3) / det0^2
-                const double pr = 0.5 * p.mat.kappa * (J - rJ);            // U'(J), SimoIso3D.h:93-96
-                sig[0] = sc * b[0] + pr; sig[1] = sc * b[1] + pr; sig[2] = sc * b[2] + pr;
-                sig[3] = sc * b[3]; sig[4] = sc * b[4]; sig[5] = sc * b[5];
+                // SimoIso3D::s_ij (SimoIso3D.cpp:127-136) folded into the force integrand.  With F' = det0 F = j adj(J0) and
+                // cof(j) = adj(j)^T:  b' cof(j) = F' F'^T cof(j) = det(j) F' adj(J0)^T = det(j) j M0,  M0 = adj(J0) adj(J0)^T, so
+                //   G = w det(j) sigma j^-T = sc det(j) (j M0) + (U'(J) - sc tr(b')/3) cof(j),   tr(b') = (j M0) : j,
+                //   sc = (mu/J) J^(-2/3) / det0^2 = mu (det(j)^5 det0)^(-1/3):  one rcbrt and no division;
+                //   1/(det0 det j) = t^3 det(j)^4 with t = sc/mu supplies 1/J for U'(J) = kappa/2 (J - 1/J) (SimoIso3D.h:93-96).
+                double M0[6], N[3][3];
+                sym_fft(J0a, M0); // adj(J0) adj(J0)^T
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    N[i][0] = j[i][0] * M0[0] + j[i][1] * M0[5] + j[i][2] * M0[4];
+                    N[i][1] = j[i][0] * M0[5] + j[i][1] * M0[1] + j[i][2] * M0[3];
+                    N[i][2] = j[i][0] * M0[4] + j[i][1] * M0[3] + j[i][2] * M0[2];
+                }
+                double trb = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; i++) trb += N[i][0] * j[i][0] + N[i][1] * j[i][1] + N[i][2] * j[i][2];
+                const double dj2 = detj * detj;
+                const double t = rcbrt(dj2 * dj2 * detj * det0);
+                const double rdd = (t * t) * t * (dj2 * dj2);               // 1 / (det0 det j)
+                const double sc = p.mat.mu * t;
+                const double pr = 0.5 * p.mat.kappa * (dj2 - det0 * det0) * rdd; // U'(J) = kappa/2 (J - 1/J)
+                const double al = sc * detj, q = pr - sc * trb * (1.0 / 3.0);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
+                mode_accumulate(A, s0, s1, s2, G);
+                continue;
             }
+            mul3(j, J0a, F); // = det0 * F
             const double J = detj * rdet0;
             if (MAT != kSimoIso) scale3(F, rdet0);
             if (MAT == kFDKStV)
@@ -136,6 +153,20 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
 #pragma unroll
         for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
     }
+}
+
+// register budget by resident CTAs per SM (MINB CTAs of THREADS threads) ...
+template <int FORM, int MAT, int MINB, int THREADS = 128>
+__global__ void __launch_bounds__(THREADS, MINB) k_internal_force(const ElemArgs p)
+{
+    internal_force_body<FORM, MAT>(p);
+}
+// ... or by an explicit register cap: 3 CTAs of 128 threads at 144 registers leave 8 K registers per SM to the node kernel that
+// runs beside the sweep in the slab pipeline (at 168 the sweep owns the whole register file and the node kernel starves)
+template <int FORM, int MAT, int REGS>
+__global__ void __launch_bounds__(128) __maxnreg__(REGS) k_internal_force_r(const ElemArgs p)
+{
+    internal_force_body<FORM, MAT>(p);
 }
 
 // K1, total-Lagrangian SimoIso3D, shared-memory variant.  The 42 read-only mode coefficients of X and x = X + u live in shared
@@ -327,7 +358,7 @@ static force_kernel_t pick_force_kernel(int form, int mat)
     if (!minb) {
         const char* s = getenv("TB2_K1_MINBLOCKS");
         minb = s ? atoi(s) : kDefaultMinBlocks;
-        if (minb < 2 || minb > 4) minb = kDefaultMinBlocks;
+        if (minb < 2 || minb > 8) minb = kDefaultMinBlocks;
     }
     // UpdatedLagrangianT shares the finite-strain body (see file header)
     if (form == kUpdatedLagrangian) form = kTotalLagrangian;
@@ -336,12 +367,30 @@ static force_kernel_t pick_force_kernel(int form, int mat)
         const char* s = getenv("TB2_K1_SMEM");
         sm_variant = s ? atoi(s) : 0;
     }
+    static int reg_variant = -1; // TB2_K1_REGS=144|152|160: explicit register cap (experiment knob)
+    if (reg_variant < 0) {
+        const char* s = getenv("TB2_K1_REGS");
+        reg_variant = s ? atoi(s) : 0;
+    }
+    if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 144) return k_internal_force_r<kTotalLagrangian, kSimoIso, 144>;
+    if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 152) return k_internal_force_r<kTotalLagrangian, kSimoIso, 152>;
+    if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 160) return k_internal_force_r<kTotalLagrangian, kSimoIso, 160>;
+    static int threads_variant = -1; // TB2_K1_THREADS=64|96: smaller CTAs at a finer register cap (experiment knob)
+    if (threads_variant < 0) {
+        const char* s = getenv("TB2_K1_THREADS");
+        threads_variant = s ? atoi(s) : 0;
+    }
+    if (form == kTotalLagrangian && mat == kSimoIso && threads_variant == 64)
+        return minb <= 6 ? k_internal_force<kTotalLagrangian, kSimoIso, 6, 64> : (minb == 7 ? k_internal_force<kTotalLagrangian, kSimoIso, 7, 64> : k_internal_force<kTotalLagrangian, kSimoIso, 8, 64>);
+    if (form == kTotalLagrangian && mat == kSimoIso && threads_variant == 96)
+        return minb <= 4 ? k_internal_force<kTotalLagrangian, kSimoIso, 4, 96> : k_internal_force<kTotalLagrangian, kSimoIso, 5, 96>;
     if (form == kTotalLagrangian && mat == kSimoIso && sm_variant > 0)
         return sm_variant <= 3 ? k_internal_force_simo_sm<3> : (sm_variant == 4 ? k_internal_force_simo_sm<4> : k_internal_force_simo_sm<5>);
     switch (form * 4 + mat) {
     case kSmallStrain * 4 + kSSKStV: return k_internal_force<kSmallStrain, kSSKStV, 2>;
     case kTotalLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV, 2>;
     case kTotalLagrangian * 4 + kSimoIso:
+        if (minb > 4) minb = 4;
         return minb == 2 ? k_internal_force<kTotalLagrangian, kSimoIso, 2>
                          : (minb == 3 ? k_internal_force<kTotalLagrangian, kSimoIso, 3> : k_internal_force<kTotalLagrangian, kSimoIso, 4>);
     case kTotalLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo, 2>;
@@ -398,7 +447,15 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
     p.hist = group_hist(g);
     p.iteration = iteration;
     p.status = g->status.p;
-    const int T = 128;
+    int T = 128;
+    if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_SIMO_ISO) {
+        static int tv = -1;
+        if (tv < 0) {
+            const char* s = getenv("TB2_K1_THREADS");
+            tv = s ? atoi(s) : 0;
+        }
+        if ((tv == 64 || tv == 96) && !(getenv("TB2_K1_SMEM") && atoi(getenv("TB2_K1_SMEM")) > 0)) T = tv;
+    }
     if (e1 <= e0) return TB2_OK;
     {
         ProfScope ps(m, kProfForce, 1, st);

@@ -77,10 +77,33 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
     double f[3] = {0.0, 0.0, 0.0};
     if (GATHER) {
         const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
-        for (int k = k0; k < k1; k++) {
-            const int ent = __ldg(inc + k);
-            const int64_t e = ent >> 3;
-            const int a3 = 3 * (ent & 7);
+        // the first 8 incident elements (all of them on a hex mesh without irregular nodes): every load is issued before the first
+        // add, so that a few resident warps keep enough bytes in flight while the element sweep holds most of the SM.  The sum
+        // runs in the same ascending-element order as the plain loop that handles any further entries.
+        int ent[8];
+        double g[8][3];
+#pragma unroll
+        for (int q = 0; q < 8; q++) ent[q] = k0 + q < k1 ? __ldg(inc + k0 + q) : -1;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const bool on = ent[q] >= 0;
+            const int64_t e = ent[q] >> 3;
+            const int a3 = 3 * (ent[q] & 7);
+            g[q][0] = on ? __ldg(fe + (int64_t)(a3)*stride + e) : 0.0;
+            g[q][1] = on ? __ldg(fe + (int64_t)(a3 + 1) * stride + e) : 0.0;
+            g[q][2] = on ? __ldg(fe + (int64_t)(a3 + 2) * stride + e) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (ent[q] >= 0) {
+                f[0] += g[q][0];
+                f[1] += g[q][1];
+                f[2] += g[q][2];
+            }
+        for (int k = k0 + 8; k < k1; k++) {
+            const int en = __ldg(inc + k);
+            const int64_t e = en >> 3;
+            const int a3 = 3 * (en & 7);
             f[0] += __ldg(fe + (int64_t)(a3)*stride + e);
             f[1] += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
             f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
@@ -267,6 +290,8 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
     const int C = (int)m->pipe_e0.size() - 1;
     const int64_t ndof = 3 * m->nn;
     const int T = 256;
+    // node-kernel CTA size in the pipeline: small CTAs fit into the registers the element sweep leaves free (experiment knob)
+    static const int T5 = (getenv("TB2_K5_THREADS") && atoi(getenv("TB2_K5_THREADS")) >= 32) ? atoi(getenv("TB2_K5_THREADS")) : 128;
     if (!m->stream2) {
         // the HBM-bound node kernels outrank the FP64-bound element sweep they run beside (their CTAs are small and short)
         int prio_lo = 0, prio_hi = 0;
@@ -286,8 +311,17 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
         k_cd_predictor<<<(unsigned)((ndof + T - 1) / T), T, 0, m->stream>>>(ndof, dt, ex->d.p, ex->v.p, ex->a.p, ex->bccode.p, ex->bcval.p,
                                                                            vs ? vs[0] : 1.0);
     }
+    // Experiment knob TB2_K1_STREAMS=2: consecutive element chunks alternate between two streams (they are independent of each
+    // other; only the events order them against the node chunks), so that chunk c+1 fills the SMs the last wave of chunk c is
+    // leaving.  Measured on B200 (1M elements): 0.269 ms/step against 0.263 with one stream -- off by default.
+    static const bool two_k1_streams = getenv("TB2_K1_STREAMS") && getenv("TB2_K1_STREAMS")[0] == '2';
+    if (two_k1_streams && !m->stream1b) {
+        TB2_CUDA(cudaStreamCreateWithFlags(&m->stream1b, cudaStreamNonBlocking));
+        TB2_CUDA(cudaEventCreateWithFlags(&m->ev_join1b, cudaEventDisableTiming));
+    }
     TB2_CUDA(cudaEventRecord(m->ev_join, m->stream));
     TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_join, 0));
+    if (two_k1_streams) TB2_CUDA(cudaStreamWaitEvent(m->stream1b, m->ev_join, 0));
     const auto t_enqueue0 = std::chrono::steady_clock::now();
     for (int s = 0; s < nsteps; s++) {
         const double fsc = fs ? fs[s] : 1.0;
@@ -321,30 +355,40 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
             TB2_CUDA(cudaStreamWaitEvent(m->stream2, cp.ev_packed, 0)); // K5 chunks of this step follow the boundary sweep
         }
         for (int c = 0; c < C; c++) {
-            if (s > 0 && m->pipe_nmax_of_ec[c] >= 0) TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_k5[m->pipe_nmax_of_ec[c]], 0));
-            TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, m->pipe_e0[c], m->pipe_e0[c + 1], m->stream, nullptr,
+            cudaStream_t sk = (two_k1_streams && (c & 1)) ? m->stream1b : m->stream;
+            if (s > 0 && m->pipe_nmax_of_ec[c] >= 0) TB2_CUDA(cudaStreamWaitEvent(sk, m->ev_k5[m->pipe_nmax_of_ec[c]], 0));
+            TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, m->pipe_e0[c], m->pipe_e0[c + 1], sk, nullptr,
                                                   multi ? cp.belem_flag : nullptr));
-            TB2_CUDA(cudaEventRecord(m->ev_k1[c], m->stream));
+            TB2_CUDA(cudaEventRecord(m->ev_k1[c], sk));
             for (; nc < C && m->pipe_emax_of_nc[nc] <= c; nc++) {
                 const int64_t n0 = m->pipe_n0[nc], n1 = m->pipe_n0[nc + 1];
-                if (m->pipe_emax_of_nc[nc] >= 0) TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_k1[m->pipe_emax_of_nc[nc]], 0));
+                if (m->pipe_emax_of_nc[nc] >= 0) {
+                    // "all element chunks <= emax are done": each of the two element streams runs its chunks in order
+                    TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_k1[m->pipe_emax_of_nc[nc]], 0));
+                    if (two_k1_streams && m->pipe_emax_of_nc[nc] >= 1)
+                        TB2_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_k1[m->pipe_emax_of_nc[nc] - 1], 0));
+                }
                 if (n1 > n0) {
                     ProfScope ps(m, kProfNodeUpdate, 1, m->stream2);
-                    const unsigned nb = (unsigned)((n1 - n0 + T - 1) / T);
+                    const unsigned nb = (unsigned)((n1 - n0 + T5 - 1) / T5);
                     if (s + 1 < nsteps)
-                        k_cd_node_update<true, true><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                        k_cd_node_update<true, true><<<nb, T5, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
                                                                               vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
                                                                               ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p, skip);
                     else
-                        k_cd_node_update<true, false><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
-                                                                               ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
-                                                                               ex->v.p, ex->a.p, ex->fint.p, skip);
+                        k_cd_node_update<true, false><<<nb, T5, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                                                                                ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
+                                                                                ex->v.p, ex->a.p, ex->fint.p, skip);
                 }
                 TB2_CUDA(cudaEventRecord(m->ev_k5[nc], m->stream2));
             }
         }
     }
     if (multi) TB2_CUDA(cudaStreamWaitEvent(m->stream, cp.ev_done, 0));
+    if (two_k1_streams) {
+        TB2_CUDA(cudaEventRecord(m->ev_join1b, m->stream1b));
+        TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join1b, 0));
+    }
     TB2_CUDA(cudaEventRecord(m->ev_join, m->stream2));
     TB2_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     TB2_CUDA(cudaGetLastError());

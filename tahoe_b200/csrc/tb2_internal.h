@@ -131,6 +131,8 @@ struct tb2_mesh {
     std::vector<cudaEvent_t> ev_h2d, ev_pred, ev_hk1, ev_hk5;
     cudaEvent_t ev_d2h_done = nullptr;
     cudaStream_t stream2 = nullptr;
+    cudaStream_t stream1b = nullptr; // odd element chunks of the slab pipeline (consecutive chunks overlap their launch tails)
+    cudaEvent_t ev_join1b = nullptr;
     std::vector<cudaEvent_t> ev_k1, ev_k5;
     cudaEvent_t ev_join = nullptr;
     bool prof_on = false;

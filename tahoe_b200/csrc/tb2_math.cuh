@@ -203,15 +203,16 @@ TB2_DEV void mode_gradient(const Modes& c, double s0, double s1, double s2, doub
 TB2_DEV void mode_accumulate(Modes& A, double s0, double s1, double s2, const double (&G)[3][3])
 {
     const double s12 = s1 * s2, s02 = s0 * s2, s01 = s0 * s1;
+    // explicit FMA chains: one instruction per term (a sum of products added to the accumulator costs one more)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         A.m[0][i] += G[i][0];
         A.m[1][i] += G[i][1];
         A.m[3][i] += G[i][2];
-        A.m[2][i] += s1 * G[i][0] + s0 * G[i][1];
-        A.m[4][i] += s2 * G[i][0] + s0 * G[i][2];
-        A.m[5][i] += s2 * G[i][1] + s1 * G[i][2];
-        A.m[6][i] += s12 * G[i][0] + s02 * G[i][1] + s01 * G[i][2];
+        A.m[2][i] = fma(s0, G[i][1], fma(s1, G[i][0], A.m[2][i]));
+        A.m[4][i] = fma(s0, G[i][2], fma(s2, G[i][0], A.m[4][i]));
+        A.m[5][i] = fma(s1, G[i][2], fma(s2, G[i][1], A.m[5][i]));
+        A.m[6][i] = fma(s01, G[i][2], fma(s02, G[i][1], fma(s12, G[i][0], A.m[6][i])));
     }
 }
 
