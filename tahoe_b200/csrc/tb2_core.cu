@@ -59,6 +59,16 @@ __global__ void k_lower_bound(int64_t nn, int64_t nkeys, const int* __restrict__
     ptr[n] = (int)lo;
 }
 
+__global__ void k_build_inc8(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc, int* __restrict__ inc8)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 8 * nn) return;
+    const int64_t n = t >> 3;
+    const int q = (int)(t & 7);
+    const int k = inc_ptr[n] + q;
+    inc8[t] = k < inc_ptr[n + 1] ? inc[k] : -1;
+}
+
 // FP64 FMA peak probe: 8 independent dependent-FMA chains per thread (the roofline denominator for K1/K3, which
 // MEASURED_PEAKS.json does not carry)
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double x, double y)
@@ -253,6 +263,7 @@ int tb2_mesh_create(int device, int64_t nn, int64_t ne, const int32_t* h_conn, c
     M_CUDA(m->X.alloc(3 * nn));
     M_CUDA(m->inc_ptr.alloc(nn + 1));
     M_CUDA(m->inc.alloc(8 * ne));
+    M_CUDA(m->inc8.alloc(8 * nn));
     M_CUDA(m->fe.alloc(24 * m->stride));
     M_CUDA(cudaMemcpyAsync(m->X.p, h_coords, 3 * nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     {
@@ -275,6 +286,7 @@ int tb2_mesh_create(int device, int64_t nn, int64_t ne, const int32_t* h_conn, c
         M_CUDA(tmp.alloc(tmp_bytes));
         M_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, m->inc.p, (int)(8 * ne), 0, end_bit, m->stream));
         k_lower_bound<<<(unsigned)((nn + 1 + T - 1) / T), T, 0, m->stream>>>(nn, 8 * ne, keys_sorted.p, m->inc_ptr.p);
+        k_build_inc8<<<(unsigned)((8 * nn + T - 1) / T), T, 0, m->stream>>>(nn, m->inc_ptr.p, m->inc.p, m->inc8.p);
         M_CUDA(cudaGetLastError());
         M_CUDA(cudaStreamSynchronize(m->stream));
     }

@@ -173,6 +173,14 @@ __global__ void __launch_bounds__(128) __maxnreg__(REGS) k_internal_force_r(cons
 // memory ([coefficient][thread]: private columns, conflict-free) instead of registers, which brings the kernel from 168-220
 // registers to ~100 and doubles the resident warps that feed the FP64 pipe.  Same arithmetic as k_internal_force except that
 // j = grad(x modes) is formed directly (the modes of x = X + u are summed once per element) instead of J0 + grad(u modes).
+// shared-memory load the compiler may neither hoist out of the integration-point loop nor keep in a register across iterations
+TB2_DEV double lds_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const ElemArgs p)
 {
@@ -208,32 +216,41 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const Elem
         double s0, s1, s2;
         ip_signs(ip, s0, s1, s2);
         const double s12 = s1 * s2, s02 = s0 * s2, s01 = s0 * s1;
-        double J0[3][3], j[3][3], J0a[3][3], ja[3][3], F[3][3], G[3][3], S[3][3];
+        double J0[3][3], j[3][3], J0a[3][3], ja[3][3], G[3][3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            J0[i][0] = sX[0 + i][tid] + s1 * sX[6 + i][tid] + s2 * sX[12 + i][tid] + s12 * sX[18 + i][tid];
-            J0[i][1] = sX[3 + i][tid] + s0 * sX[6 + i][tid] + s2 * sX[15 + i][tid] + s02 * sX[18 + i][tid];
-            J0[i][2] = sX[9 + i][tid] + s0 * sX[12 + i][tid] + s1 * sX[15 + i][tid] + s01 * sX[18 + i][tid];
-            j[i][0] = sx[0 + i][tid] + s1 * sx[6 + i][tid] + s2 * sx[12 + i][tid] + s12 * sx[18 + i][tid];
-            j[i][1] = sx[3 + i][tid] + s0 * sx[6 + i][tid] + s2 * sx[15 + i][tid] + s02 * sx[18 + i][tid];
-            j[i][2] = sx[9 + i][tid] + s0 * sx[12 + i][tid] + s1 * sx[15 + i][tid] + s01 * sx[18 + i][tid];
+            J0[i][0] = lds_f64(&sX[0 + i][tid]) + s1 * lds_f64(&sX[6 + i][tid]) + s2 * lds_f64(&sX[12 + i][tid]) + s12 * lds_f64(&sX[18 + i][tid]);
+            J0[i][1] = lds_f64(&sX[3 + i][tid]) + s0 * lds_f64(&sX[6 + i][tid]) + s2 * lds_f64(&sX[15 + i][tid]) + s02 * lds_f64(&sX[18 + i][tid]);
+            J0[i][2] = lds_f64(&sX[9 + i][tid]) + s0 * lds_f64(&sX[12 + i][tid]) + s1 * lds_f64(&sX[15 + i][tid]) + s01 * lds_f64(&sX[18 + i][tid]);
+            j[i][0] = lds_f64(&sx[0 + i][tid]) + s1 * lds_f64(&sx[6 + i][tid]) + s2 * lds_f64(&sx[12 + i][tid]) + s12 * lds_f64(&sx[18 + i][tid]);
+            j[i][1] = lds_f64(&sx[3 + i][tid]) + s0 * lds_f64(&sx[6 + i][tid]) + s2 * lds_f64(&sx[15 + i][tid]) + s02 * lds_f64(&sx[18 + i][tid]);
+            j[i][2] = lds_f64(&sx[9 + i][tid]) + s0 * lds_f64(&sx[12 + i][tid]) + s1 * lds_f64(&sx[15 + i][tid]) + s01 * lds_f64(&sx[18 + i][tid]);
         }
         const double det0 = adj3(J0, J0a);
+        double M0[6];
+        sym_fft(J0a, M0); // adj(J0) adj(J0)^T (see k_internal_force for the algebra)
         const double detj = adj3(j, ja);
         if (det0 <= 0.0 || detj <= 0.0) err = kErrBadJacobian; // ParentDomainT.cpp:451 / TotalLagrangianT.cpp:127-128
-        mul3(j, J0a, F); // = det0 * F
-        const double rdd = 1.0 / (det0 * detj);
-        const double rd0 = rdd * detj, rJ = det0 * (det0 * rdd), J = detj * rd0;
-        double b[6], sig[6];
-        sym_fft(F, b);
-        sym_dev(b);
-        const double r = rcbrt(J);
-        const double sc = (p.mat.mu * rJ) * (r * r) * (rd0 * rd0); // (mu/J) J^(-2/3) / det0^2
-        const double pr = 0.5 * p.mat.kappa * (J - rJ);            // U'(J), SimoIso3D.h:93-96
-        sig[0] = sc * b[0] + pr; sig[1] = sc * b[1] + pr; sig[2] = sc * b[2] + pr;
-        sig[3] = sc * b[3]; sig[4] = sc * b[4]; sig[5] = sc * b[5];
-        sym_to_mat(sig, S);
-        mul3_abt(S, ja, G); // G = w det(j) sigma j^-T
+        double N[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            N[i][0] = j[i][0] * M0[0] + j[i][1] * M0[5] + j[i][2] * M0[4];
+            N[i][1] = j[i][0] * M0[5] + j[i][1] * M0[1] + j[i][2] * M0[3];
+            N[i][2] = j[i][0] * M0[4] + j[i][1] * M0[3] + j[i][2] * M0[2];
+        }
+        double trb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) trb += N[i][0] * j[i][0] + N[i][1] * j[i][1] + N[i][2] * j[i][2];
+        const double dj2 = detj * detj;
+        const double t = rcbrt(dj2 * dj2 * detj * det0);
+        const double rdd = (t * t) * t * (dj2 * dj2);
+        const double sc = p.mat.mu * t;
+        const double pr = 0.5 * p.mat.kappa * (dj2 - det0 * det0) * rdd;
+        const double al = sc * detj, q = pr - sc * trb * (1.0 / 3.0);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
         mode_accumulate(A, s0, s1, s2, G);
     }
     if (err) report(p, err, e);

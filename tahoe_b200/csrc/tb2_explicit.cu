@@ -61,11 +61,14 @@ __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, d
 // a_in is the acceleration left by the predictor (0 on every dof), kept as an input for generality (a += upd).
 // GATHER = false: fint already holds the (interface-summed) internal force (multi-GPU path)
 // skip_slot (multi-GPU overlap): nodes with skip_slot[n] >= 0 lie on the partition interface and are updated by
-// k_cd_interface_update once the summed force has arrived
+// k_cd_interface_update once the summed force has arrived.
+// GATHER reads the node's incidence from the fixed-width table inc8 (one 32-byte load) and issues every load of the node --
+// the <= 8 x 3 element forces and the nodal fields -- before the first use: the kernel runs beside the element sweep, which
+// holds most of the registers of every SM, so what counts is how briefly a node-kernel CTA occupies its slot.
 template <bool GATHER, bool NEXT_PREDICTOR>
 __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
-                                                       const double* __restrict__ fe, int64_t stride, double dt, double fext_scale,
-                                                       double next_value_scale, const double* __restrict__ fext,
+                                                       const int4* __restrict__ inc8, const double* __restrict__ fe, int64_t stride, double dt,
+                                                       double fext_scale, double next_value_scale, const double* __restrict__ fext,
                                                        const double* __restrict__ minv, const unsigned char* __restrict__ code,
                                                        const double* __restrict__ bcval, double* __restrict__ d,
                                                        double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint,
@@ -75,15 +78,25 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
     if (n >= nn) return;
     if (skip_slot && skip_slot[n] >= 0) return;
     double f[3] = {0.0, 0.0, 0.0};
+    // nodal operands first: independent of the gather, in flight while it resolves its two dependent round trips
+    double fx[3], mi[3], vv[3], aa[3], dd[3] = {0.0, 0.0, 0.0};
+    unsigned char cc[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int64_t q = 3 * n + i;
+        cc[i] = code[q];
+        fx[i] = fext[q];
+        mi[i] = minv[q];
+        vv[i] = v[q];
+        aa[i] = a[q];
+        if (NEXT_PREDICTOR) dd[i] = d[q];
+    }
     if (GATHER) {
-        const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
-        // the first 8 incident elements (all of them on a hex mesh without irregular nodes): every load is issued before the first
-        // add, so that a few resident warps keep enough bytes in flight while the element sweep holds most of the SM.  The sum
-        // runs in the same ascending-element order as the plain loop that handles any further entries.
         int ent[8];
         double g[8][3];
-#pragma unroll
-        for (int q = 0; q < 8; q++) ent[q] = k0 + q < k1 ? __ldg(inc + k0 + q) : -1;
+        const int4 lo = __ldg(inc8 + 2 * n), hi = __ldg(inc8 + 2 * n + 1);
+        ent[0] = lo.x; ent[1] = lo.y; ent[2] = lo.z; ent[3] = lo.w;
+        ent[4] = hi.x; ent[5] = hi.y; ent[6] = hi.z; ent[7] = hi.w;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const bool on = ent[q] >= 0;
@@ -93,6 +106,7 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
             g[q][1] = on ? __ldg(fe + (int64_t)(a3 + 1) * stride + e) : 0.0;
             g[q][2] = on ? __ldg(fe + (int64_t)(a3 + 2) * stride + e) : 0.0;
         }
+        // ascending-element order = the reference's serial assembly order (SolverT::AssembleRHS, SolverT.cpp:446-477)
 #pragma unroll
         for (int q = 0; q < 8; q++)
             if (ent[q] >= 0) {
@@ -100,14 +114,15 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
                 f[1] += g[q][1];
                 f[2] += g[q][2];
             }
-        for (int k = k0 + 8; k < k1; k++) {
-            const int en = __ldg(inc + k);
-            const int64_t e = en >> 3;
-            const int a3 = 3 * (en & 7);
-            f[0] += __ldg(fe + (int64_t)(a3)*stride + e);
-            f[1] += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
-            f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
-        }
+        if (ent[7] >= 0) // an irregular vertex with more than 8 incident elements: the rest of its list
+            for (int k = inc_ptr[n] + 8, k1 = inc_ptr[n + 1]; k < k1; k++) {
+                const int en = __ldg(inc + k);
+                const int64_t e = en >> 3;
+                const int a3 = 3 * (en & 7);
+                f[0] += __ldg(fe + (int64_t)(a3)*stride + e);
+                f[1] += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
+                f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
+            }
     } else {
         f[0] = fint[3 * n];
         f[1] = fint[3 * n + 1];
@@ -116,14 +131,14 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int64_t q = 3 * n + i;
-        const unsigned char c = code[q];
-        const double R = __dsub_rn(__dmul_rn(fext_scale, fext[q]), f[i]);
-        const double upd = c ? 0.0 : __dmul_rn(R, minv[q]);
-        double vi = v[q], ai = a[q];
+        const unsigned char c = cc[i];
+        const double R = __dsub_rn(__dmul_rn(fext_scale, fx[i]), f[i]);
+        const double upd = c ? 0.0 : __dmul_rn(R, mi[i]);
+        double vi = vv[i], ai = aa[i];
         cd_correct(dt, vi, ai, upd);
         if (GATHER) fint[q] = f[i];
         if (NEXT_PREDICTOR) {
-            double di = d[q];
+            double di = dd[i];
             cd_predict(dt, di, vi, ai);
             ai = 0.0;
             if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
@@ -290,8 +305,8 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
     const int C = (int)m->pipe_e0.size() - 1;
     const int64_t ndof = 3 * m->nn;
     const int T = 256;
-    // node-kernel CTA size in the pipeline: small CTAs fit into the registers the element sweep leaves free (experiment knob)
-    static const int T5 = (getenv("TB2_K5_THREADS") && atoi(getenv("TB2_K5_THREADS")) >= 32) ? atoi(getenv("TB2_K5_THREADS")) : 128;
+    // node-kernel CTA size in the pipeline (experiment knob; 64 / 128 / 256 measured within 3 % of each other on B200)
+    static const int T5 = (getenv("TB2_K5_THREADS") && atoi(getenv("TB2_K5_THREADS")) >= 32) ? atoi(getenv("TB2_K5_THREADS")) : 256;
     if (!m->stream2) {
         // the HBM-bound node kernels outrank the FP64-bound element sweep they run beside (their CTAs are small and short)
         int prio_lo = 0, prio_hi = 0;
@@ -372,11 +387,11 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
                     ProfScope ps(m, kProfNodeUpdate, 1, m->stream2);
                     const unsigned nb = (unsigned)((n1 - n0 + T5 - 1) / T5);
                     if (s + 1 < nsteps)
-                        k_cd_node_update<true, true><<<nb, T5, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                        k_cd_node_update<true, true><<<nb, T5, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, fsc,
                                                                               vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
                                                                               ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p, skip);
                     else
-                        k_cd_node_update<true, false><<<nb, T5, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                        k_cd_node_update<true, false><<<nb, T5, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, fsc, 1.0,
                                                                                 ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
                                                                                 ex->v.p, ex->a.p, ex->fint.p, skip);
                 }
@@ -508,7 +523,7 @@ static int explicit_step_host_pipelined(tb2_explicit* ex, double dt, double* h_d
                     k_cd_node_update_hostout<<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, 1.0, ex->fext.p,
                                                                       ex->minv.p, ex->bccode.p, ex->v.p, ex->a.p, ex->fint.p, mv, ma);
                 else
-                    k_cd_node_update<true, false><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, 1.0, 1.0,
+                    k_cd_node_update<true, false><<<nb, T, 0, m->stream2>>>(n0, n1, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, 1.0, 1.0,
                                                                            ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p,
                                                                            ex->a.p, ex->fint.p);
             }
@@ -565,21 +580,21 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
             TB2_CHECK(tb2_comm_sum_interface(m, ex->fint.p));
             ProfScope ps(m, kProfNodeUpdate);
             if (s + 1 < nsteps)
-                k_cd_node_update<false, true><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+                k_cd_node_update<false, true><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, fsc,
                                                                        vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p,
                                                                        ex->bcval.p, ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
             else
-                k_cd_node_update<false, false><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+                k_cd_node_update<false, false><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, fsc, 1.0,
                                                                         ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p,
                                                                         ex->v.p, ex->a.p, ex->fint.p);
         } else if (s + 1 < nsteps) {
             ProfScope ps(m, kProfNodeUpdate);
-            k_cd_node_update<true, true><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc,
+            k_cd_node_update<true, true><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, fsc,
                                                             vs ? vs[s + 1] : 1.0, ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p,
                                                             ex->d.p, ex->v.p, ex->a.p, ex->fint.p);
         } else {
             ProfScope ps(m, kProfNodeUpdate);
-            k_cd_node_update<true, false><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, dt, fsc, 1.0,
+            k_cd_node_update<true, false><<<nbn, T, 0, m->stream>>>(0, m->nn, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, dt, fsc, 1.0,
                                                              ex->fext.p, ex->minv.p, ex->bccode.p, ex->bcval.p, ex->d.p, ex->v.p,
                                                              ex->a.p, ex->fint.p);
         }

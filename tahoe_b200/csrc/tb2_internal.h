@@ -112,6 +112,9 @@ struct tb2_mesh {
     tb2::DevBuf<double> X;              // [nn][3]
     tb2::DevBuf<int> inc_ptr;           // [nn+1] node -> incidence range
     tb2::DevBuf<int> inc;               // [8*ne] entries e*8+a, ascending in e within a node
+    tb2::DevBuf<int> inc8;              // [nn][8] the first 8 entries of each node (-1 padded): one 32-byte load instead of the
+                                        // inc_ptr -> inc chain in the node kernels (a hex-mesh node has <= 8 incident elements
+                                        // unless it is an irregular vertex; those continue in inc[])
     tb2::DevBuf<double> fe;             // [24][stride] element force scratch
     tb2::DevBuf<double> stage_a, stage_b, stage_c; // [nn][3] staging for the *_host entry points
     // colouring (built lazily)
