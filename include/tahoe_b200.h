@@ -162,9 +162,15 @@ int tb2_matrix_get_msr(const tb2_matrix* A, int upper_only, int32_t* h_bindx, in
 int tb2_matrix_clear(tb2_matrix* A); /* GlobalMatrixT::Clear */
 /* SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154) + FormStiffness (SmallStrainT.cpp:285-324,
  * TotalLagrangianT.cpp:40-104, UpdatedLagrangianT.cpp:94-142) + MSRMatrixT::Assemble (MSRMatrixT.cpp:66-216):
- * A += K(u), colour by colour through the element->slot map (no float atomics). */
+ * A += K(u) without float atomics: element matrices of an L2-sized element chunk, then a per-(row node, column node) gather that
+ * sums the contributions in ascending element order (the reference's serial assembly order) through the precomputed
+ * element->CSR-slot map.  TB2_K3_COLOURED=1 selects the colour-by-colour read-modify-write form instead. */
 int tb2_form_stiffness(tb2_group* group, tb2_matrix* A, const double* d_u, const double* d_u_last, int iteration);
 int tb2_form_stiffness_host(tb2_group* group, tb2_matrix* A, const double* h_u, const double* h_u_last, int iteration);
+/* the same element loop assembled into a DiagonalMatrixT in kDiagOnly mode (DiagonalMatrixT.cpp:107-113: fMatrix[eq] += elMat(i,i)),
+ * which is what <PCG_solver><diagonal_matrix/> uses as its preconditioner (SolverT.cpp:1097-1102): d_diag[nn][3] = diag K(u) per nodal dof */
+int tb2_form_stiffness_diagonal(tb2_group* group, const double* d_u, const double* d_u_last, int iteration, double* d_diag);
+int tb2_form_stiffness_diagonal_host(tb2_group* group, const double* h_u, const double* h_u_last, int iteration, double* h_diag);
 /* MSRMatrixT::Multx (MSRMatrixT.cpp:385-420): y = A x on equation-space vectors [neq] */
 int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y);
 int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y);

@@ -28,6 +28,7 @@ tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get
 tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
+tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface""".split()
 
@@ -229,6 +230,13 @@ class Group(_Handle):
         f = np.zeros((self.mesh.nn, 3))
         _chk(lib().tb2_form_internal_force_host(self.h, _p(u), _p(u_last), int(iteration), _p(f)))
         return f
+
+    def stiffness_diagonal_host(self, u, u_last=None, iteration=0):
+        """diag K(u) per nodal dof: DiagonalMatrixT kDiagOnly assembly of the element loop"""
+        u, u_last = _f64(u), _f64(u_last)
+        d = np.zeros((self.mesh.nn, 3))
+        _chk(lib().tb2_form_stiffness_diagonal_host(self.h, _p(u), _p(u_last), int(iteration), _p(d)))
+        return d
 
     def internal_force(self, d_u, d_u_last, iteration, d_f):
         _chk(lib().tb2_form_internal_force(self.h, _dp(d_u), _dp(d_u_last), int(iteration), _dp(d_f)))

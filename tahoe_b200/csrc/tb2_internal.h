@@ -210,6 +210,13 @@ struct tb2_matrix {
     tb2::DevBuf<double> scal;     // reduction scalars
     tb2::DevBuf<double> partial;  // per-block partial sums
     tb2::DevBuf<unsigned char> eq_owned; // multi-GPU: 1 if this rank owns the equation's node (dot products count it once)
+    // two-phase assembly (tb2_stiffness.cu): contributions e*64+a*8+b of every node block, ascending in e; the element-matrix
+    // scratch of one element chunk; the node range each chunk touches
+    int64_t nadj = 0;
+    tb2::DevBuf<unsigned> contrib_ptr, contrib;
+    tb2::DevBuf<double> ke;        // [k3_chunk][576] element matrices of the current chunk
+    int64_t k3_chunk = 0;
+    std::vector<int> k3_nmin, k3_nmax;
 };
 
 struct tb2_explicit {

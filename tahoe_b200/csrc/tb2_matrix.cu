@@ -634,6 +634,7 @@ int tb2_matrix_create(tb2_equations* q, tb2_matrix** out)
         set_error("a node has more than %d distinct neighbours", kMaxAdj);
         return fail(TB2_ERR_SIZE);
     }
+    A->nadj = nadj;
     A_CUDA(A->adj.alloc(nadj));
     A_CUDA(A->adj_coloff.alloc(nadj));
     k_adj_fill<<<nbn, T, 0, m->stream>>>(nn, m->inc_ptr.p, m->inc.p, m->conn.p, m->stride, A->adj_ptr.p, q->eqnos.p, A->adj.p,

@@ -12,12 +12,18 @@
 // Phase 3: each thread adds its 3x24 block to the CSR through the element->adjacency map.  Elements are processed colour by
 // colour (no two elements of a colour share a node), so plain read-modify-write is race free and the summation order per
 // matrix entry is fixed: colour order.
+#include <cub/cub.cuh>
+
+#include <cstdlib>
+
 #include "tb2_internal.h"
 
 namespace tb2 {
 
 int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration);
 J2Hist group_hist(tb2_group* g);
+int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
+int ensure_stage(tb2_mesh* m, int which);
 
 // ---- colouring ------------------------------------------------------------------------------------------------------
 // colour(e) = smallest colour not used by any lower-numbered element sharing a node with e: the sequential greedy colouring
@@ -68,31 +74,28 @@ struct StiffArgs {
     const int* adj_coloff;    // per adjacency entry
     const int* elem_adjpos;   // [64][stride]
     double* val;
+    // two-phase path: element range [e0, e1) of this launch, element-matrix scratch ke[e - e0][kstride = 576] (entry r*24+c),
+    // or (diagonal mode) the element-vector scratch fe[24][stride]
+    int64_t e0, e1, kstride;
+    double* ke;
+    double* fe;
 };
 
 static const int kElemsPerBlock = 16;
 static const int kIpDoubles = 24 + 36 + 6 + 2; // dN/dx[3][8], c[6][6], sigma[6], scale, pad
+static const int kTilePitch = 577;            // element-matrix tile of the two-phase path: [16][577] doubles
+static const size_t kElemSmem = (size_t)kElemsPerBlock * kTilePitch * sizeof(double); // >= the integration-point tile (69,632 B)
 
+// ---- phase 1 of K3: one integration point (Jacobian, F, stress, spatial tangent c, spatial dN/dx, w det j) parked in shared
+// memory; smcol = this element's column of the [ip][field][element] tile
+#define SM(ip, f) smcol[((ip)*kIpDoubles + (f)) * kElemsPerBlock]
 template <int FORM, int MAT>
-__global__ void __launch_bounds__(128) k_stiffness(const StiffArgs p)
+TB2_DEV void stiffness_point(const StiffArgs& p, const int64_t e, const int (&n)[8], const int ip, double* smcol)
 {
-    // shared: [ip][field][element-in-block]  (element minor: the 4 elements of a warp hit 4 consecutive words)
-    extern __shared__ double sm[];
-    const int el = threadIdx.x >> 3, t = threadIdx.x & 7;
-    const int64_t idx = blockIdx.x * (int64_t)kElemsPerBlock + el;
-    const bool live = idx < p.count;
-    const int64_t e = live ? p.elems[idx] : 0;
-#define SM(ip, f) sm[((ip)*kIpDoubles + (f)) * kElemsPerBlock + el]
-    int n[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
-
-    if (live) { // ---- phase 1: integration point t
         Modes cX, cU;
         load_modes(p.X, n, cX);
         load_modes(p.u, n, cU);
-        const int ip = t;
-        double s0, s1, s2;
+                double s0, s1, s2;
         ip_signs(ip, s0, s1, s2);
         double J0[3][3], H[3][3], J0a[3][3], ja[3][3], c[6][6], sig[6];
         mode_gradient(cX, s0, s1, s2, J0);
@@ -165,7 +168,24 @@ __global__ void __launch_bounds__(128) k_stiffness(const StiffArgs p)
 #pragma unroll
         for (int I = 0; I < 6; I++) SM(ip, 60 + I) = sig[I];
         SM(ip, 66) = scale;
-    }
+}
+#undef SM
+
+template <int FORM, int MAT>
+__global__ void __launch_bounds__(128) k_stiffness(const StiffArgs p)
+{
+    // shared: [ip][field][element-in-block]  (element minor: the 4 elements of a warp hit 4 consecutive words)
+    extern __shared__ double sm[];
+    const int el = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const int64_t idx = blockIdx.x * (int64_t)kElemsPerBlock + el;
+    const bool live = idx < p.count;
+    const int64_t e = live ? p.elems[idx] : 0;
+#define SM(ip, f) sm[((ip)*kIpDoubles + (f)) * kElemsPerBlock + el]
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+
+    if (live) stiffness_point<FORM, MAT>(p, e, n, t, sm + el); // ---- phase 1: integration point t
     __syncthreads();
     if (!live) return;
 
@@ -238,6 +258,224 @@ __global__ void __launch_bounds__(128) k_stiffness(const StiffArgs p)
     }
 }
 
+
+// ---- K3, two-phase form (default) ---------------------------------------------------------------------------------------
+// Phase A, k_element_stiffness: the element matrices of a contiguous element chunk go to a scratch that is sized to stay in
+// L2, laid out [element][row*24 + col]: a CTA stages its 16 matrices in shared memory and writes one contiguous 73.7 kB block.
+// Thread (el = tid & 15, t = tid >> 4): phase 1 evaluates integration point t of element el, phase 2 owns row node a = t.
+//   kKSym  symmetric tangents (SSKStV, FDKStV, SimoIso3D): only the 36 node blocks (a, (a+k) & 7), k = 0..4 (k = 4 for a < 4
+//          only) are accumulated; each is stored together with its transpose, and the diagonal block from its upper triangle --
+//          the element matrix is exactly symmetric, as the reference's MultQTBQ(kUpperOnly) + CopySymmetric
+//          (SmallStrainT.cpp:285-324, ElementMatrixT::CopySymmetric) makes it.  29 % fewer FP64 instructions than all 64 blocks.
+//   kKFull all 64 blocks (J2Simo3D: TangentType() == kNonSymmetric, J2Simo3D.cpp:18-21)
+//   kKDiag the 24 diagonal entries only, to fe[24][stride]: DiagonalMatrixT::Assemble in kDiagOnly mode
+//          (DiagonalMatrixT.cpp:107-113), the preconditioner of PCGSolver_LS
+// Phase B, k_assemble_gather: one warp per row node A; the lane of column dof j of neighbour block (A, B) sums the block's
+// contributions in ascending element order -- the order of the reference's serial ElementLHSDriver loop -- and adds the 3x3 result to the CSR.  No
+// colouring, no atomics; reruns are bit-identical.
+enum { kKSym = 0, kKFull = 1, kKDiag = 2 };
+
+template <int FORM, int MAT, int MODE>
+__global__ void __launch_bounds__(128, (MODE == kKFull || MAT == kJ2Simo) ? 2 : 3) k_element_stiffness(const StiffArgs p)
+{
+    extern __shared__ double sm[];
+    const int el = threadIdx.x & 15, t = threadIdx.x >> 4;
+    const int64_t eg = p.e0 + blockIdx.x * (int64_t)kElemsPerBlock + el;
+    const bool live = eg < p.e1;
+    const int64_t e = live ? eg : p.e0;
+#define SM(ip, f) sm[((ip)*kIpDoubles + (f)) * kElemsPerBlock + el]
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+    if (live) stiffness_point<FORM, MAT>(p, e, n, t, sm + el);
+    __syncthreads();
+
+    const int a = t;
+    constexpr int NK = MODE == kKSym ? 5 : (MODE == kKFull ? 8 : 1);
+    const int nk = MODE == kKSym ? (a < 4 ? 5 : 4) : NK; // uniform per warp (a warp holds two values of a: 2w, 2w+1)
+    double K[NK][3][3];
+#pragma unroll
+    for (int k = 0; k < NK; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) K[k][i][j] = 0.0;
+#pragma unroll 1
+    for (int ip = 0; ip < 8; ip++) {
+        const double w = SM(ip, 66);
+        const double nx = SM(ip, 0 + a) * w, ny = SM(ip, 8 + a) * w, nz = SM(ip, 16 + a) * w;
+        double D[3][6]; // w * B_a^T c
+#pragma unroll
+        for (int Jj = 0; Jj < 6; Jj++) {
+            const double c0 = SM(ip, 24 + 0 * 6 + Jj), c1 = SM(ip, 24 + 1 * 6 + Jj), c2 = SM(ip, 24 + 2 * 6 + Jj);
+            const double c3 = SM(ip, 24 + 3 * 6 + Jj), c4 = SM(ip, 24 + 4 * 6 + Jj), c5 = SM(ip, 24 + 5 * 6 + Jj);
+            D[0][Jj] = nx * c0 + nz * c4 + ny * c5;
+            D[1][Jj] = ny * c1 + nz * c3 + nx * c5;
+            D[2][Jj] = nz * c2 + ny * c3 + nx * c4;
+        }
+        double gx = 0.0, gy = 0.0, gz = 0.0; // w * sigma dN_a
+        if (FORM != kSmallStrain) {
+            const double sg0 = SM(ip, 60), sg1 = SM(ip, 61), sg2 = SM(ip, 62), sg3 = SM(ip, 63), sg4 = SM(ip, 64), sg5 = SM(ip, 65);
+            gx = sg0 * nx + sg5 * ny + sg4 * nz;
+            gy = sg5 * nx + sg1 * ny + sg3 * nz;
+            gz = sg4 * nx + sg3 * ny + sg2 * nz;
+        }
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            if (k >= nk) continue;
+            const int b = MODE == kKFull ? k : ((a + k) & 7);
+            const double bx = SM(ip, 0 + b), by = SM(ip, 8 + b), bz = SM(ip, 16 + b);
+            const double geo = FORM != kSmallStrain ? gx * bx + gy * by + gz * bz : 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                K[k][i][0] += D[i][0] * bx + D[i][4] * bz + D[i][5] * by;
+                K[k][i][1] += D[i][1] * by + D[i][3] * bz + D[i][5] * bx;
+                K[k][i][2] += D[i][2] * bz + D[i][3] * by + D[i][4] * bx;
+            }
+            K[k][0][0] += geo;
+            K[k][1][1] += geo;
+            K[k][2][2] += geo;
+        }
+    }
+#undef SM
+    if (MODE == kKDiag) {
+        if (live)
+#pragma unroll
+            for (int i = 0; i < 3; i++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = K[0][i][i];
+        return;
+    }
+    // the 16 element matrices of this CTA are laid out [element][row*24 + col] in shared memory (pitch 577: the 16 elements
+    // of a half-warp fall into distinct banks) and leave as one contiguous 73.7 kB block
+    __syncthreads(); // every thread is done reading the integration-point tile
+    double* tile = sm + el * kTilePitch;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        if (k >= nk) continue;
+        const int b = MODE == kKFull ? k : ((a + k) & 7);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double v = K[k][i][j];
+                if (MODE == kKSym && k == 0 && j < i) v = K[0][j][i]; // diagonal block from its upper triangle
+                tile[(3 * a + i) * 24 + 3 * b + j] = v;
+                if (MODE == kKSym && k > 0) tile[(3 * b + j) * 24 + 3 * a + i] = v; // the transposed block (b, a)
+            }
+    }
+    __syncthreads();
+    const int64_t first = p.e0 + blockIdx.x * (int64_t)kElemsPerBlock;
+    const int nlive = (int)(p.e1 - first < kElemsPerBlock ? p.e1 - first : kElemsPerBlock);
+    double* out = p.ke + (first - p.e0) * 576;
+    for (int idx = threadIdx.x; idx < nlive * 576; idx += 128) {
+        const int q = idx / 576;
+        out[idx] = sm[q * kTilePitch + (idx - q * 576)];
+    }
+}
+
+struct GatherArgs {
+    int64_t n0, n1;        // row nodes of this launch
+    int64_t e0, e1;        // element chunk held by the scratch ke[e - e0][576]
+    const double* ke;
+    const int* adj_ptr;
+    const int* adj;
+    const int* adj_coloff;
+    const unsigned* cptr;    // [nadj+1] contribution ranges of the node blocks
+    const unsigned* contrib; // e*64 + a*8 + b, ascending in e within a block
+    const int* eqnos;
+    const long long* rowptr;
+    double* val;
+};
+static const int kGatherWarps = 8; // row nodes per CTA
+__global__ void __launch_bounds__(32 * kGatherWarps) k_assemble_gather(const GatherArgs g)
+{
+    // One warp per row node A.  Lane slot s = 3 k + j is column dof j of neighbour block k, so the lanes of a warp walk the
+    // (contiguous) CSR rows of the node: val is read and written coalesced, and the 24 B (block) / 192 B (whole element row)
+    // runs of the [element][row][col] scratch are contiguous too.
+    const int lane = threadIdx.x & 31;
+    const int64_t A = g.n0 + blockIdx.x * (int64_t)kGatherWarps + (threadIdx.x >> 5);
+    if (A >= g.n1) return;
+    long long row[3];
+    bool any_row = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int eq = __ldg(g.eqnos + 3 * A + i);
+        row[i] = eq > 0 ? g.rowptr[eq - 1] : -1; // MSRMatrixT::Assemble skips inactive rows (MSRMatrixT.cpp:118-123)
+        any_row |= eq > 0;
+    }
+    if (!any_row) return;
+    const int b0 = __ldg(g.adj_ptr + A), len = __ldg(g.adj_ptr + A + 1) - b0;
+    for (int s = lane; s < 3 * len; s += 32) {
+        const int k = s / 3, j = s - 3 * k, blk = b0 + k;
+        const unsigned c1 = __ldg(g.cptr + blk + 1);
+        unsigned c = __ldg(g.cptr + blk);
+        while (c < c1 && (int64_t)(__ldg(g.contrib + c) >> 6) < g.e0) c++; // first contribution of this chunk (ascending in e)
+        if (c >= c1 || (int64_t)(__ldg(g.contrib + c) >> 6) >= g.e1) continue;
+        const int64_t B = __ldg(g.adj + blk);
+        const int q0 = __ldg(g.eqnos + 3 * B), q1 = __ldg(g.eqnos + 3 * B + 1), q2 = __ldg(g.eqnos + 3 * B + 2);
+        if ((j == 0 ? q0 : (j == 1 ? q1 : q2)) <= 0) continue; // inactive column
+        const int col = __ldg(g.adj_coloff + blk) + (j > 0 && q0 > 0) + (j > 1 && q1 > 0);
+        // the running sums start from the stored entries, so that chunking never changes the order of the additions:
+        // val + k_e1 + k_e2 + ... in ascending element order whatever the chunk boundaries are
+        double acc[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) acc[i] = row[i] >= 0 ? g.val[row[i] + col] : 0.0;
+        for (; c < c1; c++) {
+            const unsigned code = __ldg(g.contrib + c);
+            const int64_t e = code >> 6;
+            if (e >= g.e1) break;
+            const int a = (code >> 3) & 7, b = code & 7;
+            const double* src = g.ke + (e - g.e0) * 576 + (3 * a) * 24 + 3 * b + j;
+#pragma unroll
+            for (int i = 0; i < 3; i++) acc[i] += src[i * 24];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (row[i] >= 0) g.val[row[i] + col] = acc[i];
+    }
+}
+
+// contribution lists of the node blocks: thread per row node walks its incident (element, local node a) pairs in ascending
+// element order (the incidence is sorted) and appends e*64 + a*8 + b to block (A, conn[b]) -- every block belongs to one thread
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_contrib(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                const int* __restrict__ elem_adjpos, int64_t stride, const unsigned* __restrict__ cptr,
+                                                unsigned* __restrict__ cursor, unsigned* __restrict__ contrib)
+{
+    const int64_t A = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (A >= nn) return;
+    for (int k = inc_ptr[A]; k < inc_ptr[A + 1]; k++) {
+        const int ent = inc[k];
+        const int64_t e = ent >> 3;
+        const int a = ent & 7;
+        for (int b = 0; b < 8; b++) {
+            const int pos = elem_adjpos[(int64_t)(a * 8 + b) * stride + e];
+            const unsigned c = cursor[pos];
+            cursor[pos] = c + 1;
+            if (FILL) contrib[cptr[pos] + c] = (unsigned)(e * 64 + a * 8 + b);
+        }
+    }
+}
+// smallest / largest node of every element chunk (chunk is a multiple of 32, so a warp never straddles two chunks)
+__global__ void __launch_bounds__(256) k_chunk_node_range(int64_t ne, int64_t stride, const int* __restrict__ conn, int64_t chunk,
+                                                         int* __restrict__ nmin, int* __restrict__ nmax)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int lo = 0x7fffffff, hi = -1;
+    if (e < ne)
+        for (int a = 0; a < 8; a++) {
+            const int n = conn[a * stride + e];
+            lo = n < lo ? n : lo;
+            hi = n > hi ? n : hi;
+        }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && hi >= 0) {
+        const int64_t c = (e & ~31LL) / chunk;
+        atomicMin(nmin + c, lo);
+        atomicMax(nmax + c, hi);
+    }
+}
+
 typedef void (*stiff_kernel_t)(const StiffArgs);
 static stiff_kernel_t pick_stiff_kernel(int form, int mat)
 {
@@ -248,6 +486,110 @@ static stiff_kernel_t pick_stiff_kernel(int form, int mat)
     case kJ2Simo: return k_stiffness<kTotalLagrangian, kJ2Simo>;
     }
     return nullptr;
+}
+
+
+typedef void (*elem_kernel_t)(const StiffArgs);
+static elem_kernel_t pick_elem_kernel(int form, int mat, bool diag)
+{
+    if (form == kSmallStrain) {
+        if (mat != kSSKStV) return nullptr;
+        return diag ? k_element_stiffness<kSmallStrain, kSSKStV, kKDiag> : k_element_stiffness<kSmallStrain, kSSKStV, kKSym>;
+    }
+    switch (mat) { // UpdatedLagrangianT shares the finite-strain body
+    case kFDKStV: return diag ? k_element_stiffness<kTotalLagrangian, kFDKStV, kKDiag> : k_element_stiffness<kTotalLagrangian, kFDKStV, kKSym>;
+    case kSimoIso: return diag ? k_element_stiffness<kTotalLagrangian, kSimoIso, kKDiag> : k_element_stiffness<kTotalLagrangian, kSimoIso, kKSym>;
+    case kJ2Simo: return diag ? k_element_stiffness<kTotalLagrangian, kJ2Simo, kKDiag> : k_element_stiffness<kTotalLagrangian, kJ2Simo, kKFull>;
+    }
+    return nullptr;
+}
+
+static StiffArgs stiff_args(tb2_group* g, const double* d_u, const double* d_ul, int iteration)
+{
+    tb2_mesh* m = g->mesh;
+    StiffArgs p{};
+    p.ne = m->ne;
+    p.stride = m->stride;
+    p.conn = m->conn.p;
+    p.X = m->X.p;
+    p.u = d_u;
+    p.ul = d_ul;
+    p.mat = g->mc;
+    p.hist = group_hist(g);
+    p.iteration = iteration;
+    p.status = g->status.p;
+    return p;
+}
+
+// Contribution lists, chunk size and per-chunk node ranges of the two-phase assembly (once per matrix).
+// r01e measurements on 1M elements: L2-sized chunks (2 waves, 65 MB) 5.2 ms, 8 waves 4.2 ms, one 4.6 GB chunk 3.6 ms -- launch
+// tails and revisiting the boundary rows cost more than the DRAM round trip of the scratch; running the gather of chunk c on a
+// second stream beside the element kernel of chunk c + 1 gained nothing either (4.1 ms with 4 chunks: the element kernel owns
+// the whole register file, the gather only runs in its tail).  So: the largest chunk that fits the scratch budget, one stream.
+static int ensure_gather_plan(tb2_matrix* A, elem_kernel_t k)
+{
+    if (A->k3_chunk > 0) return TB2_OK;
+    tb2_mesh* m = A->eqs->mesh;
+    const int64_t ne = m->ne, nn = m->nn;
+    if (ne >= (1LL << 26)) {
+        set_error("two-phase assembly packs the element id in 26 bits: %lld elements on one GPU", (long long)ne);
+        return TB2_ERR_SIZE;
+    }
+    const size_t smem = kElemSmem;
+    TB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ---- contribution lists
+    DevBuf<unsigned> cursor;
+    DevBuf<unsigned char> tmp;
+    TB2_CUDA(cursor.alloc(A->nadj + 1));
+    TB2_CUDA(A->contrib_ptr.alloc(A->nadj + 1));
+    TB2_CUDA(A->contrib.alloc(64 * ne));
+    TB2_CUDA(cudaMemsetAsync(cursor.p, 0, (A->nadj + 1) * sizeof(unsigned), m->stream));
+    const unsigned nbn = (unsigned)((nn + 127) / 128);
+    k_contrib<false><<<nbn, 128, 0, m->stream>>>(nn, m->inc_ptr.p, m->inc.p, A->elem_adjpos.p, m->stride, nullptr, cursor.p, nullptr);
+    size_t tb = 0;
+    TB2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cursor.p, A->contrib_ptr.p, (int)(A->nadj + 1), m->stream));
+    TB2_CUDA(tmp.alloc(tb));
+    TB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cursor.p, A->contrib_ptr.p, (int)(A->nadj + 1), m->stream));
+    TB2_CUDA(cudaMemsetAsync(cursor.p, 0, (A->nadj + 1) * sizeof(unsigned), m->stream));
+    k_contrib<true><<<nbn, 128, 0, m->stream>>>(nn, m->inc_ptr.p, m->inc.p, A->elem_adjpos.p, m->stride, A->contrib_ptr.p, cursor.p, A->contrib.p);
+    TB2_CUDA(cudaGetLastError());
+    // ---- chunk size: the fewest chunks whose scratch stays under 6 GB, each a whole number of waves of the element kernel
+    // (TB2_K3_CHUNK overrides)
+    int sms = 148, occ = 2;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 128, smem);
+    if (occ < 1) occ = 1;
+    const int64_t wave = (int64_t)sms * occ * kElemsPerBlock;
+    const int64_t budget = (int64_t)(6.0e9 / (576 * sizeof(double)));
+    const int64_t nch = (ne + budget - 1) / budget;
+    int64_t chunk = ((ne + nch - 1) / nch + wave - 1) / wave * wave;
+    bool forced = false; // an explicit TB2_K3_CHUNK is taken as is (tests: many chunks on a shuffled mesh)
+    if (const char* s = getenv("TB2_K3_CHUNK"))
+        if (atoll(s) > 0) { chunk = atoll(s); forced = true; }
+    const int64_t ne_pad = (ne + 31) & ~31LL;
+    DevBuf<int> d_min, d_max;
+    for (;;) {
+        chunk = (chunk + 31) & ~31LL;
+        if (chunk > ne_pad) chunk = ne_pad;
+        const int nchunks = (int)((ne + chunk - 1) / chunk);
+        TB2_CUDA(d_min.alloc(nchunks));
+        TB2_CUDA(d_max.alloc(nchunks));
+        TB2_CUDA(cudaMemsetAsync(d_min.p, 0x7f, nchunks * sizeof(int), m->stream));
+        TB2_CUDA(cudaMemsetAsync(d_max.p, 0xff, nchunks * sizeof(int), m->stream));
+        k_chunk_node_range<<<(unsigned)((ne + 255) / 256), 256, 0, m->stream>>>(ne, m->stride, m->conn.p, chunk, d_min.p, d_max.p);
+        A->k3_nmin.resize(nchunks);
+        A->k3_nmax.resize(nchunks);
+        TB2_CUDA(cudaMemcpyAsync(A->k3_nmin.data(), d_min.p, nchunks * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        TB2_CUDA(cudaMemcpyAsync(A->k3_nmax.data(), d_max.p, nchunks * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        TB2_CUDA(cudaStreamSynchronize(m->stream));
+        int64_t swept = 0;
+        for (int c = 0; c < nchunks; c++) swept += (int64_t)A->k3_nmax[c] - A->k3_nmin[c] + 1;
+        if (forced || swept <= 4 * nn + 4096 || chunk >= ne_pad || chunk * 4 > budget) break;
+        chunk *= 4;
+    }
+    TB2_CUDA(A->ke.alloc((size_t)576 * chunk));
+    A->k3_chunk = chunk;
+    return TB2_OK;
 }
 
 int ensure_colouring(tb2_mesh* m)
@@ -314,7 +656,8 @@ int tb2_mesh_colouring(tb2_mesh* m, int32_t* h_colour, int32_t* num_colours)
     return TB2_OK;
 }
 
-int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const double* d_ul, int iteration)
+// the colour-by-colour read-modify-write form (TB2_K3_COLOURED=1): kept as the cross-check of the two-phase default
+static int form_stiffness_coloured(tb2_group* g, tb2_matrix* A, const double* d_u, const double* d_ul, int iteration)
 {
     TB2_ARG(g && A && d_u);
     tb2_mesh* m = g->mesh;
@@ -354,6 +697,93 @@ int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const dou
     }
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
+}
+
+
+int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const double* d_ul, int iteration)
+{
+    TB2_ARG(g && A && d_u);
+    tb2_mesh* m = g->mesh;
+    TB2_ARG(A->eqs && A->eqs->mesh == m);
+    const char* env_coloured = getenv("TB2_K3_COLOURED"); // read per call: the tests flip it to cross-check the two forms
+    const bool coloured = env_coloured && env_coloured[0] == '1';
+    if (coloured) return form_stiffness_coloured(g, A, d_u, d_ul, iteration);
+    DeviceGuard dg(m->device);
+    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, false);
+    TB2_ARG(k != nullptr);
+    TB2_CHECK(ensure_gather_plan(A, k));
+    if (g->mat.kind == TB2_J2_SIMO) {
+        TB2_ARG(d_ul != nullptr);
+        TB2_CHECK(launch_element_forces(g, d_u, d_ul, iteration)); // settles element allocation in the reference's order
+    }
+    StiffArgs p = stiff_args(g, d_u, d_ul, iteration);
+    p.ke = A->ke.p;
+    p.kstride = 576;
+    GatherArgs ga;
+    ga.ke = A->ke.p;
+    ga.adj_ptr = A->adj_ptr.p;
+    ga.adj = A->adj.p;
+    ga.adj_coloff = A->adj_coloff.p;
+    ga.cptr = A->contrib_ptr.p;
+    ga.contrib = A->contrib.p;
+    ga.eqnos = A->eqs->eqnos.p;
+    ga.rowptr = A->rowptr.p;
+    ga.val = A->val.p;
+    const size_t smem = kElemSmem;
+    const int nchunks = (int)A->k3_nmin.size();
+    for (int c = 0; c < nchunks; c++) {
+        p.e0 = (int64_t)c * A->k3_chunk;
+        p.e1 = p.e0 + A->k3_chunk < m->ne ? p.e0 + A->k3_chunk : m->ne;
+        ga.e0 = p.e0;
+        ga.e1 = p.e1;
+        ga.n0 = A->k3_nmin[c];
+        ga.n1 = (int64_t)A->k3_nmax[c] + 1;
+        ProfScope ps(m, kProfStiffness, 2);
+        k<<<(unsigned)((p.e1 - p.e0 + kElemsPerBlock - 1) / kElemsPerBlock), 128, smem, m->stream>>>(p);
+        k_assemble_gather<<<(unsigned)((ga.n1 - ga.n0 + kGatherWarps - 1) / kGatherWarps), 32 * kGatherWarps, 0, m->stream>>>(ga);
+    }
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_form_stiffness_diagonal(tb2_group* g, const double* d_u, const double* d_ul, int iteration, double* d_diag)
+{
+    TB2_ARG(g && d_u && d_diag);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, true);
+    TB2_ARG(k != nullptr);
+    const size_t smem = kElemSmem;
+    TB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (g->mat.kind == TB2_J2_SIMO) {
+        TB2_ARG(d_ul != nullptr);
+        TB2_CHECK(launch_element_forces(g, d_u, d_ul, iteration));
+    }
+    StiffArgs p = stiff_args(g, d_u, d_ul, iteration);
+    p.e0 = 0;
+    p.e1 = m->ne;
+    p.fe = m->fe.p;
+    {
+        ProfScope ps(m, kProfStiffness);
+        k<<<(unsigned)((m->ne + kElemsPerBlock - 1) / kElemsPerBlock), 128, smem, m->stream>>>(p);
+    }
+    TB2_CUDA(cudaGetLastError());
+    return launch_node_gather(m, d_diag, true);
+}
+
+int tb2_form_stiffness_diagonal_host(tb2_group* g, const double* h_u, const double* h_ul, int iteration, double* h_diag)
+{
+    TB2_ARG(g && h_u && h_diag);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    for (int w = 0; w < 3; w++) TB2_CHECK(ensure_stage(m, w));
+    TB2_CUDA(cudaMemcpyAsync(m->stage_a.p, h_u, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_ul) TB2_CUDA(cudaMemcpyAsync(m->stage_c.p, h_ul, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CHECK(tb2_form_stiffness_diagonal(g, m->stage_a.p, h_ul ? m->stage_c.p : nullptr, iteration, m->stage_b.p));
+    TB2_CUDA(cudaMemcpyAsync(h_diag, m->stage_b.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return tb2_group_status(g, nullptr);
 }
 
 int tb2_form_stiffness_host(tb2_group* g, tb2_matrix* A, const double* h_u, const double* h_ul, int iteration)

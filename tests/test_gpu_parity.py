@@ -278,6 +278,41 @@ def test_tangent_matches_oracle(tb2, oracle, form, matname):
     assert relerr(A.multx_host(x), oracle.spmv(rp, ci, kv, x)) < 1e-12
 
 
+@pytest.mark.parametrize("form,matname", FORMS)
+def test_two_phase_assembly_equals_coloured_assembly_and_diagonal(tb2, form, matname, monkeypatch):
+    """the default two-phase (element scratch + ordered gather) K3 against the colour-by-colour form, on a shuffled mesh with
+    several element chunks; the kDiagOnly entry point returns the same diagonal"""
+    X, conn, ns, u = _synthetic((9, 7, 8))
+    perm = np.random.default_rng(3).permutation(conn.shape[0])
+    conn = np.ascontiguousarray(conn[perm])
+    desc = {"type": matname, "E": 100.0, "nu": 0.25, "density": 1.0}
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    code[ns[4], 1] = 1
+    vals = {}
+    for mode, chunk in (("1", None), ("0", "96"), ("0", None)):
+        monkeypatch.setenv("TB2_K3_COLOURED", mode)
+        if chunk:
+            monkeypatch.setenv("TB2_K3_CHUNK", chunk)
+        else:
+            monkeypatch.delenv("TB2_K3_CHUNK", raising=False)
+        mesh = tb2.Mesh(X, conn)
+        grp = tb2.Group(mesh, tb2.FORM_OF[form], tb2.material(desc))
+        eqs = tb2.Equations(mesh, code)
+        A = tb2.Matrix(eqs)
+        A.form_stiffness_host(grp, u)
+        rowptr, colind, val = A.csr()
+        vals[(mode, chunk)] = val
+        if mode == "0" and chunk is None:
+            M = sp.csr_matrix((val, colind, rowptr), shape=(eqs.neq, eqs.neq))
+            assert abs(M - M.T).max() == 0.0  # exactly symmetric, as MultQTBQ(kUpperOnly) + CopySymmetric
+            diag = grp.stiffness_diagonal_host(u)
+            assert relerr(diag[eqs.eqnos() > 0], M.diagonal()) < 1e-13
+    ref = vals[("1", None)]
+    assert relerr(vals[("0", None)], ref) < 1e-13
+    assert np.array_equal(vals[("0", "96")], vals[("0", None)])  # chunking does not change the summation order
+
+
 def test_pcg_matches_oracle_and_reference(tb2, oracle):
     c = Case("syn_ss_kstv_static")
     code, _, fext = c.bc(1.0)
