@@ -16,7 +16,8 @@
  *   fint (--fint: InternalForceOnNode for every node, incl. prescribed dofs),
  *   lhs_r lhs_c lhs_v + msr_bindx (--lhs: tangent re-formed at the final state,
  *   MSRMatrixT-derived matrices only), j2_alloc j2_flags j2_data (if any element is allocated; taken right
- *   after the last CloseStep, before the extra evaluations above), iters (SolverT::IterationNumber per step),
+ *   after the last CloseStep, before the extra evaluations above), iters (SolverT::IterationNumber per step), iters_ic
+ *   (the same after FEManagerT::InitialCondition),
  *   timing (--time: wall seconds of the step loop, steps, elements)
  */
 #include <sys/stat.h>
@@ -141,6 +142,10 @@ int main(int argc, char** argv)
         /* the reference's own step loop (FEManagerT::Solve, FEManagerT.cpp:138-268) */
         ExceptionT::CodeT error = tahoe->InitialCondition();
         dump_fields(0);
+        {   /* iterations of the solve FEManagerT::InitialCondition itself runs when the load is on at t = 0 (e.g. beam.PCG.xml) */
+            int ic_iters = tahoe->Solver(solver_group)->IterationNumber();
+            put("iters_ic", "i4", &ic_iters, 4, 1, 0);
+        }
         TimeManagerT* tm = tahoe->TimeManager();
         auto t0 = std::chrono::steady_clock::now();
         int nsteps = 0;

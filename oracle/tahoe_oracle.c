@@ -7,6 +7,7 @@
  */
 #include "tahoe_oracle.h"
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -899,4 +900,208 @@ void orc_cd_corrector(int64_t ndof, double dt, double* v, double* a, const doubl
         v[i] += vcorr_a * upd;
         a[i] += upd;
     }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a21: PCGSolver_LS (solvers/PCGSolver_LS.cpp) inside NLSolver::Solve (solvers/NLSolver.cpp:57-263), with
+ * <diagonal_matrix/> as the matrix type: DiagonalMatrixT in kDiagOnly mode (SolverT.cpp:1097-1102) = diag K(u),
+ * re-formed every `restart` iterations (fReformTangentIterations = fRestart, PCGSolver_LS.cpp:97).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* SolidElementT::ElementLHSDriver assembled by DiagonalMatrixT::Assemble, kDiagOnly (DiagonalMatrixT.cpp:107-113) */
+int orc_stiffness_diagonal(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, const double* u,
+                           const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration, double* diag /*[nn][3] accumulated*/)
+{
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], ue[8][3], ul[8][3], Ke[576];
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        gather(c, u, ue);
+        if (u_last) gather(c, u_last, ul);
+        int err = orc_element_stiffness(form, m, Xe, ue, u_last ? ul : NULL, j2 ? j2 + 8 * e : NULL, alloc ? alloc + e : NULL,
+                                        iteration, Ke);
+        if (err) return err;
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) diag[3 * (int64_t)c[a] + i] += Ke[(3 * a + i) * 25];
+    }
+    return ORC_OK;
+}
+
+typedef struct {
+    int form;
+    const orc_material_t* m;
+    int64_t ne, nn, neq;
+    const int32_t *conn, *eqnos;
+    const double *X, *u_last, *fext;
+    orc_j2_ip_t* j2;
+    int* alloc;
+    double* u;     /* [nn][3] current displacement */
+    double* work;  /* [nn][3] */
+    int iteration; /* SolverT::fNumIteration */
+} nlpcg_sys_t;
+
+/* FEManagerT::FormRHS: nodal forces first (NodeManagerT::FormRHS), then the element group (-fint); active equations only */
+static int nlpcg_form_rhs(nlpcg_sys_t* s, double* R)
+{
+    memset(s->work, 0, sizeof(double) * 3 * s->nn);
+    int err = orc_internal_force(s->form, s->m, s->ne, s->conn, s->X, s->u, s->u_last, s->j2, s->alloc, s->iteration, s->work, NULL);
+    if (err) return err;
+    for (int64_t k = 0; k < 3 * s->nn; k++)
+        if (s->eqnos[k] > 0) R[s->eqnos[k] - 1] = s->fext[k] - s->work[k];
+    return ORC_OK;
+}
+/* FEManagerT::Update -> FieldT::AssembleUpdate (FieldT.cpp:531-556): u[active] += update */
+static void nlpcg_update(nlpcg_sys_t* s, const double* upd)
+{
+    for (int64_t k = 0; k < 3 * s->nn; k++)
+        if (s->eqnos[k] > 0) s->u[k] += upd[s->eqnos[k] - 1];
+}
+/* FormLHS into the cleared DiagonalMatrixT, then Factorize (DiagonalMatrixT.cpp:267-310: reciprocal unless |m| <= kSmall) */
+static int nlpcg_form_preconditioner(nlpcg_sys_t* s, double* minv)
+{
+    memset(s->work, 0, sizeof(double) * 3 * s->nn);
+    int err = orc_stiffness_diagonal(s->form, s->m, s->ne, s->conn, s->X, s->u, s->u_last, s->j2, s->alloc, s->iteration, s->work);
+    if (err) return err;
+    for (int64_t k = 0; k < 3 * s->nn; k++)
+        if (s->eqnos[k] > 0) {
+            const double d = s->work[k];
+            minv[s->eqnos[k] - 1] = fabs(d) > 1.0e-12 ? 1.0 / d : d;
+        }
+    return ORC_OK;
+}
+
+/* PCGSolver_LS::GValue (PCGSolver_LS.cpp:351-371) */
+static int nlpcg_gvalue(nlpcg_sys_t* s, const double* update, double step, double* s_current, double* R, double* scratch, double* G)
+{
+    const double ds = step - *s_current;
+    for (int64_t i = 0; i < s->neq; i++) scratch[i] = update[i] * ds;
+    *s_current = step;
+    nlpcg_update(s, scratch);
+    int err = nlpcg_form_rhs(s, R);
+    if (err) return err;
+    *G = dot(s->neq, update, R);
+    return ORC_OK;
+}
+
+int orc_nlpcg_solve(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, double* u,
+                    const double* u_last, orc_j2_ip_t* j2, int* alloc, const int32_t* eqnos, int64_t neq, const double* fext,
+                    const orc_nlpcg_params_t* prm, int* iterations, double* error_out, double* error0_out)
+{
+    nlpcg_sys_t s = {form, m, ne, nn, neq, conn, eqnos, X, u_last, fext, j2, alloc, u, NULL, -1};
+    s.work = malloc(sizeof(double) * 3 * nn);
+    double *R = malloc(8 * neq), *Rres = malloc(8 * neq), *R_last = malloc(8 * neq), *u_lastdir = malloc(8 * neq),
+           *diffR = malloc(8 * neq), *minv = malloc(8 * neq), *upd = malloc(8 * neq), *scratch = malloc(8 * neq);
+    double(*search)[2] = malloc(sizeof(double) * 2 * (prm->ls_iterations > 2 ? prm->ls_iterations : 2));
+    int status = ORC_NLPCG_CONTINUE, err = ORC_OK;
+    int num_iterations = 0, tan_iterations = 0, restart_count = -1;
+    const int reform = prm->restart; /* fReformTangentIterations = fRestart */
+    double error = 0.0, error0 = 0.0;
+
+#define EXIT_ITERATION(iter)                                                                                     \
+    do {                                                                                                          \
+        if ((iter) == -1) {                                                                                       \
+            error0 = error;                                                                                       \
+            status = error0 < prm->abs_tol ? ORC_NLPCG_CONVERGED : ORC_NLPCG_CONTINUE;                            \
+        } else {                                                                                                  \
+            const double rel = error / error0;                                                                    \
+            if (rel > prm->div_tol) status = ORC_NLPCG_FAILED;                                                    \
+            else if ((iter) < prm->min_iterations - 1) status = ORC_NLPCG_CONTINUE;                               \
+            else if (rel < prm->rel_tol || error < prm->abs_tol) status = ORC_NLPCG_CONVERGED;                    \
+            else if ((iter) >= prm->max_iterations) status = ORC_NLPCG_FAILED;                                    \
+            else status = ORC_NLPCG_CONTINUE;                                                                     \
+        }                                                                                                         \
+    } while (0)
+
+    /* NLSolver.cpp:75-86: first residual, fNumIteration = -1 */
+    if ((err = nlpcg_form_rhs(&s, R))) goto done;
+    error = sqrt(dot(neq, R, R));
+    EXIT_ITERATION(s.iteration);
+    while (status == ORC_NLPCG_CONTINUE) {
+        num_iterations++;
+        tan_iterations++;
+        int lhs_update = 0;
+        if (num_iterations == 1 || tan_iterations >= reform) { lhs_update = 1; tan_iterations = 0; }
+        if (lhs_update && (err = nlpcg_form_preconditioner(&s, minv))) goto done;
+
+        /* ---- PCGSolver_LS::Iterate (:107-118): fR = fRHS; CGSearch; Update(fRHS, &fR) */
+        memcpy(Rres, R, 8 * neq);
+        restart_count++;
+        if (restart_count == 0 || restart_count == prm->restart) { /* CGSearch :152-165 */
+            memcpy(R_last, R, 8 * neq);
+            for (int64_t i = 0; i < neq; i++) R[i] *= minv[i];
+            memcpy(u_lastdir, R, 8 * neq);
+            restart_count = 0;
+        } else { /* :166-201, Bertsekas (6.32) */
+            for (int64_t i = 0; i < neq; i++) diffR[i] = (R[i] - R_last[i]) * minv[i];
+            double beta = dot(neq, R, diffR);
+            for (int64_t i = 0; i < neq; i++) diffR[i] = R_last[i] * minv[i];
+            double denominator = dot(neq, R_last, diffR);
+            if (fabs(denominator) < 1.0e-24) { denominator = 1.0; beta = 0.0; }
+            else beta /= denominator;
+            memcpy(R_last, R, 8 * neq);
+            for (int64_t i = 0; i < neq; i++) R[i] = R[i] * minv[i] + beta * u_lastdir[i];
+            memcpy(u_lastdir, R, 8 * neq);
+        }
+        /* ---- PCGSolver_LS::Update (:213-348) */
+        if (prm->ls_iterations == 0) {
+            nlpcg_update(&s, R);
+        } else {
+            memcpy(upd, R, 8 * neq);
+            double s_current = 0.0, s_a = 0.0, G_a = dot(neq, upd, Rres), s_b = 1.0, G_b, G_new = 0.0;
+            search[0][0] = s_a; search[0][1] = G_a;
+            if ((err = nlpcg_gvalue(&s, upd, s_b, &s_current, R, scratch, &G_b))) goto done;
+            search[1][0] = s_b; search[1][1] = G_b;
+            const double G_0 = fabs(G_a) > fabs(G_b) ? G_b : G_a;
+            int count = 2, give_up = 0;
+            do {
+                const double mm = (G_a - G_b) / (s_a - s_b);
+                const double bb = G_b - mm * s_b;
+                double s_new = -bb / mm;
+                if (s_new > prm->max_step || s_new < 0.0) {
+                    give_up = 1;
+                    if (s_new > prm->max_step) {
+                        s_new = prm->max_step;
+                        if ((err = nlpcg_gvalue(&s, upd, s_new, &s_current, R, scratch, &G_new))) goto done;
+                        search[count][0] = s_new; search[count][1] = G_new;
+                        count++;
+                    }
+                    break;
+                }
+                if ((err = nlpcg_gvalue(&s, upd, s_new, &s_current, R, scratch, &G_new))) goto done;
+                search[count][0] = s_new; search[count][1] = G_new;
+                if (fabs(G_a) > fabs(G_new) && fabs(G_a) > fabs(G_b)) { G_a = G_new; s_a = s_new; give_up = 0; }
+                else if (fabs(G_b) > fabs(G_new) && fabs(G_b) > fabs(G_a)) { G_b = G_new; s_b = s_new; give_up = 0; }
+                else if (G_b * G_a > 0) {
+                    if (G_a * G_new < 0) { G_a = G_new; s_a = s_new; }
+                    else if (G_b * G_new < 0) { G_b = G_new; s_b = s_new; }
+                    else give_up = 1;
+                } else give_up = 1;
+                if (++count >= prm->ls_iterations) give_up = 1;
+            } while (fabs(G_new) > prm->abs_tol && fabs(G_new / G_0) > prm->ls_tolerance && !give_up);
+            if (give_up) { /* best step on fail (:316-340) */
+                double s_best = fabs(search[0][0]), G_best = fabs(search[0][1]);
+                int best = 0;
+                for (int i = 1; i < count; i++) {
+                    const double s_test = fabs(search[i][0]), G_test = fabs(search[i][1]);
+                    if (fabs(s_best) < 1.0e-12 || (s_test > 1.0e-12 && G_test < G_best)) { s_best = s_test; G_best = G_test; best = i; }
+                }
+                double G_dummy;
+                if ((err = nlpcg_gvalue(&s, upd, search[best][0], &s_current, R, scratch, &G_dummy))) goto done;
+            }
+        }
+        s.iteration++; /* fNumIteration++ (NLSolver.cpp:172) */
+        /* NLSolver.cpp:174-195: residual at the updated state */
+        if ((err = nlpcg_form_rhs(&s, R))) goto done;
+        error = sqrt(dot(neq, R, R));
+        if (getenv("ORC_NLPCG_TRACE")) fprintf(stderr, "%d: Relative error = %e\n", s.iteration, error / error0);
+        EXIT_ITERATION(s.iteration);
+        if (prm->solve_max_iterations >= 0 && num_iterations >= prm->solve_max_iterations) break;
+    }
+#undef EXIT_ITERATION
+done:
+    if (iterations) *iterations = s.iteration;
+    if (error_out) *error_out = error;
+    if (error0_out) *error0_out = error0;
+    free(s.work); free(R); free(Rres); free(R_last); free(u_lastdir); free(diffR); free(minv); free(upd); free(scratch); free(search);
+    return err ? -err : status;
 }

@@ -108,6 +108,26 @@ int orc_pcg_jacobi(int64_t n, const int64_t* rowptr, const int32_t* colind, cons
 void orc_cd_predictor(int64_t ndof, double dt, double* d, double* v, double* a, const uint8_t* bc, const double* bcval);
 void orc_cd_corrector(int64_t ndof, double dt, double* v, double* a, const double* R, const double* mass, const uint8_t* bc);
 
+/* a21: nonlinear preconditioned CG with secant line search, PCGSolver_LS (solvers/PCGSolver_LS.cpp:107-371) inside
+ * NLSolver::Solve / ExitIteration (solvers/NLSolver.cpp:57-263, 675-756), preconditioner = DiagonalMatrixT kDiagOnly
+ * (DiagonalMatrixT.cpp:107-113, 267-310).  u[nn][3] in/out (prescribed dofs already hold their values). */
+enum { ORC_NLPCG_CONTINUE = 0, ORC_NLPCG_CONVERGED = 1, ORC_NLPCG_FAILED = 2 }; /* SolverT::SolutionStatusT (SolverT.h:59-62) */
+typedef struct {
+    int    restart;              /* PCGSolver_LS.cpp:53 */
+    int    ls_iterations;        /* line_search_iterations */
+    double ls_tolerance;         /* line_search_tolerance */
+    double max_step;
+    double abs_tol, rel_tol, div_tol; /* NLSolver: fZeroTolerance, fTolerance, fDivTolerance */
+    int    max_iterations, min_iterations; /* NLSolver: fMaxIterations, fMinIterations */
+    int    solve_max_iterations; /* the argument of Solve(int): -1 = no limit */
+} orc_nlpcg_params_t;
+int orc_stiffness_diagonal(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, const double* u,
+                           const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration, double* diag /*[nn][3] accumulated*/);
+/* returns ORC_NLPCG_* (or -ORC_BAD_JACOBIAN ...); *iterations = SolverT::IterationNumber() at exit */
+int orc_nlpcg_solve(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, double* u,
+                    const double* u_last, orc_j2_ip_t* j2, int* alloc, const int32_t* eqnos, int64_t neq, const double* fext,
+                    const orc_nlpcg_params_t* prm, int* iterations, double* error, double* error0);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,25 @@ def reference_case(name, rel_xml, flags):
     shutil.rmtree(work)
 
 
+def pcg_history(name, rel_xml):
+    """convergence history of a PCG_solver run: the reference executable on a scratch copy of its own input with
+    output_flag="all_iterations" added (PCGSolver_LS.cpp:59-64), `Relative error` lines of NLSolver::ExitIteration"""
+    src_dir = os.path.dirname(os.path.join(REF, rel_xml))
+    work = tempfile.mkdtemp(prefix="hist_")
+    shutil.copytree(os.path.dirname(src_dir), os.path.join(work, "lvl"), ignore=shutil.ignore_patterns("benchmark", "*.run", "*.out"))
+    xml = os.path.join(work, "lvl", os.path.basename(src_dir), os.path.basename(rel_xml))
+    text = open(xml).read().replace("<PCG_solver ", '<PCG_solver output_flag="all_iterations" ')
+    open(xml, "w").write(text)
+    r = subprocess.run([os.path.join(REPO, "oracle", "_ref", "tahoe"), "-f", os.path.basename(xml)], cwd=os.path.dirname(xml),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    hist = [ln.split("=")[-1].split()[0] for ln in r.stdout.splitlines() if "Relative error =" in ln]
+    with open(os.path.join(HERE, name + "_history.txt"), "w") as f:
+        f.write("# relative error |R|/|R0| after iteration 0, 1, ... of the reference's run of benchmark_XML/%s\n" % rel_xml)
+        f.write("\n".join(hist) + "\n")
+    shutil.rmtree(work)
+    print("%-28s %d iterations" % (name + "_history", len(hist)))
+
+
 def synthetic_case(name, n, desc, flags, jitter=0.1):
     work = tempfile.mkdtemp(prefix="syn_")
     dims = n if isinstance(n, tuple) else (n, n, n)
@@ -94,6 +113,10 @@ CLAMP_X0 = [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.
 NEWTON = {"type": "nonlinear_solver", "abs_tolerance": "1.0e-12", "rel_tolerance": "1.0e-12",
           "divergence_tolerance": "1.0e+03", "max_iterations": "25", "matrix": "SPOOLES_matrix"}
 EXPLICIT = {"type": "linear_solver", "matrix": "diagonal_matrix"}
+# PCGSolver_LS with its DiagonalMatrixT preconditioner: the attributes of level.0/3D.elastostatic/beam.PCG.xml
+PCG = {"type": "PCG_solver", "abs_tolerance": "1.0e-12", "divergence_tolerance": "10.0", "line_search_iterations": "10",
+       "line_search_tolerance": "0.1", "max_iterations": "2000", "max_step": "2.5", "quick_solve_iter": "100",
+       "rel_tolerance": "1.0e-10", "restart": "30", "matrix": "diagonal_matrix"}
 
 
 def main():
@@ -109,6 +132,7 @@ def main():
         ("ref_beam_newton", "level.0/3D.elastostatic/beam.Newton.xml", ["--fint"]),
         ("ref_explicit_1", "level.0/3D.elastodynamic/explicit.1.xml", ["--every", "25", "--fint"]),
         ("ref_explicit_2", "level.0/3D.elastodynamic/explicit.2.xml", ["--every", "25", "--fint"]),
+        ("ref_beam_pcg", "level.0/3D.elastostatic/beam.PCG.xml", ["--fint"]),
         ("ref_mat_1_a", "level.1/material.solid/3D/material.01/mat.1.a.xml", ["--fint"]),
         ("ref_mat_2_a", "level.1/material.solid/3D/material.02/mat.2.a.xml", ["--fint"]),
         ("ref_mat_5_a", "level.1/material.solid/3D/material.05/mat.5.a.xml", ["--fint"]),
@@ -117,6 +141,8 @@ def main():
     for name, rel, flags in ref_cases:
         if want(name):
             reference_case(name, rel, flags)
+    if want("ref_beam_pcg"):
+        pcg_history("ref_beam_pcg", "level.0/3D.elastostatic/beam.PCG.xml")
 
     # ---- synthetic jittered cubes ----
     kstv = {"type": "small_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25}
@@ -153,6 +179,18 @@ def main():
         ("syn_ul_j2_static", 3, {"time": static(4), "integrator": "static", "kbc": pull_u(0.06), "fbc": [],
                                  "element": {"type": "updated_lagrangian"}, "material": j2, "solver": NEWTON},
          ["--every", "1", "--fint", "--lhs"]),
+        # a21: nonlinear PCG (PCGSolver_LS) -- linear, finite-strain and J2 cases
+        ("syn_ss_kstv_pcg", 3, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
+                                "element": {"type": "small_strain"}, "material": kstv, "solver": PCG}, ["--fint"]),
+        ("syn_ul_fdkstv_pcg", 3, {"time": static(2), "integrator": "static", "kbc": pull_u(0.15), "fbc": [],
+                                  "element": {"type": "updated_lagrangian"}, "material": fdkstv, "solver": PCG},
+         ["--every", "1", "--fint"]),
+        ("syn_tl_simo_pcg", 3, {"time": static(2), "integrator": "static", "kbc": pull_u(0.15), "fbc": pull_f,
+                                "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": PCG},
+         ["--every", "1", "--fint"]),
+        ("syn_ul_j2_pcg", 3, {"time": static(4), "integrator": "static", "kbc": pull_u(0.06), "fbc": [],
+                              "element": {"type": "updated_lagrangian"}, "material": j2, "solver": PCG},
+         ["--every", "1", "--fint"]),
         ("syn_tl_simo_explicit", 4, {"time": {"num_steps": 40, "time_step": 0.5 * 0.25 / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0),
                                               "schedules": [[(0.0, 1.0)]]},
                                      "integrator": "central_difference", "kbc": CLAMP_X0,

@@ -175,3 +175,36 @@ def j2_update(mat, j2, alloc):
 def j2_reset(j2, alloc):
     for e in np.nonzero(alloc)[0]:
         lib().orc_j2_reset(C.c_void_p(j2.ctypes.data + int(e) * 8 * J2_DTYPE.itemsize))
+
+
+class NlpcgParams(C.Structure):
+    """orc_nlpcg_params_t: the <PCG_solver> attributes (PCGSolver_LS.cpp:48-100, NLSolver::DefineParameters)"""
+    _fields_ = [("restart", C.c_int), ("ls_iterations", C.c_int), ("ls_tolerance", C.c_double), ("max_step", C.c_double),
+                ("abs_tol", C.c_double), ("rel_tol", C.c_double), ("div_tol", C.c_double), ("max_iterations", C.c_int),
+                ("min_iterations", C.c_int), ("solve_max_iterations", C.c_int)]
+
+
+def nlpcg_params(solver):
+    """from the parsed <PCG_solver> description (strings as in the XML); defaults of PCGSolver_LS / NLSolver"""
+    g = lambda k, d: type(d)(float(solver.get(k, d))) if not isinstance(d, int) else int(solver.get(k, d))
+    return NlpcgParams(g("restart", 50), g("line_search_iterations", 3), g("line_search_tolerance", 0.25), g("max_step", 2.5),
+                       g("abs_tolerance", 1e-10), g("rel_tolerance", 1e-12), g("divergence_tolerance", 10.0),
+                       g("max_iterations", 300), g("min_iterations", 0), -1)
+
+
+def stiffness_diagonal(form, mat, conn, X, u, u_last=None, j2=None, alloc=None, iteration=0):
+    conn = np.ascontiguousarray(conn, np.int32)
+    d = np.zeros_like(X)
+    err = lib().orc_stiffness_diagonal(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(u), _p(u_last), _p(j2),
+                                       _p(alloc), iteration, _p(d))
+    return err, d
+
+
+def nlpcg_solve(form, mat, conn, X, u, eqnos, neq, fext, prm, u_last=None, j2=None, alloc=None):
+    """PCGSolver_LS::Solve restated; u is updated in place.  returns (status, iterations, error, error0)"""
+    conn = np.ascontiguousarray(conn, np.int32)
+    it, err, err0 = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+    st = lib().orc_nlpcg_solve(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), C.c_int64(X.shape[0]), _p(X), _p(u),
+                               _p(u_last), _p(j2), _p(alloc), _p(np.ascontiguousarray(eqnos, np.int32)), C.c_int64(neq),
+                               _p(np.ascontiguousarray(fext, np.float64)), C.byref(prm), C.byref(it), C.byref(err), C.byref(err0))
+    return st, it.value, err.value, err0.value
