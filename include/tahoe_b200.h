@@ -188,6 +188,39 @@ int tb2_matrix_pcg_host(tb2_matrix* A, const double* h_b, double* h_x, double rt
 int tb2_equations_gather(const tb2_equations* eqs, const double* d_nodal, double* d_eqvec);
 int tb2_equations_scatter_add(const tb2_equations* eqs, double scale, const double* d_eqvec, double* d_nodal);
 
+/* ---- nonlinear PCG solver (SolverT subclass; the device twin of <PCG_solver><diagonal_matrix/></PCG_solver>) ------------
+ * PCGSolver_LS (solvers/PCGSolver_LS.cpp:107-371: CGSearch with Bertsekas' scaled beta, restart every `restart` iterations,
+ * secant line search of <= line_search_iterations residual evaluations, step bound max_step) inside NLSolver::Solve /
+ * ExitIteration (solvers/NLSolver.cpp:57-263, 675-756); preconditioner = diag K(u) re-formed at every restart
+ * (DiagonalMatrixT kDiagOnly, DiagonalMatrixT.cpp:107-113, 267-323).  Parameter names are the XML attributes. */
+typedef enum { TB2_SOLVER_CONTINUE = 0, TB2_SOLVER_CONVERGED = 1, TB2_SOLVER_FAILED = 2 } tb2_solver_status; /* SolverT::SolutionStatusT, SolverT.h:59-62 */
+typedef struct {
+    int32_t restart;                 /* PCGSolver_LS.cpp:53-56 */
+    int32_t line_search_iterations;  /* :66-69, default 3; 0 = full steps (NLSolver::Update) */
+    double  line_search_tolerance;   /* :71-74, default 0.25 */
+    double  max_step;                /* :76-79, default 2.5 */
+    double  abs_tolerance;           /* NLSolver fZeroTolerance */
+    double  rel_tolerance;           /* NLSolver fTolerance */
+    double  divergence_tolerance;    /* NLSolver fDivTolerance */
+    int32_t max_iterations;          /* NLSolver fMaxIterations */
+    int32_t min_iterations;          /* NLSolver fMinIterations */
+} tb2_nlpcg_params;
+typedef struct tb2_nlpcg tb2_nlpcg;
+int tb2_nlpcg_create(tb2_group* group, tb2_equations* eqs, const tb2_nlpcg_params* params, tb2_nlpcg** solver);
+int tb2_nlpcg_destroy(tb2_nlpcg* solver);
+/* SolverT::Solve(max_iterations) for one load step (SolverT::InitStep state: iteration number -1).  d_u[nn][3]: displacement
+ * with the prescribed dofs already set, updated in place; d_u_last: last converged displacement (J2 only, else NULL);
+ * d_fext[nn][3]: nodal forces of this step (FieldT::FormRHS).  solve_max_iterations = -1: no limit beyond params.
+ * *status = tb2_solver_status; *iterations = SolverT::IterationNumber() at exit; *error = |R|, *error0 = |R| of the first pass.
+ * An element failure (TB2_ERR_BAD_JACOBIAN / TB2_ERR_J2_LOCAL) is returned with *status = TB2_SOLVER_FAILED, as NLSolver::Solve
+ * turns the exception into kFailed (NLSolver.cpp:247-262). */
+int tb2_nlpcg_solve(tb2_nlpcg* solver, double* d_u, const double* d_u_last, const double* d_fext, int solve_max_iterations,
+                    int* status, int* iterations, double* error, double* error0);
+int tb2_nlpcg_solve_host(tb2_nlpcg* solver, double* h_u, const double* h_u_last, const double* h_fext, int solve_max_iterations,
+                         int* status, int* iterations, double* error, double* error0);
+/* residual sweeps (K1) and preconditioner sweeps (K3 diagonal) launched so far */
+int tb2_nlpcg_counters(const tb2_nlpcg* solver, int64_t* residual_sweeps, int64_t* preconditioner_sweeps);
+
 /* ---- multi-GPU (replaces CommManagerT::AllGather / CommunicatorT::Sum) ------------ */
 /* One process per GPU.  The harness creates an NCCL unique id on rank 0, distributes it by its own
  * means, and every rank calls tb2_comm_init on its mesh.  h_interface_nodes are this rank's local node

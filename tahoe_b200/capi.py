@@ -29,6 +29,7 @@ tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_expli
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
+tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface""".split()
 
@@ -393,3 +394,51 @@ class Matrix(_Handle):
         it, rn = C.c_int(0), C.c_double(0.0)
         _chk(lib().tb2_matrix_pcg(self.h, _dp(d_b), _dp(d_x), C.c_double(rtol), C.c_double(atol), int(max_iter), C.byref(it), C.byref(rn)))
         return it.value, rn.value
+
+
+class NlpcgParams(C.Structure):
+    """tb2_nlpcg_params: the <PCG_solver> attributes"""
+    _fields_ = [("restart", C.c_int32), ("line_search_iterations", C.c_int32), ("line_search_tolerance", C.c_double),
+                ("max_step", C.c_double), ("abs_tolerance", C.c_double), ("rel_tolerance", C.c_double),
+                ("divergence_tolerance", C.c_double), ("max_iterations", C.c_int32), ("min_iterations", C.c_int32)]
+
+
+def nlpcg_params(solver=None, **kw):
+    """from a parsed <PCG_solver> description (attribute strings) and/or keywords; defaults of PCGSolver_LS / NLSolver"""
+    d = dict(restart=50, line_search_iterations=3, line_search_tolerance=0.25, max_step=2.5, abs_tolerance=1e-10,
+             rel_tolerance=1e-12, divergence_tolerance=10.0, max_iterations=300, min_iterations=0)
+    for src in (solver or {}, kw):
+        for k, v in src.items():
+            if k in d:
+                d[k] = type(d[k])(float(v))
+    return NlpcgParams(**d)
+
+
+class NonlinearPCG(_Handle):
+    """device twin of Tahoe's PCG_solver + diagonal_matrix (PCGSolver_LS)"""
+    _destroy = "tb2_nlpcg_destroy"
+    CONTINUE, CONVERGED, FAILED = 0, 1, 2
+
+    def __init__(self, group, eqs, params):
+        self.group, self.eqs, self.params = group, eqs, params
+        self._init_handle(eqs)
+        _chk(lib().tb2_nlpcg_create(group.h, eqs.h, C.byref(params), C.byref(self.h)))
+
+    def solve_host(self, u, fext, u_last=None, solve_max_iterations=-1):
+        """u [nn][3] is updated in place; returns (status, iterations, error, error0)"""
+        assert u.dtype == np.float64 and u.flags.c_contiguous
+        st, it, e, e0 = C.c_int(0), C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+        _chk(lib().tb2_nlpcg_solve_host(self.h, _p(u), _p(_f64(u_last)), _p(_f64(fext)), int(solve_max_iterations), C.byref(st),
+                                        C.byref(it), C.byref(e), C.byref(e0)))
+        return st.value, it.value, e.value, e0.value
+
+    def solve(self, d_u, d_fext, d_u_last=None, solve_max_iterations=-1):
+        st, it, e, e0 = C.c_int(0), C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+        _chk(lib().tb2_nlpcg_solve(self.h, _dp(d_u), _dp(d_u_last), _dp(d_fext), int(solve_max_iterations), C.byref(st), C.byref(it),
+                                   C.byref(e), C.byref(e0)))
+        return st.value, it.value, e.value, e0.value
+
+    def counters(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _chk(lib().tb2_nlpcg_counters(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -1,0 +1,450 @@
+// tb2_nlpcg.cu -- the nonlinear preconditioned conjugate-gradient solver of Tahoe's <PCG_solver>, device resident.
+//
+// Replaces PCGSolver_LS (solvers/PCGSolver_LS.cpp: Iterate :107-118, CGSearch :145-211, Update :213-348, GValue :351-371) running
+// inside NLSolver::Solve / ExitIteration (solvers/NLSolver.cpp:57-263, 675-756) with <diagonal_matrix/> as its matrix type, i.e.
+// a DiagonalMatrixT in kDiagOnly mode (SolverT.cpp:1097-1102, DiagonalMatrixT.cpp:107-113, 267-323) that is re-formed every
+// `restart` iterations.  The solver needs no assembled tangent: one iteration is 2-4 residual sweeps (K1 + ordered node gather)
+// and a handful of equation-space vector kernels; displacement, residuals, search directions and the preconditioner never leave
+// the device.  The host keeps the control flow of the reference (restart counter, secant line search with its bracketing rules,
+// convergence tests) and reads two scalars per residual evaluation -- the same decisions, taken from the same quantities.
+//
+// Reductions are two-stage with a fixed block order (no float atomics): reruns are bit-identical.  Multi-GPU:
+// partial nodal forces / diagonals are summed over the partition interface, dot products count owned equations once and are
+// all-reduced (2 scalars).
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "tb2_internal.h"
+
+namespace tb2 {
+
+int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration);
+int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
+bool comm_active(tb2_mesh* m);
+const unsigned char* comm_owned_mask(tb2_mesh* m);
+int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n);
+
+static const int kNlBlocks = 148 * 4;
+
+TB2_DEV double nl_block_sum(double v, double* sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t; // valid in thread 0
+}
+
+// FEManagerT::FormRHS on the active equations: R = fext - fint (NodeManagerT::FormRHS adds the nodal forces, the element group
+// -fint); partial sums of R.R (SolverT::Residual) and, for the line search, of update.R (PCGSolver_LS::GValue)
+__global__ void __launch_bounds__(256) k_nl_residual(int64_t n, const int* __restrict__ eq_node, const double* __restrict__ fext,
+                                                    const double* __restrict__ fint, const double* __restrict__ upd,
+                                                    const unsigned char* __restrict__ w, double* __restrict__ R, double* __restrict__ partial)
+{
+    __shared__ double sh[32];
+    double rr = 0.0, gr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = __ldg(eq_node + i);
+        const double r = fext[k] - fint[k];
+        R[i] = r;
+        if (!w || w[i]) {
+            rr += r * r;
+            if (upd) gr += upd[i] * r;
+        }
+    }
+    rr = nl_block_sum(rr, sh);
+    gr = nl_block_sum(gr, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = rr;
+        partial[2 * blockIdx.x + 1] = gr;
+    }
+}
+// out[0..1] = sums of the interleaved partials, in block order
+__global__ void __launch_bounds__(1024) k_nl_sum2(int nparts, const double* __restrict__ partial, double* __restrict__ out)
+{
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    a = nl_block_sum(a, sh);
+    b = nl_block_sum(b, sh);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+// DiagonalMatrixT::Factorize (DiagonalMatrixT.cpp:267-310): reciprocal, pivots with |m| <= kSmall = 1e-12 are left as they are
+__global__ void k_nl_factorize(int64_t n, const int* __restrict__ eq_node, const double* __restrict__ diag, double* __restrict__ minv)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = diag[eq_node[i]];
+    minv[i] = fabs(d) > 1.0e-12 ? 1.0 / d : d;
+}
+// CGSearch, restart branch (PCGSolver_LS.cpp:152-165): R_last = R; dir = M^-1 R; dir_last = dir; partial of dir.R
+__global__ void __launch_bounds__(256) k_nl_steepest(int64_t n, const double* __restrict__ R, const double* __restrict__ minv,
+                                                    const unsigned char* __restrict__ w, double* __restrict__ R_last,
+                                                    double* __restrict__ dir, double* __restrict__ partial)
+{
+    __shared__ double sh[32];
+    double g = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double r = R[i], d = r * minv[i];
+        R_last[i] = r;
+        dir[i] = d;
+        if (!w || w[i]) g += d * r;
+    }
+    g = nl_block_sum(g, sh);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = g; partial[2 * blockIdx.x + 1] = 0.0; }
+}
+// Bertsekas (6.32) with the scaling matrix (PCGSolver_LS.cpp:166-186): partials of R.M^-1(R - R_last) and R_last.M^-1 R_last
+__global__ void __launch_bounds__(256) k_nl_beta_partials(int64_t n, const double* __restrict__ R, const double* __restrict__ R_last,
+                                                         const double* __restrict__ minv, const unsigned char* __restrict__ w,
+                                                         double* __restrict__ partial)
+{
+    __shared__ double sh[32];
+    double num = 0.0, den = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (w && !w[i]) continue;
+        const double r = R[i], rl = R_last[i], mi = minv[i];
+        num += r * ((r - rl) * mi);
+        den += rl * (rl * mi);
+    }
+    num = nl_block_sum(num, sh);
+    den = nl_block_sum(den, sh);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = num; partial[2 * blockIdx.x + 1] = den; }
+}
+// (:188-201) beta = num / den unless |den| < 1e-24 (then steepest descent); R_last = R; dir = M^-1 R + beta dir; partial of dir.R
+__global__ void __launch_bounds__(256) k_nl_direction(int64_t n, const double* __restrict__ red, const double* __restrict__ R,
+                                                     const double* __restrict__ minv, const unsigned char* __restrict__ w,
+                                                     double* __restrict__ R_last, double* __restrict__ dir, double* __restrict__ partial)
+{
+    __shared__ double sh[32];
+    const double beta = fabs(red[1]) < 1.0e-24 ? 0.0 : red[0] / red[1];
+    double g = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double r = R[i];
+        const double d = r * minv[i] + beta * dir[i];
+        R_last[i] = r;
+        dir[i] = d;
+        if (!w || w[i]) g += d * r;
+    }
+    g = nl_block_sum(g, sh);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = g; partial[2 * blockIdx.x + 1] = 0.0; }
+}
+// FEManagerT::Update -> FieldT::AssembleUpdate (FieldT.cpp:531-556): u[active] += ds * update
+__global__ void k_nl_update(int64_t n, const int* __restrict__ eq_node, double ds, const double* __restrict__ upd, double* __restrict__ u)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) u[eq_node[i]] += ds * upd[i];
+}
+__global__ void k_nl_eq_owned(int64_t neq, const int* __restrict__ eq_node, const unsigned char* __restrict__ node_owned, unsigned char* __restrict__ w)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < neq) w[i] = node_owned[eq_node[i] / 3];
+}
+
+} // namespace tb2
+
+using namespace tb2;
+
+struct tb2_nlpcg {
+    tb2_mesh* mesh = nullptr; // outlives the group and the equation set in every host's teardown order
+    tb2_group* group = nullptr;
+    tb2_equations* eqs = nullptr;
+    tb2_nlpcg_params prm{};
+    DevBuf<double> R, R_last, dir, minv, fint, diag, partial, red;
+    DevBuf<unsigned char> eq_owned;
+    int64_t residual_sweeps = 0, preconditioner_sweeps = 0;
+};
+
+namespace {
+
+struct Ctx {
+    tb2_nlpcg* s;
+    tb2_mesh* m;
+    cudaStream_t st;
+    int64_t n;
+    unsigned vb, nb1;
+    double* u;
+    const double* ul;
+    const double* fext;
+    const unsigned char* w;
+    int iteration; // SolverT::fNumIteration
+};
+
+int read2(Ctx& c, double out[2])
+{
+    k_nl_sum2<<<1, 1024, 0, c.st>>>((int)c.vb, c.s->partial.p, c.s->red.p);
+    if (comm_active(c.m)) TB2_CHECK(comm_allreduce_scalars(c.m, c.s->red.p, 2));
+    TB2_CUDA(cudaMemcpyAsync(out, c.s->red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.st));
+    TB2_CUDA(cudaStreamSynchronize(c.st));
+    return TB2_OK;
+}
+// R(u) on the device; h[0] = R.R, h[1] = update.R (when with_update)
+int form_rhs(Ctx& c, bool with_update, double h[2])
+{
+    tb2_nlpcg* s = c.s;
+    TB2_CHECK(launch_element_forces(s->group, c.u, c.ul, c.iteration));
+    TB2_CHECK(launch_node_gather(c.m, s->fint.p, true));
+    if (comm_active(c.m)) TB2_CHECK(tb2_comm_sum_interface(c.m, s->fint.p));
+    {
+        ProfScope ps(c.m, kProfPcgVec, 2);
+        k_nl_residual<<<c.vb, 256, 0, c.st>>>(c.n, s->eqs->eq_node.p, c.fext, s->fint.p, with_update ? s->dir.p : nullptr, c.w, s->R.p, s->partial.p);
+        TB2_CHECK(read2(c, h));
+    }
+    s->residual_sweeps++;
+    return tb2_group_status(s->group, nullptr); // kBadJacobianDet etc. surface here, as the exception does in GValue / FormRHS
+}
+int form_preconditioner(Ctx& c)
+{
+    tb2_nlpcg* s = c.s;
+    TB2_CHECK(tb2_form_stiffness_diagonal(s->group, c.u, c.ul, c.iteration, s->diag.p));
+    if (comm_active(c.m)) TB2_CHECK(tb2_comm_sum_interface(c.m, s->diag.p));
+    ProfScope ps(c.m, kProfPcgVec);
+    k_nl_factorize<<<c.nb1, 256, 0, c.st>>>(c.n, s->eqs->eq_node.p, s->diag.p, s->minv.p);
+    s->preconditioner_sweeps++;
+    return TB2_OK;
+}
+// PCGSolver_LS::GValue (:351-371)
+int gvalue(Ctx& c, double step, double& s_current, double& G, double& rr)
+{
+    {
+        ProfScope ps(c.m, kProfPcgVec);
+        k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, c.s->eqs->eq_node.p, step - s_current, c.s->dir.p, c.u);
+    }
+    s_current = step;
+    double h[2];
+    TB2_CHECK(form_rhs(c, true, h));
+    rr = h[0];
+    G = h[1];
+    return TB2_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int tb2_nlpcg_create(tb2_group* g, tb2_equations* eqs, const tb2_nlpcg_params* prm, tb2_nlpcg** out)
+{
+    TB2_ARG(g && eqs && prm && out && eqs->mesh == g->mesh);
+    TB2_ARG(prm->restart >= 0 && prm->line_search_iterations >= 0 && prm->max_iterations >= 0);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    tb2_nlpcg* s = new tb2_nlpcg;
+    s->mesh = m;
+    s->group = g;
+    s->eqs = eqs;
+    s->prm = *prm;
+    const int64_t n = eqs->neq;
+    cudaError_t e = cudaSuccess;
+    for (DevBuf<double>* b : {&s->R, &s->R_last, &s->dir, &s->minv})
+        if (e == cudaSuccess) e = b->alloc(n);
+    if (e == cudaSuccess) e = s->fint.alloc(3 * m->nn);
+    if (e == cudaSuccess) e = s->diag.alloc(3 * m->nn);
+    if (e == cudaSuccess) e = s->partial.alloc(2 * kNlBlocks);
+    if (e == cudaSuccess) e = s->red.alloc(2);
+    if (e != cudaSuccess) {
+        delete s;
+        return cuda_fail(e, "tb2_nlpcg_create: work vectors", __FILE__, __LINE__);
+    }
+    *out = s;
+    return TB2_OK;
+}
+
+int tb2_nlpcg_destroy(tb2_nlpcg* s)
+{
+    if (!s) return TB2_OK;
+    DeviceGuard dg(s->mesh->device);
+    cudaStreamSynchronize(s->mesh->stream);
+    delete s;
+    return TB2_OK;
+}
+
+int tb2_nlpcg_counters(const tb2_nlpcg* s, int64_t* residual_sweeps, int64_t* preconditioner_sweeps)
+{
+    TB2_ARG(s);
+    if (residual_sweeps) *residual_sweeps = s->residual_sweeps;
+    if (preconditioner_sweeps) *preconditioner_sweeps = s->preconditioner_sweeps;
+    return TB2_OK;
+}
+
+int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const double* d_fext, int solve_max_iterations, int* status,
+                    int* iterations, double* error_out, double* error0_out)
+{
+    TB2_ARG(s && d_u && d_fext && status);
+    tb2_mesh* m = s->group->mesh;
+    DeviceGuard dg(m->device);
+    const tb2_nlpcg_params& prm = s->prm;
+    Ctx c;
+    c.s = s;
+    c.m = m;
+    c.st = m->stream;
+    c.n = s->eqs->neq;
+    c.nb1 = (unsigned)((c.n + 255) / 256);
+    c.vb = c.nb1 < (unsigned)kNlBlocks ? c.nb1 : (unsigned)kNlBlocks;
+    c.u = d_u;
+    c.ul = d_u_last;
+    c.fext = d_fext;
+    c.iteration = -1; // SolverT::InitStep
+    c.w = nullptr;
+    if (comm_active(m)) {
+        if (!s->eq_owned.p) {
+            TB2_CUDA(s->eq_owned.alloc(c.n));
+            k_nl_eq_owned<<<c.nb1, 256, 0, c.st>>>(c.n, s->eqs->eq_node.p, comm_owned_mask(m), s->eq_owned.p);
+        }
+        c.w = s->eq_owned.p;
+    }
+    *status = TB2_SOLVER_CONTINUE;
+    int rc = TB2_OK;
+    double h[2], error = 0.0, error0 = 0.0;
+    int num_iterations = 0, tan_iterations = 0, restart_count = -1;
+    std::vector<double> search(2 * (size_t)(prm.line_search_iterations > 2 ? prm.line_search_iterations + 1 : 3));
+
+    // NLSolver::ExitIteration (NLSolver.cpp:675-756)
+    auto exit_iteration = [&](int iter) {
+        if (iter == -1) {
+            error0 = error;
+            return error0 < prm.abs_tolerance ? TB2_SOLVER_CONVERGED : TB2_SOLVER_CONTINUE;
+        }
+        const double rel = error / error0;
+        if (rel > prm.divergence_tolerance) return TB2_SOLVER_FAILED;
+        if (iter < prm.min_iterations - 1) return TB2_SOLVER_CONTINUE;
+        if (rel < prm.rel_tolerance || error < prm.abs_tolerance) return TB2_SOLVER_CONVERGED;
+        if (iter >= prm.max_iterations) return TB2_SOLVER_FAILED;
+        return TB2_SOLVER_CONTINUE;
+    };
+#define NL_TRY(call)                 \
+    do {                             \
+        rc = (call);                 \
+        if (rc != TB2_OK) goto done; \
+    } while (0)
+
+    NL_TRY(form_rhs(c, false, h));
+    error = std::sqrt(h[0]);
+    *status = exit_iteration(c.iteration);
+    while (*status == TB2_SOLVER_CONTINUE) {
+        num_iterations++;
+        tan_iterations++;
+        if (num_iterations == 1 || tan_iterations >= prm.restart) { // fReformTangentIterations = fRestart
+            tan_iterations = 0;
+            NL_TRY(form_preconditioner(c));
+        }
+        // ---- CGSearch: the new direction (in s->dir); G_a = direction . residual comes with it
+        restart_count++;
+        {
+            ProfScope ps(m, kProfPcgVec, 3);
+            if (restart_count == 0 || restart_count == prm.restart) {
+                k_nl_steepest<<<c.vb, 256, 0, c.st>>>(c.n, s->R.p, s->minv.p, c.w, s->R_last.p, s->dir.p, s->partial.p);
+                restart_count = 0;
+            } else {
+                k_nl_beta_partials<<<c.vb, 256, 0, c.st>>>(c.n, s->R.p, s->R_last.p, s->minv.p, c.w, s->partial.p);
+                k_nl_sum2<<<1, 1024, 0, c.st>>>((int)c.vb, s->partial.p, s->red.p);
+                if (comm_active(m)) NL_TRY(comm_allreduce_scalars(m, s->red.p, 2));
+                k_nl_direction<<<c.vb, 256, 0, c.st>>>(c.n, s->red.p, s->R.p, s->minv.p, c.w, s->R_last.p, s->dir.p, s->partial.p);
+            }
+        }
+        // ---- Update: secant search for the step s with R(u + s dir) . dir = 0 (PCGSolver_LS.cpp:213-348)
+        double rr_last = 0.0;
+        if (prm.line_search_iterations == 0) {
+            k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, s->eqs->eq_node.p, 1.0, s->dir.p, c.u); // NLSolver::Update: the full step
+            c.iteration++;
+            NL_TRY(form_rhs(c, false, h));
+            rr_last = h[0];
+        } else {
+            NL_TRY(read2(c, h));
+            double s_current = 0.0, s_a = 0.0, G_a = h[0], s_b = 1.0, G_b = 0.0, G_new = 0.0, rr = 0.0;
+            search[0] = s_a; search[1] = G_a;
+            NL_TRY(gvalue(c, s_b, s_current, G_b, rr));
+            search[2] = s_b; search[3] = G_b;
+            const double G_0 = std::fabs(G_a) > std::fabs(G_b) ? G_b : G_a;
+            int count = 2;
+            bool give_up = false;
+            do {
+                const double mm = (G_a - G_b) / (s_a - s_b);
+                const double bb = G_b - mm * s_b;
+                double s_new = -bb / mm;
+                if (s_new > prm.max_step || s_new < 0.0) {
+                    give_up = true;
+                    if (s_new > prm.max_step) {
+                        s_new = prm.max_step;
+                        NL_TRY(gvalue(c, s_new, s_current, G_new, rr));
+                        search[2 * count] = s_new; search[2 * count + 1] = G_new;
+                        count++;
+                    }
+                    break;
+                }
+                NL_TRY(gvalue(c, s_new, s_current, G_new, rr));
+                search[2 * count] = s_new; search[2 * count + 1] = G_new;
+                if (std::fabs(G_a) > std::fabs(G_new) && std::fabs(G_a) > std::fabs(G_b)) { G_a = G_new; s_a = s_new; give_up = false; }
+                else if (std::fabs(G_b) > std::fabs(G_new) && std::fabs(G_b) > std::fabs(G_a)) { G_b = G_new; s_b = s_new; give_up = false; }
+                else if (G_b * G_a > 0) {
+                    if (G_a * G_new < 0) { G_a = G_new; s_a = s_new; }
+                    else if (G_b * G_new < 0) { G_b = G_new; s_b = s_new; }
+                    else give_up = true;
+                } else give_up = true;
+                if (++count >= prm.line_search_iterations) give_up = true;
+            } while (std::fabs(G_new) > prm.abs_tolerance && std::fabs(G_new / G_0) > prm.line_search_tolerance && !give_up);
+            if (give_up) { // the best step tried
+                double s_best = std::fabs(search[0]), G_best = std::fabs(search[1]);
+                int best = 0;
+                for (int i = 1; i < count; i++) {
+                    const double s_test = std::fabs(search[2 * i]), G_test = std::fabs(search[2 * i + 1]);
+                    if (std::fabs(s_best) < 1.0e-12 || (s_test > 1.0e-12 && G_test < G_best)) { s_best = s_test; G_best = G_test; best = i; }
+                }
+                if (search[2 * best] != s_current) NL_TRY(gvalue(c, search[2 * best], s_current, G_new, rr));
+            }
+            // The reference now forms the residual once more at the state GValue left (NLSolver.cpp:174-195): the same sweep on
+            // the same displacements, bit for bit.  Only the solver's iteration number differs, which J2Simo3D reads
+            // (J2Simo3D.cpp:83-84) -- so that case repeats the sweep and every other material reuses the last one.
+            c.iteration++;
+            if (s->group->mat.kind == TB2_J2_SIMO) {
+                NL_TRY(form_rhs(c, false, h));
+                rr = h[0];
+            }
+            rr_last = rr;
+        }
+        error = std::sqrt(rr_last);
+        *status = exit_iteration(c.iteration);
+        if (solve_max_iterations >= 0 && num_iterations >= solve_max_iterations) break;
+    }
+#undef NL_TRY
+done:
+    if (iterations) *iterations = c.iteration;
+    if (error_out) *error_out = error;
+    if (error0_out) *error0_out = error0;
+    if (rc == TB2_ERR_BAD_JACOBIAN || rc == TB2_ERR_J2_LOCAL) { // NLSolver::Solve catches the exception and returns kFailed (NLSolver.cpp:247-262)
+        *status = TB2_SOLVER_FAILED;
+        return rc;
+    }
+    return rc;
+}
+
+int tb2_nlpcg_solve_host(tb2_nlpcg* s, double* h_u, const double* h_u_last, const double* h_fext, int solve_max_iterations, int* status,
+                         int* iterations, double* error, double* error0)
+{
+    TB2_ARG(s && h_u && h_fext && status);
+    tb2_mesh* m = s->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    DevBuf<double> u, ul, fext;
+    TB2_CUDA(u.alloc(3 * m->nn));
+    TB2_CUDA(fext.alloc(3 * m->nn));
+    TB2_CUDA(cudaMemcpyAsync(u.p, h_u, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(fext.p, h_fext, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_u_last) {
+        TB2_CUDA(ul.alloc(3 * m->nn));
+        TB2_CUDA(cudaMemcpyAsync(ul.p, h_u_last, bytes, cudaMemcpyHostToDevice, m->stream));
+    }
+    const int rc = tb2_nlpcg_solve(s, u.p, h_u_last ? ul.p : nullptr, fext.p, solve_max_iterations, status, iterations, error, error0);
+    TB2_CUDA(cudaMemcpyAsync(h_u, u.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return rc;
+}
+
+} // extern "C"

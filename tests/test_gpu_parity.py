@@ -8,7 +8,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import tahoe_input as ti
-from cases import ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import PCG, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -329,6 +329,76 @@ def test_pcg_matches_oracle_and_reference(tb2, oracle):
     d = np.zeros_like(c.X)
     d[eqs.eqnos() > 0] = x
     assert relerr(d, c.ref("d_1")) < TOL
+
+
+@pytest.mark.parametrize("name", PCG)
+def test_nonlinear_pcg_matches_reference_and_oracle(tb2, oracle, name):
+    """a21: the device PCGSolver_LS against the reference's own PCG_solver runs (iteration counts per step, converged
+    displacements, J2 history) -- the same checks tests/test_oracle_golden.py makes on the oracle"""
+    from test_oracle_golden import nlpcg_steps
+    c = Case(name)
+    code, _, _ = c.bc(0.0)
+    mesh, grp, _ = _group(tb2, c)
+    eqs = tb2.Equations(mesh, code)
+    solver = tb2.NonlinearPCG(grp, eqs, tb2.nlpcg_params(c.desc["solver"]))
+    isj2 = c.desc["material"]["type"] == "Simo_J2"
+
+    def solve_step(d, d_last, fext):
+        st, it, err, err0 = solver.solve_host(d, fext, d_last if isj2 else None)
+        return st, it
+
+    iters, ic = c.ref("iters"), int(c.ref("iters_ic")[0])
+    for k, d, it in nlpcg_steps(c, solve_step, grp.close_step if isj2 else None):
+        want = ic if k == 0 else iters[k - 1]
+        # identical decisions as long as rounding does not flip a line-search branch; the long beam run (119 iterations to
+        # |R| < 1e-12) is only pinned to +-25 %, as for the oracle
+        assert abs(it - want) <= (0.25 * abs(want) if name == "ref_beam_pcg" else max(2, 0.05 * abs(want))), (k, it, want)
+        if k in c.dump_steps:
+            assert relerr(d, c.ref("d_%d" % k)) < 1e-9
+    sweeps, precs = solver.counters()
+    assert sweeps > 0 and precs > 0
+    if isj2:
+        data, flags, alloc = grp.get_history()
+        assert np.array_equal(alloc, c.ref("j2_alloc"))
+        ref = c.ref("j2_data").reshape(c.ne, -1)
+        assert np.abs(data[alloc > 0] - ref[alloc > 0]).max() < 1e-8
+
+
+def test_nonlinear_pcg_is_deterministic_and_reports_element_failure(tb2):
+    X, conn, ns, u = _synthetic((4, 4, 4))
+    desc = {"type": "Simo_isotropic", "E": 100.0, "nu": 0.25, "density": 1.0}
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 0.05
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.TOTAL_LAGRANGIAN, tb2.material(desc))
+    eqs = tb2.Equations(mesh, code)
+    solver = tb2.NonlinearPCG(grp, eqs, tb2.nlpcg_params(restart=20, line_search_iterations=10, line_search_tolerance=0.1,
+                                                         rel_tolerance=1e-10, abs_tolerance=1e-12, max_iterations=500))
+    runs = []
+    for _ in range(2):
+        d = np.zeros_like(X)
+        st, it, err, err0 = solver.solve_host(d, fext)
+        assert st == solver.CONVERGED and err / err0 < 1e-10
+        runs.append((it, d))
+    assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1])  # bit-reproducible
+    f = grp.internal_force_host(runs[0][1])
+    free = code == 0
+    assert np.abs((fext - f)[free]).max() < 1e-9
+    # a start state with an inverted element: the residual sweep reports kBadJacobianDet, which NLSolver::Solve turns into kFailed
+    d = np.zeros_like(X)
+    d[conn[20, 6]] = [-0.6, -0.6, -0.6]
+    with pytest.raises(tb2.Tb2Error) as ei:
+        solver.solve_host(d, fext)
+    assert ei.value.code == 1
+    # a load far beyond the material's range must end as kFailed (divergence / inverted element), never as a silent success
+    d = np.zeros_like(X)
+    try:
+        st, it, err, err0 = solver.solve_host(d, 1e4 * fext)
+        assert st == solver.FAILED
+    except tb2.Tb2Error as e:
+        assert e.code in (1, 2)
 
 
 def _newton_gpu(tb2, c, linear_solve):
