@@ -154,7 +154,8 @@ __global__ void k_nl_eq_owned(int64_t neq, const int* __restrict__ eq_node, cons
 using namespace tb2;
 
 struct tb2_nlpcg {
-    tb2_mesh* mesh = nullptr; // outlives the group and the equation set in every host's teardown order
+    int device = 0; // the solver may outlive the group / mesh it was made for (FEManagerT deletes element groups before solvers):
+                    // its destructor touches nothing but its own buffers
     tb2_group* group = nullptr;
     tb2_equations* eqs = nullptr;
     tb2_nlpcg_params prm{};
@@ -237,7 +238,7 @@ int tb2_nlpcg_create(tb2_group* g, tb2_equations* eqs, const tb2_nlpcg_params* p
     tb2_mesh* m = g->mesh;
     DeviceGuard dg(m->device);
     tb2_nlpcg* s = new tb2_nlpcg;
-    s->mesh = m;
+    s->device = m->device;
     s->group = g;
     s->eqs = eqs;
     s->prm = *prm;
@@ -260,8 +261,8 @@ int tb2_nlpcg_create(tb2_group* g, tb2_equations* eqs, const tb2_nlpcg_params* p
 int tb2_nlpcg_destroy(tb2_nlpcg* s)
 {
     if (!s) return TB2_OK;
-    DeviceGuard dg(s->mesh->device);
-    cudaStreamSynchronize(s->mesh->stream);
+    DeviceGuard dg(s->device);
+    cudaDeviceSynchronize();
     delete s;
     return TB2_OK;
 }

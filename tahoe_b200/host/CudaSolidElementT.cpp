@@ -54,7 +54,8 @@ CudaSolidElementT<BaseT>::CudaSolidElementT(const ElementSupportT& support, cons
 	fGroup(NULL),
 	fEqs(NULL),
 	fMatrix(NULL),
-	fIsJ2(false)
+	fIsJ2(false),
+	fMuted(false)
 {
 	this->SetName(name);
 }
@@ -160,7 +161,7 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 	if (this->fMassType == ContinuumElementT::kNoMass) formMa = 0;
 	if (formMa || (this->fBodySchedule && this->fBody.Magnitude() > kSmall))
 		ExceptionT::GeneralFail(caller, "inertial / body-force residual terms are not on the device path (explicit lumped-mass and static analyses only)");
-	if (!formKd) return;
+	if (!formKd || fMuted) return;
 
 	const FieldT& field = this->Field();
 	const dArray2DT& disp = field[0];
@@ -194,18 +195,32 @@ void CudaSolidElementT<BaseT>::LHSDriver(GlobalT::SystemTypeT sys_type)
 
 	/* device assembly into the cooperating matrix: K3 straight into its CSR, no element matrices cross the bus */
 	const FieldT& field = this->Field();
-	if (!fEqs) { /* equation numbers exist now: prescribed dofs have eqnos <= 0 (FieldT.cpp:635-659) */
-		const iArray2DT& eq = field.Equations();
-		std::vector<uint8_t> bc(eq.Length());
-		for (int i = 0; i < eq.Length(); i++) bc[i] = eq[i] > 0 ? 0 : 1;
-		Check(tb2_equations_create(fMesh, &bc[0], &fEqs), caller);
-		Check(tb2_matrix_create(fEqs, &fMatrix), caller);
-	}
+	DeviceEquations();
+	if (!fMatrix) Check(tb2_matrix_create(fEqs, &fMatrix), caller);
 	const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
 	int iteration = this->ElementSupport().IterationNumber(this->Group());
 	Check(tb2_matrix_clear(fMatrix), caller);
 	Check(tb2_form_stiffness_host(fGroup, fMatrix, field[0].Pointer(), last, iteration), caller);
 	cuda_lhs->AddDeviceMatrix(fMatrix, constK);
+}
+
+template <class BaseT>
+tb2_equations* CudaSolidElementT<BaseT>::DeviceEquations(void)
+{
+	const char caller[] = "CudaSolidElementT::DeviceEquations";
+	if (!fEqs) { /* equation numbers exist now: prescribed dofs have eqnos <= 0 (FieldT.cpp:635-659) */
+		const iArray2DT& eq = this->Field().Equations();
+		std::vector<uint8_t> bc(eq.Length());
+		for (int i = 0; i < eq.Length(); i++) bc[i] = eq[i] > 0 ? 0 : 1;
+		Check(tb2_equations_create(fMesh, &bc[0], &fEqs), caller);
+		/* the device numbers equations as NodeManagerT::SetEquationNumbers does (node-major, no renumbering): verify once */
+		std::vector<int32_t> dev_eq(eq.Length());
+		Check(tb2_equations_get(fEqs, &dev_eq[0]), caller);
+		for (int i = 0; i < eq.Length(); i++)
+			if ((eq[i] > 0 || dev_eq[i] > 0) && eq[i] != dev_eq[i])
+				ExceptionT::GeneralFail(caller, "equation numbering differs from the device's at dof %d (renumbering matrix type?)", i);
+	}
+	return fEqs;
 }
 
 template <class BaseT>

@@ -26,12 +26,22 @@ namespace Tahoe {
 
 class CudaPCGMatrixT;
 
-/** interface the cooperating matrix uses to ask an element group for a device-assembled tangent */
+class FieldT;
+
+/** interface the cooperating matrix / solver plugins use to reach an element group's device objects */
 class CudaStiffnessSourceT
 {
 public:
 	virtual ~CudaStiffnessSourceT(void) {}
 	virtual tb2_mesh* DeviceMesh(void) = 0;
+	virtual tb2_group* DeviceGroup(void) = 0;
+	/** equation numbers of the group's field on the device (built on first use, after Tahoe has numbered the equations) */
+	virtual tb2_equations* DeviceEquations(void) = 0;
+	virtual const FieldT& DeviceField(void) const = 0;
+	virtual int SolverGroup(void) const = 0;
+	virtual bool NeedsLastDisplacement(void) const = 0;
+	/** while set, RHSDriver() adds the tractions only: a device-resident solver (CudaPCGSolverT) forms -fint itself */
+	virtual void MuteInternalForce(bool mute) = 0;
 };
 
 template <class BaseT>
@@ -53,6 +63,12 @@ public:
 	/*@}*/
 
 	virtual tb2_mesh* DeviceMesh(void) { return fMesh; }
+	virtual tb2_group* DeviceGroup(void) { return fGroup; }
+	virtual tb2_equations* DeviceEquations(void);
+	virtual const FieldT& DeviceField(void) const { return this->Field(); }
+	virtual int SolverGroup(void) const { return this->Group(); }
+	virtual bool NeedsLastDisplacement(void) const { return fIsJ2; }
+	virtual void MuteInternalForce(bool mute) { fMuted = mute; }
 
 protected:
 
@@ -72,6 +88,7 @@ private:
 	tb2_equations* fEqs;   /**< built lazily: equation numbers are set after TakeParameterList */
 	tb2_matrix* fMatrix;   /**< device tangent of this group (structure from the mesh) */
 	bool fIsJ2;
+	bool fMuted;           /**< see MuteInternalForce */
 	dArray2DT fFint;       /**< [nn][3] internal force of the whole group */
 };
 

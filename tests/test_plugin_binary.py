@@ -34,6 +34,11 @@ def _cases():
     newton = {"type": "nonlinear_solver", "abs_tolerance": "1.0e-12", "rel_tolerance": "1.0e-12", "divergence_tolerance": "1.0e+03",
               "max_iterations": "25", "matrix": "SPOOLES_matrix"}
     pcg = dict(newton, matrix="CUDA_PCG_matrix", matrix_attrs='rel_tolerance="1.0e-13" max_iterations="20000"')
+    # a21: the reference's nonlinear PCG (PCGSolver_LS + diagonal_matrix) against the device-resident CUDA_PCG_solver
+    nlpcg = {"type": "PCG_solver", "abs_tolerance": "1.0e-13", "divergence_tolerance": "10.0", "line_search_iterations": "10",
+             "line_search_tolerance": "0.1", "max_iterations": "3000", "max_step": "2.5", "quick_solve_iter": "100",
+             "rel_tolerance": "1.0e-12", "restart": "40", "matrix": "diagonal_matrix"}
+    cuda_nlpcg = dict(nlpcg, type="CUDA_PCG_solver")
     pull = CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.06}, {"nodeset": 2, "dof": 3, "type": "u", "schedule": 1, "value": 0.02}]
     n = 5
     dt = 0.25 * (1.0 / n) / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0)
@@ -49,6 +54,11 @@ def _cases():
                                 "element": {"type": "small_strain"}, "material": kstv, "solver": newton}, pcg),
         "static_tl_simo_pcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                 "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": newton}, pcg),
+        "static_tl_simo_nlpcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull,
+                                  "fbc": [{"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.004}],
+                                  "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": nlpcg}, cuda_nlpcg),
+        "static_ul_j2_nlpcg": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                "element": {"type": "updated_lagrangian"}, "material": j2, "solver": nlpcg}, cuda_nlpcg),
         # J2: device K1 with history, Tahoe's host tangent + SPOOLES (non-symmetric tangent)
         "static_ul_j2_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                              "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton}, None),
@@ -128,6 +138,10 @@ def test_plugin_reproduces_reference_output(name):
         b = _nodal_output(os.path.join(work, name + ".cuda.io0.run"))
         assert a.shape == b.shape and a.shape[0] == 6 ** 3
         assert np.abs(a).max() > 1e-6
-        assert np.abs(a - b).max() < 1e-9 * np.abs(a).max()
+        # two nonlinear-CG runs stopped at |R| < 1e-12 |R0| agree to the conditioning of the problem, not to the LU cases' 1e-9
+        tol = 1e-7 if name.endswith("nlpcg") else 1e-9
+        assert np.abs(a - b).max() < tol * np.abs(a).max()
+        if name.endswith("nlpcg"):
+            assert "device PCG" in r1.stdout
     finally:
         shutil.rmtree(work, ignore_errors=True)
