@@ -29,6 +29,7 @@ struct ElemArgs {
     const double* u;  // [nn][3]
     const double* ul; // [nn][3] (J2) or null
     double* fe;       // [24][stride]
+    const double* geo; // [8 ip][7][stride] reference-configuration cache of the Neo-Hookean fast path (k_reference_geometry), or null
     MatConst mat;
     J2Hist hist;
     int iteration;
@@ -41,17 +42,23 @@ TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
     atomicMin(p.status + 1, (unsigned long long)e);
 }
 
-template <int FORM, int MAT>
-TB2_DEV void internal_force_body(const ElemArgs& p)
+// L1 prefetch of the nodal data (X and u triples) of the element a persistent thread will process next
+TB2_DEV void prefetch_nodes(const ElemArgs& p, const int (&n)[8])
 {
-    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= p.ne) return;
-    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
-    if (p.skip && p.skip[e]) return;
-    int n[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+    for (int a = 0; a < 8; a++) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.X + 3 * (int64_t)n[a]));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.X + 3 * (int64_t)n[a] + 2));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.u + 3 * (int64_t)n[a]));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.u + 3 * (int64_t)n[a] + 2));
+    }
+}
 
+// one element: node ids n[] already in registers.  PREFETCH: n_next[] are the nodes of the thread's next element, whose nodal
+// data is pulled into L1 half-way through the integration-point loop
+template <int FORM, int MAT, bool PREFETCH>
+TB2_DEV void internal_force_element(const ElemArgs& p, const int64_t e, const int (&n)[8], const int (&n_next)[8], const bool has_next)
+{
     Modes cX, cU, cL, A;
     load_modes(p.X, n, cX);
     load_modes(p.u, n, cU);
@@ -69,6 +76,7 @@ TB2_DEV void internal_force_body(const ElemArgs& p)
 
 #pragma unroll 1
     for (int ip = 0; ip < 8; ip++) {
+        if (PREFETCH && ip == 3 && has_next) prefetch_nodes(p, n_next);
         double s0, s1, s2;
         ip_signs(ip, s0, s1, s2);
         double J0[3][3], H[3][3], J0a[3][3], G[3][3], S[3][3];
@@ -152,6 +160,50 @@ TB2_DEV void internal_force_body(const ElemArgs& p)
         modes_to_nodes(A, i, f);
 #pragma unroll
         for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
+    }
+}
+
+// one thread = one element of the launch
+template <int FORM, int MAT>
+TB2_DEV void internal_force_body(const ElemArgs& p)
+{
+    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.ne) return;
+    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
+    if (p.skip && p.skip[e]) return;
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+    internal_force_element<FORM, MAT, false>(p, e, n, n, false);
+}
+
+// Persistent form: the grid is the set of CTAs resident at once; a thread walks elements t, t + grid, ... and keeps the
+// connectivity of its next element in registers (requested a whole element ahead) and that element's nodal data on its way
+// into L1 (requested half an element ahead), so the gather latency that a one-element thread exposes at its start
+// (conn -> X, u: two dependent round trips, ~20 % of the stall cycles in profiles/r01d) overlaps the FP64 work instead.
+template <int FORM, int MAT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_internal_force_persistent(const ElemArgs p)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.ne) return;
+    int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
+    int n[8], n_next[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+    for (;;) {
+        const int64_t t_next = t + step;
+        const bool has_next = t_next < p.ne;
+        int64_t e_next = e;
+        if (has_next) e_next = p.elist ? (int64_t)__ldg(p.elist + t_next) : t_next;
+#pragma unroll
+        for (int a = 0; a < 8; a++) n_next[a] = __ldg(p.conn + a * p.stride + e_next);
+        if (!(p.skip && p.skip[e])) internal_force_element<FORM, MAT, true>(p, e, n, n_next, has_next);
+        if (!has_next) break;
+        t = t_next;
+        e = e_next;
+#pragma unroll
+        for (int a = 0; a < 8; a++) n[a] = n_next[a];
     }
 }
 
@@ -252,6 +304,107 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const Elem
 #pragma unroll
             for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
         mode_accumulate(A, s0, s1, s2, G);
+    }
+    if (err) report(p, err, e);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double f[8];
+        modes_to_nodes(A, i, f);
+#pragma unroll
+        for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
+    }
+}
+
+// ---- K1, total-Lagrangian SimoIso3D, cached reference geometry ------------------------------------------------------------
+// ncu (profiles/r01d): K1 is FP64-pipe bound (65 % pipe utilisation) while DRAM sits at 11 %.  Everything in the integrand that
+// depends on the reference configuration only -- J0 = dX/dxi, adj(J0), M0 = adj(J0) adj(J0)^T, det J0: 66 of the ~270 FP64
+// instructions per integration point -- is therefore computed once (k_reference_geometry) and streamed back in: 7 doubles per
+// point, 448 B per element per sweep of otherwise idle HBM bandwidth, read evict-first so the force scratch keeps its L2 lines.
+// The arithmetic on the cached values is the arithmetic of k_internal_force, so both kernels return the same bits.
+__global__ void __launch_bounds__(128) k_reference_geometry(int64_t ne, int64_t stride, const int* __restrict__ conn,
+                                                           const double* __restrict__ X, double* __restrict__ geo)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(conn + a * stride + e);
+    Modes cX;
+    load_modes(X, n, cX);
+#pragma unroll 1
+    for (int ip = 0; ip < 8; ip++) {
+        double s0, s1, s2, J0[3][3], J0a[3][3], M0[6];
+        ip_signs(ip, s0, s1, s2);
+        mode_gradient(cX, s0, s1, s2, J0);
+        const double det0 = adj3(J0, J0a);
+        sym_fft(J0a, M0);
+        double* g = geo + (int64_t)(ip * 7) * stride + e;
+#pragma unroll
+        for (int q = 0; q < 6; q++) g[(int64_t)q * stride] = M0[q];
+        g[(int64_t)6 * stride] = det0;
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_internal_force_simo_geo(const ElemArgs p)
+{
+    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.ne) return;
+    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
+    if (p.skip && p.skip[e]) return;
+    const double* geo = p.geo + e;
+    double gq[7]; // M0[0..5], det0 of the current point; the next point's values are requested one iteration ahead
+#pragma unroll
+    for (int q = 0; q < 7; q++) gq[q] = __ldcs(geo + (int64_t)q * p.stride);
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+    Modes cx, cU, A;
+    load_modes(p.X, n, cx);
+    load_modes(p.u, n, cU);
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            A.m[k][i] = 0.0;
+            cx.m[k][i] += cU.m[k][i]; // modes of x = X + u, summed exactly as k_internal_force does
+        }
+    int err = kErrNone;
+#pragma unroll 1
+    for (int ip = 0; ip < 8; ip++) {
+        double gn[7];
+        const int ipn = ip < 7 ? ip + 1 : 7;
+#pragma unroll
+        for (int q = 0; q < 7; q++) gn[q] = __ldcs(geo + (int64_t)(ipn * 7 + q) * p.stride);
+        double s0, s1, s2;
+        ip_signs(ip, s0, s1, s2);
+        double j[3][3], ja[3][3], N[3][3], G[3][3];
+        mode_gradient(cx, s0, s1, s2, j);
+        const double det0 = gq[6];
+        const double detj = adj3(j, ja);
+        if (det0 <= 0.0 || detj <= 0.0) err = kErrBadJacobian; // ParentDomainT.cpp:451 / TotalLagrangianT.cpp:127-128
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            N[i][0] = j[i][0] * gq[0] + j[i][1] * gq[5] + j[i][2] * gq[4];
+            N[i][1] = j[i][0] * gq[5] + j[i][1] * gq[1] + j[i][2] * gq[3];
+            N[i][2] = j[i][0] * gq[4] + j[i][1] * gq[3] + j[i][2] * gq[2];
+        }
+        double trb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) trb += N[i][0] * j[i][0] + N[i][1] * j[i][1] + N[i][2] * j[i][2];
+        const double dj2 = detj * detj;
+        const double tt = rcbrt(dj2 * dj2 * detj * det0);
+        const double rdd = (tt * tt) * tt * (dj2 * dj2);
+        const double sc = p.mat.mu * tt;
+        const double pr = 0.5 * p.mat.kappa * (dj2 - det0 * det0) * rdd;
+        const double al = sc * detj, q = pr - sc * trb * (1.0 / 3.0);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
+        mode_accumulate(A, s0, s1, s2, G);
+#pragma unroll
+        for (int q2 = 0; q2 < 7; q2++) gq[q2] = gn[q2];
     }
     if (err) report(p, err, e);
 #pragma unroll
@@ -368,7 +521,7 @@ __global__ void k_j2_reset_step(int64_t ne, J2Hist h)
 
 typedef void (*force_kernel_t)(const ElemArgs);
 static const int kDefaultMinBlocks = 3; // r01b: 168 regs, 3 CTAs/SM: K1 191 us vs 203 (2) and 201 (4) on 1M elements
-static force_kernel_t pick_force_kernel(int form, int mat)
+static force_kernel_t pick_force_kernel(int form, int mat, bool geo)
 {
     // registers-per-thread cap experiment (TB2_K1_MINBLOCKS=2|3|4 resident CTAs of 128 threads per SM); default from the ncu study
     static int minb = 0;
@@ -389,6 +542,14 @@ static force_kernel_t pick_force_kernel(int form, int mat)
         const char* s = getenv("TB2_K1_REGS");
         reg_variant = s ? atoi(s) : 0;
     }
+    static int geo_minb = 0; // TB2_K1_GEO_MINBLOCKS=2|3|4: resident CTAs of the cached-geometry kernel (experiment knob)
+    if (!geo_minb) {
+        const char* s = getenv("TB2_K1_GEO_MINBLOCKS");
+        geo_minb = s ? atoi(s) : 3;
+        if (geo_minb < 2 || geo_minb > 4) geo_minb = 3;
+    }
+    if (geo && form == kTotalLagrangian && mat == kSimoIso)
+        return geo_minb == 2 ? k_internal_force_simo_geo<2> : (geo_minb == 3 ? k_internal_force_simo_geo<3> : k_internal_force_simo_geo<4>);
     if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 144) return k_internal_force_r<kTotalLagrangian, kSimoIso, 144>;
     if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 152) return k_internal_force_r<kTotalLagrangian, kSimoIso, 152>;
     if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 160) return k_internal_force_r<kTotalLagrangian, kSimoIso, 160>;
@@ -440,7 +601,7 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
                                 const int* d_elist, const unsigned char* d_skip)
 {
     tb2_mesh* m = g->mesh;
-    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind);
+    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind, g->geo.p != nullptr);
     if (!k) {
         set_error("formulation %d does not support material %d", g->form, g->mat.kind);
         return TB2_ERR_ARG;
@@ -460,6 +621,7 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
     p.u = d_u;
     p.ul = d_ul;
     p.fe = m->fe.p;
+    p.geo = g->geo.p;
     p.mat = g->mc;
     p.hist = group_hist(g);
     p.iteration = iteration;
@@ -474,9 +636,30 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
         if ((tv == 64 || tv == 96) && !(getenv("TB2_K1_SMEM") && atoi(getenv("TB2_K1_SMEM")) > 0)) T = tv;
     }
     if (e1 <= e0) return TB2_OK;
+    unsigned grid = (unsigned)((e1 - e0 + T - 1) / T);
+    {   // persistent, prefetching form of the finite-strain Neo-Hookean sweep: experiment knob TB2_K1_PERSIST=<waves>, off by default.
+        // r01e, 1M elements: 220 us (168 registers, 244 B of spills for the 16 extra index registers) against 183 us for one
+        // thread per element; 216 us at 2 CTAs/SM (255 registers, no spills).  The sweep sits in a register-bound corner: what
+        // the prefetch saves in exposed gather latency it loses in occupancy or spills.
+        static int persist = -1, sms = 148, pminb = 3;
+        if (persist < 0) {
+            const char* s = getenv("TB2_K1_PERSIST");
+            persist = s ? atoi(s) : 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+            const char* s2 = getenv("TB2_K1_MINBLOCKS");
+            pminb = s2 ? atoi(s2) : kDefaultMinBlocks;
+            if (pminb < 2 || pminb > 4) pminb = kDefaultMinBlocks;
+        }
+        if (persist > 0 && g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_SIMO_ISO && !g->geo.p && T == 128) {
+            k = pminb == 2 ? k_internal_force_persistent<kTotalLagrangian, kSimoIso, 2>
+                           : (pminb == 3 ? k_internal_force_persistent<kTotalLagrangian, kSimoIso, 3> : k_internal_force_persistent<kTotalLagrangian, kSimoIso, 4>);
+            const unsigned resident = (unsigned)(sms * pminb * persist); // persist = waves of resident CTAs (1 = exactly resident)
+            if (grid > resident) grid = resident;
+        }
+    }
     {
         ProfScope ps(m, kProfForce, 1, st);
-        k<<<(unsigned)((e1 - e0 + T - 1) / T), T, 0, st>>>(p);
+        k<<<grid, T, 0, st>>>(p);
     }
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
@@ -533,6 +716,19 @@ int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_grou
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist.p, 0, g->hist.n * sizeof(double), mesh->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist_flag.p, 0, g->hist_flag.n * sizeof(int), mesh->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist_alloc.p, 0, g->hist_alloc.n * sizeof(int), mesh->stream);
+    }
+    // reference-configuration cache of the finite-strain Neo-Hookean force kernel: experiment knob TB2_K1_GEO=1 (448 B per element).
+    // r01e: 24 % fewer FP64 instructions (2282 -> 1724 per element) bought 3.6 % (190.5 -> 183.7 us on 1M elements, ncu) and nothing
+    // inside the slab pipeline: the sweep is bound by dependency latency at 3 warps per scheduler, not by FP64 issue, so the cache
+    // is off by default and its memory stays free.
+    const char* geo_env = getenv("TB2_K1_GEO");
+    if (e == cudaSuccess && form != TB2_SMALL_STRAIN && mat->kind == TB2_SIMO_ISO && geo_env && geo_env[0] == '1') {
+        e = g->geo.alloc((size_t)56 * mesh->stride);
+        if (e == cudaSuccess) {
+            k_reference_geometry<<<(unsigned)((mesh->ne + 127) / 128), 128, 0, mesh->stream>>>(mesh->ne, mesh->stride, mesh->conn.p, mesh->X.p, g->geo.p);
+            mesh->launches++;
+            e = cudaGetLastError();
+        }
     }
     const unsigned long long init[2] = {0ull, ~0ull};
     if (e == cudaSuccess) e = cudaMemcpyAsync(g->status.p, init, sizeof init, cudaMemcpyHostToDevice, mesh->stream);
