@@ -38,7 +38,10 @@ typedef enum {
     TB2_ERR_COMM = 7          /* ExceptionT::kMPIFail */
 } tb2_status;
 
-typedef enum { TB2_SMALL_STRAIN = 0, TB2_TOTAL_LAGRANGIAN = 1, TB2_UPDATED_LAGRANGIAN = 2 } tb2_formulation;
+typedef enum { TB2_SMALL_STRAIN = 0, TB2_TOTAL_LAGRANGIAN = 1, TB2_UPDATED_LAGRANGIAN = 2,
+               TB2_SMALL_STRAIN_BBAR = 3 /* SmallStrainT with strain_displacement="B-bar": mean-dilatation B-bar of Hughes (4.5.11-23),
+                                            SmallStrainT.cpp:337-374,404-421, SolidElementT::Set_B_bar SolidElementT.cpp:956-1044 */
+             } tb2_formulation;
 /* materials: SSKStV (Hookean/KStV/SSKStV.cpp), FDKStV (FDKStV.cpp), SimoIso3D (Simo/SimoIso3D.cpp), J2Simo3D (plasticity_J2/J2Simo3D.cpp) */
 typedef enum { TB2_SSKSTV = 0, TB2_FDKSTV = 1, TB2_SIMO_ISO = 2, TB2_J2_SIMO = 3 } tb2_material_kind;
 typedef enum { TB2_HARD_LINEAR = 0, TB2_HARD_LINEAR_EXP = 1 } tb2_hardening_kind;

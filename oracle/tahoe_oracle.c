@@ -455,6 +455,28 @@ static void set_B(double dN[3][8], double B[6][24])
     }
 }
 
+/* mean shape-function gradient, Hughes (4.5.23): SmallStrainT::SetMeanGradient (SmallStrainT.cpp:404-421) */
+static void mean_gradient(double dN[8][3][8], const double* det, double mg[3][8])
+{
+    double vol = 0.0;
+    for (int ip = 0; ip < 8; ip++) vol += det[ip]; /* unit weights */
+    memset(mg, 0, 24 * sizeof(double));
+    for (int ip = 0; ip < 8; ip++)
+        for (int d = 0; d < 3; d++)
+            for (int a = 0; a < 8; a++) mg[d][a] += det[ip] / vol * dN[ip][d][a];
+}
+/* B-bar of Hughes (4.5.11-16): SolidElementT::Set_B_bar, 3D branch (SolidElementT.cpp:1003-1043) */
+static void set_B_bar(double dN[3][8], double mg[3][8], double B[6][24])
+{
+    for (int a = 0; a < 8; a++) {
+        double nx = dN[0][a], ny = dN[1][a], nz = dN[2][a];
+        double fx = (mg[0][a] - nx) / 3.0, fy = (mg[1][a] - ny) / 3.0, fz = (mg[2][a] - nz) / 3.0;
+        B[0][3 * a + 0] = nx + fx; B[1][3 * a + 0] = fx; B[2][3 * a + 0] = fx; B[3][3 * a + 0] = 0.0; B[4][3 * a + 0] = nz; B[5][3 * a + 0] = ny;
+        B[0][3 * a + 1] = fy; B[1][3 * a + 1] = ny + fy; B[2][3 * a + 1] = fy; B[3][3 * a + 1] = nz; B[4][3 * a + 1] = 0.0; B[5][3 * a + 1] = nx;
+        B[0][3 * a + 2] = fz; B[1][3 * a + 2] = fz; B[2][3 * a + 2] = nz + fz; B[3][3 * a + 2] = ny; B[4][3 * a + 2] = nx; B[5][3 * a + 2] = 0.0;
+    }
+}
+
 /* finite-strain stress / modulus dispatch: FSSolidMatT s_ij, c_ijkl */
 static int fs_material(const orc_material_t* m, const double* F, const double* Fl, orc_j2_ip_t* j2, int ip, int* alloc,
                        int iteration, double* sig, double c[6][6])
@@ -490,6 +512,27 @@ int orc_element_force(int form, const orc_material_t* m, const double X[8][3], c
             for (int i = 0; i < 3; i++) x[a][i] = X[a][i] + u[a][i];
         err = orc_hex8_shape(x, dNc, detc);
         if (err) return err;
+    }
+    if (form == ORC_SMALL_STRAIN_BBAR) { /* SmallStrainT::SetGlobalShape B-bar branch (:340-374) + FormKd (:255-282) */
+        double mg[3][8], B[6][24];
+        mean_gradient(dN, det, mg);
+        for (int ip = 0; ip < 8; ip++) {
+            double e[6], sig[6];
+            set_B_bar(dN[ip], mg, B);
+            for (int I = 0; I < 6; I++) { /* fB.Multx(u) then ScaleOffDiagonal(0.5) */
+                double t = 0.0;
+                for (int a = 0; a < 8; a++)
+                    for (int i = 0; i < 3; i++) t += B[I][3 * a + i] * u[a][i];
+                e[I] = I < 3 ? t : 0.5 * t;
+            }
+            hooke_stress(m, e, sig);
+            for (int r = 0; r < 24; r++) { /* fB.MultTx(s_ij) */
+                double t = 0.0;
+                for (int I = 0; I < 6; I++) t += B[I][r] * sig[I];
+                fe[r] += det[ip] * t;
+            }
+        }
+        return ORC_OK;
     }
     for (int ip = 0; ip < 8; ip++) {
         double G[9], sig[6];
@@ -555,11 +598,13 @@ int orc_element_stiffness(int form, const orc_material_t* m, const double X[8][3
     }
     double kg[8][8]; /* stress stiffness */
     memset(kg, 0, sizeof kg);
+    double mg[3][8];
+    if (form == ORC_SMALL_STRAIN_BBAR) mean_gradient(dN, det, mg);
     for (int ip = 0; ip < 8; ip++) {
         double c[6][6], sig[6], B[6][24], scale;
         double(*dNx)[8]; /* spatial gradients used for B */
         double dNp[3][8];
-        if (form == ORC_SMALL_STRAIN) {
+        if (form == ORC_SMALL_STRAIN || form == ORC_SMALL_STRAIN_BBAR) {
             hooke_moduli(m, c);
             dNx = dN[ip];
             scale = det[ip];
@@ -593,7 +638,8 @@ int orc_element_stiffness(int form, const orc_material_t* m, const double X[8][3
                     kg[a][b] += scale * s;
                 }
         }
-        set_B(dNx, B);
+        if (form == ORC_SMALL_STRAIN_BBAR) set_B_bar(dNx, mg, B);
+        else set_B(dNx, B);
         for (int r = 0; r < 24; r++)
             for (int cc = 0; cc < 24; cc++) {
                 double s = 0.0;
@@ -605,7 +651,7 @@ int orc_element_stiffness(int form, const orc_material_t* m, const double X[8][3
                 Ke[r + 24 * cc] += scale * s;
             }
     }
-    if (form != ORC_SMALL_STRAIN)
+    if (form != ORC_SMALL_STRAIN && form != ORC_SMALL_STRAIN_BBAR)
         for (int a = 0; a < 8; a++)
             for (int b = 0; b < 8; b++)
                 for (int i = 0; i < 3; i++) Ke[(3 * a + i) + 24 * (3 * b + i)] += kg[a][b];

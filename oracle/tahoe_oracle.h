@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-enum { ORC_SMALL_STRAIN = 0, ORC_TOTAL_LAGRANGIAN = 1, ORC_UPDATED_LAGRANGIAN = 2 };
+enum { ORC_SMALL_STRAIN = 0, ORC_TOTAL_LAGRANGIAN = 1, ORC_UPDATED_LAGRANGIAN = 2,
+       ORC_SMALL_STRAIN_BBAR = 3 /* SmallStrainT with strain_displacement="B-bar" (kMeanDilBbar, SmallStrainT.cpp:337-374) */ };
 enum { ORC_SSKSTV = 0, ORC_FDKSTV = 1, ORC_SIMO_ISO = 2, ORC_J2_SIMO = 3 };
 enum { ORC_OK = 0, ORC_BAD_JACOBIAN = 1, ORC_J2_LOCAL_FAIL = 2 };
 enum { ORC_J2_NOTINIT = -1, ORC_J2_PLASTIC = 0, ORC_J2_ELASTIC = 1 }; /* J2SimoC0HardeningT.h:33-36 */

@@ -73,6 +73,26 @@ TB2_DEV void internal_force_element(const ElemArgs& p, const int64_t e, const in
 
     int alloc = 0, err = kErrNone;
     if (MAT == kJ2Simo) alloc = p.hist.alloc[e];
+    // Mean-dilatation B-bar (SmallStrainT.cpp:337-374).  B-bar_a = B_a + 1/3 m (b_a - grad N_a)^T with b_a the volume average of
+    // grad N_a (Hughes 4.5.23), so the strain at a point is eps + 1/3 (theta_bar - tr eps) 1 with
+    //   theta_bar = sum_a b_a . u_a = sum_ip w det0 tr(grad u) / sum_ip w det0 = sum_ip tr(H adj(J0)) / sum_ip det0,
+    // and, tr(sigma) = 3 kappa theta_bar being the same at every point for the isotropic linear material, the B-bar^T sigma
+    // integral equals the plain B^T sigma integral of those stresses (the (b_a - grad N_a) tr(sigma)/3 terms cancel in the sum).
+    double theta_bar = 0.0;
+    if (MAT == kSSKStVBbar) {
+        double num = 0.0, vol = 0.0;
+#pragma unroll 1
+        for (int ip = 0; ip < 8; ip++) {
+            double s0, s1, s2, J0[3][3], H[3][3], J0a[3][3];
+            ip_signs(ip, s0, s1, s2);
+            mode_gradient(cX, s0, s1, s2, J0);
+            mode_gradient(cU, s0, s1, s2, H);
+            vol += adj3(J0, J0a);
+#pragma unroll
+            for (int i = 0; i < 3; i++) num += H[i][0] * J0a[0][i] + H[i][1] * J0a[1][i] + H[i][2] * J0a[2][i];
+        }
+        theta_bar = num / vol;
+    }
 
 #pragma unroll 1
     for (int ip = 0; ip < 8; ip++) {
@@ -96,6 +116,10 @@ TB2_DEV void internal_force_element(const ElemArgs& p, const int64_t e, const in
             eps[3] = 0.5 * (g[1][2] + g[2][1]) * rdet0;
             eps[4] = 0.5 * (g[0][2] + g[2][0]) * rdet0;
             eps[5] = 0.5 * (g[0][1] + g[1][0]) * rdet0;
+            if (MAT == kSSKStVBbar) {
+                const double corr = (theta_bar - (eps[0] + eps[1] + eps[2])) * (1.0 / 3.0);
+                eps[0] += corr; eps[1] += corr; eps[2] += corr;
+            }
             hooke_stress(p.mat, eps, sig);
             sym_to_mat(sig, S);
             mul3_abt(S, J0a, G); // G = w detJ0 sigma J0^-T
@@ -521,8 +545,9 @@ __global__ void k_j2_reset_step(int64_t ne, J2Hist h)
 
 typedef void (*force_kernel_t)(const ElemArgs);
 static const int kDefaultMinBlocks = 3; // r01b: 168 regs, 3 CTAs/SM: K1 191 us vs 203 (2) and 201 (4) on 1M elements
-static force_kernel_t pick_force_kernel(int form, int mat, bool geo)
+static force_kernel_t pick_force_kernel(int form, int mat, bool geo, bool bbar = false)
 {
+    if (form == kSmallStrain && mat == kSSKStV && bbar) return k_internal_force<kSmallStrain, kSSKStVBbar, 2>;
     // registers-per-thread cap experiment (TB2_K1_MINBLOCKS=2|3|4 resident CTAs of 128 threads per SM); default from the ncu study
     static int minb = 0;
     if (!minb) {
@@ -601,7 +626,7 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
                                 const int* d_elist, const unsigned char* d_skip)
 {
     tb2_mesh* m = g->mesh;
-    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind, g->geo.p != nullptr);
+    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind, g->geo.p != nullptr, g->bbar);
     if (!k) {
         set_error("formulation %d does not support material %d", g->form, g->mat.kind);
         return TB2_ERR_ARG;
@@ -692,7 +717,9 @@ extern "C" {
 int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_group** out)
 {
     TB2_ARG(mesh && mat && out);
-    TB2_ARG(form >= 0 && form <= 2 && mat->kind >= 0 && mat->kind <= 3);
+    TB2_ARG(form >= 0 && form <= 3 && mat->kind >= 0 && mat->kind <= 3);
+    const bool bbar = form == TB2_SMALL_STRAIN_BBAR;
+    if (bbar) form = TB2_SMALL_STRAIN;
     if ((form == TB2_SMALL_STRAIN) != (mat->kind == TB2_SSKSTV)) {
         // SSSolidMatT materials go with SmallStrainT, FSSolidMatT materials with FiniteStrainT (MaterialListT checks)
         set_error("material %d is not valid for formulation %d", mat->kind, form);
@@ -702,6 +729,7 @@ int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_grou
     tb2_group* g = new tb2_group;
     g->mesh = mesh;
     g->form = form;
+    g->bbar = bbar;
     g->mat = *mat;
     g->mc.mu = mat->mu;
     g->mc.lambda = mat->lambda;

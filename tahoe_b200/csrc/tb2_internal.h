@@ -174,7 +174,8 @@ struct ProfScope {
 
 struct tb2_group {
     tb2_mesh* mesh = nullptr;
-    int form = 0;
+    int form = 0;      // kSmallStrain / kTotalLagrangian / kUpdatedLagrangian (TB2_SMALL_STRAIN_BBAR is stored as kSmallStrain + bbar)
+    bool bbar = false; // SmallStrainT::kMeanDilBbar
     tb2_material mat{};
     tb2::MatConst mc{};
     // J2 history

@@ -6,7 +6,8 @@
 
 namespace tb2 {
 
-enum { kSSKStV = 0, kFDKStV = 1, kSimoIso = 2, kJ2Simo = 3 };
+enum { kSSKStV = 0, kFDKStV = 1, kSimoIso = 2, kJ2Simo = 3,
+       kSSKStVBbar = 4 /* kernel-template tag only: SSKStV under SmallStrainT's mean-dilatation B-bar */ };
 enum { kSmallStrain = 0, kTotalLagrangian = 1, kUpdatedLagrangian = 2 };
 enum { kHardLinear = 0, kHardLinearExp = 1 };
 enum { kErrNone = 0, kErrBadJacobian = 1, kErrJ2Local = 2 };

@@ -105,6 +105,13 @@ TB2_DEV void stiffness_point(const StiffArgs& p, const int64_t e, const int (&n)
         double scale;
         if (FORM == kSmallStrain) {
             hooke_moduli(p.mat, c);
+            if (MAT == kSSKStVBbar) { // B-bar: B_a^T (C - kappa m m^T) B_b here, + kappa vol b_a b_b^T after the point loop (phase 2)
+                const double kappa = p.mat.lambda + 2.0 * p.mat.mu * (1.0 / 3.0);
+#pragma unroll
+                for (int I = 0; I < 3; I++)
+#pragma unroll
+                    for (int Jj = 0; Jj < 3; Jj++) c[I][Jj] -= kappa;
+            }
 #pragma unroll
             for (int I = 0; I < 6; I++) sig[I] = 0.0;
 #pragma unroll
@@ -337,6 +344,34 @@ __global__ void __launch_bounds__(128, (MODE == kKFull || MAT == kJ2Simo) ? 2 : 
             K[k][2][2] += geo;
         }
     }
+    if (MAT == kSSKStVBbar) {
+        // K-bar_ab = sum_ip w det [B_a^T C B_b - kappa g_a g_b^T] + kappa vol b_a b_b^T   (g = grad N; expand B-bar = B + m (b - g)^T / 3
+        // with C m = 3 kappa m, m^T B_b = g_b^T, m^T C m = 9 kappa): the first part was accumulated above with the deviatoric moduli
+        double vol = 0.0, ba[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int ip = 0; ip < 8; ip++) {
+            const double w = SM(ip, 66);
+            vol += w;
+            ba[0] += w * SM(ip, 0 + a); ba[1] += w * SM(ip, 8 + a); ba[2] += w * SM(ip, 16 + a);
+        }
+        const double kappa = p.mat.lambda + 2.0 * p.mat.mu * (1.0 / 3.0);
+        const double f = kappa / vol; // b = (sum w g) / vol: kappa vol b_a b_b^T = kappa / vol (sum w g_a)(sum w g_b)^T
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            if (k >= nk) continue;
+            const int b = MODE == kKFull ? k : ((a + k) & 7);
+            double bb[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+            for (int ip = 0; ip < 8; ip++) {
+                const double w = SM(ip, 66);
+                bb[0] += w * SM(ip, 0 + b); bb[1] += w * SM(ip, 8 + b); bb[2] += w * SM(ip, 16 + b);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) K[k][i][j] += f * ba[i] * bb[j];
+        }
+    }
 #undef SM
     if (MODE == kKDiag) {
         if (live)
@@ -490,10 +525,11 @@ static stiff_kernel_t pick_stiff_kernel(int form, int mat)
 
 
 typedef void (*elem_kernel_t)(const StiffArgs);
-static elem_kernel_t pick_elem_kernel(int form, int mat, bool diag)
+static elem_kernel_t pick_elem_kernel(int form, int mat, bool diag, bool bbar = false)
 {
     if (form == kSmallStrain) {
         if (mat != kSSKStV) return nullptr;
+        if (bbar) return diag ? k_element_stiffness<kSmallStrain, kSSKStVBbar, kKDiag> : k_element_stiffness<kSmallStrain, kSSKStVBbar, kKSym>;
         return diag ? k_element_stiffness<kSmallStrain, kSSKStV, kKDiag> : k_element_stiffness<kSmallStrain, kSSKStV, kKSym>;
     }
     switch (mat) { // UpdatedLagrangianT shares the finite-strain body
@@ -665,6 +701,10 @@ static int form_stiffness_coloured(tb2_group* g, tb2_matrix* A, const double* d_
     DeviceGuard dg(m->device);
     stiff_kernel_t k = pick_stiff_kernel(g->form, g->mat.kind);
     TB2_ARG(k != nullptr);
+    if (g->bbar) {
+        set_error("the coloured assembly form (TB2_K3_COLOURED=1) has no B-bar variant");
+        return TB2_ERR_ARG;
+    }
     TB2_CHECK(ensure_colouring(m));
     if (g->mat.kind == TB2_J2_SIMO) {
         TB2_ARG(d_ul != nullptr);
@@ -709,7 +749,7 @@ int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const dou
     const bool coloured = env_coloured && env_coloured[0] == '1';
     if (coloured) return form_stiffness_coloured(g, A, d_u, d_ul, iteration);
     DeviceGuard dg(m->device);
-    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, false);
+    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, false, g->bbar);
     TB2_ARG(k != nullptr);
     TB2_CHECK(ensure_gather_plan(A, k));
     if (g->mat.kind == TB2_J2_SIMO) {
@@ -751,7 +791,7 @@ int tb2_form_stiffness_diagonal(tb2_group* g, const double* d_u, const double* d
     TB2_ARG(g && d_u && d_diag);
     tb2_mesh* m = g->mesh;
     DeviceGuard dg(m->device);
-    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, true);
+    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, true, g->bbar);
     TB2_ARG(k != nullptr);
     const size_t smem = kElemSmem;
     TB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -94,9 +94,12 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 	/* the device path covers exactly the reference's Hex8 / 8-point / standard-B case */
 	if (this->GeometryCode() != GeometryT::kHexahedron || this->NumElementNodes() != 8 || this->NumIP() != 8 || this->NumSD() != 3)
 		ExceptionT::BadInputValue(caller, "the CUDA element group supports 8-node hexahedra with 8 integration points only");
-	const ParameterT* b_opt = list.Parameter("strain_displacement"); /* SmallStrainT only (SmallStrainT.cpp:38-42): 0 = standard */
-	if (b_opt && int(*b_opt) != 0)
-		ExceptionT::BadInputValue(caller, "strain_displacement must be \"standard\" (B-bar is a different formulation)");
+	const ParameterT* b_opt = list.Parameter("strain_displacement"); /* SmallStrainT only (SmallStrainT.cpp:38-42): 0 = standard, 1 = B-bar */
+	if (b_opt && int(*b_opt) != 0) {
+		if (fFormulation != TB2_SMALL_STRAIN || int(*b_opt) != 1)
+			ExceptionT::BadInputValue(caller, "strain_displacement must be \"standard\" or \"B-bar\"");
+		fFormulation = TB2_SMALL_STRAIN_BBAR; /* SmallStrainT::kMeanDilBbar */
+	}
 	if (this->fMaterialList->Length() != 1)
 		ExceptionT::BadInputValue(caller, "exactly one material per CUDA element group");
 

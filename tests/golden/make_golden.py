@@ -133,6 +133,7 @@ def main():
         ("ref_explicit_1", "level.0/3D.elastodynamic/explicit.1.xml", ["--every", "25", "--fint"]),
         ("ref_explicit_2", "level.0/3D.elastodynamic/explicit.2.xml", ["--every", "25", "--fint"]),
         ("ref_beam_pcg", "level.0/3D.elastostatic/beam.PCG.xml", ["--fint"]),
+        ("ref_beam_bbar", "level.0/3D.elastostatic/beam.B_bar.xml", ["--fint"]),
         ("ref_mat_1_a", "level.1/material.solid/3D/material.01/mat.1.a.xml", ["--fint"]),
         ("ref_mat_2_a", "level.1/material.solid/3D/material.02/mat.2.a.xml", ["--fint"]),
         ("ref_mat_5_a", "level.1/material.solid/3D/material.05/mat.5.a.xml", ["--fint"]),
@@ -179,6 +180,10 @@ def main():
         ("syn_ul_j2_static", 3, {"time": static(4), "integrator": "static", "kbc": pull_u(0.06), "fbc": [],
                                  "element": {"type": "updated_lagrangian"}, "material": j2, "solver": NEWTON},
          ["--every", "1", "--fint", "--lhs"]),
+        # a5: mean-dilatation B-bar (SmallStrainT strain_displacement="B-bar"), nearly incompressible so that it matters
+        ("syn_ss_kstv_bbar_static", 4, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
+                                        "element": {"type": "small_strain", "strain_displacement": "B-bar"},
+                                        "material": dict(kstv, nu=0.49), "solver": NEWTON}, ["--fint", "--lhs"]),
         # a21: nonlinear PCG (PCGSolver_LS) -- linear, finite-strain and J2 cases
         ("syn_ss_kstv_pcg", 3, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
                                 "element": {"type": "small_strain"}, "material": kstv, "solver": PCG}, ["--fint"]),

@@ -11,7 +11,14 @@ LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
 SMALL_STRAIN, TOTAL_LAGRANGIAN, UPDATED_LAGRANGIAN = 0, 1, 2
 SSKSTV, FDKSTV, SIMO_ISO, J2_SIMO = 0, 1, 2, 3
-FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2}
+FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2, "small_strain_B-bar": 3}
+
+
+def form_of(element):
+    """formulation code of a parsed element description: <small_strain strain_displacement="B-bar"> is its own code"""
+    if element["type"] == "small_strain" and element.get("strain_displacement", "standard") == "B-bar":
+        return FORM_OF["small_strain_B-bar"]
+    return FORM_OF[element["type"]]
 KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3}
 
 

@@ -227,6 +227,8 @@ def write_xml(path, d):
     L.append("    </field>\n  </nodes>\n  <element_list>")
     e, m = d["element"], d["material"]
     mass = ' mass_type="%s"' % e["mass_type"] if e.get("mass_type", "automatic") != "automatic" else ""
+    if e.get("strain_displacement", "standard") != "standard":  # SmallStrainT only (SmallStrainT.cpp:38-42)
+        mass += ' strain_displacement="%s"' % e["strain_displacement"]
     L.append('    <%s field_name="displacement"%s>\n      <hexahedron/>' % (e.get("tag", e["type"]), mass))
     if e.get("nodal_output"):
         L.append('      <solid_element_nodal_output displacements="1"/>')

@@ -25,7 +25,7 @@ def tb2():
 def _group(tb2, c):
     mesh = tb2.Mesh(c.X, c.conn)
     mat = tb2.material(c.desc["material"])
-    return mesh, tb2.Group(mesh, tb2.FORM_OF[c.desc["element"]["type"]], mat), mat
+    return mesh, tb2.Group(mesh, tb2.form_of(c.desc["element"]), mat), mat
 
 
 # ------------------------------------------------------------------ K1 / K4
@@ -40,7 +40,7 @@ def test_internal_force_matches_reference(tb2, name):
 
 FORMS = [("small_strain", "small_strain_StVenant"), ("total_lagrangian", "large_strain_StVenant"),
          ("total_lagrangian", "Simo_isotropic"), ("updated_lagrangian", "large_strain_StVenant"),
-         ("updated_lagrangian", "Simo_isotropic")]
+         ("updated_lagrangian", "Simo_isotropic"), ("small_strain_B-bar", "small_strain_StVenant")]
 
 
 def _synthetic(n=(7, 6, 5), amp=2e-2, seed=7):
@@ -297,6 +297,8 @@ def test_tangent_matches_oracle(tb2, oracle, form, matname):
 def test_two_phase_assembly_equals_coloured_assembly_and_diagonal(tb2, form, matname, monkeypatch):
     """the default two-phase (element scratch + ordered gather) K3 against the colour-by-colour form, on a shuffled mesh with
     several element chunks; the kDiagOnly entry point returns the same diagonal"""
+    if form == "small_strain_B-bar":
+        pytest.skip("the coloured form has no B-bar variant (the two-phase form is checked against the oracle and the reference)")
     X, conn, ns, u = _synthetic((9, 7, 8))
     perm = np.random.default_rng(3).permutation(conn.shape[0])
     conn = np.ascontiguousarray(conn[perm])

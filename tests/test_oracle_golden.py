@@ -12,7 +12,7 @@ TOL = 1e-10  # north_star: forces / displacements agree to 1e-10 relative
 
 def _setup(oracle, name):
     c = Case(name)
-    form = oracle.FORM_OF[c.desc["element"]["type"]]
+    form = oracle.form_of(c.desc["element"])
     mat = oracle.material(c.desc["material"])
     return c, form, mat
 

@@ -52,6 +52,11 @@ def _cases():
         "static_ss_kstv_pcg": ({"time": {"num_steps": 1, "time_step": 1.0, "schedules": [RAMP]}, "integrator": "static", "kbc": CLAMP,
                                 "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005}],
                                 "element": {"type": "small_strain"}, "material": kstv, "solver": newton}, pcg),
+        # a5: mean-dilatation B-bar at nu = 0.49, device K1 + K3 (B-bar variants) + device PCG
+        "static_ss_bbar_pcg": ({"time": {"num_steps": 1, "time_step": 1.0, "schedules": [RAMP]}, "integrator": "static", "kbc": CLAMP,
+                                "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005}],
+                                "element": {"type": "small_strain", "strain_displacement": "B-bar"}, "material": dict(kstv, nu=0.49),
+                                "solver": newton}, pcg),
         "static_tl_simo_pcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                 "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": newton}, pcg),
         "static_tl_simo_nlpcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull,
