@@ -224,6 +224,25 @@ int tb2_nlpcg_solve_host(tb2_nlpcg* solver, double* h_u, const double* h_u_last,
 /* residual sweeps (K1) and preconditioner sweeps (K3 diagonal) launched so far */
 int tb2_nlpcg_counters(const tb2_nlpcg* solver, int64_t* residual_sweeps, int64_t* preconditioner_sweeps);
 
+/* ---- Newton driver (<nonlinear_solver> with <CUDA_PCG_matrix/>) ----------------------------------------------------------
+ * NLSolver::Solve / Iterate / ExitIteration (solvers/NLSolver.cpp:57-263, 759-766, 675-756) for one load step, resident:
+ * residual (K1) -> ExitIteration -> every reform_tangent_iterations: GlobalMatrixT::Clear + FormLHS (K3) -> GlobalMatrixT::Solve
+ * (Jacobi-PCG, K6-K8, zero start guess) -> FieldT::AssembleUpdate.  Work vectors are those of a tb2_nlpcg object made for the
+ * same group and equations (its params are not used); A must have been created from the same tb2_equations. */
+typedef struct {
+    double  abs_tolerance, rel_tolerance, divergence_tolerance; /* NLSolver fZeroTolerance, fTolerance, fDivTolerance */
+    int32_t max_iterations, min_iterations;                     /* fMaxIterations, fMinIterations */
+    int32_t reform_tangent_iterations;                          /* fReformTangentIterations (default 1) */
+    double  pcg_rel_tolerance, pcg_abs_tolerance;               /* <CUDA_PCG_matrix rel_tolerance abs_tolerance max_iterations/> */
+    int32_t pcg_max_iterations;
+} tb2_newton_params;
+int tb2_newton_solve(tb2_nlpcg* work, tb2_matrix* A, const tb2_newton_params* params, double* d_u, const double* d_u_last,
+                     const double* d_fext, int solve_max_iterations, int* status, int* iterations, double* error, double* error0,
+                     int64_t* linear_iterations /* PCG iterations summed over the Newton iterations */);
+int tb2_newton_solve_host(tb2_nlpcg* work, tb2_matrix* A, const tb2_newton_params* params, double* h_u, const double* h_u_last,
+                          const double* h_fext, int solve_max_iterations, int* status, int* iterations, double* error, double* error0,
+                          int64_t* linear_iterations);
+
 /* ---- multi-GPU (replaces CommManagerT::AllGather / CommunicatorT::Sum) ------------ */
 /* One process per GPU.  The harness creates an NCCL unique id on rank 0, distributes it by its own
  * means, and every rank calls tb2_comm_init on its mesh.  h_interface_nodes are this rank's local node

@@ -36,7 +36,7 @@ tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_expli
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
-tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters
+tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface""".split()
 
@@ -449,3 +449,29 @@ class NonlinearPCG(_Handle):
         a, b = C.c_int64(0), C.c_int64(0)
         _chk(lib().tb2_nlpcg_counters(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class NewtonParams(C.Structure):
+    """tb2_newton_params: <nonlinear_solver> attributes + those of <CUDA_PCG_matrix/>"""
+    _fields_ = [("abs_tolerance", C.c_double), ("rel_tolerance", C.c_double), ("divergence_tolerance", C.c_double),
+                ("max_iterations", C.c_int32), ("min_iterations", C.c_int32), ("reform_tangent_iterations", C.c_int32),
+                ("pcg_rel_tolerance", C.c_double), ("pcg_abs_tolerance", C.c_double), ("pcg_max_iterations", C.c_int32)]
+
+
+def newton_params(solver=None, **kw):
+    d = dict(abs_tolerance=1e-10, rel_tolerance=1e-12, divergence_tolerance=1e3, max_iterations=25, min_iterations=0,
+             reform_tangent_iterations=1, pcg_rel_tolerance=1e-13, pcg_abs_tolerance=0.0, pcg_max_iterations=20000)
+    for src in (solver or {}, kw):
+        for k, v in src.items():
+            if k in d:
+                d[k] = type(d[k])(float(v))
+    return NewtonParams(**d)
+
+
+def newton_solve_host(work, A, params, u, fext, u_last=None, solve_max_iterations=-1):
+    """NLSolver::Solve on the device (tb2_newton_solve_host): u [nn][3] updated in place; returns (status, iterations, error,
+    error0, linear iterations)"""
+    st, it, e, e0, lin = C.c_int(0), C.c_int(0), C.c_double(0.0), C.c_double(0.0), C.c_int64(0)
+    _chk(lib().tb2_newton_solve_host(work.h, A.h, C.byref(params), _p(u), _p(_f64(u_last)), _p(_f64(fext)), int(solve_max_iterations),
+                                     C.byref(st), C.byref(it), C.byref(e), C.byref(e0), C.byref(lin)))
+    return st.value, it.value, e.value, e0.value, lin.value

@@ -1,4 +1,5 @@
-// tb2_nlpcg.cu -- the nonlinear preconditioned conjugate-gradient solver of Tahoe's <PCG_solver>, device resident.
+// tb2_nlpcg.cu -- the two nonlinear solution drivers of the hot path, device resident: Tahoe's <PCG_solver> (nonlinear PCG) and
+// <nonlinear_solver> (Newton) with the device CSR + Jacobi-PCG as its linear solve (tb2_newton_solve, end of file).
 //
 // Replaces PCGSolver_LS (solvers/PCGSolver_LS.cpp: Iterate :107-118, CGSearch :145-211, Update :213-348, GValue :351-371) running
 // inside NLSolver::Solve / ExitIteration (solvers/NLSolver.cpp:57-263, 675-756) with <diagonal_matrix/> as its matrix type, i.e.
@@ -449,3 +450,121 @@ int tb2_nlpcg_solve_host(tb2_nlpcg* s, double* h_u, const double* h_u_last, cons
 }
 
 } // extern "C"
+
+// ---- Newton driver ------------------------------------------------------------------------------------------------------
+// NLSolver::Solve / Iterate / ExitIteration (solvers/NLSolver.cpp:57-263, 759-766, 675-756) with a CUDA_PCG_matrix as fLHS:
+//   residual (K1 + ordered gather) -> |R| -> ExitIteration -> [tangent: GlobalMatrixT::Clear + K3] -> Jacobi-PCG (K6-K8) ->
+//   FieldT::AssembleUpdate, all on the device; the host reads one norm per Newton iteration.
+namespace {
+// update = solve result in equation space -> u[active] += update (full Newton step, NLSolver::Update :635-641)
+int newton_update(Ctx& c, const double* d_dx)
+{
+    ProfScope ps(c.m, kProfPcgVec);
+    k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, c.s->eqs->eq_node.p, 1.0, d_dx, c.u);
+    return TB2_OK;
+}
+} // namespace
+
+extern "C" int tb2_newton_solve(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, double* d_u, const double* d_u_last,
+                                const double* d_fext, int solve_max_iterations, int* status, int* iterations, double* error_out,
+                                double* error0_out, int64_t* linear_iterations)
+{
+    TB2_ARG(s && A && np && d_u && d_fext && status);
+    TB2_ARG(A->eqs == s->eqs);
+    tb2_mesh* m = s->group->mesh;
+    DeviceGuard dg(m->device);
+    Ctx c;
+    c.s = s;
+    c.m = m;
+    c.st = m->stream;
+    c.n = s->eqs->neq;
+    c.nb1 = (unsigned)((c.n + 255) / 256);
+    c.vb = c.nb1 < (unsigned)kNlBlocks ? c.nb1 : (unsigned)kNlBlocks;
+    c.u = d_u;
+    c.ul = d_u_last;
+    c.fext = d_fext;
+    c.iteration = -1;
+    c.w = nullptr;
+    if (comm_active(m)) {
+        if (!s->eq_owned.p) {
+            TB2_CUDA(s->eq_owned.alloc(c.n));
+            k_nl_eq_owned<<<c.nb1, 256, 0, c.st>>>(c.n, s->eqs->eq_node.p, comm_owned_mask(m), s->eq_owned.p);
+        }
+        c.w = s->eq_owned.p;
+    }
+    *status = TB2_SOLVER_CONTINUE;
+    int rc = TB2_OK, num_iterations = 0, tan_iterations = 0;
+    int64_t lin_total = 0;
+    double h[2], error = 0.0, error0 = 0.0;
+    const int reform = np->reform_tangent_iterations > 0 ? np->reform_tangent_iterations : 1;
+    auto exit_iteration = [&](int iter) {
+        if (iter == -1) {
+            error0 = error;
+            return error0 < np->abs_tolerance ? TB2_SOLVER_CONVERGED : TB2_SOLVER_CONTINUE;
+        }
+        const double rel = error / error0;
+        if (rel > np->divergence_tolerance) return TB2_SOLVER_FAILED;
+        if (iter < np->min_iterations - 1) return TB2_SOLVER_CONTINUE;
+        if (rel < np->rel_tolerance || error < np->abs_tolerance) return TB2_SOLVER_CONVERGED;
+        if (iter >= np->max_iterations) return TB2_SOLVER_FAILED;
+        return TB2_SOLVER_CONTINUE;
+    };
+    rc = form_rhs(c, false, h);
+    if (rc == TB2_OK) {
+        error = std::sqrt(h[0]);
+        *status = exit_iteration(c.iteration);
+    }
+    while (rc == TB2_OK && *status == TB2_SOLVER_CONTINUE) {
+        num_iterations++;
+        tan_iterations++;
+        if (num_iterations == 1 || tan_iterations >= reform) { // NLSolver.cpp:143-160
+            tan_iterations = 0;
+            if ((rc = tb2_matrix_clear(A)) != TB2_OK) break;
+            if ((rc = tb2_form_stiffness(s->group, A, c.u, c.ul, c.iteration)) != TB2_OK) break;
+            if ((rc = tb2_group_status(s->group, nullptr)) != TB2_OK) break;
+        }
+        // NLSolver::Iterate: fLHS->Solve(fRHS) -- the update from a zero start guess (the solve overwrites its argument)
+        if (cudaMemsetAsync(s->dir.p, 0, c.n * sizeof(double), c.st) != cudaSuccess) { rc = TB2_ERR_CUDA; break; }
+        int lin_it = 0;
+        double lin_r = 0.0;
+        rc = tb2_matrix_pcg(A, s->R.p, s->dir.p, np->pcg_rel_tolerance, np->pcg_abs_tolerance, np->pcg_max_iterations, &lin_it, &lin_r);
+        lin_total += lin_it;
+        if (rc != TB2_OK) break;
+        if ((rc = newton_update(c, s->dir.p)) != TB2_OK) break;
+        c.iteration++;
+        if ((rc = form_rhs(c, false, h)) != TB2_OK) break;
+        error = std::sqrt(h[0]);
+        *status = exit_iteration(c.iteration);
+        if (solve_max_iterations >= 0 && num_iterations >= solve_max_iterations) break;
+    }
+    if (iterations) *iterations = c.iteration;
+    if (error_out) *error_out = error;
+    if (error0_out) *error0_out = error0;
+    if (linear_iterations) *linear_iterations = lin_total;
+    if (rc != TB2_OK) *status = TB2_SOLVER_FAILED; // NLSolver::Solve: any exception -> kFailed (NLSolver.cpp:247-262)
+    return rc;
+}
+
+extern "C" int tb2_newton_solve_host(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, double* h_u, const double* h_u_last,
+                                     const double* h_fext, int solve_max_iterations, int* status, int* iterations, double* error,
+                                     double* error0, int64_t* linear_iterations)
+{
+    TB2_ARG(s && A && np && h_u && h_fext && status);
+    tb2_mesh* m = s->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    DevBuf<double> u, ul, fext;
+    TB2_CUDA(u.alloc(3 * m->nn));
+    TB2_CUDA(fext.alloc(3 * m->nn));
+    TB2_CUDA(cudaMemcpyAsync(u.p, h_u, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(fext.p, h_fext, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_u_last) {
+        TB2_CUDA(ul.alloc(3 * m->nn));
+        TB2_CUDA(cudaMemcpyAsync(ul.p, h_u_last, bytes, cudaMemcpyHostToDevice, m->stream));
+    }
+    const int rc = tb2_newton_solve(s, A, np, u.p, h_u_last ? ul.p : nullptr, fext.p, solve_max_iterations, status, iterations, error,
+                                    error0, linear_iterations);
+    TB2_CUDA(cudaMemcpyAsync(h_u, u.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return rc;
+}
