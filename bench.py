@@ -315,6 +315,20 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
     ms = e0.elapsed_time(e1)
     if it != iters or not np.isfinite(rn):
         raise SystemExit("bench.py: PCG ran %d of %d iterations, |r| = %g" % (it, iters, rn))
+    # configs[2] as one call: NLSolver::Solve on the device (tb2_newton_solve: K1 residual, K3 tangent, Jacobi-PCG to 1e-8, update)
+    newton = None
+    if world == 1:
+        work = capi.NonlinearPCG(g, eqs, capi.nlpcg_params())
+        prm = capi.newton_params(abs_tolerance=1e-30, rel_tolerance=1e-6, max_iterations=5, pcg_rel_tolerance=1e-8, pcg_max_iterations=4000)
+        un = np.zeros_like(X)
+        t0 = time.perf_counter()
+        st, nit, nerr, nerr0, lin = capi.newton_solve_host(work, A, prm, un, fext)
+        t_newton = time.perf_counter() - t0
+        newton = {"status": {0: "continue", 1: "converged", 2: "failed"}[st], "newton_iterations": nit + 1, "pcg_iterations": int(lin),
+                  "seconds": t_newton, "relative_residual": nerr / nerr0 if nerr0 > 0 else None,
+                  "dof_iters_per_s": float(A.neq) * lin / t_newton,
+                  "note": "host-buffer call: H2D of u and fext, residual + tangent assembly + PCG (rel 1e-8) + update per Newton iteration, D2H of u"}
+        work.close()
     tt = torch.tensor([ms, float(ms_cat[3]) / max(int(cnt_cat[3]), 1), float(ms_cat[6]) / iters, t_assembly_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -331,7 +345,12 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
            "workload": "BASELINE.json configs[2] at %d^3=%d small_strain + SSKStV elements per GPU (%d GPUs: %d elements, %d equations), CSR "
                        "assembled on the device (K3)%s, Jacobi-PCG with device-resident vectors"
                        % (n, n ** 3, world, int(ne_total), int(neq_total), " as sub-domain matrices" if world > 1 else ""),
-           "assembly": {"ms": t_assembly_ms, "elements_per_s": ne_total / (t_assembly_ms * 1e-3), "structure_build_s": t_struct},
+           "assembly": {"ms": t_assembly_ms, "elements_per_s": ne_total / (t_assembly_ms * 1e-3), "structure_build_s": t_struct,
+                        "kernels": "k_element_stiffness (symmetric-half element matrices -> [element][576] scratch) + k_assemble_gather "
+                                   "(ordered row gather into the CSR); no colouring, no atomics",
+                        "fp64_tflops": K3_FLOP_PER_ELEMENT * conn.shape[0] / (t_assembly_ms * 1e-3) * 1e-12,
+                        "scratch_plus_matrix_gbs": (2 * 576 * 8.0 * conn.shape[0] + 2 * 8.0 * A.nnz) / (t_assembly_ms * 1e-3) * 1e-9},
+           "newton": newton,
            "roofline": {"bound": "hbm", "kernel": "k_spmv (K6)", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9, "peak": hbm_peak,
                         "unit": "GB/s", "frac": spmv_bytes / (spmv_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": spmv_ms,
                         "share_of_iteration": spmv_ms * iters / ms, "traffic": PCG_SPMV_TRAFFIC_BYTES_PER_NNZ * A.nnz,
@@ -565,11 +584,13 @@ def main():
         run_gpu_arm(args)
 
 
-# Per-element figures of K1 <TL, SimoIso> from the ncu --set full capture profiles/r01c_k1_full (284,160-element slab launch):
-# thread-level DFMA 1280 + DMUL 715 + DADD 450 = 2445 FP64 instructions = 3725 flop; dram read 23.5 MB + write 7.9 MB = 110.5 B/element.
-K1_FLOP_PER_ELEMENT = 3725.0
-K1_FP64_INST_PER_ELEMENT = 2445.0
-K1_TRAFFIC_BYTES_PER_ELEMENT = 110.5
+# Per-element figures of K1 <TL, SimoIso> from the ncu --set full capture profiles/r01d_k1_details.csv (284,160-element slab launch):
+# thread-level DFMA 1316 + DMUL 573 + DADD 285 = 2174 FP64 instructions = 3490 flop; dram read 23.5 MB + write 11.6 MB = 123.5 B/element.
+K1_FLOP_PER_ELEMENT = 3490.0
+K1_FP64_INST_PER_ELEMENT = 2174.0
+K1_TRAFFIC_BYTES_PER_ELEMENT = 123.5
+# K3 element kernel <small strain, SSKStV, symmetric half> (profiles/r01e_k3_*): DFMA 7961 + DMUL 4683 + DADD 2979 per element
+K3_FLOP_PER_ELEMENT = 2 * 7961.0 + 4683.0 + 2979.0
 # k_spmv DRAM read+write per stored non-zero (ncu --set full, profiles/r01c_spmv_full: 2.465 GB for 242,991,882 nnz)
 PCG_SPMV_TRAFFIC_BYTES_PER_NNZ = 10.15
 
