@@ -56,6 +56,31 @@ def static_pcg(m, X, ns):
     return d, it
 
 
+def nonlinear_solves(m, X, ns):
+    """the two resident nonlinear drivers on this rank's sub-domain (the library takes the distributed path when the mesh has a
+    communicator): PCGSolver_LS twin and Newton + Jacobi-PCG on a total-Lagrangian Neo-Hookean block.  Returns displacements and
+    iteration counts."""
+    g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material({"type": "Simo_isotropic", "E": 100.0, "nu": 0.25, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    eqs = capi.Equations(m, code)
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 2e-3  # full nodal load on every sharer
+    fext[ns[2], 1] = 5e-4
+    solver = capi.NonlinearPCG(g, eqs, capi.nlpcg_params(restart=30, line_search_iterations=10, line_search_tolerance=0.1,
+                                                         rel_tolerance=1e-10, abs_tolerance=1e-14, max_iterations=2000))
+    d_cg = np.zeros_like(X)
+    st, it_cg, err, err0 = solver.solve_host(d_cg, fext)
+    assert st == solver.CONVERGED, "nonlinear PCG status %d" % st
+    A = capi.Matrix(eqs)
+    d_nw = np.zeros_like(X)
+    st, it_nw, err, err0, lin = capi.newton_solve_host(solver, A, capi.newton_params(abs_tolerance=1e-14, rel_tolerance=1e-10,
+                                                                                      pcg_rel_tolerance=1e-13), d_nw, fext)
+    assert st == 1, "Newton status %d" % st
+    A.close(); solver.close(); eqs.close(); g.close()
+    return d_cg, it_cg, d_nw, it_nw
+
+
 def pipelined_phase(rank, world, local):
     """64^3 elements per rank -> 3+ slab chunks: the overlapped schedule (boundary elements first, all-reduce beside the slab
     pipeline, interface nodes updated last) must give bitwise the fields of the serial schedule (single-step calls), and both
@@ -114,10 +139,12 @@ def main():
     d, v, a = ex.get_state()
     mass = ex.mass_host()
     xs, its = static_pcg(m, part["coords"], part["nodesets"])
+    d_cg, it_cg, d_nw, it_nw = nonlinear_solves(m, part["coords"], part["nodesets"])
     nn_glob = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
     # gather every rank's fields on rank 0 keyed by global node id
     out = [None] * world
-    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass, "xs": xs, "its": its})
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass, "xs": xs, "its": its,
+                                 "d_cg": d_cg, "it_cg": it_cg, "d_nw": d_nw, "it_nw": it_nw})
     ok = True
     if rank == 0:
         X, conn, ns = tmesh.structured_cube(*dims, jitter=0.15)
@@ -127,6 +154,9 @@ def main():
         d1, v1, a1 = ex1.get_state()
         mass1 = ex1.mass_host()
         xs1, its1 = static_pcg(m1, X, ns)
+        d_cg1, it_cg1, d_nw1, it_nw1 = nonlinear_solves(m1, X, ns)
+        print("nonlinear PCG iterations: single GPU %d, partitioned %s; Newton: %d, %s"
+              % (it_cg1, [o["it_cg"] for o in out], it_nw1, [o["it_nw"] for o in out]))
         print("PCG iterations: single GPU %d, partitioned %s" % (its1, [o["its"] for o in out]))
         seen = {}
         for r, o in enumerate(out):
@@ -134,6 +164,11 @@ def main():
             if not err < 1e-9 or abs(o["its"] - its1) > 3:
                 print("rank %d static PCG solution differs from the single-GPU solve: %.3e (its %d vs %d)" % (r, err, o["its"], its1))
                 ok = False
+            for nm, ref, cnt, cnt1, tol in (("d_cg", d_cg1, o["it_cg"], it_cg1, 1e-7), ("d_nw", d_nw1, o["it_nw"], it_nw1, 1e-9)):
+                err = np.abs(o[nm] - ref[o["gid"]]).max() / np.abs(ref).max()
+                if not err < tol or abs(cnt - cnt1) > max(2, 0.1 * cnt1):
+                    print("rank %d %s differs from the single-GPU solve: %.3e (iterations %d vs %d)" % (r, nm, err, cnt, cnt1))
+                    ok = False
             for nm, ref in (("d", d1), ("v", v1), ("a", a1), ("mass", mass1)):
                 err = np.abs(o[nm] - ref[o["gid"]]).max() / max(np.abs(ref).max(), 1e-300)
                 if not err < 1e-12:
