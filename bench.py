@@ -176,19 +176,26 @@ def _run_reference_batch(work, nsteps, procs):
     return time.perf_counter() - t0
 
 
-def reference_rate(n, s_lo, s_hi, procs):
+def reference_rate(n, s_lo, s_hi, procs, min_seconds=2.0):
     """element-updates/s of `procs` concurrent serial reference processes on an n^3 cube, from the wall-clock difference
-    between an s_hi-step and an s_lo-step run (cancels input parsing, set-up and FEManagerT::InitialCondition)"""
+    between an s_hi-step and an s_lo-step run (cancels input parsing, set-up and FEManagerT::InitialCondition).  If the difference
+    is shorter than min_seconds (a short --steps request) the long run is repeated with 4x the steps, so the rate never comes
+    from timer noise.  Returns (rate, seconds, elements, timed steps)."""
     work = tempfile.mkdtemp(prefix="tb2_ref_")
     try:
         ne = _write_reference_case(work, n, s_lo)
-        _write_reference_case(work, n, s_hi)
         t_lo = _run_reference_batch(work, s_lo, procs)
-        t_hi = _run_reference_batch(work, s_hi, procs)
+        k = s_hi - s_lo
+        for _ in range(4):
+            _write_reference_case(work, n, s_lo + k)
+            dt = _run_reference_batch(work, s_lo + k, procs) - t_lo
+            if dt >= min_seconds:
+                break
+            k *= 4
     finally:
         shutil.rmtree(work, ignore_errors=True)
-    dt = max(t_hi - t_lo, 1e-9)
-    return procs * ne * (s_hi - s_lo) / dt, dt, ne
+    dt = max(dt, 1e-3)
+    return procs * ne * k / dt, dt, ne, k
 
 
 def oracle_port_rate(n, steps):
@@ -206,10 +213,10 @@ def oracle_port_rate(n, steps):
 
 def cpu_baseline(sample_n=40, s_lo=2, s_hi=42):
     if os.path.exists(REF_BIN):
-        rate, dt, ne = reference_rate(sample_n, s_lo, s_hi, 1)
+        rate, dt, ne, k = reference_rate(sample_n, s_lo, s_hi, 1)
         return {"value": rate, "unit": METRIC, "cores": 1, "kind": "reference",
                 "sample": "%d^3=%d-element jittered cube, %d explicit steps of oracle/_ref/tahoe (classic total_lagrangian + Simo_isotropic, "
-                          "lumped mass, central_difference), wall(%d steps) - wall(%d steps) = %.2f s" % (sample_n, ne, s_hi - s_lo, s_hi, s_lo, dt)}
+                          "lumped mass, central_difference), wall(%d steps) - wall(%d steps) = %.2f s" % (sample_n, ne, k, s_lo + k, s_lo, dt)}
     rate, ne = oracle_port_rate(24, 4)
     return {"value": rate, "unit": METRIC, "cores": 1, "kind": "port",
             "sample": "24^3=%d elements x 4 internal-force sweeps of oracle/tahoe_oracle.c (reference binary absent)" % ne}
@@ -224,7 +231,7 @@ def run_reference_arm(args):
     w, k = max(args.warmup, 1), max(args.steps, 1)
     k = min(k, 60)
     if os.path.exists(REF_BIN):
-        rate, dt, ne = reference_rate(n, w, w + k, cores)
+        rate, dt, ne, k = reference_rate(n, w, w + k, cores)
         kind, sample = "reference", ("%d concurrent serial oracle/_ref/tahoe processes (one per host core; no MPI/METIS on this box), each a %d^3=%d-element "
                                      "jittered cube, %d timed explicit steps (wall(%d) - wall(%d) steps)" % (cores, n, ne, k, w + k, w))
     else:
@@ -376,8 +383,8 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the env wins over /etc/nccl.conf)
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, world, args.gpus))
     if not torch.cuda.is_available():
@@ -578,10 +585,16 @@ def main():
     ap.add_argument("--k1-traffic-bytes-per-element", type=float, default=K1_TRAFFIC_BYTES_PER_ELEMENT)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: whatever a library prints to fd 1 meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
+    sys.stdout.flush()
 
 
 # Per-element figures of K1 <TL, SimoIso> from the ncu --set full capture profiles/r01d_k1_details.csv (284,160-element slab launch):
