@@ -1151,3 +1151,220 @@ done:
     free(s.work); free(R); free(Rres); free(R_last); free(u_lastdir); free(diffR); free(minv); free(upd); free(scratch); free(search);
     return err ? -err : status;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * <explicit_solid> on Hex8 -- ExplicitElementT::BatchedInternalForce (elements/explicit/ExplicitElementT.cpp:
+ * 649-993) with Hex8KernelT::ComputeIPData (kernels/Hex8KernelT.cpp:13-79: 2x2x2 Gauss, unit weights), ExplNeoHookeanT::
+ * ComputeStress3D (materials/ExplNeoHookeanT.cpp:79-111) or ExplJ2PlasticityT::ComputeStress3D (materials/ExplJ2PlasticityT.cpp:
+ * 87-310), CFL estimate (:404-478) and fixed mass scaling (:492-571, LHSDriver :576-618).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static double xs_ip_data(int ip, const double x[8][3], double dN[3][8])
+{
+    static const double g = 0.5773502691896258;
+    static const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+    const double xi = sx[ip] * g, eta = sy[ip] * g, mu = sz[ip] * g;
+    double dxi[8], deta[8], dmu[8];
+    for (int n = 0; n < 8; n++) {
+        dxi[n] = 0.125 * sx[n] * (1.0 + sy[n] * eta) * (1.0 + sz[n] * mu);
+        deta[n] = 0.125 * sy[n] * (1.0 + sx[n] * xi) * (1.0 + sz[n] * mu);
+        dmu[n] = 0.125 * sz[n] * (1.0 + sx[n] * xi) * (1.0 + sy[n] * eta);
+    }
+    double J[3][3] = {{0.0}};
+    for (int n = 0; n < 8; n++)
+        for (int r = 0; r < 3; r++) {
+            J[r][0] += x[n][r] * dxi[n];
+            J[r][1] += x[n][r] * deta[n];
+            J[r][2] += x[n][r] * dmu[n];
+        }
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    const double inv = 1.0 / det;
+    double Ji[3][3];
+    Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * inv;
+    Ji[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) * inv;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * inv;
+    Ji[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]) * inv;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * inv;
+    Ji[1][2] = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]) * inv;
+    Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * inv;
+    Ji[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]) * inv;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * inv;
+    for (int n = 0; n < 8; n++)
+        for (int c = 0; c < 3; c++) dN[c][n] = Ji[0][c] * dxi[n] + Ji[1][c] * deta[n] + Ji[2][c] * dmu[n];
+    return det;
+}
+
+/* F row-major F[3*i+j]; sig Voigt 11,22,33,23,13,12 */
+static void xs_neo_hookean(const orc_material_t* m, const double* F, double* sig)
+{
+    const double J = F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
+    const double b11 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2], b22 = F[3] * F[3] + F[4] * F[4] + F[5] * F[5],
+                 b33 = F[6] * F[6] + F[7] * F[7] + F[8] * F[8], b12 = F[0] * F[3] + F[1] * F[4] + F[2] * F[5],
+                 b13 = F[0] * F[6] + F[1] * F[7] + F[2] * F[8], b23 = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
+    const double muJ = m->mu / J, pres = m->kappa * (J - 1.0) / J;
+    sig[0] = muJ * (b11 - 1.0) + pres;
+    sig[1] = muJ * (b22 - 1.0) + pres;
+    sig[2] = muJ * (b33 - 1.0) + pres;
+    sig[3] = muJ * b23;
+    sig[4] = muJ * b13;
+    sig[5] = muJ * b12;
+}
+
+static void inv3_rowmajor(const double* A, double* Ai)
+{
+    const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    const double id = 1.0 / det;
+    Ai[0] = (A[4] * A[8] - A[5] * A[7]) * id;
+    Ai[1] = -(A[1] * A[8] - A[2] * A[7]) * id;
+    Ai[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    Ai[3] = -(A[3] * A[8] - A[5] * A[6]) * id;
+    Ai[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+    Ai[5] = -(A[0] * A[5] - A[2] * A[3]) * id;
+    Ai[6] = (A[3] * A[7] - A[4] * A[6]) * id;
+    Ai[7] = -(A[0] * A[7] - A[1] * A[6]) * id;
+    Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+static void mul3_rowmajor(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+/* Hughes-Winget J2 with linear isotropic hardening; h[16] = F_n (9), sigma_n (6), eps_p; updated in place on every call */
+static void xs_j2(const orc_material_t* m, const double* F, double* h, double* sig)
+{
+    const double mu = m->mu, lam = m->kappa - 2.0 * m->mu / 3.0, sigY0 = m->hard[0], H = m->hard[1];
+    double Fi[9], f[9];
+    inv3_rowmajor(h, Fi);
+    mul3_rowmajor(F, Fi, f);
+    const double de11 = f[0] - 1.0, de22 = f[4] - 1.0, de33 = f[8] - 1.0, de23 = 0.5 * (f[5] + f[7]), de13 = 0.5 * (f[2] + f[6]),
+                 de12 = 0.5 * (f[1] + f[3]);
+    const double w23 = 0.25 * (f[5] - f[7]), w13 = 0.25 * (f[2] - f[6]), w12 = 0.25 * (f[1] - f[3]);
+    const double B[9] = {1.0, w12, -w13, -w12, 1.0, w23, w13, -w23, 1.0}, A[9] = {1.0, -w12, w13, w12, 1.0, -w23, -w13, w23, 1.0};
+    double Binv[9], Q[9];
+    inv3_rowmajor(B, Binv);
+    mul3_rowmajor(Binv, A, Q);
+    const double sn11 = h[9], sn22 = h[10], sn33 = h[11], sn23 = h[12], sn13 = h[13], sn12 = h[14];
+    const double T11 = Q[0] * sn11 + Q[1] * sn12 + Q[2] * sn13, T12 = Q[0] * sn12 + Q[1] * sn22 + Q[2] * sn23,
+                 T13 = Q[0] * sn13 + Q[1] * sn23 + Q[2] * sn33, T21 = Q[3] * sn11 + Q[4] * sn12 + Q[5] * sn13,
+                 T22 = Q[3] * sn12 + Q[4] * sn22 + Q[5] * sn23, T23 = Q[3] * sn13 + Q[4] * sn23 + Q[5] * sn33,
+                 T31 = Q[6] * sn11 + Q[7] * sn12 + Q[8] * sn13, T32 = Q[6] * sn12 + Q[7] * sn22 + Q[8] * sn23,
+                 T33 = Q[6] * sn13 + Q[7] * sn23 + Q[8] * sn33;
+    const double sr11 = T11 * Q[0] + T12 * Q[1] + T13 * Q[2], sr22 = T21 * Q[3] + T22 * Q[4] + T23 * Q[5],
+                 sr33 = T31 * Q[6] + T32 * Q[7] + T33 * Q[8], sr23 = T21 * Q[6] + T22 * Q[7] + T23 * Q[8],
+                 sr13 = T11 * Q[6] + T12 * Q[7] + T13 * Q[8], sr12 = T11 * Q[3] + T12 * Q[4] + T13 * Q[5];
+    const double lamTr = lam * (de11 + de22 + de33);
+    const double st11 = sr11 + lamTr + 2.0 * mu * de11, st22 = sr22 + lamTr + 2.0 * mu * de22, st33 = sr33 + lamTr + 2.0 * mu * de33,
+                 st23 = sr23 + 2.0 * mu * de23, st13 = sr13 + 2.0 * mu * de13, st12 = sr12 + 2.0 * mu * de12;
+    const double p = (st11 + st22 + st33) / 3.0;
+    const double s11 = st11 - p, s22 = st22 - p, s33 = st33 - p;
+    const double eps_p = h[15], sig_Y = sigY0 + H * eps_p;
+    const double s2 = s11 * s11 + s22 * s22 + s33 * s33 + 2.0 * (st23 * st23 + st13 * st13 + st12 * st12);
+    const double q = sqrt(1.5 * s2), phi = q - sig_Y;
+    double new_eps_p = eps_p;
+    if (phi > 0.0) { /* radial return */
+        const double dlam = phi / (3.0 * mu + H);
+        const double factor = 1.0 - 3.0 * mu * dlam / q;
+        sig[0] = s11 * factor + p;
+        sig[1] = s22 * factor + p;
+        sig[2] = s33 * factor + p;
+        sig[3] = st23 * factor;
+        sig[4] = st13 * factor;
+        sig[5] = st12 * factor;
+        new_eps_p = eps_p + dlam;
+    } else {
+        sig[0] = s11 + p;
+        sig[1] = s22 + p;
+        sig[2] = s33 + p;
+        sig[3] = st23;
+        sig[4] = st13;
+        sig[5] = st12;
+    }
+    for (int k = 0; k < 9; k++) h[k] = F[k];
+    for (int k = 0; k < 6; k++) h[9 + k] = sig[k];
+    h[15] = new_eps_p;
+}
+
+void orc_explicit_solid_init_history(int64_t ne, double* hist)
+{
+    memset(hist, 0, sizeof(double) * 128 * ne); /* ExplJ2PlasticityT::InitializeHistory: F_n = I */
+    for (int64_t k = 0; k < 8 * ne; k++) hist[16 * k + 0] = hist[16 * k + 4] = hist[16 * k + 8] = 1.0;
+}
+
+int orc_explicit_solid_force(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, const double* u,
+                             double* hist /*[ne][8][16], EXPL_J2 only*/, double* f /*[nn][3] accumulated: +B^T sigma*/)
+{
+    for (int64_t e = 0; e < ne; e++) {
+        const int32_t* c = conn + 8 * e;
+        double xr[8][3], xc[8][3], fe[8][3];
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) {
+                xr[a][i] = X[3 * (int64_t)c[a] + i];
+                xc[a][i] = xr[a][i] + u[3 * (int64_t)c[a] + i]; /* ElementSupportT::CurrentCoordinates */
+                fe[a][i] = 0.0;
+            }
+        for (int ip = 0; ip < 8; ip++) {
+            double dNX[3][8], dNx[3][8], F[9] = {0.0}, sig[6];
+            xs_ip_data(ip, xr, dNX);
+            const double det = xs_ip_data(ip, xc, dNx);
+            for (int n = 0; n < 8; n++)
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) F[3 * i + j] += xc[n][i] * dNX[j][n];
+            if (m->kind == ORC_EXPL_J2) xs_j2(m, F, hist + 16 * (8 * e + ip), sig);
+            else xs_neo_hookean(m, F, sig);
+            for (int n = 0; n < 8; n++) {
+                fe[n][0] += (dNx[0][n] * sig[0] + dNx[1][n] * sig[5] + dNx[2][n] * sig[4]) * det;
+                fe[n][1] += (dNx[0][n] * sig[5] + dNx[1][n] * sig[1] + dNx[2][n] * sig[3]) * det;
+                fe[n][2] += (dNx[0][n] * sig[4] + dNx[1][n] * sig[3] + dNx[2][n] * sig[2]) * det;
+            }
+        }
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) f[3 * (int64_t)c[a] + i] += fe[a][i];
+    }
+    return ORC_OK;
+}
+
+/* characteristic length of ExplicitElementT::ComputeStableTimeStep / ApplyMassScaling: cbrt of the three-diagonal volume estimate */
+static double xs_char_length(const int32_t* c, const double* X)
+{
+    double d[3][3];
+    static const int pa[3] = {6, 7, 5}, pb[3] = {0, 1, 3};
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < 3; i++) d[k][i] = X[3 * (int64_t)c[pa[k]] + i] - X[3 * (int64_t)c[pb[k]] + i];
+    const double vol = fabs(d[0][0] * (d[1][1] * d[2][2] - d[1][2] * d[2][1]) - d[0][1] * (d[1][0] * d[2][2] - d[1][2] * d[2][0]) +
+                            d[0][2] * (d[1][0] * d[2][1] - d[1][1] * d[2][0])) / 6.0;
+    return cbrt(vol);
+}
+double orc_explicit_solid_stable_dt(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X)
+{
+    const double c = sqrt((m->kappa + 4.0 * m->mu / 3.0) / m->density);
+    double dt_min = 1.0e30;
+    for (int64_t e = 0; e < ne; e++) {
+        const double dt = xs_char_length(conn + 8 * e, X) / c;
+        if (dt < dt_min) dt_min = dt;
+    }
+    return dt_min;
+}
+void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, double target_dt,
+                                   double scale_factor, double* scale)
+{
+    const double c = sqrt((m->kappa + 4.0 * m->mu / 3.0) / m->density), target = target_dt * scale_factor;
+    for (int64_t e = 0; e < ne; e++) {
+        const double dt = xs_char_length(conn + 8 * e, X) / c;
+        const double alpha = target / dt;
+        scale[e] = dt < target ? alpha * alpha : 1.0;
+    }
+}
+/* ExplicitElementT::LHSDriver (:576-618): FormMass with density * fMassScale[e] */
+int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass)
+{
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], me[8];
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        int err = orc_element_lumped_mass(density * (scale ? scale[e] : 1.0), Xe, me);
+        if (err) return err;
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) mass[3 * (int64_t)c[a] + i] += me[a];
+    }
+    return ORC_OK;
+}

@@ -25,7 +25,8 @@ extern "C" {
 
 enum { ORC_SMALL_STRAIN = 0, ORC_TOTAL_LAGRANGIAN = 1, ORC_UPDATED_LAGRANGIAN = 2,
        ORC_SMALL_STRAIN_BBAR = 3 /* SmallStrainT with strain_displacement="B-bar" (kMeanDilBbar, SmallStrainT.cpp:337-374) */ };
-enum { ORC_SSKSTV = 0, ORC_FDKSTV = 1, ORC_SIMO_ISO = 2, ORC_J2_SIMO = 3 };
+enum { ORC_SSKSTV = 0, ORC_FDKSTV = 1, ORC_SIMO_ISO = 2, ORC_J2_SIMO = 3,
+       ORC_EXPL_NEO = 4, ORC_EXPL_J2 = 5 /* <explicit_solid> materials: ExplNeoHookeanT, ExplJ2PlasticityT (hard[0] = sigma_Y, hard[1] = H) */ };
 enum { ORC_OK = 0, ORC_BAD_JACOBIAN = 1, ORC_J2_LOCAL_FAIL = 2 };
 enum { ORC_J2_NOTINIT = -1, ORC_J2_PLASTIC = 0, ORC_J2_ELASTIC = 1 }; /* J2SimoC0HardeningT.h:33-36 */
 enum { ORC_HARD_LINEAR = 0, ORC_HARD_LINEAR_EXP = 1 };
@@ -108,6 +109,17 @@ int orc_pcg_jacobi(int64_t n, const int64_t* rowptr, const int32_t* colind, cons
 /* a19: central difference.  bc code per dof: 0 free, 1 fixed (kFix), 2 prescribed displacement (kDsp, value in bcval) */
 void orc_cd_predictor(int64_t ndof, double dt, double* d, double* v, double* a, const uint8_t* bc, const double* bcval);
 void orc_cd_corrector(int64_t ndof, double dt, double* v, double* a, const double* R, const double* mass, const uint8_t* bc);
+
+/* <explicit_solid> on Hex8 (ExplicitElementT::BatchedInternalForce, ExplicitElementT.cpp:649-993; Hex8KernelT;
+ * ExplNeoHookeanT / ExplJ2PlasticityT; CFL estimate :404-478; fixed mass scaling :492-571 and LHSDriver :576-618).
+ * hist[ne][8][16] (ExplJ2PlasticityT.h:8-11: F_n row-major, sigma_n Voigt, eps_p) is updated on EVERY force evaluation. */
+void orc_explicit_solid_init_history(int64_t ne, double* hist);
+int orc_explicit_solid_force(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, const double* u, double* hist,
+                             double* f /*[nn][3] accumulated*/);
+double orc_explicit_solid_stable_dt(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X);
+void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, double target_dt,
+                                   double scale_factor, double* scale /*[ne]*/);
+int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass);
 
 /* a21: nonlinear preconditioned CG with secant line search, PCGSolver_LS (solvers/PCGSolver_LS.cpp:107-371) inside
  * NLSolver::Solve / ExitIteration (solvers/NLSolver.cpp:57-263, 675-756), preconditioner = DiagonalMatrixT kDiagOnly

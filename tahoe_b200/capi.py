@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libtahoe_b200.so")
 
 SMALL_STRAIN, TOTAL_LAGRANGIAN, UPDATED_LAGRANGIAN, SMALL_STRAIN_BBAR = 0, 1, 2, 3
 SSKSTV, FDKSTV, SIMO_ISO, J2_SIMO = 0, 1, 2, 3
-FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2, "small_strain_B-bar": 3}
+FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2, "small_strain_B-bar": 3,
+           "explicit_solid": 2}  # ExplicitElementT derives from UpdatedLagrangianT
 
 
 def form_of(element):
@@ -22,7 +23,8 @@ def form_of(element):
     if element["type"] == "small_strain" and element.get("strain_displacement", "standard") == "B-bar":
         return FORM_OF["small_strain_B-bar"]
     return FORM_OF[element["type"]]
-KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3}
+KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3,
+           "explicit_neo_hookean": 4, "explicit_J2": 5}  # 4, 5: <explicit_solid> materials (ExplNeoHookeanT, ExplJ2PlasticityT)
 STATUS = {0: "ok", 1: "bad_jacobian", 2: "j2_local", 3: "cuda", 4: "argument", 5: "size", 6: "pcg_breakdown", 7: "comm"}
 J2_BLOCK = 5 * 48 + 64  # doubles per element in the reference's ElementCardT layout
 

@@ -109,6 +109,7 @@ def synthetic_case(name, n, desc, flags, jitter=0.1):
 
 
 RAMP = [(0.0, 0.0), (1.0, 1.0)]
+RAMP_FAST = [(0.0, 0.0), (0.4, 1.0), (10.0, 1.0)]
 CLAMP_X0 = [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)]
 NEWTON = {"type": "nonlinear_solver", "abs_tolerance": "1.0e-12", "rel_tolerance": "1.0e-12",
           "divergence_tolerance": "1.0e+03", "max_iterations": "25", "matrix": "SPOOLES_matrix"}
@@ -211,6 +212,32 @@ def main():
                                        "element": {"type": "updated_lagrangian", "mass_type": "lumped_mass"},
                                        "material": fdkstv, "solver": EXPLICIT},
          ["--every", "10", "--fint"]),
+        # explicit_solid (ExplicitElementT: batched UL force, ExplNeoHookeanT / ExplJ2PlasticityT, mass scaling)
+        ("syn_xs_neo_explicit", 4, {"time": {"num_steps": 40, "time_step": 0.5 * 0.25 / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0),
+                                             "schedules": [[(0.0, 1.0)]]},
+                                    "integrator": "central_difference", "kbc": CLAMP_X0,
+                                    "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02},
+                                            {"nodeset": 2, "dof": 3, "schedule": 1, "value": -0.01}],
+                                    "element": {"type": "explicit_solid", "mass_type": "lumped_mass"},
+                                    "material": {"type": "explicit_neo_hookean", "density": 1.0, "kappa": 1000.0, "mu": 5.0},
+                                    "solver": EXPLICIT}, ["--every", "10", "--fint"]),
+        ("syn_xs_j2_explicit", 4, {"time": {"num_steps": 400, "time_step": 0.4 * 0.25 / np.sqrt(1000.0 + 4.0 * 50.0 / 3.0),
+                                            "schedules": [RAMP_FAST]},
+                                   "integrator": "central_difference",
+                                   "kbc": CLAMP_X0 + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.08}],
+                                   "fbc": [],
+                                   "element": {"type": "explicit_solid", "mass_type": "lumped_mass"},
+                                   "material": {"type": "explicit_J2", "density": 1.0, "kappa": 1000.0, "mu": 50.0, "sigma_Y": 2.0,
+                                                "hardening_modulus": 100.0},
+                                   "solver": EXPLICIT}, ["--every", "100", "--fint"]),
+        ("syn_xs_neo_massscaled_explicit", 4, {"time": {"num_steps": 40, "time_step": 0.5 * 0.25 / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0),
+                                                        "schedules": [[(0.0, 1.0)]]},
+                                               "integrator": "central_difference", "kbc": CLAMP_X0,
+                                               "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
+                                               "element": {"type": "explicit_solid", "mass_type": "lumped_mass",
+                                                           "mass_scaling": {"type": "fixed", "target_dt": "0.0077", "scale_factor": "0.9"}},
+                                               "material": {"type": "explicit_neo_hookean", "density": 1.0, "kappa": 1000.0, "mu": 5.0},
+                                               "solver": EXPLICIT}, ["--every", "10", "--fint"]),
     ]
     for name, n, desc, flags in syn:
         if want(name):

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
 SMALL_STRAIN, TOTAL_LAGRANGIAN, UPDATED_LAGRANGIAN = 0, 1, 2
 SSKSTV, FDKSTV, SIMO_ISO, J2_SIMO = 0, 1, 2, 3
-FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2, "small_strain_B-bar": 3}
+FORM_OF = {"small_strain": 0, "total_lagrangian": 1, "updated_lagrangian": 2, "small_strain_B-bar": 3,
+           "explicit_solid": 2}  # ExplicitElementT derives from UpdatedLagrangianT
 
 
 def form_of(element):
@@ -19,7 +20,8 @@ def form_of(element):
     if element["type"] == "small_strain" and element.get("strain_displacement", "standard") == "B-bar":
         return FORM_OF["small_strain_B-bar"]
     return FORM_OF[element["type"]]
-KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3}
+KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotropic": 2, "Simo_J2": 3,
+           "explicit_neo_hookean": 4, "explicit_J2": 5}  # 4, 5: <explicit_solid> materials (ExplNeoHookeanT, ExplJ2PlasticityT)
 
 
 class Material(C.Structure):
@@ -67,6 +69,8 @@ def material(desc_mat):
     else:  # IsotropicT::Set_mu_kappa
         m.kind, m.mu, m.kappa, m.density = kind, desc_mat["mu"], desc_mat["kappa"], desc_mat["density"]
         m.lam = m.kappa - 2.0 * m.mu / 3.0
+    if desc_mat["type"] == "explicit_J2":  # ExplJ2PlasticityT: hard[0] = sigma_Y, hard[1] = H
+        m.hard[0], m.hard[1] = desc_mat["sigma_Y"], desc_mat["hardening_modulus"]
     h = desc_mat.get("hardening")
     if h:
         if h["type"] == "linear_function":
@@ -215,3 +219,38 @@ def nlpcg_solve(form, mat, conn, X, u, eqnos, neq, fext, prm, u_last=None, j2=No
                                _p(u_last), _p(j2), _p(alloc), _p(np.ascontiguousarray(eqnos, np.int32)), C.c_int64(neq),
                                _p(np.ascontiguousarray(fext, np.float64)), C.byref(prm), C.byref(it), C.byref(err), C.byref(err0))
     return st, it.value, err.value, err0.value
+
+
+def explicit_solid_force(mat, conn, X, u, hist=None):
+    """+B^T sigma of <explicit_solid>; hist [ne][8][16] is updated in place (every evaluation, as the reference does)"""
+    conn = np.ascontiguousarray(conn, np.int32)
+    f = np.zeros_like(X)
+    err = lib().orc_explicit_solid_force(C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(np.ascontiguousarray(u)), _p(hist), _p(f))
+    return err, f
+
+
+def explicit_solid_history(ne):
+    h = np.zeros((ne, 8, 16))
+    lib().orc_explicit_solid_init_history(C.c_int64(ne), _p(h))
+    return h
+
+
+def explicit_solid_stable_dt(mat, conn, X):
+    conn = np.ascontiguousarray(conn, np.int32)
+    lib().orc_explicit_solid_stable_dt.restype = C.c_double
+    return lib().orc_explicit_solid_stable_dt(C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), _p(X))
+
+
+def explicit_solid_mass_scale(mat, conn, X, target_dt, scale_factor):
+    conn = np.ascontiguousarray(conn, np.int32)
+    s = np.zeros(conn.shape[0])
+    lib().orc_explicit_solid_mass_scale(C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), _p(X), C.c_double(target_dt), C.c_double(scale_factor), _p(s))
+    return s
+
+
+def lumped_mass_scaled(density, conn, X, scale):
+    conn = np.ascontiguousarray(conn, np.int32)
+    m = np.zeros_like(X)
+    err = lib().orc_lumped_mass_scaled(C.c_double(density), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(scale), _p(m))
+    assert err == 0
+    return m

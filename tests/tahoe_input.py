@@ -149,8 +149,8 @@ def read_geom(path):
 # ----------------------------------------------------------------------------
 # XML parameter tree (hot-path subset)
 # ----------------------------------------------------------------------------
-ELEMENT_TAGS = ("small_strain", "total_lagrangian", "updated_lagrangian")
-MATERIAL_TAGS = ("small_strain_StVenant", "large_strain_StVenant", "Simo_isotropic", "Simo_J2")
+ELEMENT_TAGS = ("small_strain", "total_lagrangian", "updated_lagrangian", "explicit_solid")
+MATERIAL_TAGS = ("small_strain_StVenant", "large_strain_StVenant", "Simo_isotropic", "Simo_J2", "RG_split_general")
 SOLVER_TAGS = ("nonlinear_solver", "linear_solver", "PCG_solver")
 
 
@@ -195,6 +195,16 @@ def parse_xml(path):
     le = mat.find("linear_exponential")
     if le is not None:
         md["hardening"] = {"type": "linear_exponential", **{k: float(le.get(k)) for k in "abcd"}}
+    if mat.tag == "RG_split_general":  # explicit_solid: ExplicitElementT scans the sub-tree for mu / kappa (ExplicitElementT.cpp:176-200)
+        nh = mat.find("rg_eq_potential").find("neo-hookean")
+        md = {"type": "explicit_neo_hookean", "density": float(mat.get("density", 1.0)), "kappa": float(nh.get("kappa")), "mu": float(nh.get("mu"))}
+        j2 = el.find("j2_plasticity")
+        if j2 is not None:
+            md["type"] = "explicit_J2"
+            md["sigma_Y"], md["hardening_modulus"] = float(j2.get("sigma_Y")), float(j2.get("hardening"))
+        ms = el.find("mass_scaling")
+        if ms is not None:
+            d["element"]["mass_scaling"] = {k: ms.get(k) for k in ("type", "target_dt", "scale_factor", "update_interval") if ms.get(k)}
     d["material"] = md
     for tag in SOLVER_TAGS:
         s = root.find(tag)
@@ -236,15 +246,29 @@ def write_xml(path, d):
     blk = "small_strain_element_block" if small else "large_strain_element_block"
     mlist = "small_strain_material_3D" if small else "large_strain_material_3D"
     L.append('      <%s><block_ID_list><String value="1"/></block_ID_list>\n        <%s>' % (blk, mlist))
-    L.append('          <%s density="%.17g">' % (m["type"], m["density"]))
-    if "E" in m:
+    explicit = m["type"] in ("explicit_neo_hookean", "explicit_J2")
+    if explicit:
+        L.append('          <RG_split_general density="%.17g"><rg_eq_potential><neo-hookean kappa="%.17g" mu="%.17g"/></rg_eq_potential>'
+                 % (m["density"], m["kappa"], m["mu"]))
+        L.append("          </RG_split_general>\n        </%s>\n      </%s>" % (mlist, blk))
+        if m["type"] == "explicit_J2":
+            L.append('      <j2_plasticity sigma_Y="%.17g" hardening="%.17g"/>' % (m["sigma_Y"], m["hardening_modulus"]))
+        if e.get("mass_scaling"):
+            L.append("      <mass_scaling %s/>" % " ".join('%s="%s"' % kv for kv in e["mass_scaling"].items()))
+        L.append("    </%s>\n  </element_list>" % e.get("tag", e["type"]))
+    else:
+        L.append('          <%s density="%.17g">' % (m["type"], m["density"]))
+    if explicit:
+        pass
+    elif "E" in m:
         L.append('            <E_and_nu Poisson_ratio="%.17g" Young_modulus="%.17g"/>' % (m["nu"], m["E"]))
     else:
         L.append('            <bulk_and_shear bulk_modulus="%.17g" shear_modulus="%.17g"/>' % (m["kappa"], m["mu"]))
     h = m.get("hardening")
     if h:
         L.append("            <%s %s/>" % (h["type"], " ".join('%s="%.17g"' % (k, v) for k, v in h.items() if k != "type")))
-    L.append("          </%s>\n        </%s>\n      </%s>\n    </%s>\n  </element_list>" % (m["type"], mlist, blk, e.get("tag", e["type"])))
+    if not explicit:
+        L.append("          </%s>\n        </%s>\n      </%s>\n    </%s>\n  </element_list>" % (m["type"], mlist, blk, e.get("tag", e["type"])))
     s = d["solver"]
     attrs = " ".join('%s="%s"' % (k, v) for k, v in s.items() if k not in ("type", "matrix", "matrix_attrs"))
     L.append("  <%s %s><%s %s/></%s>\n</tahoe>" % (s["type"], attrs, s["matrix"], s.get("matrix_attrs", ""), s["type"]))

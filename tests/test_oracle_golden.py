@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from cases import PCG, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import PCG, XS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 TOL = 1e-10  # north_star: forces / displacements agree to 1e-10 relative
 
@@ -30,7 +30,7 @@ def test_equation_numbers_bit_exact(oracle, name):
         assert np.array_equal(eq, ref)
 
 
-@pytest.mark.parametrize("name", [n for n in ALL if "j2" not in n and "09" not in n])
+@pytest.mark.parametrize("name", [n for n in ALL if "j2" not in n and "09" not in n and "_xs_" not in n])
 def test_internal_force_matches_reference(oracle, name):
     c, form, mat = _setup(oracle, name)
     d = c.ref("d_%d" % c.dump_steps[-1])
@@ -96,6 +96,40 @@ def test_explicit_central_difference_matches_reference(oracle, name):
             assert relerr(d, c.ref("d_%d" % k)) < TOL
             assert relerr(v, c.ref("v_%d" % k)) < TOL
             assert relerr(a, c.ref("a_%d" % k)) < TOL
+
+
+@pytest.mark.parametrize("name", XS)
+def test_explicit_solid_matches_reference(oracle, name):
+    """<explicit_solid> (ExplicitElementT batched force + ExplNeoHookeanT / ExplJ2PlasticityT + fixed mass scaling)
+    restated in the oracle against the reference's own runs: d, v, a over the whole central-difference run"""
+    c = Case(name)
+    mat = oracle.material(c.desc["material"])
+    isj2 = c.desc["material"]["type"] == "explicit_J2"
+    hist = oracle.explicit_solid_history(c.ne) if isj2 else None
+    ms = c.desc["element"].get("mass_scaling")
+    scale = None
+    if ms:
+        scale = oracle.explicit_solid_mass_scale(mat, c.conn, c.X, float(ms["target_dt"]), float(ms.get("scale_factor", 0.9)))
+        assert scale.max() > 1.05 and scale.min() == 1.0  # the fixture really scales some elements and leaves others alone
+    mass = oracle.lumped_mass_scaled(mat.density, c.conn, c.X, scale)
+    d, v = c.ref("d_0").copy(), c.ref("v_0").copy()
+    code, val, fext = c.bc(0.0)
+    err, f = oracle.explicit_solid_force(mat, c.conn, c.X, d, hist)
+    a = np.where(code == 0, (fext - f) / mass, 0.0)  # FEManagerT::InitialCondition
+    assert np.abs(a - c.ref("a_0")).max() < 1e-12 * max(np.abs(a).max(), 1.0)
+    for k in range(1, c.nsteps + 1):
+        code, val, fext = c.bc(k * c.dt)
+        oracle.cd_predictor(c.dt, d, v, a, code, val)
+        err, f = oracle.explicit_solid_force(mat, c.conn, c.X, d, hist)
+        assert err == 0
+        oracle.cd_corrector(c.dt, v, a, fext - f, mass, code)
+        if k in c.dump_steps:
+            assert relerr(d, c.ref("d_%d" % k)) < TOL
+            assert relerr(v, c.ref("v_%d" % k)) < TOL
+            assert relerr(a, c.ref("a_%d" % k)) < TOL
+    if isj2:
+        assert hist[:, :, 15].max() > 1e-3  # the run really yields (equivalent plastic strain)
+    assert 0.0 < oracle.explicit_solid_stable_dt(mat, c.conn, c.X) < 1.0
 
 
 def newton(oracle, c, form, mat, solve):
