@@ -43,7 +43,11 @@ typedef enum { TB2_SMALL_STRAIN = 0, TB2_TOTAL_LAGRANGIAN = 1, TB2_UPDATED_LAGRA
                                             SmallStrainT.cpp:337-374,404-421, SolidElementT::Set_B_bar SolidElementT.cpp:956-1044 */
              } tb2_formulation;
 /* materials: SSKStV (Hookean/KStV/SSKStV.cpp), FDKStV (FDKStV.cpp), SimoIso3D (Simo/SimoIso3D.cpp), J2Simo3D (plasticity_J2/J2Simo3D.cpp) */
-typedef enum { TB2_SSKSTV = 0, TB2_FDKSTV = 1, TB2_SIMO_ISO = 2, TB2_J2_SIMO = 3 } tb2_material_kind;
+typedef enum { TB2_SSKSTV = 0, TB2_FDKSTV = 1, TB2_SIMO_ISO = 2, TB2_J2_SIMO = 3,
+               /* the materials of <explicit_solid> (ExplicitElementT), valid with TB2_UPDATED_LAGRANGIAN:
+                  ExplNeoHookeanT (elements/explicit/materials/ExplNeoHookeanT.cpp:79-111) and ExplJ2PlasticityT
+                  (ExplJ2PlasticityT.cpp:87-310; hard[0] = sigma_Y, hard[1] = hardening modulus H) */
+               TB2_EXPL_NEO_HOOKEAN = 4, TB2_EXPL_J2 = 5 } tb2_material_kind;
 typedef enum { TB2_HARD_LINEAR = 0, TB2_HARD_LINEAR_EXP = 1 } tb2_hardening_kind;
 /* kinematic boundary condition codes per dof (KBC_CardT::CodeT subset used by nExplicitCD::ConsistentKBC, nExplicitCD.cpp:20-69) */
 typedef enum { TB2_BC_FREE = 0, TB2_BC_FIX = 1, TB2_BC_DSP = 2 } tb2_bc_code;
@@ -116,6 +120,17 @@ int tb2_group_status(tb2_group* group, int64_t* bad_element);
 /* ContinuumElementT::FormMass kLumpedMass (ContinuumElementT.cpp:767-842) summed to nodes: d_mass[nn][3] */
 int tb2_form_lumped_mass(tb2_group* group, double* d_mass);
 int tb2_form_lumped_mass_host(tb2_group* group, double* h_mass);
+/* <explicit_solid> extras.  ExplicitElementT::ComputeStableTimeStep (ExplicitElementT.cpp:404-478): min over
+ * the elements of h / c, h = cbrt of the three-diagonal volume estimate, c = sqrt((kappa + 4 mu / 3) / rho). */
+int tb2_group_stable_time_step(tb2_group* group, double* dt);
+/* ExplicitElementT::ApplyMassScaling, fixed type (:492-571): elements with h / c < target_dt * scale_factor get the mass factor
+ * (target / dt_elem)^2, applied to the density in the lumped-mass assembly (LHSDriver :576-618), i.e. by every later
+ * tb2_form_lumped_mass / tb2_explicit_create of this group.  h_scale[ne] (may be NULL) receives the factors. */
+int tb2_group_set_mass_scaling(tb2_group* group, double target_dt, double scale_factor, int64_t* num_scaled, double* max_factor,
+                               double* h_scale);
+/* ExplJ2PlasticityT history in the reference's layout [ip][16][element] (ExplicitElementT.h:75-79): h_hist[8][16][ne] */
+int tb2_group_get_explicit_history(tb2_group* group, double* h_hist);
+
 /* J2 history: SolidElementT::CloseStep -> J2Simo3D::UpdateHistory (J2SimoC0HardeningT.cpp:341-384), ResetStep -> ResetHistory (:387-407) */
 int tb2_group_close_step(tb2_group* group);
 int tb2_group_reset_step(tb2_group* group);

@@ -32,7 +32,7 @@ J2_BLOCK = 5 * 48 + 64  # doubles per element in the reference's ElementCardT la
 SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2_memcpy_h2d tb2_memcpy_d2h tb2_host_register
 tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
-tb2_form_lumped_mass_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
+tb2_form_lumped_mass_host tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
 tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
@@ -108,6 +108,8 @@ def material(desc_mat):
     else:
         m.mu, m.kappa = desc_mat["mu"], desc_mat["kappa"]
         m.lam = m.kappa - 2.0 * m.mu / 3.0
+    if desc_mat["type"] == "explicit_J2":  # ExplJ2PlasticityT: hard[0] = sigma_Y, hard[1] = H
+        m.hard[0], m.hard[1] = desc_mat["sigma_Y"], desc_mat["hardening_modulus"]
     h = desc_mat.get("hardening")
     if h:
         if h["type"] == "linear_function":
@@ -259,6 +261,24 @@ class Group(_Handle):
         m = np.zeros((self.mesh.nn, 3))
         _chk(lib().tb2_form_lumped_mass_host(self.h, _p(m)))
         return m
+
+    def stable_time_step(self):
+        """ExplicitElementT::ComputeStableTimeStep"""
+        dt = C.c_double(0.0)
+        _chk(lib().tb2_group_stable_time_step(self.h, C.byref(dt)))
+        return dt.value
+
+    def set_mass_scaling(self, target_dt, scale_factor=0.9):
+        """ExplicitElementT::ApplyMassScaling (fixed): returns (number of scaled elements, largest factor, factors[ne])"""
+        n, mx, sc = C.c_int64(0), C.c_double(0.0), np.zeros(self.mesh.ne)
+        _chk(lib().tb2_group_set_mass_scaling(self.h, C.c_double(target_dt), C.c_double(scale_factor), C.byref(n), C.byref(mx), _p(sc)))
+        return n.value, mx.value, sc
+
+    def explicit_history(self):
+        """ExplJ2PlasticityT history [ip][16][element]"""
+        h = np.zeros((8, 16, self.mesh.ne))
+        _chk(lib().tb2_group_get_explicit_history(self.h, _p(h)))
+        return h
 
     def close_step(self):
         _chk(lib().tb2_group_close_step(self.h))

@@ -15,6 +15,8 @@
 // each node's <= 8 contributions in ascending element order -- the order of the reference's serial assembly
 // (SolverT::AssembleRHS, SolverT.cpp:446-477) -- so there are no float atomics and reruns are bit-reproducible.
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "tb2_internal.h"
 
@@ -158,11 +160,34 @@ TB2_DEV void internal_force_element(const ElemArgs& p, const int64_t e, const in
                 mode_accumulate(A, s0, s1, s2, G);
                 continue;
             }
+            if (MAT == kExplNeo) {
+                // ExplNeoHookeanT folded into the force integrand like SimoIso3D above: sigma = (mu/J)(b - 1) + kappa (1 - 1/J) 1 and
+                // b cof(j) = det(j)/det0^2 j M0 give  G = w det(j) sigma j^-T = (mu/det0) (j M0) + (kappa (1 - 1/J) - mu/J) cof(j)
+                double M0[6], N[3][3];
+                sym_fft(J0a, M0);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    N[i][0] = j[i][0] * M0[0] + j[i][1] * M0[5] + j[i][2] * M0[4];
+                    N[i][1] = j[i][0] * M0[5] + j[i][1] * M0[1] + j[i][2] * M0[3];
+                    N[i][2] = j[i][0] * M0[4] + j[i][1] * M0[3] + j[i][2] * M0[2];
+                }
+                const double r = 1.0 / (det0 * detj); // one reciprocal: 1/det0 = det(j) r, 1/J = det0^2 r
+                const double rJ = det0 * det0 * r;
+                const double al = p.mat.mu * detj * r, q = p.mat.kappa * (1.0 - rJ) - p.mat.mu * rJ;
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
+                mode_accumulate(A, s0, s1, s2, G);
+                continue;
+            }
             mul3(j, J0a, F); // = det0 * F
             const double J = detj * rdet0;
             if (MAT != kSimoIso) scale3(F, rdet0);
             if (MAT == kFDKStV)
                 fdkstv_stress(p.mat, F, J, sig);
+            else if (MAT == kExplJ2)
+                expl_j2_stress(p.mat, p.hist.data + (int64_t)(ip * 16) * p.stride + e, p.stride, F, sig);
             else if (MAT == kJ2Simo) {
                 double Hl[3][3], Fl[3][3], c[6][6];
                 mode_gradient(cL, s0, s1, s2, Hl);
@@ -443,10 +468,11 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_geo(const Ele
 // K4: ContinuumElementT::FormMass, kLumpedMass branch (ContinuumElementT.cpp:767-842).  me[a] -> fe[a][stride]
 __global__ void __launch_bounds__(128) k_lumped_mass(int64_t ne, int64_t stride, const int* __restrict__ conn,
                                                     const double* __restrict__ X, double density, double* __restrict__ fe,
-                                                    unsigned long long* status)
+                                                    unsigned long long* status, const double* __restrict__ mass_scale = nullptr)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= ne) return;
+    if (mass_scale) density *= mass_scale[e]; // ExplicitElementT::LHSDriver: FormMass with density * fMassScale[e]
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(conn + a * stride + e);
@@ -508,6 +534,41 @@ __global__ void __launch_bounds__(256) k_node_gather(int64_t nn, const int* __re
     out[3 * n + 2] = f2;
 }
 
+// ExplicitElementT::ComputeStableTimeStep / ApplyMassScaling (ExplicitElementT.cpp:404-478, 492-571): per element dt = h / c with
+// h = cbrt(|d1 . (d2 x d3)| / 6) of the diagonals 0-6, 1-7, 3-5; scale = (target / dt)^2 where dt < target, else 1
+__global__ void __launch_bounds__(128) k_explicit_solid_dt(int64_t ne, int64_t stride, const int* __restrict__ conn, const double* __restrict__ X,
+                                                          double c, double target, double* __restrict__ dt_out, double* __restrict__ scale)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const int pa[3] = {6, 7, 5}, pb[3] = {0, 1, 3};
+    double d[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int64_t na = conn[pa[k] * stride + e], nb = conn[pb[k] * stride + e];
+#pragma unroll
+        for (int i = 0; i < 3; i++) d[k][i] = X[3 * na + i] - X[3 * nb + i];
+    }
+    const double vol = fabs(d[0][0] * (d[1][1] * d[2][2] - d[1][2] * d[2][1]) - d[0][1] * (d[1][0] * d[2][2] - d[1][2] * d[2][0]) +
+                            d[0][2] * (d[1][0] * d[2][1] - d[1][1] * d[2][0])) / 6.0;
+    const double dt = cbrt(vol) / c;
+    if (dt_out) dt_out[e] = dt;
+    if (scale) {
+        const double alpha = target / dt;
+        scale[e] = dt < target ? alpha * alpha : 1.0;
+    }
+}
+// ExplJ2PlasticityT::InitializeHistory: F_n = 1
+__global__ void k_expl_j2_init(int64_t ne, int64_t stride, double* __restrict__ hist)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t e = t % stride;
+    const int ip = (int)(t / stride);
+    if (ip >= 8 || e >= ne) return;
+    double* h = hist + (int64_t)(ip * 16) * stride + e;
+    h[0] = 1.0; h[4 * stride] = 1.0; h[8 * stride] = 1.0;
+}
+
 __global__ void k_j2_close_step(int64_t ne, J2Hist h, double mu)
 {
     // J2SimoC0HardeningT::Update (J2SimoC0HardeningT.cpp:341-384), allocated elements only; one thread per (e, ip)
@@ -548,6 +609,8 @@ static const int kDefaultMinBlocks = 3; // r01b: 168 regs, 3 CTAs/SM: K1 191 us 
 static force_kernel_t pick_force_kernel(int form, int mat, bool geo, bool bbar = false)
 {
     if (form == kSmallStrain && mat == kSSKStV && bbar) return k_internal_force<kSmallStrain, kSSKStVBbar, 2>;
+    if (mat == TB2_EXPL_NEO_HOOKEAN) return form == kSmallStrain ? nullptr : k_internal_force<kTotalLagrangian, kExplNeo, 3>;
+    if (mat == TB2_EXPL_J2) return form == kSmallStrain ? nullptr : k_internal_force<kTotalLagrangian, kExplJ2, 2>;
     // registers-per-thread cap experiment (TB2_K1_MINBLOCKS=2|3|4 resident CTAs of 128 threads per SM); default from the ncu study
     static int minb = 0;
     if (!minb) {
@@ -717,7 +780,7 @@ extern "C" {
 int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_group** out)
 {
     TB2_ARG(mesh && mat && out);
-    TB2_ARG(form >= 0 && form <= 3 && mat->kind >= 0 && mat->kind <= 3);
+    TB2_ARG(form >= 0 && form <= 3 && mat->kind >= 0 && mat->kind <= 5);
     const bool bbar = form == TB2_SMALL_STRAIN_BBAR;
     if (bbar) form = TB2_SMALL_STRAIN;
     if ((form == TB2_SMALL_STRAIN) != (mat->kind == TB2_SSKSTV)) {
@@ -737,6 +800,14 @@ int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_grou
     g->mc.hard_kind = mat->hard_kind;
     for (int i = 0; i < 4; i++) g->mc.hard[i] = mat->hard[i];
     cudaError_t e = g->status.alloc(2);
+    if (e == cudaSuccess && mat->kind == TB2_EXPL_J2) { // [ip][16][stride], F_n = 1
+        e = g->hist.alloc((size_t)16 * 8 * mesh->stride);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->hist.p, 0, g->hist.n * sizeof(double), mesh->stream);
+        if (e == cudaSuccess) {
+            k_expl_j2_init<<<(unsigned)((8 * mesh->stride + 255) / 256), 256, 0, mesh->stream>>>(mesh->ne, mesh->stride, g->hist.p);
+            e = cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess && mat->kind == TB2_J2_SIMO) {
         e = g->hist.alloc((size_t)kHNumDouble * 8 * mesh->stride);
         if (e == cudaSuccess) e = g->hist_flag.alloc(8 * mesh->stride);
@@ -822,6 +893,69 @@ int tb2_form_internal_force_host(tb2_group* g, const double* h_u, const double* 
     return tb2_group_status(g, nullptr);
 }
 
+// ---- <explicit_solid> extras ------------------------------------------------------------------------------
+static int explicit_solid_dt(tb2_group* g, double target, std::vector<double>* h_dt, bool want_scale)
+{
+    tb2_mesh* m = g->mesh;
+    const double c = sqrt((g->mat.kappa + 4.0 * g->mat.mu / 3.0) / g->mat.density); // ExplicitMaterialT::WaveSpeed
+    DevBuf<double> dt;
+    if (h_dt) TB2_CUDA(dt.alloc(m->ne));
+    if (want_scale && !g->mass_scale.p) TB2_CUDA(g->mass_scale.alloc(m->ne));
+    k_explicit_solid_dt<<<(unsigned)((m->ne + 127) / 128), 128, 0, m->stream>>>(m->ne, m->stride, m->conn.p, m->X.p, c, target, dt.p,
+                                                                               want_scale ? g->mass_scale.p : nullptr);
+    m->launches++;
+    TB2_CUDA(cudaGetLastError());
+    if (h_dt) {
+        h_dt->resize(m->ne);
+        TB2_CUDA(cudaMemcpyAsync(h_dt->data(), dt.p, m->ne * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    }
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
+
+int tb2_group_stable_time_step(tb2_group* g, double* dt)
+{
+    TB2_ARG(g && dt);
+    DeviceGuard dg(g->mesh->device);
+    std::vector<double> h;
+    TB2_CHECK(explicit_solid_dt(g, 0.0, &h, false));
+    double dt_min = 1.0e30; // the reference's start value
+    for (double v : h) dt_min = v < dt_min ? v : dt_min;
+    *dt = dt_min;
+    return TB2_OK;
+}
+
+int tb2_group_set_mass_scaling(tb2_group* g, double target_dt, double scale_factor, int64_t* num_scaled, double* max_factor, double* h_scale)
+{
+    TB2_ARG(g && target_dt > 0.0 && scale_factor > 0.0);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CHECK(explicit_solid_dt(g, target_dt * scale_factor, nullptr, true));
+    std::vector<double> sc(m->ne);
+    TB2_CUDA(cudaMemcpy(sc.data(), g->mass_scale.p, m->ne * sizeof(double), cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    double mx = 1.0;
+    for (double v : sc) {
+        n += v != 1.0;
+        mx = v > mx ? v : mx;
+    }
+    if (num_scaled) *num_scaled = n;
+    if (max_factor) *max_factor = mx;
+    if (h_scale) memcpy(h_scale, sc.data(), m->ne * sizeof(double));
+    return TB2_OK;
+}
+
+int tb2_group_get_explicit_history(tb2_group* g, double* h_hist)
+{
+    TB2_ARG(g && h_hist && g->mat.kind == TB2_EXPL_J2);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    TB2_CUDA(cudaMemcpy2D(h_hist, m->ne * sizeof(double), g->hist.p, m->stride * sizeof(double), m->ne * sizeof(double), 128,
+                          cudaMemcpyDeviceToHost));
+    return TB2_OK;
+}
+
 int tb2_form_lumped_mass(tb2_group* g, double* d_mass)
 {
     TB2_ARG(g && d_mass);
@@ -830,7 +964,7 @@ int tb2_form_lumped_mass(tb2_group* g, double* d_mass)
     const int T = 128;
     ProfScope ps(m, kProfOther);
     k_lumped_mass<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(m->ne, m->stride, m->conn.p, m->X.p, g->mat.density, m->fe.p,
-                                                                       g->status.p);
+                                                                       g->status.p, g->mass_scale.p);
     TB2_CUDA(cudaGetLastError());
     return launch_node_gather(m, d_mass, false);
 }

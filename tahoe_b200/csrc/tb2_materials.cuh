@@ -7,7 +7,8 @@
 namespace tb2 {
 
 enum { kSSKStV = 0, kFDKStV = 1, kSimoIso = 2, kJ2Simo = 3,
-       kSSKStVBbar = 4 /* kernel-template tag only: SSKStV under SmallStrainT's mean-dilatation B-bar */ };
+       kSSKStVBbar = 4, /* kernel-template tag only: SSKStV under SmallStrainT's mean-dilatation B-bar */
+       kExplNeo = 5, kExplJ2 = 6 /* <explicit_solid> materials (public kinds TB2_EXPL_NEO_HOOKEAN = 4, TB2_EXPL_J2 = 5) */ };
 enum { kSmallStrain = 0, kTotalLagrangian = 1, kUpdatedLagrangian = 2 };
 enum { kHardLinear = 0, kHardLinearExp = 1 };
 enum { kErrNone = 0, kErrBadJacobian = 1, kErrJ2Local = 2 };
@@ -60,6 +61,75 @@ TB2_DEV void hooke_moduli(const MatConst& m, double (&c)[6][6])
         c[i][i] = m.lambda + 2.0 * m.mu;
         c[i + 3][i + 3] = m.mu;
     }
+}
+
+// ---- <explicit_solid> materials ---------------------------------------------------------------------------
+// ExplNeoHookeanT::ComputeStress3D (elements/explicit/materials/ExplNeoHookeanT.cpp:79-111): sigma = (mu/J)(b - 1) + kappa (J - 1)/J 1
+TB2_DEV void expl_neo_stress(const MatConst& m, const double (&F)[3][3], double J, double (&sig)[6])
+{
+    double b[6];
+    sym_fft(F, b);
+    const double rJ = 1.0 / J, muJ = m.mu * rJ, pres = m.kappa * (J - 1.0) * rJ;
+    sig[0] = muJ * (b[0] - 1.0) + pres;
+    sig[1] = muJ * (b[1] - 1.0) + pres;
+    sig[2] = muJ * (b[2] - 1.0) + pres;
+    sig[3] = muJ * b[3];
+    sig[4] = muJ * b[4];
+    sig[5] = muJ * b[5];
+}
+// ExplJ2PlasticityT::ComputeStress3D (materials/ExplJ2PlasticityT.cpp:87-310): Hughes-Winget incrementally objective J2 with
+// linear isotropic hardening (hard[0] = sigma_Y, hard[1] = H).  h points at this (element, ip)'s 16 history values, pitch
+// `stride` doubles: F_n (row-major), sigma_n (Voigt), eps_p -- read and overwritten on EVERY evaluation, as the reference does.
+TB2_DEV void expl_j2_stress(const MatConst& m, double* __restrict__ h, int64_t stride, const double (&F)[3][3], double (&sig)[6])
+{
+    double Fn[3][3], Fa[3][3], f[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) Fn[i][k] = h[(int64_t)(3 * i + k) * stride];
+    const double rdet = 1.0 / adj3(Fn, Fa); // adj3 returns det and the adjugate: Fn^-1 = adj / det
+    mul3(F, Fa, f);
+    scale3(f, rdet); // f_rel = F F_n^-1
+    const double de11 = f[0][0] - 1.0, de22 = f[1][1] - 1.0, de33 = f[2][2] - 1.0, de23 = 0.5 * (f[1][2] + f[2][1]),
+                 de13 = 0.5 * (f[0][2] + f[2][0]), de12 = 0.5 * (f[0][1] + f[1][0]);
+    const double w23 = 0.25 * (f[1][2] - f[2][1]), w13 = 0.25 * (f[0][2] - f[2][0]), w12 = 0.25 * (f[0][1] - f[1][0]);
+    // Cayley transform Q = (1 - W)^-1 (1 + W)
+    const double B[3][3] = {{1.0, w12, -w13}, {-w12, 1.0, w23}, {w13, -w23, 1.0}}, A[3][3] = {{1.0, -w12, w13}, {w12, 1.0, -w23}, {-w13, w23, 1.0}};
+    double Ba[3][3], Q[3][3];
+    const double rB = 1.0 / adj3(B, Ba);
+    mul3(Ba, A, Q);
+    scale3(Q, rB);
+    double sn[6], sr[6];
+#pragma unroll
+    for (int I = 0; I < 6; I++) sn[I] = h[(int64_t)(9 + I) * stride];
+    sym_qsqt(Q, sn, sr); // Q sigma_n Q^T
+    const double lam = m.kappa - 2.0 * m.mu * (1.0 / 3.0), lamTr = lam * (de11 + de22 + de33), mu2 = 2.0 * m.mu;
+    const double st11 = sr[0] + lamTr + mu2 * de11, st22 = sr[1] + lamTr + mu2 * de22, st33 = sr[2] + lamTr + mu2 * de33;
+    const double st23 = sr[3] + mu2 * de23, st13 = sr[4] + mu2 * de13, st12 = sr[5] + mu2 * de12;
+    const double pm = (st11 + st22 + st33) * (1.0 / 3.0);
+    const double s11 = st11 - pm, s22 = st22 - pm, s33 = st33 - pm;
+    const double eps_p = h[(int64_t)15 * stride];
+    const double q = sqrt(1.5 * (s11 * s11 + s22 * s22 + s33 * s33 + 2.0 * (st23 * st23 + st13 * st13 + st12 * st12)));
+    const double phi = q - (m.hard[0] + m.hard[1] * eps_p);
+    double factor = 1.0, new_eps = eps_p;
+    if (phi > 0.0) { // radial return
+        const double dlam = phi / (3.0 * m.mu + m.hard[1]);
+        factor = 1.0 - 3.0 * m.mu * dlam / q;
+        new_eps = eps_p + dlam;
+    }
+    sig[0] = s11 * factor + pm;
+    sig[1] = s22 * factor + pm;
+    sig[2] = s33 * factor + pm;
+    sig[3] = st23 * factor;
+    sig[4] = st13 * factor;
+    sig[5] = st12 * factor;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) h[(int64_t)(3 * i + k) * stride] = F[i][k];
+#pragma unroll
+    for (int I = 0; I < 6; I++) h[(int64_t)(9 + I) * stride] = sig[I];
+    h[(int64_t)15 * stride] = new_eps;
 }
 
 // ---- FDKStV: FDHookeanMatT::s_ij (FDHookeanMatT.cpp:39-55): E = (F^T F - 1)/2, S = C:E, sigma = F S F^T / J

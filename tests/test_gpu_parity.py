@@ -8,7 +8,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import tahoe_input as ti
-from cases import PCG, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import PCG, XS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -128,6 +128,60 @@ def test_explicit_central_difference_matches_reference(tb2, name):
         assert relerr(d, c.ref("d_%d" % k)) < TOL
         assert relerr(v, c.ref("v_%d" % k)) < TOL
         assert relerr(a, c.ref("a_%d" % k)) < TOL
+
+
+@pytest.mark.parametrize("name", XS)
+def test_explicit_solid_matches_reference_and_oracle(tb2, oracle, name):
+    """<explicit_solid> on the device (UL sweep with the ExplNeoHookeanT / ExplJ2PlasticityT materials, fixed mass
+    scaling, CFL estimate) against the reference's own explicit_solid runs: d, v, a over the whole run; J2 history and mass
+    factors against the oracle"""
+    c = Case(name)
+    mesh, grp, mat = _group(tb2, c)
+    omat = oracle.material(c.desc["material"])
+    assert abs(grp.stable_time_step() / oracle.explicit_solid_stable_dt(omat, c.conn, c.X) - 1.0) < 1e-13
+    ms = c.desc["element"].get("mass_scaling")
+    if ms:
+        n, mx, sc = grp.set_mass_scaling(float(ms["target_dt"]), float(ms.get("scale_factor", 0.9)))
+        ref_sc = oracle.explicit_solid_mass_scale(omat, c.conn, c.X, float(ms["target_dt"]), float(ms.get("scale_factor", 0.9)))
+        assert 0 < n < c.ne and n == (ref_sc != 1.0).sum() and relerr(sc, ref_sc) < 1e-13
+    ex = tb2.Explicit(grp)
+    code, val, fext = c.bc(0.0)
+    ex.set_state(c.ref("d_0"), c.ref("v_0"), np.zeros_like(c.X))
+    ex.set_bc(code, val, fext)
+    ex.initial_condition()
+    _, _, a0 = ex.get_state()
+    # an unloaded start gives a_0 = rounding noise / nodal mass (1e-12 here) on both sides: absolute bound
+    assert np.abs(a0 - c.ref("a_0")).max() < 1e-10 * max(np.abs(a0).max(), 1.0)
+    done = 0
+    for k in c.dump_steps:
+        if k == 0:
+            continue
+        for s in range(done + 1, k + 1):
+            code, val, fext = c.bc(s * c.dt)
+            ex.set_bc(code, val, fext)
+            ex.run(c.dt, 1)
+        done = k
+        d, v, a = ex.get_state()
+        assert relerr(d, c.ref("d_%d" % k)) < TOL
+        assert relerr(v, c.ref("v_%d" % k)) < TOL
+        assert relerr(a, c.ref("a_%d" % k)) < TOL
+    if c.desc["material"]["type"] == "explicit_J2":
+        # the same run in the oracle: equivalent plastic strain and stored stresses agree point by point
+        hist = oracle.explicit_solid_history(c.ne)
+        mass = oracle.lumped_mass_scaled(omat.density, c.conn, c.X, None)
+        d0, v0 = c.ref("d_0").copy(), c.ref("v_0").copy()
+        code, val, fext = c.bc(0.0)
+        _, f = oracle.explicit_solid_force(omat, c.conn, c.X, d0, hist)
+        a0 = np.where(code == 0, (fext - f) / mass, 0.0)
+        for s in range(1, c.nsteps + 1):
+            code, val, fext = c.bc(s * c.dt)
+            oracle.cd_predictor(c.dt, d0, v0, a0, code, val)
+            _, f = oracle.explicit_solid_force(omat, c.conn, c.X, d0, hist)
+            oracle.cd_corrector(c.dt, v0, a0, fext - f, mass, code)
+        got = grp.explicit_history().transpose(2, 0, 1)  # -> [element][ip][16]
+        assert hist[:, :, 15].max() > 1e-3
+        assert np.abs(got[:, :, 15] - hist[:, :, 15]).max() < 1e-10
+        assert np.abs(got[:, :, 9:15] - hist[:, :, 9:15]).max() < 1e-9 * np.abs(hist[:, :, 9:15]).max()
 
 
 @pytest.mark.parametrize("pinned", [False, True])
