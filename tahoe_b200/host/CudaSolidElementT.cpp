@@ -23,13 +23,15 @@
 using namespace Tahoe;
 
 namespace Tahoe {
-const char* kCudaSolidElementNames[3] = {"cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian"};
+const char* kCudaSolidElementNames[kNumCudaSolidElementNames] = {"cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian",
+	"cuda_explicit_solid"};
 
 ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& support)
 {
 	if (name == kCudaSolidElementNames[0]) return new CudaSmallStrainT(support, kCudaSolidElementNames[0], TB2_SMALL_STRAIN);
 	if (name == kCudaSolidElementNames[1]) return new CudaTotalLagrangianT(support, kCudaSolidElementNames[1], TB2_TOTAL_LAGRANGIAN);
 	if (name == kCudaSolidElementNames[2]) return new CudaUpdatedLagrangianT(support, kCudaSolidElementNames[2], TB2_UPDATED_LAGRANGIAN);
+	if (name == kCudaSolidElementNames[3]) return new CudaExplicitSolidT(support, kCudaSolidElementNames[3], TB2_UPDATED_LAGRANGIAN);
 	return NULL;
 }
 } // namespace Tahoe
@@ -102,39 +104,77 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 	}
 	if (this->fMaterialList->Length() != 1)
 		ExceptionT::BadInputValue(caller, "exactly one material per CUDA element group");
+	fIsJ2 = false;
 
-	/* material constants */
-	ContinuumMaterialT* cmat = (*(this->fMaterialList))[0];
 	tb2_material mat;
 	memset(&mat, 0, sizeof(mat));
-	if (dynamic_cast<SSKStV*>(cmat)) mat.kind = TB2_SSKSTV;
-	else if (dynamic_cast<FDKStV*>(cmat)) mat.kind = TB2_FDKSTV;
-	else if (dynamic_cast<J2Simo3D*>(cmat)) mat.kind = TB2_J2_SIMO; /* before its base SimoIso3D */
-	else if (dynamic_cast<SimoIso3D*>(cmat)) mat.kind = TB2_SIMO_ISO;
-	else ExceptionT::BadInputValue(caller, "material \"%s\" has no device implementation", cmat->Name().Pointer());
-	const IsotropicT* iso = dynamic_cast<const IsotropicT*>(cmat);
-	const SolidMaterialT* smat = dynamic_cast<const SolidMaterialT*>(cmat);
-	if (!iso || !smat) ExceptionT::GeneralFail(caller, "material is not isotropic");
-	mat.mu = iso->Mu();
-	mat.lambda = iso->Lambda();
-	mat.kappa = iso->Kappa();
-	mat.density = const_cast<SolidMaterialT*>(smat)->Density();
-	fIsJ2 = (mat.kind == TB2_J2_SIMO);
-	if (fIsJ2) { /* K(alpha): C1functions/LinearT.h:71, LinearExponentialT.cpp:48-57 */
-		const ParameterListT* lin = FindList(list, "linear_function");
-		const ParameterListT* lexp = FindList(list, "linear_exponential");
-		if (lin) {
-			mat.hard_kind = TB2_HARD_LINEAR;
-			mat.hard[0] = lin->GetParameter("a");
-			mat.hard[1] = lin->GetParameter("b");
-		} else if (lexp) {
-			mat.hard_kind = TB2_HARD_LINEAR_EXP;
-			mat.hard[0] = lexp->GetParameter("a");
-			mat.hard[1] = lexp->GetParameter("b");
-			mat.hard[2] = lexp->GetParameter("c");
-			mat.hard[3] = lexp->GetParameter("d");
-		} else
-			ExceptionT::BadInputValue(caller, "Simo_J2 hardening must be linear_function or linear_exponential");
+	if (this->Name() == kCudaSolidElementNames[3]) {
+		/* <explicit_solid>: mu / kappa / density are scanned from the material sub-tree and <j2_plasticity> selects the law, exactly
+		 * as ExplicitElementT::TakeParameterList does (ExplicitElementT.cpp:166-213) */
+		struct Finder {
+			static void Find(const ParameterListT& p, double& mu, double& kappa, double& density, bool& has_mu, bool& has_kappa) {
+				const ParameterT* pm = p.Parameter("mu");
+				const ParameterT* pk = p.Parameter("kappa");
+				const ParameterT* pd = p.Parameter("density");
+				if (pm) { mu = *pm; has_mu = true; }
+				if (pk) { kappa = *pk; has_kappa = true; }
+				if (pd) density = *pd;
+				const ArrayT<ParameterListT>& subs = p.Lists();
+				for (int i = 0; i < subs.Length(); i++) Find(subs[i], mu, kappa, density, has_mu, has_kappa);
+			}
+		};
+		double mu = 0.0, kappa = 0.0, density = 1.0;
+		bool has_mu = false, has_kappa = false;
+		const ParameterListT& block = list.GetList("large_strain_element_block");
+		Finder::Find(block.GetListChoice(*this, "large_strain_material_choice"), mu, kappa, density, has_mu, has_kappa);
+		if (!has_mu || !has_kappa) ExceptionT::BadInputValue(caller, "explicit_solid needs mu and kappa in its material sub-tree");
+		mat.kind = TB2_EXPL_NEO_HOOKEAN;
+		mat.mu = mu;
+		mat.kappa = kappa;
+		mat.lambda = kappa - 2.0 * mu / 3.0;
+		mat.density = density;
+		if (list.NumLists("j2_plasticity") > 0) {
+			const ParameterListT& j2 = list.GetList("j2_plasticity");
+			mat.kind = TB2_EXPL_J2;
+			mat.hard[0] = j2.GetParameter("sigma_Y");
+			mat.hard[1] = j2.GetParameter("hardening");
+		}
+		if (list.NumLists("mass_scaling") > 0 && int(list.GetList("mass_scaling").GetParameter("type")) != 1 /* kFixedMassScaling */)
+			ExceptionT::BadInputValue(caller, "adaptive mass scaling re-forms the mass inside RHSDriver; only type=\"fixed\" is supported with the CUDA group");
+		if (list.NumLists("anp_tet4") > 0) ExceptionT::BadInputValue(caller, "anp_tet4 is a Tet4 option; the CUDA group is Hex8 only");
+	} else {
+		/* material constants */
+		ContinuumMaterialT* cmat = (*(this->fMaterialList))[0];
+		if (dynamic_cast<SSKStV*>(cmat)) mat.kind = TB2_SSKSTV;
+		else if (dynamic_cast<FDKStV*>(cmat)) mat.kind = TB2_FDKSTV;
+		else if (dynamic_cast<J2Simo3D*>(cmat)) mat.kind = TB2_J2_SIMO; /* before its base SimoIso3D */
+		else if (dynamic_cast<SimoIso3D*>(cmat)) mat.kind = TB2_SIMO_ISO;
+		else ExceptionT::BadInputValue(caller, "material \"%s\" has no device implementation", cmat->Name().Pointer());
+		const IsotropicT* iso = dynamic_cast<const IsotropicT*>(cmat);
+		const SolidMaterialT* smat = dynamic_cast<const SolidMaterialT*>(cmat);
+		if (!iso || !smat) ExceptionT::GeneralFail(caller, "material is not isotropic");
+		mat.mu = iso->Mu();
+		mat.lambda = iso->Lambda();
+		mat.kappa = iso->Kappa();
+		mat.density = const_cast<SolidMaterialT*>(smat)->Density();
+		fIsJ2 = (mat.kind == TB2_J2_SIMO);
+		if (fIsJ2) { /* K(alpha): C1functions/LinearT.h:71, LinearExponentialT.cpp:48-57 */
+			const ParameterListT* lin = FindList(list, "linear_function");
+			const ParameterListT* lexp = FindList(list, "linear_exponential");
+			if (lin) {
+				mat.hard_kind = TB2_HARD_LINEAR;
+				mat.hard[0] = lin->GetParameter("a");
+				mat.hard[1] = lin->GetParameter("b");
+			} else if (lexp) {
+				mat.hard_kind = TB2_HARD_LINEAR_EXP;
+				mat.hard[0] = lexp->GetParameter("a");
+				mat.hard[1] = lexp->GetParameter("b");
+				mat.hard[2] = lexp->GetParameter("c");
+				mat.hard[3] = lexp->GetParameter("d");
+			} else
+				ExceptionT::BadInputValue(caller, "Simo_J2 hardening must be linear_function or linear_exponential");
+		}
+
 	}
 
 	/* connectivity of all blocks, in block order then file order (ElementBaseT.cpp:607-632) */
@@ -246,4 +286,5 @@ namespace Tahoe {
 template class CudaSolidElementT<SmallStrainT>;
 template class CudaSolidElementT<TotalLagrangianT>;
 template class CudaSolidElementT<UpdatedLagrangianT>;
+template class CudaSolidElementT<ExplicitElementT>;
 }

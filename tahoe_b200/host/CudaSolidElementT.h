@@ -3,7 +3,8 @@
  *
  * The class template derives from Tahoe's own SmallStrainT / TotalLagrangianT / UpdatedLagrangianT, so the XML
  * parameters, material lists, output, mass matrix and restart code are inherited unchanged and an input file differs
- * from a classic one by the element tag only (<total_lagrangian> -> <cuda_total_lagrangian>).  What is replaced is the
+ * from a classic one by the element tag only (<total_lagrangian> -> <cuda_total_lagrangian>, <explicit_solid> ->
+ * <cuda_explicit_solid>).  What is replaced is the
  * per-element virtual-call loop:
  *   RHSDriver()  : SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295)  -> tb2_form_internal_force_host
  *   LHSDriver()  : SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154)  -> tb2_form_stiffness into the
@@ -18,6 +19,7 @@
 #include "SmallStrainT.h"
 #include "TotalLagrangianT.h"
 #include "UpdatedLagrangianT.h"
+#include "ExplicitElementT.h"
 #include "dArray2DT.h"
 
 #include "tahoe_b200.h"
@@ -95,11 +97,14 @@ private:
 typedef CudaSolidElementT<SmallStrainT> CudaSmallStrainT;
 typedef CudaSolidElementT<TotalLagrangianT> CudaTotalLagrangianT;
 typedef CudaSolidElementT<UpdatedLagrangianT> CudaUpdatedLagrangianT;
+/** <cuda_explicit_solid>: ExplicitElementT's XML (incl. <j2_plasticity>, <mass_scaling>) and host-side lumped mass, the batched internal force on the device */
+typedef CudaSolidElementT<ExplicitElementT> CudaExplicitSolidT;
 
 /** factory used by the one-line registration in ElementListT::NewElement; returns NULL for other names */
 ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& support);
 /** the XML tags handled by NewCudaSolidElement */
-extern const char* kCudaSolidElementNames[3];
+static const int kNumCudaSolidElementNames = 4;
+extern const char* kCudaSolidElementNames[kNumCudaSolidElementNames];
 
 } // namespace Tahoe
 #endif

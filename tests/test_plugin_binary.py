@@ -48,6 +48,21 @@ def _cases():
                               "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
                               "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": simo,
                               "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        # the reference's batched <explicit_solid> against <cuda_explicit_solid>: Neo-Hookean with fixed mass scaling
+        # (host-side lumped mass incl. the scaling, device force) and Hughes-Winget J2 pulled past yield (device-resident history)
+        "explicit_solid_neo": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                                "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
+                                "element": {"type": "explicit_solid", "mass_type": "lumped_mass",
+                                            "mass_scaling": {"type": "fixed", "target_dt": "%.6g" % (1.25 * 0.874 * 0.2 / np.sqrt(1000.0 + 20.0 / 3.0)),
+                                                             "scale_factor": "0.9"}},
+                                "material": {"type": "explicit_neo_hookean", "density": 1.0, "kappa": 1000.0, "mu": 5.0},
+                                "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        "explicit_solid_j2": ({"time": {"num_steps": 300, "time_step": 0.4 * 0.2 / np.sqrt(1000.0 + 200.0 / 3.0), "schedules": [[(0.0, 0.0), (0.3, 1.0), (10.0, 1.0)]]},
+                               "integrator": "central_difference",
+                               "kbc": CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.08}], "fbc": [],
+                               "element": {"type": "explicit_solid", "mass_type": "lumped_mass"},
+                               "material": {"type": "explicit_J2", "density": 1.0, "kappa": 1000.0, "mu": 50.0, "sigma_Y": 2.0, "hardening_modulus": 100.0},
+                               "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
         # static Newton: device K1 + device K3 + device PCG against the reference's SPOOLES LU
         "static_ss_kstv_pcg": ({"time": {"num_steps": 1, "time_step": 1.0, "schedules": [RAMP]}, "integrator": "static", "kbc": CLAMP,
                                 "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005}],
