@@ -150,7 +150,10 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the unmodified reference binary on a bounded sample
 # ---------------------------------------------------------------------------------------------------------------------
-def _write_reference_case(work, n, nsteps):
+XS_MATERIAL = {"type": "explicit_neo_hookean", "density": 1.0, "kappa": 1000.0, "mu": 5.0}  # vectorized_hex_*.xml (level.5/explicit_benchmark)
+
+
+def _write_reference_case(work, n, nsteps, element="total_lagrangian", material=None):
     import tahoe_input as ti
     X, conn, ns = ti.structured_cube(n, jitter=0.1)
     if not os.path.exists(os.path.join(work, "mesh.geom")):
@@ -160,36 +163,36 @@ def _write_reference_case(work, n, nsteps):
             "integrator": "central_difference",
             "kbc": [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)],
             "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02 / (n * n)}],
-            "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": MATERIAL,
+            "element": {"type": element, "mass_type": "lumped_mass"}, "material": material or MATERIAL,
             "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}
     ti.write_xml(os.path.join(work, "run_%d.xml" % nsteps), desc)
     return conn.shape[0]
 
 
-def _run_reference_batch(work, nsteps, procs):
+def _run_reference_batch(work, nsteps, procs, omp_threads=1):
     t0 = time.perf_counter()
     ps = [subprocess.Popen([REF_BIN, "-f", "run_%d.xml" % nsteps], cwd=work, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
-                           env=dict(os.environ, OMP_NUM_THREADS="1")) for _ in range(procs)]
+                           env=dict(os.environ, OMP_NUM_THREADS=str(omp_threads))) for _ in range(procs)]
     rc = [p.wait() for p in ps]
     if any(rc):
         raise RuntimeError("reference binary failed: %s" % rc)
     return time.perf_counter() - t0
 
 
-def reference_rate(n, s_lo, s_hi, procs, min_seconds=2.0):
+def reference_rate(n, s_lo, s_hi, procs, min_seconds=2.0, element="total_lagrangian", material=None, omp_threads=1):
     """element-updates/s of `procs` concurrent serial reference processes on an n^3 cube, from the wall-clock difference
     between an s_hi-step and an s_lo-step run (cancels input parsing, set-up and FEManagerT::InitialCondition).  If the difference
     is shorter than min_seconds (a short --steps request) the long run is repeated with 4x the steps, so the rate never comes
     from timer noise.  Returns (rate, seconds, elements, timed steps)."""
     work = tempfile.mkdtemp(prefix="tb2_ref_")
     try:
-        ne = _write_reference_case(work, n, s_lo)
-        t_lo = _run_reference_batch(work, s_lo, procs)
+        ne = _write_reference_case(work, n, s_lo, element, material)
+        t_lo = _run_reference_batch(work, s_lo, procs, omp_threads)
         k = s_hi - s_lo
-        for _ in range(4):
-            _write_reference_case(work, n, s_lo + k)
-            dt = _run_reference_batch(work, s_lo + k, procs) - t_lo
-            if dt >= min_seconds:
+        for attempt in range(5):
+            _write_reference_case(work, n, s_lo + k, element, material)
+            dt = _run_reference_batch(work, s_lo + k, procs, omp_threads) - t_lo
+            if dt >= min_seconds or attempt == 4:
                 break
             k *= 4
     finally:
@@ -368,6 +371,60 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
            "interface_exchange_ms_per_iteration": comm_ms if world > 1 else None,
            "iteration_hbm_frac": iter_bytes * iters / (ms * 1e-3) * 1e-9 / hbm_peak}
     A.close(); eqs.close(); g.close(); m.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own fast path, <explicit_solid> (ExplicitElementT, 8-point Hex8, ExplNeoHookeanT)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_explicit_solid(torch, capi, tmesh, local, n, steps, warmup, hbm_peak, with_cpu):
+    """device-resident explicit steps of the explicit_solid element on one n^3 cube, and (with_cpu) the reference executable on the
+    same input family with its OpenMP batch loop on all host cores (ExplicitElementT.cpp:697-704) and with one thread"""
+    X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+    m = capi.Mesh(X, conn, device=local)
+    g = capi.Group(m, capi.UPDATED_LAGRANGIAN, capi.material(XS_MATERIAL))
+    dt_cfl = g.stable_time_step()
+    ex = capi.Explicit(g)
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 0.02 / (n * n)
+    ex.set_bc(code, np.zeros_like(X), fext)
+    ex.set_state(initial_displacement(X), np.zeros_like(X), np.zeros_like(X))
+    dt = float(stable_dt(n))
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
+    ex.run(dt, warmup)
+    m.synchronize()
+    m.profile_reserve(steps * 16 + 64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.profile_begin()
+    e0.record(stream)
+    ex.run(dt, steps)
+    e1.record(stream)
+    ms_cat, cnt_cat, launches = m.profile_end()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    d, v, a = ex.get_state()
+    if not np.isfinite(d).all():
+        raise SystemExit("bench.py: non-finite state in the explicit_solid leg")
+    ne = conn.shape[0]
+    k1_ms = float(ms_cat[0]) / steps
+    out = {"metric": METRIC, "value": ne * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "gpu_launches": int(launches),
+           "workload": "%d^3=%d-element jittered cube, <explicit_solid>: 8-point Hex8, ExplNeoHookeanT kappa=1000 mu=5, lumped mass, central difference; "
+                       "CFL estimate of the element (ExplicitElementT::ComputeStableTimeStep) %.3e, dt used %.3e" % (n, ne, dt_cfl, dt),
+           "roofline": {"bound": "hbm", "kernel": "k_internal_force<UL,ExplNeoHookean> (K1)", "achieved": 104.0 * ne / (k1_ms * 1e-3) * 1e-9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": 104.0 * ne / (k1_ms * 1e-3) * 1e-9 / hbm_peak, "ms_per_step": k1_ms,
+                        "share_of_step": k1_ms * steps / ms, "note": "FP64-pipe bound like the SimoIso3D sweep; no cube root in this law"},
+           "cpu_reference": None}
+    ex.close(); g.close(); m.close()
+    if with_cpu and os.path.exists(REF_BIN):
+        cores = os.cpu_count() or 1
+        nref = 32  # 256 batches of 128 elements >= 4 x threads: the reference's OpenMP loop engages (ExplicitElementT.cpp:701)
+        r_omp, t_omp, ne_ref, k_omp = reference_rate(nref, 3, 13, 1, 2.0, "explicit_solid", XS_MATERIAL, cores)
+        r_one, t_one, _, k_one = reference_rate(nref, 3, 13, 1, 2.0, "explicit_solid", XS_MATERIAL, 1)
+        out["cpu_reference"] = {"omp": {"value": r_omp, "threads": cores, "steps": k_omp, "seconds": t_omp},
+                                "serial": {"value": r_one, "threads": 1, "steps": k_one, "seconds": t_one}, "unit": METRIC,
+                                "sample": "oracle/_ref/tahoe on a %d^3=%d-element <explicit_solid> input of the same family" % (nref, ne_ref)}
     return out
 
 
@@ -558,7 +615,12 @@ def run_gpu_arm(args):
     except (OSError, KeyError, ValueError):
         pass
     pcg = None if args.no_pcg else run_pcg(torch, dist, capi, tmesh, local, rank, world, args.pcg_n, args.pcg_iters, hbm_peak_all)
+    xs = None
+    if world == 1 and not args.no_explicit_solid:
+        xs = run_explicit_solid(torch, capi, tmesh, local, n, min(args.steps, 200), args.warmup, hbm_peak_all, not args.no_cpu_baseline)
     if rank == 0:
+        if xs:
+            line["explicit_solid"] = xs
         if pcg:
             line["pcg"] = pcg
         print(json.dumps(line))
@@ -576,6 +638,7 @@ def main():
     ap.add_argument("--impl", default="tahoe_b200", choices=["tahoe_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the PCG DOF-iters/s leg")
+    ap.add_argument("--no-explicit-solid", action="store_true", help="skip the <explicit_solid> leg (SURVEY.md 8f-1)")
     ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")
     ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")
     ap.add_argument("--pcg-iters", type=int, default=100)
