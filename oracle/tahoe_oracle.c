@@ -1368,3 +1368,70 @@ int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, cons
     }
     return ORC_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * nodal stress output.  SolidElementT::ComputeOutput (SolidElementT.cpp:1352-1840), iNodalStress branch:
+ * Cauchy stress at the 8 points -> ShapeFunctionT::Extrapolate = ParentDomainT::NodalValues (ParentDomainT.cpp:1954-1998) with the
+ * smoothing matrix of HexahedronT::SetExtrapolation (HexahedronT.cpp:2099-2150: E[a][ip] = (1 + sqrt3 s_a.s_ip)/8) ->
+ * ElementSupportT::AssembleAverage / GroupAverageT::Average (toolbox/src/misc/GroupAverageT.cpp:40-49, 190-205).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, const double* u,
+                     double* out /*[nn][6]*/)
+{
+    static const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+    const double sqrt3 = sqrt(3.0);
+    int* count = calloc(nn, sizeof(int));
+    memset(out, 0, sizeof(double) * 6 * nn);
+    for (int64_t e = 0; e < ne; e++) {
+        const int32_t* c = conn + 8 * e;
+        double Xe[8][3], ue[8][3], dN[8][3][8], det[8], nodal[8][6], mg[3][8];
+        gather(c, X, Xe);
+        gather(c, u, ue);
+        int err = orc_hex8_shape(Xe, dN, det);
+        if (err) { free(count); return err; }
+        if (form == ORC_SMALL_STRAIN_BBAR) mean_gradient(dN, det, mg);
+        memset(nodal, 0, sizeof nodal);
+        for (int ip = 0; ip < 8; ip++) {
+            double G[9], sig[6];
+            grad_u(ue, dN[ip], G);
+            if (form == ORC_SMALL_STRAIN || form == ORC_SMALL_STRAIN_BBAR) {
+                double eps[6];
+                if (form == ORC_SMALL_STRAIN_BBAR) {
+                    double B[6][24];
+                    set_B_bar(dN[ip], mg, B);
+                    for (int I = 0; I < 6; I++) {
+                        double t = 0.0;
+                        for (int a = 0; a < 8; a++)
+                            for (int i = 0; i < 3; i++) t += B[I][3 * a + i] * ue[a][i];
+                        eps[I] = I < 3 ? t : 0.5 * t;
+                    }
+                } else {
+                    eps[0] = G[0]; eps[1] = G[4]; eps[2] = G[8];
+                    eps[3] = 0.5 * (G[5] + G[7]); eps[4] = 0.5 * (G[2] + G[6]); eps[5] = 0.5 * (G[1] + G[3]);
+                }
+                hooke_stress(m, eps, sig);
+            } else {
+                double F[9];
+                memcpy(F, G, sizeof F);
+                F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+                err = fs_material(m, F, F, NULL, ip, NULL, 0, sig, NULL);
+                if (err) { free(count); return err; }
+            }
+            for (int a = 0; a < 8; a++) {
+                const double E = 0.125 * (1.0 + sqrt3 * (sx[a] * sx[ip] + sy[a] * sy[ip] + sz[a] * sz[ip]));
+                for (int I = 0; I < 6; I++) nodal[a][I] += E * sig[I];
+            }
+        }
+        for (int a = 0; a < 8; a++) {
+            count[c[a]]++;
+            for (int I = 0; I < 6; I++) out[6 * (int64_t)c[a] + I] += nodal[a][I];
+        }
+    }
+    for (int64_t n = 0; n < nn; n++)
+        if (count[n] > 0) {
+            const double s = 1.0 / count[n];
+            for (int I = 0; I < 6; I++) out[6 * n + I] *= s;
+        }
+    free(count);
+    return ORC_OK;
+}

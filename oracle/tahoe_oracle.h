@@ -121,6 +121,11 @@ void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const in
                                    double scale_factor, double* scale /*[ne]*/);
 int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass);
 
+/* nodal Cauchy stress as SolidElementT::ComputeOutput writes it (extrapolated with HexahedronT::SetExtrapolation,
+ * averaged over the elements at a node); SSKStV (incl. B-bar), FDKStV, SimoIso3D.  out[nn][6], order 11,22,33,23,13,12 */
+int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, const double* u,
+                     double* out);
+
 /* a21: nonlinear preconditioned CG with secant line search, PCGSolver_LS (solvers/PCGSolver_LS.cpp:107-371) inside
  * NLSolver::Solve / ExitIteration (solvers/NLSolver.cpp:57-263, 675-756), preconditioner = DiagonalMatrixT kDiagOnly
  * (DiagonalMatrixT.cpp:107-113, 267-310).  u[nn][3] in/out (prescribed dofs already hold their values). */

@@ -26,3 +26,24 @@ mb = n * 8 / 1e6
 for name, fn in (("h2d", h2d), ("d2h", d2h), ("both", both), ("chunked16", chunked)):
     ms = t(fn)
     print(f"{name}: {ms:.3f} ms  ({mb/ms:.1f} GB/s per direction)")
+
+# copies beside kernels: does SM / HBM activity slow the copy engines down?
+s3 = torch.cuda.Stream()
+A = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+big = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device="cuda")
+def with_fp64():
+    with torch.cuda.stream(s3):
+        for _ in range(3): torch.mm(A, A)
+    chunked()
+def with_hbm():
+    with torch.cuda.stream(s3):
+        for _ in range(6): big.add_(1.0)
+    chunked()
+def chunked48():
+    c = n // 48
+    for i in range(48):
+        with torch.cuda.stream(s1): d_a[i*c:(i+1)*c].copy_(h_in[i*c:(i+1)*c], non_blocking=True)
+        with torch.cuda.stream(s2): h_out[i*c:(i+1)*c].copy_(d_b[i*c:(i+1)*c], non_blocking=True)
+for name, fn in (("chunked48 (1.5 MB copies)", chunked48), ("chunked16 beside FP64 GEMMs", with_fp64), ("chunked16 beside HBM-bound kernels", with_hbm)):
+    ms = t(fn)
+    print(f"{name}: {ms:.3f} ms")

@@ -13,6 +13,7 @@ PCG = [n for n in ALL if n.endswith("_pcg")]  # PCGSolver_LS runs (a21): converg
 STATIC = [n for n in ALL if n not in PCG and ("static" in n or n.startswith("ref_mat") or n.startswith("ref_beam") or n == "ref_traction_a")]
 XS = [n for n in ALL if "_xs_" in n]  # <explicit_solid> runs; their `fint` dump comes from the classic element path, not used
 EXPLICIT = [n for n in ALL if "explicit" in n and n not in XS]
+STRESS = [n for n in ALL if n.endswith("_stress")]  # nodal stress output
 WITH_LHS = [n for n in ALL if n.startswith("syn_") and "static" in n]
 
 

@@ -56,6 +56,12 @@ def run_case(name, xml_path, flags, desc, coords, conn, nodesets):
         payload["ns_%d" % sid] = np.asarray(ids, np.int32)
     for k, v in dump.items():
         payload["ref_" + k] = v
+    if desc["element"].get("nodal_output") == "stress":
+        # SolidElementT::ComputeOutput (SolidElementT.cpp:1352-1840): Cauchy stress extrapolated to the nodes and averaged, as the
+        # reference's own TextOutputT wrote it during the run (13 significant digits)
+        labels, table = ti.read_nodal_table(os.path.splitext(xml_path)[0] + ".io0.run")
+        assert labels[-6:] == ["s11", "s22", "s33", "s23", "s13", "s12"], labels
+        payload["ref_nodal_stress"] = table[:, -6:]
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **payload)
     print("%-28s %7.1f kB  %s" % (name, os.path.getsize(path) / 1024, " ".join(sorted(dump))))
@@ -185,6 +191,16 @@ def main():
         ("syn_ss_kstv_bbar_static", 4, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
                                         "element": {"type": "small_strain", "strain_displacement": "B-bar"},
                                         "material": dict(kstv, nu=0.49), "solver": NEWTON}, ["--fint", "--lhs"]),
+        # nodal stress output (extrapolation + averaging) after a static solve
+        ("syn_tl_simo_stress", 3, {"time": static(1), "integrator": "static", "kbc": pull_u(0.15), "fbc": [], "output_inc": 1,
+                                   "element": {"type": "total_lagrangian", "nodal_output": "stress"}, "material": simo_soft, "solver": NEWTON},
+         ["--fint"]),
+        ("syn_ss_kstv_stress", 4, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f, "output_inc": 1,
+                                   "element": {"type": "small_strain", "nodal_output": "stress"}, "material": kstv, "solver": NEWTON},
+         ["--fint"]),
+        ("syn_ul_fdkstv_stress", 3, {"time": static(1), "integrator": "static", "kbc": pull_u(0.15), "fbc": [], "output_inc": 1,
+                                     "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": fdkstv, "solver": NEWTON},
+         ["--fint"]),
         # a21: nonlinear PCG (PCGSolver_LS) -- linear, finite-strain and J2 cases
         ("syn_ss_kstv_pcg", 3, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
                                 "element": {"type": "small_strain"}, "material": kstv, "solver": PCG}, ["--fint"]),

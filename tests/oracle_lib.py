@@ -254,3 +254,11 @@ def lumped_mass_scaled(density, conn, X, scale):
     err = lib().orc_lumped_mass_scaled(C.c_double(density), C.c_int64(conn.shape[0]), _p(conn), _p(X), _p(scale), _p(m))
     assert err == 0
     return m
+
+
+def nodal_stress(form, mat, conn, X, u):
+    conn = np.ascontiguousarray(conn, np.int32)
+    out = np.zeros((X.shape[0], 6))
+    err = lib().orc_nodal_stress(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), C.c_int64(X.shape[0]), _p(X),
+                                 _p(np.ascontiguousarray(u)), _p(out))
+    return err, out

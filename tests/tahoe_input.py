@@ -241,7 +241,7 @@ def write_xml(path, d):
         mass += ' strain_displacement="%s"' % e["strain_displacement"]
     L.append('    <%s field_name="displacement"%s>\n      <hexahedron/>' % (e.get("tag", e["type"]), mass))
     if e.get("nodal_output"):
-        L.append('      <solid_element_nodal_output displacements="1"/>')
+        L.append('      <solid_element_nodal_output displacements="1"%s/>' % (' stress="1"' if e["nodal_output"] == "stress" else ""))
     small = e["type"] == "small_strain"
     blk = "small_strain_element_block" if small else "large_strain_element_block"
     mlist = "small_strain_material_3D" if small else "large_strain_material_3D"
@@ -302,3 +302,22 @@ def bc_arrays(desc, nodesets, nn, t):
         ids = nodesets[k["nodeset"]]
         fext[ids, k["dof"] - 1] += k["value"] * schedule_value(sch[k["schedule"] - 1], t)
     return code, val, fext
+
+
+def read_nodal_table(run_file):
+    """last 'Nodal data' table of a Tahoe text .run file (TextOutputT, 12 digits after the point) -> (labels, array [nn][nvalues])"""
+    import glob
+    import re
+    parts = sorted(glob.glob(run_file + ".ps*"))  # one file per print step next to the table of contents
+    text = open(parts[-1] if parts else run_file).read()
+    block = text[text.rindex("Nodal data:"):]
+    rows, labels = [], []
+    for line in block.splitlines():
+        f = line.split()
+        if len(f) >= 3 and f[0] == "index" and f[1] == "node":
+            labels = f[2:]
+        elif len(f) >= 5 and re.match(r"^\d+$", f[0]) and re.match(r"^\d+$", f[1]):
+            rows.append([float(x) for x in f[2:]])
+        elif rows and not f:
+            break
+    return labels, np.array(rows)

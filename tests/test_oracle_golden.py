@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from cases import PCG, XS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 TOL = 1e-10  # north_star: forces / displacements agree to 1e-10 relative
 
@@ -130,6 +130,15 @@ def test_explicit_solid_matches_reference(oracle, name):
     if isj2:
         assert hist[:, :, 15].max() > 1e-3  # the run really yields (equivalent plastic strain)
     assert 0.0 < oracle.explicit_solid_stable_dt(mat, c.conn, c.X) < 1.0
+
+
+@pytest.mark.parametrize("name", STRESS)
+def test_nodal_stress_output_matches_reference(oracle, name):
+    """extrapolated + averaged nodal Cauchy stress against the table the reference's own TextOutputT wrote"""
+    c, form, mat = _setup(oracle, name)
+    err, s = oracle.nodal_stress(form, mat, c.conn, c.X, c.ref("d_%d" % c.dump_steps[-1]))
+    assert err == 0
+    assert relerr(s, c.ref("nodal_stress")) < 5e-12  # 13 printed digits
 
 
 def newton(oracle, c, form, mat, solve):
