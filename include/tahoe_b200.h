@@ -131,6 +131,13 @@ int tb2_group_set_mass_scaling(tb2_group* group, double target_dt, double scale_
 /* ExplJ2PlasticityT history in the reference's layout [ip][16][element] (ExplicitElementT.h:75-79): h_hist[8][16][ne] */
 int tb2_group_get_explicit_history(tb2_group* group, double* h_hist);
 
+/* Nodal stress output: SolidElementT::ComputeOutput, iNodalStress branch (SolidElementT.cpp:1352-1840) -- Cauchy
+ * stress at the integration points, extrapolated with HexahedronT::SetExtrapolation (HexahedronT.cpp:2099-2150) and averaged over
+ * the elements at each node (GroupAverageT.cpp:40-49,190-205).  d_stress[nn][6], order 11,22,33,23,13,12.  SSKStV (incl. B-bar),
+ * FDKStV and SimoIso3D; other materials return TB2_ERR_ARG. */
+int tb2_group_nodal_stress(tb2_group* group, const double* d_u, double* d_stress);
+int tb2_group_nodal_stress_host(tb2_group* group, const double* h_u, double* h_stress);
+
 /* J2 history: SolidElementT::CloseStep -> J2Simo3D::UpdateHistory (J2SimoC0HardeningT.cpp:341-384), ResetStep -> ResetHistory (:387-407) */
 int tb2_group_close_step(tb2_group* group);
 int tb2_group_reset_step(tb2_group* group);

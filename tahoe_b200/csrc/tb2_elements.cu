@@ -465,6 +465,111 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_geo(const Ele
     }
 }
 
+// ---- nodal stress output ---------------------------------------------------------------------------------
+// SolidElementT::ComputeOutput, iNodalStress (SolidElementT.cpp:1352-1840): Cauchy stress at the 8 points, extrapolated to the
+// element's nodes with HexahedronT::SetExtrapolation's matrix E[a][ip] = (1 + sqrt3 s_a . s_ip) / 8 (HexahedronT.cpp:2099-2150),
+// then averaged over the elements at each node (GroupAverageT).  With S0 = sum_ip sigma and S_d = sum_ip s_ip,d sigma the
+// extrapolation is (S0 + sqrt3 (s_a,0 S_1 + s_a,1 S_2 + s_a,2 S_3)) / 8: 4 x 6 accumulators instead of an 8 x 8 matrix product.
+template <int FORM, int MAT>
+__global__ void __launch_bounds__(128) k_nodal_stress(const ElemArgs p, double* __restrict__ out48)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= p.ne) return;
+    int n[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
+    Modes cX, cU;
+    load_modes(p.X, n, cX);
+    load_modes(p.u, n, cU);
+    double theta_bar = 0.0;
+    if (MAT == kSSKStVBbar) { // see internal_force_element
+        double num = 0.0, vol = 0.0;
+#pragma unroll 1
+        for (int ip = 0; ip < 8; ip++) {
+            double s0, s1, s2, J0[3][3], H[3][3], J0a[3][3];
+            ip_signs(ip, s0, s1, s2);
+            mode_gradient(cX, s0, s1, s2, J0);
+            mode_gradient(cU, s0, s1, s2, H);
+            vol += adj3(J0, J0a);
+#pragma unroll
+            for (int i = 0; i < 3; i++) num += H[i][0] * J0a[0][i] + H[i][1] * J0a[1][i] + H[i][2] * J0a[2][i];
+        }
+        theta_bar = num / vol;
+    }
+    double S[4][6];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int I = 0; I < 6; I++) S[k][I] = 0.0;
+    int err = kErrNone;
+#pragma unroll 1
+    for (int ip = 0; ip < 8; ip++) {
+        double s0, s1, s2, J0[3][3], H[3][3], J0a[3][3], g[3][3], sig[6];
+        ip_signs(ip, s0, s1, s2);
+        mode_gradient(cX, s0, s1, s2, J0);
+        mode_gradient(cU, s0, s1, s2, H);
+        const double det0 = adj3(J0, J0a);
+        if (det0 <= 0.0) err = kErrBadJacobian;
+        const double rdet0 = 1.0 / det0;
+        mul3(H, J0a, g);
+        scale3(g, rdet0); // grad_X u
+        if (FORM == kSmallStrain) {
+            double eps[6] = {g[0][0], g[1][1], g[2][2], 0.5 * (g[1][2] + g[2][1]), 0.5 * (g[0][2] + g[2][0]), 0.5 * (g[0][1] + g[1][0])};
+            if (MAT == kSSKStVBbar) {
+                const double corr = (theta_bar - (eps[0] + eps[1] + eps[2])) * (1.0 / 3.0);
+                eps[0] += corr; eps[1] += corr; eps[2] += corr;
+            }
+            hooke_stress(p.mat, eps, sig);
+        } else {
+            g[0][0] += 1.0; g[1][1] += 1.0; g[2][2] += 1.0; // F
+            const double J = det3(g);
+            if (J <= 0.0) err = kErrBadJacobian;
+            if (MAT == kFDKStV) fdkstv_stress(p.mat, g, J, sig);
+            else {
+                double b_bar[6];
+                simo_bbar(g, J, b_bar);
+                simo_cauchy(p.mat, J, b_bar, sig);
+            }
+        }
+#pragma unroll
+        for (int I = 0; I < 6; I++) {
+            S[0][I] += sig[I];
+            S[1][I] += s0 * sig[I];
+            S[2][I] += s1 * sig[I];
+            S[3][I] += s2 * sig[I];
+        }
+    }
+    if (err) report(p, err, e);
+    const double r3 = 1.7320508075688772935;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        double s0, s1, s2;
+        ip_signs(a, s0, s1, s2); // node a sits in the corner of integration point a
+#pragma unroll
+        for (int I = 0; I < 6; I++)
+            out48[(int64_t)(6 * a + I) * p.stride + e] = 0.125 * (S[0][I] + r3 * (s0 * S[1][I] + s1 * S[2][I] + s2 * S[3][I]));
+    }
+}
+// GroupAverageT::AssembleAverage + Average: sum of the incident elements' nodal values (ascending element order) times 1 / count
+__global__ void __launch_bounds__(256) k_node_average6(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                      const double* __restrict__ out48, int64_t stride, double* __restrict__ out)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= nn) return;
+    const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k = k0; k < k1; k++) {
+        const int ent = __ldg(inc + k);
+        const int64_t e = ent >> 3;
+        const int a = ent & 7;
+#pragma unroll
+        for (int I = 0; I < 6; I++) acc[I] += __ldg(out48 + (int64_t)(6 * a + I) * stride + e);
+    }
+    const double s = k1 > k0 ? 1.0 / (double)(k1 - k0) : 0.0;
+#pragma unroll
+    for (int I = 0; I < 6; I++) out[6 * n + I] = acc[I] * s;
+}
+
 // K4: ContinuumElementT::FormMass, kLumpedMass branch (ContinuumElementT.cpp:767-842).  me[a] -> fe[a][stride]
 __global__ void __launch_bounds__(128) k_lumped_mass(int64_t ne, int64_t stride, const int* __restrict__ conn,
                                                     const double* __restrict__ X, double density, double* __restrict__ fe,
@@ -954,6 +1059,52 @@ int tb2_group_get_explicit_history(tb2_group* g, double* h_hist)
     TB2_CUDA(cudaMemcpy2D(h_hist, m->ne * sizeof(double), g->hist.p, m->stride * sizeof(double), m->ne * sizeof(double), 128,
                           cudaMemcpyDeviceToHost));
     return TB2_OK;
+}
+
+int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
+{
+    TB2_ARG(g && d_u && d_stress);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    void (*k)(const ElemArgs, double*) = nullptr;
+    if (g->form == TB2_SMALL_STRAIN && g->mat.kind == TB2_SSKSTV)
+        k = g->bbar ? k_nodal_stress<kSmallStrain, kSSKStVBbar> : k_nodal_stress<kSmallStrain, kSSKStV>;
+    else if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_FDKSTV) k = k_nodal_stress<kTotalLagrangian, kFDKStV>;
+    else if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_SIMO_ISO) k = k_nodal_stress<kTotalLagrangian, kSimoIso>;
+    if (!k) {
+        set_error("nodal stress output is implemented for SSKStV, FDKStV and SimoIso3D (material %d)", g->mat.kind);
+        return TB2_ERR_ARG;
+    }
+    if (!m->out48.p) TB2_CUDA(m->out48.alloc((size_t)48 * m->stride));
+    ElemArgs p{};
+    p.e_begin = 0;
+    p.ne = m->ne;
+    p.stride = m->stride;
+    p.conn = m->conn.p;
+    p.X = m->X.p;
+    p.u = d_u;
+    p.mat = g->mc;
+    p.status = g->status.p;
+    ProfScope ps(m, kProfOther, 2);
+    k<<<(unsigned)((m->ne + 127) / 128), 128, 0, m->stream>>>(p, m->out48.p);
+    k_node_average6<<<(unsigned)((m->nn + 255) / 256), 256, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->out48.p, m->stride, d_stress);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
+int tb2_group_nodal_stress_host(tb2_group* g, const double* h_u, double* h_stress)
+{
+    TB2_ARG(g && h_u && h_stress);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CHECK(ensure_stage(m, 0));
+    DevBuf<double> out;
+    TB2_CUDA(out.alloc(6 * m->nn));
+    TB2_CUDA(cudaMemcpyAsync(m->stage_a.p, h_u, 3 * m->nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    TB2_CHECK(tb2_group_nodal_stress(g, m->stage_a.p, out.p));
+    TB2_CUDA(cudaMemcpyAsync(h_stress, out.p, 6 * m->nn * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return tb2_group_status(g, nullptr);
 }
 
 int tb2_form_lumped_mass(tb2_group* g, double* d_mass)

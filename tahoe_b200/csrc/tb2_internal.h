@@ -117,6 +117,7 @@ struct tb2_mesh {
                                         // unless it is an irregular vertex; those continue in inc[])
     tb2::DevBuf<double> fe;             // [24][stride] element force scratch
     tb2::DevBuf<double> stage_a, stage_b, stage_c; // [nn][3] staging for the *_host entry points
+    tb2::DevBuf<double> out48;          // [48][stride] per-element nodal output values (tb2_group_nodal_stress), built on first use
     // colouring (built lazily)
     int ncolours = 0;
     std::vector<int32_t> colour_host;   // [ne]

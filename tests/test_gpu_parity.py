@@ -8,7 +8,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import tahoe_input as ti
-from cases import PCG, XS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -77,6 +77,25 @@ def test_cached_reference_geometry_returns_the_same_bits(tb2, form, monkeypatch)
         grp = tb2.Group(mesh, tb2.FORM_OF[form], tb2.material(desc))
         out[flag] = grp.internal_force_host(u)
     assert np.abs(out["0"]).max() > 0 and np.array_equal(out["0"], out["1"])
+
+
+@pytest.mark.parametrize("name", STRESS)
+def test_nodal_stress_output_matches_reference(tb2, name):
+    """device nodal stress (IP Cauchy stress, extrapolation, nodal average) against the reference's output table"""
+    c = Case(name)
+    mesh, grp, _ = _group(tb2, c)
+    s = grp.nodal_stress_host(c.ref("d_%d" % c.dump_steps[-1]))
+    assert relerr(s, c.ref("nodal_stress")) < TOL
+
+
+@pytest.mark.parametrize("form,matname", FORMS)
+def test_nodal_stress_output_matches_oracle(tb2, oracle, form, matname):
+    X, conn, _, u = _synthetic((6, 5, 7))
+    desc = {"type": matname, "E": 100.0, "nu": 0.3, "density": 1.0}
+    err, ref = oracle.nodal_stress(oracle.FORM_OF[form], oracle.material(desc), conn, X, u)
+    assert err == 0
+    grp = tb2.Group(tb2.Mesh(X, conn), tb2.FORM_OF[form], tb2.material(desc))
+    assert relerr(grp.nodal_stress_host(u), ref) < TOL
 
 
 def test_lumped_mass_matches_oracle(tb2, oracle):
