@@ -47,3 +47,16 @@ def chunked48():
 for name, fn in (("chunked48 (1.5 MB copies)", chunked48), ("chunked16 beside FP64 GEMMs", with_fp64), ("chunked16 beside HBM-bound kernels", with_hbm)):
     ms = t(fn)
     print(f"{name}: {ms:.3f} ms")
+
+# 48 copies per direction spread over 2 / 3 streams per direction: do the per-copy set-up gaps overlap?
+def multi(kstreams):
+    hs = [torch.cuda.Stream() for _ in range(kstreams)]
+    ds = [torch.cuda.Stream() for _ in range(kstreams)]
+    c = n // 48
+    def fn():
+        for i in range(48):
+            with torch.cuda.stream(hs[i % kstreams]): d_a[i*c:(i+1)*c].copy_(h_in[i*c:(i+1)*c], non_blocking=True)
+            with torch.cuda.stream(ds[i % kstreams]): h_out[i*c:(i+1)*c].copy_(d_b[i*c:(i+1)*c], non_blocking=True)
+    return fn
+for k in (1, 2, 3, 4):
+    print(f"chunked48 over {k} stream(s) per direction: {t(multi(k)):.3f} ms")

@@ -135,3 +135,64 @@ def _global_interface_ids(nx, ny, nz, sx, sy, sz):
     if not ids:
         return np.zeros(0, np.int64)
     return np.unique(np.concatenate(ids))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# general meshes: element partition by recursive coordinate bisection (METIS is absent in this image; the reference
+# itself ships a non-METIS partitioner, GraphBaseT::Partition)
+# ---------------------------------------------------------------------------------------------------------------------
+def rcb_element_owner(coords, conn, nranks):
+    """owner rank of every element: recursive coordinate bisection of the element centroids along the longest extent, split at
+    the weighted median so that rank counts need not be powers of two.  Deterministic (stable sorts, ties by element id)."""
+    cent = coords[conn].mean(axis=1)
+    owner = np.zeros(conn.shape[0], np.int32)
+
+    def split(ids, r0, nr):
+        if nr == 1:
+            owner[ids] = r0
+            return
+        nl = nr // 2
+        c = cent[ids]
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        order = ids[np.lexsort((ids, c[:, axis]))]
+        cut = (len(ids) * nl) // nr
+        split(order[:cut], r0, nl)
+        split(order[cut:], r0 + nl, nr - nl)
+
+    split(np.arange(conn.shape[0]), 0, nranks)
+    return owner
+
+
+def partition_mesh(coords, conn, nranks, rank, nodesets=None, owner=None):
+    """This rank's part of an arbitrary Hex8 mesh, with the interface description tb2_comm_init wants (same contract as
+    partition_cube).  Elements keep their global order inside a part (so summation orders follow the global numbering), local
+    nodes are numbered by ascending global id; an interface node is owned by the lowest rank that touches it.
+    Every rank computes the same global description from the whole connectivity (host work, once)."""
+    owner = rcb_element_owner(coords, conn, nranks) if owner is None else np.asarray(owner, np.int32)
+    nn = coords.shape[0]
+    # ranks touching each node: bit mask (<= 64 ranks on one box)
+    touch = np.zeros(nn, np.uint64)
+    for r in range(nranks):
+        nodes = np.unique(conn[owner == r])
+        touch[nodes] |= np.uint64(1) << np.uint64(r)
+    nshare = np.zeros(nn, np.int32)
+    lowest = np.full(nn, -1, np.int32)
+    for r in range(nranks - 1, -1, -1):
+        has = (touch >> np.uint64(r)) & np.uint64(1) != 0
+        nshare += has
+        lowest[has] = r
+    gi = np.nonzero(nshare > 1)[0].astype(np.int64)  # global interface nodes, ascending global id = slot order
+    mine = owner == rank
+    elem_gid = np.nonzero(mine)[0].astype(np.int64)
+    node_gid = np.unique(conn[mine]).astype(np.int64)
+    g2l = np.full(nn, -1, np.int32)
+    g2l[node_gid] = np.arange(len(node_gid), dtype=np.int32)
+    part = {"coords": np.ascontiguousarray(coords[node_gid]), "conn": np.ascontiguousarray(g2l[conn[mine]]).astype(np.int32),
+            "node_gid": node_gid, "elem_gid": elem_gid, "owner": owner}
+    part["nodesets"] = {k: g2l[v][g2l[v] >= 0].astype(np.int32) for k, v in (nodesets or {}).items()}
+    shared_local = np.nonzero(nshare[node_gid] > 1)[0].astype(np.int32)
+    part["if_nodes"] = shared_local
+    part["if_slots"] = np.searchsorted(gi, node_gid[shared_local]).astype(np.int32)
+    part["n_global_interface"] = len(gi)
+    part["owned"] = (lowest[node_gid] == rank).astype(np.uint8)
+    return part

@@ -81,6 +81,45 @@ def nonlinear_solves(m, X, ns):
     return d_cg, it_cg, d_nw, it_nw
 
 
+def general_mesh_phase(rank, world, local):
+    """a mesh with shuffled node and element numbering, partitioned by recursive coordinate bisection (tmesh.partition_mesh):
+    explicit steps on the parts must reproduce the single-GPU run of the whole mesh"""
+    X, conn, ns = tmesh.structured_cube(14, 11, 9, jitter=0.15)
+    rng = np.random.default_rng(5)
+    nperm = rng.permutation(X.shape[0])
+    Xs = np.empty_like(X)
+    Xs[nperm] = X
+    conn_s = np.ascontiguousarray(nperm[conn][rng.permutation(conn.shape[0])].astype(np.int32))
+    ns_s = {k: np.sort(nperm[v]).astype(np.int32) for k, v in ns.items()}
+    part = tmesh.partition_mesh(Xs, conn_s, world, rank, ns_s)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
+    m, g, ex = setup(part["coords"], part["conn"], part["nodesets"], local, comm)
+    dt, nsteps = 2e-4, 12
+    ex.initial_condition()
+    ex.run(dt, nsteps)
+    d, v, a = ex.get_state()
+    out = [None] * world
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a})
+    ex.close(); g.close(); m.close()
+    ok = True
+    if rank == 0:
+        m1, g1, ex1 = setup(Xs, conn_s, ns_s, local)
+        ex1.initial_condition()
+        ex1.run(dt, nsteps)
+        ref = dict(zip("dva", ex1.get_state()))
+        for r, o in enumerate(out):
+            for nm in "dva":
+                err = np.abs(o[nm] - ref[nm][o["gid"]]).max() / max(np.abs(ref[nm]).max(), 1e-300)
+                if not err < 1e-12:
+                    print("general mesh phase: rank %d field %s differs from the single-GPU run: %.3e" % (r, nm, err))
+                    ok = False
+        ex1.close(); g1.close(); m1.close()
+        print("multi_gpu_check: general (RCB-partitioned, shuffled) mesh world=%d %s" % (world, "OK" if ok else "FAILED"))
+    return ok
+
+
 def pipelined_phase(rank, world, local):
     """64^3 elements per rank -> 3+ slab chunks: the overlapped schedule (boundary elements first, all-reduce beside the slab
     pipeline, interface nodes updated last) must give bitwise the fields of the serial schedule (single-step calls), and both
@@ -183,6 +222,7 @@ def main():
         assert len(seen) == nn_glob
         print("multi_gpu_check: world=%d %s" % (world, "OK" if ok else "FAILED"))
     ex.close(); g.close(); m.close()
+    ok = general_mesh_phase(rank, world, local) and ok
     ok = pipelined_phase(rank, world, local) and ok
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
