@@ -98,6 +98,79 @@ def test_nodal_stress_output_matches_oracle(tb2, oracle, form, matname):
     assert relerr(grp.nodal_stress_host(u), ref) < TOL
 
 
+def test_irregular_valence_mesh_matches_oracle(tb2, oracle):
+    """nodes with more than 8 incident elements (here up to 16: a layer of elements is present twice) leave the fixed-width
+    incidence table and take the general paths of the node gather, the adjacency / contribution lists and the colouring"""
+    X, conn, ns, u = _synthetic((5, 4, 4))
+    conn = np.ascontiguousarray(np.vstack([conn, conn[20:60]]))
+    valence = np.bincount(conn.ravel(), minlength=X.shape[0])
+    assert valence.max() == 16
+    desc = {"type": "Simo_isotropic", "E": 100.0, "nu": 0.25, "density": 1.0}
+    omat = oracle.material(desc)
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.TOTAL_LAGRANGIAN, tb2.material(desc))
+    err, f_ref = oracle.internal_force(oracle.TOTAL_LAGRANGIAN, omat, conn, X, u)
+    assert err == 0 and relerr(grp.internal_force_host(u), f_ref) < TOL
+    assert relerr(grp.lumped_mass_host(), oracle.lumped_mass(1.0, conn, X)) < 1e-13
+    assert relerr(grp.nodal_stress_host(u), oracle.nodal_stress(oracle.TOTAL_LAGRANGIAN, omat, conn, X, u)[1]) < TOL
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    eq, neq = oracle.equation_numbers(code)
+    rp, ci = oracle.csr_structure(conn, eq, neq)
+    err, kv = oracle.assemble_stiffness(oracle.TOTAL_LAGRANGIAN, omat, conn, X, u, eq, neq, rp, ci)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    A.form_stiffness_host(grp, u)
+    rowptr, colind, val = A.csr()
+    assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci) and relerr(val, kv) < TOL
+    ncol, col = mesh.colouring()
+    ncol_ref, col_ref = oracle.colouring(conn, X.shape[0])
+    assert ncol == ncol_ref and np.array_equal(col, col_ref)
+    # explicit steps through the slab pipeline's node kernel
+    ex = tb2.Explicit(grp)
+    ex.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    ex.set_state(u, np.zeros_like(X), np.zeros_like(X))
+    ex.run(1e-4, 3)
+    d, v, a = ex.get_state()
+    mass = oracle.lumped_mass(1.0, conn, X)
+    d0, v0, a0 = u.copy(), np.zeros_like(X), np.zeros_like(X)
+    for _ in range(3):
+        oracle.cd_predictor(1e-4, d0, v0, a0, code, np.zeros_like(X))
+        _, fi = oracle.internal_force(oracle.TOTAL_LAGRANGIAN, omat, conn, X, d0)
+        oracle.cd_corrector(1e-4, v0, a0, -fi, mass, code)
+    assert relerr(d, d0) < TOL and relerr(v, v0) < TOL and relerr(a, a0) < TOL
+
+
+def test_empty_ragged_and_mismatched_inputs_are_rejected(tb2):
+    """the error behaviour of the boundary: status codes, never a crash or a silent result (tb2_status <-> ExceptionT::CodeT)"""
+    X, conn, ns, u = _synthetic((3, 3, 3))
+    with pytest.raises(tb2.Tb2Error) as e:          # no elements (ElementBaseT with an empty block list)
+        tb2.Mesh(X, conn[:0])
+    assert e.value.code == 4
+    bad = conn.copy()
+    bad[7, 3] = X.shape[0]                          # node id past the coordinate array: kOutOfRange
+    with pytest.raises(tb2.Tb2Error) as e:
+        tb2.Mesh(X, bad)
+    assert e.value.code == 5
+    mesh = tb2.Mesh(X, conn)
+    with pytest.raises(tb2.Tb2Error) as e:          # SSSolidMatT material under a finite-strain element (MaterialListT check)
+        tb2.Group(mesh, tb2.TOTAL_LAGRANGIAN, tb2.material({"type": "small_strain_StVenant", "E": 1.0, "nu": 0.3, "density": 1.0}))
+    assert e.value.code == 4
+    with pytest.raises(tb2.Tb2Error) as e:          # explicit_solid law under SmallStrainT
+        tb2.Group(mesh, tb2.SMALL_STRAIN, tb2.material({"type": "explicit_neo_hookean", "mu": 1.0, "kappa": 10.0, "density": 1.0}))
+    assert e.value.code == 4
+    grp = tb2.Group(mesh, tb2.UPDATED_LAGRANGIAN, tb2.material({"type": "explicit_neo_hookean", "mu": 1.0, "kappa": 10.0, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    A = tb2.Matrix(tb2.Equations(mesh, code))
+    with pytest.raises(tb2.Tb2Error) as e:          # no tangent for the explicit-only laws: kBadInputValue, not a wrong matrix
+        A.form_stiffness_host(grp, u)
+    assert e.value.code == 4
+    with pytest.raises(tb2.Tb2Error) as e:          # every dof prescribed: an empty equation system
+        tb2.Matrix(tb2.Equations(mesh, np.ones(X.shape, np.uint8)))
+    assert e.value.code in (4, 5)
+
+
 def test_lumped_mass_matches_oracle(tb2, oracle):
     X, conn, _, _ = _synthetic()
     mesh = tb2.Mesh(X, conn)
