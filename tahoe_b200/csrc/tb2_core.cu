@@ -124,27 +124,47 @@ static void build_pipeline(tb2_mesh* m, const int32_t* h_conn, int sm_count)
     }
 }
 
-// the same bookkeeping for the host-buffer step: C equal slabs (no wave rounding: the copies, not the kernels, set the pace)
+// the same bookkeeping for the host-buffer step (no wave rounding: the copies, not the kernels, set the pace).
+// Default: 16 equal slabs.  Every copy costs ~7 us on this platform whatever its size (profiles/r01_summary.md: 48 + 48 copies of
+// 1.5 MB take 2.2 ms where 1 + 1 take 1.5 ms), and a node slab can only go back two slabs after it arrived (its update needs the
+// forces of the next element slab, which needs the predicted nodes of the slab after) -- fewer / unequal slabs trade one cost for
+// the other: r01g sweep, 1M elements: equal 16: 2.39 ms; weights 1,2,3,4,4,4,4,3,2,1: 2.37; 1,1,2,4,8,8,4,2,1,1: 2.50; 1,3,9,9,9,3,1:
+// 2.51 (TB2_HOST_PLAN=<weights> or TB2_HOST_CHUNKS=<n> select other plans).
 static void build_host_plan(tb2_mesh* m, const int32_t* h_conn)
 {
     PipePlan& P = m->hplan;
-    int64_t C = 16;
+    std::vector<double> w;
+    const char* plan = getenv("TB2_HOST_PLAN");
     if (const char* s = getenv("TB2_HOST_CHUNKS")) {
         const int want = atoi(s);
-        if (want >= 1) C = want;
+        if (want >= 1) w.assign(want, 1.0);
     }
-    if (m->ne < 64 * C) C = 1;
-    const int64_t chunk = (m->ne + C - 1) / C;
+    if (w.empty()) {
+        if (plan && plan[0] >= '0' && plan[0] <= '9') { // explicit weights "1,2,4,..."
+            for (const char* q = plan; *q;) {
+                w.push_back(atof(q));
+                while (*q && *q != ',') q++;
+                if (*q == ',') q++;
+            }
+        } else w.assign(16, 1.0);
+    }
+    int64_t C = (int64_t)w.size();
+    if (m->ne < 64 * C) { C = 1; w.assign(1, 1.0); }
+    double wsum = 0.0;
+    for (double v : w) wsum += v;
     P.e0.assign(C + 1, 0);
     P.n0.assign(C + 1, 0);
+    double acc = 0.0;
     for (int64_t c = 0; c <= C; c++) {
-        P.e0[c] = c * chunk < m->ne ? c * chunk : m->ne;
-        P.n0[c] = m->nn * c / C;
+        P.e0[c] = c == C ? m->ne : (int64_t)(m->ne * (acc / wsum));
+        P.n0[c] = c == C ? m->nn : (int64_t)(m->nn * (acc / wsum));
+        if (c < C) acc += w[c];
     }
     P.emax_of_nc.assign(C, -1);
     P.nmax_of_ec.assign(C, -1);
+    int ce = 0;
     for (int64_t e = 0; e < m->ne; e++) {
-        const int ce = (int)(e / chunk);
+        while (ce + 1 < C && P.e0[ce + 1] <= e) ce++;
         for (int a = 0; a < 8; a++) {
             const int64_t n = h_conn[8 * e + a];
             int nc = (int)(n * C / m->nn);
