@@ -10,6 +10,7 @@
 #include "IsotropicT.h"
 #include "J2Simo3D.h"
 #include "MaterialListT.h"
+#include "OutputSetT.h"
 #include "ParameterListT.h"
 #include "SSKStV.h"
 #include "SimoIso3D.h"
@@ -57,7 +58,8 @@ CudaSolidElementT<BaseT>::CudaSolidElementT(const ElementSupportT& support, cons
 	fEqs(NULL),
 	fMatrix(NULL),
 	fIsJ2(false),
-	fMuted(false)
+	fMuted(false),
+	fMaterialKind(-1)
 {
 	this->SetName(name);
 }
@@ -186,6 +188,7 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 	const dArray2DT& X = this->ElementSupport().InitialCoordinates();
 	Check(tb2_mesh_create(0, X.MajorDim(), (int64_t)(conn.size() / 8), &conn[0], X.Pointer(), &fMesh), caller);
 	Check(tb2_group_create(fMesh, fFormulation, &mat, &fGroup), caller);
+	fMaterialKind = mat.kind;
 	fFint.Dimension(X.MajorDim(), 3);
 }
 
@@ -245,6 +248,41 @@ void CudaSolidElementT<BaseT>::LHSDriver(GlobalT::SystemTypeT sys_type)
 	Check(tb2_matrix_clear(fMatrix), caller);
 	Check(tb2_form_stiffness_host(fGroup, fMatrix, field[0].Pointer(), last, iteration), caller);
 	cuda_lhs->AddDeviceMatrix(fMatrix, constK);
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::ComputeOutput(const iArrayT& n_codes, dArray2DT& n_values, const iArrayT& e_codes, dArray2DT& e_values)
+{
+	const char caller[] = "CudaSolidElementT::ComputeOutput";
+	const int n_out = n_codes.Sum();
+	const bool device_material = fMaterialKind == TB2_SSKSTV || fMaterialKind == TB2_FDKSTV || fMaterialKind == TB2_SIMO_ISO;
+	const bool device_codes = e_codes.Sum() == 0 && n_out > 0 && n_codes[SolidElementT::iNodalStress] == 6 &&
+		n_out == n_codes[SolidElementT::iNodalDisp] + n_codes[SolidElementT::iNodalStress] &&
+		(n_codes[SolidElementT::iNodalDisp] == 0 || n_codes[SolidElementT::iNodalDisp] == 3);
+	if (!device_material || !device_codes || this->qUseSimo || this->qNoExtrap) {
+		BaseT::ComputeOutput(n_codes, n_values, e_codes, e_values);
+		return;
+	}
+	/* SolidElementT::ComputeOutput (SolidElementT.cpp:1352-1840) for [displacements | extrapolated stresses]: IP Cauchy stress,
+	 * HexahedronT::SetExtrapolation, GroupAverageT averaging -- one device call for the whole group */
+	const dArray2DT& disp = this->Field()[0];
+	dArray2DT stress(disp.MajorDim(), 6);
+	Check(tb2_group_nodal_stress_host(fGroup, disp.Pointer(), stress.Pointer()), caller);
+	static bool announced = false;
+	if (!announced) {
+		cout << "\n " << caller << ": nodal stresses extrapolated and averaged on the device" << endl;
+		announced = true;
+	}
+	const iArrayT& nodes_used = this->ElementSupport().OutputSet(this->fOutputID).NodesUsed();
+	const int ndisp = n_codes[SolidElementT::iNodalDisp];
+	n_values.Dimension(nodes_used.Length(), n_out);
+	for (int r = 0; r < nodes_used.Length(); r++) {
+		double* row = n_values(r);
+		const int node = nodes_used[r];
+		for (int i = 0; i < ndisp; i++) row[i] = disp(node, i);
+		for (int I = 0; I < 6; I++) row[ndisp + I] = stress(node, I);
+	}
+	e_values.Dimension(this->NumElements(), 0);
 }
 
 template <class BaseT>

@@ -80,6 +80,10 @@ protected:
 	/** tangent: device assembly when the solver's matrix is a CudaPCGMatrixT, else inherited */
 	virtual void LHSDriver(GlobalT::SystemTypeT sys_type);
 
+	/** nodal output: displacements and extrapolated, nodally averaged Cauchy stresses from the device (tb2_group_nodal_stress_host)
+	 * when nothing else is requested; any other combination of output codes runs SolidElementT::ComputeOutput on the host */
+	virtual void ComputeOutput(const iArrayT& n_codes, dArray2DT& n_values, const iArrayT& e_codes, dArray2DT& e_values);
+
 private:
 
 	void Check(int status, const char* caller) const;
@@ -92,6 +96,7 @@ private:
 	bool fIsJ2;
 	bool fMuted;           /**< see MuteInternalForce */
 	dArray2DT fFint;       /**< [nn][3] internal force of the whole group */
+	int fMaterialKind;     /**< tb2_material_kind */
 };
 
 typedef CudaSolidElementT<SmallStrainT> CudaSmallStrainT;

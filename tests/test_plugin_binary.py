@@ -72,6 +72,9 @@ def _cases():
                                 "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005}],
                                 "element": {"type": "small_strain", "strain_displacement": "B-bar"}, "material": dict(kstv, nu=0.49),
                                 "solver": newton}, pcg),
+        # nodal stress output through the plugin's ComputeOutput (device extrapolation + averaging)
+        "static_tl_simo_stress_out": ({"time": {"num_steps": 1, "time_step": 1.0, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                       "element": {"type": "total_lagrangian", "nodal_output": "stress"}, "material": simo_soft, "solver": newton}, pcg),
         "static_tl_simo_pcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                 "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": newton}, pcg),
         "static_tl_simo_nlpcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull,
@@ -90,7 +93,7 @@ def _write(work, name, desc, cuda, solver_override, n=5):
     if not os.path.exists(os.path.join(work, "mesh.geom")):
         ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
     d = dict(desc, geometry_file="mesh.geom", output_inc=desc["time"]["num_steps"])
-    d["element"] = dict(desc["element"], nodal_output=True)
+    d["element"] = dict(desc["element"], nodal_output=desc["element"].get("nodal_output", True))
     if cuda:
         d["element"]["tag"] = "cuda_" + desc["element"]["type"]
         if solver_override:
@@ -163,5 +166,9 @@ def test_plugin_reproduces_reference_output(name):
         assert np.abs(a - b).max() < tol * np.abs(a).max()
         if name.endswith("nlpcg"):
             assert "device PCG" in r1.stdout
+        if name.endswith("stress_out"):
+            assert a.shape[1] == 9 and "nodal stresses extrapolated and averaged on the device" in r1.stdout
+            for col in range(9):  # every column against its own scale: D_X D_Y D_Z s11 s22 s33 s23 s13 s12
+                assert np.abs(a[:, col] - b[:, col]).max() < 1e-9 * np.abs(a[:, col]).max()
     finally:
         shutil.rmtree(work, ignore_errors=True)
