@@ -429,6 +429,49 @@ def run_explicit_solid(torch, capi, tmesh, local, n, steps, warmup, hbm_peak, wi
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: UpdatedLagrangianT + J2Simo3D, implicit static step with the (matrix-free) nonlinear PCG
+# ---------------------------------------------------------------------------------------------------------------------
+def run_nlpcg_j2(torch, capi, tmesh, local, n, iters):
+    """one load step of the resident PCGSolver_LS twin (tb2_nlpcg_solve) on an n^3 J2 cube pulled past yield: `iters` nonlinear-CG
+    iterations (each 2-4 residual sweeps of the return-mapping kernel + preconditioner refreshes).  J2Simo3D's tangent is
+    non-symmetric (J2Simo3D.cpp:18-21), so the reference solves this config with LU or with PCG_solver; the latter is this path."""
+    X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+    m = capi.Mesh(X, conn, device=local)
+    mat = {"type": "Simo_J2", "E": 100.0, "nu": 0.25, "density": 1.0, "hardening": {"type": "linear_function", "a": 0.05, "b": 0.25}}  # mat.09.a.xml
+    g = capi.Group(m, capi.UPDATED_LAGRANGIAN, capi.material(mat))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    code[ns[2], 0] = 1
+    eqs = capi.Equations(m, code)
+    solver = capi.NonlinearPCG(g, eqs, capi.nlpcg_params(restart=30, line_search_iterations=10, line_search_tolerance=0.1, rel_tolerance=1e-30,
+                                                         abs_tolerance=1e-30, max_iterations=10 ** 6))
+    dev = torch.device("cuda", local)
+    u = np.zeros_like(X)
+    u[:, 0] = 0.02 * X[:, 0]   # 2 % stretch (well past yield: sigma_Y / E ~ 0.3 %), homogeneous start; the solver finds the lateral contraction
+    d_u = torch.from_numpy(u).to(dev)
+    d_ul = torch.zeros_like(d_u)
+    d_f = torch.zeros_like(d_u)
+    torch.cuda.synchronize()
+    st, it, err, err0 = solver.solve(d_u, d_f, d_ul, solve_max_iterations=2)  # warm-up (allocation of the yielded elements' history)
+    sw0, pc0 = solver.counters()
+    m.synchronize()
+    t0 = time.perf_counter()
+    st, it, err, err0 = solver.solve(d_u, d_f, d_ul, solve_max_iterations=iters)
+    m.synchronize()
+    dt = time.perf_counter() - t0
+    sw1, pc1 = solver.counters()
+    data, flags, alloc = (None, None, None)
+    n_alloc = int(g.get_history()[2].sum()) if n <= 64 else None
+    out = {"workload": "BASELINE.json configs[3] at %d^3=%d updated_lagrangian + Simo_J2 elements (E=100, nu=0.25, linear hardening 0.05 a + 0.25), "
+                       "2 %% stretch, %d equations; nonlinear PCG (restart 30, 10 line-search evaluations), device resident" % (n, conn.shape[0], eqs.neq),
+           "iterations": iters, "seconds": dt, "residual_sweeps": sw1 - sw0, "preconditioner_sweeps": pc1 - pc0,
+           "dof_iters_per_s": eqs.neq * iters / dt, "element_sweeps_per_s": conn.shape[0] * (sw1 - sw0) / dt,
+           "relative_residual": err / err0 if err0 > 0 else None, "yielded_elements": n_alloc}
+    solver.close(); eqs.close(); g.close(); m.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -618,7 +661,12 @@ def run_gpu_arm(args):
     xs = None
     if world == 1 and not args.no_explicit_solid:
         xs = run_explicit_solid(torch, capi, tmesh, local, n, min(args.steps, 200), args.warmup, hbm_peak_all, not args.no_cpu_baseline)
+    j2 = None
+    if world == 1 and args.nlpcg_n > 0:
+        j2 = run_nlpcg_j2(torch, capi, tmesh, local, args.nlpcg_n, args.nlpcg_iters)
     if rank == 0:
+        if j2:
+            line["nlpcg_j2"] = j2
         if xs:
             line["explicit_solid"] = xs
         if pcg:
@@ -639,6 +687,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the PCG DOF-iters/s leg")
     ap.add_argument("--no-explicit-solid", action="store_true", help="skip the <explicit_solid> leg (SURVEY.md 8f-1)")
+    ap.add_argument("--nlpcg-n", type=int, default=48, help="cube edge of the J2 nonlinear-PCG leg (configs[3]; 159 -> 4M elements; 0 = skip)")
+    ap.add_argument("--nlpcg-iters", type=int, default=20)
     ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")
     ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")
     ap.add_argument("--pcg-iters", type=int, default=100)
