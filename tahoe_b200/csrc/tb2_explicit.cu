@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "tb2_internal.h"
+#include "tb2_node_update.cuh"
 
 namespace tb2 {
 
@@ -19,23 +20,12 @@ int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, i
 int launch_node_gather(tb2_mesh* m, double* d_out, bool per_dof);
 int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d_ul, int iteration, int64_t e0, int64_t e1, cudaStream_t st,
                                 const int* d_elist = nullptr, const unsigned char* d_skip = nullptr);
+bool fused_step_supported(tb2_group* g);
+int launch_fused_forces_nodes(tb2_group* g, const double* d_u, int64_t e0, int64_t e1, cudaStream_t st, const NodeArgs& q,
+                              const unsigned char* d_skip);
 bool comm_active(tb2_mesh* m);
 bool comm_plan(tb2_mesh* m, CommPlan* out);
 int comm_allreduce_packed(tb2_mesh* m);
-
-// nExplicitCD::Predictor (nExplicitCD.cpp:72-96) / Corrector (:98-139) with explicit roundings, so that the stand-alone and
-// the fused kernels produce bit-identical fields
-TB2_DEV void cd_predict(double dt, double& d, double& v, double a)
-{
-    d = __fma_rn(dt, v, d);
-    d = __fma_rn(__dmul_rn(__dmul_rn(0.5, dt), dt), a, d);
-    v = __fma_rn(__dmul_rn(0.5, dt), a, v);
-}
-TB2_DEV void cd_correct(double dt, double& v, double& a, double upd)
-{
-    v = __fma_rn(__dmul_rn(0.5, dt), upd, v);
-    a = __dadd_rn(a, upd);
-}
 
 // predictor + ConsistentKBC, one thread per dof
 __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, double* __restrict__ d, double* __restrict__ v,
@@ -76,78 +66,8 @@ __global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t
 {
     const int64_t n = n_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= nn) return;
-    if (skip_slot && skip_slot[n] >= 0) return;
-    double f[3] = {0.0, 0.0, 0.0};
-    // nodal operands first: independent of the gather, in flight while it resolves its two dependent round trips
-    double fx[3], mi[3], vv[3], aa[3], dd[3] = {0.0, 0.0, 0.0};
-    unsigned char cc[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int64_t q = 3 * n + i;
-        cc[i] = code[q];
-        fx[i] = fext[q];
-        mi[i] = minv[q];
-        vv[i] = v[q];
-        aa[i] = a[q];
-        if (NEXT_PREDICTOR) dd[i] = d[q];
-    }
-    if (GATHER) {
-        int ent[8];
-        double g[8][3];
-        const int4 lo = __ldg(inc8 + 2 * n), hi = __ldg(inc8 + 2 * n + 1);
-        ent[0] = lo.x; ent[1] = lo.y; ent[2] = lo.z; ent[3] = lo.w;
-        ent[4] = hi.x; ent[5] = hi.y; ent[6] = hi.z; ent[7] = hi.w;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const bool on = ent[q] >= 0;
-            const int64_t e = ent[q] >> 3;
-            const int a3 = 3 * (ent[q] & 7);
-            g[q][0] = on ? __ldg(fe + (int64_t)(a3)*stride + e) : 0.0;
-            g[q][1] = on ? __ldg(fe + (int64_t)(a3 + 1) * stride + e) : 0.0;
-            g[q][2] = on ? __ldg(fe + (int64_t)(a3 + 2) * stride + e) : 0.0;
-        }
-        // ascending-element order = the reference's serial assembly order (SolverT::AssembleRHS, SolverT.cpp:446-477)
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (ent[q] >= 0) {
-                f[0] += g[q][0];
-                f[1] += g[q][1];
-                f[2] += g[q][2];
-            }
-        if (ent[7] >= 0) // an irregular vertex with more than 8 incident elements: the rest of its list
-            for (int k = inc_ptr[n] + 8, k1 = inc_ptr[n + 1]; k < k1; k++) {
-                const int en = __ldg(inc + k);
-                const int64_t e = en >> 3;
-                const int a3 = 3 * (en & 7);
-                f[0] += __ldg(fe + (int64_t)(a3)*stride + e);
-                f[1] += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
-                f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
-            }
-    } else {
-        f[0] = fint[3 * n];
-        f[1] = fint[3 * n + 1];
-        f[2] = fint[3 * n + 2];
-    }
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int64_t q = 3 * n + i;
-        const unsigned char c = cc[i];
-        const double R = __dsub_rn(__dmul_rn(fext_scale, fx[i]), f[i]);
-        const double upd = c ? 0.0 : __dmul_rn(R, mi[i]);
-        double vi = vv[i], ai = aa[i];
-        cd_correct(dt, vi, ai, upd);
-        if (GATHER) fint[q] = f[i];
-        if (NEXT_PREDICTOR) {
-            double di = dd[i];
-            cd_predict(dt, di, vi, ai);
-            ai = 0.0;
-            if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
-            else if (c == TB2_BC_DSP) di = next_value_scale * bcval[q];
-            d[q] = di;
-        }
-        v[q] = vi;
-        a[q] = ai;
-    }
+    cd_node_update_one<GATHER, NEXT_PREDICTOR>(n, inc_ptr, inc, inc8, fe, stride, dt, fext_scale, next_value_scale, fext, minv, code, bcval, d, v, a,
+                                               fint, skip_slot);
 }
 
 // Host-buffer step: k_cd_node_update<gather, no next predictor> that also writes v and a to the caller's (mapped, pinned) host
@@ -325,6 +245,82 @@ static int explicit_steps_pipelined(tb2_explicit* ex, double dt, int nsteps, con
         ProfScope ps(m, kProfPredictor);
         k_cd_predictor<<<(unsigned)((ndof + T - 1) / T), T, 0, m->stream>>>(ndof, dt, ex->d.p, ex->v.p, ex->a.p, ex->bccode.p, ex->bcval.p,
                                                                            vs ? vs[0] : 1.0);
+    }
+    // Experiment knob TB2_FUSED_STEP=1 (single GPU): fused element + node launches on ONE stream (see k_fused_force_update in
+    // tb2_elements.cu).  Bitwise the same fields (tested), but measured slower on B200, 1M elements: 0.299 ms/step with 4 slabs
+    // (0.333 / 0.376 / 0.512 with 8 / 16 / 32) against 0.266 for the two-stream form below -- a node CTA holds a third of an SM's
+    // registers under the sweep's 168-register allocation while it waits on memory, and back-to-back launches on one stream lose
+    // the tail filling the second stream provides.  Off by default.
+    static const bool fused_on = getenv("TB2_FUSED_STEP") && getenv("TB2_FUSED_STEP")[0] == '1';
+    if (!multi && fused_on && C >= 3 && fused_step_supported(g)) {
+        NodeArgs base{};
+        base.inc_ptr = m->inc_ptr.p;
+        base.inc = m->inc.p;
+        base.inc8 = (const int4*)m->inc8.p;
+        base.fe = m->fe.p;
+        base.stride = m->stride;
+        base.dt = dt;
+        base.fext = ex->fext.p;
+        base.minv = ex->minv.p;
+        base.code = ex->bccode.p;
+        base.bcval = ex->bcval.p;
+        base.d = ex->d.p;
+        base.v = ex->v.p;
+        base.a = ex->a.p;
+        base.fint = ex->fint.p;
+        base.skip_slot = nullptr;
+        NodeArgs pending = base; // node slabs whose forces are complete, waiting for a launch to ride on
+        int pending_first = -1;
+        auto flush_alone = [&]() -> int {
+            if (pending.n1 > pending.n0) {
+                ProfScope ps(m, kProfNodeUpdate);
+                const unsigned nb = (unsigned)((pending.n1 - pending.n0 + T - 1) / T);
+                if (pending.next_predictor)
+                    k_cd_node_update<true, true><<<nb, T, 0, m->stream>>>(pending.n0, pending.n1, base.inc_ptr, base.inc, base.inc8, base.fe, base.stride, dt,
+                                                                         pending.fext_scale, pending.next_value_scale, base.fext, base.minv, base.code,
+                                                                         base.bcval, base.d, base.v, base.a, base.fint, nullptr);
+                else
+                    k_cd_node_update<true, false><<<nb, T, 0, m->stream>>>(pending.n0, pending.n1, base.inc_ptr, base.inc, base.inc8, base.fe, base.stride, dt,
+                                                                          pending.fext_scale, 1.0, base.fext, base.minv, base.code, base.bcval, base.d,
+                                                                          base.v, base.a, base.fint, nullptr);
+            }
+            pending.n0 = pending.n1 = 0;
+            return TB2_OK;
+        };
+        for (int s = 0; s < nsteps; s++) {
+            const double fsc = fs ? fs[s] : 1.0;
+            int nc = 0;
+            for (int c = 0; c < C; c++) {
+                // the nodes carried over from the previous step must not be read by this element slab (c = 0 only)
+                if (c == 0 && pending.n1 > pending.n0 && pending_first <= m->pipe_nmax_of_ec[0]) TB2_CHECK(flush_alone());
+                TB2_CHECK(launch_fused_forces_nodes(g, ex->d.p, m->pipe_e0[c], m->pipe_e0[c + 1], m->stream, pending, nullptr));
+                pending.n0 = pending.n1 = 0;
+                const int first = nc;
+                for (; nc < C && m->pipe_emax_of_nc[nc] <= c; nc++) {}
+                if (nc > first) {
+                    pending = base;
+                    pending.n0 = m->pipe_n0[first];
+                    pending.n1 = m->pipe_n0[nc];
+                    pending.fext_scale = fsc;
+                    pending.next_predictor = s + 1 < nsteps ? 1 : 0;
+                    pending.next_value_scale = (s + 1 < nsteps && vs) ? vs[s + 1] : 1.0;
+                    pending_first = first;
+                }
+            }
+            if (nc < C) { // node slabs no element slab closes (cannot happen with monotone maps; kept for safety)
+                TB2_CHECK(flush_alone());
+                pending = base;
+                pending.n0 = m->pipe_n0[nc];
+                pending.n1 = m->pipe_n0[C];
+                pending.fext_scale = fsc;
+                pending.next_predictor = s + 1 < nsteps ? 1 : 0;
+                pending.next_value_scale = (s + 1 < nsteps && vs) ? vs[s + 1] : 1.0;
+                pending_first = nc;
+            }
+        }
+        TB2_CHECK(flush_alone());
+        TB2_CUDA(cudaGetLastError());
+        return TB2_OK;
     }
     // Experiment knob TB2_K1_STREAMS=2: consecutive element chunks alternate between two streams (they are independent of each
     // other; only the events order them against the node chunks), so that chunk c+1 fills the SMs the last wave of chunk c is
