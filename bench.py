@@ -356,10 +356,10 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
                        "assembled on the device (K3)%s, Jacobi-PCG with device-resident vectors"
                        % (n, n ** 3, world, int(ne_total), int(neq_total), " as sub-domain matrices" if world > 1 else ""),
            "assembly": {"ms": t_assembly_ms, "elements_per_s": ne_total / (t_assembly_ms * 1e-3), "structure_build_s": t_struct,
-                        "kernels": "k_element_stiffness (symmetric-half element matrices -> [element][576] scratch) + k_assemble_gather "
+                        "kernels": "k_element_stiffness (symmetric-half element matrices -> packed [element][300] scratch) + k_assemble_gather "
                                    "(ordered row gather into the CSR); no colouring, no atomics",
                         "fp64_tflops": K3_FLOP_PER_ELEMENT * conn.shape[0] / (t_assembly_ms * 1e-3) * 1e-12,
-                        "scratch_plus_matrix_gbs": (2 * 576 * 8.0 * conn.shape[0] + 2 * 8.0 * A.nnz) / (t_assembly_ms * 1e-3) * 1e-9},
+                        "scratch_plus_matrix_gbs": (2 * 300 * 8.0 * conn.shape[0] + 2 * 8.0 * A.nnz) / (t_assembly_ms * 1e-3) * 1e-9},
            "newton": newton,
            "roofline": {"bound": "hbm", "kernel": "k_spmv (K6)", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9, "peak": hbm_peak,
                         "unit": "GB/s", "frac": spmv_bytes / (spmv_ms * 1e-3) * 1e-9 / hbm_peak, "avg_launch_ms": spmv_ms,

@@ -218,8 +218,9 @@ struct tb2_matrix {
     // scratch of one element chunk; the node range each chunk touches
     int64_t nadj = 0;
     tb2::DevBuf<unsigned> contrib_ptr, contrib;
-    tb2::DevBuf<double> ke;        // [k3_chunk][576] element matrices of the current chunk
+    tb2::DevBuf<double> ke;        // [k3_chunk][k3_rec] element matrices of the current chunk (k3_rec = 300 packed upper triangle or 576)
     int64_t k3_chunk = 0;
+    int k3_rec = 0;
     std::vector<int> k3_nmin, k3_nmax;
 };
 

@@ -83,6 +83,9 @@ struct StiffArgs {
 
 static const int kElemsPerBlock = 16;
 static const int kIpDoubles = 24 + 36 + 6 + 2; // dN/dx[3][8], c[6][6], sigma[6], scale, pad
+// upper-triangle packing of a symmetric 24 x 24 element matrix: entry (r, c), r <= c, at r*24 - r(r-1)/2 + (c - r); 300 entries
+TB2_DEV int tri24(int r, int c) { return r * 24 - ((r * (r - 1)) >> 1) + (c - r); }
+static const int kSymEntries = 300;
 static const int kTilePitch = 577;            // element-matrix tile of the two-phase path: [16][577] doubles
 static const size_t kElemSmem = (size_t)kElemsPerBlock * kTilePitch * sizeof(double); // >= the integration-point tile (69,632 B)
 
@@ -273,7 +276,8 @@ __global__ void __launch_bounds__(128) k_stiffness(const StiffArgs p)
 //   kKSym  symmetric tangents (SSKStV, FDKStV, SimoIso3D): only the 36 node blocks (a, (a+k) & 7), k = 0..4 (k = 4 for a < 4
 //          only) are accumulated; each is stored together with its transpose, and the diagonal block from its upper triangle --
 //          the element matrix is exactly symmetric, as the reference's MultQTBQ(kUpperOnly) + CopySymmetric
-//          (SmallStrainT.cpp:285-324, ElementMatrixT::CopySymmetric) makes it.  29 % fewer FP64 instructions than all 64 blocks.
+//          (SmallStrainT.cpp:285-324, ElementMatrixT::CopySymmetric) makes it.  29 % fewer FP64 instructions than all 64 blocks;
+//          the scratch holds the packed upper triangle (300 entries per element).
 //   kKFull all 64 blocks (J2Simo3D: TangentType() == kNonSymmetric, J2Simo3D.cpp:18-21)
 //   kKDiag the 24 diagonal entries only, to fe[24][stride]: DiagonalMatrixT::Assemble in kDiagOnly mode
 //          (DiagonalMatrixT.cpp:107-113), the preconditioner of PCGSolver_LS
@@ -379,10 +383,12 @@ __global__ void __launch_bounds__(128, (MODE == kKFull || MAT == kJ2Simo) ? 2 : 
             for (int i = 0; i < 3; i++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = K[0][i][i];
         return;
     }
-    // the 16 element matrices of this CTA are laid out [element][row*24 + col] in shared memory (pitch 577: the 16 elements
-    // of a half-warp fall into distinct banks) and leave as one contiguous 73.7 kB block
+    // The 16 element matrices of this CTA are staged in shared memory and leave as one contiguous block.  Symmetric tangents keep
+    // the upper triangle only (300 of 576 entries, pitch 301: the 16 elements of a half-warp fall into distinct banks), which
+    // halves the scratch traffic of both phases; J2's non-symmetric matrices keep [row*24 + col] (pitch 577).
     __syncthreads(); // every thread is done reading the integration-point tile
-    double* tile = sm + el * kTilePitch;
+    constexpr int REC = MODE == kKSym ? kSymEntries : 576, PITCH = REC + 1;
+    double* tile = sm + el * PITCH;
 #pragma unroll
     for (int k = 0; k < NK; k++) {
         if (k >= nk) continue;
@@ -391,25 +397,28 @@ __global__ void __launch_bounds__(128, (MODE == kKFull || MAT == kJ2Simo) ? 2 : 
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                double v = K[k][i][j];
-                if (MODE == kKSym && k == 0 && j < i) v = K[0][j][i]; // diagonal block from its upper triangle
-                tile[(3 * a + i) * 24 + 3 * b + j] = v;
-                if (MODE == kKSym && k > 0) tile[(3 * b + j) * 24 + 3 * a + i] = v; // the transposed block (b, a)
+                const int r = 3 * a + i, c = 3 * b + j;
+                if (MODE == kKSym) {
+                    if (k == 0 && j < i) continue;                       // diagonal block: its upper triangle only
+                    tile[r <= c ? tri24(r, c) : tri24(c, r)] = K[k][i][j]; // block (a, b) with b < a is stored as its transpose
+                } else
+                    tile[r * 24 + c] = K[k][i][j];
             }
     }
     __syncthreads();
     const int64_t first = p.e0 + blockIdx.x * (int64_t)kElemsPerBlock;
     const int nlive = (int)(p.e1 - first < kElemsPerBlock ? p.e1 - first : kElemsPerBlock);
-    double* out = p.ke + (first - p.e0) * 576;
-    for (int idx = threadIdx.x; idx < nlive * 576; idx += 128) {
-        const int q = idx / 576;
-        out[idx] = sm[q * kTilePitch + (idx - q * 576)];
+    double* out = p.ke + (first - p.e0) * REC;
+    for (int idx = threadIdx.x; idx < nlive * REC; idx += 128) {
+        const int q = idx / REC;
+        out[idx] = sm[q * PITCH + (idx - q * REC)];
     }
 }
 
 struct GatherArgs {
     int64_t n0, n1;        // row nodes of this launch
-    int64_t e0, e1;        // element chunk held by the scratch ke[e - e0][576]
+    int64_t e0, e1;        // element chunk held by the scratch ke[e - e0][rec]
+    int sym;               // 1: records are packed upper triangles (300 entries), 0: full 24 x 24 (576)
     const double* ke;
     const int* adj_ptr;
     const int* adj;
@@ -459,9 +468,19 @@ __global__ void __launch_bounds__(32 * kGatherWarps) k_assemble_gather(const Gat
             const int64_t e = code >> 6;
             if (e >= g.e1) break;
             const int a = (code >> 3) & 7, b = code & 7;
-            const double* src = g.ke + (e - g.e0) * 576 + (3 * a) * 24 + 3 * b + j;
+            if (g.sym) {
+                const double* rec = g.ke + (e - g.e0) * kSymEntries;
+                const int cc = 3 * b + j;
 #pragma unroll
-            for (int i = 0; i < 3; i++) acc[i] += src[i * 24];
+                for (int i = 0; i < 3; i++) {
+                    const int r = 3 * a + i;
+                    acc[i] += rec[r <= cc ? tri24(r, cc) : tri24(cc, r)];
+                }
+            } else {
+                const double* src = g.ke + (e - g.e0) * 576 + (3 * a) * 24 + 3 * b + j;
+#pragma unroll
+                for (int i = 0; i < 3; i++) acc[i] += src[i * 24];
+            }
         }
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -562,9 +581,9 @@ static StiffArgs stiff_args(tb2_group* g, const double* d_u, const double* d_ul,
 // tails and revisiting the boundary rows cost more than the DRAM round trip of the scratch; running the gather of chunk c on a
 // second stream beside the element kernel of chunk c + 1 gained nothing either (4.1 ms with 4 chunks: the element kernel owns
 // the whole register file, the gather only runs in its tail).  So: the largest chunk that fits the scratch budget, one stream.
-static int ensure_gather_plan(tb2_matrix* A, elem_kernel_t k)
+static int ensure_gather_plan(tb2_matrix* A, elem_kernel_t k, int rec)
 {
-    if (A->k3_chunk > 0) return TB2_OK;
+    if (A->k3_chunk > 0 && A->k3_rec >= rec) return TB2_OK; // (a later group with a larger record re-plans)
     tb2_mesh* m = A->eqs->mesh;
     const int64_t ne = m->ne, nn = m->nn;
     if (ne >= (1LL << 26)) {
@@ -596,7 +615,7 @@ static int ensure_gather_plan(tb2_matrix* A, elem_kernel_t k)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 128, smem);
     if (occ < 1) occ = 1;
     const int64_t wave = (int64_t)sms * occ * kElemsPerBlock;
-    const int64_t budget = (int64_t)(6.0e9 / (576 * sizeof(double)));
+    const int64_t budget = (int64_t)(6.0e9 / (rec * sizeof(double)));
     const int64_t nch = (ne + budget - 1) / budget;
     int64_t chunk = ((ne + nch - 1) / nch + wave - 1) / wave * wave;
     bool forced = false; // an explicit TB2_K3_CHUNK is taken as is (tests: many chunks on a shuffled mesh)
@@ -623,7 +642,8 @@ static int ensure_gather_plan(tb2_matrix* A, elem_kernel_t k)
         if (forced || swept <= 4 * nn + 4096 || chunk >= ne_pad || chunk * 4 > budget) break;
         chunk *= 4;
     }
-    TB2_CUDA(A->ke.alloc((size_t)576 * chunk));
+    TB2_CUDA(A->ke.alloc((size_t)rec * chunk));
+    A->k3_rec = rec;
     A->k3_chunk = chunk;
     return TB2_OK;
 }
@@ -751,7 +771,7 @@ int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const dou
     DeviceGuard dg(m->device);
     elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, false, g->bbar);
     TB2_ARG(k != nullptr);
-    TB2_CHECK(ensure_gather_plan(A, k));
+    TB2_CHECK(ensure_gather_plan(A, k, g->mat.kind == TB2_J2_SIMO ? 576 : kSymEntries));
     if (g->mat.kind == TB2_J2_SIMO) {
         TB2_ARG(d_ul != nullptr);
         TB2_CHECK(launch_element_forces(g, d_u, d_ul, iteration)); // settles element allocation in the reference's order
@@ -760,6 +780,7 @@ int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const dou
     p.ke = A->ke.p;
     p.kstride = 576;
     GatherArgs ga;
+    ga.sym = g->mat.kind == TB2_J2_SIMO ? 0 : 1; // must match the MODE pick_elem_kernel chose (kKFull for J2, kKSym otherwise)
     ga.ke = A->ke.p;
     ga.adj_ptr = A->adj_ptr.p;
     ga.adj = A->adj.p;
