@@ -22,6 +22,7 @@
  */
 #ifndef TAHOE_B200_H
 #define TAHOE_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {

@@ -43,3 +43,20 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(capi.Tb2Error) as e:
         capi.Mesh(X, conn)
     assert e.value.code == 3  # TB2_ERR_CUDA
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/tahoe_b200.h must compile as C99 (no C++ types, no CUDA headers) and every
+    declared function must link against the shared library"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    names = _declared()
+    body = "\n".join("    p[%d] = (fn_t)%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "tahoe_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n    fn_t p[%d];\n%s\n'
+                   '    printf("%%s %%d\\n", tb2_version(), (int)(sizeof p / sizeof p[0]));\n    return p[0] == 0;\n}\n' % (len(names), body))
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(REPO, "tahoe_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-ltahoe_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout and str(len(names)) in out.stdout
