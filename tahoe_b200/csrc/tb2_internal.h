@@ -214,6 +214,11 @@ struct tb2_matrix {
     tb2::DevBuf<double> scal;     // reduction scalars
     tb2::DevBuf<double> partial;  // per-block partial sums
     tb2::DevBuf<unsigned char> eq_owned; // multi-GPU: 1 if this rank owns the equation's node (dot products count it once)
+    // CUDA graph of 16 PCG iterations (5 launches each) for the solution vector / tolerances it was captured with
+    cudaGraphExec_t pcg_exec = nullptr;
+    const double* pcg_x = nullptr;
+    double pcg_rtol = 0.0, pcg_atol = 0.0;
+    int pcg_maxit = 0;
     // two-phase assembly (tb2_stiffness.cu): contributions e*64+a*8+b of every node block, ascending in e; the element-matrix
     // scratch of one element chunk; the node range each chunk touches
     int64_t nadj = 0;
