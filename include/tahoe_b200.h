@@ -121,6 +121,10 @@ int tb2_group_status(tb2_group* group, int64_t* bad_element);
 /* ContinuumElementT::FormMass kLumpedMass (ContinuumElementT.cpp:767-842) summed to nodes: d_mass[nn][3] */
 int tb2_form_lumped_mass(tb2_group* group, double* d_mass);
 int tb2_form_lumped_mass_host(tb2_group* group, double* h_mass);
+/* ElementCardT status flags (ElementBaseT::SetStatus; the element loops skip ElementCardT::kOFF elements: SolidElementT.cpp:1116,
+ * 1177).  h_off[ne]: 1 = off, 0 = on; NULL = all on.  Off elements contribute no force, tangent or mass. */
+int tb2_group_set_element_status(tb2_group* group, const uint8_t* h_off);
+
 /* <explicit_solid> extras.  ExplicitElementT::ComputeStableTimeStep (ExplicitElementT.cpp:404-478): min over
  * the elements of h / c, h = cbrt of the three-diagonal volume estimate, c = sqrt((kappa + 4 mu / 3) / rho). */
 int tb2_group_stable_time_step(tb2_group* group, double* dt);

@@ -32,7 +32,7 @@ J2_BLOCK = 5 * 48 + 64  # doubles per element in the reference's ElementCardT la
 SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2_memcpy_h2d tb2_memcpy_d2h tb2_host_register
 tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
-tb2_form_lumped_mass_host tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
+tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
 tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
@@ -261,6 +261,10 @@ class Group(_Handle):
         m = np.zeros((self.mesh.nn, 3))
         _chk(lib().tb2_form_lumped_mass_host(self.h, _p(m)))
         return m
+
+    def set_element_status(self, off):
+        """ElementCardT::kOFF flags: off[ne] != 0 switches an element off (None: all on)"""
+        _chk(lib().tb2_group_set_element_status(self.h, None if off is None else _p(np.ascontiguousarray(np.asarray(off) != 0, np.uint8))))
 
     def stable_time_step(self):
         """ExplicitElementT::ComputeStableTimeStep"""

@@ -27,6 +27,7 @@ struct ElemArgs {
     int64_t e_begin, ne, stride; // elements [e_begin, ne), or entries [e_begin, ne) of elist
     const int* elist; // optional element index list (multi-GPU: the elements touching partition-interface nodes)
     const unsigned char* skip; // optional [ne] flags: elements a range launch leaves to the index-list launch
+    const unsigned char* off;  // optional [ne] flags: ElementCardT::kOFF elements contribute nothing (their scratch rows are zeroed)
     const int* conn;  // [8][stride]
     const double* X;  // [nn][3]
     const double* u;  // [nn][3]
@@ -43,6 +44,16 @@ TB2_DEV void report(const ElemArgs& p, int err, int64_t e)
 {
     atomicMax(p.status, (unsigned long long)err);
     atomicMin(p.status + 1, (unsigned long long)e);
+}
+
+// ElementCardT::kOFF (SolidElementT.cpp:1177, ElementRHSDriver: "if (CurrentElement().Flag() != ElementCardT::kOFF)"): the element
+// contributes nothing; its 24 scratch rows are zeroed so that the node gather adds zeros
+TB2_DEV bool element_is_off(const ElemArgs& p, const int64_t e)
+{
+    if (!(p.off && p.off[e])) return false;
+#pragma unroll
+    for (int r = 0; r < 24; r++) p.fe[(int64_t)r * p.stride + e] = 0.0;
+    return true;
 }
 
 // L1 prefetch of the nodal data (X and u triples) of the element a persistent thread will process next
@@ -221,6 +232,7 @@ TB2_DEV void internal_force_body(const ElemArgs& p, const unsigned cta = blockId
     if (t >= p.ne) return;
     const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
     if (p.skip && p.skip[e]) return;
+    if (element_is_off(p, e)) return;
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_persistent(const E
         if (has_next) e_next = p.elist ? (int64_t)__ldg(p.elist + t_next) : t_next;
 #pragma unroll
         for (int a = 0; a < 8; a++) n_next[a] = __ldg(p.conn + a * p.stride + e_next);
-        if (!(p.skip && p.skip[e])) internal_force_element<FORM, MAT, true>(p, e, n, n_next, has_next);
+        if (!(p.skip && p.skip[e]) && !element_is_off(p, e)) internal_force_element<FORM, MAT, true>(p, e, n, n_next, has_next);
         if (!has_next) break;
         t = t_next;
         e = e_next;
@@ -327,6 +339,7 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const Elem
     if (t >= p.ne) return;
     const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
     if (p.skip && p.skip[e]) return;
+    if (element_is_off(p, e)) return;
     {
         int n[8];
 #pragma unroll
@@ -437,6 +450,7 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_geo(const Ele
     if (t >= p.ne) return;
     const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
     if (p.skip && p.skip[e]) return;
+    if (element_is_off(p, e)) return;
     const double* geo = p.geo + e;
     double gq[7]; // M0[0..5], det0 of the current point; the next point's values are requested one iteration ahead
 #pragma unroll
@@ -609,11 +623,17 @@ __global__ void __launch_bounds__(256) k_node_average6(int64_t nn, const int* __
 // K4: ContinuumElementT::FormMass, kLumpedMass branch (ContinuumElementT.cpp:767-842).  me[a] -> fe[a][stride]
 __global__ void __launch_bounds__(128) k_lumped_mass(int64_t ne, int64_t stride, const int* __restrict__ conn,
                                                     const double* __restrict__ X, double density, double* __restrict__ fe,
-                                                    unsigned long long* status, const double* __restrict__ mass_scale = nullptr)
+                                                    unsigned long long* status, const double* __restrict__ mass_scale = nullptr,
+                                                    const unsigned char* __restrict__ off = nullptr)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= ne) return;
     if (mass_scale) density *= mass_scale[e]; // ExplicitElementT::LHSDriver: FormMass with density * fMassScale[e]
+    if (off && off[e]) { // ElementCardT::kOFF (SolidElementT.cpp:1116): no mass contribution
+#pragma unroll
+        for (int a = 0; a < 8; a++) fe[(int64_t)a * stride + e] = 0.0;
+        return;
+    }
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(conn + a * stride + e);
@@ -850,6 +870,7 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
     p.u = d_u;
     p.ul = d_ul;
     p.fe = m->fe.p;
+    p.off = g->off.p;
     p.geo = g->geo.p;
     p.mat = g->mc;
     p.hist = group_hist(g);
@@ -922,6 +943,7 @@ int launch_fused_forces_nodes(tb2_group* g, const double* d_u, int64_t e0, int64
     p.ne = e1;
     p.stride = m->stride;
     p.skip = d_skip;
+    p.off = g->off.p;
     p.conn = m->conn.p;
     p.X = m->X.p;
     p.u = d_u;
@@ -1099,6 +1121,22 @@ static int explicit_solid_dt(tb2_group* g, double target, std::vector<double>* h
     return TB2_OK;
 }
 
+int tb2_group_set_element_status(tb2_group* g, const uint8_t* h_off)
+{
+    TB2_ARG(g);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    if (!h_off) {
+        g->off.release();
+        return TB2_OK;
+    }
+    if (!g->off.p) TB2_CUDA(g->off.alloc(m->stride));
+    TB2_CUDA(cudaMemset(g->off.p, 0, m->stride));
+    TB2_CUDA(cudaMemcpy(g->off.p, h_off, m->ne, cudaMemcpyHostToDevice));
+    return TB2_OK;
+}
+
 int tb2_group_stable_time_step(tb2_group* g, double* dt)
 {
     TB2_ARG(g && dt);
@@ -1156,6 +1194,10 @@ int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
         set_error("nodal stress output is implemented for SSKStV, FDKStV and SimoIso3D (material %d)", g->mat.kind);
         return TB2_ERR_ARG;
     }
+    if (g->off.p) {
+        set_error("nodal stress output with switched-off elements is not implemented (the averaging counts would differ)");
+        return TB2_ERR_ARG;
+    }
     if (!m->out48.p) TB2_CUDA(m->out48.alloc((size_t)48 * m->stride));
     ElemArgs p{};
     p.e_begin = 0;
@@ -1196,7 +1238,7 @@ int tb2_form_lumped_mass(tb2_group* g, double* d_mass)
     const int T = 128;
     ProfScope ps(m, kProfOther);
     k_lumped_mass<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(m->ne, m->stride, m->conn.p, m->X.p, g->mat.density, m->fe.p,
-                                                                       g->status.p, g->mass_scale.p);
+                                                                       g->status.p, g->mass_scale.p, g->off.p);
     TB2_CUDA(cudaGetLastError());
     return launch_node_gather(m, d_mass, false);
 }

@@ -186,6 +186,7 @@ struct tb2_group {
     tb2::DevBuf<int> hist_alloc;   // [stride]
     tb2::DevBuf<unsigned long long> status; // [0] error code, [1] first bad element
     tb2::DevBuf<double> mass_scale; // [ne] ExplicitElementT::fMassScale (null: no mass scaling)
+    tb2::DevBuf<unsigned char> off; // [ne] 1 = ElementCardT::kOFF: the element loops skip it (null: every element is on)
     tb2::DevBuf<double> geo;       // [8][7][stride] M0 = adj(J0) adj(J0)^T and det J0 per integration point (finite-strain SimoIso3D fast path)
 };
 

@@ -65,6 +65,7 @@ struct StiffArgs {
     J2Hist hist;
     int iteration;
     unsigned long long* status;
+    const unsigned char* off; // [ne] 1 = ElementCardT::kOFF: zero element matrix
     // colour slice
     const int* elems; // element ids of this colour
     int64_t count;
@@ -177,7 +178,7 @@ TB2_DEV void stiffness_point(const StiffArgs& p, const int64_t e, const int (&n)
             for (int Jj = 0; Jj < 6; Jj++) SM(ip, 24 + I * 6 + Jj) = c[I][Jj];
 #pragma unroll
         for (int I = 0; I < 6; I++) SM(ip, 60 + I) = sig[I];
-        SM(ip, 66) = scale;
+        SM(ip, 66) = (p.off && p.off[e]) ? 0.0 : scale; // ElementCardT::kOFF (SolidElementT.cpp:1116): weight 0, so K_e = 0 exactly
 }
 #undef SM
 
@@ -573,6 +574,7 @@ static StiffArgs stiff_args(tb2_group* g, const double* d_u, const double* d_ul,
     p.hist = group_hist(g);
     p.iteration = iteration;
     p.status = g->status.p;
+    p.off = g->off.p;
     return p;
 }
 
@@ -741,6 +743,7 @@ static int form_stiffness_coloured(tb2_group* g, tb2_matrix* A, const double* d_
     p.hist = group_hist(g);
     p.iteration = iteration;
     p.status = g->status.p;
+    p.off = g->off.p;
     p.eqnos = A->eqs->eqnos.p;
     p.rowptr = A->rowptr.p;
     p.adj_coloff = A->adj_coloff.p;

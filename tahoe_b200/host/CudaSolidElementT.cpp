@@ -305,6 +305,20 @@ tb2_equations* CudaSolidElementT<BaseT>::DeviceEquations(void)
 }
 
 template <class BaseT>
+void CudaSolidElementT<BaseT>::SetStatus(const ArrayT<ElementCardT::StatusT>& status)
+{
+	BaseT::SetStatus(status);
+	if (!fGroup) return;
+	std::vector<uint8_t> off(status.Length());
+	bool any = false;
+	for (int i = 0; i < status.Length(); i++) {
+		off[i] = status[i] == ElementCardT::kOFF ? 1 : 0;
+		any = any || off[i];
+	}
+	Check(tb2_group_set_element_status(fGroup, any ? &off[0] : NULL), "CudaSolidElementT::SetStatus");
+}
+
+template <class BaseT>
 void CudaSolidElementT<BaseT>::CloseStep(void)
 {
 	BaseT::CloseStep();

@@ -58,6 +58,10 @@ public:
 	/** build the device mesh / element group after Tahoe has read connectivity and materials */
 	virtual void TakeParameterList(const ParameterListT& list);
 
+	/** element status flags (ElementCardT::kOFF elements are skipped by the element loops, SolidElementT.cpp:1116,1177): mirrored
+	 * on the device */
+	virtual void SetStatus(const ArrayT<ElementCardT::StatusT>& status);
+
 	/** \name history */
 	/*@{*/
 	virtual void CloseStep(void);

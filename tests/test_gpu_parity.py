@@ -171,6 +171,38 @@ def test_empty_ragged_and_mismatched_inputs_are_rejected(tb2):
     assert e.value.code in (4, 5)
 
 
+def test_switched_off_elements_contribute_nothing(tb2, oracle):
+    """ElementCardT::kOFF: the element loops skip the element (SolidElementT.cpp:1116, 1177).  Force, lumped mass, tangent and the
+    explicit step with some elements switched off equal the oracle on the mesh without those elements (same node arrays)."""
+    X, conn, ns, u = _synthetic((6, 5, 5))
+    rng = np.random.default_rng(2)
+    off = rng.random(conn.shape[0]) < 0.2
+    off[:3] = True
+    conn_on = np.ascontiguousarray(conn[~off])
+    desc = {"type": "Simo_isotropic", "E": 100.0, "nu": 0.25, "density": 1.5}
+    omat = oracle.material(desc)
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.TOTAL_LAGRANGIAN, tb2.material(desc))
+    f_all = grp.internal_force_host(u)
+    grp.set_element_status(off)
+    err, f_ref = oracle.internal_force(oracle.TOTAL_LAGRANGIAN, omat, conn_on, X, u)
+    f = grp.internal_force_host(u)
+    assert err == 0 and relerr(f, f_ref) < TOL and relerr(f, f_all) > 1e-3
+    assert relerr(grp.lumped_mass_host(), oracle.lumped_mass(1.5, conn_on, X)) < 1e-13
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    eq, neq = oracle.equation_numbers(code)
+    rp, ci = oracle.csr_structure(conn, eq, neq)       # the sparsity keeps the off elements' slots (structure is set up once)
+    err, kv = oracle.assemble_stiffness(oracle.TOTAL_LAGRANGIAN, omat, conn_on, X, u, eq, neq, rp, ci)
+    A = tb2.Matrix(tb2.Equations(mesh, code))
+    A.form_stiffness_host(grp, u)
+    assert err == 0 and relerr(A.csr()[2], kv) < TOL
+    diag = grp.stiffness_diagonal_host(u)
+    assert relerr(diag[eq > 0], sp.csr_matrix((kv, ci, rp), shape=(neq, neq)).diagonal()) < TOL
+    grp.set_element_status(None)                        # all on again
+    assert np.array_equal(grp.internal_force_host(u), f_all)
+
+
 def test_lumped_mass_matches_oracle(tb2, oracle):
     X, conn, _, _ = _synthetic()
     mesh = tb2.Mesh(X, conn)
