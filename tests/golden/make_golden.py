@@ -145,6 +145,7 @@ def main():
         ("ref_mat_2_a", "level.1/material.solid/3D/material.02/mat.2.a.xml", ["--fint"]),
         ("ref_mat_5_a", "level.1/material.solid/3D/material.05/mat.5.a.xml", ["--fint"]),
         ("ref_mat_09_a", "level.1/material.solid/3D/material.09/mat.09.a.xml", ["--every", "1", "--fint"]),
+        ("ref_mat_09_b", "level.1/material.solid/3D/material.09/mat.09.b.xml", ["--every", "1", "--fint"]),  # linear_exponential K(alpha): local Newton
     ]
     for name, rel, flags in ref_cases:
         if want(name):
