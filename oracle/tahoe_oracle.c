@@ -1435,3 +1435,11 @@ int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_
     free(count);
     return ORC_OK;
 }
+
+/* one evaluation of the <explicit_solid> laws for known-answer tests (the reference's tests/materials/test_ExplJ2Plasticity.cpp calls
+ * ExplJ2PlasticityT::ComputeStress3D the same way): F row-major, h[16] updated in place (EXPL_J2 only), sig Voigt 11,22,33,23,13,12 */
+void orc_explicit_material_stress(const orc_material_t* m, const double* F, double* h, double* sig)
+{
+    if (m->kind == ORC_EXPL_J2) xs_j2(m, F, h, sig);
+    else xs_neo_hookean(m, F, sig);
+}

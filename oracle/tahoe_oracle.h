@@ -120,6 +120,8 @@ double orc_explicit_solid_stable_dt(const orc_material_t* m, int64_t ne, const i
 void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, double target_dt,
                                    double scale_factor, double* scale /*[ne]*/);
 int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass);
+/* one material evaluation (known-answer tests): F row-major [9], h[16] in/out (EXPL_J2), sig[6] */
+void orc_explicit_material_stress(const orc_material_t* m, const double* F, double* h, double* sig);
 
 /* nodal Cauchy stress as SolidElementT::ComputeOutput writes it (extrapolated with HexahedronT::SetExtrapolation,
  * averaged over the elements at a node); SSKStV (incl. B-bar), FDKStV, SimoIso3D.  out[nn][6], order 11,22,33,23,13,12 */

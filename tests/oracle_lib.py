@@ -262,3 +262,10 @@ def nodal_stress(form, mat, conn, X, u):
     err = lib().orc_nodal_stress(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), C.c_int64(X.shape[0]), _p(X),
                                  _p(np.ascontiguousarray(u)), _p(out))
     return err, out
+
+
+def explicit_material_stress(mat, F, h=None):
+    """one evaluation of ExplNeoHookeanT / ExplJ2PlasticityT (F 3x3 row-major; h[16] updated in place for the J2 law)"""
+    sig = np.zeros(6)
+    lib().orc_explicit_material_stress(C.byref(mat), _p(np.ascontiguousarray(F, np.float64).ravel()), _p(h), _p(sig))
+    return sig
