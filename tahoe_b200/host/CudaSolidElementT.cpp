@@ -260,6 +260,8 @@ void CudaSolidElementT<BaseT>::ComputeOutput(const iArrayT& n_codes, dArray2DT& 
 		n_out == n_codes[SolidElementT::iNodalDisp] + n_codes[SolidElementT::iNodalStress] &&
 		(n_codes[SolidElementT::iNodalDisp] == 0 || n_codes[SolidElementT::iNodalDisp] == 3);
 	if (!device_material || !device_codes || this->qUseSimo || this->qNoExtrap) {
+		/* host output of a Simo_J2 group evaluates J2Simo3D at the integration points: it needs the converged history */
+		if (fIsJ2) HistoryToCards();
 		BaseT::ComputeOutput(n_codes, n_values, e_codes, e_values);
 		return;
 	}
@@ -331,6 +333,66 @@ GlobalT::RelaxCodeT CudaSolidElementT<BaseT>::ResetStep(void)
 	GlobalT::RelaxCodeT relax = BaseT::ResetStep();
 	if (fGroup) Check(tb2_group_reset_step(fGroup), "CudaSolidElementT::ResetStep");
 	return relax;
+}
+
+/* J2SimoC0HardeningT keeps 8 flags and 5*48 + 64 doubles per element, allocated at the first plastic step (AllocateElement
+ * :312-333); tb2_group_get_history returns exactly that layout, so the cards written here are what the classic element would hold */
+static const int kJ2CardInts = 8, kJ2CardDoubles = 5 * 48 + 64;
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::HistoryToCards(void) const
+{
+	const char caller[] = "CudaSolidElementT::HistoryToCards";
+	if (!fIsJ2 || !fGroup) return;
+	const int ne = this->fElementCards.Length();
+	std::vector<double> data((size_t) ne * kJ2CardDoubles);
+	std::vector<int32_t> flags((size_t) ne * kJ2CardInts), alloc(ne);
+	Check(tb2_group_get_history(fGroup, &data[0], &flags[0], &alloc[0]), caller);
+	for (int e = 0; e < ne; e++) {
+		if (!alloc[e]) continue;
+		ElementCardT& card = const_cast<ElementCardT&>(this->fElementCards[e]);
+		card.Dimension(kJ2CardInts, kJ2CardDoubles);
+		for (int i = 0; i < kJ2CardInts; i++) card.IntegerData()[i] = flags[(size_t) e * kJ2CardInts + i];
+		memcpy(card.DoubleData().Pointer(), &data[(size_t) e * kJ2CardDoubles], sizeof(double) * kJ2CardDoubles);
+	}
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::HistoryFromCards(void)
+{
+	const char caller[] = "CudaSolidElementT::HistoryFromCards";
+	if (!fIsJ2 || !fGroup) return;
+	const int ne = this->fElementCards.Length();
+	std::vector<double> data((size_t) ne * kJ2CardDoubles, 0.0);
+	std::vector<int32_t> flags((size_t) ne * kJ2CardInts, 0), alloc(ne, 0);
+	for (int e = 0; e < ne; e++) {
+		const ElementCardT& card = this->fElementCards[e];
+		if (!card.IsAllocated()) continue;
+		if (card.IntegerData().Length() != kJ2CardInts || card.DoubleData().Length() != kJ2CardDoubles)
+			ExceptionT::SizeMismatch(caller, "element %d: restart data is not a Simo_J2 Hex8 record", e + 1);
+		alloc[e] = 1;
+		for (int i = 0; i < kJ2CardInts; i++) flags[(size_t) e * kJ2CardInts + i] = card.IntegerData()[i];
+		memcpy(&data[(size_t) e * kJ2CardDoubles], card.DoubleData().Pointer(), sizeof(double) * kJ2CardDoubles);
+	}
+	Check(tb2_group_set_history(fGroup, &data[0], &flags[0], &alloc[0]), caller);
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::ReadRestart(istream& in)
+{
+	BaseT::ReadRestart(in); /* status flags + element cards */
+	HistoryFromCards();
+	/* status flags may have changed */
+	ArrayT<ElementCardT::StatusT> status(this->fElementCards.Length());
+	for (int i = 0; i < status.Length(); i++) status[i] = this->fElementCards[i].Flag();
+	SetStatus(status);
+}
+
+template <class BaseT>
+void CudaSolidElementT<BaseT>::WriteRestart(ostream& out) const
+{
+	HistoryToCards();
+	BaseT::WriteRestart(out);
 }
 
 /* explicit instantiation */

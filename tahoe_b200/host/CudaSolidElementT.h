@@ -2,7 +2,7 @@
  * the C ABI of libtahoe_b200.so (include/tahoe_b200.h).
  *
  * The class template derives from Tahoe's own SmallStrainT / TotalLagrangianT / UpdatedLagrangianT, so the XML
- * parameters, material lists, output, mass matrix and restart code are inherited unchanged and an input file differs
+ * parameters, material lists, output, mass matrix and restart format are inherited unchanged and an input file differs
  * from a classic one by the element tag only (<total_lagrangian> -> <cuda_total_lagrangian>, <explicit_solid> ->
  * <cuda_explicit_solid>).  What is replaced is the
  * per-element virtual-call loop:
@@ -10,6 +10,8 @@
  *   LHSDriver()  : SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154)  -> tb2_form_stiffness into the
  *                  device CSR of a cooperating CudaPCGMatrixT; any other matrix type keeps Tahoe's host assembly
  *   CloseStep()/ResetStep() : J2 history commit / reset on the device.
+ *   ReadRestart()/WriteRestart() and host-side output of a Simo_J2 group: the device-resident history is moved through the
+ *                  group's ElementCardT storage, so restart files are interchangeable with the classic element's.
  * Results leave through ElementSupportT::AssembleRHS (ElementSupportT.h:43) with the field's equation array, i.e. one
  * call for the whole group instead of one per element.
  */
@@ -66,6 +68,9 @@ public:
 	/*@{*/
 	virtual void CloseStep(void);
 	virtual GlobalT::RelaxCodeT ResetStep(void);
+	/** restart files in ContinuumElementT's format (ContinuumElementT.cpp:217-249): the device J2 history passes through the element cards */
+	virtual void ReadRestart(istream& in);
+	virtual void WriteRestart(ostream& out) const;
 	/*@}*/
 
 	virtual tb2_mesh* DeviceMesh(void) { return fMesh; }
@@ -91,6 +96,11 @@ protected:
 private:
 
 	void Check(int status, const char* caller) const;
+
+	/** device J2 history -> ElementCardT storage in J2SimoC0HardeningT's layout (AllocateElement :312-333, LoadData :429-452) */
+	void HistoryToCards(void) const;
+	/** ElementCardT storage -> device */
+	void HistoryFromCards(void);
 
 	int fFormulation;
 	tb2_mesh* fMesh;

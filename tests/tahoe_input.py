@@ -215,7 +215,8 @@ def parse_xml(path):
 
 def write_xml(path, d):
     t = d["time"]
-    L = ['<?xml version="1.0"?>', '<tahoe geometry_file="%s">' % d["geometry_file"],
+    top = "".join(' %s="%s"' % kv for kv in d.get("tahoe_attrs", {}).items())  # restart_file / restart_output_inc (FEManagerT.cpp:1412-1419)
+    L = ['<?xml version="1.0"?>', '<tahoe geometry_file="%s"%s>' % (d["geometry_file"], top),
          '  <time num_steps="%d" output_inc="%d" time_step="%.17g">' % (t["num_steps"], d.get("output_inc", 0), t["time_step"])]
     for s in t["schedules"]:
         L.append("    <schedule_function><piecewise_linear>")

@@ -82,13 +82,16 @@ def _cases():
                                   "element": {"type": "total_lagrangian"}, "material": simo_soft, "solver": nlpcg}, cuda_nlpcg),
         "static_ul_j2_nlpcg": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                 "element": {"type": "updated_lagrangian"}, "material": j2, "solver": nlpcg}, cuda_nlpcg),
+        # J2 stress output: the host ComputeOutput evaluates J2Simo3D from the element cards, which the plugin fills from the device history
+        "static_ul_j2_host_stress_out": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                          "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": j2, "solver": newton}, None),
         # J2: device K1 with history, Tahoe's host tangent + SPOOLES (non-symmetric tangent)
         "static_ul_j2_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                              "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton}, None),
     }
 
 
-def _write(work, name, desc, cuda, solver_override, n=5):
+def _write(work, name, desc, cuda, solver_override, n=5, tahoe_attrs=None, suffix=""):
     X, conn, ns = ti.structured_cube(n, jitter=0.15)
     if not os.path.exists(os.path.join(work, "mesh.geom")):
         ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
@@ -98,7 +101,9 @@ def _write(work, name, desc, cuda, solver_override, n=5):
         d["element"]["tag"] = "cuda_" + desc["element"]["type"]
         if solver_override:
             d["solver"] = solver_override
-    path = os.path.join(work, name + (".cuda" if cuda else ".ref") + ".xml")
+    if tahoe_attrs:
+        d["tahoe_attrs"] = tahoe_attrs
+    path = os.path.join(work, name + (".cuda" if cuda else ".ref") + suffix + ".xml")
     ti.write_xml(path, d)
     return path
 
@@ -167,8 +172,42 @@ def test_plugin_reproduces_reference_output(name):
         if name.endswith("nlpcg"):
             assert "device PCG" in r1.stdout
         if name.endswith("stress_out"):
-            assert a.shape[1] == 9 and "nodal stresses extrapolated and averaged on the device" in r1.stdout
+            assert a.shape[1] == 9
+            assert ("nodal stresses extrapolated and averaged on the device" in r1.stdout) == (not name.endswith("host_stress_out"))
             for col in range(9):  # every column against its own scale: D_X D_Y D_Z s11 s22 s33 s23 s13 s12
                 assert np.abs(a[:, col] - b[:, col]).max() < 1e-9 * np.abs(a[:, col]).max()
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("writer", ["ref", "cuda"])
+def test_plugin_restart_files_are_interchangeable_with_the_reference(writer):
+    """SURVEY 8(f)-2 restart hand-off: a Simo_J2 run is stopped after step 2 of 3 by one executable and finished from the restart
+    file by the other (FEManagerT::WriteRestart/ReadRestart, FEManagerT.cpp:2086-2240; ContinuumElementT.cpp:217-249 element
+    records).  The device-resident plastic history has to survive the hand-off in both directions."""
+    desc, _ = _cases()["static_ul_j2_lu"]
+    work = tempfile.mkdtemp(prefix="tb2_restart_")
+    try:
+        full = _write(work, "full", desc, False, None)
+        r = _run(REF_BIN, full)
+        assert r.returncode == 0, r.stdout[-2000:]
+        want = _nodal_output(os.path.join(work, "full.ref.io0.run"))
+        bins = {"ref": REF_BIN, "cuda": PLUGIN_BIN}
+        reader = "cuda" if writer == "ref" else "ref"
+        first = _write(work, "first", desc, writer == "cuda", None, tahoe_attrs={"restart_output_inc": "2"})
+        r = _run(bins[writer], first)
+        assert r.returncode == 0, r.stdout[-2000:]
+        rs = "first.%s.rs2of3" % writer
+        assert os.path.exists(os.path.join(work, rs)) and os.path.exists(os.path.join(work, rs + ".elem0"))
+        # the element record holds allocated (yielded) elements: "1" lines followed by "<flag> 8 304"
+        elem = open(os.path.join(work, rs + ".elem0")).read()
+        assert " 8 304" in elem
+        second = _write(work, "second", desc, reader == "cuda", None, tahoe_attrs={"restart_file": rs})
+        r = _run(bins[reader], second)
+        assert r.returncode == 0 and "Restart file" in r.stdout, r.stdout[-3000:]
+        got = _nodal_output(os.path.join(work, "second.%s.io0.run" % reader))
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-9 * np.abs(want).max()
     finally:
         shutil.rmtree(work, ignore_errors=True)
