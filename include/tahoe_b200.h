@@ -65,6 +65,7 @@ typedef struct tb2_mesh      tb2_mesh;      /* device-resident connectivity + re
 typedef struct tb2_group     tb2_group;     /* one continuum-solid element group (SolidElementT subclass + its material + history) */
 typedef struct tb2_equations tb2_equations; /* equation numbers + sparsity (FieldT::fEqnos, MSRBuilderT) */
 typedef struct tb2_matrix    tb2_matrix;    /* device CSR global matrix (GlobalMatrixT subclass; MSRMatrixT semantics) */
+typedef struct tb2_traction  tb2_traction;  /* natural_bc traction cards of one element group (ContinuumElementT::fTractionList) */
 typedef struct tb2_explicit  tb2_explicit;  /* d, v, a, lumped mass, BCs on device: FieldT + nExplicitCD + DiagonalMatrixT */
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -150,6 +151,20 @@ int tb2_group_reset_step(tb2_group* group);
  * h_data[ne][5*48+64] doubles, h_flags[ne][8], h_alloc[ne] (restart hand-off, ContinuumElementT.cpp:217-249) */
 int tb2_group_get_history(tb2_group* group, double* h_data, int32_t* h_flags, int32_t* h_alloc);
 int tb2_group_set_history(tb2_group* group, const double* h_data, const int32_t* h_flags, const int32_t* h_alloc);
+
+/* ---- natural_bc tractions: ContinuumElementT::ApplyTractionBC (ContinuumElementT.cpp:514-665).
+ * One card per loaded element facet, as ContinuumElementT::TakeNaturalBC builds them (:1008-1123): h_elem[ncards] element in the
+ * group (0-based), h_facet[ncards] facet 0..5 in HexahedronT::NodesOnFacet numbering (HexahedronT.cpp:1913-1918; the .geom side-set
+ * value minus one), h_tract[ncards][4][3] traction vectors at the four facet nodes in facet-node order, coord_system as
+ * Traction_CardT::CoordSystemT.  tb2_traction_form integrates the cards on the initial coordinates with the traction scaled by
+ * `scale` (the schedule value, Traction_CardT::CurrentValue) and sums them into d_f[nn][3] in card order (accumulate != 0: added
+ * to d_f, else d_f is overwritten).  A degenerate facet with a local frame returns TB2_ERR_BAD_JACOBIAN. */
+enum { TB2_TRACTION_GLOBAL = 0 /* Traction_CardT::kCartesian */, TB2_TRACTION_LOCAL = 1 /* kLocal: (t1, t2, normal) */ };
+int tb2_traction_create(tb2_mesh* mesh, int64_t ncards, const int32_t* h_elem, const int32_t* h_facet, const double* h_tract,
+                        int coord_system, tb2_traction** traction);
+int tb2_traction_destroy(tb2_traction* traction);
+int tb2_traction_form(tb2_traction* traction, double scale, int accumulate, double* d_f);
+int tb2_traction_form_host(tb2_traction* traction, double scale, int accumulate, double* h_f);
 
 /* ---- explicit central difference (nExplicitCD.cpp:72-139, DiagonalMatrixT.cpp:267-323, FieldT.cpp:531-556) */
 int tb2_explicit_create(tb2_group* group, tb2_explicit** ex); /* forms and inverts the lumped mass */

@@ -1443,3 +1443,66 @@ void orc_explicit_material_stress(const orc_material_t* m, const double* F, doub
     if (m->kind == ORC_EXPL_J2) xs_j2(m, F, h, sig);
     else xs_neo_hookean(m, F, sig);
 }
+
+/* ---- natural_bc tractions: ContinuumElementT::ApplyTractionBC (ContinuumElementT.cpp:514-665) on Hex8 facets ------------------
+ * facet nodes HexahedronT::NodesOnFacet (HexahedronT.cpp:1913-1918); 4-node quad facet shape with the 2x2 rule the hexahedron gets
+ * (DomainIntegrationT.cpp:117-131; QuadT.cpp:75-81,379-389, weights 1); surface Jacobian |x,r x x,s| on the INITIAL coordinates
+ * (LocalArrayT::kInitCoords, :533) and, for coordinate_system="local", Q = [x,r/|x,r| , n x t1 , n] (ParentDomainT.cpp:362-422).
+ * tract[card][4][3] are the nodal traction vectors (Traction_CardT, already in facet-node order), scale = schedule value. */
+int orc_traction_force(int64_t ncards, const int32_t* elem, const int32_t* facet, const int32_t* conn, const double* X,
+                       const double* tract, int coord_system, double scale, double* f)
+{
+    static const int fn[6][4] = {{0, 3, 2, 1}, {4, 5, 6, 7}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}};
+    static const double qr[4] = {-1.0, 1.0, 1.0, -1.0}, qs[4] = {-1.0, -1.0, 1.0, 1.0};
+    const double g = 1.0 / sqrt(3.0);
+    for (int64_t c = 0; c < ncards; c++) {
+        if (facet[c] < 0 || facet[c] > 5) return -1;
+        int node[4];
+        double x[4][3], t[4][3], rhs[4][3];
+        for (int a = 0; a < 4; a++) {
+            node[a] = conn[elem[c] * 8 + fn[facet[c]][a]];
+            for (int i = 0; i < 3; i++) {
+                x[a][i] = X[node[a] * 3 + i];
+                t[a][i] = scale * tract[(c * 4 + a) * 3 + i];
+                rhs[a][i] = 0.0;
+            }
+        }
+        for (int j = 0; j < 4; j++) {
+            const double r = g * qr[j], s = g * qs[j];
+            double Na[4], m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0}, tip[3] = {0, 0, 0};
+            for (int a = 0; a < 4; a++) {
+                const double tr = 1.0 + qr[a] * r, ts = 1.0 + qs[a] * s;
+                Na[a] = 0.25 * tr * ts;
+                const double dr = 0.25 * qr[a] * ts, ds = 0.25 * tr * qs[a];
+                for (int i = 0; i < 3; i++) {
+                    m1[i] += x[a][i] * dr;
+                    m2[i] += x[a][i] * ds;
+                    tip[i] += Na[a] * t[a][i];
+                }
+            }
+            double n3[3] = {m1[1] * m2[2] - m1[2] * m2[1], m1[2] * m2[0] - m1[0] * m2[2], m1[0] * m2[1] - m1[1] * m2[0]};
+            const double jn = sqrt(n3[0] * n3[0] + n3[1] * n3[1] + n3[2] * n3[2]);
+            double tj[3] = {tip[0], tip[1], tip[2]};
+            if (coord_system == 1) { /* Traction_CardT::kLocal */
+                const double j1 = sqrt(m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2]);
+                if (jn <= 0.0 || j1 <= 0.0) return ORC_BAD_JACOBIAN;
+                double n1[3], n2[3];
+                for (int i = 0; i < 3; i++) {
+                    n3[i] /= jn;
+                    n1[i] = m1[i] / j1;
+                }
+                n2[0] = n3[1] * n1[2] - n3[2] * n1[1];
+                n2[1] = n3[2] * n1[0] - n3[0] * n1[2];
+                n2[2] = n3[0] * n1[1] - n3[1] * n1[0];
+                for (int i = 0; i < 3; i++) tj[i] = n1[i] * tip[0] + n2[i] * tip[1] + n3[i] * tip[2];
+            }
+            for (int l = 0; l < 3; l++) {
+                const double fact = jn * tj[l]; /* weights are 1 */
+                for (int a = 0; a < 4; a++) rhs[a][l] += fact * Na[a];
+            }
+        }
+        for (int a = 0; a < 4; a++)
+            for (int i = 0; i < 3; i++) f[node[a] * 3 + i] += rhs[a][i];
+    }
+    return ORC_OK;
+}

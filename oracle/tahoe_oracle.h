@@ -120,6 +120,10 @@ double orc_explicit_solid_stable_dt(const orc_material_t* m, int64_t ne, const i
 void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, double target_dt,
                                    double scale_factor, double* scale /*[ne]*/);
 int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass);
+/* natural_bc tractions (ContinuumElementT::ApplyTractionBC, ContinuumElementT.cpp:514-665): f[nn][3] += consistent nodal forces of
+ * ncards facet cards (elem, facet 0-based; tract[card][4][3] nodal traction vectors in facet-node order; coord_system 0 global, 1 local) */
+int orc_traction_force(int64_t ncards, const int32_t* elem, const int32_t* facet, const int32_t* conn, const double* X,
+                       const double* tract, int coord_system, double scale, double* f);
 /* one material evaluation (known-answer tests): F row-major [9], h[16] in/out (EXPL_J2), sig[6] */
 void orc_explicit_material_stress(const orc_material_t* m, const double* F, double* h, double* sig);
 

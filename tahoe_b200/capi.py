@@ -33,6 +33,7 @@ SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2
 tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
 tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
+tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
 tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
@@ -305,6 +306,27 @@ class Group(_Handle):
     def set_history(self, data, flags, alloc):
         data, flags, alloc = _f64(data), np.ascontiguousarray(flags, np.int32), np.ascontiguousarray(alloc, np.int32)
         _chk(lib().tb2_group_set_history(self.h, _p(data), _p(flags), _p(alloc)))
+
+
+class Traction(_Handle):
+    """natural_bc traction cards of a group (ContinuumElementT::ApplyTractionBC): elem / facet 0-based [ncards], tract [ncards][4][3]
+    (or one vector [3] for all cards and nodes), coord_system "global" | "local" """
+    _destroy = "tb2_traction_destroy"
+
+    def __init__(self, mesh, elem, facet, tract, coord_system="global"):
+        elem = np.ascontiguousarray(elem, np.int32)
+        facet = np.ascontiguousarray(facet, np.int32)
+        tract = _f64(np.broadcast_to(np.asarray(tract, np.float64), (elem.shape[0], 4, 3)))
+        self.mesh = mesh
+        self._init_handle(mesh)
+        _chk(lib().tb2_traction_create(mesh.h, C.c_int64(elem.shape[0]), _p(elem), _p(facet), _p(tract),
+                                       {"global": 0, "local": 1}[coord_system], C.byref(self.h)))
+
+    def form_host(self, scale=1.0, out=None):
+        """nodal forces [nn][3]; added to `out` when given"""
+        f = np.zeros((self.mesh.nn, 3)) if out is None else _f64(out)
+        _chk(lib().tb2_traction_form_host(self.h, C.c_double(scale), 0 if out is None else 1, _p(f)))
+        return f
 
 
 class Explicit(_Handle):

@@ -40,7 +40,7 @@ def load_dump(d):
     return out
 
 
-def run_case(name, xml_path, flags, desc, coords, conn, nodesets):
+def run_case(name, xml_path, flags, desc, coords, conn, nodesets, sidesets=None):
     out = tempfile.mkdtemp(prefix="dump_")
     r = subprocess.run([DUMP, os.path.basename(xml_path), out] + flags, cwd=os.path.dirname(xml_path),
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -54,6 +54,10 @@ def run_case(name, xml_path, flags, desc, coords, conn, nodesets):
     payload = {"desc": np.array(json.dumps(desc))}
     for sid, ids in nodesets.items():
         payload["ns_%d" % sid] = np.asarray(ids, np.int32)
+    used = {nb["side_set"] for nb in desc["element"].get("natural_bc") or []}
+    for sid, sides in (sidesets or {}).items():
+        if sid in used:
+            payload["ss_%d" % sid] = np.asarray(sides, np.int32)
     for k, v in dump.items():
         payload["ref_" + k] = v
     if desc["element"].get("nodal_output") == "stress":
@@ -76,8 +80,9 @@ def reference_case(name, rel_xml, flags):
     xml = os.path.join(work, "lvl", os.path.basename(src_dir), os.path.basename(rel_xml))
     desc = ti.parse_xml(xml)
     desc["source"] = "benchmark_XML/" + rel_xml
-    coords, conn, nodesets = ti.read_geom(os.path.normpath(os.path.join(os.path.dirname(xml), desc["geometry_file"])))
-    run_case(name, xml, flags, desc, coords, conn, nodesets)
+    geom = os.path.normpath(os.path.join(os.path.dirname(xml), desc["geometry_file"]))
+    coords, conn, nodesets = ti.read_geom(geom)
+    run_case(name, xml, flags, desc, coords, conn, nodesets, ti.read_sidesets(geom))
     shutil.rmtree(work)
 
 
@@ -104,13 +109,21 @@ def synthetic_case(name, n, desc, flags, jitter=0.1):
     work = tempfile.mkdtemp(prefix="syn_")
     dims = n if isinstance(n, tuple) else (n, n, n)
     coords, conn, nodesets = ti.structured_cube(*dims, jitter=jitter, seed=12345)
-    ti.write_geom(os.path.join(work, "mesh.geom"), coords, conn, nodesets)
+    sidesets = None
+    if desc["element"].get("natural_bc"):  # traction cases: curved faces, side sets in the .geom
+        coords = ti.warp(coords)
+        sidesets = ti.cube_side_sets(*dims)
+    ti.write_geom(os.path.join(work, "mesh.geom"), coords, conn, nodesets, sidesets=sidesets)
     coords, conn2, nodesets2 = ti.read_geom(os.path.join(work, "mesh.geom"))  # what the reference will read
     assert np.array_equal(conn, conn2)
     desc = dict(desc, geometry_file="mesh.geom", source="synthetic %dx%dx%d jitter %g seed 12345" % (*dims, jitter))
     xml = os.path.join(work, name + ".xml")
     ti.write_xml(xml, desc)
-    run_case(name, xml, flags, desc, coords, conn, nodesets2)
+    if sidesets:
+        back = ti.read_sidesets(os.path.join(work, "mesh.geom"))
+        assert all(np.array_equal(back[k], sidesets[k]) for k in sidesets)
+        desc["source"] += " warped"
+    run_case(name, xml, flags, desc, coords, conn, nodesets2, sidesets)
     shutil.rmtree(work)
 
 
@@ -202,6 +215,18 @@ def main():
         ("syn_ul_fdkstv_stress", 3, {"time": static(1), "integrator": "static", "kbc": pull_u(0.15), "fbc": [], "output_inc": 1,
                                      "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": fdkstv, "solver": NEWTON},
          ["--fint"]),
+        # natural_bc tractions on curved faces: a follower-free pressure-like load in the facet frame with a different
+        # vector at each facet node, plus a constant global shear on another face
+        ("syn_tl_simo_traction", 3, {"time": static(2), "integrator": "static", "kbc": CLAMP_X0, "fbc": [],
+                                     "element": {"type": "total_lagrangian", "natural_bc": [
+                                         {"side_set": 2, "schedule": 1, "coordinate_system": "local",
+                                          "values": [[0.3, 0.1, -2.0], [0.2, 0.0, -2.5], [0.1, -0.1, -3.0], [0.0, 0.2, -1.5]]},
+                                         {"side_set": 6, "schedule": 1, "coordinate_system": "global", "values": [[0.0, 0.5, 0.25]]}]},
+                                     "material": simo_soft, "solver": NEWTON}, ["--every", "1", "--fint"]),
+        ("syn_ss_kstv_traction", 4, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
+                                     "element": {"type": "small_strain", "natural_bc": [
+                                         {"side_set": 4, "schedule": 1, "coordinate_system": "local", "values": [[0.0, 0.0, -1.0]]}]},
+                                     "material": kstv, "solver": NEWTON}, ["--fint", "--lhs"]),
         # a21: nonlinear PCG (PCGSolver_LS) -- linear, finite-strain and J2 cases
         ("syn_ss_kstv_pcg", 3, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
                                 "element": {"type": "small_strain"}, "material": kstv, "solver": PCG}, ["--fint"]),

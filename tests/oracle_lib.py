@@ -269,3 +269,16 @@ def explicit_material_stress(mat, F, h=None):
     sig = np.zeros(6)
     lib().orc_explicit_material_stress(C.byref(mat), _p(np.ascontiguousarray(F, np.float64).ravel()), _p(h), _p(sig))
     return sig
+
+
+def traction_force(conn, X, elem, facet, tract, coord_system="global", scale=1.0, out=None):
+    """ContinuumElementT::ApplyTractionBC: nodal forces [nn][3] of the facet cards (tract [ncards][4][3] or one vector)"""
+    conn = np.ascontiguousarray(conn, np.int32)
+    elem = np.ascontiguousarray(elem, np.int32)
+    facet = np.ascontiguousarray(facet, np.int32)
+    tract = np.ascontiguousarray(np.broadcast_to(np.asarray(tract, np.float64), (elem.shape[0], 4, 3)))
+    f = np.zeros_like(X) if out is None else out
+    err = lib().orc_traction_force(C.c_int64(elem.shape[0]), _p(elem), _p(facet), _p(conn), _p(np.ascontiguousarray(X)), _p(tract),
+                                   {"global": 0, "local": 1}[coord_system], C.c_double(scale), _p(f))
+    assert err == 0, err
+    return f

@@ -62,10 +62,33 @@ def structured_cube(nx, ny=None, nz=None, jitter=0.1, seed=12345, lengths=(1.0, 
     return coords, conn, {s: v.astype(np.int32) for s, v in nodesets.items()}
 
 
+def cube_side_sets(nx, ny=None, nz=None):
+    """side sets of structured_cube as {id: [[element, facet], ...]} (0-based; facets in HexahedronT::NodesOnFacet numbering,
+    HexahedronT.cpp:1913-1918), ids as the node sets: 1: x=0, 2: x=L, 3: y=0, 4: y=L, 5: z=0, 6: z=L"""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    ek, ej, ei = [a.ravel() for a in np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")]
+    e = np.arange(nx * ny * nz)
+    pick = {1: (ei == 0, 5), 2: (ei == nx - 1, 3), 3: (ej == 0, 2), 4: (ej == ny - 1, 4), 5: (ek == 0, 0), 6: (ek == nz - 1, 1)}
+    return {sid: np.stack([e[m], np.full(m.sum(), f)], axis=1).astype(np.int32) for sid, (m, f) in pick.items()}
+
+
+def warp(coords):
+    """smooth map that keeps the x = 0 face fixed and makes every other face of the unit cube curved (non-planar facets,
+    non-constant surface Jacobians for the traction tests)"""
+    x, y, z = coords[:, 0].copy(), coords[:, 1].copy(), coords[:, 2].copy()
+    out = coords.copy()
+    out[:, 0] += 0.08 * x * (y - 0.5) * (z + 0.3)
+    out[:, 1] += 0.12 * x * z * (1.0 - 0.5 * y)
+    out[:, 2] += 0.10 * x * x * y
+    return out
+
+
 # ----------------------------------------------------------------------------
 # TahoeII .geom
 # ----------------------------------------------------------------------------
-def write_geom(path, coords, conn, nodesets, title="structured hex block"):
+def write_geom(path, coords, conn, nodesets, title="structured hex block", sidesets=None):
+    sidesets = sidesets or {}
     nn, ne = coords.shape[0], conn.shape[0]
     with open(path, "w") as f:
         f.write("*version\n1.0\n*title\n%s\n*dimensions\n" % title)
@@ -74,13 +97,23 @@ def write_geom(path, coords, conn, nodesets, title="structured hex block"):
         f.write("%d  # number of node sets\n# [ID] [nnd]\n" % len(nodesets))
         for sid in sorted(nodesets):
             f.write("%d %d\n" % (sid, len(nodesets[sid])))
-        f.write("0  # number of side sets\n# end dimensions\n*nodesets\n")
+        f.write("%d  # number of side sets\n" % len(sidesets))
+        if sidesets:
+            f.write("# [ID] [element set ID] [ns]\n")
+        for sid in sorted(sidesets):
+            f.write("%d 1 %d\n" % (sid, len(sidesets[sid])))
+        f.write("# end dimensions\n*nodesets\n")
         for sid in sorted(nodesets):
             ids = np.asarray(nodesets[sid]) + 1
             f.write("*set\n%d  # number of nodes\n" % len(ids))
             for s in range(0, len(ids), 10):
                 f.write(" ".join(str(int(v)) for v in ids[s:s + 10]) + "\n")
-        f.write("# end node sets\n*sidesets\n*elements\n*set\n%d  # number of elements\n8  # number of element nodes\n" % ne)
+        f.write("# end node sets\n*sidesets\n")
+        for sid in sorted(sidesets):  # [element in its block] [facet], both 1-based
+            f.write("*set\n%d  # number of sides\n" % len(sidesets[sid]))
+            for e, fc in sidesets[sid]:
+                f.write("%d %d\n" % (e + 1, fc + 1))
+        f.write("*elements\n*set\n%d  # number of elements\n8  # number of element nodes\n" % ne)
         for e in range(ne):
             f.write("%d %s\n" % (e + 1, " ".join(str(int(v) + 1) for v in conn[e])))
         f.write("# end elements\n*nodes\n%d  # number of nodes\n3  # number of spatial dimensions\n" % nn)
@@ -146,6 +179,27 @@ def read_geom(path):
     return coords, np.concatenate(conns).astype(np.int32), nodesets
 
 
+def read_sidesets(path):
+    """side sets of a single-block .geom as {id: [[element, facet], ...]} 0-based (ModelManagerT::SideSet)"""
+    tok = _tokens(path)
+    p = tok.index("*dimensions") + 1
+    nblocks = int(tok[p + 2])
+    p += 3 + 3 * nblocks
+    nns = int(tok[p]); p += 1 + 2 * nns
+    nss = int(tok[p]); p += 1
+    dims = []
+    for _ in range(nss):
+        dims.append((int(tok[p]), int(tok[p + 1]), int(tok[p + 2]))); p += 3
+    p = tok.index("*sidesets") + 1
+    out = {}
+    for sid, _blk, _cnt in dims:
+        assert tok[p] == "*set"; p += 1
+        cnt = int(tok[p]); p += 1
+        out[sid] = np.array([int(v) - 1 for v in tok[p:p + 2 * cnt]], dtype=np.int32).reshape(cnt, 2)
+        p += 2 * cnt
+    return out
+
+
 # ----------------------------------------------------------------------------
 # XML parameter tree (hot-path subset)
 # ----------------------------------------------------------------------------
@@ -177,7 +231,11 @@ def parse_xml(path):
             break
     d["element"] = {"type": el.tag, "mass_type": el.get("mass_type", "automatic"),
                     "strain_displacement": el.get("strain_displacement", "standard"),
-                    "natural_bc": el.find("natural_bc") is not None}
+                    # ContinuumElementT::TakeNaturalBC (ContinuumElementT.cpp:1008-1095): 1 vector for the whole facet or one per facet node
+                    "natural_bc": [{"side_set": int(nb.get("side_set_ID")), "schedule": int(nb.get("schedule")),
+                                    "coordinate_system": nb.get("coordinate_system", "global"),
+                                    "values": [[float(x.get("value")) for x in dl.findall("Double")] for dl in nb.findall("DoubleList")]}
+                                   for nb in el.findall("natural_bc")]}
     mat = None
     for m in el.iter():
         if m.tag in MATERIAL_TAGS:
@@ -241,6 +299,11 @@ def write_xml(path, d):
     if e.get("strain_displacement", "standard") != "standard":  # SmallStrainT only (SmallStrainT.cpp:38-42)
         mass += ' strain_displacement="%s"' % e["strain_displacement"]
     L.append('    <%s field_name="displacement"%s>\n      <hexahedron/>' % (e.get("tag", e["type"]), mass))
+    for nb in e.get("natural_bc") or []:
+        L.append('      <natural_bc schedule="%d" side_set_ID="%d" coordinate_system="%s">' % (nb["schedule"], nb["side_set"], nb["coordinate_system"]))
+        for vec in nb["values"]:
+            L.append("        <DoubleList>" + "".join('<Double value="%.17g"/>' % v for v in vec) + "</DoubleList>")
+        L.append("      </natural_bc>")
     if e.get("nodal_output"):
         L.append('      <solid_element_nodal_output displacements="1"%s/>' % (' stress="1"' if e["nodal_output"] == "stress" else ""))
     small = e["type"] == "small_strain"
@@ -284,8 +347,22 @@ def schedule_value(sched, t):
     return float(np.interp(t, xs, ys))
 
 
+def traction_cards(desc, sidesets):
+    """natural_bc lists -> [(elem, facet, tract[ncards,4,3], coordinate_system, schedule index)] as ContinuumElementT::TakeNaturalBC
+    builds the cards (one per side, the same nodal vectors for every side of a set)"""
+    out = []
+    for nb in desc["element"].get("natural_bc") or []:
+        sides = sidesets[nb["side_set"]]
+        vals = np.asarray(nb["values"], np.float64)
+        nodal = np.broadcast_to(vals, (4, 3)) if vals.shape[0] == 1 else vals
+        out.append((sides[:, 0].copy(), sides[:, 1].copy(), np.broadcast_to(nodal, (len(sides), 4, 3)).copy(),
+                    nb["coordinate_system"], nb["schedule"] - 1))
+    return out
+
+
 def bc_arrays(desc, nodesets, nn, t):
-    """(code[nn,3] uint8: 0 free / 1 fixed / 2 prescribed-u, value[nn,3], fext[nn,3]) at time t"""
+    """(code[nn,3] uint8: 0 free / 1 fixed / 2 prescribed-u, value[nn,3], fext[nn,3]) at time t (nodal forces only; tractions are
+    added by cases.Case.bc through the implementation under test)"""
     code = np.zeros((nn, 3), np.uint8)
     val = np.zeros((nn, 3))
     fext = np.zeros((nn, 3))

@@ -8,7 +8,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import tahoe_input as ti
-from cases import PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import TRACTION, PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -25,6 +25,11 @@ def tb2():
 def _group(tb2, c):
     mesh = tb2.Mesh(c.X, c.conn)
     mat = tb2.material(c.desc["material"])
+
+    def device_traction(conn, X, elem, facet, tract, system, scale, out):  # natural_bc loads of the case: formed on the device
+        out[:] = tb2.Traction(mesh, elem, facet, tract, system).form_host(scale, out=out)
+
+    c.traction_fn = device_traction
     return mesh, tb2.Group(mesh, tb2.form_of(c.desc["element"]), mat), mat
 
 
@@ -628,7 +633,7 @@ def _newton_gpu(tb2, c, linear_solve):
         yield k, d, it, grp
 
 
-@pytest.mark.parametrize("name", [n for n in STATIC if n != "ref_traction_a"])
+@pytest.mark.parametrize("name", STATIC)
 def test_native_newton_driver_matches_reference(tb2, name):
     """a20: NLSolver::Solve as one C-ABI call (tb2_newton_solve_host: K1 residuals, K3 tangent, device PCG, update) against the
     reference's Newton + direct-solver runs: same Newton iteration counts, displacements to 1e-10"""
@@ -664,7 +669,7 @@ def _solve_direct(A, R):
     return spla.spsolve(sp.csr_matrix((val, colind, rowptr), shape=(A.neq, A.neq)).tocsc(), R)
 
 
-@pytest.mark.parametrize("name", [n for n in STATIC if n != "ref_traction_a" and "j2" not in n and "09" not in n])
+@pytest.mark.parametrize("name", [n for n in STATIC if "j2" not in n and "09" not in n])
 def test_static_newton_pcg_matches_reference(tb2, name):
     """device K1 + K3 + Jacobi-PCG inside the reference's Newton loop reproduces the reference's displacements"""
     c = Case(name)
@@ -693,6 +698,59 @@ def test_static_newton_j2_matches_reference(tb2, name):
     assert sel.sum() > 0
     assert np.abs(data[sel] - ref[sel]).max() < 1e-10
     assert np.array_equal(flags[sel], c.ref("j2_flags")[sel])
+
+
+# ------------------------------------------------------------------ natural_bc tractions
+@pytest.mark.parametrize("name", TRACTION)
+def test_traction_force_matches_oracle_and_reference(tb2, oracle, name):
+    """ContinuumElementT::ApplyTractionBC on the device: equal to the oracle's restatement card by card, and in balance with the
+    reference's internal force at its converged state on every free dof"""
+    c = Case(name)
+    mesh, grp, _ = _group(tb2, c)
+    t_end = c.nsteps * c.dt
+    _, _, fext = c.bc(t_end)
+    c.traction_fn = oracle.traction_force
+    _, _, want = c.bc(t_end)
+    assert np.abs(want).max() > 1e-3 and relerr(fext, want) < 1e-13
+    ref_eq = c.ref("eqnos")
+    rhs = np.zeros_like(fext)
+    rhs[ref_eq > 0] = c.ref("rhs")[ref_eq[ref_eq > 0] - 1]
+    assert np.abs(fext - c.ref("fint") - rhs)[ref_eq > 0].max() < TOL * np.abs(fext).max()
+
+
+def test_traction_properties_and_errors(tb2, oracle):
+    """size-independent properties on a warped 20^3 block: a unit normal traction in the facet frame over the closed surface sums
+    to zero force (divergence theorem), a constant global traction sums to traction x area, accumulation and scaling are linear,
+    repeated evaluations return the same bits; bad cards are rejected"""
+    n = 20
+    X, conn, _ = ti.structured_cube(n, jitter=0.1)
+    X = ti.warp(X)
+    sides = np.concatenate(list(ti.cube_side_sets(n).values()))
+    mesh = tb2.Mesh(X, conn)
+    press = tb2.Traction(mesh, sides[:, 0], sides[:, 1], [0.0, 0.0, -1.0], "local")
+    f = press.form_host(2.5)
+    assert np.abs(f).max() > 1e-4 and np.abs(f.sum(axis=0)).max() < 1e-13
+    assert np.array_equal(f, press.form_host(2.5))
+    assert relerr(f, oracle.traction_force(conn, X, sides[:, 0], sides[:, 1], [0.0, 0.0, -1.0], "local", 2.5)) < 1e-13
+    top = ti.cube_side_sets(n)[6]
+    shear = tb2.Traction(mesh, top[:, 0], top[:, 1], [0.3, -0.2, 0.1], "global")
+    g = shear.form_host(1.0)
+    one = oracle.traction_force(conn, X, top[:, 0], top[:, 1], [1.0, 0.0, 0.0], "global")[:, 0].sum()  # = area of the curved face
+    assert np.abs(g.sum(axis=0) - one * np.array([0.3, -0.2, 0.1])).max() < 1e-12 * one
+    both = shear.form_host(1.0, out=f.copy())
+    assert relerr(both, f + g) < 1e-15
+    empty = tb2.Traction(mesh, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 4, 3)))
+    assert np.all(empty.form_host() == 0.0)
+    with pytest.raises(tb2.Tb2Error):
+        tb2.Traction(mesh, [conn.shape[0]], [0], [1.0, 0.0, 0.0])
+    with pytest.raises(tb2.Tb2Error):
+        tb2.Traction(mesh, [0], [6], [1.0, 0.0, 0.0])
+    flat = X.copy()
+    flat[conn[0, [1, 2, 6, 5]]] = flat[conn[0, 1]]  # collapse facet 3 of element 0 to a point
+    bad = tb2.Traction(tb2.Mesh(flat, conn), [0], [3], [0.0, 0.0, 1.0], "local")
+    with pytest.raises(tb2.Tb2Error) as e:
+        bad.form_host()
+    assert e.value.code == 1
 
 
 # ------------------------------------------------------------------ size-independent properties at larger sizes

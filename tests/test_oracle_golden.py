@@ -5,13 +5,15 @@ import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from cases import PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+import tahoe_input as ti
+from cases import TRACTION, PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 TOL = 1e-10  # north_star: forces / displacements agree to 1e-10 relative
 
 
 def _setup(oracle, name):
     c = Case(name)
+    c.traction_fn = oracle.traction_force  # natural_bc cases: ContinuumElementT::ApplyTractionBC restated in the oracle
     form = oracle.form_of(c.desc["element"])
     mat = oracle.material(c.desc["material"])
     return c, form, mat
@@ -37,10 +39,13 @@ def test_internal_force_matches_reference(oracle, name):
     err, f = oracle.internal_force(form, mat, c.conn, c.X, d)
     assert err == 0
     assert relerr(f, c.ref("fint")) < TOL
-    if not c.renumbered and not c.desc["element"].get("natural_bc") and c.desc["integrator"] == "static":
+    if c.desc["integrator"] == "static":
+        # FormRHS at the final state on the active equations: external load (nodal forces + natural_bc tractions) minus fint
         code, _, fext = c.bc(c.nsteps * c.dt)
-        eq, _ = oracle.equation_numbers(code)
-        assert np.abs((fext - f)[eq > 0] - c.ref("rhs")).max() < TOL * max(np.abs(f).max(), 1.0)
+        ref_eq = c.ref("eqnos")  # the reference's own numbering (profile_matrix renumbers)
+        rhs = np.zeros_like(f)
+        rhs[ref_eq > 0] = c.ref("rhs")[ref_eq[ref_eq > 0] - 1]
+        assert np.abs((fext - f)[ref_eq > 0] - rhs[ref_eq > 0]).max() < TOL * max(np.abs(f).max(), 1.0)
 
 
 @pytest.mark.parametrize("name", WITH_LHS)
@@ -184,7 +189,7 @@ def _direct(rowptr, colind, kv, R):
     return spla.spsolve(sp.csr_matrix((kv, colind, rowptr), shape=(n, n)).tocsc(), R)
 
 
-@pytest.mark.parametrize("name", [n for n in STATIC if n != "ref_traction_a"])
+@pytest.mark.parametrize("name", STATIC)
 def test_static_newton_matches_reference(oracle, name):
     """displacements, Newton iteration counts and (J2) committed history vs the reference's Newton + direct solve"""
     c, form, mat = _setup(oracle, name)
@@ -203,6 +208,26 @@ def test_static_newton_matches_reference(oracle, name):
                 assert np.abs(j2[e][nm] - data[e, 48 * i:48 * (i + 1)].reshape(8, 6)).max() < 1e-10
             assert np.abs(j2[e]["internal"] - data[e, 240:].reshape(8, 8)).max() < 1e-10
             assert np.array_equal(j2[e]["flag"], flags[e])
+
+
+@pytest.mark.parametrize("name", TRACTION)
+def test_traction_force_balances_reference_internal_force(oracle, name):
+    """8(f)-4: at the reference's converged state its internal force equals the external load on every free dof, so the traction
+    integral (ContinuumElementT::ApplyTractionBC restated) is pinned by the reference's own fint and residual dumps"""
+    c, form, mat = _setup(oracle, name)
+    cards = ti.traction_cards(c.desc, c.sidesets)
+    assert cards and sum(len(cd[0]) for cd in cards) > 0
+    _, _, fext = c.bc(c.nsteps * c.dt)
+    ref_eq = c.ref("eqnos")
+    rhs = np.zeros_like(fext)
+    rhs[ref_eq > 0] = c.ref("rhs")[ref_eq[ref_eq > 0] - 1]
+    free = ref_eq > 0
+    assert np.abs(fext[free]).max() > 1e-3
+    assert np.abs(fext - c.ref("fint") - rhs)[free].max() < 1e-10 * np.abs(fext).max()
+    # a constant global traction integrates to traction x area: total force of the z-face load of the reference's own case
+    if name == "ref_traction_a":
+        area = np.ptp(c.X[:, 0]) * np.ptp(c.X[:, 1])
+        assert abs(fext[:, 2].sum() + area) < 1e-12 and np.abs(fext[:, :2]).max() < 1e-15
 
 
 def nlpcg_steps(c, solve_step, update_history=None):
