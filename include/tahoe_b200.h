@@ -49,7 +49,9 @@ typedef enum { TB2_SSKSTV = 0, TB2_FDKSTV = 1, TB2_SIMO_ISO = 2, TB2_J2_SIMO = 3
                   ExplNeoHookeanT (elements/explicit/materials/ExplNeoHookeanT.cpp:79-111) and ExplJ2PlasticityT
                   (ExplJ2PlasticityT.cpp:87-310; hard[0] = sigma_Y, hard[1] = hardening modulus H) */
                TB2_EXPL_NEO_HOOKEAN = 4, TB2_EXPL_J2 = 5 } tb2_material_kind;
-typedef enum { TB2_HARD_LINEAR = 0, TB2_HARD_LINEAR_EXP = 1 } tb2_hardening_kind;
+typedef enum { TB2_HARD_LINEAR = 0, TB2_HARD_LINEAR_EXP = 1, TB2_HARD_POWER_LAW = 2, TB2_HARD_CUBIC_SPLINE = 3 } tb2_hardening_kind;
+enum { TB2_MAX_KNOTS = 16 };
+enum { TB2_SPLINE_PARABOLIC = 0, TB2_SPLINE_FREE_RUN = 1 }; /* CubicSplineT::FixityT (CubicSplineT.h:29-30) */
 /* kinematic boundary condition codes per dof (KBC_CardT::CodeT subset used by nExplicitCD::ConsistentKBC, nExplicitCD.cpp:20-69) */
 typedef enum { TB2_BC_FREE = 0, TB2_BC_FIX = 1, TB2_BC_DSP = 2 } tb2_bc_code;
 
@@ -58,7 +60,12 @@ typedef struct {
     int32_t hard_kind; /* tb2_hardening_kind (J2 only) */
     double  mu, lambda, kappa, density; /* IsotropicT (materials/primitives/IsotropicT.cpp:32-45) */
     double  hard[4];   /* linear: K = hard[0]*alpha + hard[1] (C1functions/LinearT.h:71);
-                          linear_exponential: K = hard[0] + hard[1]*alpha + hard[2]*(1 - exp(-alpha/hard[3])) */
+                          linear_exponential: K = hard[0] + hard[1]*alpha + hard[2]*(1 - exp(-alpha/hard[3]));
+                          power_law: K = hard[0]*(hard[1] + hard[2]*alpha)^hard[3] (C1functions/PowerLawT.cpp:28-37) */
+    /* cubic_spline (C1functions/CubicSplineT.cpp): the <OrderedPair> knots and the fixity; the library forms the spline
+       coefficients as CubicSplineT::SetSpline does (:254-324).  3 <= num_knots <= TB2_MAX_KNOTS, knot_x ascending. */
+    int32_t num_knots, spline_fixity;
+    double  knot_x[TB2_MAX_KNOTS], knot_y[TB2_MAX_KNOTS];
 } tb2_material;
 
 typedef struct tb2_mesh      tb2_mesh;      /* device-resident connectivity + reference coordinates (ModelManagerT / ElementBaseT::fConnectivities) */

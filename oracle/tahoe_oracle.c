@@ -211,17 +211,103 @@ static int simo_eval(const orc_material_t* m, const double* F, double* sig, doub
     return ORC_OK;
 }
 
+/* CubicSplineT (toolbox/src/C1functions/CubicSplineT.cpp): natural / parabolic-run-out cubic spline through the knots, stored as
+ * nknots+1 rows of (a0..a3) about the left knot of each interval; rows 0 and nknots extend the curve beyond the ends (:303-323) */
+int orc_material_set_spline(orc_material_t* m, int n, const double* x, const double* y, int fixity)
+{
+    if (n < 3 || n > ORC_MAX_KNOTS || (fixity != 0 && fixity != 1)) return -1;
+    double dxi[ORC_MAX_KNOTS], ddy[ORC_MAX_KNOTS], L[ORC_MAX_KNOTS], D[ORC_MAX_KNOTS], R[ORC_MAX_KNOTS];
+    for (int i = 1; i < n; i++) dxi[i - 1] = x[i] - x[i - 1];
+    const int neq = n - 2;
+    double* rhs = ddy + 1;
+    for (int i = 0; i < neq; i++) { /* :271-277 */
+        L[i] = dxi[i] / 6.0;
+        D[i] = (dxi[i] + dxi[i + 1]) / 3.0;
+        R[i] = dxi[i + 1] / 6.0;
+        rhs[i] = ((y[i + 2] - y[i + 1]) / dxi[i + 1]) - ((y[i + 1] - y[i]) / dxi[i]);
+    }
+    if (fixity == 0) { /* kParabolic :280-284 */
+        D[0] += dxi[0] / 6.0;
+        D[neq - 1] += dxi[neq - 1] / 6.0;
+    }
+    /* TriDiagdMatrixT::LinearSolve (TriDiagdMatrixT.cpp:25-80) */
+    for (int i = 1; i < neq; i++) {
+        const double factor = L[i] / D[i - 1];
+        D[i] -= R[i - 1] * factor;
+        rhs[i] -= rhs[i - 1] * factor;
+    }
+    rhs[neq - 1] /= D[neq - 1];
+    for (int i = neq - 2; i >= 0; i--) rhs[i] = (rhs[i] - R[i] * rhs[i + 1]) / D[i];
+    if (fixity == 1) ddy[0] = ddy[neq + 1] = 0.0;
+    else {
+        ddy[0] = ddy[1];
+        ddy[neq + 1] = ddy[neq];
+    }
+    m->nknots = n;
+    for (int i = 0; i < n; i++) m->knot_x[i] = x[i];
+    double* c = m->spline;
+    for (int j = 1; j < n; j++) { /* :303-313 */
+        const int i = j - 1;
+        const double dx = dxi[i];
+        c[j * 4 + 0] = y[i];
+        c[j * 4 + 1] = -dx * (2.0 * ddy[i] + ddy[i + 1]) / 6.0 + (y[i + 1] - y[i]) / dx;
+        c[j * 4 + 2] = ddy[i] / 2.0;
+        c[j * 4 + 3] = (ddy[i + 1] - ddy[i]) / (6.0 * dx);
+    }
+    c[0] = c[4]; c[1] = c[5]; c[2] = c[6]; c[3] = 0.0; /* extensions :316-323 */
+    const int dex = n - 1;
+    c[(dex + 1) * 4 + 0] = y[dex];
+    c[(dex + 1) * 4 + 1] = dxi[dex - 1] * (ddy[dex - 1] + 2.0 * ddy[dex]) / 6.0 + (y[dex] - y[dex - 1]) / dxi[dex - 1];
+    c[(dex + 1) * 4 + 2] = ddy[dex] / 2.0;
+    c[(dex + 1) * 4 + 3] = 0.0;
+    return 0;
+}
+
+/* dRangeArrayT::Range (toolbox/src/abc/other/dRangeArrayT.cpp:66-87) and the interval-local abscissa of CubicSplineT::function */
+static const double* spline_row(const orc_material_t* m, double x, double* dx)
+{
+    int i = 0;
+    if (!(x < m->knot_x[0])) {
+        int lower = 0, upper = m->nknots;
+        do {
+            const int dex = (lower + upper) / 2;
+            if (x > m->knot_x[dex]) lower = dex;
+            else upper = dex;
+        } while (upper > lower + 1);
+        i = upper;
+    }
+    *dx = (i == 0) ? x - m->knot_x[0] : x - m->knot_x[i - 1];
+    return m->spline + 4 * i;
+}
+
 /* J2 hardening K(alpha), K'(alpha) (J2_C0HardeningT.h:68-69; C1functions/LinearT.h:71,
- * LinearExponentialT.cpp:48-57) */
+ * LinearExponentialT.cpp:48-57, PowerLawT.cpp:28-37, CubicSplineT.cpp:162-182) */
 static double j2_K(const orc_material_t* m, double a)
 {
     if (m->hard_kind == ORC_HARD_LINEAR) return m->hard[0] * a + m->hard[1];
+    if (m->hard_kind == ORC_HARD_POWER_LAW) return m->hard[0] * pow(m->hard[1] + m->hard[2] * a, m->hard[3]);
+    if (m->hard_kind == ORC_HARD_CUBIC_SPLINE) {
+        double dx;
+        const double* c = spline_row(m, a, &dx);
+        return c[0] + c[1] * dx + c[2] * dx * dx + c[3] * dx * dx * dx;
+    }
     return m->hard[0] + m->hard[1] * a + m->hard[2] * (1.0 - exp(-a / m->hard[3]));
 }
 static double j2_dK(const orc_material_t* m, double a)
 {
     if (m->hard_kind == ORC_HARD_LINEAR) return m->hard[0];
+    if (m->hard_kind == ORC_HARD_POWER_LAW) return m->hard[0] * m->hard[2] * m->hard[3] * pow(m->hard[1] + m->hard[2] * a, m->hard[3] - 1.0);
+    if (m->hard_kind == ORC_HARD_CUBIC_SPLINE) {
+        double dx;
+        const double* c = spline_row(m, a, &dx);
+        return c[1] + 2.0 * c[2] * dx + 3.0 * c[3] * dx * dx;
+    }
     return m->hard[1] + m->hard[2] * exp(-a / m->hard[3]) / m->hard[3];
+}
+void orc_hardening(const orc_material_t* m, double alpha, double* K, double* dK)
+{
+    *K = j2_K(m, alpha);
+    *dK = j2_dK(m, alpha);
 }
 enum { kalpha = 0, kstressnorm = 1, kdgamma = 2, kftrial = 3, kmu_bar = 4, kmu_bar_bar = 5, kDetF_tot = 6, kHeatIncr = 7 };
 

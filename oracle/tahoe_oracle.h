@@ -29,14 +29,19 @@ enum { ORC_SSKSTV = 0, ORC_FDKSTV = 1, ORC_SIMO_ISO = 2, ORC_J2_SIMO = 3,
        ORC_EXPL_NEO = 4, ORC_EXPL_J2 = 5 /* <explicit_solid> materials: ExplNeoHookeanT, ExplJ2PlasticityT (hard[0] = sigma_Y, hard[1] = H) */ };
 enum { ORC_OK = 0, ORC_BAD_JACOBIAN = 1, ORC_J2_LOCAL_FAIL = 2 };
 enum { ORC_J2_NOTINIT = -1, ORC_J2_PLASTIC = 0, ORC_J2_ELASTIC = 1 }; /* J2SimoC0HardeningT.h:33-36 */
-enum { ORC_HARD_LINEAR = 0, ORC_HARD_LINEAR_EXP = 1 };
+enum { ORC_HARD_LINEAR = 0, ORC_HARD_LINEAR_EXP = 1, ORC_HARD_POWER_LAW = 2, ORC_HARD_CUBIC_SPLINE = 3 };
+enum { ORC_MAX_KNOTS = 16 };
 
 typedef struct {
     int    kind;       /* ORC_SSKSTV ... */
     double mu, lambda, kappa, density;
     int    hard_kind;  /* J2: hardening function K(alpha) */
     double hard[4];    /* linear: K = hard[0]*alpha + hard[1];
-                          linear_exponential: K = hard[0] + hard[1]*alpha + hard[2]*(1-exp(-alpha/hard[3])) */
+                          linear_exponential: K = hard[0] + hard[1]*alpha + hard[2]*(1-exp(-alpha/hard[3]));
+                          power_law: K = hard[0]*(hard[1] + hard[2]*alpha)^hard[3] (C1functions/PowerLawT.cpp:28-37) */
+    int    nknots;     /* cubic_spline (C1functions/CubicSplineT.cpp): knots and the nknots+1 coefficient rows set by orc_material_set_spline */
+    double knot_x[ORC_MAX_KNOTS];
+    double spline[(ORC_MAX_KNOTS + 1) * 4];
 } orc_material_t;
 
 /* J2 history of one integration point, field order of
@@ -120,6 +125,10 @@ double orc_explicit_solid_stable_dt(const orc_material_t* m, int64_t ne, const i
 void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, double target_dt,
                                    double scale_factor, double* scale /*[ne]*/);
 int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass);
+/* CubicSplineT::SetSpline (CubicSplineT.cpp:254-324): fixity 0 parabolic, 1 free_run; returns nonzero on bad input */
+int orc_material_set_spline(orc_material_t* m, int n, const double* x, const double* y, int fixity);
+/* the hardening function and its derivative (known-answer checks) */
+void orc_hardening(const orc_material_t* m, double alpha, double* K, double* dK);
 /* natural_bc tractions (ContinuumElementT::ApplyTractionBC, ContinuumElementT.cpp:514-665): f[nn][3] += consistent nodal forces of
  * ncards facet cards (elem, facet 0-based; tract[card][4][3] nodal traction vectors in facet-node order; coord_system 0 global, 1 local) */
 int orc_traction_force(int64_t ncards, const int32_t* elem, const int32_t* facet, const int32_t* conn, const double* X,

@@ -52,7 +52,8 @@ class Tb2Error(RuntimeError):
 
 class Material(C.Structure):
     _fields_ = [("kind", C.c_int32), ("hard_kind", C.c_int32), ("mu", C.c_double), ("lam", C.c_double), ("kappa", C.c_double),
-                ("density", C.c_double), ("hard", C.c_double * 4)]
+                ("density", C.c_double), ("hard", C.c_double * 4), ("num_knots", C.c_int32), ("spline_fixity", C.c_int32),
+                ("knot_x", C.c_double * 16), ("knot_y", C.c_double * 16)]
 
 
 _lib = None
@@ -116,6 +117,16 @@ def material(desc_mat):
         if h["type"] == "linear_function":
             m.hard_kind = 0
             m.hard[0], m.hard[1] = h["a"], h["b"]
+        elif h["type"] == "power_law":  # PowerLawT: a (b + c x)^n
+            m.hard_kind = 2
+            for i, k in enumerate("abcn"):
+                m.hard[i] = h[k]
+        elif h["type"] == "cubic_spline":  # CubicSplineT: knots + fixity, coefficients are formed by the library
+            m.hard_kind = 3
+            m.num_knots = len(h["points"])
+            m.spline_fixity = {"parabolic": 0, "free_run": 1}[h["fixity"]]
+            for i, (x, y) in enumerate(h["points"]):
+                m.knot_x[i], m.knot_y[i] = x, y
         else:
             m.hard_kind = 1
             for i, k in enumerate("abcd"):

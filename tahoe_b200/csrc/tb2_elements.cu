@@ -983,6 +983,66 @@ int ensure_stage(tb2_mesh* m, int which)
 
 using namespace tb2;
 
+// CubicSplineT::SetSpline (toolbox/src/C1functions/CubicSplineT.cpp:254-324): second derivatives at the knots from the tridiagonal
+// continuity system (free_run: zero end curvature; parabolic: end curvature equal to the neighbour's), then one cubic per interval
+// about its left knot, plus one row before the first and after the last knot that continue the curve with its end slope/curvature.
+// table = [knot_x[n] | (n+1) x 4 coefficients]
+static bool spline_table(const tb2_material& mat, std::vector<double>& table)
+{
+    const int n = mat.num_knots;
+    if (n < 3 || n > TB2_MAX_KNOTS) return false;
+    if (mat.spline_fixity != TB2_SPLINE_PARABOLIC && mat.spline_fixity != TB2_SPLINE_FREE_RUN) return false;
+    const double* x = mat.knot_x;
+    const double* y = mat.knot_y;
+    std::vector<double> h(n - 1), m2(n, 0.0), lo(n), di(n), up(n);
+    for (int i = 0; i + 1 < n; i++) {
+        h[i] = x[i + 1] - x[i];
+        if (!(h[i] > 0.0)) return false;
+    }
+    const int neq = n - 2;
+    for (int i = 0; i < neq; i++) {
+        lo[i] = h[i] / 6.0;
+        di[i] = (h[i] + h[i + 1]) / 3.0;
+        up[i] = h[i + 1] / 6.0;
+        m2[i + 1] = (y[i + 2] - y[i + 1]) / h[i + 1] - (y[i + 1] - y[i]) / h[i];
+    }
+    if (mat.spline_fixity == TB2_SPLINE_PARABOLIC) {
+        di[0] += h[0] / 6.0;
+        di[neq - 1] += h[neq - 1] / 6.0;
+    }
+    for (int i = 1; i < neq; i++) { // Thomas algorithm in TriDiagdMatrixT::LinearSolve's operation order
+        const double factor = lo[i] / di[i - 1];
+        di[i] -= up[i - 1] * factor;
+        m2[i + 1] -= m2[i] * factor;
+    }
+    m2[neq] /= di[neq - 1];
+    for (int i = neq - 2; i >= 0; i--) m2[i + 1] = (m2[i + 1] - up[i] * m2[i + 2]) / di[i];
+    if (mat.spline_fixity == TB2_SPLINE_PARABOLIC) {
+        m2[0] = m2[1];
+        m2[n - 1] = m2[n - 2];
+    } else
+        m2[0] = m2[n - 1] = 0.0;
+    table.assign((size_t)n + 4 * (n + 1), 0.0);
+    for (int i = 0; i < n; i++) table[i] = x[i];
+    double* c = table.data() + n;
+    for (int j = 1; j < n; j++) {
+        const int i = j - 1;
+        c[4 * j + 0] = y[i];
+        c[4 * j + 1] = -h[i] * (2.0 * m2[i] + m2[i + 1]) / 6.0 + (y[i + 1] - y[i]) / h[i];
+        c[4 * j + 2] = m2[i] / 2.0;
+        c[4 * j + 3] = (m2[i + 1] - m2[i]) / (6.0 * h[i]);
+    }
+    c[0] = c[4];
+    c[1] = c[5];
+    c[2] = c[6];
+    c[3] = 0.0;
+    c[4 * n + 0] = y[n - 1];
+    c[4 * n + 1] = h[n - 2] * (m2[n - 2] + 2.0 * m2[n - 1]) / 6.0 + (y[n - 1] - y[n - 2]) / h[n - 2];
+    c[4 * n + 2] = m2[n - 1] / 2.0;
+    c[4 * n + 3] = 0.0;
+    return true;
+}
+
 extern "C" {
 
 int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_group** out)
@@ -1007,7 +1067,21 @@ int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_grou
     g->mc.kappa = mat->kappa;
     g->mc.hard_kind = mat->hard_kind;
     for (int i = 0; i < 4; i++) g->mc.hard[i] = mat->hard[i];
+    g->mc.nknots = 0;
+    g->mc.spline = nullptr;
     cudaError_t e = g->status.alloc(2);
+    if (e == cudaSuccess && mat->kind == TB2_J2_SIMO && mat->hard_kind == TB2_HARD_CUBIC_SPLINE) {
+        std::vector<double> table;
+        if (!spline_table(*mat, table)) {
+            delete g;
+            set_error("cubic_spline hardening needs 3..%d knots in ascending order and a valid fixity", (int)TB2_MAX_KNOTS);
+            return TB2_ERR_ARG;
+        }
+        e = g->spline.alloc(table.size());
+        if (e == cudaSuccess) e = cudaMemcpy(g->spline.p, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice);
+        g->mc.nknots = mat->num_knots;
+        g->mc.spline = g->spline.p;
+    }
     if (e == cudaSuccess && mat->kind == TB2_EXPL_J2) { // [ip][16][stride], F_n = 1
         e = g->hist.alloc((size_t)16 * 8 * mesh->stride);
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist.p, 0, g->hist.n * sizeof(double), mesh->stream);

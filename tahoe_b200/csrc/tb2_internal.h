@@ -184,6 +184,7 @@ struct tb2_group {
     tb2::DevBuf<double> hist_save; // committed copy for ResetStep is not needed: trial fields are recomputed
     tb2::DevBuf<int> hist_flag;    // [8][stride]
     tb2::DevBuf<int> hist_alloc;   // [stride]
+    tb2::DevBuf<double> spline;    // cubic_spline hardening table (MatConst::spline)
     tb2::DevBuf<unsigned long long> status; // [0] error code, [1] first bad element
     tb2::DevBuf<double> mass_scale; // [ne] ExplicitElementT::fMassScale (null: no mass scaling)
     tb2::DevBuf<unsigned char> off; // [ne] 1 = ElementCardT::kOFF: the element loops skip it (null: every element is on)

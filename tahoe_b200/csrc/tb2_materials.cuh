@@ -10,7 +10,7 @@ enum { kSSKStV = 0, kFDKStV = 1, kSimoIso = 2, kJ2Simo = 3,
        kSSKStVBbar = 4, /* kernel-template tag only: SSKStV under SmallStrainT's mean-dilatation B-bar */
        kExplNeo = 5, kExplJ2 = 6 /* <explicit_solid> materials (public kinds TB2_EXPL_NEO_HOOKEAN = 4, TB2_EXPL_J2 = 5) */ };
 enum { kSmallStrain = 0, kTotalLagrangian = 1, kUpdatedLagrangian = 2 };
-enum { kHardLinear = 0, kHardLinearExp = 1 };
+enum { kHardLinear = 0, kHardLinearExp = 1, kHardPowerLaw = 2, kHardCubicSpline = 3 };
 enum { kErrNone = 0, kErrBadJacobian = 1, kErrJ2Local = 2 };
 // J2SimoC0HardeningT.h:33-36
 enum { kJ2NotInit = -1, kJ2Plastic = 0, kJ2Elastic = 1 };
@@ -23,6 +23,10 @@ struct MatConst {
     double mu, lambda, kappa;
     int hard_kind;
     double hard[4];
+    // cubic_spline hardening: [knot_x[nknots] | (nknots+1) rows of 4 coefficients] in global memory (a few hundred bytes, read
+    // through the read-only path by the yielding points of a J2 group only)
+    int nknots;
+    const double* spline;
 };
 
 // J2 history, SoA: data[(field*8 + ip)*stride + e], flag[ip*stride + e], alloc[e]
@@ -207,15 +211,44 @@ TB2_DEV void simo_bbar(const double (&F)[3][3], double J, double (&b_bar)[6])
     for (int I = 0; I < 6; I++) b_bar[I] *= sc;
 }
 
-// ---- J2 hardening K(alpha), K'(alpha) (J2_C0HardeningT.h:68-69)
+// ---- J2 hardening K(alpha), K'(alpha) (J2_C0HardeningT.h:68-69): LinearT, LinearExponentialT, PowerLawT (PowerLawT.cpp:28-37),
+// CubicSplineT (CubicSplineT.cpp:162-182 with dRangeArrayT::Range, dRangeArrayT.cpp:66-87)
+TB2_DEV const double* j2_spline_row(const MatConst& m, double x, double& dx)
+{
+    const double* kx = m.spline;
+    int i = 0;
+    if (!(x < __ldg(kx))) {
+        int lower = 0, upper = m.nknots;
+        do {
+            const int dex = (lower + upper) / 2;
+            if (x > __ldg(kx + dex)) lower = dex;
+            else upper = dex;
+        } while (upper > lower + 1);
+        i = upper;
+    }
+    dx = x - __ldg(kx + (i == 0 ? 0 : i - 1));
+    return kx + m.nknots + 4 * i;
+}
 TB2_DEV double j2_K(const MatConst& m, double a)
 {
     if (m.hard_kind == kHardLinear) return m.hard[0] * a + m.hard[1];
+    if (m.hard_kind == kHardPowerLaw) return m.hard[0] * pow(m.hard[1] + m.hard[2] * a, m.hard[3]);
+    if (m.hard_kind == kHardCubicSpline) {
+        double dx;
+        const double* c = j2_spline_row(m, a, dx);
+        return __ldg(c) + __ldg(c + 1) * dx + __ldg(c + 2) * dx * dx + __ldg(c + 3) * dx * dx * dx;
+    }
     return m.hard[0] + m.hard[1] * a + m.hard[2] * (1.0 - exp(-a / m.hard[3]));
 }
 TB2_DEV double j2_dK(const MatConst& m, double a)
 {
     if (m.hard_kind == kHardLinear) return m.hard[0];
+    if (m.hard_kind == kHardPowerLaw) return m.hard[0] * m.hard[2] * m.hard[3] * pow(m.hard[1] + m.hard[2] * a, m.hard[3] - 1.0);
+    if (m.hard_kind == kHardCubicSpline) {
+        double dx;
+        const double* c = j2_spline_row(m, a, dx);
+        return __ldg(c + 1) + 2.0 * __ldg(c + 2) * dx + 3.0 * __ldg(c + 3) * dx * dx;
+    }
     return m.hard[1] + m.hard[2] * exp(-a / m.hard[3]) / m.hard[3];
 }
 

@@ -163,6 +163,8 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 		if (fIsJ2) { /* K(alpha): C1functions/LinearT.h:71, LinearExponentialT.cpp:48-57 */
 			const ParameterListT* lin = FindList(list, "linear_function");
 			const ParameterListT* lexp = FindList(list, "linear_exponential");
+			const ParameterListT* plaw = FindList(list, "power_law");
+			const ParameterListT* spline = FindList(list, "cubic_spline");
 			if (lin) {
 				mat.hard_kind = TB2_HARD_LINEAR;
 				mat.hard[0] = lin->GetParameter("a");
@@ -173,8 +175,25 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 				mat.hard[1] = lexp->GetParameter("b");
 				mat.hard[2] = lexp->GetParameter("c");
 				mat.hard[3] = lexp->GetParameter("d");
+			} else if (plaw) { /* PowerLawT.cpp:28-37 */
+				mat.hard_kind = TB2_HARD_POWER_LAW;
+				mat.hard[0] = plaw->GetParameter("a");
+				mat.hard[1] = plaw->GetParameter("b");
+				mat.hard[2] = plaw->GetParameter("c");
+				mat.hard[3] = plaw->GetParameter("n");
+			} else if (spline) { /* CubicSplineT::TakeParameterList (CubicSplineT.cpp:352-381): the library forms the coefficients */
+				mat.hard_kind = TB2_HARD_CUBIC_SPLINE;
+				mat.num_knots = spline->NumLists("OrderedPair");
+				if (mat.num_knots > TB2_MAX_KNOTS) ExceptionT::BadInputValue(caller, "cubic_spline hardening: at most %d knots", TB2_MAX_KNOTS);
+				int fixity = spline->GetParameter("fixity");
+				mat.spline_fixity = fixity == 1 ? TB2_SPLINE_FREE_RUN : TB2_SPLINE_PARABOLIC;
+				for (int i = 0; i < mat.num_knots; i++) {
+					const ParameterListT* knot = spline->List("OrderedPair", i);
+					mat.knot_x[i] = knot->GetParameter("x");
+					mat.knot_y[i] = knot->GetParameter("y");
+				}
 			} else
-				ExceptionT::BadInputValue(caller, "Simo_J2 hardening must be linear_function or linear_exponential");
+				ExceptionT::BadInputValue(caller, "Simo_J2 hardening must be linear_function, linear_exponential, power_law or cubic_spline");
 		}
 
 	}

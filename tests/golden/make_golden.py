@@ -159,6 +159,8 @@ def main():
         ("ref_mat_5_a", "level.1/material.solid/3D/material.05/mat.5.a.xml", ["--fint"]),
         ("ref_mat_09_a", "level.1/material.solid/3D/material.09/mat.09.a.xml", ["--every", "1", "--fint"]),
         ("ref_mat_09_b", "level.1/material.solid/3D/material.09/mat.09.b.xml", ["--every", "1", "--fint"]),  # linear_exponential K(alpha): local Newton
+        ("ref_mat_09_c", "level.1/material.solid/3D/material.09/mat.09.c.xml", ["--every", "1", "--fint"]),  # cubic_spline K(alpha)
+        ("ref_mat_09_d", "level.1/material.solid/3D/material.09/mat.09.d.xml", ["--every", "1", "--fint"]),  # power_law K(alpha)
     ]
     for name, rel, flags in ref_cases:
         if want(name):
@@ -201,6 +203,12 @@ def main():
         ("syn_ul_j2_static", 3, {"time": static(4), "integrator": "static", "kbc": pull_u(0.06), "fbc": [],
                                  "element": {"type": "updated_lagrangian"}, "material": j2, "solver": NEWTON},
          ["--every", "1", "--fint", "--lhs"]),
+        # Simo_J2 with a parabolic-run-out cubic_spline K(alpha) on non-uniform knots (the local Newton crosses several spline intervals)
+        ("syn_ul_j2_spline_static", 3, {"time": static(4), "integrator": "static", "kbc": pull_u(0.08), "fbc": [],
+                                        "element": {"type": "updated_lagrangian"},
+                                        "material": dict(j2, hardening={"type": "cubic_spline", "fixity": "parabolic",
+                                                                        "points": [[0.0, 0.25], [0.005, 0.255], [0.02, 0.26], [0.04, 0.30], [0.1, 0.31]]}),
+                                        "solver": NEWTON}, ["--every", "1", "--fint", "--lhs"]),
         # a5: mean-dilatation B-bar (SmallStrainT strain_displacement="B-bar"), nearly incompressible so that it matters
         ("syn_ss_kstv_bbar_static", 4, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
                                         "element": {"type": "small_strain", "strain_displacement": "B-bar"},

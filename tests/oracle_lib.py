@@ -26,7 +26,8 @@ KIND_OF = {"small_strain_StVenant": 0, "large_strain_StVenant": 1, "Simo_isotrop
 
 class Material(C.Structure):
     _fields_ = [("kind", C.c_int), ("mu", C.c_double), ("lam", C.c_double), ("kappa", C.c_double),
-                ("density", C.c_double), ("hard_kind", C.c_int), ("hard", C.c_double * 4)]
+                ("density", C.c_double), ("hard_kind", C.c_int), ("hard", C.c_double * 4),
+                ("nknots", C.c_int), ("knot_x", C.c_double * 16), ("spline", C.c_double * (17 * 4))]
 
 
 J2_DTYPE = np.dtype([("b_bar", "f8", 6), ("unit_norm", "f8", 6), ("beta_bar", "f8", 6), ("b_bar_trial", "f8", 6),
@@ -76,11 +77,28 @@ def material(desc_mat):
         if h["type"] == "linear_function":
             m.hard_kind = 0
             m.hard[0], m.hard[1] = h["a"], h["b"]
+        elif h["type"] == "power_law":  # PowerLawT: a (b + c x)^n
+            m.hard_kind = 2
+            for i, k in enumerate("abcn"):
+                m.hard[i] = h[k]
+        elif h["type"] == "cubic_spline":
+            m.hard_kind = 3
+            pts = np.asarray(h["points"], np.float64)
+            x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+            err = lib().orc_material_set_spline(C.byref(m), len(x), _p(x), _p(y), {"parabolic": 0, "free_run": 1}[h["fixity"]])
+            assert err == 0
         else:
             m.hard_kind = 1
             for i, k in enumerate("abcd"):
                 m.hard[i] = h[k]
     return m
+
+
+def hardening(mat, alpha):
+    """K(alpha), K'(alpha) of a J2 material"""
+    K, dK = C.c_double(0), C.c_double(0)
+    lib().orc_hardening(C.byref(mat), C.c_double(alpha), C.byref(K), C.byref(dK))
+    return K.value, dK.value
 
 
 def internal_force(form, mat, conn, X, u, u_last=None, j2=None, alloc=None, iteration=0):

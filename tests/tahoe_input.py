@@ -253,6 +253,13 @@ def parse_xml(path):
     le = mat.find("linear_exponential")
     if le is not None:
         md["hardening"] = {"type": "linear_exponential", **{k: float(le.get(k)) for k in "abcd"}}
+    pl = mat.find("power_law")
+    if pl is not None:
+        md["hardening"] = {"type": "power_law", **{k: float(pl.get(k)) for k in "abcn"}}
+    cs = mat.find("cubic_spline")
+    if cs is not None:
+        md["hardening"] = {"type": "cubic_spline", "fixity": cs.get("fixity", "parabolic"),
+                           "points": [[float(o.get("x")), float(o.get("y"))] for o in cs.findall("OrderedPair")]}
     if mat.tag == "RG_split_general":  # explicit_solid: ExplicitElementT scans the sub-tree for mu / kappa (ExplicitElementT.cpp:176-200)
         nh = mat.find("rg_eq_potential").find("neo-hookean")
         md = {"type": "explicit_neo_hookean", "density": float(mat.get("density", 1.0)), "kappa": float(nh.get("kappa")), "mu": float(nh.get("mu"))}
@@ -329,7 +336,11 @@ def write_xml(path, d):
     else:
         L.append('            <bulk_and_shear bulk_modulus="%.17g" shear_modulus="%.17g"/>' % (m["kappa"], m["mu"]))
     h = m.get("hardening")
-    if h:
+    if h and h["type"] == "cubic_spline":
+        L.append('            <cubic_spline fixity="%s">' % h["fixity"])
+        L += ['              <OrderedPair x="%.17g" y="%.17g"/>' % (x, y) for x, y in h["points"]]
+        L.append("            </cubic_spline>")
+    elif h:
         L.append("            <%s %s/>" % (h["type"], " ".join('%s="%.17g"' % (k, v) for k, v in h.items() if k != "type")))
     if not explicit:
         L.append("          </%s>\n        </%s>\n      </%s>\n    </%s>\n  </element_list>" % (m["type"], mlist, blk, e.get("tag", e["type"])))

@@ -350,3 +350,34 @@ def test_colouring_is_valid_and_8_on_structured(oracle):
     for cc in range(ncol):
         nodes = conn[col == cc].ravel()
         assert len(np.unique(nodes)) == len(nodes)
+
+
+def test_hardening_functions_known_answers(oracle):
+    """C1FunctionT hardening laws of Simo_J2 (J2_C0HardeningT.h:68-69): closed forms, and the cubic spline's defining properties
+    (CubicSplineT.cpp): interpolates the knots, C1/C2 across knots, free_run = zero end curvature with a straight continuation,
+    parabolic = constant end curvature"""
+    base = {"type": "Simo_J2", "density": 1.0, "E": 100.0, "nu": 0.25}
+    m = oracle.material(dict(base, hardening={"type": "power_law", "a": 0.25, "b": 1.0, "c": 400.0, "n": 0.8}))
+    K, dK = oracle.hardening(m, 0.01)
+    assert abs(K - 0.25 * 5.0 ** 0.8) < 1e-14 and abs(dK - 0.25 * 400.0 * 0.8 * 5.0 ** -0.2) < 1e-12
+    pts = [[0.0, 0.25], [0.01, 0.255], [0.05, 0.26], [0.10, 0.30]]  # mat.09.c.xml
+    for fixity in ("free_run", "parabolic"):
+        m = oracle.material(dict(base, hardening={"type": "cubic_spline", "fixity": fixity, "points": pts}))
+        for x, y in pts:
+            assert abs(oracle.hardening(m, x)[0] - y) < 1e-15
+        eps = 1e-7
+        for x, _ in pts[1:-1]:  # value (and, for free_run, slope) continuous across interior knots.  The reference's parabolic end
+            # condition adds dxi[numeqs-1]/6 to the last row where the last interval is dxi[numeqs] (CubicSplineT.cpp:283), so its
+            # parabolic spline has a slope jump at the last interior knot on non-uniform knots; the restatement keeps that.
+            (Kl, dl), (Kr, dr) = oracle.hardening(m, x - eps), oracle.hardening(m, x + eps)
+            assert abs(Kl - Kr) < 1e-5 and (abs(dl - dr) < 1e-4 or fixity == "parabolic")
+        # beyond the last knot: free_run continues straight, parabolic keeps the end curvature
+        d1, d2, d3 = (oracle.hardening(m, 0.10 + k * 0.01)[1] for k in (1, 2, 3))
+        if fixity == "free_run":
+            assert abs(d1 - d2) < 1e-13 and abs(d2 - d3) < 1e-13
+        else:
+            assert abs((d2 - d1) - (d3 - d2)) < 1e-13 and abs(d2 - d1) > 1e-6
+        # central difference of K against K'
+        for x in (0.003, 0.02, 0.07, 0.12):
+            num = (oracle.hardening(m, x + 1e-6)[0] - oracle.hardening(m, x - 1e-6)[0]) / 2e-6
+            assert abs(num - oracle.hardening(m, x)[1]) < 1e-7

@@ -85,6 +85,16 @@ def _cases():
         # J2 stress output: the host ComputeOutput evaluates J2Simo3D from the element cards, which the plugin fills from the device history
         "static_ul_j2_host_stress_out": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                           "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": j2, "solver": newton}, None),
+        # Simo_J2 with tabulated / power-law hardening: the plugin hands the knots (or a, b, c, n) to the library
+        "static_ul_j2_spline_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                    "element": {"type": "updated_lagrangian"},
+                                    "material": dict(j2, hardening={"type": "cubic_spline", "fixity": "free_run",
+                                                                    "points": [[0.0, 0.25], [0.01, 0.255], [0.05, 0.26], [0.10, 0.30]]}),
+                                    "solver": newton}, None),
+        "static_ul_j2_powerlaw_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                      "element": {"type": "updated_lagrangian"},
+                                      "material": dict(j2, hardening={"type": "power_law", "a": 0.25, "b": 1.0, "c": 400.0, "n": 0.8}),
+                                      "solver": newton}, None),
         # J2: device K1 with history, Tahoe's host tangent + SPOOLES (non-symmetric tangent)
         "static_ul_j2_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                              "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton}, None),
