@@ -129,6 +129,13 @@ int tb2_group_status(tb2_group* group, int64_t* bad_element);
 /* ContinuumElementT::FormMass kLumpedMass (ContinuumElementT.cpp:767-842) summed to nodes: d_mass[nn][3] */
 int tb2_form_lumped_mass(tb2_group* group, double* d_mass);
 int tb2_form_lumped_mass_host(tb2_group* group, double* h_mass);
+/* inertia branches of the element loops (implicit dynamics): ContinuumElementT::MassTypeT and
+ * FormMa (ContinuumElementT.cpp:868-1002, called from SolidElementT::ElementRHSDriver :1243-1265): d_f[nn][3] = scale * M a with the
+ * consistent (sum_ip rho w detJ0 N_a N_b) or lumped (HRZ diagonal, as tb2_form_lumped_mass) element mass on the reference
+ * configuration.  Tahoe's RHS receives -constMa * (this). */
+enum { TB2_MASS_CONSISTENT = 1 /* kConsistentMass */, TB2_MASS_LUMPED = 2 /* kLumpedMass */ };
+int tb2_form_inertial_force(tb2_group* group, int mass_type, double scale, const double* d_acc, double* d_f);
+int tb2_form_inertial_force_host(tb2_group* group, int mass_type, double scale, const double* h_acc, double* h_f);
 /* ElementCardT status flags (ElementBaseT::SetStatus; the element loops skip ElementCardT::kOFF elements: SolidElementT.cpp:1116,
  * 1177).  h_off[ne]: 1 = off, 0 = on; NULL = all on.  Off elements contribute no force, tangent or mass. */
 int tb2_group_set_element_status(tb2_group* group, const uint8_t* h_off);
@@ -219,6 +226,11 @@ int tb2_matrix_clear(tb2_matrix* A); /* GlobalMatrixT::Clear */
  * element->CSR-slot map.  TB2_K3_COLOURED=1 selects the colour-by-colour read-modify-write form instead. */
 int tb2_form_stiffness(tb2_group* group, tb2_matrix* A, const double* d_u, const double* d_u_last, int iteration);
 int tb2_form_stiffness_host(tb2_group* group, tb2_matrix* A, const double* h_u, const double* h_u_last, int iteration);
+/* ElementLHSDriver with formM (SolidElementT.cpp:1100-1154 -> ContinuumElementT::FormMass, ContinuumElementT.cpp:678-866):
+ * A += constM * M, mass_type as TB2_MASS_*; with tb2_matrix_scale this forms the effective matrix of an implicit integrator,
+ * constM * M + constK * K (eLinearHHTalpha::eComputeParameters: constM = 1, constK = (1 + alpha) beta dt^2) */
+int tb2_form_mass(tb2_group* group, tb2_matrix* A, int mass_type, double constM);
+int tb2_matrix_scale(tb2_matrix* A, double s); /* val *= s */
 /* the same element loop assembled into a DiagonalMatrixT in kDiagOnly mode (DiagonalMatrixT.cpp:107-113: fMatrix[eq] += elMat(i,i)),
  * which is what <PCG_solver><diagonal_matrix/> uses as its preconditioner (SolverT.cpp:1097-1102): d_diag[nn][3] = diag K(u) per nodal dof */
 int tb2_form_stiffness_diagonal(tb2_group* group, const double* d_u, const double* d_u_last, int iteration, double* d_diag);

@@ -1592,3 +1592,96 @@ int orc_traction_force(int64_t ncards, const int32_t* elem, const int32_t* facet
     }
     return ORC_OK;
 }
+
+/* ---- inertia: ContinuumElementT::FormMass / FormMa (ContinuumElementT.cpp:678-866, 868-1002) -----------------------------------
+ * mass_type 1 = kConsistentMass: M_(a i)(b j) = delta_ij sum_ip rho w detJ0 N_a N_b (reference configuration);
+ * mass_type 2 = kLumpedMass: the HRZ diagonal of orc_element_lumped_mass.  Element matrix is column-major 24 x 24 like Ke. */
+static int element_mass(double density, int mass_type, const double X[8][3], double Me[576])
+{
+    for (int i = 0; i < 576; i++) Me[i] = 0.0;
+    if (mass_type == 2) {
+        double me[8];
+        int err = orc_element_lumped_mass(density, X, me);
+        if (err) return err;
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) Me[(3 * a + i) * 25] = me[a];
+        return ORC_OK;
+    }
+    double Na[8][8], DNa[8][3][8], w[8], dN[8][3][8], det[8];
+    orc_hex8_parent(Na, DNa, w);
+    int err = orc_hex8_shape(X, dN, det);
+    if (err) return err;
+    for (int ip = 0; ip < 8; ip++) {
+        const double temp = density * w[ip] * det[ip];
+        for (int a = 0; a < 8; a++)
+            for (int b = 0; b < 8; b++)
+                for (int i = 0; i < 3; i++) Me[(3 * a + i) + 24 * (3 * b + i)] += temp * Na[ip][a] * Na[ip][b];
+    }
+    return ORC_OK;
+}
+/* f[nn][3] += scale * sum_e M_e a_e, accumulated element by element as SolidElementT::ElementRHSDriver does (:1243-1265):
+ * consistent: per ip the interpolated acceleration times rho w detJ0 N_a (:940-966); lumped: diagonal times nodal value (:969-997) */
+int orc_inertial_force(double density, int mass_type, int64_t ne, const int32_t* conn, const double* X, const double* acc,
+                       double scale, double* f)
+{
+    double Na[8][8], DNa[8][3][8], w[8];
+    orc_hex8_parent(Na, DNa, w);
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], ae[8][3], fe[24] = {0};
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        gather(c, acc, ae);
+        if (mass_type == 2) {
+            double me[8];
+            int err = orc_element_lumped_mass(scale * density, Xe, me);
+            if (err) return err;
+            for (int a = 0; a < 8; a++)
+                for (int i = 0; i < 3; i++) fe[3 * a + i] += ae[a][i] * me[a];
+        } else {
+            double dN[8][3][8], det[8];
+            int err = orc_hex8_shape(Xe, dN, det);
+            if (err) return err;
+            for (int ip = 0; ip < 8; ip++) {
+                double aip[3] = {0, 0, 0};
+                for (int a = 0; a < 8; a++)
+                    for (int i = 0; i < 3; i++) aip[i] += Na[ip][a] * ae[a][i];
+                const double temp = scale * density * w[ip] * det[ip];
+                for (int a = 0; a < 8; a++) {
+                    const double temp2 = temp * Na[ip][a];
+                    for (int i = 0; i < 3; i++) fe[3 * a + i] += temp2 * aip[i];
+                }
+            }
+        }
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) f[3 * (int64_t)c[a] + i] += fe[3 * a + i];
+    }
+    return ORC_OK;
+}
+/* val += constM * M on the CSR of orc_csr_structure (SolidElementT::ElementLHSDriver with formM, SolidElementT.cpp:1100-1154) */
+int orc_assemble_mass(double density, int mass_type, double constM, int64_t ne, const int32_t* conn, const double* X,
+                      const int32_t* eqnos, const int64_t* rowptr, const int32_t* colind, double* val)
+{
+    for (int64_t e = 0; e < ne; e++) {
+        double Xe[8][3], Me[576];
+        const int32_t* c = conn + 8 * e;
+        gather(c, X, Xe);
+        int err = element_mass(constM * density, mass_type, Xe, Me);
+        if (err) return err;
+        int32_t eq[24];
+        for (int a = 0; a < 8; a++)
+            for (int i = 0; i < 3; i++) eq[3 * a + i] = eqnos[3 * (int64_t)c[a] + i];
+        for (int r = 0; r < 24; r++) {
+            if (eq[r] <= 0) continue;
+            const int64_t row = eq[r] - 1;
+            for (int cc = 0; cc < 24; cc++) {
+                if (eq[cc] <= 0 || Me[r + 24 * cc] == 0.0) continue;
+                const int32_t col = eq[cc] - 1;
+                int64_t lo = rowptr[row], hi = rowptr[row + 1] - 1;
+                while (lo < hi) { int64_t mid = (lo + hi) / 2; if (colind[mid] < col) lo = mid + 1; else hi = mid; }
+                if (colind[lo] != col) return -1;
+                val[lo] += Me[r + 24 * cc];
+            }
+        }
+    }
+    return ORC_OK;
+}

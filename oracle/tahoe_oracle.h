@@ -125,6 +125,12 @@ double orc_explicit_solid_stable_dt(const orc_material_t* m, int64_t ne, const i
 void orc_explicit_solid_mass_scale(const orc_material_t* m, int64_t ne, const int32_t* conn, const double* X, double target_dt,
                                    double scale_factor, double* scale /*[ne]*/);
 int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, const double* X, const double* scale, double* mass);
+/* inertia (ContinuumElementT::FormMa / FormMass, ContinuumElementT.cpp:678-1002): mass_type 1 consistent, 2 lumped (HRZ).
+ * orc_inertial_force: f[nn][3] += scale * M a;  orc_assemble_mass: CSR val += constM * M */
+int orc_inertial_force(double density, int mass_type, int64_t ne, const int32_t* conn, const double* X, const double* acc,
+                       double scale, double* f);
+int orc_assemble_mass(double density, int mass_type, double constM, int64_t ne, const int32_t* conn, const double* X,
+                      const int32_t* eqnos, const int64_t* rowptr, const int32_t* colind, double* val);
 /* CubicSplineT::SetSpline (CubicSplineT.cpp:254-324): fixity 0 parabolic, 1 free_run; returns nonzero on bad input */
 int orc_material_set_spline(orc_material_t* m, int n, const double* x, const double* y, int fixity);
 /* the hardening function and its derivative (known-answer checks) */

@@ -33,6 +33,7 @@ SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2
 tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
 tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
+tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_scale
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
 tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
@@ -296,6 +297,12 @@ class Group(_Handle):
         _chk(lib().tb2_group_get_explicit_history(self.h, _p(h)))
         return h
 
+    def inertial_force_host(self, mass_type, acc, scale=1.0):
+        """scale * M a [nn][3] (ContinuumElementT::FormMa; mass_type 1 consistent, 2 lumped)"""
+        out = np.zeros((self.mesh.nn, 3))
+        _chk(lib().tb2_form_inertial_force_host(self.h, int(mass_type), C.c_double(scale), _p(_f64(acc)), _p(out)))
+        return out
+
     def nodal_stress_host(self, u):
         """extrapolated + averaged nodal Cauchy stress [nn][6] (SolidElementT::ComputeOutput)"""
         out = np.zeros((self.mesh.nn, 6))
@@ -442,6 +449,14 @@ class Matrix(_Handle):
 
     def form_stiffness_host(self, group, u, u_last=None, iteration=0):
         _chk(lib().tb2_form_stiffness_host(group.h, self.h, _p(_f64(u)), _p(_f64(u_last)), int(iteration)))
+
+    def form_mass(self, group, mass_type, constM=1.0):
+        """A += constM * M (ContinuumElementT::FormMass through the element LHS loop)"""
+        _chk(lib().tb2_form_mass(group.h, self.h, int(mass_type), C.c_double(constM)))
+        _chk(lib().tb2_group_status(group.h, None))
+
+    def scale(self, s):
+        _chk(lib().tb2_matrix_scale(self.h, C.c_double(s)))
 
     def form_stiffness(self, group, d_u, d_u_last=None, iteration=0):
         _chk(lib().tb2_form_stiffness(group.h, self.h, _dp(d_u), _dp(d_u_last), int(iteration)))

@@ -667,6 +667,126 @@ __global__ void __launch_bounds__(128) k_lumped_mass(int64_t ne, int64_t stride,
     for (int a = 0; a < 8; a++) fe[(int64_t)a * stride + e] = diagmass * nee[a];
 }
 
+// ---- inertia (a2 FormMa, a16 FormMass): ContinuumElementT::FormMass / FormMa (ContinuumElementT.cpp:678-866, 868-1002) on the
+// reference configuration.  mass_type 1 = kConsistentMass (M_ab = sum_ip rho w detJ0 N_a N_b on equal dofs), 2 = kLumpedMass (the
+// HRZ diagonal of K4).  One thread per element; `rho` carries the integrator constant (constM or constMa).
+struct ElemMass {
+    double M[8][8]; // consistent: upper triangle a <= b; lumped: diagonal only
+};
+TB2_DEV bool element_mass(const int* __restrict__ conn, const double* __restrict__ X, int64_t stride, int64_t e, double rho, int mass_type,
+                          ElemMass& out, int (&n)[8])
+{
+#pragma unroll
+    for (int a = 0; a < 8; a++) n[a] = __ldg(conn + a * stride + e);
+    Modes cX;
+    load_modes(X, n, cX);
+    const double RA[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, SA[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, TA[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) out.M[a][b] = 0.0;
+    double dsum = 0.0, totmas = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int ip = 0; ip < 8; ip++) {
+        double J0[3][3];
+        mode_gradient(cX, RA[ip], SA[ip], TA[ip], J0);
+        const double det0 = det3(J0);
+        ok = ok && det0 > 0.0;
+        const double temp = rho * det0; // weight = 1
+        totmas += temp;
+        double Na[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            Na[a] = 0.125 * (1.0 + RA[a] * RA[ip] * TB2_G) * (1.0 + SA[a] * SA[ip] * TB2_G) * (1.0 + TA[a] * TA[ip] * TB2_G);
+        if (mass_type == 1) {
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = a; b < 8; b++) out.M[a][b] += temp * Na[a] * Na[b];
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const double temp2 = temp * Na[a] * Na[a];
+                dsum += temp2;
+                out.M[a][a] += temp2;
+            }
+        }
+    }
+    if (mass_type != 1) {
+        const double diagmass = totmas / dsum;
+#pragma unroll
+        for (int a = 0; a < 8; a++) out.M[a][a] *= diagmass;
+    }
+    return ok;
+}
+
+// f_e = M_e a_e -> fe[24][stride] (then the K1 node gather)
+__global__ void __launch_bounds__(128) k_inertial_force(int64_t ne, int64_t stride, const int* __restrict__ conn, const double* __restrict__ X,
+                                                       const double* __restrict__ acc, double rho, int mass_type,
+                                                       const double* __restrict__ mass_scale, const unsigned char* __restrict__ off,
+                                                       double* __restrict__ fe, unsigned long long* status)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    if (off && off[e]) {
+#pragma unroll
+        for (int r = 0; r < 24; r++) fe[(int64_t)r * stride + e] = 0.0;
+        return;
+    }
+    if (mass_scale) rho *= mass_scale[e];
+    ElemMass em;
+    int n[8];
+    if (!element_mass(conn, X, stride, e, rho, mass_type, em, n)) {
+        atomicMax(status, (unsigned long long)kErrBadJacobian);
+        atomicMin(status + 1, (unsigned long long)e);
+    }
+    double a[8][3];
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) a[b][i] = __ldg(acc + (int64_t)n[b] * 3 + i);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) s += (r <= b ? em.M[r][b] : em.M[b][r]) * a[b][i];
+            fe[(int64_t)(3 * r + i) * stride + e] = s;
+        }
+}
+
+// element mass matrices of [e0, e1) as packed upper triangles ke[e - e0][300] (entry tri24(r, c)), the record form of the two-phase
+// assembly (tb2_stiffness.cu): only entries on equal dofs are non-zero
+TB2_DEV int mass_tri24(int r, int c) { return r * 24 - ((r * (r - 1)) >> 1) + (c - r); }
+__global__ void __launch_bounds__(128) k_element_mass(int64_t e0, int64_t e1, int64_t stride, const int* __restrict__ conn,
+                                                     const double* __restrict__ X, double rho, int mass_type,
+                                                     const double* __restrict__ mass_scale, const unsigned char* __restrict__ off,
+                                                     double* __restrict__ ke, unsigned long long* status)
+{
+    const int64_t e = e0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= e1) return;
+    double* rec = ke + (e - e0) * 300;
+    for (int q = 0; q < 300; q++) rec[q] = 0.0;
+    if (off && off[e]) return;
+    if (mass_scale) rho *= mass_scale[e];
+    ElemMass em;
+    int n[8];
+    if (!element_mass(conn, X, stride, e, rho, mass_type, em, n)) {
+        atomicMax(status, (unsigned long long)kErrBadJacobian);
+        atomicMin(status + 1, (unsigned long long)e);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = a; b < 8; b++) {
+            if (mass_type != 1 && b != a) continue;
+#pragma unroll
+            for (int i = 0; i < 3; i++) rec[mass_tri24(3 * a + i, 3 * b + i)] = em.M[a][b];
+        }
+}
+
 // node gather: out[n][i] = sum over incident (e,a), ascending e, of fe[rows(a,i)][e].
 // PER_DOF: rows = 3a+i (forces); else rows = a for all three dofs (lumped mass: same value on the 3 dofs of a node)
 template <bool PER_DOF>
@@ -1327,6 +1447,48 @@ int tb2_form_lumped_mass_host(tb2_group* g, double* h_mass)
     TB2_CUDA(cudaMemcpyAsync(h_mass, m->stage_b.p, 3 * m->nn * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     return tb2_group_status(g, nullptr);
 }
+
+// a2: the inertia term of SolidElementT::ElementRHSDriver (SolidElementT.cpp:1243-1265): d_f = scale * M a
+int tb2_form_inertial_force(tb2_group* g, int mass_type, double scale, const double* d_acc, double* d_f)
+{
+    TB2_ARG(g && d_acc && d_f && (mass_type == TB2_MASS_CONSISTENT || mass_type == TB2_MASS_LUMPED));
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    const int T = 128;
+    ProfScope ps(m, kProfOther);
+    k_inertial_force<<<(unsigned)((m->ne + T - 1) / T), T, 0, m->stream>>>(m->ne, m->stride, m->conn.p, m->X.p, d_acc, scale * g->mat.density,
+                                                                          mass_type, g->mass_scale.p, g->off.p, m->fe.p, g->status.p);
+    TB2_CUDA(cudaGetLastError());
+    return launch_node_gather(m, d_f, true);
+}
+
+int tb2_form_inertial_force_host(tb2_group* g, int mass_type, double scale, const double* h_acc, double* h_f)
+{
+    TB2_ARG(g && h_acc && h_f);
+    tb2_mesh* m = g->mesh;
+    DeviceGuard dg(m->device);
+    TB2_CHECK(ensure_stage(m, 0));
+    TB2_CHECK(ensure_stage(m, 1));
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    TB2_CUDA(cudaMemcpyAsync(m->stage_a.p, h_acc, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CHECK(tb2_form_inertial_force(g, mass_type, scale, m->stage_a.p, m->stage_b.p));
+    TB2_CUDA(cudaMemcpyAsync(h_f, m->stage_b.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    return tb2_group_status(g, nullptr);
+}
+
+} // extern "C"
+
+// element mass records of [e0, e1) for the two-phase assembly (tb2_form_mass in tb2_stiffness.cu)
+int launch_element_mass(tb2_group* g, int mass_type, double constM, int64_t e0, int64_t e1, double* ke)
+{
+    tb2_mesh* m = g->mesh;
+    const int T = 128;
+    k_element_mass<<<(unsigned)((e1 - e0 + T - 1) / T), T, 0, m->stream>>>(e0, e1, m->stride, m->conn.p, m->X.p, constM * g->mat.density,
+                                                                        mass_type, g->mass_scale.p, g->off.p, ke, g->status.p);
+    return cudaGetLastError() == cudaSuccess ? TB2_OK : TB2_ERR_CUDA;
+}
+
+extern "C" {
 
 int tb2_group_close_step(tb2_group* g)
 {

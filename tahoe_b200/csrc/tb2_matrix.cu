@@ -812,6 +812,23 @@ int tb2_matrix_clear(tb2_matrix* A)
     return TB2_OK;
 }
 
+// val *= s (the integrator's constK on an assembled tangent: eLinearHHTalpha::FormK, eLinearHHTalpha.cpp:30-34)
+__global__ void __launch_bounds__(256) k_scale_values(long long n, double s, double* __restrict__ v)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[i] *= s;
+}
+int tb2_matrix_scale(tb2_matrix* A, double s)
+{
+    TB2_ARG(A);
+    tb2_mesh* m = A->ctx;
+    DeviceGuard dg(m->device);
+    if (A->nnz == 0) return TB2_OK;
+    const long long blocks = (A->nnz + 255) / 256;
+    k_scale_values<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, m->stream>>>((long long)A->nnz, s, A->val.p);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
 int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y)
 {
     TB2_ARG(A && d_x && d_y);

@@ -18,6 +18,8 @@
 
 #include "tb2_internal.h"
 
+int launch_element_mass(tb2_group* g, int mass_type, double constM, int64_t e0, int64_t e1, double* ke); // tb2_elements.cu
+
 namespace tb2 {
 
 int launch_element_forces(tb2_group* g, const double* d_u, const double* d_ul, int iteration);
@@ -864,6 +866,42 @@ int tb2_form_stiffness_host(tb2_group* g, tb2_matrix* A, const double* h_u, cons
     }
     TB2_CHECK(tb2_form_stiffness(g, A, m->stage_a.p, h_ul ? m->stage_c.p : nullptr, iteration));
     return tb2_group_status(g, nullptr);
+}
+
+// a16 with formM (SolidElementT::ElementLHSDriver, SolidElementT.cpp:1100-1154 -> ContinuumElementT::FormMass): A += constM * M through
+// the same two-phase path as the tangent: packed-upper-triangle element records, then the per-node gather in element order
+int tb2_form_mass(tb2_group* g, tb2_matrix* A, int mass_type, double constM)
+{
+    TB2_ARG(g && A && (mass_type == TB2_MASS_CONSISTENT || mass_type == TB2_MASS_LUMPED));
+    tb2_mesh* m = g->mesh;
+    TB2_ARG(A->eqs && A->eqs->mesh == m);
+    DeviceGuard dg(m->device);
+    elem_kernel_t k = pick_elem_kernel(g->form, g->mat.kind, false, g->bbar);
+    TB2_ARG(k != nullptr);
+    TB2_CHECK(ensure_gather_plan(A, k, g->mat.kind == TB2_J2_SIMO ? 576 : kSymEntries));
+    GatherArgs ga;
+    ga.sym = 1;
+    ga.ke = A->ke.p;
+    ga.adj_ptr = A->adj_ptr.p;
+    ga.adj = A->adj.p;
+    ga.adj_coloff = A->adj_coloff.p;
+    ga.cptr = A->contrib_ptr.p;
+    ga.contrib = A->contrib.p;
+    ga.eqnos = A->eqs->eqnos.p;
+    ga.rowptr = A->rowptr.p;
+    ga.val = A->val.p;
+    const int nchunks = (int)A->k3_nmin.size();
+    for (int c = 0; c < nchunks; c++) {
+        ga.e0 = (int64_t)c * A->k3_chunk;
+        ga.e1 = ga.e0 + A->k3_chunk < m->ne ? ga.e0 + A->k3_chunk : m->ne;
+        ga.n0 = A->k3_nmin[c];
+        ga.n1 = (int64_t)A->k3_nmax[c] + 1;
+        ProfScope ps(m, kProfStiffness, 2);
+        TB2_CHECK(launch_element_mass(g, mass_type, constM, ga.e0, ga.e1, A->ke.p));
+        k_assemble_gather<<<(unsigned)((ga.n1 - ga.n0 + kGatherWarps - 1) / kGatherWarps), 32 * kGatherWarps, 0, m->stream>>>(ga);
+    }
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
 }
 
 } // extern "C"

@@ -152,6 +152,7 @@ def main():
         ("ref_beam_newton", "level.0/3D.elastostatic/beam.Newton.xml", ["--fint"]),
         ("ref_explicit_1", "level.0/3D.elastodynamic/explicit.1.xml", ["--every", "25", "--fint"]),
         ("ref_explicit_2", "level.0/3D.elastodynamic/explicit.2.xml", ["--every", "25", "--fint"]),
+        ("ref_implicit_1", "level.0/3D.elastodynamic/implicit.1.xml", ["--every", "1", "--fint"]),  # nonlinear_HHT + consistent_mass
         ("ref_beam_pcg", "level.0/3D.elastostatic/beam.PCG.xml", ["--fint"]),
         ("ref_beam_bbar", "level.0/3D.elastostatic/beam.B_bar.xml", ["--fint"]),
         ("ref_mat_1_a", "level.1/material.solid/3D/material.01/mat.1.a.xml", ["--fint"]),
@@ -262,6 +263,19 @@ def main():
                                        "element": {"type": "updated_lagrangian", "mass_type": "lumped_mass"},
                                        "material": fdkstv, "solver": EXPLICIT},
          ["--every", "10", "--fint"]),
+        # a2/a16 inertia branches: implicit dynamics (nonlinear_HHT = Newmark beta 1/4, gamma 1/2) with consistent and lumped mass
+        ("syn_ul_fdkstv_implicit", 3, {"time": {"num_steps": 4, "time_step": 0.05, "schedules": [[(0.0, 1.0)]]},
+                                       "integrator": "nonlinear_HHT", "kbc": CLAMP_X0,
+                                       "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.05},
+                                               {"nodeset": 2, "dof": 3, "schedule": 1, "value": -0.02}],
+                                       "element": {"type": "updated_lagrangian", "mass_type": "consistent_mass"},
+                                       "material": fdkstv, "solver": NEWTON}, ["--every", "1", "--fint"]),
+        ("syn_tl_simo_implicit", 3, {"time": {"num_steps": 4, "time_step": 0.05, "schedules": [RAMP_FAST]},
+                                     "integrator": "nonlinear_HHT",
+                                     "kbc": CLAMP_X0 + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.1}],
+                                     "fbc": [{"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.05}],
+                                     "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"},
+                                     "material": simo_soft, "solver": NEWTON}, ["--every", "1", "--fint"]),
         # explicit_solid (ExplicitElementT: batched UL force, ExplNeoHookeanT / ExplJ2PlasticityT, mass scaling)
         ("syn_xs_neo_explicit", 4, {"time": {"num_steps": 40, "time_step": 0.5 * 0.25 / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0),
                                              "schedules": [[(0.0, 1.0)]]},

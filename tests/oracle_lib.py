@@ -300,3 +300,22 @@ def traction_force(conn, X, elem, facet, tract, coord_system="global", scale=1.0
                                    {"global": 0, "local": 1}[coord_system], C.c_double(scale), _p(f))
     assert err == 0, err
     return f
+
+
+def inertial_force(density, mass_type, conn, X, acc, scale=1.0):
+    """ContinuumElementT::FormMa summed over the mesh: M a [nn][3] (mass_type 1 consistent, 2 lumped)"""
+    conn = np.ascontiguousarray(conn, np.int32)
+    f = np.zeros_like(X)
+    err = lib().orc_inertial_force(C.c_double(density), int(mass_type), C.c_int64(conn.shape[0]), _p(conn), _p(np.ascontiguousarray(X)),
+                                   _p(np.ascontiguousarray(acc)), C.c_double(scale), _p(f))
+    assert err == 0
+    return f
+
+
+def assemble_mass(density, mass_type, constM, conn, X, eqnos, rowptr, colind, val):
+    """val += constM * M on the CSR of csr_structure (ContinuumElementT::FormMass through ElementLHSDriver)"""
+    conn = np.ascontiguousarray(conn, np.int32)
+    err = lib().orc_assemble_mass(C.c_double(density), int(mass_type), C.c_double(constM), C.c_int64(conn.shape[0]), _p(conn),
+                                  _p(np.ascontiguousarray(X)), _p(eqnos), _p(rowptr), _p(colind), _p(val))
+    assert err == 0
+    return val

@@ -8,7 +8,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import tahoe_input as ti
-from cases import TRACTION, PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import IMPLICIT, MASS_TYPE, implicit_dynamics, TRACTION, PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -40,6 +40,8 @@ def test_internal_force_matches_reference(tb2, name):
     mesh, grp, _ = _group(tb2, c)
     d = c.ref("d_%d" % c.dump_steps[-1])
     f = grp.internal_force_host(d)
+    if name in IMPLICIT:  # the element residual of an implicit-dynamics run carries the inertia term too (SolidElementT.cpp:1243-1265)
+        f += grp.inertial_force_host(MASS_TYPE[c.desc["element"]["mass_type"]], c.ref("a_%d" % c.dump_steps[-1]))
     assert relerr(f, c.ref("fint")) < TOL
 
 
@@ -698,6 +700,69 @@ def test_static_newton_j2_matches_reference(tb2, name):
     assert sel.sum() > 0
     assert np.abs(data[sel] - ref[sel]).max() < 1e-10
     assert np.array_equal(flags[sel], c.ref("j2_flags")[sel])
+
+
+# ------------------------------------------------------------------ inertia branches (a2 FormMa, a16 FormMass)
+@pytest.mark.parametrize("mass_type", [1, 2])
+def test_inertial_force_and_mass_matrix_match_oracle(tb2, oracle, mass_type):
+    """ContinuumElementT::FormMa / FormMass on the device against the oracle on a jittered block with some dofs fixed, plus
+    size-independent properties: M a assembled = A_M a on the active dofs, total mass = 3 rho V, symmetry of the assembled matrix"""
+    X, conn, ns = ti.structured_cube(7, 6, 5, jitter=0.2)
+    rho = 2.5
+    rng = np.random.default_rng(3)
+    acc = rng.standard_normal(X.shape)
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.form_of({"type": "total_lagrangian"}), tb2.material({"type": "Simo_isotropic", "density": rho, "kappa": 10.0, "mu": 1.0}))
+    f = grp.inertial_force_host(mass_type, acc, scale=0.75)
+    assert relerr(f, oracle.inertial_force(rho, mass_type, conn, X, acc, 0.75)) < 1e-13
+    total = grp.inertial_force_host(mass_type, np.ones_like(X)).sum()
+    assert abs(total - 3.0 * rho * 1.0) < 1e-12 * total  # the unit cube: every dof direction carries the whole mass
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    A.clear()
+    A.form_mass(grp, mass_type, 1.5)
+    rowptr, colind, val = A.csr()
+    eq = eqs.eqnos()
+    want = oracle.assemble_mass(rho, mass_type, 1.5, conn, X, eq, rowptr, colind, np.zeros_like(val))
+    assert relerr(val, want) < 1e-13
+    M = sp.csr_matrix((val, colind, rowptr), shape=(A.neq, A.neq))
+    assert abs(M - M.T).max() == 0.0
+    a0 = np.where(eq > 0, acc, 0.0)  # zero acceleration on the fixed dofs: the assembled operator and the element sweep agree
+    assert relerr(M @ a0[eq > 0], 1.5 * grp.inertial_force_host(mass_type, a0)[eq > 0]) < 1e-12
+    A.scale(2.0)
+    assert np.array_equal(A.csr()[2], 2.0 * val)
+
+
+@pytest.mark.parametrize("name", IMPLICIT)
+def test_implicit_dynamics_matches_reference(tb2, name):
+    """the reference's nonlinear_HHT runs (its own implicit.1.xml, consistent and lumped mass) with the device's internal force,
+    inertia force, tangent + mass assembly and Jacobi-PCG inside the reference's predictor / Newton / corrector loop"""
+    c = Case(name)
+    mesh, grp, mat = _group(tb2, c)
+    mt = MASS_TYPE[c.desc["element"]["mass_type"]]
+    code, _, _ = c.bc(0.0)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    act = eqs.eqnos() > 0
+
+    def solve(d, constM, constK, R):
+        A.clear()
+        if constK != 0.0:
+            A.form_stiffness_host(grp, d)
+            A.scale(constK)
+        A.form_mass(grp, mt, constM)
+        x, it, rn = A.pcg_host(R, rtol=1e-14, max_iter=20000)
+        return x
+
+    iters, ic = c.ref("iters"), int(c.ref("iters_ic")[0])
+    for k, d, v, a, it in implicit_dynamics(c, act, grp.internal_force_host, lambda acc: grp.inertial_force_host(mt, acc), solve):
+        assert it == (ic if k == 0 else iters[k - 1])
+        if k in c.dump_steps:
+            for nm, arr in (("d", d), ("v", v), ("a", a)):
+                ref = c.ref("%s_%d" % (nm, k))
+                assert np.abs(arr - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300) + 1e-13, (k, nm)
 
 
 # ------------------------------------------------------------------ natural_bc tractions (SURVEY 8f-4)

@@ -6,7 +6,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import tahoe_input as ti
-from cases import TRACTION, PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
+from cases import IMPLICIT, MASS_TYPE, implicit_dynamics, TRACTION, PCG, XS, STRESS, ALL, EXPLICIT, STATIC, WITH_LHS, Case, relerr
 
 TOL = 1e-10  # north_star: forces / displacements agree to 1e-10 relative
 
@@ -38,6 +38,9 @@ def test_internal_force_matches_reference(oracle, name):
     d = c.ref("d_%d" % c.dump_steps[-1])
     err, f = oracle.internal_force(form, mat, c.conn, c.X, d)
     assert err == 0
+    if name in IMPLICIT:  # the element residual of an implicit-dynamics run carries the inertia term too (SolidElementT.cpp:1243-1265)
+        f += oracle.inertial_force(c.desc["material"]["density"], MASS_TYPE[c.desc["element"]["mass_type"]], c.conn, c.X,
+                                   c.ref("a_%d" % c.dump_steps[-1]))
     assert relerr(f, c.ref("fint")) < TOL
     if c.desc["integrator"] == "static":
         # FormRHS at the final state on the active equations: external load (nodal forces + natural_bc tractions) minus fint
@@ -381,3 +384,37 @@ def test_hardening_functions_known_answers(oracle):
         for x in (0.003, 0.02, 0.07, 0.12):
             num = (oracle.hardening(m, x + 1e-6)[0] - oracle.hardening(m, x - 1e-6)[0]) / 2e-6
             assert abs(num - oracle.hardening(m, x)[1]) < 1e-7
+
+
+@pytest.mark.parametrize("name", IMPLICIT)
+def test_implicit_dynamics_matches_reference(oracle, name):
+    """a2 (FormMa) / a16 (FormMass) inertia branches: the reference's nonlinear_HHT runs (its own implicit.1.xml with a consistent
+    mass, synthetic consistent- and lumped-mass cases) reproduced with the oracle's M a and M + beta dt^2 K: displacements,
+    velocities, accelerations and Newton iteration counts of every step, incl. the dt = 0 initial-acceleration solve"""
+    c, form, mat = _setup(oracle, name)
+    mt = MASS_TYPE[c.desc["element"]["mass_type"]]
+    rho = c.desc["material"]["density"]
+    code, _, _ = c.bc(0.0)
+    eq, neq = oracle.equation_numbers(code)
+    rowptr, colind = oracle.csr_structure(c.conn, eq, neq)
+    act = eq > 0
+
+    def fint(d):
+        err, f = oracle.internal_force(form, mat, c.conn, c.X, d)
+        assert err == 0
+        return f
+
+    def solve(d, constM, constK, R):
+        err, kv = oracle.assemble_stiffness(form, mat, c.conn, c.X, d, eq, neq, rowptr, colind)
+        assert err == 0
+        kv *= constK
+        oracle.assemble_mass(rho, mt, constM, c.conn, c.X, eq, rowptr, colind, kv)
+        return _direct(rowptr, colind, kv, R)
+
+    iters, ic = c.ref("iters"), int(c.ref("iters_ic")[0])
+    for k, d, v, a, it in implicit_dynamics(c, act, fint, lambda acc: oracle.inertial_force(rho, mt, c.conn, c.X, acc), solve):
+        assert it == (ic if k == 0 else iters[k - 1])
+        if k in c.dump_steps:
+            for nm, arr in (("d", d), ("v", v), ("a", a)):
+                ref = c.ref("%s_%d" % (nm, k))
+                assert np.abs(arr - ref).max() <= TOL * max(np.abs(ref).max(), 1e-300) + 1e-14, (k, nm)
