@@ -224,18 +224,32 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 	int formMa = this->fIntegrator->FormMa(constMa);
 	int formKd = this->fIntegrator->FormKd(constKd);
 	if (this->fMassType == ContinuumElementT::kNoMass) formMa = 0;
-	if (formMa || (this->fBodySchedule && this->fBody.Magnitude() > kSmall))
-		ExceptionT::GeneralFail(caller, "inertial / body-force residual terms are not on the device path (explicit lumped-mass and static analyses only)");
-	if (!formKd || fMuted) return;
+	if (this->fBodySchedule && this->fBody.Magnitude() > kSmall)
+		ExceptionT::GeneralFail(caller, "body-force residual terms are not on the device path");
+	if (fMuted) return;
+	if (formMa && !formKd) constKd = 0.0;
+	if (!formKd && !formMa) return;
 
 	const FieldT& field = this->Field();
 	const dArray2DT& disp = field[0];
-	const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
-	int iteration = this->ElementSupport().IterationNumber(this->Group());
-	Check(tb2_form_internal_force_host(fGroup, disp.Pointer(), last, iteration, fFint.Pointer()), caller);
+	fFint = 0.0;
+	if (formKd) {
+		const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
+		int iteration = this->ElementSupport().IterationNumber(this->Group());
+		Check(tb2_form_internal_force_host(fGroup, disp.Pointer(), last, iteration, fFint.Pointer()), caller);
+		fFint *= -constKd;
+	}
 
-	/* RHS += -constKd * fint on the active equations: one call for the whole group (SolverT::AssembleRHS, SolverT.cpp:446-477) */
-	fFint *= -constKd;
+	/* inertia term of an implicit integrator (SolidElementT.cpp:1243-1265): -constMa M a with the group's mass type */
+	if (formMa) {
+		if (this->fMassType != ContinuumElementT::kConsistentMass && this->fMassType != ContinuumElementT::kLumpedMass)
+			ExceptionT::GeneralFail(caller, "unresolved mass type %d", int(this->fMassType));
+		if (fMa.MajorDim() != disp.MajorDim()) fMa.Dimension(disp.MajorDim(), 3);
+		Check(tb2_form_inertial_force_host(fGroup, int(this->fMassType), -constMa, field[2].Pointer(), fMa.Pointer()), caller);
+		fFint += fMa;
+	}
+
+	/* RHS += -(constKd fint + constMa M a) on the active equations: one call for the whole group (SolverT::AssembleRHS, SolverT.cpp:446-477) */
 	this->ElementSupport().AssembleRHS(this->Group(), fFint, field.Equations());
 }
 
@@ -250,7 +264,9 @@ void CudaSolidElementT<BaseT>::LHSDriver(GlobalT::SystemTypeT sys_type)
 	int formK = this->fIntegrator->FormK(constK);
 	const GlobalMatrixT& lhs = this->ElementSupport().FEManager().LHS(this->Group());
 	CudaPCGMatrixT* cuda_lhs = const_cast<CudaPCGMatrixT*>(dynamic_cast<const CudaPCGMatrixT*>(&lhs));
-	if (!cuda_lhs || formM || !formK || fabs(constK) < kSmall) {
+	if (this->fMassType == ContinuumElementT::kNoMass) formM = 0;
+	const bool haveK = formK && fabs(constK) > kSmall, haveM = formM && fabs(constM) > kSmall;
+	if (!cuda_lhs || (!haveK && !haveM)) {
 		BaseT::LHSDriver(sys_type);
 		return;
 	}
@@ -265,8 +281,13 @@ void CudaSolidElementT<BaseT>::LHSDriver(GlobalT::SystemTypeT sys_type)
 	const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
 	int iteration = this->ElementSupport().IterationNumber(this->Group());
 	Check(tb2_matrix_clear(fMatrix), caller);
-	Check(tb2_form_stiffness_host(fGroup, fMatrix, field[0].Pointer(), last, iteration), caller);
-	cuda_lhs->AddDeviceMatrix(fMatrix, constK);
+	if (haveK) {
+		Check(tb2_form_stiffness_host(fGroup, fMatrix, field[0].Pointer(), last, iteration), caller);
+		if (fabs(constK - 1.0) > 0.0) Check(tb2_matrix_scale(fMatrix, constK), caller); /* eLinearHHTalpha::FormK: (1 + alpha) beta dt^2 */
+	}
+	if (haveM) /* effective mass of an implicit integrator: constM M (ContinuumElementT::FormMass) */
+		Check(tb2_form_mass(fGroup, fMatrix, int(this->fMassType), constM), caller);
+	cuda_lhs->AddDeviceMatrix(fMatrix, 1.0);
 }
 
 template <class BaseT>

@@ -7,6 +7,7 @@
  * <cuda_explicit_solid>).  What is replaced is the
  * per-element virtual-call loop:
  *   RHSDriver()  : SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295)  -> tb2_form_internal_force_host
+ *                  (+ tb2_form_inertial_force_host when the integrator asks for M a: implicit dynamics)
  *   LHSDriver()  : SolidElementT::ElementLHSDriver (SolidElementT.cpp:1100-1154)  -> tb2_form_stiffness into the
  *                  device CSR of a cooperating CudaPCGMatrixT; any other matrix type keeps Tahoe's host assembly
  *   CloseStep()/ResetStep() : J2 history commit / reset on the device.
@@ -110,6 +111,7 @@ private:
 	bool fIsJ2;
 	bool fMuted;           /**< see MuteInternalForce */
 	dArray2DT fFint;       /**< [nn][3] internal force of the whole group */
+	dArray2DT fMa;         /**< [nn][3] inertia force of the whole group (implicit integrators) */
 	int fMaterialKind;     /**< tb2_material_kind */
 };
 

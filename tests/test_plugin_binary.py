@@ -85,6 +85,19 @@ def _cases():
         # J2 stress output: the host ComputeOutput evaluates J2Simo3D from the element cards, which the plugin fills from the device history
         "static_ul_j2_host_stress_out": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                           "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": j2, "solver": newton}, None),
+        # implicit dynamics (nonlinear_HHT): device fint + M a, device K and M assembled into the CUDA_PCG_matrix, against SPOOLES
+        "implicit_ul_kstv_consistent_pcg": ({"time": {"num_steps": 4, "time_step": 0.05, "schedules": [[(0.0, 1.0)]]}, "integrator": "nonlinear_HHT",
+                                             "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.05},
+                                                                   {"nodeset": 2, "dof": 3, "schedule": 1, "value": -0.02}],
+                                             "element": {"type": "updated_lagrangian", "mass_type": "consistent_mass"},
+                                             "material": {"type": "large_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25},
+                                             "solver": newton}, pcg),
+        "implicit_tl_simo_lumped_pcg": ({"time": {"num_steps": 4, "time_step": 0.05, "schedules": [[(0.0, 0.0), (0.1, 1.0), (10.0, 1.0)]]},
+                                         "integrator": "nonlinear_HHT",
+                                         "kbc": CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.05}],
+                                         "fbc": [{"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.02}],
+                                         "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": simo_soft,
+                                         "solver": newton}, pcg),
         # Simo_J2 with tabulated / power-law hardening: the plugin hands the knots (or a, b, c, n) to the library
         "static_ul_j2_spline_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                     "element": {"type": "updated_lagrangian"},
