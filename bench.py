@@ -248,6 +248,43 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def pcg_cpu_reference(n=16):
+    """the reference's own iterative static solve -- <PCG_solver> with a <diagonal_matrix> preconditioner
+    (PCGSolver_LS: nonlinear CG, >= 2 element residual sweeps per iteration) -- on a small_strain + SSKStV cube of the PCG leg's
+    family, one host core.  Iterations are counted from the printed error history, seconds are the binary's own `Solution:` time."""
+    import re
+    import tahoe_input as ti
+    if not os.path.exists(REF_BIN):
+        return None
+    work = tempfile.mkdtemp(prefix="tb2_refpcg_")
+    try:
+        X, conn, ns = ti.structured_cube(n, jitter=0.1)
+        ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
+        desc = {"geometry_file": "mesh.geom", "time": {"num_steps": 1, "time_step": 1.0, "schedules": [[(0.0, 0.0), (1.0, 1.0)]]},
+                "integrator": "static",
+                "kbc": [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)],
+                "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02 / (n * n)}],
+                "element": {"type": "small_strain"}, "material": {"type": "small_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25},
+                "solver": {"type": "PCG_solver", "output_flag": "all_iterations", "abs_tolerance": "1.0e-14", "divergence_tolerance": "1.0e+06",
+                           "line_search_iterations": "10", "line_search_tolerance": "0.1", "max_iterations": "5000", "max_step": "2.5",
+                           "quick_solve_iter": "100", "rel_tolerance": "1.0e-08", "restart": "50", "matrix": "diagonal_matrix"}}
+        ti.write_xml(os.path.join(work, "pcg.xml"), desc)
+        r = subprocess.run([REF_BIN, "-f", "pcg.xml"], cwd=work, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                           env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=600)
+        its = len([ln for ln in r.stdout.splitlines() if "Relative error =" in ln]) - 1
+        sec = re.search(r"Solution:\s*([0-9.eE+-]+)\s*sec", r.stdout)
+        if r.returncode != 0 or its < 1 or not sec:
+            return {"unavailable": "reference PCG_solver run failed (rc %d)" % r.returncode}
+        neq = 3 * (X.shape[0] - len(ns[1]))
+        seconds = float(sec.group(1))
+        return {"value": neq * its / max(seconds, 1e-6), "unit": "DOF-iters/s", "cores": 1, "kind": "reference", "iterations": its,
+                "num_equations": neq, "seconds": seconds,
+                "sample": "oracle/_ref/tahoe, <PCG_solver><diagonal_matrix/> (nonlinear CG with line search, rel. tolerance 1e-8) on a "
+                          "%d^3=%d-element small_strain + SSKStV jittered cube, one static step" % (n, conn.shape[0])}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def workload_config(n, gpus):
     return {"workload": "BASELINE.json configs[1]: %d^3=%d-element structured Hex8 cube per GPU (jitter 0.1 h, seed 12345), total_lagrangian + "
                         "Simo_isotropic Neo-Hookean (kappa=1000, mu=5, rho=1), 8 integration points, lumped mass, explicit central difference"
@@ -679,6 +716,8 @@ def run_gpu_arm(args):
         if xs:
             line["explicit_solid"] = xs
         if pcg:
+            if world == 1 and not args.no_cpu_baseline:
+                pcg["cpu_reference"] = pcg_cpu_reference()
             line["pcg"] = pcg
         print(json.dumps(line))
     if world > 1:
