@@ -13,6 +13,7 @@
 #include "OutputSetT.h"
 #include "ParameterListT.h"
 #include "SSKStV.h"
+#include "ScheduleT.h"
 #include "SimoIso3D.h"
 #include "SolidMaterialT.h"
 #include "eIntegratorT.h"
@@ -224,11 +225,14 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 	int formMa = this->fIntegrator->FormMa(constMa);
 	int formKd = this->fIntegrator->FormKd(constKd);
 	if (this->fMassType == ContinuumElementT::kNoMass) formMa = 0;
-	if (this->fBodySchedule && this->fBody.Magnitude() > kSmall)
-		ExceptionT::GeneralFail(caller, "body-force residual terms are not on the device path");
+	/* body force (SolidElementT.cpp:1204-1211): formed through the mass operator, also when the integrator itself needs no M a */
+	int formBody = 0;
+	if (this->fMassType != ContinuumElementT::kNoMass && this->fBodySchedule && this->fBody.Magnitude() > kSmall) {
+		formBody = 1;
+		if (!formMa) constMa = 1.0;
+	}
 	if (fMuted) return;
-	if (formMa && !formKd) constKd = 0.0;
-	if (!formKd && !formMa) return;
+	if (!formKd && !formMa && !formBody) return;
 
 	const FieldT& field = this->Field();
 	const dArray2DT& disp = field[0];
@@ -241,11 +245,20 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 	}
 
 	/* inertia term of an implicit integrator (SolidElementT.cpp:1243-1265): -constMa M a with the group's mass type */
-	if (formMa) {
+	if (formMa || formBody) {
 		if (this->fMassType != ContinuumElementT::kConsistentMass && this->fMassType != ContinuumElementT::kLumpedMass)
 			ExceptionT::GeneralFail(caller, "unresolved mass type %d", int(this->fMassType));
 		if (fMa.MajorDim() != disp.MajorDim()) fMa.Dimension(disp.MajorDim(), 3);
-		Check(tb2_form_inertial_force_host(fGroup, int(this->fMassType), -constMa, field[2].Pointer(), fMa.Pointer()), caller);
+		const double* acc = field[2].Pointer();
+		if (formBody) {
+			/* ContinuumElementT::AddBodyForce (ContinuumElementT.cpp:849-865) sets every nodal value to -b * schedule (it does not
+			 * add to the acceleration), so the element loop integrates the mass operator against that constant field */
+			if (fBodyAcc.MajorDim() != disp.MajorDim()) fBodyAcc.Dimension(disp.MajorDim(), 3);
+			const double loadfactor = this->fBodySchedule->Value();
+			for (int i = 0; i < 3; i++) fBodyAcc.SetColumn(i, -this->fBody[i] * loadfactor);
+			acc = fBodyAcc.Pointer();
+		}
+		Check(tb2_form_inertial_force_host(fGroup, int(this->fMassType), -constMa, acc, fMa.Pointer()), caller);
 		fFint += fMa;
 	}
 

@@ -112,6 +112,7 @@ private:
 	bool fMuted;           /**< see MuteInternalForce */
 	dArray2DT fFint;       /**< [nn][3] internal force of the whole group */
 	dArray2DT fMa;         /**< [nn][3] inertia force of the whole group (implicit integrators) */
+	dArray2DT fBodyAcc;    /**< [nn][3] the constant nodal field -b * schedule of a body force */
 	int fMaterialKind;     /**< tb2_material_kind */
 };
 

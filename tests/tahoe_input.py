@@ -306,6 +306,9 @@ def write_xml(path, d):
     if e.get("strain_displacement", "standard") != "standard":  # SmallStrainT only (SmallStrainT.cpp:38-42)
         mass += ' strain_displacement="%s"' % e["strain_displacement"]
     L.append('    <%s field_name="displacement"%s>\n      <hexahedron/>' % (e.get("tag", e["type"]), mass))
+    if e.get("body_force"):  # ContinuumElementT::NewSub("body_force"): schedule + one <Double> per direction
+        bf = e["body_force"]
+        L.append('      <body_force schedule="%d">%s</body_force>' % (bf["schedule"], "".join('<Double value="%.17g"/>' % v for v in bf["vector"])))
     for nb in e.get("natural_bc") or []:
         L.append('      <natural_bc schedule="%d" side_set_ID="%d" coordinate_system="%s">' % (nb["schedule"], nb["side_set"], nb["coordinate_system"]))
         for vec in nb["values"]:

@@ -85,6 +85,14 @@ def _cases():
         # J2 stress output: the host ComputeOutput evaluates J2Simo3D from the element cards, which the plugin fills from the device history
         "static_ul_j2_host_stress_out": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                                           "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": j2, "solver": newton}, None),
+        # body force in an explicit run: -M b formed on the device through the mass operator (SolidElementT.cpp:1204-1265)
+        "explicit_tl_simo_gravity": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                                      "kbc": CLAMP, "fbc": [],
+                                      "element": {"type": "total_lagrangian", "mass_type": "lumped_mass",
+                                                  "body_force": {"schedule": 1, "vector": [0.0, 0.3, -9.81]}},
+                                      "material": simo, "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        # (with an implicit integrator the reference's AddBodyForce overwrites the nodal accelerations, ContinuumElementT.cpp:858-863,
+        #  and its own Newton loop cannot converge -- not a usable combination, so it is not a test case)
         # implicit dynamics (nonlinear_HHT): device fint + M a, device K and M assembled into the CUDA_PCG_matrix, against SPOOLES
         "implicit_ul_kstv_consistent_pcg": ({"time": {"num_steps": 4, "time_step": 0.05, "schedules": [[(0.0, 1.0)]]}, "integrator": "nonlinear_HHT",
                                              "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.05},
