@@ -72,6 +72,7 @@ typedef struct tb2_mesh      tb2_mesh;      /* device-resident connectivity + re
 typedef struct tb2_group     tb2_group;     /* one continuum-solid element group (SolidElementT subclass + its material + history) */
 typedef struct tb2_equations tb2_equations; /* equation numbers + sparsity (FieldT::fEqnos, MSRBuilderT) */
 typedef struct tb2_matrix    tb2_matrix;    /* device CSR global matrix (GlobalMatrixT subclass; MSRMatrixT semantics) */
+typedef struct tb2_geom      tb2_geom;      /* a parsed TahoeII .geom file (host memory) */
 typedef struct tb2_traction  tb2_traction;  /* natural_bc traction cards of one element group (ContinuumElementT::fTractionList) */
 typedef struct tb2_explicit  tb2_explicit;  /* d, v, a, lumped mass, BCs on device: FieldT + nExplicitCD + DiagonalMatrixT */
 
@@ -112,6 +113,19 @@ void* tb2_mesh_stream(const tb2_mesh* mesh); /* cudaStream_t all kernels of this
 /* Greedy element colouring in element order (no reference counterpart; pinned to
  * oracle/tahoe_oracle.c:orc_greedy_colouring).  h_colour[num_elements], returns the colour count. */
 int tb2_mesh_colouring(tb2_mesh* mesh, int32_t* h_colour, int32_t* num_colours);
+
+/* ---- TahoeII text geometry at scale: what ModelManagerT gets from TahoeInputT / ModelFileT
+ * (toolbox/src/dataio/input/TahoeInputT.cpp, database/ModelFileT.cpp), parsed with all host threads.  No CUDA calls.
+ * Ids come back 0-based: connectivity rows in file order, node-set members, side sets as (element in its block, facet).
+ * Element and node sections may be inline or in the external files the main file names (cube.1.geom style).  A negative
+ * node-set entry (the files' "all model nodes" marker, beam.1.geom) comes back as -1. */
+int tb2_geom_open(const char* path, tb2_geom** geom);
+int tb2_geom_close(tb2_geom* geom);
+int tb2_geom_sizes(const tb2_geom* geom, int64_t* nn, int32_t* nsd, int32_t* nblocks, int32_t* nnodesets, int32_t* nsidesets);
+int tb2_geom_coords(const tb2_geom* geom, double* h_X /*[nn][3], zero-padded when nsd < 3*/);
+int tb2_geom_block(const tb2_geom* geom, int32_t block, int32_t* id, int64_t* nel, int32_t* nen, int32_t* h_conn /*[nel][nen] or NULL*/);
+int tb2_geom_nodeset(const tb2_geom* geom, int32_t set, int32_t* id, int64_t* n, int32_t* h_nodes /*[n] or NULL*/);
+int tb2_geom_sideset(const tb2_geom* geom, int32_t set, int32_t* id, int32_t* block_id, int64_t* n, int32_t* h_sides /*[n][2] or NULL*/);
 
 /* ---- element group (SolidElementT / SmallStrainT / TotalLagrangianT / UpdatedLagrangianT) -------- */
 int tb2_group_create(tb2_mesh* mesh, int formulation, const tb2_material* material, tb2_group** group);

@@ -34,6 +34,7 @@ tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_me
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
 tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
 tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_scale
+tb2_geom_open tb2_geom_close tb2_geom_sizes tb2_geom_coords tb2_geom_block tb2_geom_nodeset tb2_geom_sideset
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
 tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
@@ -324,6 +325,40 @@ class Group(_Handle):
     def set_history(self, data, flags, alloc):
         data, flags, alloc = _f64(data), np.ascontiguousarray(flags, np.int32), np.ascontiguousarray(alloc, np.int32)
         _chk(lib().tb2_group_set_history(self.h, _p(data), _p(flags), _p(alloc)))
+
+
+def read_geom(path):
+    """TahoeII .geom -> (coords [nn,3], [conn per block], {node set id: nodes}, {side set id: [[element, facet]]}), all 0-based,
+    through the library's multi-threaded reader (tb2_geom_*)"""
+    h = C.c_void_p()
+    _chk(lib().tb2_geom_open(path.encode(), C.byref(h)))
+    try:
+        nn, nsd, nb, nns, nss = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _chk(lib().tb2_geom_sizes(h, C.byref(nn), C.byref(nsd), C.byref(nb), C.byref(nns), C.byref(nss)))
+        X = np.zeros((nn.value, 3))
+        _chk(lib().tb2_geom_coords(h, _p(X)))
+        blocks, nodesets, sidesets = [], {}, {}
+        for k in range(nb.value):
+            bid, nel, nen = C.c_int32(), C.c_int64(), C.c_int32()
+            _chk(lib().tb2_geom_block(h, k, C.byref(bid), C.byref(nel), C.byref(nen), None))
+            conn = np.zeros((nel.value, nen.value), np.int32)
+            _chk(lib().tb2_geom_block(h, k, None, None, None, _p(conn)))
+            blocks.append(conn)
+        for k in range(nns.value):
+            sid, n = C.c_int32(), C.c_int64()
+            _chk(lib().tb2_geom_nodeset(h, k, C.byref(sid), C.byref(n), None))
+            nodes = np.zeros(n.value, np.int32)
+            _chk(lib().tb2_geom_nodeset(h, k, None, None, _p(nodes)))
+            nodesets[sid.value] = nodes
+        for k in range(nss.value):
+            sid, blk, n = C.c_int32(), C.c_int32(), C.c_int64()
+            _chk(lib().tb2_geom_sideset(h, k, C.byref(sid), C.byref(blk), C.byref(n), None))
+            sides = np.zeros((n.value, 2), np.int32)
+            _chk(lib().tb2_geom_sideset(h, k, None, None, None, _p(sides)))
+            sidesets[sid.value] = sides
+        return X, blocks, nodesets, sidesets
+    finally:
+        lib().tb2_geom_close(h)
 
 
 class Traction(_Handle):

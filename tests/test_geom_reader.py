@@ -1,0 +1,101 @@
+"""the library's multi-threaded TahoeII .geom reader (tb2_geom_*; host code, runs without a GPU) against the
+reference's own geometry files as the reference reads them (coordinates / connectivity of the golden fixtures come from
+ModelManagerT through oracle/ref_dump.cpp) and against the test-side reader on generated meshes."""
+import os
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+
+import tahoe_input as ti
+from cases import Case
+
+REF_GEOM = "/root/reference/benchmark_XML/level.0/geometry"
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from tahoe_b200 import capi
+    capi.lib()
+    return capi
+
+
+def _same(capi, path):
+    X, blocks, ns, ss = capi.read_geom(path)
+    X0, conn0, ns0 = ti.read_geom(path)
+    assert np.array_equal(X, X0) and np.array_equal(np.concatenate(blocks), conn0)
+    # a negative entry ("all model nodes", beam.1.geom) stays -1 in the library; the test-side reader shifts it like an id
+    assert sorted(ns) == sorted(ns0) and all(np.array_equal(ns[k], np.where(ns0[k] < 0, -1, ns0[k])) for k in ns0)
+    ss0 = ti.read_sidesets(path)
+    assert sorted(ss) == sorted(ss0) and all(np.array_equal(ss[k], ss0[k]) for k in ss0)
+    return X, blocks, ns, ss
+
+
+@pytest.mark.parametrize("threads_worth", [3, 40])
+def test_generated_mesh_round_trip(capi, threads_worth):
+    """inline sections, jittered coordinates at full precision, side sets; the 40^3 file (6 MB) goes through the threaded path"""
+    n = threads_worth
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        X, conn, ns = ti.structured_cube(n, jitter=0.1)
+        X = ti.warp(X)
+        path = os.path.join(work, "mesh.geom")
+        ti.write_geom(path, X, conn, ns, sidesets=ti.cube_side_sets(n))
+        Xr, blocks, nsr, ssr = _same(capi, path)
+        assert np.array_equal(Xr, X) and np.array_equal(blocks[0], conn)  # %.17e round-trips every double
+        assert all(np.array_equal(nsr[k], ns[k]) for k in ns)
+        assert all(np.array_equal(ssr[k], ti.cube_side_sets(n)[k]) for k in ssr)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def test_node_records_in_any_order_and_comments(capi):
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        X, conn, ns = ti.structured_cube(2, jitter=0.0)
+        path = os.path.join(work, "mesh.geom")
+        ti.write_geom(path, X, conn, ns)
+        text = open(path).read()
+        head, nodes = text.split("*nodes\n")
+        lines = nodes.strip().splitlines()
+        body = lines[2:]
+        body = body[::-1]  # node records reversed: ids decide where a row goes
+        body.insert(3, "# a comment line in the middle of the records")
+        body[5] += "   # trailing comment"
+        open(path, "w").write(head + "*nodes\n" + "\n".join(lines[:2] + body) + "\n")
+        Xr, blocks, _, _ = capi.read_geom(path)
+        assert np.array_equal(Xr, X) and np.array_equal(blocks[0], conn)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def test_malformed_files_are_rejected(capi):
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        X, conn, ns = ti.structured_cube(2, jitter=0.0)
+        path = os.path.join(work, "mesh.geom")
+        ti.write_geom(path, X, conn, ns)
+        text = open(path).read()
+        for bad in (text.replace("*nodes", "*knots"), text[:len(text) // 2], text.replace("27  # number of nodes", "26  # number of nodes", 1),
+                    text.replace("\n1 1 2 5 4 10 11 14 13\n", "\n1 1 2 5 4 10 11 14 99\n")):
+            assert bad != text
+            open(path, "w").write(bad)
+            with pytest.raises(capi.Tb2Error):
+                capi.read_geom(path)
+        with pytest.raises(capi.Tb2Error):
+            capi.read_geom(os.path.join(work, "missing.geom"))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_GEOM), reason="the reference tree exists in the authoring container only")
+@pytest.mark.parametrize("geom,fixture", [("cube.1.geom", "ref_traction_a"), ("beam.1.geom", "ref_beam_newton")])
+def test_reference_geometry_files_as_the_reference_reads_them(capi, geom, fixture):
+    """external .elem / .node files (cube.1.geom style); coordinates and connectivity equal what ModelManagerT handed the
+    reference run that wrote the golden fixture"""
+    X, blocks, ns, ss = _same(capi, os.path.join(REF_GEOM, geom))
+    c = Case(fixture)
+    assert np.array_equal(X, c.X) and np.array_equal(np.concatenate(blocks), c.conn)
+    assert all(np.array_equal(ns[k], np.where(c.nodesets[k] < 0, -1, c.nodesets[k])) for k in c.nodesets)
+    assert all(np.array_equal(ss[k], c.sidesets[k]) for k in c.sidesets)
