@@ -146,7 +146,9 @@ int tb2_form_lumped_mass_host(tb2_group* group, double* h_mass);
 /* inertia branches of the element loops (implicit dynamics): ContinuumElementT::MassTypeT and
  * FormMa (ContinuumElementT.cpp:868-1002, called from SolidElementT::ElementRHSDriver :1243-1265): d_f[nn][3] = scale * M a with the
  * consistent (sum_ip rho w detJ0 N_a N_b) or lumped (HRZ diagonal, as tb2_form_lumped_mass) element mass on the reference
- * configuration.  Tahoe's RHS receives -constMa * (this). */
+ * configuration.  Tahoe's RHS receives -constMa * (this).  On a partitioned mesh the result is the rank's partial sum, like the
+ * internal force: follow with tb2_comm_sum_interface (the same holds for tb2_traction_form; tb2_form_mass adds to the rank's
+ * unassembled sub-domain matrix, which the distributed PCG already sums on the interface rows). */
 enum { TB2_MASS_CONSISTENT = 1 /* kConsistentMass */, TB2_MASS_LUMPED = 2 /* kLumpedMass */ };
 int tb2_form_inertial_force(tb2_group* group, int mass_type, double scale, const double* d_acc, double* d_f);
 int tb2_form_inertial_force_host(tb2_group* group, int mass_type, double scale, const double* h_acc, double* h_f);
