@@ -56,6 +56,28 @@ def static_pcg(m, X, ns):
     return d, it
 
 
+def dynamic_pcg(m, X, ns):
+    """effective system of an implicit step, (M + beta dt^2 K) x = f, from the rank's unassembled sub-domain matrices
+    (tb2_form_stiffness + tb2_matrix_scale + tb2_form_mass with a consistent mass): x on the local nodes, iteration count"""
+    g = capi.Group(m, capi.SMALL_STRAIN, capi.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    eqs = capi.Equations(m, code)
+    A = capi.Matrix(eqs)
+    A.form_stiffness_host(g, np.zeros_like(X))
+    A.scale(0.25 * 0.05 ** 2)
+    A.form_mass(g, 1, 1.0)
+    fext = np.zeros_like(X)
+    fext[ns[2], 0] = 1e-3
+    fext[ns[4], 1] = -2e-4
+    act = eqs.eqnos() > 0
+    x, it, rn = A.pcg_host(fext[act], rtol=1e-13, max_iter=20000)
+    d = np.zeros_like(X)
+    d[act] = x
+    A.close(); eqs.close(); g.close()
+    return d, it
+
+
 def nonlinear_solves(m, X, ns):
     """the two resident nonlinear drivers on this rank's sub-domain (the library takes the distributed path when the mesh has a
     communicator): PCGSolver_LS twin and Newton + Jacobi-PCG on a total-Lagrangian Neo-Hookean block.  Returns displacements and
@@ -178,11 +200,12 @@ def main():
     d, v, a = ex.get_state()
     mass = ex.mass_host()
     xs, its = static_pcg(m, part["coords"], part["nodesets"])
+    xd, itd = dynamic_pcg(m, part["coords"], part["nodesets"])
     d_cg, it_cg, d_nw, it_nw = nonlinear_solves(m, part["coords"], part["nodesets"])
     nn_glob = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
     # gather every rank's fields on rank 0 keyed by global node id
     out = [None] * world
-    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass, "xs": xs, "its": its,
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "mass": mass, "xs": xs, "its": its, "xd": xd, "itd": itd,
                                  "d_cg": d_cg, "it_cg": it_cg, "d_nw": d_nw, "it_nw": it_nw})
     ok = True
     if rank == 0:
@@ -193,6 +216,7 @@ def main():
         d1, v1, a1 = ex1.get_state()
         mass1 = ex1.mass_host()
         xs1, its1 = static_pcg(m1, X, ns)
+        xd1, itd1 = dynamic_pcg(m1, X, ns)
         d_cg1, it_cg1, d_nw1, it_nw1 = nonlinear_solves(m1, X, ns)
         print("nonlinear PCG iterations: single GPU %d, partitioned %s; Newton: %d, %s"
               % (it_cg1, [o["it_cg"] for o in out], it_nw1, [o["it_nw"] for o in out]))
@@ -202,6 +226,10 @@ def main():
             err = np.abs(o["xs"] - xs1[o["gid"]]).max() / np.abs(xs1).max()
             if not err < 1e-9 or abs(o["its"] - its1) > 3:
                 print("rank %d static PCG solution differs from the single-GPU solve: %.3e (its %d vs %d)" % (r, err, o["its"], its1))
+                ok = False
+            err = np.abs(o["xd"] - xd1[o["gid"]]).max() / np.abs(xd1).max()
+            if not err < 1e-9 or abs(o["itd"] - itd1) > 3:
+                print("rank %d implicit-step system (M + beta dt^2 K) differs from the single-GPU solve: %.3e (its %d vs %d)" % (r, err, o["itd"], itd1))
                 ok = False
             for nm, ref, cnt, cnt1, tol in (("d_cg", d_cg1, o["it_cg"], it_cg1, 1e-7), ("d_nw", d_nw1, o["it_nw"], it_nw1, 1e-9)):
                 err = np.abs(o[nm] - ref[o["gid"]]).max() / np.abs(ref).max()
