@@ -320,6 +320,24 @@ int tb2_newton_solve_host(tb2_nlpcg* work, tb2_matrix* A, const tb2_newton_param
                           const double* h_fext, int solve_max_iterations, int* status, int* iterations, double* error, double* error0,
                           int64_t* linear_iterations);
 
+/* The same driver for an implicit time integrator (FEManagerT::SolveStep with nonlinear_HHT, IntegratorT_factory.cpp:45-47): the
+ * unknown is the acceleration increment.  Residual = fext - constKd fint(u) - constMa M a (eNLHHTalpha.cpp:17-36), effective matrix
+ * constM M + constK K(u) (eLinearHHTalpha::eComputeParameters: constM = 1, constK = (1 + alpha) beta dt^2), update
+ * u += dcorr_a da, v += vcorr_a da, a += da on the active equations (nNLHHTalpha::Corrector, nNLHHTalpha.cpp:131-160,219-229:
+ * dcorr_a = beta dt^2, vcorr_a = gamma dt).  The caller applies the predictor and the kinematic BCs before the call.  With dt = 0
+ * (constK = dcorr_a = vcorr_a = 0) this is the initial-acceleration solve of FEManagerT::InitialCondition (FEManagerT.cpp:2053-2080). */
+typedef struct {
+    int32_t mass_type; /* TB2_MASS_CONSISTENT | TB2_MASS_LUMPED */
+    double  constM, constK, constMa, constKd, dcorr_a, vcorr_a;
+} tb2_dynamics;
+int tb2_newton_solve_dynamic(tb2_nlpcg* work, tb2_matrix* A, const tb2_newton_params* params, const tb2_dynamics* dynamics, double* d_u,
+                             double* d_v, double* d_a, const double* d_u_last, const double* d_fext, int solve_max_iterations,
+                             int* status, int* iterations, double* error, double* error0, int64_t* linear_iterations);
+int tb2_newton_solve_dynamic_host(tb2_nlpcg* work, tb2_matrix* A, const tb2_newton_params* params, const tb2_dynamics* dynamics,
+                                  double* h_u, double* h_v, double* h_a, const double* h_u_last, const double* h_fext,
+                                  int solve_max_iterations, int* status, int* iterations, double* error, double* error0,
+                                  int64_t* linear_iterations);
+
 /* ---- multi-GPU (replaces CommManagerT::AllGather / CommunicatorT::Sum) ------------ */
 /* One process per GPU.  The harness creates an NCCL unique id on rank 0, distributes it by its own
  * means, and every rank calls tb2_comm_init on its mesh.  h_interface_nodes are this rank's local node

@@ -33,7 +33,7 @@ SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2
 tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
 tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
-tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_scale
+tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_scale tb2_newton_solve_dynamic tb2_newton_solve_dynamic_host
 tb2_geom_open tb2_geom_close tb2_geom_sizes tb2_geom_coords tb2_geom_block tb2_geom_nodeset tb2_geom_sideset
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
@@ -589,4 +589,27 @@ def newton_solve_host(work, A, params, u, fext, u_last=None, solve_max_iteration
     st, it, e, e0, lin = C.c_int(0), C.c_int(0), C.c_double(0.0), C.c_double(0.0), C.c_int64(0)
     _chk(lib().tb2_newton_solve_host(work.h, A.h, C.byref(params), _p(u), _p(_f64(u_last)), _p(_f64(fext)), int(solve_max_iterations),
                                      C.byref(st), C.byref(it), C.byref(e), C.byref(e0), C.byref(lin)))
+    return st.value, it.value, e.value, e0.value, lin.value
+
+
+class Dynamics(C.Structure):
+    """tb2_dynamics: element / nodal constants of an implicit integrator step"""
+    _fields_ = [("mass_type", C.c_int32), ("constM", C.c_double), ("constK", C.c_double), ("constMa", C.c_double), ("constKd", C.c_double),
+                ("dcorr_a", C.c_double), ("vcorr_a", C.c_double)]
+
+
+def hht_dynamics(mass_type, dt, alpha=0.0):
+    """constants of NLHHTalpha(alpha) (HHTalpha::Set2ndOrder, eLinearHHTalpha / eNLHHTalpha::eComputeParameters,
+    nNLHHTalpha::nComputeParameters); `nonlinear_HHT` is alpha = 0: beta = 1/4, gamma = 1/2"""
+    gamma, beta = 0.5 * (1.0 - 2.0 * alpha), 0.25 * (1.0 - alpha) ** 2
+    return Dynamics(int(mass_type), 1.0, (1.0 + alpha) * beta * dt * dt, 1.0, 1.0 + alpha, beta * dt * dt, gamma * dt)
+
+
+def newton_solve_dynamic_host(work, A, params, dyn, u, v, a, fext, u_last=None, solve_max_iterations=-1):
+    """one implicit step's Newton solve on the device (tb2_newton_solve_dynamic_host): u, v, a [nn][3] updated in place; returns
+    (status, iterations, error, error0, linear iterations)"""
+    st, it, e, e0, lin = C.c_int(0), C.c_int(0), C.c_double(0.0), C.c_double(0.0), C.c_int64(0)
+    _chk(lib().tb2_newton_solve_dynamic_host(work.h, A.h, C.byref(params), C.byref(dyn), _p(u), _p(v), _p(a), _p(_f64(u_last)),
+                                             _p(_f64(fext)), int(solve_max_iterations), C.byref(st), C.byref(it), C.byref(e), C.byref(e0),
+                                             C.byref(lin)))
     return st.value, it.value, e.value, e0.value, lin.value

@@ -149,6 +149,12 @@ __global__ void k_nl_eq_owned(int64_t neq, const int* __restrict__ eq_node, cons
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < neq) w[i] = node_owned[eq_node[i] / 3];
 }
+// y = alpha y + x
+__global__ void __launch_bounds__(256) k_nl_axpby(int64_t n, double alpha, double* __restrict__ y, const double* __restrict__ x)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = alpha * y[i] + x[i];
+}
 
 } // namespace tb2
 
@@ -161,6 +167,7 @@ struct tb2_nlpcg {
     tb2_equations* eqs = nullptr;
     tb2_nlpcg_params prm{};
     DevBuf<double> R, R_last, dir, minv, fint, diag, partial, red;
+    DevBuf<double> fma; // [nn][3] inertia force of an implicit step
     DevBuf<unsigned char> eq_owned;
     int64_t residual_sweeps = 0, preconditioner_sweeps = 0;
 };
@@ -178,6 +185,10 @@ struct Ctx {
     const double* fext;
     const unsigned char* w;
     int iteration; // SolverT::fNumIteration
+    // implicit dynamics (tb2_newton_solve_dynamic): the unknown is the acceleration increment; null for static solves
+    const tb2_dynamics* dyn = nullptr;
+    double* v = nullptr;
+    double* a = nullptr;
 };
 
 int read2(Ctx& c, double out[2])
@@ -194,6 +205,12 @@ int form_rhs(Ctx& c, bool with_update, double h[2])
     tb2_nlpcg* s = c.s;
     TB2_CHECK(launch_element_forces(s->group, c.u, c.ul, c.iteration));
     TB2_CHECK(launch_node_gather(c.m, s->fint.p, true));
+    if (c.dyn) { // element residual of an implicit integrator: constKd fint + constMa M a (SolidElementT.cpp:1237-1265)
+        if (!s->fma.p) TB2_CUDA(s->fma.alloc(3 * c.m->nn));
+        TB2_CHECK(tb2_form_inertial_force(s->group, c.dyn->mass_type, c.dyn->constMa, c.a, s->fma.p));
+        const int64_t n3 = 3 * c.m->nn;
+        k_nl_axpby<<<(unsigned)((n3 + 255) / 256), 256, 0, c.st>>>(n3, c.dyn->constKd, s->fint.p, s->fma.p);
+    }
     if (comm_active(c.m)) TB2_CHECK(tb2_comm_sum_interface(c.m, s->fint.p));
     {
         ProfScope ps(c.m, kProfPcgVec, 2);
@@ -460,16 +477,23 @@ namespace {
 int newton_update(Ctx& c, const double* d_dx)
 {
     ProfScope ps(c.m, kProfPcgVec);
+    if (c.dyn) { // nNLHHTalpha::Corrector on the active equations (nNLHHTalpha.cpp:131-160): d += beta dt^2 da, v += gamma dt da, a += da
+        k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, c.s->eqs->eq_node.p, c.dyn->dcorr_a, d_dx, c.u);
+        k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, c.s->eqs->eq_node.p, c.dyn->vcorr_a, d_dx, c.v);
+        k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, c.s->eqs->eq_node.p, 1.0, d_dx, c.a);
+        return TB2_OK;
+    }
     k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, c.s->eqs->eq_node.p, 1.0, d_dx, c.u);
     return TB2_OK;
 }
 } // namespace
 
-extern "C" int tb2_newton_solve(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, double* d_u, const double* d_u_last,
-                                const double* d_fext, int solve_max_iterations, int* status, int* iterations, double* error_out,
-                                double* error0_out, int64_t* linear_iterations)
+static int newton_core(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, const tb2_dynamics* dyn, double* d_u, double* d_v,
+                       double* d_a, const double* d_u_last, const double* d_fext, int solve_max_iterations, int* status, int* iterations,
+                       double* error_out, double* error0_out, int64_t* linear_iterations)
 {
     TB2_ARG(s && A && np && d_u && d_fext && status);
+    TB2_ARG(!dyn || (d_v && d_a && (dyn->mass_type == TB2_MASS_CONSISTENT || dyn->mass_type == TB2_MASS_LUMPED)));
     TB2_ARG(A->eqs == s->eqs);
     tb2_mesh* m = s->group->mesh;
     DeviceGuard dg(m->device);
@@ -485,6 +509,9 @@ extern "C" int tb2_newton_solve(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_pa
     c.fext = d_fext;
     c.iteration = -1;
     c.w = nullptr;
+    c.dyn = dyn;
+    c.v = d_v;
+    c.a = d_a;
     if (comm_active(m)) {
         if (!s->eq_owned.p) {
             TB2_CUDA(s->eq_owned.alloc(c.n));
@@ -520,7 +547,11 @@ extern "C" int tb2_newton_solve(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_pa
         if (num_iterations == 1 || tan_iterations >= reform) { // NLSolver.cpp:143-160
             tan_iterations = 0;
             if ((rc = tb2_matrix_clear(A)) != TB2_OK) break;
-            if ((rc = tb2_form_stiffness(s->group, A, c.u, c.ul, c.iteration)) != TB2_OK) break;
+            if (!dyn || dyn->constK != 0.0) {
+                if ((rc = tb2_form_stiffness(s->group, A, c.u, c.ul, c.iteration)) != TB2_OK) break;
+                if (dyn && dyn->constK != 1.0 && (rc = tb2_matrix_scale(A, dyn->constK)) != TB2_OK) break;
+            }
+            if (dyn && dyn->constM != 0.0 && (rc = tb2_form_mass(s->group, A, dyn->mass_type, dyn->constM)) != TB2_OK) break; // effective mass
             if ((rc = tb2_group_status(s->group, nullptr)) != TB2_OK) break;
         }
         // NLSolver::Iterate: fLHS->Solve(fRHS) -- the update from a zero start guess (the solve overwrites its argument)
@@ -542,6 +573,54 @@ extern "C" int tb2_newton_solve(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_pa
     if (error0_out) *error0_out = error0;
     if (linear_iterations) *linear_iterations = lin_total;
     if (rc != TB2_OK) *status = TB2_SOLVER_FAILED; // NLSolver::Solve: any exception -> kFailed (NLSolver.cpp:247-262)
+    return rc;
+}
+
+extern "C" int tb2_newton_solve(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, double* d_u, const double* d_u_last,
+                                const double* d_fext, int solve_max_iterations, int* status, int* iterations, double* error_out,
+                                double* error0_out, int64_t* linear_iterations)
+{
+    return newton_core(s, A, np, nullptr, d_u, nullptr, nullptr, d_u_last, d_fext, solve_max_iterations, status, iterations, error_out,
+                       error0_out, linear_iterations);
+}
+
+extern "C" int tb2_newton_solve_dynamic(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, const tb2_dynamics* dyn, double* d_u,
+                                        double* d_v, double* d_a, const double* d_u_last, const double* d_fext, int solve_max_iterations,
+                                        int* status, int* iterations, double* error_out, double* error0_out, int64_t* linear_iterations)
+{
+    TB2_ARG(dyn);
+    return newton_core(s, A, np, dyn, d_u, d_v, d_a, d_u_last, d_fext, solve_max_iterations, status, iterations, error_out, error0_out,
+                       linear_iterations);
+}
+
+extern "C" int tb2_newton_solve_dynamic_host(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np, const tb2_dynamics* dyn, double* h_u,
+                                             double* h_v, double* h_a, const double* h_u_last, const double* h_fext,
+                                             int solve_max_iterations, int* status, int* iterations, double* error, double* error0,
+                                             int64_t* linear_iterations)
+{
+    TB2_ARG(s && A && np && dyn && h_u && h_v && h_a && h_fext && status);
+    tb2_mesh* m = s->group->mesh;
+    DeviceGuard dg(m->device);
+    const size_t bytes = 3 * m->nn * sizeof(double);
+    DevBuf<double> u, v, a, ul, fext;
+    TB2_CUDA(u.alloc(3 * m->nn));
+    TB2_CUDA(v.alloc(3 * m->nn));
+    TB2_CUDA(a.alloc(3 * m->nn));
+    TB2_CUDA(fext.alloc(3 * m->nn));
+    TB2_CUDA(cudaMemcpyAsync(u.p, h_u, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(v.p, h_v, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(a.p, h_a, bytes, cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(fext.p, h_fext, bytes, cudaMemcpyHostToDevice, m->stream));
+    if (h_u_last) {
+        TB2_CUDA(ul.alloc(3 * m->nn));
+        TB2_CUDA(cudaMemcpyAsync(ul.p, h_u_last, bytes, cudaMemcpyHostToDevice, m->stream));
+    }
+    const int rc = tb2_newton_solve_dynamic(s, A, np, dyn, u.p, v.p, a.p, h_u_last ? ul.p : nullptr, fext.p, solve_max_iterations, status,
+                                            iterations, error, error0, linear_iterations);
+    TB2_CUDA(cudaMemcpyAsync(h_u, u.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(h_v, v.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(h_a, a.p, bytes, cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
     return rc;
 }
 

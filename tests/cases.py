@@ -63,13 +63,14 @@ def relerr(a, b):
 MASS_TYPE = {"consistent_mass": 1, "lumped_mass": 2}  # ContinuumElementT::MassTypeT
 
 
-def implicit_dynamics(c, act, fint, inertia, solve):
+def implicit_dynamics(c, act, fint, inertia, solve, step_solve=None):
     """FEManagerT's step loop for the `nonlinear_HHT` integrator (IntegratorT_factory.cpp:45-47: NLHHTalpha(0.0), i.e. Newmark with
     beta = 1/4, gamma = 1/2) around NLSolver::Solve, restated for the tests.  The unknown of the Newton iteration is the acceleration
     increment: nNLHHTalpha::Predictor / ConsistentKBC / Corrector (nNLHHTalpha.cpp:24-160,219-229), element constants
     eLinearHHTalpha::eComputeParameters (constM = 1, constK = beta dt^2) and eNLHHTalpha (constMa = constKd = 1).
     FEManagerT::InitialCondition first solves the same system with dt = 0 for the initial acceleration (FEManagerT.cpp:2053-2080).
     fint(d) -> [nn,3]; inertia(a) -> M a [nn,3]; solve(d, constM, constK, R[act]) -> acceleration increment on the active dofs.
+    step_solve(d, v, a, fext, dt) -> iteration number, when given, replaces the Newton loop (a resident driver under test).
     Yields (step, d, v, a, iteration_number); step 0 is the initial-condition solve."""
     beta, gamma = 0.25, 0.5
     s = c.desc["solver"]
@@ -87,6 +88,9 @@ def implicit_dynamics(c, act, fint, inertia, solve):
         a[fixed] = (target[fixed] - d[fixed]) / dcorr_a if abs(dcorr_a) > 1e-12 else 0.0
         d[fixed] = target[fixed]
         v[fixed] += vcorr_a * a[fixed]
+        if step_solve is not None:
+            yield k, d, v, a, step_solve(d, v, a, fext, dt)
+            continue
         it = -1
         R = (fext - fint(d) - inertia(a))[act]
         e0 = e = np.linalg.norm(R)

@@ -765,6 +765,33 @@ def test_implicit_dynamics_matches_reference(tb2, name):
                 assert np.abs(arr - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300) + 1e-13, (k, nm)
 
 
+@pytest.mark.parametrize("name", IMPLICIT)
+def test_resident_implicit_newton_driver_matches_reference(tb2, name):
+    """a20 for an implicit integrator: the Newton solve of every nonlinear_HHT step (incl. the dt = 0 initial-acceleration solve) as
+    one C-ABI call (tb2_newton_solve_dynamic_host: residual with M a, M + beta dt^2 K, device PCG, corrector on d, v, a)"""
+    c = Case(name)
+    mesh, grp, mat = _group(tb2, c)
+    mt = MASS_TYPE[c.desc["element"]["mass_type"]]
+    code, _, _ = c.bc(0.0)
+    eqs = tb2.Equations(mesh, code)
+    A = tb2.Matrix(eqs)
+    work = tb2.NonlinearPCG(grp, eqs, tb2.nlpcg_params())
+    prm = tb2.newton_params(c.desc["solver"], pcg_rel_tolerance=1e-14)
+
+    def step_solve(d, v, a, fext, dt):
+        st, it, err, err0, lin = tb2.newton_solve_dynamic_host(work, A, prm, tb2.hht_dynamics(mt, dt), d, v, a, fext)
+        assert st == 1
+        return it
+
+    iters, ic = c.ref("iters"), int(c.ref("iters_ic")[0])
+    for k, d, v, a, it in implicit_dynamics(c, eqs.eqnos() > 0, None, None, None, step_solve):
+        assert it == (ic if k == 0 else iters[k - 1])
+        if k in c.dump_steps:
+            for nm, arr in (("d", d), ("v", v), ("a", a)):
+                ref = c.ref("%s_%d" % (nm, k))
+                assert np.abs(arr - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300) + 1e-13, (k, nm)
+
+
 # ------------------------------------------------------------------ natural_bc tractions (SURVEY 8f-4)
 @pytest.mark.parametrize("name", TRACTION)
 def test_traction_force_matches_oracle_and_reference(tb2, oracle, name):
