@@ -142,8 +142,10 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 			mat.hard[0] = j2.GetParameter("sigma_Y");
 			mat.hard[1] = j2.GetParameter("hardening");
 		}
-		if (list.NumLists("mass_scaling") > 0 && int(list.GetList("mass_scaling").GetParameter("type")) != 1 /* kFixedMassScaling */)
-			ExceptionT::BadInputValue(caller, "adaptive mass scaling re-forms the mass inside RHSDriver; only type=\"fixed\" is supported with the CUDA group");
+		/* <mass_scaling type="fixed" | "adaptive">: the scale factors and the scaled lumped mass stay ExplicitElementT's own host code
+		 * (ApplyMassScaling / LHSDriver, ExplicitElementT.cpp:492-618).  The adaptive type re-evaluates the factors every
+		 * update_interval calls from the INITIAL coordinates (:499-560) and the explicit mass is formed once, so in this reference it
+		 * is the fixed type; nothing on the device depends on it. */
 		if (list.NumLists("anp_tet4") > 0) ExceptionT::BadInputValue(caller, "anp_tet4 is a Tet4 option; the CUDA group is Hex8 only");
 	} else {
 		/* material constants */

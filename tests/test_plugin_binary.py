@@ -57,6 +57,13 @@ def _cases():
                                                              "scale_factor": "0.9"}},
                                 "material": {"type": "explicit_neo_hookean", "density": 1.0, "kappa": 1000.0, "mu": 5.0},
                                 "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        "explicit_solid_neo_adaptive": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                                         "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
+                                         "element": {"type": "explicit_solid", "mass_type": "lumped_mass",
+                                                     "mass_scaling": {"type": "adaptive", "target_dt": "%.6g" % (1.25 * 0.874 * 0.2 / np.sqrt(1000.0 + 20.0 / 3.0)),
+                                                                      "scale_factor": "0.9", "update_interval": "7"}},
+                                         "material": {"type": "explicit_neo_hookean", "density": 1.0, "kappa": 1000.0, "mu": 5.0},
+                                         "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
         "explicit_solid_j2": ({"time": {"num_steps": 300, "time_step": 0.4 * 0.2 / np.sqrt(1000.0 + 200.0 / 3.0), "schedules": [[(0.0, 0.0), (0.3, 1.0), (10.0, 1.0)]]},
                                "integrator": "central_difference",
                                "kbc": CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.08}], "fbc": [],
