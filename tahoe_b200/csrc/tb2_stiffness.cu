@@ -587,6 +587,9 @@ static StiffArgs stiff_args(tb2_group* g, const double* d_u, const double* d_ul,
 // the whole register file, the gather only runs in its tail).  So: the largest chunk that fits the scratch budget, one stream.
 static int ensure_gather_plan(tb2_matrix* A, elem_kernel_t k, int rec)
 {
+    // every element kernel that assembles into this matrix needs the opt-in shared-memory size (several groups -- one per material --
+    // may share a matrix, each with its own template instance)
+    TB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kElemSmem));
     if (A->k3_chunk > 0 && A->k3_rec >= rec) return TB2_OK; // (a later group with a larger record re-plans)
     tb2_mesh* m = A->eqs->mesh;
     const int64_t ne = m->ne, nn = m->nn;

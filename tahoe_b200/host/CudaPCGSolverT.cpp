@@ -82,6 +82,8 @@ SolverT::SolutionStatusT CudaPCGSolverT::Solve(int max_iterations)
 		const dArray2DT& disp = field[0];
 		const int ndof = eqnos.Length();
 		if (!fSolver) {
+			if (!dev->DeviceGroup())
+				ExceptionT::BadInputValue(caller, "CUDA_PCG_solver drives a single-material CUDA element group (this one has several materials)");
 			int status = tb2_nlpcg_create(dev->DeviceGroup(), dev->DeviceEquations(), &fParams, &fSolver);
 			if (status != TB2_OK) ExceptionT::GeneralFail(caller, "%s", tb2_last_error());
 		}

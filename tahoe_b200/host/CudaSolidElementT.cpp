@@ -70,7 +70,8 @@ CudaSolidElementT<BaseT>::~CudaSolidElementT(void)
 {
 	if (fMatrix) tb2_matrix_destroy(fMatrix);
 	if (fEqs) tb2_equations_destroy(fEqs);
-	if (fGroup) tb2_group_destroy(fGroup);
+	for (size_t i = 0; i < fGroups.size(); i++)
+		if (fGroups[i]) tb2_group_destroy(fGroups[i]);
 	if (fMesh) tb2_mesh_destroy(fMesh);
 }
 
@@ -105,13 +106,16 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 			ExceptionT::BadInputValue(caller, "strain_displacement must be \"standard\" or \"B-bar\"");
 		fFormulation = TB2_SMALL_STRAIN_BBAR; /* SmallStrainT::kMeanDilBbar */
 	}
-	if (this->fMaterialList->Length() != 1)
-		ExceptionT::BadInputValue(caller, "exactly one material per CUDA element group");
 	fIsJ2 = false;
 
+	/* one device group per material of the list (= per element block, SmallStrainT::CollectMaterialInfo :161-186); the groups share the
+	 * device mesh and each sees the elements of the other materials as switched off */
+	std::vector<tb2_material> mats;
+	const int num_materials = this->fMaterialList->Length();
 	tb2_material mat;
 	memset(&mat, 0, sizeof(mat));
 	if (this->Name() == kCudaSolidElementNames[3]) {
+		if (num_materials != 1) ExceptionT::BadInputValue(caller, "explicit_solid takes one material (ExplicitElementT scans a single mu / kappa)");
 		/* <explicit_solid>: mu / kappa / density are scanned from the material sub-tree and <j2_plasticity> selects the law, exactly
 		 * as ExplicitElementT::TakeParameterList does (ExplicitElementT.cpp:166-213) */
 		struct Finder {
@@ -147,9 +151,14 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 		 * update_interval calls from the INITIAL coordinates (:499-560) and the explicit mass is formed once, so in this reference it
 		 * is the fixed type; nothing on the device depends on it. */
 		if (list.NumLists("anp_tet4") > 0) ExceptionT::BadInputValue(caller, "anp_tet4 is a Tet4 option; the CUDA group is Hex8 only");
-	} else {
+		mats.push_back(mat);
+	} else
+	for (int im = 0; im < num_materials; im++) {
+		memset(&mat, 0, sizeof(mat));
+		const char* block_name = (fFormulation == TB2_SMALL_STRAIN || fFormulation == TB2_SMALL_STRAIN_BBAR) ? "small_strain_element_block" : "large_strain_element_block";
+		const ParameterListT& scope = (list.NumLists(block_name) == num_materials) ? list.GetList(block_name, im) : list;
 		/* material constants */
-		ContinuumMaterialT* cmat = (*(this->fMaterialList))[0];
+		ContinuumMaterialT* cmat = (*(this->fMaterialList))[im];
 		if (dynamic_cast<SSKStV*>(cmat)) mat.kind = TB2_SSKSTV;
 		else if (dynamic_cast<FDKStV*>(cmat)) mat.kind = TB2_FDKSTV;
 		else if (dynamic_cast<J2Simo3D*>(cmat)) mat.kind = TB2_J2_SIMO; /* before its base SimoIso3D */
@@ -162,12 +171,12 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 		mat.lambda = iso->Lambda();
 		mat.kappa = iso->Kappa();
 		mat.density = const_cast<SolidMaterialT*>(smat)->Density();
-		fIsJ2 = (mat.kind == TB2_J2_SIMO);
-		if (fIsJ2) { /* K(alpha): C1functions/LinearT.h:71, LinearExponentialT.cpp:48-57 */
-			const ParameterListT* lin = FindList(list, "linear_function");
-			const ParameterListT* lexp = FindList(list, "linear_exponential");
-			const ParameterListT* plaw = FindList(list, "power_law");
-			const ParameterListT* spline = FindList(list, "cubic_spline");
+		fIsJ2 = fIsJ2 || (mat.kind == TB2_J2_SIMO);
+		if (mat.kind == TB2_J2_SIMO) { /* K(alpha): C1functions/LinearT.h:71, LinearExponentialT.cpp:48-57 */
+			const ParameterListT* lin = FindList(scope, "linear_function");
+			const ParameterListT* lexp = FindList(scope, "linear_exponential");
+			const ParameterListT* plaw = FindList(scope, "power_law");
+			const ParameterListT* spline = FindList(scope, "cubic_spline");
 			if (lin) {
 				mat.hard_kind = TB2_HARD_LINEAR;
 				mat.hard[0] = lin->GetParameter("a");
@@ -198,7 +207,7 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 			} else
 				ExceptionT::BadInputValue(caller, "Simo_J2 hardening must be linear_function, linear_exponential, power_law or cubic_spline");
 		}
-
+		mats.push_back(mat);
 	}
 
 	/* connectivity of all blocks, in block order then file order (ElementBaseT.cpp:607-632) */
@@ -209,9 +218,21 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 	}
 	const dArray2DT& X = this->ElementSupport().InitialCoordinates();
 	Check(tb2_mesh_create(0, X.MajorDim(), (int64_t)(conn.size() / 8), &conn[0], X.Pointer(), &fMesh), caller);
-	Check(tb2_group_create(fMesh, fFormulation, &mat, &fGroup), caller);
-	fMaterialKind = mat.kind;
+	fGroups.resize(mats.size(), NULL);
+	fKinds.resize(mats.size());
+	for (size_t im = 0; im < mats.size(); im++) {
+		Check(tb2_group_create(fMesh, fFormulation, &mats[im], &fGroups[im]), caller);
+		fKinds[im] = mats[im].kind;
+	}
+	fGroup = fGroups[0];
+	fMaterialKind = mats.size() == 1 ? mats[0].kind : -1; /* device stress output: single-material groups */
 	fFint.Dimension(X.MajorDim(), 3);
+	if (fGroups.size() > 1) {
+		fPart.Dimension(X.MajorDim(), 3);
+		ArrayT<ElementCardT::StatusT> status;
+		this->GetStatus(status);
+		SetStatus(status); /* installs the per-material element masks */
+	}
 }
 
 template <class BaseT>
@@ -242,7 +263,11 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 	if (formKd) {
 		const double* last = fIsJ2 ? field(-1, 0).Pointer() : NULL;
 		int iteration = this->ElementSupport().IterationNumber(this->Group());
-		Check(tb2_form_internal_force_host(fGroup, disp.Pointer(), last, iteration, fFint.Pointer()), caller);
+		Check(tb2_form_internal_force_host(fGroups[0], disp.Pointer(), fKinds[0] == TB2_J2_SIMO ? last : NULL, iteration, fFint.Pointer()), caller);
+		for (size_t i = 1; i < fGroups.size(); i++) { /* further materials: elements of the others are masked off, the parts add up */
+			Check(tb2_form_internal_force_host(fGroups[i], disp.Pointer(), fKinds[i] == TB2_J2_SIMO ? last : NULL, iteration, fPart.Pointer()), caller);
+			fFint += fPart;
+		}
 		fFint *= -constKd;
 	}
 
@@ -260,8 +285,10 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 			for (int i = 0; i < 3; i++) fBodyAcc.SetColumn(i, -this->fBody[i] * loadfactor);
 			acc = fBodyAcc.Pointer();
 		}
-		Check(tb2_form_inertial_force_host(fGroup, int(this->fMassType), -constMa, acc, fMa.Pointer()), caller);
-		fFint += fMa;
+		for (size_t i = 0; i < fGroups.size(); i++) { /* each material with its own density */
+			Check(tb2_form_inertial_force_host(fGroups[i], int(this->fMassType), -constMa, acc, fMa.Pointer()), caller);
+			fFint += fMa;
+		}
 	}
 
 	/* RHS += -(constKd fint + constMa M a) on the active equations: one call for the whole group (SolverT::AssembleRHS, SolverT.cpp:446-477) */
@@ -297,11 +324,13 @@ void CudaSolidElementT<BaseT>::LHSDriver(GlobalT::SystemTypeT sys_type)
 	int iteration = this->ElementSupport().IterationNumber(this->Group());
 	Check(tb2_matrix_clear(fMatrix), caller);
 	if (haveK) {
-		Check(tb2_form_stiffness_host(fGroup, fMatrix, field[0].Pointer(), last, iteration), caller);
+		for (size_t i = 0; i < fGroups.size(); i++)
+			Check(tb2_form_stiffness_host(fGroups[i], fMatrix, field[0].Pointer(), fKinds[i] == TB2_J2_SIMO ? last : NULL, iteration), caller);
 		if (fabs(constK - 1.0) > 0.0) Check(tb2_matrix_scale(fMatrix, constK), caller); /* eLinearHHTalpha::FormK: (1 + alpha) beta dt^2 */
 	}
 	if (haveM) /* effective mass of an implicit integrator: constM M (ContinuumElementT::FormMass) */
-		Check(tb2_form_mass(fGroup, fMatrix, int(this->fMassType), constM), caller);
+		for (size_t i = 0; i < fGroups.size(); i++)
+			Check(tb2_form_mass(fGroups[i], fMatrix, int(this->fMassType), constM), caller);
 	cuda_lhs->AddDeviceMatrix(fMatrix, 1.0);
 }
 
@@ -365,28 +394,31 @@ template <class BaseT>
 void CudaSolidElementT<BaseT>::SetStatus(const ArrayT<ElementCardT::StatusT>& status)
 {
 	BaseT::SetStatus(status);
-	if (!fGroup) return;
+	if (fGroups.empty()) return;
 	std::vector<uint8_t> off(status.Length());
-	bool any = false;
-	for (int i = 0; i < status.Length(); i++) {
-		off[i] = status[i] == ElementCardT::kOFF ? 1 : 0;
-		any = any || off[i];
+	for (size_t g = 0; g < fGroups.size(); g++) {
+		bool any = false;
+		for (int i = 0; i < status.Length(); i++) {
+			/* off for this device group: switched off by the user, or an element of another material */
+			off[i] = (status[i] == ElementCardT::kOFF || (fGroups.size() > 1 && this->fElementCards[i].MaterialNumber() != int(g))) ? 1 : 0;
+			any = any || off[i];
+		}
+		Check(tb2_group_set_element_status(fGroups[g], any ? &off[0] : NULL), "CudaSolidElementT::SetStatus");
 	}
-	Check(tb2_group_set_element_status(fGroup, any ? &off[0] : NULL), "CudaSolidElementT::SetStatus");
 }
 
 template <class BaseT>
 void CudaSolidElementT<BaseT>::CloseStep(void)
 {
 	BaseT::CloseStep();
-	if (fGroup) Check(tb2_group_close_step(fGroup), "CudaSolidElementT::CloseStep");
+	for (size_t i = 0; i < fGroups.size(); i++) Check(tb2_group_close_step(fGroups[i]), "CudaSolidElementT::CloseStep");
 }
 
 template <class BaseT>
 GlobalT::RelaxCodeT CudaSolidElementT<BaseT>::ResetStep(void)
 {
 	GlobalT::RelaxCodeT relax = BaseT::ResetStep();
-	if (fGroup) Check(tb2_group_reset_step(fGroup), "CudaSolidElementT::ResetStep");
+	for (size_t i = 0; i < fGroups.size(); i++) Check(tb2_group_reset_step(fGroups[i]), "CudaSolidElementT::ResetStep");
 	return relax;
 }
 
@@ -398,17 +430,20 @@ template <class BaseT>
 void CudaSolidElementT<BaseT>::HistoryToCards(void) const
 {
 	const char caller[] = "CudaSolidElementT::HistoryToCards";
-	if (!fIsJ2 || !fGroup) return;
+	if (!fIsJ2 || fGroups.empty()) return;
 	const int ne = this->fElementCards.Length();
 	std::vector<double> data((size_t) ne * kJ2CardDoubles);
 	std::vector<int32_t> flags((size_t) ne * kJ2CardInts), alloc(ne);
-	Check(tb2_group_get_history(fGroup, &data[0], &flags[0], &alloc[0]), caller);
+	for (size_t g = 0; g < fGroups.size(); g++) {
+	if (fKinds[g] != TB2_J2_SIMO) continue;
+	Check(tb2_group_get_history(fGroups[g], &data[0], &flags[0], &alloc[0]), caller);
 	for (int e = 0; e < ne; e++) {
-		if (!alloc[e]) continue;
+		if (!alloc[e] || (fGroups.size() > 1 && this->fElementCards[e].MaterialNumber() != int(g))) continue;
 		ElementCardT& card = const_cast<ElementCardT&>(this->fElementCards[e]);
 		card.Dimension(kJ2CardInts, kJ2CardDoubles);
 		for (int i = 0; i < kJ2CardInts; i++) card.IntegerData()[i] = flags[(size_t) e * kJ2CardInts + i];
 		memcpy(card.DoubleData().Pointer(), &data[(size_t) e * kJ2CardDoubles], sizeof(double) * kJ2CardDoubles);
+	}
 	}
 }
 
@@ -416,20 +451,23 @@ template <class BaseT>
 void CudaSolidElementT<BaseT>::HistoryFromCards(void)
 {
 	const char caller[] = "CudaSolidElementT::HistoryFromCards";
-	if (!fIsJ2 || !fGroup) return;
+	if (!fIsJ2 || fGroups.empty()) return;
 	const int ne = this->fElementCards.Length();
+	for (size_t g = 0; g < fGroups.size(); g++) {
+	if (fKinds[g] != TB2_J2_SIMO) continue;
 	std::vector<double> data((size_t) ne * kJ2CardDoubles, 0.0);
 	std::vector<int32_t> flags((size_t) ne * kJ2CardInts, 0), alloc(ne, 0);
 	for (int e = 0; e < ne; e++) {
 		const ElementCardT& card = this->fElementCards[e];
-		if (!card.IsAllocated()) continue;
+		if (!card.IsAllocated() || (fGroups.size() > 1 && card.MaterialNumber() != int(g))) continue;
 		if (card.IntegerData().Length() != kJ2CardInts || card.DoubleData().Length() != kJ2CardDoubles)
 			ExceptionT::SizeMismatch(caller, "element %d: restart data is not a Simo_J2 Hex8 record", e + 1);
 		alloc[e] = 1;
 		for (int i = 0; i < kJ2CardInts; i++) flags[(size_t) e * kJ2CardInts + i] = card.IntegerData()[i];
 		memcpy(&data[(size_t) e * kJ2CardDoubles], card.DoubleData().Pointer(), sizeof(double) * kJ2CardDoubles);
 	}
-	Check(tb2_group_set_history(fGroup, &data[0], &flags[0], &alloc[0]), caller);
+	Check(tb2_group_set_history(fGroups[g], &data[0], &flags[0], &alloc[0]), caller);
+	}
 }
 
 template <class BaseT>

@@ -27,6 +27,8 @@
 
 #include "tahoe_b200.h"
 
+#include <vector>
+
 namespace Tahoe {
 
 class CudaPCGMatrixT;
@@ -75,7 +77,8 @@ public:
 	/*@}*/
 
 	virtual tb2_mesh* DeviceMesh(void) { return fMesh; }
-	virtual tb2_group* DeviceGroup(void) { return fGroup; }
+	/** the device group of a single-material element group (what the resident solvers drive); NULL when the group has several materials */
+	virtual tb2_group* DeviceGroup(void) { return fGroups.size() == 1 ? fGroup : NULL; }
 	virtual tb2_equations* DeviceEquations(void);
 	virtual const FieldT& DeviceField(void) const { return this->Field(); }
 	virtual int SolverGroup(void) const { return this->Group(); }
@@ -105,7 +108,10 @@ private:
 
 	int fFormulation;
 	tb2_mesh* fMesh;
-	tb2_group* fGroup;
+	tb2_group* fGroup;               /**< fGroups[0] */
+	std::vector<tb2_group*> fGroups; /**< one device group per material of the list; they share fMesh and mask each other's elements off */
+	std::vector<int> fKinds;         /**< tb2_material_kind of each */
+	dArray2DT fPart;                 /**< [nn][3] one material's share of a nodal force */
 	tb2_equations* fEqs;   /**< built lazily: equation numbers are set after TakeParameterList */
 	tb2_matrix* fMatrix;   /**< device tangent of this group (structure from the mesh) */
 	bool fIsJ2;

@@ -87,13 +87,16 @@ def warp(coords):
 # ----------------------------------------------------------------------------
 # TahoeII .geom
 # ----------------------------------------------------------------------------
-def write_geom(path, coords, conn, nodesets, title="structured hex block", sidesets=None):
+def write_geom(path, coords, conn, nodesets, title="structured hex block", sidesets=None, block_sizes=None):
+    """block_sizes: element counts of consecutive element blocks (ids 1, 2, ...); default one block"""
     sidesets = sidesets or {}
+    block_sizes = block_sizes or [conn.shape[0]]
+    assert sum(block_sizes) == conn.shape[0]
     nn, ne = coords.shape[0], conn.shape[0]
     with open(path, "w") as f:
         f.write("*version\n1.0\n*title\n%s\n*dimensions\n" % title)
-        f.write("%d  # number of nodes\n3  # number of spatial dimensions\n1  # number of element sets\n" % nn)
-        f.write("# [ID] [nel] [nen]\n1 %d 8\n" % ne)
+        f.write("%d  # number of nodes\n3  # number of spatial dimensions\n%d  # number of element sets\n" % (nn, len(block_sizes)))
+        f.write("# [ID] [nel] [nen]\n" + "".join("%d %d 8\n" % (b + 1, nb) for b, nb in enumerate(block_sizes)))
         f.write("%d  # number of node sets\n# [ID] [nnd]\n" % len(nodesets))
         for sid in sorted(nodesets):
             f.write("%d %d\n" % (sid, len(nodesets[sid])))
@@ -113,9 +116,13 @@ def write_geom(path, coords, conn, nodesets, title="structured hex block", sides
             f.write("*set\n%d  # number of sides\n" % len(sidesets[sid]))
             for e, fc in sidesets[sid]:
                 f.write("%d %d\n" % (e + 1, fc + 1))
-        f.write("*elements\n*set\n%d  # number of elements\n8  # number of element nodes\n" % ne)
-        for e in range(ne):
-            f.write("%d %s\n" % (e + 1, " ".join(str(int(v) + 1) for v in conn[e])))
+        f.write("*elements\n")
+        e0 = 0
+        for nb in block_sizes:
+            f.write("*set\n%d  # number of elements\n8  # number of element nodes\n" % nb)
+            for e in range(e0, e0 + nb):  # element ids restart in every block
+                f.write("%d %s\n" % (e - e0 + 1, " ".join(str(int(v) + 1) for v in conn[e])))
+            e0 += nb
         f.write("# end elements\n*nodes\n%d  # number of nodes\n3  # number of spatial dimensions\n" % nn)
         for n in range(nn):
             f.write("%d %.17e %.17e %.17e\n" % (n + 1, coords[n, 0], coords[n, 1], coords[n, 2]))
@@ -319,9 +326,9 @@ def write_xml(path, d):
     small = e["type"] == "small_strain"
     blk = "small_strain_element_block" if small else "large_strain_element_block"
     mlist = "small_strain_material_3D" if small else "large_strain_material_3D"
-    L.append('      <%s><block_ID_list><String value="1"/></block_ID_list>\n        <%s>' % (blk, mlist))
     explicit = m["type"] in ("explicit_neo_hookean", "explicit_J2")
     if explicit:
+        L.append('      <%s><block_ID_list><String value="1"/></block_ID_list>\n        <%s>' % (blk, mlist))
         L.append('          <RG_split_general density="%.17g"><rg_eq_potential><neo-hookean kappa="%.17g" mu="%.17g"/></rg_eq_potential>'
                  % (m["density"], m["kappa"], m["mu"]))
         L.append("          </RG_split_general>\n        </%s>\n      </%s>" % (mlist, blk))
@@ -329,24 +336,23 @@ def write_xml(path, d):
             L.append('      <j2_plasticity sigma_Y="%.17g" hardening="%.17g"/>' % (m["sigma_Y"], m["hardening_modulus"]))
         if e.get("mass_scaling"):
             L.append("      <mass_scaling %s/>" % " ".join('%s="%s"' % kv for kv in e["mass_scaling"].items()))
-        L.append("    </%s>\n  </element_list>" % e.get("tag", e["type"]))
-    else:
-        L.append('          <%s density="%.17g">' % (m["type"], m["density"]))
-    if explicit:
-        pass
-    elif "E" in m:
-        L.append('            <E_and_nu Poisson_ratio="%.17g" Young_modulus="%.17g"/>' % (m["nu"], m["E"]))
-    else:
-        L.append('            <bulk_and_shear bulk_modulus="%.17g" shear_modulus="%.17g"/>' % (m["kappa"], m["mu"]))
-    h = m.get("hardening")
-    if h and h["type"] == "cubic_spline":
-        L.append('            <cubic_spline fixity="%s">' % h["fixity"])
-        L += ['              <OrderedPair x="%.17g" y="%.17g"/>' % (x, y) for x, y in h["points"]]
-        L.append("            </cubic_spline>")
-    elif h:
-        L.append("            <%s %s/>" % (h["type"], " ".join('%s="%.17g"' % (k, v) for k, v in h.items() if k != "type")))
-    if not explicit:
-        L.append("          </%s>\n        </%s>\n      </%s>\n    </%s>\n  </element_list>" % (m["type"], mlist, blk, e.get("tag", e["type"])))
+    # one element block per material: block i+1 of the .geom takes materials[i] (default: one block, d["material"])
+    for ib, mi in enumerate([] if explicit else (d.get("materials") or [m])):
+        L.append('      <%s><block_ID_list><String value="%d"/></block_ID_list>\n        <%s>' % (blk, ib + 1, mlist))
+        L.append('          <%s density="%.17g">' % (mi["type"], mi["density"]))
+        if "E" in mi:
+            L.append('            <E_and_nu Poisson_ratio="%.17g" Young_modulus="%.17g"/>' % (mi["nu"], mi["E"]))
+        else:
+            L.append('            <bulk_and_shear bulk_modulus="%.17g" shear_modulus="%.17g"/>' % (mi["kappa"], mi["mu"]))
+        h = mi.get("hardening")
+        if h and h["type"] == "cubic_spline":
+            L.append('            <cubic_spline fixity="%s">' % h["fixity"])
+            L += ['              <OrderedPair x="%.17g" y="%.17g"/>' % (x, y) for x, y in h["points"]]
+            L.append("            </cubic_spline>")
+        elif h:
+            L.append("            <%s %s/>" % (h["type"], " ".join('%s="%.17g"' % (k, v) for k, v in h.items() if k != "type")))
+        L.append("          </%s>\n        </%s>\n      </%s>" % (mi["type"], mlist, blk))
+    L.append("    </%s>\n  </element_list>" % e.get("tag", e["type"]))
     s = d["solver"]
     attrs = " ".join('%s="%s"' % (k, v) for k, v in s.items() if k not in ("type", "matrix", "matrix_attrs"))
     L.append("  <%s %s><%s %s/></%s>\n</tahoe>" % (s["type"], attrs, s["matrix"], s.get("matrix_attrs", ""), s["type"]))

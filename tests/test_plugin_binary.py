@@ -123,6 +123,21 @@ def _cases():
                                       "element": {"type": "updated_lagrangian"},
                                       "material": dict(j2, hardening={"type": "power_law", "a": 0.25, "b": 1.0, "c": 400.0, "n": 0.8}),
                                       "solver": newton}, None),
+        # two element blocks with different materials in one element group (a1: ElementCardT material ids): one device group per material
+        "static_tl_two_materials_pcg": ({"time": {"num_steps": 2, "time_step": 0.5, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                         "element": {"type": "total_lagrangian", "nodal_output": "stress"}, "material": simo_soft,
+                                         "materials": [simo_soft, {"type": "large_strain_StVenant", "density": 2.0, "E": 300.0, "nu": 0.3}],
+                                         "solver": newton}, pcg),
+        "static_ul_j2_and_elastic_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                         "element": {"type": "updated_lagrangian"}, "material": j2,
+                                         "materials": [dict(j2, hardening={"type": "power_law", "a": 0.25, "b": 1.0, "c": 400.0, "n": 0.8}), simo_soft, ],
+                                         "solver": newton}, None),
+        "explicit_tl_two_materials_gravity": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                                               "kbc": CLAMP, "fbc": [],
+                                               "element": {"type": "total_lagrangian", "mass_type": "lumped_mass",
+                                                           "body_force": {"schedule": 1, "vector": [0.0, 0.3, -9.81]}},
+                                               "material": simo, "materials": [simo, dict(simo, density=3.0, mu=8.0)],
+                                               "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
         # J2: device K1 with history, Tahoe's host tangent + SPOOLES (non-symmetric tangent)
         "static_ul_j2_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                              "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton}, None),
@@ -132,7 +147,8 @@ def _cases():
 def _write(work, name, desc, cuda, solver_override, n=5, tahoe_attrs=None, suffix=""):
     X, conn, ns = ti.structured_cube(n, jitter=0.15)
     if not os.path.exists(os.path.join(work, "mesh.geom")):
-        ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
+        nmat = len(desc.get("materials") or [0])  # several materials: the bottom two element layers are block 1, the rest block 2
+        ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns, block_sizes=None if nmat == 1 else [2 * n * n, (n - 2) * n * n])
     d = dict(desc, geometry_file="mesh.geom", output_inc=desc["time"]["num_steps"])
     d["element"] = dict(desc["element"], nodal_output=desc["element"].get("nodal_output", True))
     if cuda:
@@ -209,9 +225,9 @@ def test_plugin_reproduces_reference_output(name):
         assert np.abs(a - b).max() < tol * np.abs(a).max()
         if name.endswith("nlpcg"):
             assert "device PCG" in r1.stdout
-        if name.endswith("stress_out"):
+        if name.endswith("stress_out") or name == "static_tl_two_materials_pcg":
             assert a.shape[1] == 9
-            assert ("nodal stresses extrapolated and averaged on the device" in r1.stdout) == (not name.endswith("host_stress_out"))
+            assert ("nodal stresses extrapolated and averaged on the device" in r1.stdout) == name.endswith("simo_stress_out")
             for col in range(9):  # every column against its own scale: D_X D_Y D_Z s11 s22 s33 s23 s13 s12
                 assert np.abs(a[:, col] - b[:, col]).max() < 1e-9 * np.abs(a[:, col]).max()
     finally:
