@@ -525,6 +525,7 @@ __global__ void __launch_bounds__(128) k_nodal_stress(const ElemArgs p, double* 
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= p.ne) return;
+    if (p.off && p.off[e]) return; // SolidElementT::ComputeOutput skips kOFF elements (SolidElementT.cpp:1450); the averaging does too
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
@@ -600,22 +601,27 @@ __global__ void __launch_bounds__(128) k_nodal_stress(const ElemArgs p, double* 
             out48[(int64_t)(6 * a + I) * p.stride + e] = 0.125 * (S[0][I] + r3 * (s0 * S[1][I] + s1 * S[2][I] + s2 * S[3][I]));
     }
 }
-// GroupAverageT::AssembleAverage + Average: sum of the incident elements' nodal values (ascending element order) times 1 / count
+// GroupAverageT::AssembleAverage + Average: sum of the incident ACTIVE elements' nodal values (ascending element order) times
+// 1 / their count; a node with no active element keeps zeros (GroupAverageT.cpp:190-205 divides only where the count is positive)
 __global__ void __launch_bounds__(256) k_node_average6(int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
-                                                      const double* __restrict__ out48, int64_t stride, double* __restrict__ out)
+                                                      const double* __restrict__ out48, int64_t stride,
+                                                      const unsigned char* __restrict__ off, double* __restrict__ out)
 {
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= nn) return;
     const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
     double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int count = 0;
     for (int k = k0; k < k1; k++) {
         const int ent = __ldg(inc + k);
         const int64_t e = ent >> 3;
         const int a = ent & 7;
+        if (off && off[e]) continue;
+        count++;
 #pragma unroll
         for (int I = 0; I < 6; I++) acc[I] += __ldg(out48 + (int64_t)(6 * a + I) * stride + e);
     }
-    const double s = k1 > k0 ? 1.0 / (double)(k1 - k0) : 0.0;
+    const double s = count > 0 ? 1.0 / (double)count : 0.0;
 #pragma unroll
     for (int I = 0; I < 6; I++) out[6 * n + I] = acc[I] * s;
 }
@@ -1388,10 +1394,6 @@ int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
         set_error("nodal stress output is implemented for SSKStV, FDKStV and SimoIso3D (material %d)", g->mat.kind);
         return TB2_ERR_ARG;
     }
-    if (g->off.p) {
-        set_error("nodal stress output with switched-off elements is not implemented (the averaging counts would differ)");
-        return TB2_ERR_ARG;
-    }
     if (!m->out48.p) TB2_CUDA(m->out48.alloc((size_t)48 * m->stride));
     ElemArgs p{};
     p.e_begin = 0;
@@ -1402,9 +1404,10 @@ int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
     p.u = d_u;
     p.mat = g->mc;
     p.status = g->status.p;
+    p.off = g->off.p;
     ProfScope ps(m, kProfOther, 2);
     k<<<(unsigned)((m->ne + 127) / 128), 128, 0, m->stream>>>(p, m->out48.p);
-    k_node_average6<<<(unsigned)((m->nn + 255) / 256), 256, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->out48.p, m->stride, d_stress);
+    k_node_average6<<<(unsigned)((m->nn + 255) / 256), 256, 0, m->stream>>>(m->nn, m->inc_ptr.p, m->inc.p, m->out48.p, m->stride, g->off.p, d_stress);
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
 }

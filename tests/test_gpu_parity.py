@@ -105,6 +105,25 @@ def test_nodal_stress_output_matches_oracle(tb2, oracle, form, matname):
     assert relerr(grp.nodal_stress_host(u), ref) < TOL
 
 
+def test_nodal_stress_output_with_switched_off_elements(tb2):
+    """ElementCardT::kOFF elements take no part in the output (SolidElementT.cpp:1450) nor in the nodal averaging counts: the device
+    result equals the output of the mesh that only has the active elements, bit for bit; nodes without an active element keep 0"""
+    X, conn, _ = ti.structured_cube(6, 5, 4, jitter=0.15)
+    u = 0.02 * X @ np.array([[0.3, -0.2, 0.1], [0.05, 0.4, -0.3], [0.2, 0.1, -0.25]])
+    off = np.zeros(conn.shape[0], np.uint8)
+    off[::3] = 1
+    off[:31] = 1  # a whole corner region: some nodes lose all their elements
+    mat = tb2.material({"type": "Simo_isotropic", "density": 1.0, "kappa": 80.0, "mu": 30.0})
+    form = tb2.form_of({"type": "updated_lagrangian"})
+    full = tb2.Group(tb2.Mesh(X, conn), form, mat)
+    full.set_element_status(off)
+    got = full.nodal_stress_host(u)
+    want = tb2.Group(tb2.Mesh(X, conn[off == 0]), form, mat).nodal_stress_host(u)
+    assert np.array_equal(got, want)
+    orphan = np.setdiff1d(np.arange(X.shape[0]), np.unique(conn[off == 0]))
+    assert len(orphan) > 0 and np.all(got[orphan] == 0.0) and np.abs(got).max() > 0.1
+
+
 def test_irregular_valence_mesh_matches_oracle(tb2, oracle):
     """nodes with more than 8 incident elements (here up to 16: a layer of elements is present twice) leave the fixed-width
     incidence table and take the general paths of the node gather, the adjacency / contribution lists and the colouring"""
