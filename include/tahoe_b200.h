@@ -170,9 +170,15 @@ int tb2_group_get_explicit_history(tb2_group* group, double* h_hist);
 /* Nodal stress output: SolidElementT::ComputeOutput, iNodalStress branch (SolidElementT.cpp:1352-1840) -- Cauchy
  * stress at the integration points, extrapolated with HexahedronT::SetExtrapolation (HexahedronT.cpp:2099-2150) and averaged over
  * the elements at each node (GroupAverageT.cpp:40-49,190-205).  d_stress[nn][6], order 11,22,33,23,13,12.  SSKStV (incl. B-bar),
- * FDKStV and SimoIso3D; other materials return TB2_ERR_ARG. */
+ * FDKStV and SimoIso3D (J2Simo3D through tb2_group_nodal_stress_at); other materials return TB2_ERR_ARG.  Switched-off elements take
+ * no part in the values or in the averaging counts. */
 int tb2_group_nodal_stress(tb2_group* group, const double* d_u, double* d_stress);
 int tb2_group_nodal_stress_host(tb2_group* group, const double* h_u, double* h_stress);
+/* the same for a history material (J2Simo3D): SolidElementT::ComputeOutput calls J2Simo3D::s_ij at every integration point with the
+ * element history, the last converged displacement (FiniteStrainT::SetGlobalShape, F_last) and the solver's iteration number, before
+ * the step's history update (FEManagerT::CloseStep, FEManagerT.cpp:639-645).  d_u_last = NULL gives tb2_group_nodal_stress. */
+int tb2_group_nodal_stress_at(tb2_group* group, const double* d_u, const double* d_u_last, int iteration, double* d_stress);
+int tb2_group_nodal_stress_at_host(tb2_group* group, const double* h_u, const double* h_u_last, int iteration, double* h_stress);
 
 /* J2 history: SolidElementT::CloseStep -> J2Simo3D::UpdateHistory (J2SimoC0HardeningT.cpp:341-384), ResetStep -> ResetHistory (:387-407) */
 int tb2_group_close_step(tb2_group* group);

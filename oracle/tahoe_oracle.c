@@ -1461,8 +1461,8 @@ int orc_lumped_mass_scaled(double density, int64_t ne, const int32_t* conn, cons
  * smoothing matrix of HexahedronT::SetExtrapolation (HexahedronT.cpp:2099-2150: E[a][ip] = (1 + sqrt3 s_a.s_ip)/8) ->
  * ElementSupportT::AssembleAverage / GroupAverageT::Average (toolbox/src/misc/GroupAverageT.cpp:40-49, 190-205).
  * ------------------------------------------------------------------------------------------------------------------ */
-int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, const double* u,
-                     double* out /*[nn][6]*/)
+static int nodal_stress_core(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, const double* u,
+                             const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration, double* out /*[nn][6]*/)
 {
     static const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
     const double sqrt3 = sqrt(3.0);
@@ -1471,8 +1471,10 @@ int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_
     for (int64_t e = 0; e < ne; e++) {
         const int32_t* c = conn + 8 * e;
         double Xe[8][3], ue[8][3], dN[8][3][8], det[8], nodal[8][6], mg[3][8];
+        double ule[8][3];
         gather(c, X, Xe);
         gather(c, u, ue);
+        if (u_last) gather(c, u_last, ule);
         int err = orc_hex8_shape(Xe, dN, det);
         if (err) { free(count); return err; }
         if (form == ORC_SMALL_STRAIN_BBAR) mean_gradient(dN, det, mg);
@@ -1497,10 +1499,15 @@ int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_
                 }
                 hooke_stress(m, eps, sig);
             } else {
-                double F[9];
+                double F[9], Fl[9];
                 memcpy(F, G, sizeof F);
                 F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
-                err = fs_material(m, F, F, NULL, ip, NULL, 0, sig, NULL);
+                memcpy(Fl, F, sizeof Fl);
+                if (u_last) { /* J2: F of the last converged step (FiniteStrainT::SetGlobalShape) and the element's history */
+                    grad_u(ule, dN[ip], Fl);
+                    Fl[0] += 1.0; Fl[4] += 1.0; Fl[8] += 1.0;
+                }
+                err = fs_material(m, F, Fl, j2 ? j2 + 8 * e : NULL, ip, alloc ? alloc + e : NULL, iteration, sig, NULL);
                 if (err) { free(count); return err; }
             }
             for (int a = 0; a < 8; a++) {
@@ -1520,6 +1527,19 @@ int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_
         }
     free(count);
     return ORC_OK;
+}
+
+int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, const double* u,
+                     double* out)
+{
+    return nodal_stress_core(form, m, ne, conn, nn, X, u, NULL, NULL, NULL, 0, out);
+}
+/* the same output for a history material (J2Simo3D): SolidElementT::ComputeOutput evaluates s_ij at every integration point with the
+ * element's history and the last converged displacement, BEFORE the step's history update (FEManagerT::CloseStep :639-645) */
+int orc_nodal_stress_history(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X,
+                             const double* u, const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration, double* out)
+{
+    return nodal_stress_core(form, m, ne, conn, nn, X, u, u_last, j2, alloc, iteration, out);
 }
 
 /* one evaluation of the <explicit_solid> laws for known-answer tests (the reference's tests/materials/test_ExplJ2Plasticity.cpp calls

@@ -146,6 +146,9 @@ void orc_explicit_material_stress(const orc_material_t* m, const double* F, doub
  * averaged over the elements at a node); SSKStV (incl. B-bar), FDKStV, SimoIso3D.  out[nn][6], order 11,22,33,23,13,12 */
 int orc_nodal_stress(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X, const double* u,
                      double* out);
+/* the same with a history material (J2Simo3D): last converged displacement, element history, iteration number */
+int orc_nodal_stress_history(int form, const orc_material_t* m, int64_t ne, const int32_t* conn, int64_t nn, const double* X,
+                             const double* u, const double* u_last, orc_j2_ip_t* j2, int* alloc, int iteration, double* out);
 
 /* a21: nonlinear preconditioned CG with secant line search, PCGSolver_LS (solvers/PCGSolver_LS.cpp:107-371) inside
  * NLSolver::Solve / ExitIteration (solvers/NLSolver.cpp:57-263, 675-756), preconditioner = DiagonalMatrixT kDiagOnly

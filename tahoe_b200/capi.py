@@ -32,7 +32,7 @@ J2_BLOCK = 5 * 48 + 64  # doubles per element in the reference's ElementCardT la
 SYMBOLS = """tb2_version tb2_last_error tb2_device_count tb2_malloc tb2_free tb2_memcpy_h2d tb2_memcpy_d2h tb2_host_register
 tb2_host_unregister tb2_profile_reserve tb2_profile_begin tb2_profile_end tb2_mesh_synchronize tb2_measure_fp64_peak tb2_mesh_create tb2_mesh_destroy tb2_mesh_sizes tb2_mesh_device tb2_mesh_stream tb2_mesh_colouring
 tb2_group_create tb2_group_destroy tb2_form_internal_force tb2_form_internal_force_host tb2_group_status tb2_form_lumped_mass
-tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
+tb2_form_lumped_mass_host tb2_group_set_element_status tb2_group_stable_time_step tb2_group_set_mass_scaling tb2_group_get_explicit_history tb2_group_nodal_stress tb2_group_nodal_stress_host tb2_group_nodal_stress_at tb2_group_nodal_stress_at_host tb2_group_close_step tb2_group_reset_step tb2_group_get_history tb2_group_set_history
 tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_scale tb2_newton_solve_dynamic tb2_newton_solve_dynamic_host
 tb2_geom_open tb2_geom_close tb2_geom_sizes tb2_geom_coords tb2_geom_block tb2_geom_nodeset tb2_geom_sideset
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
@@ -304,10 +304,10 @@ class Group(_Handle):
         _chk(lib().tb2_form_inertial_force_host(self.h, int(mass_type), C.c_double(scale), _p(_f64(acc)), _p(out)))
         return out
 
-    def nodal_stress_host(self, u):
-        """extrapolated + averaged nodal Cauchy stress [nn][6] (SolidElementT::ComputeOutput)"""
+    def nodal_stress_host(self, u, u_last=None, iteration=0):
+        """extrapolated + averaged nodal Cauchy stress [nn][6] (SolidElementT::ComputeOutput); J2: pass the last converged displacement"""
         out = np.zeros((self.mesh.nn, 6))
-        _chk(lib().tb2_group_nodal_stress_host(self.h, _p(_f64(u)), _p(out)))
+        _chk(lib().tb2_group_nodal_stress_at_host(self.h, _p(_f64(u)), _p(_f64(u_last)), int(iteration), _p(out)))
         return out
 
     def close_step(self):

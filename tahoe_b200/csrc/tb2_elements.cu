@@ -529,9 +529,14 @@ __global__ void __launch_bounds__(128) k_nodal_stress(const ElemArgs p, double* 
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
-    Modes cX, cU;
+    Modes cX, cU, cL;
     load_modes(p.X, n, cX);
     load_modes(p.u, n, cU);
+    int alloc = 0;
+    if (MAT == kJ2Simo) { // history material: F of the last converged step and the element's history, as K1 reads them
+        load_modes(p.ul, n, cL);
+        alloc = p.hist.alloc[e];
+    }
     double theta_bar = 0.0;
     if (MAT == kSSKStVBbar) { // see internal_force_element
         double num = 0.0, vol = 0.0;
@@ -576,7 +581,15 @@ __global__ void __launch_bounds__(128) k_nodal_stress(const ElemArgs p, double* 
             const double J = det3(g);
             if (J <= 0.0) err = kErrBadJacobian;
             if (MAT == kFDKStV) fdkstv_stress(p.mat, g, J, sig);
-            else {
+            else if (MAT == kJ2Simo) { // J2Simo3D::s_ij as in the residual sweep; the trial fields it rewrites hold the same values
+                double Hl[3][3], Fl[3][3], c[6][6];
+                mode_gradient(cL, s0, s1, s2, Hl);
+                mul3(Hl, J0a, Fl);
+                scale3(Fl, rdet0);
+                Fl[0][0] += 1.0; Fl[1][1] += 1.0; Fl[2][2] += 1.0;
+                const int e2 = j2_eval<false>(p.mat, p.hist, e, ip, alloc, p.iteration, g, Fl, J, sig, c);
+                if (e2) err = e2 > err ? e2 : err;
+            } else {
                 double b_bar[6];
                 simo_bbar(g, J, b_bar);
                 simo_cauchy(p.mat, J, b_bar, sig);
@@ -1380,7 +1393,7 @@ int tb2_group_get_explicit_history(tb2_group* g, double* h_hist)
     return TB2_OK;
 }
 
-int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
+int tb2_group_nodal_stress_at(tb2_group* g, const double* d_u, const double* d_ul, int iteration, double* d_stress)
 {
     TB2_ARG(g && d_u && d_stress);
     tb2_mesh* m = g->mesh;
@@ -1390,8 +1403,9 @@ int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
         k = g->bbar ? k_nodal_stress<kSmallStrain, kSSKStVBbar> : k_nodal_stress<kSmallStrain, kSSKStV>;
     else if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_FDKSTV) k = k_nodal_stress<kTotalLagrangian, kFDKStV>;
     else if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_SIMO_ISO) k = k_nodal_stress<kTotalLagrangian, kSimoIso>;
+    else if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_J2_SIMO && d_ul) k = k_nodal_stress<kTotalLagrangian, kJ2Simo>;
     if (!k) {
-        set_error("nodal stress output is implemented for SSKStV, FDKStV and SimoIso3D (material %d)", g->mat.kind);
+        set_error("nodal stress output is implemented for SSKStV, FDKStV, SimoIso3D and (with the last displacement) J2Simo3D (material %d)", g->mat.kind);
         return TB2_ERR_ARG;
     }
     if (!m->out48.p) TB2_CUDA(m->out48.alloc((size_t)48 * m->stride));
@@ -1402,6 +1416,9 @@ int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
     p.conn = m->conn.p;
     p.X = m->X.p;
     p.u = d_u;
+    p.ul = d_ul;
+    p.iteration = iteration;
+    p.hist = group_hist(g);
     p.mat = g->mc;
     p.status = g->status.p;
     p.off = g->off.p;
@@ -1412,7 +1429,12 @@ int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
     return TB2_OK;
 }
 
-int tb2_group_nodal_stress_host(tb2_group* g, const double* h_u, double* h_stress)
+int tb2_group_nodal_stress(tb2_group* g, const double* d_u, double* d_stress)
+{
+    return tb2_group_nodal_stress_at(g, d_u, nullptr, 0, d_stress);
+}
+
+int tb2_group_nodal_stress_at_host(tb2_group* g, const double* h_u, const double* h_ul, int iteration, double* h_stress)
 {
     TB2_ARG(g && h_u && h_stress);
     tb2_mesh* m = g->mesh;
@@ -1421,10 +1443,19 @@ int tb2_group_nodal_stress_host(tb2_group* g, const double* h_u, double* h_stres
     DevBuf<double> out;
     TB2_CUDA(out.alloc(6 * m->nn));
     TB2_CUDA(cudaMemcpyAsync(m->stage_a.p, h_u, 3 * m->nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
-    TB2_CHECK(tb2_group_nodal_stress(g, m->stage_a.p, out.p));
+    if (h_ul) {
+        TB2_CHECK(ensure_stage(m, 2));
+        TB2_CUDA(cudaMemcpyAsync(m->stage_c.p, h_ul, 3 * m->nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    }
+    TB2_CHECK(tb2_group_nodal_stress_at(g, m->stage_a.p, h_ul ? m->stage_c.p : nullptr, iteration, out.p));
     TB2_CUDA(cudaMemcpyAsync(h_stress, out.p, 6 * m->nn * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     return tb2_group_status(g, nullptr);
+}
+
+int tb2_group_nodal_stress_host(tb2_group* g, const double* h_u, double* h_stress)
+{
+    return tb2_group_nodal_stress_at_host(g, h_u, nullptr, 0, h_stress);
 }
 
 int tb2_form_lumped_mass(tb2_group* g, double* d_mass)

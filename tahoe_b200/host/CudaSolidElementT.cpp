@@ -339,7 +339,8 @@ void CudaSolidElementT<BaseT>::ComputeOutput(const iArrayT& n_codes, dArray2DT& 
 {
 	const char caller[] = "CudaSolidElementT::ComputeOutput";
 	const int n_out = n_codes.Sum();
-	const bool device_material = fMaterialKind == TB2_SSKSTV || fMaterialKind == TB2_FDKSTV || fMaterialKind == TB2_SIMO_ISO;
+	const bool device_material = fMaterialKind == TB2_SSKSTV || fMaterialKind == TB2_FDKSTV || fMaterialKind == TB2_SIMO_ISO ||
+		fMaterialKind == TB2_J2_SIMO;
 	const bool device_codes = e_codes.Sum() == 0 && n_out > 0 && n_codes[SolidElementT::iNodalStress] == 6 &&
 		n_out == n_codes[SolidElementT::iNodalDisp] + n_codes[SolidElementT::iNodalStress] &&
 		(n_codes[SolidElementT::iNodalDisp] == 0 || n_codes[SolidElementT::iNodalDisp] == 3);
@@ -353,7 +354,9 @@ void CudaSolidElementT<BaseT>::ComputeOutput(const iArrayT& n_codes, dArray2DT& 
 	 * HexahedronT::SetExtrapolation, GroupAverageT averaging -- one device call for the whole group */
 	const dArray2DT& disp = this->Field()[0];
 	dArray2DT stress(disp.MajorDim(), 6);
-	Check(tb2_group_nodal_stress_host(fGroup, disp.Pointer(), stress.Pointer()), caller);
+	/* J2Simo3D::s_ij reads the element history, F of the last converged step and the iteration number (J2Simo3D.cpp:64-105) */
+	const double* last = fMaterialKind == TB2_J2_SIMO ? this->Field()(-1, 0).Pointer() : NULL;
+	Check(tb2_group_nodal_stress_at_host(fGroup, disp.Pointer(), last, this->ElementSupport().IterationNumber(this->Group()), stress.Pointer()), caller);
 	static bool announced = false;
 	if (!announced) {
 		cout << "\n " << caller << ": nodal stresses extrapolated and averaged on the device" << endl;

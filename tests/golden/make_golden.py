@@ -236,6 +236,9 @@ def main():
                                      "element": {"type": "small_strain", "natural_bc": [
                                          {"side_set": 4, "schedule": 1, "coordinate_system": "local", "values": [[0.0, 0.0, -1.0]]}]},
                                      "material": kstv, "solver": NEWTON}, ["--fint", "--lhs"]),
+        ("syn_ul_j2_stress", 3, {"time": static(3), "integrator": "static", "kbc": pull_u(0.06), "fbc": [], "output_inc": 3,
+                                 "element": {"type": "updated_lagrangian", "nodal_output": "stress"}, "material": j2, "solver": NEWTON},
+         ["--every", "1", "--fint"]),
         # a21: nonlinear PCG (PCGSolver_LS) -- linear, finite-strain and J2 cases
         ("syn_ss_kstv_pcg", 3, {"time": static(1), "integrator": "static", "kbc": CLAMP_X0, "fbc": pull_f,
                                 "element": {"type": "small_strain"}, "material": kstv, "solver": PCG}, ["--fint"]),

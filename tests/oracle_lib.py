@@ -274,11 +274,16 @@ def lumped_mass_scaled(density, conn, X, scale):
     return m
 
 
-def nodal_stress(form, mat, conn, X, u):
+def nodal_stress(form, mat, conn, X, u, u_last=None, j2=None, alloc=None, iteration=0):
     conn = np.ascontiguousarray(conn, np.int32)
     out = np.zeros((X.shape[0], 6))
-    err = lib().orc_nodal_stress(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), C.c_int64(X.shape[0]), _p(X),
-                                 _p(np.ascontiguousarray(u)), _p(out))
+    if u_last is None:
+        err = lib().orc_nodal_stress(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), C.c_int64(X.shape[0]), _p(X),
+                                     _p(np.ascontiguousarray(u)), _p(out))
+    else:
+        err = lib().orc_nodal_stress_history(form, C.byref(mat), C.c_int64(conn.shape[0]), _p(conn), C.c_int64(X.shape[0]), _p(X),
+                                             _p(np.ascontiguousarray(u)), _p(np.ascontiguousarray(u_last)), _p(j2), _p(alloc),
+                                             int(iteration), _p(out))
     return err, out
 
 

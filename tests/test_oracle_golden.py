@@ -144,13 +144,28 @@ def test_explicit_solid_matches_reference(oracle, name):
 def test_nodal_stress_output_matches_reference(oracle, name):
     """extrapolated + averaged nodal Cauchy stress against the table the reference's own TextOutputT wrote"""
     c, form, mat = _setup(oracle, name)
-    err, s = oracle.nodal_stress(form, mat, c.conn, c.X, c.ref("d_%d" % c.dump_steps[-1]))
-    assert err == 0
+    if mat.kind == oracle.J2_SIMO:
+        # a history material: the stresses come from J2Simo3D::s_ij with the element history of the run, evaluated before the last
+        # step's history update -- replay the run
+        got = {}
+
+        def output(k, d, d_last, it, j2, alloc):
+            if k == c.nsteps:
+                err, got["s"] = oracle.nodal_stress(form, mat, c.conn, c.X, d, d_last, j2, alloc, it)
+                assert err == 0
+
+        for _ in newton(oracle, c, form, mat, _direct, before_close=output):
+            pass
+        s = got["s"]
+    else:
+        err, s = oracle.nodal_stress(form, mat, c.conn, c.X, c.ref("d_%d" % c.dump_steps[-1]))
+        assert err == 0
     assert relerr(s, c.ref("nodal_stress")) < 5e-12  # 13 printed digits
 
 
-def newton(oracle, c, form, mat, solve):
-    """NLSolver::Solve restated (solvers/NLSolver.cpp:57-263): yields (step, d, iteration_number)"""
+def newton(oracle, c, form, mat, solve, before_close=None):
+    """NLSolver::Solve restated (solvers/NLSolver.cpp:57-263): yields (step, d, iteration_number).  before_close(k, d, d_last, it, j2,
+    alloc) runs where FEManagerT::CloseStep writes the output: after the solve, before the history update (FEManagerT.cpp:639-645)"""
     code, _, _ = c.bc(0.0)
     eq, neq = oracle.equation_numbers(code)
     rowptr, colind = oracle.csr_structure(c.conn, eq, neq)
@@ -181,6 +196,8 @@ def newton(oracle, c, form, mat, solve):
             assert err == 0
             R = (fext - f)[act]
             e = np.linalg.norm(R)
+        if before_close:
+            before_close(k, d, d_last, it, j2, alloc)
         if isj2:
             oracle.j2_update(mat, j2, alloc)
         d_last = d.copy()
