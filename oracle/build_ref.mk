@@ -6,6 +6,7 @@
 # only outputs kept are
 #     oracle/_ref/tahoe            the reference executable (CPU baseline, kind="reference")
 #     oracle/_ref/tahoe_dump       in-process dumper (full-precision RHS/LHS/fields; oracle/ref_dump.cpp)
+#     oracle/_ref/compare          the reference's own benchmark comparator (benchmark_XML/comparator/src), used by the plugin tests
 #     oracle/_ref/lib*.a           static libs the dumper / plugin demo link against
 # oracle/_ref/ is git-ignored but travels to the GPU box.
 #
@@ -56,7 +57,7 @@ LIBS := $(OUT)/libtahoe.a $(OUT)/libtoolbox.a $(OUT)/libdevelopment.a $(OUT)/lib
 LINK := -Wl,--start-group -Wl,--whole-archive $(OUT)/libtahoe.a $(OUT)/libtoolbox.a -Wl,--no-whole-archive $(OUT)/libdevelopment.a \
         $(OUT)/libtahoe_spooles.a $(OUT)/libtahoe_expat.a $(OUT)/libtahoe_f2c.a -Wl,--end-group -fopenmp -lm -ldl
 
-all: $(OUT)/tahoe $(OUT)/tahoe_dump
+all: $(OUT)/tahoe $(OUT)/tahoe_dump $(OUT)/compare
 
 $(OBJ)/incs.rsp:
 	@mkdir -p $(OBJ)
@@ -98,3 +99,10 @@ $(OUT)/tahoe_dump: $(OBJ)/ref_dump.o $(LIBS)
 
 libs: $(LIBS)
 .PHONY: all libs
+
+# the reference's regression comparator (run_benchmarks.sh: `compare -f case.xml` checks case.io0.run against benchmark/case.io0.run
+# with its default tolerances -- a value fails when it is off by more than 1e-8 relative AND 1e-10 absolute -- and prints "case.xml: PASS")
+$(OUT)/compare: $(REF)/benchmark_XML/comparator/src/main.cpp $(REF)/benchmark_XML/comparator/src/ComparatorT.cpp $(OUT)/libtoolbox.a $(OUT)/libtahoe_expat.a $(OBJ)/incs.rsp
+	@$(CXX) -std=c++14 -fpermissive $(WARN) $(OPT) -D__EXPAT__ -DNDEBUG @$(OBJ)/incs.rsp -I$(REF)/benchmark_XML/comparator/src \
+	    $(REF)/benchmark_XML/comparator/src/main.cpp $(REF)/benchmark_XML/comparator/src/ComparatorT.cpp -o $@ \
+	    -Wl,--start-group $(OUT)/libtoolbox.a $(OUT)/libtahoe_expat.a -Wl,--end-group -fopenmp -lm

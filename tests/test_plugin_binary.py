@@ -19,6 +19,7 @@ import tahoe_input as ti
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(REPO, "oracle", "_ref", "tahoe")
 PLUGIN_BIN = os.path.join(REPO, "tahoe_b200", "host", "_build", "tahoe_b200")
+COMPARE_BIN = os.path.join(REPO, "oracle", "_ref", "compare")  # the reference's own regression comparator (benchmark_XML/comparator)
 needs_bins = pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(PLUGIN_BIN)),
                                 reason="reference / plugin executables are built in the authoring container (make -C tahoe_b200/host)")
 
@@ -225,6 +226,18 @@ def test_plugin_reproduces_reference_output(name):
         assert np.abs(a - b).max() < tol * np.abs(a).max()
         if name.endswith("nlpcg"):
             assert "device PCG" in r1.stdout
+        if override is None and os.path.exists(COMPARE_BIN):
+            # the reference's own acceptance test (run_benchmarks.sh) for the cases that keep the reference's solver: its comparator,
+            # with its default tolerances (a value fails when it is off by more than 1e-8 relative AND 1e-10 absolute), checks the CUDA
+            # run's output files against the classic run's as the `benchmark/` reference
+            import glob
+            os.makedirs(os.path.join(work, "benchmark"), exist_ok=True)
+            for f in glob.glob(os.path.join(work, name + ".ref.io0.*")):
+                dst = os.path.join(work, "benchmark", os.path.basename(f).replace(".ref.", ".cuda."))
+                with open(f) as src, open(dst, "w") as out:  # the .run table of contents names its .ps files
+                    out.write(src.read().replace(name + ".ref.", name + ".cuda."))
+            rc = subprocess.run([COMPARE_BIN, "-f", name + ".cuda.xml"], cwd=work, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+            assert (name + ".cuda.xml: PASS") in rc.stdout, rc.stdout[-2500:]
         if name.endswith("stress_out") or name == "static_tl_two_materials_pcg":
             assert a.shape[1] == 9
             # single-material groups take the device path; the two-material group goes through Tahoe's host ComputeOutput
