@@ -50,6 +50,23 @@ def test_generated_mesh_round_trip(capi, threads_worth):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def test_several_element_blocks(capi):
+    """a .geom with two element sets (one per material of a multi-material group): block ids, sizes and rows in file order"""
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        n = 5
+        X, conn, ns = ti.structured_cube(n, jitter=0.1)
+        path = os.path.join(work, "mesh.geom")
+        ti.write_geom(path, X, conn, ns, block_sizes=[2 * n * n, 3 * n * n])
+        Xr, blocks, nsr, _ = capi.read_geom(path)
+        assert [b.shape for b in blocks] == [(2 * n * n, 8), (3 * n * n, 8)]
+        assert np.array_equal(np.concatenate(blocks), conn) and np.array_equal(Xr, X)
+        X0, conn0, _ = ti.read_geom(path)  # the test-side reader concatenates the blocks in file order too
+        assert np.array_equal(conn0, conn)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def test_node_records_in_any_order_and_comments(capi):
     work = tempfile.mkdtemp(prefix="tb2_geom_")
     try:
