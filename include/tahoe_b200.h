@@ -3,9 +3,9 @@
  *
  * Tahoe has no FFI today: the boundary is three C++ abstract classes.  Every entry point
  * below names the reference member function (file:line under the Tahoe source tree) whose work it
- * performs, so that the C++ plugin classes in tahoe_b200/host/ (CudaSolidElementT : ElementBaseT,
- * CudaCSRMatrixT : GlobalMatrixT, CudaExplicitCD) are thin forwarding shells.  INTEGRATION.md shows the
- * reference-side registration.
+ * performs, so that the C++ plugin classes in tahoe_b200/host/ (CudaSolidElementT : SolidElementT's
+ * subclasses, CudaPCGMatrixT : GlobalMatrixT, CudaPCGSolverT : PCGSolver_LS, CudaExplicitSolverT : SolverT) are thin
+ * forwarding shells.  INTEGRATION.md shows the reference-side registration.
  *
  * Conventions (identical to the reference):
  *   - nodal arrays are [node][dof] doubles (dArray2DT), ndof = nsd = 3;
@@ -217,6 +217,14 @@ int tb2_explicit_initial_condition(tb2_explicit* ex);
 int tb2_explicit_run(tb2_explicit* ex, double dt, int nsteps, const double* h_fext_scale, const double* h_value_scale);
 /* one step through host arrays: H2D d,v,a ; step ; D2H d,v,a  (what a drop-in does when Tahoe's FieldT stays authoritative) */
 int tb2_explicit_step_host(tb2_explicit* ex, double dt, double* h_d, double* h_v, double* h_a);
+/* The resident drop-in's mode of operation (FEManagerT::SolveStep with the fields on the device, FEManagerT.cpp:451-686):
+ * nsteps steps as tb2_explicit_run, then the displacement d -> h_d[nn][3] on a copy stream.  Returns WITHOUT waiting: the
+ * copy overlaps the kernels of later calls (pinned h_d: tb2_host_register).  *ticket identifies the call; h_d is complete
+ * (and element errors of the steps are reported) when tb2_explicit_wait(ex, ticket) returns.  At most two calls may be
+ * outstanding per buffer pair: wait for ticket t before reusing the h_d of ticket t. */
+int tb2_explicit_run_async(tb2_explicit* ex, double dt, int nsteps, const double* h_fext_scale, const double* h_value_scale,
+                           double* h_d, int* ticket);
+int tb2_explicit_wait(tb2_explicit* ex, int ticket);
 /* device views for cooperating plugins / multi-GPU harness: which = 0 d, 1 v, 2 a, 3 mass, 4 fext, 5 fint */
 double* tb2_explicit_device_array(tb2_explicit* ex, int which);
 

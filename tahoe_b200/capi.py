@@ -37,7 +37,7 @@ tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_sc
 tb2_geom_open tb2_geom_close tb2_geom_sizes tb2_geom_coords tb2_geom_block tb2_geom_nodeset tb2_geom_sideset
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
-tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_device_array tb2_equations_create
+tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_run_async tb2_explicit_wait tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
@@ -149,6 +149,11 @@ def host_register(arr):
 
 def host_unregister(arr):
     _chk(lib().tb2_host_unregister(C.c_void_p(arr.ctypes.data)))
+
+
+def memcpy_d2h(device, out, dptr):
+    """device pointer -> host array (tb2_memcpy_d2h)"""
+    _chk(lib().tb2_memcpy_d2h(int(device), _p(out), C.c_void_p(dptr), C.c_size_t(out.nbytes)))
 
 
 def measure_fp64_peak(device=0):
@@ -416,6 +421,17 @@ class Explicit(_Handle):
         """d, v, a: C-contiguous float64 host arrays (ideally pinned), updated in place"""
         _chk(lib().tb2_explicit_step_host(self.h, C.c_double(dt), C.c_void_p(d.ctypes.data), C.c_void_p(v.ctypes.data),
                                           C.c_void_p(a.ctypes.data)))
+
+    def run_async(self, dt, nsteps, out_d, fext_scale=None, value_scale=None):
+        """nsteps resident steps, then d -> out_d (host array or raw pointer, ideally pinned) without waiting; returns the ticket"""
+        fs, vs = _f64(fext_scale), _f64(value_scale)
+        ptr = out_d if isinstance(out_d, int) else out_d.ctypes.data
+        t = C.c_int(-1)
+        _chk(lib().tb2_explicit_run_async(self.h, C.c_double(dt), int(nsteps), _p(fs), _p(vs), C.c_void_p(ptr), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        _chk(lib().tb2_explicit_wait(self.h, int(ticket)))
 
     def step_host_ptr(self, dt, pd, pv, pa):
         _chk(lib().tb2_explicit_step_host(self.h, C.c_double(dt), C.c_void_p(pd), C.c_void_p(pv), C.c_void_p(pa)))

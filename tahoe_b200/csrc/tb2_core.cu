@@ -81,105 +81,6 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     out[blockIdx.x * (int64_t)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
-// slab pipeline bookkeeping (tb2_explicit.cu): contiguous element / node index chunks and their dependency ranges
-static void build_pipeline(tb2_mesh* m, const int32_t* h_conn, int sm_count)
-{
-    const int64_t wave = (int64_t)sm_count * 3 * 128; // elements of one resident wave of K1 (3 CTAs of 128 threads per SM)
-    // measured on a 1M-element cube (r01): 4 chunks of ~4.4 waves beat 9 chunks of 2 waves (launch tails) and 3 chunks (too little
-    // overlap): keep chunks near 4-5 waves, at least 4 and at most 32 of them
-    int64_t C = m->ne / (9 * wave / 2);
-    if (C < 4) C = 4;
-    if (C > 32) C = 32;
-    if (const char* s = getenv("TB2_PIPE_CHUNKS")) { // experiment knob
-        const int want = atoi(s);
-        if (want >= 1) C = want;
-    }
-    int64_t chunk = ((m->ne + C - 1) / C + wave - 1) / wave * wave;
-    C = (m->ne + chunk - 1) / chunk;
-    if (C < 3) C = 1;
-    m->pipe_e0.assign(C + 1, 0);
-    m->pipe_n0.assign(C + 1, 0);
-    for (int64_t c = 0; c <= C; c++) {
-        m->pipe_e0[c] = C == 1 ? (c ? m->ne : 0) : (c * chunk < m->ne ? c * chunk : m->ne);
-        m->pipe_n0[c] = m->nn * c / C;
-    }
-    m->pipe_emax_of_nc.assign(C, -1);
-    m->pipe_nmax_of_ec.assign(C, -1);
-    if (C == 1) return;
-    for (int64_t e = 0; e < m->ne; e++) {
-        const int ce = (int)(e / chunk);
-        for (int a = 0; a < 8; a++) {
-            const int64_t n = h_conn[8 * e + a];
-            int nc = (int)(n * C / m->nn);
-            while (nc + 1 < C && m->pipe_n0[nc + 1] <= n) nc++;
-            while (nc > 0 && m->pipe_n0[nc] > n) nc--;
-            if (ce > m->pipe_emax_of_nc[nc]) m->pipe_emax_of_nc[nc] = ce;
-            if (nc > m->pipe_nmax_of_ec[ce]) m->pipe_nmax_of_ec[ce] = nc;
-        }
-    }
-    // both streams run their chunks in index order, so a dependency on "all chunks <= k" is a wait on chunk k: make the maps monotone
-    for (int64_t c = 1; c < C; c++) {
-        if (m->pipe_emax_of_nc[c] < m->pipe_emax_of_nc[c - 1]) m->pipe_emax_of_nc[c] = m->pipe_emax_of_nc[c - 1];
-        if (m->pipe_nmax_of_ec[c] < m->pipe_nmax_of_ec[c - 1]) m->pipe_nmax_of_ec[c] = m->pipe_nmax_of_ec[c - 1];
-    }
-}
-
-// the same bookkeeping for the host-buffer step (no wave rounding: the copies, not the kernels, set the pace).
-// Default: 16 equal slabs.  Every copy costs ~7 us on this platform whatever its size (profiles/r01_summary.md: 48 + 48 copies of
-// 1.5 MB take 2.2 ms where 1 + 1 take 1.5 ms), and a node slab can only go back two slabs after it arrived (its update needs the
-// forces of the next element slab, which needs the predicted nodes of the slab after) -- fewer / unequal slabs trade one cost for
-// the other: r01g sweep, 1M elements: equal 16: 2.39 ms; weights 1,2,3,4,4,4,4,3,2,1: 2.37; 1,1,2,4,8,8,4,2,1,1: 2.50; 1,3,9,9,9,3,1:
-// 2.51 (TB2_HOST_PLAN=<weights> or TB2_HOST_CHUNKS=<n> select other plans).
-static void build_host_plan(tb2_mesh* m, const int32_t* h_conn)
-{
-    PipePlan& P = m->hplan;
-    std::vector<double> w;
-    const char* plan = getenv("TB2_HOST_PLAN");
-    if (const char* s = getenv("TB2_HOST_CHUNKS")) {
-        const int want = atoi(s);
-        if (want >= 1) w.assign(want, 1.0);
-    }
-    if (w.empty()) {
-        if (plan && plan[0] >= '0' && plan[0] <= '9') { // explicit weights "1,2,4,..."
-            for (const char* q = plan; *q;) {
-                w.push_back(atof(q));
-                while (*q && *q != ',') q++;
-                if (*q == ',') q++;
-            }
-        } else w.assign(16, 1.0);
-    }
-    int64_t C = (int64_t)w.size();
-    if (m->ne < 64 * C) { C = 1; w.assign(1, 1.0); }
-    double wsum = 0.0;
-    for (double v : w) wsum += v;
-    P.e0.assign(C + 1, 0);
-    P.n0.assign(C + 1, 0);
-    double acc = 0.0;
-    for (int64_t c = 0; c <= C; c++) {
-        P.e0[c] = c == C ? m->ne : (int64_t)(m->ne * (acc / wsum));
-        P.n0[c] = c == C ? m->nn : (int64_t)(m->nn * (acc / wsum));
-        if (c < C) acc += w[c];
-    }
-    P.emax_of_nc.assign(C, -1);
-    P.nmax_of_ec.assign(C, -1);
-    int ce = 0;
-    for (int64_t e = 0; e < m->ne; e++) {
-        while (ce + 1 < C && P.e0[ce + 1] <= e) ce++;
-        for (int a = 0; a < 8; a++) {
-            const int64_t n = h_conn[8 * e + a];
-            int nc = (int)(n * C / m->nn);
-            while (nc + 1 < C && P.n0[nc + 1] <= n) nc++;
-            while (nc > 0 && P.n0[nc] > n) nc--;
-            if (ce > P.emax_of_nc[nc]) P.emax_of_nc[nc] = ce;
-            if (nc > P.nmax_of_ec[ce]) P.nmax_of_ec[ce] = nc;
-        }
-    }
-    for (int64_t c = 1; c < C; c++) {
-        if (P.emax_of_nc[c] < P.emax_of_nc[c - 1]) P.emax_of_nc[c] = P.emax_of_nc[c - 1];
-        if (P.nmax_of_ec[c] < P.nmax_of_ec[c - 1]) P.nmax_of_ec[c] = P.nmax_of_ec[c - 1];
-    }
-}
-
 } // namespace tb2
 
 using namespace tb2;
@@ -311,10 +212,6 @@ int tb2_mesh_create(int device, int64_t nn, int64_t ne, const int32_t* h_conn, c
         M_CUDA(cudaStreamSynchronize(m->stream));
     }
 #undef M_CUDA
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
-    build_pipeline(m, h_conn, prop.multiProcessorCount);
-    build_host_plan(m, h_conn);
     *out = m;
     return TB2_OK;
 }
@@ -327,29 +224,11 @@ int tb2_mesh_destroy(tb2_mesh* m)
     DeviceGuard g(m->device);
     if (m->comm) tb2_comm_destroy(m);
     cudaStreamSynchronize(m->stream);
-    if (m->stream1b) {
-        cudaStreamSynchronize(m->stream1b);
-        cudaStreamDestroy(m->stream1b);
-    }
-    if (m->ev_join1b) cudaEventDestroy(m->ev_join1b);
-    if (m->stream2) {
-        cudaStreamSynchronize(m->stream2);
-        cudaStreamDestroy(m->stream2);
-    }
     for (auto& r : m->prof) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
-    for (cudaStream_t st : {m->stream_h2d, m->stream_d2h})
-        if (st) {
-            cudaStreamSynchronize(st);
-            cudaStreamDestroy(st);
-        }
-    for (auto* v : {&m->ev_h2d, &m->ev_pred, &m->ev_hk1, &m->ev_hk5})
-        for (auto e : *v) cudaEventDestroy(e);
-    if (m->ev_d2h_done) cudaEventDestroy(m->ev_d2h_done);
-    for (auto e : m->ev_k1) cudaEventDestroy(e);
-    for (auto e : m->ev_k5) cudaEventDestroy(e);
+    if (m->ev_k5) cudaEventDestroy(m->ev_k5);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     cudaStreamDestroy(m->stream);
     delete m;

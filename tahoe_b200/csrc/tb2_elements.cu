@@ -1,23 +1,23 @@
 // tb2_elements.cu -- K1 (internal force), K4 (lumped mass), the deterministic node gather, and the element-group API.
 //
-// K1 replaces SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295).  One thread owns one element and
-// walks its 8 integration points in the reference's order.  Instead of the per-IP 8x3 shape-function table
-// (HexahedronT.cpp:421-430) the kernel works on the trilinear modes of X and u (tb2_math.cuh), which cuts the
-// Jacobian / grad-u / B^T sigma work from 72 to 27-36 FMA each and keeps everything in registers.
-//
-// Finite strain.  With j = dx/dxi = J0 + du/dxi (J0 = dX/dxi):   F = j J0^-1,  det F = det j / det J0, and both
-//   TotalLagrangianT::FormKd  (f_a = sum_ip w detJ0 J (sigma F^-T) dN_a/dX,  TotalLagrangianT.cpp:107-144) and
-//   UpdatedLagrangianT::FormKd (f_a = sum_ip w det j  sigma dN_a/dx,          UpdatedLagrangianT.cpp:145-171)
-// reduce to  f_a = sum_ip w sigma adj(j)^T dN_a/dxi  (adj = det * inverse): the two reference classes are two
-// roundings of the same integral, so one kernel body serves both and needs no reciprocal of det j.
+// K1 replaces SolidElementT::ElementRHSDriver (SolidElementT.cpp:1166-1295).  One thread owns one element and walks its 8
+// integration points; the integration-point loop itself lives in tb2_force_core.cuh (trilinear-mode form: no shape-function
+// table, 27-36 FMA per 3x3 instead of 72).
 //
 // Scatter.  Threads write the 24 element values to an SoA scratch fe[24][stride] (coalesced); a node kernel then sums
 // each node's <= 8 contributions in ascending element order -- the order of the reference's serial assembly
 // (SolverT::AssembleRHS, SolverT.cpp:446-477) -- so there are no float atomics and reruns are bit-reproducible.
+//
+// Round 2 measured the alternatives to this two-kernel scheme on B200 (profiles/r02_summary.md, profiles/tools/k1_lab.cu):
+// forces kept in shared memory with a block-local ordered sum and in-kernel node updates -- as one CTA per element block and as
+// a persistent warp-specialised kernel with setmaxnreg -- and a two-stream slab pipeline with a register-lean sweep.  All were
+// slower than sweep + node kernel back to back: the node work costs more when it is done block-locally (8-byte scattered
+// accesses, release atomics and completion reads) than as one streaming pass at 92 % of the HBM peak.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
+#include "tb2_force_core.cuh"
 #include "tb2_internal.h"
 #include "tb2_node_update.cuh"
 
@@ -33,7 +33,6 @@ struct ElemArgs {
     const double* u;  // [nn][3]
     const double* ul; // [nn][3] (J2) or null
     double* fe;       // [24][stride]
-    const double* geo; // [8 ip][7][stride] reference-configuration cache of the Neo-Hookean fast path (k_reference_geometry), or null
     MatConst mat;
     J2Hist hist;
     int iteration;
@@ -56,165 +55,18 @@ TB2_DEV bool element_is_off(const ElemArgs& p, const int64_t e)
     return true;
 }
 
-// L1 prefetch of the nodal data (X and u triples) of the element a persistent thread will process next
-TB2_DEV void prefetch_nodes(const ElemArgs& p, const int (&n)[8])
+// element of thread t of the launch, or -1 if the thread has nothing to do (out of range, left to another launch, kOFF)
+TB2_DEV int64_t element_of_thread(const ElemArgs& p)
 {
-#pragma unroll
-    for (int a = 0; a < 8; a++) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.X + 3 * (int64_t)n[a]));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.X + 3 * (int64_t)n[a] + 2));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.u + 3 * (int64_t)n[a]));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.u + 3 * (int64_t)n[a] + 2));
-    }
+    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.ne) return -1;
+    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
+    if (p.skip && p.skip[e]) return -1;
+    if (element_is_off(p, e)) return -1;
+    return e;
 }
-
-// one element: node ids n[] already in registers.  PREFETCH: n_next[] are the nodes of the thread's next element, whose nodal
-// data is pulled into L1 half-way through the integration-point loop
-template <int FORM, int MAT, bool PREFETCH>
-TB2_DEV void internal_force_element(const ElemArgs& p, const int64_t e, const int (&n)[8], const int (&n_next)[8], const bool has_next)
+TB2_DEV void store_element_forces(const ElemArgs& p, const int64_t e, const Modes& A)
 {
-    Modes cX, cU, cL, A;
-    load_modes(p.X, n, cX);
-    load_modes(p.u, n, cU);
-    if (MAT == kJ2Simo) load_modes(p.ul, n, cL);
-#pragma unroll
-    for (int k = 0; k < 7; k++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            A.m[k][i] = 0.0;
-            if (FORM != kSmallStrain) cU.m[k][i] += cX.m[k][i]; // finite strain: modes of x = X + u, so that j = dx/dxi directly
-        }
-
-    int alloc = 0, err = kErrNone;
-    if (MAT == kJ2Simo) alloc = p.hist.alloc[e];
-    // Mean-dilatation B-bar (SmallStrainT.cpp:337-374).  B-bar_a = B_a + 1/3 m (b_a - grad N_a)^T with b_a the volume average of
-    // grad N_a (Hughes 4.5.23), so the strain at a point is eps + 1/3 (theta_bar - tr eps) 1 with
-    //   theta_bar = sum_a b_a . u_a = sum_ip w det0 tr(grad u) / sum_ip w det0 = sum_ip tr(H adj(J0)) / sum_ip det0,
-    // and, tr(sigma) = 3 kappa theta_bar being the same at every point for the isotropic linear material, the B-bar^T sigma
-    // integral equals the plain B^T sigma integral of those stresses (the (b_a - grad N_a) tr(sigma)/3 terms cancel in the sum).
-    double theta_bar = 0.0;
-    if (MAT == kSSKStVBbar) {
-        double num = 0.0, vol = 0.0;
-#pragma unroll 1
-        for (int ip = 0; ip < 8; ip++) {
-            double s0, s1, s2, J0[3][3], H[3][3], J0a[3][3];
-            ip_signs(ip, s0, s1, s2);
-            mode_gradient(cX, s0, s1, s2, J0);
-            mode_gradient(cU, s0, s1, s2, H);
-            vol += adj3(J0, J0a);
-#pragma unroll
-            for (int i = 0; i < 3; i++) num += H[i][0] * J0a[0][i] + H[i][1] * J0a[1][i] + H[i][2] * J0a[2][i];
-        }
-        theta_bar = num / vol;
-    }
-
-#pragma unroll 1
-    for (int ip = 0; ip < 8; ip++) {
-        if (PREFETCH && ip == 3 && has_next) prefetch_nodes(p, n_next);
-        double s0, s1, s2;
-        ip_signs(ip, s0, s1, s2);
-        double J0[3][3], H[3][3], J0a[3][3], G[3][3], S[3][3];
-        mode_gradient(cX, s0, s1, s2, J0);
-        mode_gradient(cU, s0, s1, s2, H); // small strain: du/dxi; finite strain: j = dx/dxi
-        const double det0 = adj3(J0, J0a);
-        if (det0 <= 0.0) err = kErrBadJacobian; // ParentDomainT::ComputeDNa, ParentDomainT.cpp:451
-        const double rdet0 = 1.0 / det0;
-        double sig[6];
-        if (FORM == kSmallStrain) {
-            // SmallStrainT::SetGlobalShape (SmallStrainT.cpp:327-401): eps = sym(grad_X u), grad_X u = H J0^-1
-            double g[3][3], eps[6];
-            mul3(H, J0a, g);
-            eps[0] = g[0][0] * rdet0;
-            eps[1] = g[1][1] * rdet0;
-            eps[2] = g[2][2] * rdet0;
-            eps[3] = 0.5 * (g[1][2] + g[2][1]) * rdet0;
-            eps[4] = 0.5 * (g[0][2] + g[2][0]) * rdet0;
-            eps[5] = 0.5 * (g[0][1] + g[1][0]) * rdet0;
-            if (MAT == kSSKStVBbar) {
-                const double corr = (theta_bar - (eps[0] + eps[1] + eps[2])) * (1.0 / 3.0);
-                eps[0] += corr; eps[1] += corr; eps[2] += corr;
-            }
-            hooke_stress(p.mat, eps, sig);
-            sym_to_mat(sig, S);
-            mul3_abt(S, J0a, G); // G = w detJ0 sigma J0^-T
-        } else {
-            double ja[3][3], F[3][3];
-            const double (&j)[3][3] = H;
-            const double detj = adj3(j, ja);
-            if (detj <= 0.0) err = kErrBadJacobian; // TotalLagrangianT.cpp:127-128 / current-configuration ComputeDNa
-            if (MAT == kSimoIso) {
-                // SimoIso3D::s_ij (SimoIso3D.cpp:127-136) folded into the force integrand.  With F' = det0 F = j adj(J0) and
-                // cof(j) = adj(j)^T:  b' cof(j) = F' F'^T cof(j) = det(j) F' adj(J0)^T = det(j) j M0,  M0 = adj(J0) adj(J0)^T, so
-                //   G = w det(j) sigma j^-T = sc det(j) (j M0) + (U'(J) - sc tr(b')/3) cof(j),   tr(b') = (j M0) : j,
-                //   sc = (mu/J) J^(-2/3) / det0^2 = mu (det(j)^5 det0)^(-1/3):  one rcbrt and no division;
-                //   1/(det0 det j) = t^3 det(j)^4 with t = sc/mu supplies 1/J for U'(J) = kappa/2 (J - 1/J) (SimoIso3D.h:93-96).
-                double M0[6], N[3][3];
-                sym_fft(J0a, M0); // adj(J0) adj(J0)^T
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    N[i][0] = j[i][0] * M0[0] + j[i][1] * M0[5] + j[i][2] * M0[4];
-                    N[i][1] = j[i][0] * M0[5] + j[i][1] * M0[1] + j[i][2] * M0[3];
-                    N[i][2] = j[i][0] * M0[4] + j[i][1] * M0[3] + j[i][2] * M0[2];
-                }
-                double trb = 0.0;
-#pragma unroll
-                for (int i = 0; i < 3; i++) trb += N[i][0] * j[i][0] + N[i][1] * j[i][1] + N[i][2] * j[i][2];
-                const double dj2 = detj * detj;
-                const double t = rcbrt(dj2 * dj2 * detj * det0);
-                const double rdd = (t * t) * t * (dj2 * dj2);               // 1 / (det0 det j)
-                const double sc = p.mat.mu * t;
-                const double pr = 0.5 * p.mat.kappa * (dj2 - det0 * det0) * rdd; // U'(J) = kappa/2 (J - 1/J)
-                const double al = sc * detj, q = pr - sc * trb * (1.0 / 3.0);
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
-                mode_accumulate(A, s0, s1, s2, G);
-                continue;
-            }
-            if (MAT == kExplNeo) {
-                // ExplNeoHookeanT folded into the force integrand like SimoIso3D above: sigma = (mu/J)(b - 1) + kappa (1 - 1/J) 1 and
-                // b cof(j) = det(j)/det0^2 j M0 give  G = w det(j) sigma j^-T = (mu/det0) (j M0) + (kappa (1 - 1/J) - mu/J) cof(j)
-                double M0[6], N[3][3];
-                sym_fft(J0a, M0);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    N[i][0] = j[i][0] * M0[0] + j[i][1] * M0[5] + j[i][2] * M0[4];
-                    N[i][1] = j[i][0] * M0[5] + j[i][1] * M0[1] + j[i][2] * M0[3];
-                    N[i][2] = j[i][0] * M0[4] + j[i][1] * M0[3] + j[i][2] * M0[2];
-                }
-                const double r = 1.0 / (det0 * detj); // one reciprocal: 1/det0 = det(j) r, 1/J = det0^2 r
-                const double rJ = det0 * det0 * r;
-                const double al = p.mat.mu * detj * r, q = p.mat.kappa * (1.0 - rJ) - p.mat.mu * rJ;
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
-                mode_accumulate(A, s0, s1, s2, G);
-                continue;
-            }
-            mul3(j, J0a, F); // = det0 * F
-            const double J = detj * rdet0;
-            if (MAT != kSimoIso) scale3(F, rdet0);
-            if (MAT == kFDKStV)
-                fdkstv_stress(p.mat, F, J, sig);
-            else if (MAT == kExplJ2)
-                expl_j2_stress(p.mat, p.hist.data + (int64_t)(ip * 16) * p.stride + e, p.stride, F, sig);
-            else if (MAT == kJ2Simo) {
-                double Hl[3][3], Fl[3][3], c[6][6];
-                mode_gradient(cL, s0, s1, s2, Hl);
-                mul3(Hl, J0a, Fl);
-                scale3(Fl, rdet0);
-                Fl[0][0] += 1.0; Fl[1][1] += 1.0; Fl[2][2] += 1.0; // FiniteStrainT::SetGlobalShape, FiniteStrainT.cpp:267-304
-                const int e2 = j2_eval<false>(p.mat, p.hist, e, ip, alloc, p.iteration, F, Fl, J, sig, c);
-                if (e2) err = e2 > err ? e2 : err;
-            }
-            sym_to_mat(sig, S);
-            mul3_abt(S, ja, G); // G = w det(j) sigma j^-T
-        }
-        mode_accumulate(A, s0, s1, s2, G);
-    }
-    if (err) report(p, err, e);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         double f[8];
@@ -224,122 +76,48 @@ TB2_DEV void internal_force_element(const ElemArgs& p, const int64_t e, const in
     }
 }
 
-// one thread = one element of the launch
-template <int FORM, int MAT>
-TB2_DEV void internal_force_body(const ElemArgs& p, const unsigned cta = blockIdx.x)
+// K1, general form: one thread = one element, modes in registers.  MINB resident CTAs of 128 threads set the register budget.
+template <int FORM, int MAT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_internal_force(const ElemArgs p)
 {
-    const int64_t t = p.e_begin + cta * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= p.ne) return;
-    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
-    if (p.skip && p.skip[e]) return;
-    if (element_is_off(p, e)) return;
+    const int64_t e = element_of_thread(p);
+    if (e < 0) return;
     int n[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
-    internal_force_element<FORM, MAT, false>(p, e, n, n, false);
-}
-
-// Persistent form: the grid is the set of CTAs resident at once; a thread walks elements t, t + grid, ... and keeps the
-// connectivity of its next element in registers (requested a whole element ahead) and that element's nodal data on its way
-// into L1 (requested half an element ahead), so the gather latency that a one-element thread exposes at its start
-// (conn -> X, u: two dependent round trips, ~20 % of the stall cycles in profiles/r01d) overlaps the FP64 work instead.
-template <int FORM, int MAT, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_internal_force_persistent(const ElemArgs p)
-{
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;
-    int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= p.ne) return;
-    int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
-    int n[8], n_next[8];
+    Modes cX, cU, cL, A;
+    load_modes(p.X, n, cX);
+    load_modes(p.u, n, cU);
+    if (MAT == kJ2Simo) load_modes(p.ul, n, cL);
+    if (FORM != kSmallStrain) {
 #pragma unroll
-    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
-    for (;;) {
-        const int64_t t_next = t + step;
-        const bool has_next = t_next < p.ne;
-        int64_t e_next = e;
-        if (has_next) e_next = p.elist ? (int64_t)__ldg(p.elist + t_next) : t_next;
+        for (int k = 0; k < 7; k++)
 #pragma unroll
-        for (int a = 0; a < 8; a++) n_next[a] = __ldg(p.conn + a * p.stride + e_next);
-        if (!(p.skip && p.skip[e]) && !element_is_off(p, e)) internal_force_element<FORM, MAT, true>(p, e, n, n_next, has_next);
-        if (!has_next) break;
-        t = t_next;
-        e = e_next;
-#pragma unroll
-        for (int a = 0; a < 8; a++) n[a] = n_next[a];
+            for (int i = 0; i < 3; i++) cU.m[k][i] += cX.m[k][i]; // finite strain: modes of x = X + u, so that j = dx/dxi directly
     }
+    ForceCtx fc;
+    fc.mat = p.mat;
+    fc.hist = p.hist;
+    fc.e = e;
+    fc.stride = p.stride;
+    fc.iteration = p.iteration;
+    const int err = force_modes<FORM, MAT>(fc, RegModes(cX), RegModes(cU), cL, A);
+    if (err) report(p, err, e);
+    store_element_forces(p, e, A);
 }
 
-// ---- fused element + node launch of the explicit slab pipeline ---------------------------------------------------------------
-// ncu (profiles/r01d): the element sweep's three CTAs per SM own the whole register file, so a separate node kernel only runs in
-// the sweep's tails and the step costs K1 + K5 (0.183 + 0.082 ms on 1M elements).  Here ONE launch carries the element CTAs of
-// slab c and the node CTAs of the node slabs that became ready with slab c - 1 (their forces are complete: kernel boundary); the
-// two kinds alternate in block-index order, so every SM holds FP64-bound element CTAs and HBM-bound node CTAs side by side under
-// the same register allocation.  The node range is never read by the element CTAs of the same launch (no element of slab >= c
-// touches it), so there is no intra-launch dependency, no flag and no spin-wait.  Same arithmetic as the separate kernels.
-template <int FORM, int MAT, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_fused_force_update(const ElemArgs p, const NodeArgs q, const unsigned n_elem_ctas,
-                                                                  const unsigned n_node_ctas)
+// K1 of the finite-strain Neo-Hookean laws (SimoIso3D, ExplNeoHookeanT: the explicit headline path).  The 42 read-only mode
+// coefficients of X and x = X + u live in private shared-memory columns [coefficient][thread] (conflict-free), the integration
+// points are taken in pairs (tb2_force_core.cuh: force_modes_neo_pairs), and only the 21 force modes stay in registers across
+// the loop: 160 registers, no spills, 3 CTAs/SM.  B200, 10^6 elements (profiles/r02_summary.md): 149 us against 168 us for the
+// one-point-per-iteration register form (1934 instead of 2174 FP64 instructions per element, two dependency chains per warp).
+template <int MAT>
+__global__ void __launch_bounds__(128, 3) k_internal_force_neo(const ElemArgs p)
 {
-    const unsigned b = blockIdx.x, pairs = n_elem_ctas < n_node_ctas ? n_elem_ctas : n_node_ctas;
-    bool node_cta;
-    unsigned idx;
-    if (b < 2 * pairs) {
-        node_cta = (b & 1u) != 0;
-        idx = b >> 1;
-    } else {
-        node_cta = n_node_ctas > n_elem_ctas;
-        idx = b - pairs;
-    }
-    if (node_cta) {
-        const int64_t n = q.n0 + idx * (int64_t)blockDim.x + threadIdx.x;
-        if (n >= q.n1) return;
-        if (q.next_predictor)
-            cd_node_update_one<true, true>(n, q.inc_ptr, q.inc, q.inc8, q.fe, q.stride, q.dt, q.fext_scale, q.next_value_scale, q.fext, q.minv,
-                                           q.code, q.bcval, q.d, q.v, q.a, q.fint, q.skip_slot);
-        else
-            cd_node_update_one<true, false>(n, q.inc_ptr, q.inc, q.inc8, q.fe, q.stride, q.dt, q.fext_scale, q.next_value_scale, q.fext, q.minv,
-                                            q.code, q.bcval, q.d, q.v, q.a, q.fint, q.skip_slot);
-        return;
-    }
-    internal_force_body<FORM, MAT>(p, idx);
-}
-
-// register budget by resident CTAs per SM (MINB CTAs of THREADS threads) ...
-template <int FORM, int MAT, int MINB, int THREADS = 128>
-__global__ void __launch_bounds__(THREADS, MINB) k_internal_force(const ElemArgs p)
-{
-    internal_force_body<FORM, MAT>(p);
-}
-// ... or by an explicit register cap: 3 CTAs of 128 threads at 144 registers leave 8 K registers per SM to the node kernel that
-// runs beside the sweep in the slab pipeline (at 168 the sweep owns the whole register file and the node kernel starves)
-template <int FORM, int MAT, int REGS>
-__global__ void __launch_bounds__(128) __maxnreg__(REGS) k_internal_force_r(const ElemArgs p)
-{
-    internal_force_body<FORM, MAT>(p);
-}
-
-// K1, total-Lagrangian SimoIso3D, shared-memory variant.  The 42 read-only mode coefficients of X and x = X + u live in shared
-// memory ([coefficient][thread]: private columns, conflict-free) instead of registers, which brings the kernel from 168-220
-// registers to ~100 and doubles the resident warps that feed the FP64 pipe.  Same arithmetic as k_internal_force except that
-// j = grad(x modes) is formed directly (the modes of x = X + u are summed once per element) instead of J0 + grad(u modes).
-// shared-memory load the compiler may neither hoist out of the integration-point loop nor keep in a register across iterations
-TB2_DEV double lds_f64(const double* p)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
-    return v;
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const ElemArgs p)
-{
-    __shared__ double sX[21][128], sx[21][128];
+    __shared__ double sX[21 * 128], sx[21 * 128];
+    const int64_t e = element_of_thread(p);
+    if (e < 0) return;
     const int tid = threadIdx.x;
-    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + tid;
-    if (t >= p.ne) return;
-    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
-    if (p.skip && p.skip[e]) return;
-    if (element_is_off(p, e)) return;
     {
         int n[8];
 #pragma unroll
@@ -351,168 +129,14 @@ __global__ void __launch_bounds__(128, MINB) k_internal_force_simo_sm(const Elem
         for (int k = 0; k < 7; k++)
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                sX[3 * k + i][tid] = cX.m[k][i];
-                sx[3 * k + i][tid] = cX.m[k][i] + cU.m[k][i];
+                sX[(3 * k + i) * 128 + tid] = cX.m[k][i];
+                sx[(3 * k + i) * 128 + tid] = cX.m[k][i] + cU.m[k][i];
             }
     }
     Modes A;
-#pragma unroll
-    for (int k = 0; k < 7; k++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) A.m[k][i] = 0.0;
-    int err = kErrNone;
-#pragma unroll 1
-    for (int ip = 0; ip < 8; ip++) {
-        double s0, s1, s2;
-        ip_signs(ip, s0, s1, s2);
-        const double s12 = s1 * s2, s02 = s0 * s2, s01 = s0 * s1;
-        double J0[3][3], j[3][3], J0a[3][3], ja[3][3], G[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            J0[i][0] = lds_f64(&sX[0 + i][tid]) + s1 * lds_f64(&sX[6 + i][tid]) + s2 * lds_f64(&sX[12 + i][tid]) + s12 * lds_f64(&sX[18 + i][tid]);
-            J0[i][1] = lds_f64(&sX[3 + i][tid]) + s0 * lds_f64(&sX[6 + i][tid]) + s2 * lds_f64(&sX[15 + i][tid]) + s02 * lds_f64(&sX[18 + i][tid]);
-            J0[i][2] = lds_f64(&sX[9 + i][tid]) + s0 * lds_f64(&sX[12 + i][tid]) + s1 * lds_f64(&sX[15 + i][tid]) + s01 * lds_f64(&sX[18 + i][tid]);
-            j[i][0] = lds_f64(&sx[0 + i][tid]) + s1 * lds_f64(&sx[6 + i][tid]) + s2 * lds_f64(&sx[12 + i][tid]) + s12 * lds_f64(&sx[18 + i][tid]);
-            j[i][1] = lds_f64(&sx[3 + i][tid]) + s0 * lds_f64(&sx[6 + i][tid]) + s2 * lds_f64(&sx[15 + i][tid]) + s02 * lds_f64(&sx[18 + i][tid]);
-            j[i][2] = lds_f64(&sx[9 + i][tid]) + s0 * lds_f64(&sx[12 + i][tid]) + s1 * lds_f64(&sx[15 + i][tid]) + s01 * lds_f64(&sx[18 + i][tid]);
-        }
-        const double det0 = adj3(J0, J0a);
-        double M0[6];
-        sym_fft(J0a, M0); // adj(J0) adj(J0)^T (see k_internal_force for the algebra)
-        const double detj = adj3(j, ja);
-        if (det0 <= 0.0 || detj <= 0.0) err = kErrBadJacobian; // ParentDomainT.cpp:451 / TotalLagrangianT.cpp:127-128
-        double N[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            N[i][0] = j[i][0] * M0[0] + j[i][1] * M0[5] + j[i][2] * M0[4];
-            N[i][1] = j[i][0] * M0[5] + j[i][1] * M0[1] + j[i][2] * M0[3];
-            N[i][2] = j[i][0] * M0[4] + j[i][1] * M0[3] + j[i][2] * M0[2];
-        }
-        double trb = 0.0;
-#pragma unroll
-        for (int i = 0; i < 3; i++) trb += N[i][0] * j[i][0] + N[i][1] * j[i][1] + N[i][2] * j[i][2];
-        const double dj2 = detj * detj;
-        const double t = rcbrt(dj2 * dj2 * detj * det0);
-        const double rdd = (t * t) * t * (dj2 * dj2);
-        const double sc = p.mat.mu * t;
-        const double pr = 0.5 * p.mat.kappa * (dj2 - det0 * det0) * rdd;
-        const double al = sc * detj, q = pr - sc * trb * (1.0 / 3.0);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
-        mode_accumulate(A, s0, s1, s2, G);
-    }
+    const int err = force_modes_neo_pairs<MAT>(p.mat, SmemModes(sX + tid, 128), SmemModes(sx + tid, 128), A);
     if (err) report(p, err, e);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        double f[8];
-        modes_to_nodes(A, i, f);
-#pragma unroll
-        for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
-    }
-}
-
-// ---- K1, total-Lagrangian SimoIso3D, cached reference geometry ------------------------------------------------------------
-// ncu (profiles/r01d): K1 is FP64-pipe bound (65 % pipe utilisation) while DRAM sits at 11 %.  Everything in the integrand that
-// depends on the reference configuration only -- J0 = dX/dxi, adj(J0), M0 = adj(J0) adj(J0)^T, det J0: 66 of the ~270 FP64
-// instructions per integration point -- is therefore computed once (k_reference_geometry) and streamed back in: 7 doubles per
-// point, 448 B per element per sweep of otherwise idle HBM bandwidth, read evict-first so the force scratch keeps its L2 lines.
-// The arithmetic on the cached values is the arithmetic of k_internal_force, so both kernels return the same bits.
-__global__ void __launch_bounds__(128) k_reference_geometry(int64_t ne, int64_t stride, const int* __restrict__ conn,
-                                                           const double* __restrict__ X, double* __restrict__ geo)
-{
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= ne) return;
-    int n[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) n[a] = __ldg(conn + a * stride + e);
-    Modes cX;
-    load_modes(X, n, cX);
-#pragma unroll 1
-    for (int ip = 0; ip < 8; ip++) {
-        double s0, s1, s2, J0[3][3], J0a[3][3], M0[6];
-        ip_signs(ip, s0, s1, s2);
-        mode_gradient(cX, s0, s1, s2, J0);
-        const double det0 = adj3(J0, J0a);
-        sym_fft(J0a, M0);
-        double* g = geo + (int64_t)(ip * 7) * stride + e;
-#pragma unroll
-        for (int q = 0; q < 6; q++) g[(int64_t)q * stride] = M0[q];
-        g[(int64_t)6 * stride] = det0;
-    }
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_internal_force_simo_geo(const ElemArgs p)
-{
-    const int64_t t = p.e_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= p.ne) return;
-    const int64_t e = p.elist ? (int64_t)__ldg(p.elist + t) : t;
-    if (p.skip && p.skip[e]) return;
-    if (element_is_off(p, e)) return;
-    const double* geo = p.geo + e;
-    double gq[7]; // M0[0..5], det0 of the current point; the next point's values are requested one iteration ahead
-#pragma unroll
-    for (int q = 0; q < 7; q++) gq[q] = __ldcs(geo + (int64_t)q * p.stride);
-    int n[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) n[a] = __ldg(p.conn + a * p.stride + e);
-    Modes cx, cU, A;
-    load_modes(p.X, n, cx);
-    load_modes(p.u, n, cU);
-#pragma unroll
-    for (int k = 0; k < 7; k++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            A.m[k][i] = 0.0;
-            cx.m[k][i] += cU.m[k][i]; // modes of x = X + u, summed exactly as k_internal_force does
-        }
-    int err = kErrNone;
-#pragma unroll 1
-    for (int ip = 0; ip < 8; ip++) {
-        double gn[7];
-        const int ipn = ip < 7 ? ip + 1 : 7;
-#pragma unroll
-        for (int q = 0; q < 7; q++) gn[q] = __ldcs(geo + (int64_t)(ipn * 7 + q) * p.stride);
-        double s0, s1, s2;
-        ip_signs(ip, s0, s1, s2);
-        double j[3][3], ja[3][3], N[3][3], G[3][3];
-        mode_gradient(cx, s0, s1, s2, j);
-        const double det0 = gq[6];
-        const double detj = adj3(j, ja);
-        if (det0 <= 0.0 || detj <= 0.0) err = kErrBadJacobian; // ParentDomainT.cpp:451 / TotalLagrangianT.cpp:127-128
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            N[i][0] = j[i][0] * gq[0] + j[i][1] * gq[5] + j[i][2] * gq[4];
-            N[i][1] = j[i][0] * gq[5] + j[i][1] * gq[1] + j[i][2] * gq[3];
-            N[i][2] = j[i][0] * gq[4] + j[i][1] * gq[3] + j[i][2] * gq[2];
-        }
-        double trb = 0.0;
-#pragma unroll
-        for (int i = 0; i < 3; i++) trb += N[i][0] * j[i][0] + N[i][1] * j[i][1] + N[i][2] * j[i][2];
-        const double dj2 = detj * detj;
-        const double tt = rcbrt(dj2 * dj2 * detj * det0);
-        const double rdd = (tt * tt) * tt * (dj2 * dj2);
-        const double sc = p.mat.mu * tt;
-        const double pr = 0.5 * p.mat.kappa * (dj2 - det0 * det0) * rdd;
-        const double al = sc * detj, q = pr - sc * trb * (1.0 / 3.0);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) G[i][k] = al * N[i][k] + q * ja[k][i];
-        mode_accumulate(A, s0, s1, s2, G);
-#pragma unroll
-        for (int q2 = 0; q2 < 7; q2++) gq[q2] = gn[q2];
-    }
-    if (err) report(p, err, e);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        double f[8];
-        modes_to_nodes(A, i, f);
-#pragma unroll
-        for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
-    }
+    store_element_forces(p, e, A);
 }
 
 // ---- nodal stress output ---------------------------------------------------------------------------------
@@ -538,7 +162,7 @@ __global__ void __launch_bounds__(128) k_nodal_stress(const ElemArgs p, double* 
         alloc = p.hist.alloc[e];
     }
     double theta_bar = 0.0;
-    if (MAT == kSSKStVBbar) { // see internal_force_element
+    if (MAT == kSSKStVBbar) { // see force_modes (tb2_force_core.cuh)
         double num = 0.0, vol = 0.0;
 #pragma unroll 1
         for (int ip = 0; ip < 8; ip++) {
@@ -905,61 +529,21 @@ __global__ void k_j2_reset_step(int64_t ne, J2Hist h)
 }
 
 typedef void (*force_kernel_t)(const ElemArgs);
-static const int kDefaultMinBlocks = 3; // r01b: 168 regs, 3 CTAs/SM: K1 191 us vs 203 (2) and 201 (4) on 1M elements
-static force_kernel_t pick_force_kernel(int form, int mat, bool geo, bool bbar = false)
+// Register budgets (resident CTAs of 128 threads per SM) from the ncu studies: the small-strain and history materials run at 2
+// (<= 255 registers, no spills); the finite-strain Neo-Hookean laws use the shared-memory pair kernel.
+static force_kernel_t pick_force_kernel(int form, int mat, bool bbar = false)
 {
-    if (form == kSmallStrain && mat == kSSKStV && bbar) return k_internal_force<kSmallStrain, kSSKStVBbar, 2>;
-    if (mat == TB2_EXPL_NEO_HOOKEAN) return form == kSmallStrain ? nullptr : k_internal_force<kTotalLagrangian, kExplNeo, 3>;
-    if (mat == TB2_EXPL_J2) return form == kSmallStrain ? nullptr : k_internal_force<kTotalLagrangian, kExplJ2, 2>;
-    // registers-per-thread cap experiment (TB2_K1_MINBLOCKS=2|3|4 resident CTAs of 128 threads per SM); default from the ncu study
-    static int minb = 0;
-    if (!minb) {
-        const char* s = getenv("TB2_K1_MINBLOCKS");
-        minb = s ? atoi(s) : kDefaultMinBlocks;
-        if (minb < 2 || minb > 8) minb = kDefaultMinBlocks;
+    if (form == kSmallStrain) {
+        if (mat != TB2_SSKSTV) return nullptr;
+        return bbar ? k_internal_force<kSmallStrain, kSSKStVBbar, 2> : k_internal_force<kSmallStrain, kSSKStV, 2>;
     }
-    // UpdatedLagrangianT shares the finite-strain body (see file header)
-    if (form == kUpdatedLagrangian) form = kTotalLagrangian;
-    static int sm_variant = -1; // TB2_K1_SMEM=<resident CTAs per SM> selects the shared-memory-modes variant (experiment knob)
-    if (sm_variant < 0) {
-        const char* s = getenv("TB2_K1_SMEM");
-        sm_variant = s ? atoi(s) : 0;
-    }
-    static int reg_variant = -1; // TB2_K1_REGS=144|152|160: explicit register cap (experiment knob)
-    if (reg_variant < 0) {
-        const char* s = getenv("TB2_K1_REGS");
-        reg_variant = s ? atoi(s) : 0;
-    }
-    static int geo_minb = 0; // TB2_K1_GEO_MINBLOCKS=2|3|4: resident CTAs of the cached-geometry kernel (experiment knob)
-    if (!geo_minb) {
-        const char* s = getenv("TB2_K1_GEO_MINBLOCKS");
-        geo_minb = s ? atoi(s) : 3;
-        if (geo_minb < 2 || geo_minb > 4) geo_minb = 3;
-    }
-    if (geo && form == kTotalLagrangian && mat == kSimoIso)
-        return geo_minb == 2 ? k_internal_force_simo_geo<2> : (geo_minb == 3 ? k_internal_force_simo_geo<3> : k_internal_force_simo_geo<4>);
-    if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 144) return k_internal_force_r<kTotalLagrangian, kSimoIso, 144>;
-    if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 152) return k_internal_force_r<kTotalLagrangian, kSimoIso, 152>;
-    if (form == kTotalLagrangian && mat == kSimoIso && reg_variant == 160) return k_internal_force_r<kTotalLagrangian, kSimoIso, 160>;
-    static int threads_variant = -1; // TB2_K1_THREADS=64|96: smaller CTAs at a finer register cap (experiment knob)
-    if (threads_variant < 0) {
-        const char* s = getenv("TB2_K1_THREADS");
-        threads_variant = s ? atoi(s) : 0;
-    }
-    if (form == kTotalLagrangian && mat == kSimoIso && threads_variant == 64)
-        return minb <= 6 ? k_internal_force<kTotalLagrangian, kSimoIso, 6, 64> : (minb == 7 ? k_internal_force<kTotalLagrangian, kSimoIso, 7, 64> : k_internal_force<kTotalLagrangian, kSimoIso, 8, 64>);
-    if (form == kTotalLagrangian && mat == kSimoIso && threads_variant == 96)
-        return minb <= 4 ? k_internal_force<kTotalLagrangian, kSimoIso, 4, 96> : k_internal_force<kTotalLagrangian, kSimoIso, 5, 96>;
-    if (form == kTotalLagrangian && mat == kSimoIso && sm_variant > 0)
-        return sm_variant <= 3 ? k_internal_force_simo_sm<3> : (sm_variant == 4 ? k_internal_force_simo_sm<4> : k_internal_force_simo_sm<5>);
-    switch (form * 4 + mat) {
-    case kSmallStrain * 4 + kSSKStV: return k_internal_force<kSmallStrain, kSSKStV, 2>;
-    case kTotalLagrangian * 4 + kFDKStV: return k_internal_force<kTotalLagrangian, kFDKStV, 2>;
-    case kTotalLagrangian * 4 + kSimoIso:
-        if (minb > 4) minb = 4;
-        return minb == 2 ? k_internal_force<kTotalLagrangian, kSimoIso, 2>
-                         : (minb == 3 ? k_internal_force<kTotalLagrangian, kSimoIso, 3> : k_internal_force<kTotalLagrangian, kSimoIso, 4>);
-    case kTotalLagrangian * 4 + kJ2Simo: return k_internal_force<kTotalLagrangian, kJ2Simo, 2>;
+    // UpdatedLagrangianT shares the finite-strain body (tb2_force_core.cuh)
+    switch (mat) {
+    case TB2_FDKSTV: return k_internal_force<kTotalLagrangian, kFDKStV, 2>;
+    case TB2_SIMO_ISO: return k_internal_force_neo<kSimoIso>;
+    case TB2_J2_SIMO: return k_internal_force<kTotalLagrangian, kJ2Simo, 2>;
+    case TB2_EXPL_NEO_HOOKEAN: return k_internal_force_neo<kExplNeo>;
+    case TB2_EXPL_J2: return k_internal_force<kTotalLagrangian, kExplJ2, 2>;
     }
     return nullptr;
 }
@@ -989,7 +573,7 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
                                 const int* d_elist, const unsigned char* d_skip)
 {
     tb2_mesh* m = g->mesh;
-    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind, g->geo.p != nullptr, g->bbar);
+    force_kernel_t k = pick_force_kernel(g->form, g->mat.kind, g->bbar);
     if (!k) {
         set_error("formulation %d does not support material %d", g->form, g->mat.kind);
         return TB2_ERR_ARG;
@@ -1010,91 +594,16 @@ int launch_element_forces_range(tb2_group* g, const double* d_u, const double* d
     p.ul = d_ul;
     p.fe = m->fe.p;
     p.off = g->off.p;
-    p.geo = g->geo.p;
     p.mat = g->mc;
     p.hist = group_hist(g);
     p.iteration = iteration;
     p.status = g->status.p;
-    int T = 128;
-    if (g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_SIMO_ISO) {
-        static int tv = -1;
-        if (tv < 0) {
-            const char* s = getenv("TB2_K1_THREADS");
-            tv = s ? atoi(s) : 0;
-        }
-        if ((tv == 64 || tv == 96) && !(getenv("TB2_K1_SMEM") && atoi(getenv("TB2_K1_SMEM")) > 0)) T = tv;
-    }
     if (e1 <= e0) return TB2_OK;
-    unsigned grid = (unsigned)((e1 - e0 + T - 1) / T);
-    {   // persistent, prefetching form of the finite-strain Neo-Hookean sweep: experiment knob TB2_K1_PERSIST=<waves>, off by default.
-        // r01e, 1M elements: 220 us (168 registers, 244 B of spills for the 16 extra index registers) against 183 us for one
-        // thread per element; 216 us at 2 CTAs/SM (255 registers, no spills).  The sweep sits in a register-bound corner: what
-        // the prefetch saves in exposed gather latency it loses in occupancy or spills.
-        static int persist = -1, sms = 148, pminb = 3;
-        if (persist < 0) {
-            const char* s = getenv("TB2_K1_PERSIST");
-            persist = s ? atoi(s) : 0;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-            const char* s2 = getenv("TB2_K1_MINBLOCKS");
-            pminb = s2 ? atoi(s2) : kDefaultMinBlocks;
-            if (pminb < 2 || pminb > 4) pminb = kDefaultMinBlocks;
-        }
-        if (persist > 0 && g->form != TB2_SMALL_STRAIN && g->mat.kind == TB2_SIMO_ISO && !g->geo.p && T == 128) {
-            k = pminb == 2 ? k_internal_force_persistent<kTotalLagrangian, kSimoIso, 2>
-                           : (pminb == 3 ? k_internal_force_persistent<kTotalLagrangian, kSimoIso, 3> : k_internal_force_persistent<kTotalLagrangian, kSimoIso, 4>);
-            const unsigned resident = (unsigned)(sms * pminb * persist); // persist = waves of resident CTAs (1 = exactly resident)
-            if (grid > resident) grid = resident;
-        }
-    }
+    const int T = 128;
+    const unsigned grid = (unsigned)((e1 - e0 + T - 1) / T);
     {
         ProfScope ps(m, kProfForce, 1, st);
         k<<<grid, T, 0, st>>>(p);
-    }
-    TB2_CUDA(cudaGetLastError());
-    return TB2_OK;
-}
-
-typedef void (*fused_kernel_t)(const ElemArgs, const NodeArgs, const unsigned, const unsigned);
-static fused_kernel_t pick_fused_kernel(tb2_group* g)
-{
-    if (g->bbar || g->geo.p) return nullptr;
-    const int form = g->form == kUpdatedLagrangian ? kTotalLagrangian : g->form;
-    if (form == kSmallStrain && g->mat.kind == TB2_SSKSTV) return k_fused_force_update<kSmallStrain, kSSKStV, 2>;
-    if (form == kTotalLagrangian && g->mat.kind == TB2_FDKSTV) return k_fused_force_update<kTotalLagrangian, kFDKStV, 2>;
-    if (form == kTotalLagrangian && g->mat.kind == TB2_SIMO_ISO) return k_fused_force_update<kTotalLagrangian, kSimoIso, 3>;
-    if (form == kTotalLagrangian && g->mat.kind == TB2_EXPL_NEO_HOOKEAN) return k_fused_force_update<kTotalLagrangian, kExplNeo, 3>;
-    return nullptr; // history materials keep the separate kernels
-}
-bool fused_step_supported(tb2_group* g) { return pick_fused_kernel(g) != nullptr; }
-
-// elements [e0, e1) + nodes [q.n0, q.n1) in one launch on stream st (tb2_explicit.cu: explicit_steps_pipelined)
-int launch_fused_forces_nodes(tb2_group* g, const double* d_u, int64_t e0, int64_t e1, cudaStream_t st, const NodeArgs& q,
-                              const unsigned char* d_skip)
-{
-    tb2_mesh* m = g->mesh;
-    fused_kernel_t k = pick_fused_kernel(g);
-    if (!k) {
-        set_error("no fused element + node kernel for formulation %d / material %d", g->form, g->mat.kind);
-        return TB2_ERR_ARG;
-    }
-    ElemArgs p{};
-    p.e_begin = e0;
-    p.ne = e1;
-    p.stride = m->stride;
-    p.skip = d_skip;
-    p.off = g->off.p;
-    p.conn = m->conn.p;
-    p.X = m->X.p;
-    p.u = d_u;
-    p.fe = m->fe.p;
-    p.mat = g->mc;
-    p.hist = group_hist(g);
-    p.status = g->status.p;
-    const unsigned ne_ctas = (unsigned)((e1 - e0 + 127) / 128), nn_ctas = (unsigned)((q.n1 - q.n0 + 127) / 128);
-    if (ne_ctas + nn_ctas == 0) return TB2_OK;
-    {
-        ProfScope ps(m, kProfForce, 1, st);
-        k<<<ne_ctas + nn_ctas, 128, 0, st>>>(p, q, ne_ctas, nn_ctas);
     }
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
@@ -1236,19 +745,6 @@ int tb2_group_create(tb2_mesh* mesh, int form, const tb2_material* mat, tb2_grou
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist.p, 0, g->hist.n * sizeof(double), mesh->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist_flag.p, 0, g->hist_flag.n * sizeof(int), mesh->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(g->hist_alloc.p, 0, g->hist_alloc.n * sizeof(int), mesh->stream);
-    }
-    // reference-configuration cache of the finite-strain Neo-Hookean force kernel: experiment knob TB2_K1_GEO=1 (448 B per element).
-    // r01e: 24 % fewer FP64 instructions (2282 -> 1724 per element) bought 3.6 % (190.5 -> 183.7 us on 1M elements, ncu) and nothing
-    // inside the slab pipeline: the sweep is bound by dependency latency at 3 warps per scheduler, not by FP64 issue, so the cache
-    // is off by default and its memory stays free.
-    const char* geo_env = getenv("TB2_K1_GEO");
-    if (e == cudaSuccess && form != TB2_SMALL_STRAIN && mat->kind == TB2_SIMO_ISO && geo_env && geo_env[0] == '1') {
-        e = g->geo.alloc((size_t)56 * mesh->stride);
-        if (e == cudaSuccess) {
-            k_reference_geometry<<<(unsigned)((mesh->ne + 127) / 128), 128, 0, mesh->stream>>>(mesh->ne, mesh->stride, mesh->conn.p, mesh->X.p, g->geo.p);
-            mesh->launches++;
-            e = cudaGetLastError();
-        }
     }
     const unsigned long long init[2] = {0ull, ~0ull};
     if (e == cudaSuccess) e = cudaMemcpyAsync(g->status.p, init, sizeof init, cudaMemcpyHostToDevice, mesh->stream);

@@ -95,15 +95,6 @@ struct ProfRec {
 
 } // namespace tb2
 
-namespace tb2 {
-// contiguous element / node index chunks and their dependency ranges (slab pipelines of tb2_explicit.cu)
-struct PipePlan {
-    std::vector<int64_t> e0, n0;            // element chunks [e0[c], e0[c+1]), node chunks likewise
-    std::vector<int> emax_of_nc, nmax_of_ec; // last element chunk touching node chunk c / last node chunk touched by element chunk c
-    int chunks() const { return (int)e0.size() - 1; }
-};
-} // namespace tb2
-
 struct tb2_mesh {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -124,21 +115,7 @@ struct tb2_mesh {
     tb2::DevBuf<int> colour_elems;      // elements sorted by colour
     std::vector<int64_t> colour_start;  // [ncolours+1]
     tb2::Comm* comm = nullptr;
-    // slab pipeline of the explicit step (tb2_explicit.cu): element chunks [pipe_e0[c], pipe_e0[c+1]), node chunks likewise;
-    // pipe_emax_of_nc[c] = last element chunk touching node chunk c, pipe_nmax_of_ec[c] = last node chunk touched by element chunk c
-    std::vector<int64_t> pipe_e0, pipe_n0;
-    std::vector<int> pipe_emax_of_nc, pipe_nmax_of_ec;
-    // host-buffer step (tb2_explicit_step_host): finer slabs, so that the H2D copy of the later slabs and the D2H copy of the
-    // finished ones overlap (full-duplex PCIe) with the kernels in between
-    tb2::PipePlan hplan;
-    cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
-    std::vector<cudaEvent_t> ev_h2d, ev_pred, ev_hk1, ev_hk5;
-    cudaEvent_t ev_d2h_done = nullptr;
-    cudaStream_t stream2 = nullptr;
-    cudaStream_t stream1b = nullptr; // odd element chunks of the slab pipeline (consecutive chunks overlap their launch tails)
-    cudaEvent_t ev_join1b = nullptr;
-    std::vector<cudaEvent_t> ev_k1, ev_k5;
-    cudaEvent_t ev_join = nullptr;
+    cudaEvent_t ev_join = nullptr, ev_k5 = nullptr; // the two lanes of the multi-GPU explicit step (tb2_explicit.cu)
     bool prof_on = false;
     std::vector<tb2::ProfRec> prof; // event pool
     size_t prof_used = 0;
@@ -188,7 +165,6 @@ struct tb2_group {
     tb2::DevBuf<unsigned long long> status; // [0] error code, [1] first bad element
     tb2::DevBuf<double> mass_scale; // [ne] ExplicitElementT::fMassScale (null: no mass scaling)
     tb2::DevBuf<unsigned char> off; // [ne] 1 = ElementCardT::kOFF: the element loops skip it (null: every element is on)
-    tb2::DevBuf<double> geo;       // [8][7][stride] M0 = adj(J0) adj(J0)^T and det J0 per integration point (finite-strain SimoIso3D fast path)
 };
 
 struct tb2_equations {
@@ -235,4 +211,11 @@ struct tb2_explicit {
     tb2_group* group = nullptr;
     tb2::DevBuf<double> d, v, a, mass, minv, fext, fint, bcval;
     tb2::DevBuf<unsigned char> bccode;
+    bool has_fext = false; // fext holds a non-zero entry (an all-zero external force is not read by the node kernel)
+    // tb2_explicit_run_async: displacement snapshots on their way to the host beside the next steps' kernels
+    tb2::DevBuf<double> dsnap[2];
+    cudaStream_t stream_copy = nullptr;
+    cudaEvent_t ev_snap[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    unsigned long long* h_status = nullptr; // pinned [2][2]: the group's status words as of each delivered snapshot
+    int tickets = 0;
 };

@@ -1,12 +1,12 @@
-// tb2_node_update.cuh -- the node kernel body of the explicit step (K5), shared by the stand-alone kernel (tb2_explicit.cu) and
-// the fused element + node launches of the slab pipeline (tb2_elements.cu).
+// tb2_node_update.cuh -- the node kernel body of the explicit step (K5).
 #pragma once
+#include "../../include/tahoe_b200.h"
 #include "tb2_math.cuh"
 
 namespace tb2 {
 
-// nExplicitCD::Predictor (nExplicitCD.cpp:72-96) / Corrector (:98-139) with explicit roundings, so that the stand-alone and
-// the fused kernels produce bit-identical fields
+// nExplicitCD::Predictor (nExplicitCD.cpp:72-96) / Corrector (:98-139) with explicit roundings, so that every kernel that
+// carries them produces bit-identical fields
 TB2_DEV void cd_predict(double dt, double& d, double& v, double a)
 {
     d = __fma_rn(dt, v, d);
@@ -19,30 +19,61 @@ TB2_DEV void cd_correct(double dt, double& v, double& a, double upd)
     a = __dadd_rn(a, upd);
 }
 
-// one node: gather fint, R = s*fext - fint, upd = minv*R on free dofs, corrector; optionally the next predictor (see k_cd_node_update)
-template <bool GATHER, bool NEXT_PREDICTOR>
-TB2_DEV void cd_node_update_one(const int64_t n, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
-                                const int4* __restrict__ inc8, const double* __restrict__ fe, int64_t stride, double dt,
-                                double fext_scale, double next_value_scale, const double* __restrict__ fext,
-                                const double* __restrict__ minv, const unsigned char* __restrict__ code,
-                                const double* __restrict__ bcval, double* __restrict__ d,
-                                double* __restrict__ v, double* __restrict__ a, double* __restrict__ fint,
-                                const int* __restrict__ skip_slot)
+struct StepConsts {
+    double dt, fext_scale, next_value_scale;
+};
+
+// One nodal dof from its assembled internal force f: R = s fext - f (LinearSolver::Solve), upd = M^-1 R on free dofs
+// (DiagonalMatrixT.cpp:313-323, FieldT::AssembleUpdate: prescribed dofs get 0), corrector; NEXT_PREDICTOR: the next step's
+// predictor and ConsistentKBC (nExplicitCD.cpp:20-69).  The acceleration the predictor left behind is 0 on every dof
+// (nExplicitCD.cpp:93), so it is not read; after a fused next predictor it is 0 again and not written.
+template <bool NEXT_PREDICTOR>
+TB2_DEV void cd_update_dof(const StepConsts& u, const unsigned char c, const double f, const double fx, const double mi, const double bcv,
+                           double& di, double& vi, double& ai)
 {
-    if (skip_slot && skip_slot[n] >= 0) return;
+    const double R = __dsub_rn(__dmul_rn(u.fext_scale, fx), f);
+    const double upd = c ? 0.0 : __dmul_rn(R, mi);
+    ai = 0.0;
+    cd_correct(u.dt, vi, ai, upd);
+    if (NEXT_PREDICTOR) {
+        cd_predict(u.dt, di, vi, ai);
+        ai = 0.0;
+        if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
+        else if (c == TB2_BC_DSP) di = u.next_value_scale * bcv;
+    }
+}
+
+struct NodeArrays {
+    const double* fext; // null: no external force
+    const double* minv;
+    const unsigned char* code;
+    const double* bcval;
+    double* d;
+    double* v;
+    double* a;
+    double* fint;
+};
+
+// one node: gather fint (GATHER) or take it from fint[] (multi-GPU: the interface-summed force), then the update above.
+// GATHER reads the node's incidence from the fixed-width table inc8 (one 32-byte load) and issues every load of the node -- the
+// <= 8 x 3 element forces and the nodal fields -- before the first use.  Per node and step the steady state (NEXT_PREDICTOR) moves
+// d, v in and out, 1/m, the boundary codes and fext (when there is one) in: a stays 0 and fint is written by the last step only.
+template <bool GATHER, bool NEXT_PREDICTOR>
+TB2_DEV void cd_node_update_one(const int64_t n, const int* __restrict__ inc_ptr, const int* __restrict__ inc, const int4* __restrict__ inc8,
+                                const double* __restrict__ fe, int64_t stride, const StepConsts& sc, const NodeArrays& na)
+{
     double f[3] = {0.0, 0.0, 0.0};
     // nodal operands first: independent of the gather, in flight while it resolves its two dependent round trips
-    double fx[3], mi[3], vv[3], aa[3], dd[3] = {0.0, 0.0, 0.0};
+    double fx[3], mi[3], vv[3], dd[3] = {0.0, 0.0, 0.0};
     unsigned char cc[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int64_t q = 3 * n + i;
-        cc[i] = code[q];
-        fx[i] = fext[q];
-        mi[i] = minv[q];
-        vv[i] = v[q];
-        aa[i] = a[q];
-        if (NEXT_PREDICTOR) dd[i] = d[q];
+        cc[i] = na.code[q];
+        fx[i] = na.fext ? na.fext[q] : 0.0;
+        mi[i] = na.minv[q];
+        vv[i] = na.v[q];
+        if (NEXT_PREDICTOR) dd[i] = na.d[q];
     }
     if (GATHER) {
         int ent[8];
@@ -77,51 +108,23 @@ TB2_DEV void cd_node_update_one(const int64_t n, const int* __restrict__ inc_ptr
                 f[2] += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
             }
     } else {
-        f[0] = fint[3 * n];
-        f[1] = fint[3 * n + 1];
-        f[2] = fint[3 * n + 2];
+        f[0] = na.fint[3 * n];
+        f[1] = na.fint[3 * n + 1];
+        f[2] = na.fint[3 * n + 2];
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int64_t q = 3 * n + i;
-        const unsigned char c = cc[i];
-        const double R = __dsub_rn(__dmul_rn(fext_scale, fx[i]), f[i]);
-        const double upd = c ? 0.0 : __dmul_rn(R, mi[i]);
-        double vi = vv[i], ai = aa[i];
-        cd_correct(dt, vi, ai, upd);
-        if (GATHER) fint[q] = f[i];
-        if (NEXT_PREDICTOR) {
-            double di = dd[i];
-            cd_predict(dt, di, vi, ai);
-            ai = 0.0;
-            if (c == TB2_BC_FIX) { di = 0.0; vi = 0.0; }
-            else if (c == TB2_BC_DSP) di = next_value_scale * bcval[q];
-            d[q] = di;
+        double di = dd[i], vi = vv[i], ai;
+        const double bcv = (NEXT_PREDICTOR && cc[i] == TB2_BC_DSP) ? na.bcval[q] : 0.0;
+        cd_update_dof<NEXT_PREDICTOR>(sc, cc[i], f[i], fx[i], mi[i], bcv, di, vi, ai);
+        if (NEXT_PREDICTOR) na.d[q] = di;
+        else {
+            na.a[q] = ai;
+            if (GATHER) na.fint[q] = f[i];
         }
-        v[q] = vi;
-        a[q] = ai;
+        na.v[q] = vi;
     }
 }
-
-// arguments of the node part of a fused launch
-struct NodeArgs {
-    int64_t n0, n1; // node range updated by this launch (empty: element work only)
-    const int* inc_ptr;
-    const int* inc;
-    const int4* inc8;
-    const double* fe;
-    int64_t stride;
-    double dt, fext_scale, next_value_scale;
-    const double* fext;
-    const double* minv;
-    const unsigned char* code;
-    const double* bcval;
-    double* d;
-    double* v;
-    double* a;
-    double* fint;
-    const int* skip_slot;
-    int next_predictor;
-};
 
 } // namespace tb2

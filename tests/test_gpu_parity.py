@@ -350,8 +350,8 @@ def test_explicit_solid_matches_reference_and_oracle(tb2, oracle, name):
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("dims", [(6, 6, 6), (24, 20, 17), (40, 40, 40)])
 def test_explicit_step_host_equals_resident_run(tb2, dims, pinned):
-    """host-buffer step (tb2_explicit_step_host; >= 1024 elements: the slab pipeline that overlaps the upload, the kernels and
-    the download; pinned = registered host arrays, which the kernels write directly) against the device-resident run: bitwise"""
+    """host-buffer step (tb2_explicit_step_host: Tahoe's FieldT stays authoritative, d, v, a in and out every step; pinned =
+    registered host arrays) against the device-resident run: bitwise"""
     X, conn, ns, u = _synthetic(dims, amp=5e-3)
     mesh = tb2.Mesh(X, conn)
     grp = tb2.Group(mesh, 1, tb2.material({"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0}))
@@ -377,10 +377,10 @@ def test_explicit_step_host_equals_resident_run(tb2, dims, pinned):
     assert np.array_equal(d, d1) and np.array_equal(v, v1) and np.array_equal(a, a1)
 
 
-def test_pipelined_explicit_run_is_bitwise_the_serial_schedule(tb2):
-    """64^3 elements -> 3 slab chunks: the two-stream pipeline (tb2_explicit_run with nsteps > 1) must give bitwise the
-    result of single steps (serial schedule), and the same again on a rerun"""
-    n = 64
+def test_fused_predictor_run_is_bitwise_single_steps_and_reruns(tb2):
+    """tb2_explicit_run with nsteps > 1 fuses the next step's predictor into the node kernel (a stays 0 on the device, fint is
+    written by the last step only): bitwise the result of single steps, and the same again on a rerun; with a non-zero fext"""
+    n = 40
     X, conn, ns = ti.structured_cube(n, jitter=0.1)
     mesh = tb2.Mesh(X, conn)
     grp = tb2.Group(mesh, 1, tb2.material({"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0}))
@@ -391,22 +391,70 @@ def test_pipelined_explicit_run_is_bitwise_the_serial_schedule(tb2):
     dt = 0.25 / n / np.sqrt(1000.0 + 20.0 / 3.0)
     u0 = 1e-3 * np.sin(5.0 * X[:, ::-1])
     out = []
-    for mode in ("pipelined", "single", "pipelined"):
+    for mode in ("fused", "single", "fused"):
         ex = tb2.Explicit(grp)
         ex.set_bc(code, np.zeros_like(X), fext)
         ex.set_state(u0, np.zeros_like(X), np.zeros_like(X))
-        if mode == "pipelined":
+        if mode == "fused":
             ex.run(dt, 7)
         else:
             for _ in range(7):
                 ex.run(dt, 1)
-        out.append(ex.get_state())
+        fint = np.zeros_like(X)
+        tb2.memcpy_d2h(mesh.device, fint, ex.device_array(5))
+        out.append(ex.get_state() + (fint,))
         ex.close()
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     for a, b in zip(out[0], out[2]):
         assert np.array_equal(a, b)
-    assert np.abs(out[0][0] - u0).max() > 0
+    assert np.abs(out[0][0] - u0).max() > 0 and np.abs(out[0][3]).max() > 0
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_explicit_run_async_delivers_the_resident_displacements(tb2, pinned):
+    """tb2_explicit_run_async / tb2_explicit_wait (the resident drop-in's mode: v, a stay on the device, d goes to the host on a
+    copy stream beside the next steps): every delivered snapshot is bitwise the displacement of the synchronous run at that step,
+    with two calls in flight and the host buffers reused alternately"""
+    X, conn, ns, u = _synthetic((20, 16, 12), amp=5e-3)
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, 1, tb2.material({"type": "Simo_isotropic", "kappa": 1000.0, "mu": 5.0, "density": 1.0}))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    dt = 1e-4
+    nsnap, per = 6, (1, 2, 1, 3, 1, 1)
+    ref = tb2.Explicit(grp)
+    ref.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    ref.set_state(u, np.zeros_like(X), np.zeros_like(X))
+    want = []
+    for k in range(nsnap):
+        ref.run(dt, per[k])
+        want.append(ref.get_state()[0])
+    ex = tb2.Explicit(grp)
+    ex.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    ex.set_state(u, np.zeros_like(X), np.zeros_like(X))
+    bufs = [np.zeros_like(X), np.zeros_like(X)]
+    if pinned:
+        for b in bufs:
+            tb2.host_register(b)
+    try:
+        tickets = []
+        for k in range(nsnap):
+            if k >= 2:  # the buffer about to be reused: wait for the call that filled it, then check it
+                ex.wait(tickets[k - 2])
+                assert np.array_equal(bufs[k & 1], want[k - 2])
+            tickets.append(ex.run_async(dt, per[k], bufs[k & 1]))
+        ex.wait(tickets[-2])
+        assert np.array_equal(bufs[nsnap & 1], want[-2])
+        ex.wait(tickets[-1])
+        assert np.array_equal(bufs[(nsnap - 1) & 1], want[-1])
+    finally:
+        if pinned:
+            for b in bufs:
+                tb2.host_unregister(b)
+    d, v, a = ex.get_state()
+    dr, vr, ar = ref.get_state()
+    assert np.array_equal(d, dr) and np.array_equal(v, vr) and np.array_equal(a, ar)
 
 
 # ------------------------------------------------------------------ K9 structure
