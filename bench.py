@@ -242,7 +242,12 @@ def run_reference_arm(args):
         dt, cores, kind, sample = ne * k / rate, 1, "port", "oracle/tahoe_oracle.c internal-force sweeps on 24^3 (reference binary absent)"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": METRIC, "n_gpus": args.gpus, "steps": k, "warmup": w,
             "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args.n, args.gpus),
+            "data": "synthetic",
+            # the workload family and metric of the GPU arm; what is actually timed is `reference_workload` (CPU rates are
+            # taken per element on sizes the reference finishes in minutes -- a cache-resident size without communication favours the CPU)
+            "config": dict(workload_config(args.n, args.gpus), same_config=False,
+                           reference_workload="%d^3=%d-element cube x %d concurrent serial processes (one per host core), per-element rate "
+                                              "extrapolated to the %d^3 workload" % (n, ne, cores, args.n)),
             "cpu_baseline": {"value": rate, "unit": METRIC, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -525,6 +530,121 @@ def run_nlpcg_j2(torch, capi, tmesh, local, n, iters):
 # ---------------------------------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def parity_check(torch, dist, capi, tmesh, rank, world, local):
+    """Before anything is timed: the partitioned run must reproduce the single-GPU run of the same mesh.  N > 1: 16^3 elements per
+    rank, 8 explicit steps (TL Neo-Hookean) and one small-strain Jacobi-PCG solve on the element-partitioned cube against rank 0's
+    own single-GPU run of the whole cube -- max relative difference over d, v, a and over the PCG solution, and whether all sharers
+    of an interface node hold bitwise identical values.  N = 1: the same steps twice, bit for bit.  Returns the "parity" object."""
+    n = 16
+    dev = local
+
+    def explicit(X, conn, ns, comm, nsteps=8):
+        m = capi.Mesh(X, conn, device=dev)
+        if comm:
+            m.comm_init(*comm)
+        g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MATERIAL))
+        ex = capi.Explicit(g)
+        code = np.zeros(X.shape, np.uint8)
+        code[ns[1]] = 1
+        fext = np.zeros_like(X)
+        fext[ns[2], 0] = 1e-3
+        ex.set_bc(code, np.zeros_like(X), fext)
+        ex.set_state(0.01 * X @ np.array([[0.3, -0.2, 0.1], [0.05, 0.4, -0.3], [0.2, 0.1, -0.25]]) + 1e-3 * np.sin(7.0 * X[:, ::-1]),
+                     np.zeros_like(X), np.zeros_like(X))
+        ex.run(2e-4, nsteps)
+        out = ex.get_state()
+        # the implicit side: K x = f with this rank's sub-domain matrix
+        g2 = capi.Group(m, capi.SMALL_STRAIN, capi.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
+        eqs = capi.Equations(m, code)
+        A = capi.Matrix(eqs)
+        A.form_stiffness_host(g2, np.zeros_like(X))
+        act = eqs.eqnos() > 0
+        x, it, rn = A.pcg_host(fext[act], rtol=1e-12, max_iter=20000)
+        xs = np.zeros_like(X)
+        xs[act] = x
+        A.close(); eqs.close(); g2.close(); ex.close(); g.close(); m.close()
+        return out + (xs, it)
+
+    if world == 1:
+        X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+        a, b = explicit(X, conn, ns, None), explicit(X, conn, ns, None)
+        same = all(np.array_equal(p, q) for p, q in zip(a[:4], b[:4]))
+        if not same:
+            raise SystemExit("bench.py: two runs of the same steps differ bitwise")
+        return {"kind": "rerun", "bitwise_rerun": True, "note": "N = 1: 8 explicit steps + one PCG solve of a 16^3 cube run twice, identical bits; "
+                "parity against the oracle is tests/ (-m gpu), incl. configs[1] at full size"}
+    gx, gy, gz = tmesh.brick_grid(world)
+    dims = (n * gx, n * gy, n * gz)
+    part = tmesh.partition_cube(*dims, world, rank, jitter=0.1)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    d, v, a, xs, it = explicit(part["coords"], part["conn"], part["nodesets"],
+                               (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"]))
+    out = [None] * world
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a, "xs": xs, "it": it})
+    res = None
+    if rank == 0:
+        X, conn, ns = tmesh.structured_cube(*dims, jitter=0.1)
+        d1, v1, a1, xs1, it1 = explicit(X, conn, ns, None)
+        worst, worst_pcg, bitwise, seen = 0.0, 0.0, True, {}
+        for o in out:
+            for got, ref in ((o["d"], d1), (o["v"], v1), (o["a"], a1)):
+                worst = max(worst, float(np.abs(got - ref[o["gid"]]).max() / max(np.abs(ref).max(), 1e-300)))
+            worst_pcg = max(worst_pcg, float(np.abs(o["xs"] - xs1[o["gid"]]).max() / np.abs(xs1).max()))
+            rows = np.hstack([o["d"], o["v"], o["a"]])
+            for gid, row in zip(o["gid"], rows):
+                prev = seen.get(gid)
+                if prev is not None and not np.array_equal(prev, row):
+                    bitwise = False
+                seen[gid] = row
+        res = {"kind": "partitioned vs single GPU", "max_rel": worst, "bitwise_sharers": bitwise, "pcg_max_rel": worst_pcg,
+               "pcg_iterations": {"single": int(it1), "partitioned": [int(o["it"]) for o in out]},
+               "workload": "%dx%dx%d elements in %d bricks, 8 explicit steps (d, v, a) and one Jacobi-PCG solve to 1e-12" % (dims + (world,))}
+    flag = torch.tensor([0.0], device="cuda", dtype=torch.float64)
+    if rank == 0 and (not res["max_rel"] < 1e-10 or not res["bitwise_sharers"] or not res["pcg_max_rel"] < 1e-8):
+        flag += 1.0
+    dist.all_reduce(flag)
+    if float(flag.item()) > 0:
+        if rank == 0:
+            print("bench.py: multi-GPU parity check FAILED: %s" % json.dumps(res), file=sys.stderr)
+        raise SystemExit(3)
+    return res
+
+
+def run_shuffled(torch, capi, tmesh, local, n, steps, dt):
+    """the headline workload on a node- and element-shuffled copy of the mesh (no gather locality to rely on): element-updates/s"""
+    X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+    rng = np.random.default_rng(7)
+    nperm = rng.permutation(X.shape[0])
+    Xs = np.empty_like(X)
+    Xs[nperm] = X
+    conn_s = np.ascontiguousarray(nperm[conn][rng.permutation(conn.shape[0])].astype(np.int32))
+    m = capi.Mesh(Xs, conn_s, device=local)
+    g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MATERIAL))
+    ex = capi.Explicit(g)
+    code = np.zeros(Xs.shape, np.uint8)
+    code[nperm[ns[1]]] = 1
+    ex.set_bc(code, np.zeros_like(Xs), np.zeros_like(Xs))
+    ex.set_state(initial_displacement(Xs), np.zeros_like(Xs), np.zeros_like(Xs))
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
+    ex.run(dt, 5)
+    m.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ex.run(dt, steps)
+    e1.record(stream)
+    m.synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    d, v, a = ex.get_state()
+    ok = bool(np.isfinite(d).all())
+    ex.close(); g.close(); m.close()
+    if not ok:
+        raise SystemExit("bench.py: non-finite state on the shuffled mesh")
+    return {"value": conn.shape[0] * steps / (ms * 1e-3), "unit": METRIC, "ms_per_step": ms / steps, "steps": steps,
+            "workload": "the same %d^3 cube with node and element numbers permuted at random (seed 7)" % n}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -545,6 +665,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.lib()
     n = args.n
+    parity = None if args.no_parity else parity_check(torch, dist, capi, tmesh, rank, world, local)
     # ---- mesh: one n^3 brick per rank (weak scaling)
     if world == 1:
         X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
@@ -679,7 +800,7 @@ def run_gpu_arm(args):
         k1_bytes = 104.0 * ne_local / k1_lps
         k1_flops = args.k1_flop_per_element * ne_local / k1_lps
         k1_insts = args.k1_fp64_inst_per_element * ne_local / k1_lps
-        roof = {"bound": "hbm", "kernel": "k_internal_force<TL,SimoIso> (K1)", "achieved": k1_bytes / (k1_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak,
+        roof = {"bound": "hbm", "kernel": "k_internal_force_neo<SimoIso> (K1)", "achieved": k1_bytes / (k1_launch_ms * 1e-3) * 1e-9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": k1_bytes / (k1_launch_ms * 1e-3) * 1e-9 / hbm_peak,
                 "traffic": args.k1_traffic_bytes_per_element * ne_local / k1_lps, "peak_source": hbm_src,
                 "avg_launch_ms": k1_launch_ms, "launches_per_step": k1_lps, "elements_per_launch": ne_local / k1_lps,
@@ -723,6 +844,7 @@ def run_gpu_arm(args):
                              "interior elements -> private nodes on the main stream"),
                 "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
                 "interface_exchange_ms": comm_ms if world > 1 else None,
+                "parity": parity,
                 "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None}
     ex.close(); g.close(); m.close()
     hbm_peak_all = 6650.0
@@ -734,10 +856,13 @@ def run_gpu_arm(args):
     xs = None
     if world == 1 and not args.no_explicit_solid:
         xs = run_explicit_solid(torch, capi, tmesh, local, n, min(args.steps, 200), args.warmup, hbm_peak_all, not args.no_cpu_baseline)
+    shuffled = run_shuffled(torch, capi, tmesh, local, n, min(args.steps, 100), dt) if (world == 1 and not args.no_shuffled) else None
     j2 = None
     if world == 1 and args.nlpcg_n > 0:
         j2 = run_nlpcg_j2(torch, capi, tmesh, local, args.nlpcg_n, args.nlpcg_iters)
     if rank == 0:
+        if shuffled:
+            line["shuffled_numbering"] = shuffled
         if j2:
             line["nlpcg_j2"] = j2
         if xs:
@@ -764,6 +889,8 @@ def main():
     ap.add_argument("--no-explicit-solid", action="store_true", help="skip the <explicit_solid> leg (SURVEY.md 8f-1)")
     ap.add_argument("--nlpcg-n", type=int, default=48, help="cube edge of the J2 nonlinear-PCG leg (configs[3]; 159 -> 4M elements; 0 = skip)")
     ap.add_argument("--nlpcg-iters", type=int, default=20)
+    ap.add_argument("--no-parity", action="store_true", help="skip the partitioned-vs-single-GPU check that precedes the timing")
+    ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-numbering leg")
     ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")
     ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")
     ap.add_argument("--pcg-iters", type=int, default=100)
@@ -785,11 +912,12 @@ def main():
     sys.stdout.flush()
 
 
-# Per-element figures of K1 <TL, SimoIso> from the ncu --set full capture profiles/r01d_k1_details.csv (284,160-element slab launch):
-# thread-level DFMA 1316 + DMUL 573 + DADD 285 = 2174 FP64 instructions = 3490 flop; dram read 23.5 MB + write 11.6 MB = 123.5 B/element.
-K1_FLOP_PER_ELEMENT = 3490.0
-K1_FP64_INST_PER_ELEMENT = 2174.0
-K1_TRAFFIC_BYTES_PER_ELEMENT = 123.5
+# Per-element figures of K1 <TL, SimoIso> (k_internal_force_neo) from the ncu --set full capture profiles/r02_k1_details.csv (one launch over
+# 10^6 elements): thread-level DFMA 905 + DMUL 539 + DADD 426 = 1870 FP64 instructions = 2775 flop (round 1: 2174 / 3490: the pair-wise
+# integration-point loop executes fewer); dram read 81.5 MB + write 135.5 MB = 217 B/element (the 192 B/element force scratch is the bulk).
+K1_FLOP_PER_ELEMENT = 2775.0
+K1_FP64_INST_PER_ELEMENT = 1870.0
+K1_TRAFFIC_BYTES_PER_ELEMENT = 217.0
 # K3 element kernel <small strain, SSKStV, symmetric half> (profiles/r01e_k3_*): DFMA 7961 + DMUL 4683 + DADD 2979 per element
 K3_FLOP_PER_ELEMENT = 2 * 7961.0 + 4683.0 + 2979.0
 # k_spmv DRAM read+write per stored non-zero (ncu --set full, profiles/r01c_spmv_full: 2.465 GB for 242,991,882 nnz)

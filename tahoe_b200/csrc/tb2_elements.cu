@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(128, 3) k_internal_force_neo(const ElemArgs p)
                 sx[(3 * k + i) * 128 + tid] = cX.m[k][i] + cU.m[k][i];
             }
     }
+    asm volatile("" ::: "memory"); // the mode loads of the loop are volatile asms the compiler must keep behind these stores
     Modes A;
     const int err = force_modes_neo_pairs<MAT>(p.mat, SmemModes(sX + tid, 128), SmemModes(sx + tid, 128), A);
     if (err) report(p, err, e);

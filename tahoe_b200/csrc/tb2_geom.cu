@@ -186,25 +186,45 @@ bool next_int(Cursor& c, int64_t& v)
     return next_token(c, b, e) && to_i64(b, e, v);
 }
 
+// ModelFileT::GetElementSet -> nArray2DT::ReadNumbered (nArray2DT.h:1071): each record is "<number> n1 .. nen" and the row goes
+// to index number - 1, whatever the order of the records (side sets address elements by that number).  A record can straddle a
+// thread chunk, so rows are staged per record and scattered afterwards; numbers outside 1..nel and repeated numbers are errors.
 bool parse_element_set(Cursor c, tb2_geom::Block& blk, int64_t nn, Cursor* after)
 {
     int64_t nel, nen;
     if (!next_int(c, nel) || !next_int(c, nen) || nel != blk.nel || nen != blk.nen) return false;
-    blk.conn.resize((size_t)nel * nen);
-    int32_t* conn = blk.conn.data();
+    blk.conn.assign((size_t)nel * nen, 0);
+    std::vector<int32_t> stage((size_t)nel * nen);
+    std::vector<int64_t> row((size_t)nel, -1);
+    int32_t* st = stage.data();
+    int64_t* rowp = row.data();
     const int per = (int)nen + 1;
     bool okr = parse_records(c, nel, per, [=](int64_t rec, int fld, const char* b, const char* e) {
         int64_t v;
         if (!to_i64(b, e, v)) return false;
-        if (fld == 0) return true; // element id: rows are kept in file order
+        if (fld == 0) {
+            if (v < 1 || v > nel) return false;
+            rowp[rec] = v - 1;
+            return true;
+        }
         if (v < 1 || v > nn) return false;
-        conn[rec * (per - 1) + fld - 1] = (int32_t)(v - 1);
+        st[rec * (per - 1) + fld - 1] = (int32_t)(v - 1);
         return true;
     });
+    if (!okr) return false;
+    std::vector<char> seen((size_t)nel, 0);
+    int32_t* conn = blk.conn.data();
+    for (int64_t r = 0; r < nel; r++) {
+        const int64_t to = rowp[r];
+        if (to < 0 || seen[to]) return false;
+        seen[to] = 1;
+        memcpy(conn + to * nen, st + r * nen, (size_t)nen * sizeof(int32_t));
+    }
     if (after) *after = c;
-    return okr;
+    return true;
 }
 
+// ModelFileT::GetCoordinates -> dArray2DT::ReadNumbered: "<number> x y z", placed by number; repeated numbers are errors
 bool parse_nodes(Cursor c, tb2_geom& g, Cursor* after)
 {
     int64_t nn, nsd;
@@ -231,8 +251,10 @@ bool parse_nodes(Cursor c, tb2_geom& g, Cursor* after)
         return true;
     });
     if (!okr) return false;
+    std::vector<char> seen((size_t)nn, 0);
     for (int64_t r = 0; r < nn; r++) {
-        if (rowp[r] < 0) return false;
+        if (rowp[r] < 0 || seen[rowp[r]]) return false;
+        seen[rowp[r]] = 1;
         for (int j = 0; j < (int)nsd; j++) X[rowp[r] * 3 + j] = st[r * nsd + j];
     }
     if (after) *after = c;

@@ -197,6 +197,8 @@ struct tb2_matrix {
     const double* pcg_x = nullptr;
     double pcg_rtol = 0.0, pcg_atol = 0.0;
     int pcg_maxit = 0;
+    bool pcg_last_converged = true; // the last tb2_matrix_pcg met rtol / atol (false: it stopped at max_iter)
+    double pcg_last_rel = 0.0;      // its |r| / |r0|
     // two-phase assembly (tb2_stiffness.cu): contributions e*64+a*8+b of every node block, ascending in e; the element-matrix
     // scratch of one element chunk; the node range each chunk touches
     int64_t nadj = 0;

@@ -923,6 +923,8 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     TB2_CUDA(cudaStreamSynchronize(st));
     if (iterations) *iterations = h.iters;
     if (final_rnorm) *final_rnorm = hs[kRNORM];
+    A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]); // the device's own stop test (k_reduce_rz)
+    A->pcg_last_rel = hs[kR0] > 0.0 ? hs[kRNORM] / hs[kR0] : 0.0;
     if (h.breakdown) {
         set_error("PCG breakdown: p.Ap = %g <= 0 (matrix not positive definite)", hs[kPAP]);
         return TB2_ERR_PCG_BREAKDOWN;
@@ -1003,10 +1005,20 @@ int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, d
     TB2_CUDA(cudaStreamSynchronize(st));
     if (iterations) *iterations = h.iters;
     if (final_rnorm) *final_rnorm = hs[kRNORM];
+    A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]); // the device's own stop test (k_reduce_rz)
+    A->pcg_last_rel = hs[kR0] > 0.0 ? hs[kRNORM] / hs[kR0] : 0.0;
     if (h.breakdown) {
         set_error("PCG breakdown: p.Ap = %g <= 0 (matrix not positive definite)", hs[kPAP]);
         return TB2_ERR_PCG_BREAKDOWN;
     }
+    return TB2_OK;
+}
+
+int tb2_matrix_pcg_converged(const tb2_matrix* A, int* converged, double* relative_residual)
+{
+    TB2_ARG(A);
+    if (converged) *converged = A->pcg_last_converged ? 1 : 0;
+    if (relative_residual) *relative_residual = A->pcg_last_rel;
     return TB2_OK;
 }
 

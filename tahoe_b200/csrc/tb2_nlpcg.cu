@@ -347,7 +347,7 @@ int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const dou
     NL_TRY(form_rhs(c, false, h));
     error = std::sqrt(h[0]);
     *status = exit_iteration(c.iteration);
-    while (*status == TB2_SOLVER_CONTINUE) {
+    while (*status == TB2_SOLVER_CONTINUE && (solve_max_iterations < 0 || num_iterations < solve_max_iterations)) { // NLSolver.cpp:130-131
         num_iterations++;
         tan_iterations++;
         if (num_iterations == 1 || tan_iterations >= prm.restart) { // fReformTangentIterations = fRestart
@@ -430,7 +430,6 @@ int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const dou
         }
         error = std::sqrt(rr_last);
         *status = exit_iteration(c.iteration);
-        if (solve_max_iterations >= 0 && num_iterations >= solve_max_iterations) break;
     }
 #undef NL_TRY
 done:
@@ -522,6 +521,8 @@ static int newton_core(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np,
     *status = TB2_SOLVER_CONTINUE;
     int rc = TB2_OK, num_iterations = 0, tan_iterations = 0;
     int64_t lin_total = 0;
+    int lin_unconverged = 0;
+    double lin_worst = 0.0;
     double h[2], error = 0.0, error0 = 0.0;
     const int reform = np->reform_tangent_iterations > 0 ? np->reform_tangent_iterations : 1;
     auto exit_iteration = [&](int iter) {
@@ -541,7 +542,8 @@ static int newton_core(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np,
         error = std::sqrt(h[0]);
         *status = exit_iteration(c.iteration);
     }
-    while (rc == TB2_OK && *status == TB2_SOLVER_CONTINUE) {
+    // NLSolver::Solve tests the bound in the loop condition (NLSolver.cpp:130-131): max_iterations == 0 does no iteration at all
+    while (rc == TB2_OK && *status == TB2_SOLVER_CONTINUE && (solve_max_iterations < 0 || num_iterations < solve_max_iterations)) {
         num_iterations++;
         tan_iterations++;
         if (num_iterations == 1 || tan_iterations >= reform) { // NLSolver.cpp:143-160
@@ -561,17 +563,28 @@ static int newton_core(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np,
         rc = tb2_matrix_pcg(A, s->R.p, s->dir.p, np->pcg_rel_tolerance, np->pcg_abs_tolerance, np->pcg_max_iterations, &lin_it, &lin_r);
         lin_total += lin_it;
         if (rc != TB2_OK) break;
+        {   // the reference's direct solve is exact; an iterative solve that ran out of iterations is reported (tb2_last_error)
+            int conv = 1;
+            double rel = 0.0;
+            tb2_matrix_pcg_converged(A, &conv, &rel);
+            if (!conv) {
+                lin_unconverged++;
+                if (rel > lin_worst) lin_worst = rel;
+            }
+        }
         if ((rc = newton_update(c, s->dir.p)) != TB2_OK) break;
         c.iteration++;
         if ((rc = form_rhs(c, false, h)) != TB2_OK) break;
         error = std::sqrt(h[0]);
         *status = exit_iteration(c.iteration);
-        if (solve_max_iterations >= 0 && num_iterations >= solve_max_iterations) break;
     }
     if (iterations) *iterations = c.iteration;
     if (error_out) *error_out = error;
     if (error0_out) *error0_out = error0;
     if (linear_iterations) *linear_iterations = lin_total;
+    if (rc == TB2_OK && lin_unconverged > 0)
+        set_error("Newton: %d of %d linear solves stopped at pcg_max_iterations = %d without meeting their tolerance (largest |r|/|r0| = %.3e); "
+                  "the updates of those iterations are inexact", lin_unconverged, num_iterations, np->pcg_max_iterations, lin_worst);
     if (rc != TB2_OK) *status = TB2_SOLVER_FAILED; // NLSolver::Solve: any exception -> kFailed (NLSolver.cpp:247-262)
     return rc;
 }

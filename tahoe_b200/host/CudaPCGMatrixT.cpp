@@ -135,5 +135,13 @@ void CudaPCGMatrixT::BackSubstitute(dArrayT& result)
 	int status = tb2_matrix_pcg_host(A, result.Pointer(), x.Pointer(), fRelTol, fAbsTol, fMaxIterations, &fLastIterations, &fLastResidual);
 	if (status != TB2_OK) ExceptionT::GeneralFail(caller, "%s", tb2_last_error());
 	fOut << " CudaPCGMatrixT: " << fLastIterations << " PCG iterations, |r| = " << fLastResidual << '\n';
+	/* an iterative solve that ran out of iterations is a failed solve: GlobalMatrixT::Solve catches the exception and returns
+	 * false (GlobalMatrixT.cpp:77-113), as it does for a zero pivot of a direct solver */
+	int converged = 1;
+	double rel = 0.0;
+	tb2_matrix_pcg_converged(A, &converged, &rel);
+	if (!converged)
+		ExceptionT::GeneralFail(caller, "no convergence in %d iterations: |r|/|r0| = %g (rel_tolerance %g, abs_tolerance %g)",
+			fLastIterations, rel, fRelTol, fAbsTol);
 	result = x;
 }

@@ -87,6 +87,48 @@ def test_node_records_in_any_order_and_comments(capi):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def test_element_records_in_any_order_go_to_their_numbered_row(capi):
+    """ModelFileT::GetElementSet -> nArray2DT::ReadNumbered (nArray2DT.h:1071) places a record "<number> n1..n8" at row number - 1;
+    side sets address elements by that number.  Shuffled element records (through the threaded path too: 30^3) must come back in
+    numbered order, so the side-set entries still point at the elements they were written for"""
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        for n in (3, 30):
+            X, conn, ns = ti.structured_cube(n, jitter=0.1)
+            path = os.path.join(work, "mesh%d.geom" % n)
+            ti.write_geom(path, X, conn, ns, sidesets=ti.cube_side_sets(n))
+            text = open(path).read()
+            head, rest = text.split("8  # number of element nodes\n")
+            body, tail = rest.split("# end elements")
+            lines = body.strip().splitlines()
+            rng = np.random.default_rng(n)
+            lines = [lines[k] for k in rng.permutation(len(lines))]
+            open(path, "w").write(head + "8  # number of element nodes\n" + "\n".join(lines) + "\n# end elements" + tail)
+            Xr, blocks, nsr, ssr = capi.read_geom(path)
+            assert np.array_equal(blocks[0], conn) and np.array_equal(Xr, X)
+            assert all(np.array_equal(ssr[k], ti.cube_side_sets(n)[k]) for k in ssr)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def test_repeated_and_out_of_range_record_numbers_are_rejected(capi):
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        X, conn, ns = ti.structured_cube(2, jitter=0.0)
+        path = os.path.join(work, "mesh.geom")
+        ti.write_geom(path, X, conn, ns)
+        text = open(path).read()
+        for bad in (text.replace("\n2 2 3 6 5 11 12 15 14\n", "\n1 2 3 6 5 11 12 15 14\n"),      # element number 1 twice
+                    text.replace("\n2 2 3 6 5 11 12 15 14\n", "\n9 2 3 6 5 11 12 15 14\n"),      # element number past nel
+                    text.replace("\n2 5.0", "\n1 5.0", 1)):                                       # node number 1 twice
+            assert bad != text
+            open(path, "w").write(bad)
+            with pytest.raises(capi.Tb2Error):
+                capi.read_geom(path)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def test_malformed_files_are_rejected(capi):
     work = tempfile.mkdtemp(prefix="tb2_geom_")
     try:

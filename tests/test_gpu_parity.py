@@ -608,9 +608,14 @@ def test_pcg_matches_oracle_and_reference(tb2, oracle):
     x_ref, it_ref, _ = oracle.pcg_jacobi(rowptr, colind, val, b, rtol=1e-14, max_iter=5000)
     assert 0 < it < 5000 and abs(it - it_ref) <= 2
     assert relerr(x, x_ref) < TOL
+    assert A.pcg_converged()[0]
     d = np.zeros_like(c.X)
     d[eqs.eqnos() > 0] = x
     assert relerr(d, c.ref("d_1")) < TOL
+    # a solve that runs out of iterations still returns TB2_OK (callers may ask for a fixed count) but says so when asked
+    x2, it2, rn2 = A.pcg_host(b, rtol=1e-14, max_iter=max(it // 4, 1))
+    conv, rel = A.pcg_converged()
+    assert it2 == max(it // 4, 1) and not conv and rel > 1e-14
 
 
 @pytest.mark.parametrize("name", PCG)
