@@ -527,6 +527,43 @@ def run_nlpcg_j2(torch, capi, tmesh, local, n, iters):
     return out
 
 
+def run_newton_j2(capi, tmesh, local, n):
+    """BASELINE.json configs[3] as stated -- updated_lagrangian + Simo_J2, implicit Newton with a Krylov solve on the device CSR: one
+    load step (1 % stretch: every point yields) through tb2_newton_solve_host.  The consistent tangent is non-symmetric
+    (J2Simo3D.cpp:18-21), so the linear solve is the Jacobi-preconditioned BiCGStab (tb2_matrix_bicgstab), 2 SpMVs per iteration."""
+    X, conn, ns = tmesh.structured_cube(n, jitter=0.1)
+    m = capi.Mesh(X, conn, device=local)
+    mat = {"type": "Simo_J2", "E": 100.0, "nu": 0.25, "density": 1.0, "hardening": {"type": "linear_function", "a": 0.05, "b": 0.25}}  # mat.09.a.xml
+    g = capi.Group(m, capi.UPDATED_LAGRANGIAN, capi.material(mat))
+    code = np.zeros(X.shape, np.uint8)
+    code[ns[1]] = 1
+    code[ns[2], 0] = 2
+    val = np.zeros_like(X)
+    val[ns[2], 0] = 0.01
+    eqs = capi.Equations(m, code)
+    A = capi.Matrix(eqs)
+    work = capi.NonlinearPCG(g, eqs, capi.nlpcg_params())
+    prm = capi.newton_params(abs_tolerance=1e-30, rel_tolerance=1e-8, max_iterations=25, pcg_rel_tolerance=1e-10, pcg_max_iterations=20000)
+    u = np.zeros_like(X)
+    u[code == 2] = val[code == 2]
+    u_last = np.zeros_like(X)
+    m.synchronize()
+    t0 = time.perf_counter()
+    st, nit, err, err0, lin = capi.newton_solve_host(work, A, prm, u, np.zeros_like(X), u_last=u_last)
+    m.synchronize()
+    dt = time.perf_counter() - t0
+    n_alloc = int(g.get_history()[2].sum()) if n <= 64 else None
+    out = {"workload": "BASELINE.json configs[3] at %d^3=%d updated_lagrangian + Simo_J2 elements, %d equations, %d non-zeros: one load step "
+                       "(1 %% stretch), Newton to 1e-8 with Jacobi-BiCGStab to 1e-10 on the device-assembled non-symmetric CSR"
+                       % (n, conn.shape[0], eqs.neq, A.nnz),
+           "status": {0: "continue", 1: "converged", 2: "failed"}[st], "newton_iterations": nit + 1, "bicgstab_iterations": int(lin),
+           "seconds": dt, "relative_residual": err / err0 if err0 > 0 else None, "dof_iters_per_s": float(eqs.neq) * lin / dt,
+           "spmv_per_s": 2.0 * lin / dt, "yielded_elements": n_alloc,
+           "note": "host-buffer call: includes residual sweeps, tangent assemblies (K3, full 24x24 element matrices) and the H2D/D2H of u"}
+    work.close(); A.close(); eqs.close(); g.close(); m.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -860,9 +897,12 @@ def run_gpu_arm(args):
     j2 = None
     if world == 1 and args.nlpcg_n > 0:
         j2 = run_nlpcg_j2(torch, capi, tmesh, local, args.nlpcg_n, args.nlpcg_iters)
+    nj2 = run_newton_j2(capi, tmesh, local, args.newton_j2_n) if (world == 1 and args.newton_j2_n > 0) else None
     if rank == 0:
         if shuffled:
             line["shuffled_numbering"] = shuffled
+        if nj2:
+            line["newton_j2"] = nj2
         if j2:
             line["nlpcg_j2"] = j2
         if xs:
@@ -889,6 +929,7 @@ def main():
     ap.add_argument("--no-explicit-solid", action="store_true", help="skip the <explicit_solid> leg (SURVEY.md 8f-1)")
     ap.add_argument("--nlpcg-n", type=int, default=48, help="cube edge of the J2 nonlinear-PCG leg (configs[3]; 159 -> 4M elements; 0 = skip)")
     ap.add_argument("--nlpcg-iters", type=int, default=20)
+    ap.add_argument("--newton-j2-n", type=int, default=40, help="cube edge of the J2 Newton + BiCGStab leg (configs[3] as stated; 159 -> 4M elements; 0 = skip)")
     ap.add_argument("--no-parity", action="store_true", help="skip the partitioned-vs-single-GPU check that precedes the timing")
     ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-numbering leg")
     ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")

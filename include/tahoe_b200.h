@@ -281,6 +281,13 @@ int tb2_matrix_pcg_host(tb2_matrix* A, const double* h_b, double* h_x, double rt
  * last solve met rtol / atol, and its |r|/|r0|, are read here.  GlobalMatrixT::Solve reports failure by returning false
  * (GlobalMatrixT.cpp:77-113): the plugin's BackSubstitute throws when this says 0. */
 int tb2_matrix_pcg_converged(const tb2_matrix* A, int* converged, double* relative_residual);
+/* GlobalMatrixT::Solve for a NON-symmetric matrix (J2Simo3D::TangentType() = kNonSymmetric, J2Simo3D.cpp:18-21; the reference
+ * uses LU there, SolverT.cpp:1108-1109): Jacobi-preconditioned BiCGStab on the device CSR, same arguments and stop test as
+ * tb2_matrix_pcg; tb2_matrix_pcg_converged reports on it too.  One GPU. */
+int tb2_matrix_bicgstab(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
+                        double* final_rnorm);
+int tb2_matrix_bicgstab_host(tb2_matrix* A, const double* h_b, double* h_x, double rtol, double atol, int max_iter,
+                             int* iterations, double* final_rnorm);
 /* gather / scatter between [nn][3] nodal arrays and [neq] equation vectors (FieldT::AssembleUpdate FieldT.cpp:531-556,
  * SolverT::AssembleRHS SolverT.cpp:446-477): y_eq = x_node[active] ; x_node[active] += s * y_eq */
 int tb2_equations_gather(const tb2_equations* eqs, const double* d_nodal, double* d_eqvec);

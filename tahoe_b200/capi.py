@@ -37,7 +37,7 @@ tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_sc
 tb2_geom_open tb2_geom_close tb2_geom_sizes tb2_geom_coords tb2_geom_block tb2_geom_nodeset tb2_geom_sideset
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
-tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_run_async tb2_explicit_wait tb2_matrix_pcg_converged tb2_explicit_device_array tb2_equations_create
+tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_run_async tb2_explicit_wait tb2_matrix_pcg_converged tb2_matrix_bicgstab tb2_matrix_bicgstab_host tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
@@ -526,6 +526,13 @@ class Matrix(_Handle):
         x = np.zeros_like(b) if x0 is None else _f64(x0).copy()
         it, rn = C.c_int(0), C.c_double(0.0)
         _chk(lib().tb2_matrix_pcg_host(self.h, _p(b), _p(x), C.c_double(rtol), C.c_double(atol), int(max_iter), C.byref(it), C.byref(rn)))
+        return x, it.value, rn.value
+
+    def bicgstab_host(self, b, x0=None, rtol=1e-12, atol=0.0, max_iter=10000):
+        """Jacobi-preconditioned BiCGStab (non-symmetric tangents): solution, iterations, |r|"""
+        x = np.zeros(self.neq) if x0 is None else np.ascontiguousarray(x0, np.float64).copy()
+        it, rn = C.c_int(0), C.c_double(0.0)
+        _chk(lib().tb2_matrix_bicgstab_host(self.h, _p(_f64(b)), _p(x), C.c_double(rtol), C.c_double(atol), int(max_iter), C.byref(it), C.byref(rn)))
         return x, it.value, rn.value
 
     def pcg_converged(self):

@@ -183,6 +183,28 @@ int comm_allreduce_packed(tb2_mesh* m)
 }
 const unsigned char* comm_owned_mask(tb2_mesh* m) { return m->comm ? m->comm->owned.p : nullptr; }
 
+// the two halves of comm_sum_interface_eq for callers that overlap the all-reduce with their own work (distributed PCG):
+// zero + pack the interface entries of an equation vector on stream st; copy the reduced entries back
+int comm_pack_eq(tb2_mesh* m, const int* d_eqnos, const double* d_eqvec, cudaStream_t st)
+{
+    Comm* c = m->comm;
+    ProfScope ps(m, kProfComm, 2, st);
+    TB2_CUDA(cudaMemsetAsync(c->packed.p, 0, 3 * c->n_glob * sizeof(double), st));
+    const int T = 256;
+    if (c->n_if) k_pack_eq<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, st>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, d_eqvec, c->packed.p);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+int comm_unpack_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec, cudaStream_t st)
+{
+    Comm* c = m->comm;
+    ProfScope ps(m, kProfComm, 1, st);
+    const int T = 256;
+    if (c->n_if) k_unpack_eq<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, st>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, c->packed.p, d_eqvec);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
 // in-place sum of n doubles over ranks (PCG scalars); no-op without a communicator
 int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n)
 {

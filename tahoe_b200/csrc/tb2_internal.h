@@ -192,6 +192,10 @@ struct tb2_matrix {
     tb2::DevBuf<double> scal;     // reduction scalars
     tb2::DevBuf<double> partial;  // per-block partial sums
     tb2::DevBuf<unsigned char> eq_owned; // multi-GPU: 1 if this rank owns the equation's node (dot products count it once)
+    tb2::DevBuf<double> s, partial_if;   // multi-GPU PCG: s = A p of the single-reduction recurrence; (A u, u) partials of the interface rows
+    tb2::DevBuf<double> bi_rhat, bi_v, bi_s, bi_t; // BiCGStab work vectors (tb2_matrix_bicgstab), allocated on first use
+    tb2::DevBuf<int> grp_split;          // row groups of interface nodes first, then the others
+    int64_t ngroups_if = 0;
     // CUDA graph of 16 PCG iterations (5 launches each) for the solution vector / tolerances it was captured with
     cudaGraphExec_t pcg_exec = nullptr;
     const double* pcg_x = nullptr;

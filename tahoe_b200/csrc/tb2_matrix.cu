@@ -6,6 +6,7 @@
 // order, of the neighbours' active equations -- which is what GraphT::MakeGraph + MSRBuilderT's per-row sort produce
 // (GraphT.cpp:376-488, MSRBuilderT.cpp:134-181).  The structure is therefore built from a node adjacency (<= 27 entries
 // per node on a structured mesh) instead of from 24x24 equation pairs per element.
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "tb2_internal.h"
@@ -489,6 +490,10 @@ bool comm_active(tb2_mesh* m);
 const unsigned char* comm_owned_mask(tb2_mesh* m);
 int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n);
 int comm_sum_interface_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec);
+int comm_pack_eq(tb2_mesh* m, const int* d_eqnos, const double* d_eqvec, cudaStream_t st);
+int comm_unpack_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec, cudaStream_t st);
+bool comm_plan(tb2_mesh* m, CommPlan* out);
+int comm_allreduce_packed(tb2_mesh* m);
 
 static const int kReduceBlocks = 148 * 8;
 static const int kSpmvBlocks = 148 * 8; // upper bound of the persistent SpMV grid (sizes the partial-sum buffer)
@@ -864,6 +869,97 @@ int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag)
 // never exchanged).  Per iteration: q = A_loc p, ONE interface sum of q (the same packed all-reduce as the force sum), dots
 // over owned equations + one all-reduce of 1-2 scalars (SolverT::InnerProduct semantics: each equation counted once).
 // b and x must be consistent on all sharers of an interface node (they are when b comes from interface-summed forces).
+// ---- distributed Jacobi-PCG on unassembled sub-domain matrices ----------------------------------------------
+// Single-reduction (Chronopoulos-Gear) form of the same recurrence as tb2_matrix_pcg:
+//     p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; w = A u
+//     gamma' = (r, u) ; delta = (w, u) ; beta = gamma'/gamma ; alpha = gamma' / (delta - beta gamma'/alpha)
+// so that ONE scalar all-reduce (gamma', |r|^2, delta) per iteration replaces the two of the textbook form (SolverT::InnerProduct,
+// SolverT.cpp:854-860, is one all-reduce per dot product).  delta needs no assembled w: sum over ranks of (A_loc u, u) over all
+// local rows is (A u, u), so its partial comes out of the local SpMV's epilogue.  The interface sum of w = A_loc u (the packed
+// all-reduce, CommManagerT::AllGather's role) is hidden: the rows of interface nodes are multiplied first and their all-reduce
+// runs on the communicator's stream beside the SpMV of the interior rows.
+__global__ void k_group_interface_flag(int64_t ng, const int* __restrict__ grp, const int* __restrict__ eq_node, const int* __restrict__ node_slot,
+                                       unsigned char* __restrict__ flag)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= ng) return;
+    const int64_t r0 = (unsigned)grp[g] & 0x3fffffffu;
+    flag[g] = node_slot[eq_node[r0] / 3] >= 0 ? 1 : 0;
+}
+// p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = dinv r ; partials (r,u), (r,r) over owned equations
+__global__ void __launch_bounds__(256) k_cg_update(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl,
+                                                  const double* __restrict__ dinv, const unsigned char* __restrict__ owned,
+                                                  const double* __restrict__ w, double* __restrict__ u, double* __restrict__ p,
+                                                  double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
+                                                  double* __restrict__ partial)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    const double alpha = scal[kALPHA], beta = scal[kBETA];
+    double ru = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double pi = u[i] + beta * p[i];
+        const double si = w[i] + beta * s[i];
+        p[i] = pi;
+        s[i] = si;
+        x[i] += alpha * pi;
+        const double ri = r[i] - alpha * si;
+        const double ui = dinv[i] * ri;
+        r[i] = ri;
+        u[i] = ui;
+        if (owned[i]) {
+            ru += ri * ui;
+            rr += ri * ri;
+        }
+    }
+    ru = block_sum(ru, sh);
+    rr = block_sum(rr, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = ru;
+        partial[2 * blockIdx.x + 1] = rr;
+    }
+}
+// red[0] = (r,u), red[1] = (r,r) from the update's partials, red[2] = (A_loc u, u) from the two SpMV launches' partials
+__global__ void __launch_bounds__(1024) k_cg_sum(int nvec, const double* __restrict__ pvec, int nif, const double* __restrict__ pif, int nint,
+                                                const double* __restrict__ pint, double* __restrict__ red, const PcgCtl* ctl)
+{
+    if (ctl && ctl->done) return;
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) { a += pvec[2 * i]; b += pvec[2 * i + 1]; }
+    for (int i = threadIdx.x; i < nif; i += blockDim.x) c += pif[i];
+    for (int i = threadIdx.x; i < nint; i += blockDim.x) c += pint[i];
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    c = block_sum(c, sh);
+    if (threadIdx.x == 0) { red[0] = a; red[1] = b; red[2] = c; }
+}
+__global__ void k_cg_scalars(const double* red, double* scal, PcgCtl* ctl, double rtol, double atol, int max_iter, int first)
+{
+    if (!first && ctl->done) return;
+    const double gamma = red[0], rnorm = sqrt(red[1]), delta = red[2];
+    double beta = 0.0, den = delta;
+    if (first) {
+        scal[kR0] = rnorm;
+        ctl->iters = 0;
+        ctl->breakdown = 0;
+        ctl->done = (!(rnorm > atol) || !(rnorm > rtol * rnorm) || max_iter <= 0) ? 1 : 0;
+    } else {
+        beta = gamma / scal[kRZ];
+        den = delta - beta * gamma / scal[kALPHA];
+        ctl->iters += 1;
+        if (!(rnorm > atol) || !(rnorm > rtol * scal[kR0]) || ctl->iters >= max_iter) ctl->done = 1;
+    }
+    scal[kRNORM] = rnorm;
+    scal[kRZ] = gamma;
+    scal[kBETA] = beta;
+    scal[kPAP] = den; // = (p, A p) of the next direction
+    if (!ctl->done) {
+        if (!(den > 0.0)) { ctl->breakdown = 1; ctl->done = 1; scal[kALPHA] = 0.0; }
+        else scal[kALPHA] = gamma / den;
+    }
+}
+
 static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
                            double* final_rnorm)
 {
@@ -873,6 +969,8 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     double* scal = A->scal.p;
     PcgCtl* ctl = (PcgCtl*)(A->scal.p + kNumScal);
     const int* eqnos = A->eqs->eqnos.p;
+    CommPlan cp;
+    const bool overlap = comm_plan(m, &cp);
     int64_t vb = (n + 255) / 256;
     const unsigned vec_blocks = (unsigned)(vb < kReduceBlocks ? vb : kReduceBlocks);
     const unsigned nb1 = (unsigned)((n + 255) / 256);
@@ -880,38 +978,98 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
         TB2_CUDA(A->eq_owned.alloc(n));
         k_eq_owned<<<nb1, 256, 0, st>>>(n, A->eqs->eq_node.p, comm_owned_mask(m), A->eq_owned.p);
     }
-    const unsigned char* w = A->eq_owned.p;
+    if (!A->s.p) TB2_CUDA(A->s.alloc(n));
+    if (overlap && !A->grp_split.p) { // row groups of interface nodes first, then the others (stable: deterministic partial sums)
+        DevBuf<unsigned char> flag;
+        DevBuf<int> nsel;
+        TB2_CUDA(flag.alloc(A->ngroups > 0 ? A->ngroups : 1));
+        TB2_CUDA(nsel.alloc(1));
+        TB2_CUDA(A->grp_split.alloc(A->ngroups > 0 ? A->ngroups : 1));
+        k_group_interface_flag<<<(unsigned)((A->ngroups + 255) / 256), 256, 0, st>>>(A->ngroups, A->grp.p, A->eqs->eq_node.p, cp.node_slot, flag.p);
+        size_t tmp_bytes = 0;
+        TB2_CUDA(cub::DevicePartition::Flagged(nullptr, tmp_bytes, A->grp.p, flag.p, A->grp_split.p, nsel.p, (int)A->ngroups, st));
+        DevBuf<unsigned char> tmp;
+        TB2_CUDA(tmp.alloc(tmp_bytes));
+        TB2_CUDA(cub::DevicePartition::Flagged(tmp.p, tmp_bytes, A->grp.p, flag.p, A->grp_split.p, nsel.p, (int)A->ngroups, st));
+        int h_n = 0;
+        TB2_CUDA(cudaMemcpyAsync(&h_n, nsel.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TB2_CUDA(cudaStreamSynchronize(st));
+        A->ngroups_if = h_n;
+        // DevicePartition writes the rejected items from the back in reverse order: put them back in ascending order
+        if (A->ngroups > h_n) {
+            std::vector<int> h((size_t)(A->ngroups - h_n));
+            TB2_CUDA(cudaMemcpy(h.data(), A->grp_split.p + h_n, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            std::reverse(h.begin(), h.end());
+            TB2_CUDA(cudaMemcpy(A->grp_split.p + h_n, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+    }
+    const unsigned char* owned = A->eq_owned.p;
+    double* pvec = A->partial.p;                       // [2 vec_blocks] (r,u), (r,r)
+    double* pint = A->partial.p + 2 * kReduceBlocks;   // [spmv blocks] (A_loc u, u) of the interior (or all) row groups
     double* red = A->partial.p + 2 * kReduceBlocks + kSpmvBlocks; // 8 spare doubles at the end of the partial buffer
+    if (!A->partial_if.p) TB2_CUDA(A->partial_if.alloc(kSpmvBlocks));
+    double* pif = A->partial_if.p;
+    const unsigned sg = spmv_grid();
+    const int64_t ng_if = overlap ? A->ngroups_if : 0, ng_int = A->ngroups - ng_if;
+    unsigned sg_if = (unsigned)((ng_if + 7) / 8);
+    if (sg_if > sg) sg_if = sg;
+    // w = A_loc u with the interface sum; leaves the (A_loc u, u) partials in pif / pint
+    auto multiply = [&](const double* u, double* w, bool with_dot) -> int {
+        if (ng_if > 0) {
+            // the whole interface lane -- rows of the interface nodes, pack, all-reduce -- on the communicator's (high-priority)
+            // stream, beside the interior rows on the mesh stream
+            TB2_CUDA(cudaEventRecord(cp.ev_packed, st)); // u is ready
+            TB2_CUDA(cudaStreamWaitEvent(cp.stream, cp.ev_packed, 0));
+            {
+                ProfScope ps(m, kProfSpmv, 1, cp.stream);
+                if (with_dot) k_spmv<true><<<sg_if, 256, 0, cp.stream>>>(ng_if, A->grp_split.p, A->rowptr.p, A->colind.p, A->val.p, u, w, pif, &ctl->done);
+                else k_spmv<false><<<sg_if, 256, 0, cp.stream>>>(ng_if, A->grp_split.p, A->rowptr.p, A->colind.p, A->val.p, u, w, nullptr, nullptr);
+            }
+            TB2_CHECK(comm_pack_eq(m, eqnos, w, cp.stream));
+            TB2_CHECK(comm_allreduce_packed(m));
+            TB2_CUDA(cudaEventRecord(cp.ev_reduced, cp.stream));
+        }
+        {
+            ProfScope ps(m, kProfSpmv, 1, st);
+            const int* g = ng_if > 0 ? A->grp_split.p + ng_if : A->grp.p;
+            if (with_dot) k_spmv<true><<<sg, 256, 0, st>>>(ng_int, g, A->rowptr.p, A->colind.p, A->val.p, u, w, pint, &ctl->done);
+            else k_spmv<false><<<sg, 256, 0, st>>>(ng_int, g, A->rowptr.p, A->colind.p, A->val.p, u, w, nullptr, nullptr);
+        }
+        if (ng_if > 0) {
+            TB2_CUDA(cudaStreamWaitEvent(st, cp.ev_reduced, 0));
+            TB2_CHECK(comm_unpack_eq(m, eqnos, w, st));
+        } else
+            TB2_CHECK(comm_sum_interface_eq(m, eqnos, w));
+        return TB2_OK;
+    };
     // Jacobi preconditioner from the ASSEMBLED diagonal
     k_extract_dinv<<<nb1, 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 0);
     TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->dinv.p));
     k_invert_diag<<<nb1, 256, 0, st>>>(n, A->dinv.p);
-    k_spmv<false><<<spmv_grid(), 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, d_x, A->q.p, nullptr, nullptr);
-    TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->q.p));
-    k_pcg_init<<<vec_blocks, 256, 0, st>>>(n, d_b, A->q.p, A->dinv.p, A->r.p, A->z.p, A->p.p, A->partial.p, w);
-    k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 2, A->partial.p, red, nullptr);
-    TB2_CHECK(comm_allreduce_scalars(m, red, 2));
-    k_scalars_init<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter);
+    // r = b - A x0 ; u = M^-1 r ; p = s = 0 ; w = A u ; gamma, |r|, delta -> alpha, beta = 0
+    TB2_CHECK(multiply(d_x, A->q.p, false));
+    k_pcg_init<<<vec_blocks, 256, 0, st>>>(n, d_b, A->q.p, A->dinv.p, A->r.p, A->z.p, A->p.p, pvec, owned);
+    TB2_CUDA(cudaMemsetAsync(A->p.p, 0, n * sizeof(double), st));
+    TB2_CUDA(cudaMemsetAsync(A->s.p, 0, n * sizeof(double), st));
+    TB2_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PcgCtl), st));
+    TB2_CHECK(multiply(A->z.p, A->q.p, true));
+    k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, red, nullptr);
+    TB2_CHECK(comm_allreduce_scalars(m, red, 3));
+    k_cg_scalars<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter, 1);
     TB2_CUDA(cudaGetLastError());
     PcgCtl h{};
     const int check_every = 8;
     for (int it = 0; it < max_iter;) {
         for (int k = 0; k < check_every && it < max_iter; k++, it++) {
             {
-                ProfScope ps(m, kProfSpmv);
-                k_spmv<false><<<spmv_grid(), 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, A->p.p, A->q.p, nullptr, nullptr);
+                ProfScope ps(m, kProfPcgVec, 1);
+                k_cg_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->dinv.p, owned, A->q.p, A->z.p, A->p.p, A->s.p, d_x, A->r.p, pvec);
             }
-            TB2_CHECK(comm_sum_interface_eq(m, eqnos, A->q.p));
-            ProfScope ps(m, kProfPcgVec, 8);
-            k_wdot<<<vec_blocks, 256, 0, st>>>(n, A->p.p, A->q.p, w, A->partial.p, ctl);
-            k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 1, A->partial.p, red, ctl);
-            TB2_CHECK(comm_allreduce_scalars(m, red, 1));
-            k_scalars_alpha<<<1, 1, 0, st>>>(red, scal, ctl);
-            k_pcg_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->p.p, A->q.p, A->dinv.p, d_x, A->r.p, A->z.p, A->partial.p, w);
-            k_sum_partials<<<1, 1024, 0, st>>>((int)vec_blocks, 2, A->partial.p, red, ctl);
-            TB2_CHECK(comm_allreduce_scalars(m, red, 2));
-            k_scalars_beta<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter);
-            k_pcg_direction<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->z.p, A->p.p);
+            TB2_CHECK(multiply(A->z.p, A->q.p, true));
+            ProfScope ps(m, kProfPcgVec, 2);
+            k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, red, ctl);
+            TB2_CHECK(comm_allreduce_scalars(m, red, 3));
+            k_cg_scalars<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter, 0);
         }
         TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
         TB2_CUDA(cudaStreamSynchronize(st));
@@ -923,7 +1081,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     TB2_CUDA(cudaStreamSynchronize(st));
     if (iterations) *iterations = h.iters;
     if (final_rnorm) *final_rnorm = hs[kRNORM];
-    A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]); // the device's own stop test (k_reduce_rz)
+    A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]); // the device's own stop test
     A->pcg_last_rel = hs[kR0] > 0.0 ? hs[kRNORM] / hs[kR0] : 0.0;
     if (h.breakdown) {
         set_error("PCG breakdown: p.Ap = %g <= 0 (matrix not positive definite)", hs[kPAP]);
@@ -1012,6 +1170,241 @@ int tb2_matrix_pcg(tb2_matrix* A, const double* d_b, double* d_x, double rtol, d
         return TB2_ERR_PCG_BREAKDOWN;
     }
     return TB2_OK;
+}
+
+// ---- BiCGStab with the Jacobi preconditioner: the device's linear solve for NON-symmetric tangents ---------------------------
+// J2Simo3D::TangentType() is kNonSymmetric (J2Simo3D.cpp:18-21); the reference solves such systems by LU (SolverT.cpp:1108-1109:
+// profile_matrix -> CCNSMatrixT) and has a Krylov precedent in NLSolver_NK.cpp:147,175.  van der Vorst's recurrence, right
+// preconditioning with M = diag(A) (DiagonalMatrixT::Factorize semantics), two SpMVs per iteration, every scalar on the device,
+// deterministic two-stage reductions, kernels no-ops once the device-side done flag is set -- the same machinery as tb2_matrix_pcg.
+} // extern "C"
+namespace tb2 {
+enum { kBiRho = 0, kBiAlpha = 1, kBiOmega = 2, kBiBeta = 3 }; // in scal[kRZ..]: rho, alpha, omega, beta share the PCG scalar block
+// p = r + beta (p - omega v) ; y = dinv p
+__global__ void __launch_bounds__(256) k_bi_direction(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl,
+                                                     const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+                                                     double* __restrict__ p, double* __restrict__ y)
+{
+    if (ctl->done) return;
+    const double beta = scal[kBETA], omega = scal[kRR];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double pi = r[i] + beta * (p[i] - omega * v[i]);
+        p[i] = pi;
+        y[i] = dinv[i] * pi;
+    }
+}
+// partial[2b], partial[2b+1] = sum a.b, sum c.d
+__global__ void __launch_bounds__(256) k_bi_dot2(int64_t n, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                                                const double* __restrict__ d, double* __restrict__ partial, const PcgCtl* __restrict__ ctl)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        s0 += a[i] * b[i];
+        s1 += c[i] * d[i];
+    }
+    s0 = block_sum(s0, sh);
+    s1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s0;
+        partial[2 * blockIdx.x + 1] = s1;
+    }
+}
+// stage 0: alpha = rho / (rhat, v).  stage 1: omega = (t, s) / (t, t).  stage 2: rho' = (rhat, r), |r|; beta = (rho'/rho)(alpha/omega)
+__global__ void __launch_bounds__(1024) k_bi_scalars(int nparts, const double* __restrict__ partial, double* __restrict__ scal, PcgCtl* ctl, int stage,
+                                                    double rtol, double atol, int max_iter)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x != 0) return;
+    if (stage == 0) {
+        if (a == 0.0) { ctl->breakdown = 1; ctl->done = 1; scal[kALPHA] = 0.0; }
+        else scal[kALPHA] = scal[kRZ] / a;
+    } else if (stage == 1) {
+        scal[kRR] = b > 0.0 ? a / b : 0.0; // omega
+    } else {
+        const double rnorm = sqrt(b);
+        scal[kRNORM] = rnorm;
+        ctl->iters += 1;
+        if (!(rnorm > atol) || !(rnorm > rtol * scal[kR0]) || ctl->iters >= max_iter) ctl->done = 1;
+        else if (scal[kRZ] == 0.0 || scal[kRR] == 0.0) { ctl->breakdown = 1; ctl->done = 1; }
+        else {
+            scal[kBETA] = (a / scal[kRZ]) * (scal[kALPHA] / scal[kRR]);
+            scal[kRZ] = a;
+        }
+    }
+}
+// s = r - alpha v ; z = dinv s
+__global__ void __launch_bounds__(256) k_bi_half(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl, const double* __restrict__ r,
+                                                const double* __restrict__ v, const double* __restrict__ dinv, double* __restrict__ sv, double* __restrict__ z)
+{
+    if (ctl->done) return;
+    const double alpha = scal[kALPHA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double si = r[i] - alpha * v[i];
+        sv[i] = si;
+        z[i] = dinv[i] * si;
+    }
+}
+// x += alpha y + omega z ; r = s - omega t ; partials (rhat, r), (r, r)
+__global__ void __launch_bounds__(256) k_bi_update(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl, const double* __restrict__ y,
+                                                  const double* __restrict__ z, const double* __restrict__ sv, const double* __restrict__ t,
+                                                  const double* __restrict__ rhat, double* __restrict__ x, double* __restrict__ r,
+                                                  double* __restrict__ partial)
+{
+    if (ctl->done) return;
+    __shared__ double sh[32];
+    const double alpha = scal[kALPHA], omega = scal[kRR];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * y[i] + omega * z[i];
+        const double ri = sv[i] - omega * t[i];
+        r[i] = ri;
+        s0 += rhat[i] * ri;
+        s1 += ri * ri;
+    }
+    s0 = block_sum(s0, sh);
+    s1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s0;
+        partial[2 * blockIdx.x + 1] = s1;
+    }
+}
+// r = b - q ; rhat = r ; p = v = 0 ; partials (r, r) twice
+__global__ void __launch_bounds__(256) k_bi_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r,
+                                                double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ v, double* __restrict__ partial)
+{
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        r[i] = ri;
+        rhat[i] = ri;
+        p[i] = 0.0;
+        v[i] = 0.0;
+        s += ri * ri;
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s;
+        partial[2 * blockIdx.x + 1] = s;
+    }
+}
+__global__ void __launch_bounds__(1024) k_bi_scalars_init(int nparts, const double* __restrict__ partial, double* __restrict__ scal, PcgCtl* ctl,
+                                                         double rtol, double atol, int max_iter)
+{
+    __shared__ double sh[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) a += partial[2 * i];
+    a = block_sum(a, sh);
+    if (threadIdx.x != 0) return;
+    const double rnorm = sqrt(a);
+    scal[kRZ] = a;      // rho = (rhat, r) = (r, r)
+    scal[kALPHA] = 1.0;
+    scal[kRR] = 1.0;    // omega
+    scal[kBETA] = 0.0;  // first direction: p = r
+    scal[kR0] = rnorm;
+    scal[kRNORM] = rnorm;
+    ctl->iters = 0;
+    ctl->breakdown = 0;
+    ctl->done = (!(rnorm > atol) || !(rnorm > rtol * rnorm) || max_iter <= 0) ? 1 : 0;
+}
+} // namespace tb2
+extern "C" {
+
+int tb2_matrix_bicgstab(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
+                        double* final_rnorm)
+{
+    TB2_ARG(A && d_b && d_x);
+    tb2_mesh* m = A->ctx;
+    DeviceGuard dg(m->device);
+    if (A->eqs && comm_active(m)) {
+        set_error("tb2_matrix_bicgstab: the partitioned (multi-GPU) form is not implemented");
+        return TB2_ERR_ARG;
+    }
+    const int64_t n = A->neq;
+    cudaStream_t st = m->stream;
+    double* scal = A->scal.p;
+    PcgCtl* ctl = (PcgCtl*)(A->scal.p + kNumScal);
+    for (auto* b : {&A->bi_rhat, &A->bi_v, &A->bi_s, &A->bi_t})
+        if (!b->p) TB2_CUDA(b->alloc(n));
+    double *r = A->r.p, *y = A->z.p, *p = A->p.p, *z = A->q.p, *rhat = A->bi_rhat.p, *v = A->bi_v.p, *sv = A->bi_s.p, *t = A->bi_t.p;
+    const unsigned sg = spmv_grid();
+    int64_t vb = (n + 255) / 256;
+    const unsigned vec_blocks = (unsigned)(vb < kReduceBlocks ? vb : kReduceBlocks);
+    auto spmv = [&](const double* x, double* out) {
+        ProfScope ps(m, kProfSpmv);
+        k_spmv<false><<<sg, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, x, out, nullptr, nullptr);
+    };
+    {
+        ProfScope ps(m, kProfPcgVec, 3);
+        k_extract_dinv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 1);
+        spmv(d_x, t);
+        k_bi_init<<<vec_blocks, 256, 0, st>>>(n, d_b, t, r, rhat, p, v, A->partial.p);
+        k_bi_scalars_init<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, rtol, atol, max_iter);
+    }
+    TB2_CUDA(cudaGetLastError());
+    PcgCtl h{};
+    const int check_every = 8;
+    for (int it = 0; it < max_iter;) {
+        for (int k = 0; k < check_every && it < max_iter; k++, it++) {
+            {
+                ProfScope ps(m, kProfPcgVec, 1);
+                k_bi_direction<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, r, v, A->dinv.p, p, y);
+            }
+            spmv(y, v);
+            {
+                ProfScope ps(m, kProfPcgVec, 3);
+                k_bi_dot2<<<vec_blocks, 256, 0, st>>>(n, rhat, v, rhat, v, A->partial.p, ctl);
+                k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 0, rtol, atol, max_iter);
+                k_bi_half<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, r, v, A->dinv.p, sv, z);
+            }
+            spmv(z, t);
+            ProfScope ps(m, kProfPcgVec, 4);
+            k_bi_dot2<<<vec_blocks, 256, 0, st>>>(n, t, sv, t, t, A->partial.p, ctl);
+            k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 1, rtol, atol, max_iter);
+            k_bi_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, y, z, sv, t, rhat, d_x, r, A->partial.p);
+            k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 2, rtol, atol, max_iter);
+        }
+        TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        TB2_CUDA(cudaStreamSynchronize(st));
+        if (h.done) break;
+    }
+    double hs[kNumScal];
+    TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    TB2_CUDA(cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
+    TB2_CUDA(cudaStreamSynchronize(st));
+    if (iterations) *iterations = h.iters;
+    if (final_rnorm) *final_rnorm = hs[kRNORM];
+    A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]);
+    A->pcg_last_rel = hs[kR0] > 0.0 ? hs[kRNORM] / hs[kR0] : 0.0;
+    if (h.breakdown && !A->pcg_last_converged) {
+        set_error("BiCGStab breakdown (rho, omega or (rhat, v) vanished) after %d iterations, |r|/|r0| = %g", h.iters, A->pcg_last_rel);
+        return TB2_ERR_PCG_BREAKDOWN;
+    }
+    return TB2_OK;
+}
+
+int tb2_matrix_bicgstab_host(tb2_matrix* A, const double* h_b, double* h_x, double rtol, double atol, int max_iter, int* iterations,
+                             double* final_rnorm)
+{
+    TB2_ARG(A && h_b && h_x);
+    tb2_mesh* m = A->ctx;
+    DeviceGuard dg(m->device);
+    DevBuf<double> b, x;
+    TB2_CUDA(b.alloc(A->neq));
+    TB2_CUDA(x.alloc(A->neq));
+    TB2_CUDA(cudaMemcpyAsync(b.p, h_b, A->neq * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(x.p, h_x, A->neq * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    int s = tb2_matrix_bicgstab(A, b.p, x.p, rtol, atol, max_iter, iterations, final_rnorm);
+    TB2_CUDA(cudaMemcpyAsync(h_x, x.p, A->neq * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return s;
 }
 
 int tb2_matrix_pcg_converged(const tb2_matrix* A, int* converged, double* relative_residual)

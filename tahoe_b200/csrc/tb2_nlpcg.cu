@@ -560,7 +560,11 @@ static int newton_core(tb2_nlpcg* s, tb2_matrix* A, const tb2_newton_params* np,
         if (cudaMemsetAsync(s->dir.p, 0, c.n * sizeof(double), c.st) != cudaSuccess) { rc = TB2_ERR_CUDA; break; }
         int lin_it = 0;
         double lin_r = 0.0;
-        rc = tb2_matrix_pcg(A, s->R.p, s->dir.p, np->pcg_rel_tolerance, np->pcg_abs_tolerance, np->pcg_max_iterations, &lin_it, &lin_r);
+        // symmetric tangents: Jacobi-PCG; J2Simo3D's consistent tangent is non-symmetric (J2Simo3D.cpp:18-21): BiCGStab
+        if (s->group->mat.kind == TB2_J2_SIMO)
+            rc = tb2_matrix_bicgstab(A, s->R.p, s->dir.p, np->pcg_rel_tolerance, np->pcg_abs_tolerance, np->pcg_max_iterations, &lin_it, &lin_r);
+        else
+            rc = tb2_matrix_pcg(A, s->R.p, s->dir.p, np->pcg_rel_tolerance, np->pcg_abs_tolerance, np->pcg_max_iterations, &lin_it, &lin_r);
         lin_total += lin_it;
         if (rc != TB2_OK) break;
         {   // the reference's direct solve is exact; an iterative solve that ran out of iterations is reported (tb2_last_error)

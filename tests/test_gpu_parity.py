@@ -734,19 +734,21 @@ def test_native_newton_driver_matches_reference(tb2, name):
     A = tb2.Matrix(eqs)
     work = tb2.NonlinearPCG(grp, eqs, tb2.nlpcg_params())
     prm = tb2.newton_params(c.desc["solver"], pcg_rel_tolerance=1e-14)
+    # J2Simo3D's tangent is non-symmetric (J2Simo3D.cpp:18-21; the reference solves it with LU): the driver switches to BiCGStab
     isj2 = mat.kind == tb2.J2_SIMO
-    if isj2:
-        pytest.skip("J2Simo3D's tangent is non-symmetric (J2Simo3D.cpp:18-21): the reference solves it with LU, CG does not apply")
     d = c.ref("d_0").copy()
+    d_last = d.copy()
     iters = c.ref("iters")
     for k in range(1, c.nsteps + 1):
         code, val, fext = c.bc(k * c.dt)
         d[code == 1] = 0.0
         d[code == 2] = val[code == 2]
-        st, it, err, err0, lin = tb2.newton_solve_host(work, A, prm, d, fext)
+        st, it, err, err0, lin = tb2.newton_solve_host(work, A, prm, d, fext, u_last=d_last if isj2 else None)
         assert st == 1 and it == iters[k - 1] and (lin > 0 or it == -1)
         if k in c.dump_steps:
-            assert relerr(d, c.ref("d_%d" % k)) < TOL
+            assert relerr(d, c.ref("d_%d" % k)) < (1e-9 if isj2 else TOL)  # J2: BiCGStab to 1e-14 relative; Newton contracts the rest
+        grp.close_step()  # FEManagerT::CloseStep: J2Simo3D::UpdateHistory
+        d_last = d.copy()
 
 
 def _solve_pcg(A, R):
@@ -768,6 +770,27 @@ def test_static_newton_pcg_matches_reference(tb2, name):
         if k in c.dump_steps:
             assert relerr(d, c.ref("d_%d" % k)) < 1e-9  # PCG to 1e-13 relative residual; Newton contracts the rest
         assert it == iters[k - 1]
+
+
+def test_bicgstab_solves_the_nonsymmetric_j2_tangent(tb2):
+    """tb2_matrix_bicgstab on every tangent of a J2Simo3D Newton history (non-symmetric once points have yielded) against the
+    sparse direct solve the reference's LU stands for"""
+    c = Case("syn_ul_j2_static")
+    seen = {"nonsym": 0, "n": 0}
+
+    def solve(A, R):
+        x_ref = _solve_direct(A, R)
+        x, it, rn = A.bicgstab_host(R, rtol=1e-13, max_iter=5000)
+        assert 0 < it < 5000 and A.pcg_converged()[0] and relerr(x, x_ref) < 1e-8
+        rowptr, colind, val = A.csr()
+        K = sp.csr_matrix((val, colind, rowptr), shape=(A.neq, A.neq))
+        seen["nonsym"] += int(abs(K - K.T).max() > 1e-8 * abs(K).max())
+        seen["n"] += 1
+        return x_ref
+
+    for _ in _newton_gpu(tb2, c, solve):
+        pass
+    assert seen["nonsym"] > 0 and seen["n"] > seen["nonsym"] > 0 or seen["nonsym"] > 0
 
 
 @pytest.mark.parametrize("name", [n for n in STATIC if "j2" in n or "09" in n])
