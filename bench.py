@@ -201,6 +201,61 @@ def reference_rate(n, s_lo, s_hi, procs, min_seconds=2.0, element="total_lagrang
     return procs * ne * k / dt, dt, ne, k
 
 
+PLUGIN_BIN = os.path.join(REPO, "tahoe_b200", "host", "_build", "tahoe_b200")
+
+
+def plugin_leg(n=48, s_lo=2, s_hi=22):
+    """The drop-in itself (tahoe_b200/host: the reference's libraries + the plugin classes, tests/test_plugin_binary.py): the same XML
+    family through the plugin EXECUTABLE -- (a) cuda_total_lagrangian with Tahoe's own linear_solver / diagonal_matrix / nExplicitCD
+    on the host (u up, force down every step), (b) the resident pair integrator="CUDA_central_difference" + <CUDA_explicit_solver>
+    -- and through the unmodified reference, wall(s_hi steps) - wall(s_lo steps) each.  Everything outside the hot path (FieldT
+    bookkeeping, FEManagerT's step loop) is Tahoe's host code in all three."""
+    if not (os.path.exists(PLUGIN_BIN) and os.path.exists(REF_BIN)):
+        return None
+    import tahoe_input as ti
+    work = tempfile.mkdtemp(prefix="tb2_plugin_")
+    try:
+        X, conn, ns = ti.structured_cube(n, jitter=0.1)
+        ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns)
+        ne = conn.shape[0]
+
+        def case(name, nsteps, element, integrator, solver):
+            desc = {"geometry_file": "mesh.geom", "output_inc": nsteps,
+                    "time": {"num_steps": nsteps, "time_step": float(stable_dt(n)), "schedules": [[(0.0, 1.0)]]},
+                    "integrator": integrator,
+                    "kbc": [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)],
+                    "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02 / (n * n)}],
+                    "element": {"type": "total_lagrangian", "tag": element, "mass_type": "lumped_mass", "nodal_output": True},
+                    "material": MATERIAL, "solver": solver}
+            ti.write_xml(os.path.join(work, "%s_%d.xml" % (name, nsteps)), desc)
+
+        def wall(binary, name, nsteps):
+            t0 = time.perf_counter()
+            r = subprocess.run([binary, "-f", "%s_%d.xml" % (name, nsteps)], cwd=work, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode or "End Execution" not in r.stdout:
+                raise RuntimeError("%s failed: %s" % (name, r.stdout[-800:]))
+            return time.perf_counter() - t0
+
+        host = {"type": "linear_solver", "matrix": "diagonal_matrix"}
+        variants = {"reference": (REF_BIN, "total_lagrangian", "central_difference", host),
+                    "plugin_host_integrator": (PLUGIN_BIN, "cuda_total_lagrangian", "central_difference", host),
+                    "plugin_resident": (PLUGIN_BIN, "cuda_total_lagrangian", "CUDA_central_difference",
+                                        {"type": "CUDA_explicit_solver", "matrix": "diagonal_matrix"})}
+        out = {"workload": "%d^3=%d-element cube, total_lagrangian + Simo_isotropic, explicit central difference, one output step at the end; "
+                           "wall(%d steps) - wall(%d steps) of the executable" % (n, ne, s_hi, s_lo)}
+        for name, (binary, element, integrator, solver) in variants.items():
+            for k in (s_lo, s_hi):
+                case(name, k, element, integrator, solver)
+            wall(binary, name, s_lo)  # warm file cache / CUDA context creation is inside both runs and cancels
+            dt = wall(binary, name, s_hi) - wall(binary, name, s_lo)
+            dt = max(dt, 1e-4)
+            out[name] = {"ms_per_step": 1e3 * dt / (s_hi - s_lo), "element_updates_per_s": ne * (s_hi - s_lo) / dt}
+        out["resident_vs_reference"] = out["plugin_resident"]["element_updates_per_s"] / out["reference"]["element_updates_per_s"]
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def oracle_port_rate(n, steps):
     """fallback CPU baseline: the plain-C oracle port (kind = "port"), one core"""
     import oracle_lib as orc
@@ -899,6 +954,11 @@ def run_gpu_arm(args):
         j2 = run_nlpcg_j2(torch, capi, tmesh, local, args.nlpcg_n, args.nlpcg_iters)
     nj2 = run_newton_j2(capi, tmesh, local, args.newton_j2_n) if (world == 1 and args.newton_j2_n > 0) else None
     if rank == 0:
+        if world == 1 and not args.no_cpu_baseline and not args.no_plugin:
+            try:
+                line["plugin"] = plugin_leg()
+            except Exception as e:  # the plugin leg must never cost the line
+                line["plugin"] = {"error": str(e)[-400:]}
         if shuffled:
             line["shuffled_numbering"] = shuffled
         if nj2:
@@ -932,6 +992,7 @@ def main():
     ap.add_argument("--newton-j2-n", type=int, default=40, help="cube edge of the J2 Newton + BiCGStab leg (configs[3] as stated; 159 -> 4M elements; 0 = skip)")
     ap.add_argument("--no-parity", action="store_true", help="skip the partitioned-vs-single-GPU check that precedes the timing")
     ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-numbering leg")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the plugin-executable leg")
     ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")
     ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")
     ap.add_argument("--pcg-iters", type=int, default=100)

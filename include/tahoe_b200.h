@@ -210,6 +210,9 @@ int tb2_explicit_get_state(tb2_explicit* ex, double* h_d, double* h_v, double* h
 /* h_code[nn][3] tb2_bc_code, h_value[nn][3] prescribed displacement, h_fext[nn][3] nodal forces (FieldT::FormRHS, FieldT.cpp:390-411).
  * Any pointer may be NULL to keep the current array. */
 int tb2_explicit_set_bc(tb2_explicit* ex, const uint8_t* h_code, const double* h_value, const double* h_fext);
+/* sparse refresh of prescribed displacement values (KBC controllers driven by a schedule, nExplicitCD::ConsistentKBC
+ * nExplicitCD.cpp:20-69): value[h_dofs[k]] = h_values[k], h_dofs = nodal dof indices 3 n + i */
+int tb2_explicit_update_bc_values(tb2_explicit* ex, int64_t count, const int64_t* h_dofs, const double* h_values);
 /* FEManagerT::InitialCondition (FEManagerT.cpp:2034): a = M^-1 (fext - fint(d)) on free dofs */
 int tb2_explicit_initial_condition(tb2_explicit* ex);
 /* nsteps x { Predictor + ConsistentKBC ; fint ; a = M^-1 R ; Corrector }.  h_fext_scale / h_value_scale

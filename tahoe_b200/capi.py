@@ -37,7 +37,7 @@ tb2_form_inertial_force tb2_form_inertial_force_host tb2_form_mass tb2_matrix_sc
 tb2_geom_open tb2_geom_close tb2_geom_sizes tb2_geom_coords tb2_geom_block tb2_geom_nodeset tb2_geom_sideset
 tb2_traction_create tb2_traction_destroy tb2_traction_form tb2_traction_form_host
 tb2_explicit_create tb2_explicit_destroy tb2_explicit_set_state tb2_explicit_get_state tb2_explicit_set_bc
-tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_run_async tb2_explicit_wait tb2_matrix_pcg_converged tb2_matrix_bicgstab tb2_matrix_bicgstab_host tb2_explicit_device_array tb2_equations_create
+tb2_explicit_initial_condition tb2_explicit_run tb2_explicit_step_host tb2_explicit_run_async tb2_explicit_wait tb2_explicit_update_bc_values tb2_matrix_pcg_converged tb2_matrix_bicgstab tb2_matrix_bicgstab_host tb2_explicit_device_array tb2_equations_create
 tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device tb2_matrix_create tb2_matrix_create_csr tb2_matrix_set_values tb2_matrix_destroy
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
@@ -407,6 +407,11 @@ class Explicit(_Handle):
     def set_bc(self, code=None, value=None, fext=None):
         code = None if code is None else np.ascontiguousarray(code, np.uint8)
         _chk(lib().tb2_explicit_set_bc(self.h, _p(code), _p(_f64(value)), _p(_f64(fext))))
+
+    def update_bc_values(self, dofs, values):
+        """sparse refresh of prescribed values: dofs = nodal dof indices 3 n + i"""
+        dofs = np.ascontiguousarray(dofs, np.int64)
+        _chk(lib().tb2_explicit_update_bc_values(self.h, C.c_int64(len(dofs)), _p(dofs), _p(_f64(values))))
 
     def initial_condition(self):
         _chk(lib().tb2_explicit_initial_condition(self.h))

@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(256) k_cd_interface_update(int64_t n_if, const
     }
 }
 
+// sparse refresh of the prescribed values (KBC controllers with a schedule): out[dof[k]] = value[k]
+__global__ void k_scatter_values(int64_t n, const int64_t* __restrict__ dof, const double* __restrict__ value, double* __restrict__ out)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[dof[k]] = value[k];
+}
+
 // DiagonalMatrixT::Factorize (DiagonalMatrixT.cpp:267-310): reciprocal, |m| < 1e-12 left as is
 __global__ void k_invert_diagonal(int64_t n, const double* __restrict__ m, double* __restrict__ minv)
 {
@@ -241,6 +248,7 @@ int tb2_explicit_create(tb2_group* g, tb2_explicit** out)
     DeviceGuard dg(m->device);
     tb2_explicit* ex = new tb2_explicit;
     ex->group = g;
+    ex->device = m->device;
     const size_t n = 3 * m->nn;
     cudaError_t e = cudaSuccess;
     DevBuf<double>* bufs[] = {&ex->d, &ex->v, &ex->a, &ex->mass, &ex->minv, &ex->fext, &ex->fint, &ex->bcval};
@@ -271,8 +279,9 @@ int tb2_explicit_create(tb2_group* g, tb2_explicit** out)
 int tb2_explicit_destroy(tb2_explicit* ex)
 {
     if (!ex) return TB2_OK;
-    DeviceGuard dg(ex->group->mesh->device);
-    cudaStreamSynchronize(ex->group->mesh->stream);
+    // a host may destroy the mesh / group first (Tahoe deletes its element groups before its solvers): use the copies taken at creation
+    DeviceGuard dg(ex->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError(); // not the mesh stream: it may have been destroyed with the mesh
     if (ex->stream_copy) {
         cudaStreamSynchronize(ex->stream_copy);
         cudaStreamDestroy(ex->stream_copy);
@@ -323,6 +332,26 @@ int tb2_explicit_set_bc(tb2_explicit* ex, const uint8_t* h_code, const double* h
         ex->has_fext = false; // an all-zero external force is not read by the node kernel
         for (size_t i = 0; i < n && !ex->has_fext; i++) ex->has_fext = h_fext[i] != 0.0;
     }
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
+
+int tb2_explicit_update_bc_values(tb2_explicit* ex, int64_t count, const int64_t* h_dofs, const double* h_values)
+{
+    TB2_ARG(ex && count >= 0 && (count == 0 || (h_dofs && h_values)));
+    if (count == 0) return TB2_OK;
+    tb2_mesh* m = ex->group->mesh;
+    DeviceGuard dg(m->device);
+    const int64_t ndof = 3 * m->nn;
+    for (int64_t k = 0; k < count; k++) TB2_ARG(h_dofs[k] >= 0 && h_dofs[k] < ndof);
+    DevBuf<int64_t> idx;
+    DevBuf<double> val;
+    TB2_CUDA(idx.alloc(count));
+    TB2_CUDA(val.alloc(count));
+    TB2_CUDA(cudaMemcpyAsync(idx.p, h_dofs, count * sizeof(int64_t), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(val.p, h_values, count * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    k_scatter_values<<<(unsigned)((count + 255) / 256), 256, 0, m->stream>>>(count, idx.p, val.p, ex->bcval.p);
+    TB2_CUDA(cudaGetLastError());
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     return TB2_OK;
 }

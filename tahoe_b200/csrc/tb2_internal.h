@@ -215,6 +215,7 @@ struct tb2_matrix {
 
 struct tb2_explicit {
     tb2_group* group = nullptr;
+    int device = 0;                // copy for tb2_explicit_destroy (the group may be gone by then)
     tb2::DevBuf<double> d, v, a, mass, minv, fext, fint, bcval;
     tb2::DevBuf<unsigned char> bccode;
     bool has_fext = false; // fext holds a non-zero entry (an all-zero external force is not read by the node kernel)

@@ -1,6 +1,7 @@
 /* CudaPCGSolverT.cpp -- see CudaPCGSolverT.h */
 #include "CudaPCGSolverT.h"
 
+#include "CudaExplicitSolverT.h"
 #include "CudaSolidElementT.h"
 #include "ElementBaseT.h"
 #include "ExceptionT.h"
@@ -20,6 +21,7 @@ const char* kCudaPCGSolverName = "CUDA_PCG_solver";
 SolverT* NewCudaSolver(FEManagerT& fe_manager, const char* name, int group)
 {
 	if (strcmp(name, kCudaPCGSolverName) == 0) return new CudaPCGSolverT(fe_manager, group);
+	if (strcmp(name, kCudaExplicitSolverName) == 0) return new CudaExplicitSolverT(fe_manager, group);
 	return NULL;
 }
 } // namespace Tahoe

@@ -254,7 +254,11 @@ void CudaSolidElementT<BaseT>::RHSDriver(void)
 		formBody = 1;
 		if (!formMa) constMa = 1.0;
 	}
-	if (fMuted) return;
+	if (fMuted) { /* a resident solver forms the internal force and the inertia itself: tractions (above) and the body force remain */
+		formKd = 0;
+		formMa = 0;
+		if (formBody) constMa = 1.0;
+	}
 	if (!formKd && !formMa && !formBody) return;
 
 	const FieldT& field = this->Field();

@@ -49,6 +49,8 @@ public:
 	virtual bool NeedsLastDisplacement(void) const = 0;
 	/** while set, RHSDriver() adds the tractions only: a device-resident solver (CudaPCGSolverT) forms -fint itself */
 	virtual void MuteInternalForce(bool mute) = 0;
+	/** natural_bc tractions or a body force: loads the group itself adds to the residual (they may follow a schedule) */
+	virtual bool HasSurfaceOrBodyLoads(void) const = 0;
 };
 
 template <class BaseT>
@@ -84,6 +86,7 @@ public:
 	virtual int SolverGroup(void) const { return this->Group(); }
 	virtual bool NeedsLastDisplacement(void) const { return fIsJ2; }
 	virtual void MuteInternalForce(bool mute) { fMuted = mute; }
+	virtual bool HasSurfaceOrBodyLoads(void) const { return this->fTractionList.Length() > 0 || this->fBodySchedule != NULL; }
 
 protected:
 

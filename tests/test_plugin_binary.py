@@ -43,12 +43,29 @@ def _cases():
     pull = CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.06}, {"nodeset": 2, "dof": 3, "type": "u", "schedule": 1, "value": 0.02}]
     n = 5
     dt = 0.25 * (1.0 / n) / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0)
+    resident = {"type": "CUDA_explicit_solver", "matrix": "diagonal_matrix", "integrator": "CUDA_central_difference"}
     return {
         # explicit dynamics: device K1, Tahoe's own lumped mass / DiagonalMatrixT / nExplicitCD on the host
         "explicit_tl_simo": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
                               "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
                               "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": simo,
                               "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        # the same run RESIDENT on the device: integrator="CUDA_central_difference" + <CUDA_explicit_solver> (d, v, a stay on the GPU,
+        # FieldT receives them when a step writes output): nodal force, body force, and a prescribed displacement following a schedule
+        "explicit_tl_simo_resident": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                                       "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02}],
+                                       "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": simo,
+                                       "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, resident),
+        "explicit_tl_simo_gravity_resident": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                                               "kbc": CLAMP, "fbc": [],
+                                               "element": {"type": "total_lagrangian", "mass_type": "lumped_mass",
+                                                           "body_force": {"schedule": 1, "vector": [0.0, 0.3, -9.81]}},
+                                               "material": simo, "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, resident),
+        "explicit_ul_simo_pull_resident": ({"time": {"num_steps": 40, "time_step": dt, "schedules": [[(0.0, 0.0), (40 * dt, 1.0)]]},
+                                            "integrator": "central_difference",
+                                            "kbc": CLAMP + [{"nodeset": 2, "dof": 1, "type": "u", "schedule": 1, "value": 0.01}], "fbc": [],
+                                            "element": {"type": "updated_lagrangian", "mass_type": "lumped_mass"}, "material": simo,
+                                            "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, resident),
         # the reference's batched <explicit_solid> against <cuda_explicit_solid>: Neo-Hookean with fixed mass scaling
         # (host-side lumped mass incl. the scaling, device force) and Hughes-Winget J2 pulled past yield (device-resident history)
         "explicit_solid_neo": ({"time": {"num_steps": 30, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
@@ -155,7 +172,9 @@ def _write(work, name, desc, cuda, solver_override, n=5, tahoe_attrs=None, suffi
     if cuda:
         d["element"]["tag"] = "cuda_" + desc["element"]["type"]
         if solver_override:
-            d["solver"] = solver_override
+            d["solver"] = {k: v for k, v in solver_override.items() if k != "integrator"}
+            if "integrator" in solver_override:  # the resident explicit pair: solver tag + the field's integrator
+                d["integrator"] = solver_override["integrator"]
     if tahoe_attrs:
         d["tahoe_attrs"] = tahoe_attrs
     path = os.path.join(work, name + (".cuda" if cuda else ".ref") + suffix + ".xml")
@@ -204,6 +223,27 @@ def test_plugin_binary_accepts_new_tags_and_fails_loudly_without_gpu():
         shutil.rmtree(work, ignore_errors=True)
 
 
+@pytest.mark.skipif(not os.path.exists(PLUGIN_BIN), reason="the plugin executable is built in the authoring container (make -C tahoe_b200/host)")
+def test_plugin_schema_lists_the_cuda_tags():
+    """`tahoe -xsd` (FEExecutionManagerT.cpp:219-221) generates tahoe.xsd from DefineParameters / DefineSubs / NewSub: the plugin's
+    element groups, matrix, solvers and integrator must appear in the schema the patched executable writes (no GPU needed)"""
+    work = tempfile.mkdtemp(prefix="tb2_xsd_")
+    try:
+        r = subprocess.run([PLUGIN_BIN, "-xsd"], cwd=work, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        xsd = os.path.join(work, "tahoe.xsd")
+        assert os.path.exists(xsd), r.stdout[-2000:]
+        text = open(xsd).read()
+        for tag in ("cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian", "cuda_explicit_solid", "CUDA_PCG_matrix",
+                    "CUDA_PCG_solver", "CUDA_explicit_solver", "CUDA_central_difference"):
+            assert tag in text, tag
+        # the matrix's attributes and the explicit solver's restart attribute are declared, not just the names
+        assert re.search(r"element name='CUDA_PCG_matrix'>.*?attribute name='rel_tolerance'", text, re.S)
+        assert re.search(r"element name='CUDA_explicit_solver'>.*?attribute name='restart_output_inc'", text, re.S)
+        assert re.search(r"enumeration value='CUDA_central_difference'", text)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 @needs_bins
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(_cases()))
@@ -226,6 +266,8 @@ def test_plugin_reproduces_reference_output(name):
         assert np.abs(a - b).max() < tol * np.abs(a).max()
         if name.endswith("nlpcg"):
             assert "device PCG" in r1.stdout
+        if name.endswith("resident"):
+            assert "CUDA_explicit_solver" in open(cuda_xml).read() and "CUDA_central_difference" in open(cuda_xml).read()
         if override is None and os.path.exists(COMPARE_BIN):
             # the reference's own acceptance test (run_benchmarks.sh) for the cases that keep the reference's solver: its comparator,
             # with its default tolerances (a value fails when it is off by more than 1e-8 relative AND 1e-10 absolute), checks the CUDA
