@@ -1342,43 +1342,61 @@ int tb2_matrix_bicgstab(tb2_matrix* A, const double* d_b, double* d_x, double rt
         k_spmv<false><<<sg, 256, 0, st>>>(A->ngroups, A->grp.p, A->rowptr.p, A->colind.p, A->val.p, x, out, nullptr, nullptr);
     };
     {
-        ProfScope ps(m, kProfPcgVec, 3);
+        ProfScope ps(m, kProfPcgVec, 1);
         k_extract_dinv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A->rowptr.p, A->colind.p, A->val.p, A->dinv.p, 1);
-        spmv(d_x, t);
-        k_bi_init<<<vec_blocks, 256, 0, st>>>(n, d_b, t, r, rhat, p, v, A->partial.p);
-        k_bi_scalars_init<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, rtol, atol, max_iter);
     }
-    TB2_CUDA(cudaGetLastError());
     PcgCtl h{};
-    const int check_every = 8;
-    for (int it = 0; it < max_iter;) {
-        for (int k = 0; k < check_every && it < max_iter; k++, it++) {
-            {
-                ProfScope ps(m, kProfPcgVec, 1);
-                k_bi_direction<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, r, v, A->dinv.p, p, y);
+    double hs[kNumScal];
+    double r0_first = -1.0;
+    int done_iters = 0;
+    const int check_every = 8, max_restarts = 50;
+    // A breakdown ((rhat, v), rho or omega vanish: the shadow residual has lost its grip) is answered the standard way: restart
+    // from the current iterate with rhat = r.  Tolerances stay relative to the FIRST residual.
+    for (int attempt = 0; attempt <= max_restarts; attempt++) {
+        {
+            ProfScope ps(m, kProfPcgVec, 3);
+            spmv(d_x, t);
+            k_bi_init<<<vec_blocks, 256, 0, st>>>(n, d_b, t, r, rhat, p, v, A->partial.p);
+            k_bi_scalars_init<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, rtol, atol, max_iter - done_iters);
+        }
+        if (attempt > 0) { // keep the stop test relative to the first residual
+            TB2_CUDA(cudaMemcpyAsync(scal + kR0, &r0_first, sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        TB2_CUDA(cudaGetLastError());
+        for (int it = 0; it < max_iter - done_iters;) {
+            for (int k = 0; k < check_every && it < max_iter - done_iters; k++, it++) {
+                {
+                    ProfScope ps(m, kProfPcgVec, 1);
+                    k_bi_direction<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, r, v, A->dinv.p, p, y);
+                }
+                spmv(y, v);
+                {
+                    ProfScope ps(m, kProfPcgVec, 3);
+                    k_bi_dot2<<<vec_blocks, 256, 0, st>>>(n, rhat, v, rhat, v, A->partial.p, ctl);
+                    k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 0, rtol, atol, max_iter - done_iters);
+                    k_bi_half<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, r, v, A->dinv.p, sv, z);
+                }
+                spmv(z, t);
+                ProfScope ps(m, kProfPcgVec, 4);
+                k_bi_dot2<<<vec_blocks, 256, 0, st>>>(n, t, sv, t, t, A->partial.p, ctl);
+                k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 1, rtol, atol, max_iter - done_iters);
+                k_bi_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, y, z, sv, t, rhat, d_x, r, A->partial.p);
+                k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 2, rtol, atol, max_iter - done_iters);
             }
-            spmv(y, v);
-            {
-                ProfScope ps(m, kProfPcgVec, 3);
-                k_bi_dot2<<<vec_blocks, 256, 0, st>>>(n, rhat, v, rhat, v, A->partial.p, ctl);
-                k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 0, rtol, atol, max_iter);
-                k_bi_half<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, r, v, A->dinv.p, sv, z);
-            }
-            spmv(z, t);
-            ProfScope ps(m, kProfPcgVec, 4);
-            k_bi_dot2<<<vec_blocks, 256, 0, st>>>(n, t, sv, t, t, A->partial.p, ctl);
-            k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 1, rtol, atol, max_iter);
-            k_bi_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, y, z, sv, t, rhat, d_x, r, A->partial.p);
-            k_bi_scalars<<<1, 1024, 0, st>>>((int)vec_blocks, A->partial.p, scal, ctl, 2, rtol, atol, max_iter);
+            TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+            TB2_CUDA(cudaStreamSynchronize(st));
+            if (h.done) break;
         }
         TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        TB2_CUDA(cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
         TB2_CUDA(cudaStreamSynchronize(st));
-        if (h.done) break;
+        if (attempt == 0) r0_first = hs[kR0];
+        done_iters += h.iters;
+        const bool converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * r0_first);
+        if (converged || !h.breakdown || done_iters >= max_iter) break;
     }
-    double hs[kNumScal];
-    TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
-    TB2_CUDA(cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
-    TB2_CUDA(cudaStreamSynchronize(st));
+    h.iters = done_iters;
+    hs[kR0] = r0_first;
     if (iterations) *iterations = h.iters;
     if (final_rnorm) *final_rnorm = hs[kRNORM];
     A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]);

@@ -150,7 +150,19 @@ SolverT::SolutionStatusT CudaExplicitSolverT::Solve(int)
 
 		/* external load on the active equations: Tahoe's own FormRHS (nodal forces of FieldT::FormRHS, tractions and body forces
 		 * of the element group) with the group's internal force left out -- formed while there is something to form */
-		if (fHasLoads || !fLoadsChecked) {
+		/* loads follow time through the schedules only (FBC cards, tractions, body forces all scale with a ScheduleT value): they are
+		 * formed again when a schedule value moved, not every step */
+		bool schedules_moved = !fLoadsChecked;
+		{
+			const TimeManagerT* tm = fFEManager.TimeManager();
+			const int ns = tm->NumSchedule();
+			if ((int)fScheduleValue.size() != ns) { fScheduleValue.assign(ns, 0.0); schedules_moved = true; }
+			for (int k = 0; k < ns; k++) {
+				const double v = tm->ScheduleValue(k);
+				if (v != fScheduleValue[k]) { fScheduleValue[k] = v; schedules_moved = true; }
+			}
+		}
+		if ((fHasLoads && schedules_moved) || !fLoadsChecked) {
 			fRHS_lock = kOpen;
 			fLHS_lock = kIgnore;
 			fRHS = 0.0;

@@ -89,6 +89,7 @@ private:
 	std::vector<int64_t> fPrescribed;  /**< nodal dof indices 3 n + i with a kinematic boundary condition */
 	std::vector<double> fPrescribedValue, fScratch;
 	std::vector<double> fFext;         /**< [nn][3] external load of the step */
+	std::vector<double> fScheduleValue; /**< schedule values the loads on the device were formed with */
 	bool fHasLoads;                    /**< the field has nodal forces, or the first muted FormRHS was non-zero */
 	bool fLoadsChecked;
 	int fSteps, fDownloads, fRestartInc;
