@@ -768,6 +768,19 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    # run (and first-touch the pinned host buffers) on the CPUs NVML reports as local to this rank's GPU: the e2e leg's D2H copies
+    # then stay on the GPU's own PCIe root / NUMA node instead of all ranks sharing one socket's path (round 1: 23 % e2e efficiency at N = 8)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local).uuid)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.lib()
