@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(128, MINB) k_base_force(const BaseArgs p)
         for (int a = 0; a < 8; a++) p.fe[(int64_t)(3 * a + i) * p.stride + e] = f[a];
     }
 }
-template <bool DESC, bool NOFEXT>
-__global__ void __launch_bounds__(256) k_base_node(int64_t n0, int64_t nn, const int4* __restrict__ inc8, const double* __restrict__ fe, int64_t stride,
+template <bool DESC, bool NOFEXT, int T = 256, int MINB = 1>
+__global__ void __launch_bounds__(T, MINB) k_base_node(int64_t n0, int64_t nn, const int4* __restrict__ inc8, const double* __restrict__ fe, int64_t stride,
                                                   DofUpdate du, const double* __restrict__ fext, const double* __restrict__ minv,
                                                   const unsigned char* __restrict__ code, double* d, double* v)
 {
@@ -273,6 +273,33 @@ int main(int argc, char** argv)
     run_base(k_base_force<3, 0, false, true>, "pairs regs3 +K5");
     run_base(k_base_force<2, 0, false, true>, "pairs regs2 +K5");
     run_base(k_base_force<2, 1, false, true>, "pairs xsmem2 +K5");
+    if (getenv("LAB_K5")) { // the node kernel alone (scratch left by one sweep): occupancy / CTA-size variants
+        BaseArgs b{0, ne, stride, d_conn, d_X, F.d, d_fe, mat, d_status};
+        reset();
+        k_base_force<3, 0, false><<<(unsigned)((ne + 127) / 128), 128>>>(b);
+        auto t5 = [&](auto kern, int T, const char* name) {
+            reset();
+            const unsigned gn = (unsigned)((nn + T - 1) / T);
+            for (int w = 0; w < 3; w++) kern<<<gn, T>>>(0, nn, (const int4*)d_inc8, d_fe, stride, du, d_fext, d_minv, d_code, F.d, F.v);
+            CK(cudaEventRecord(ev0));
+            for (int s = 0; s < steps; s++) kern<<<gn, T>>>(0, nn, (const int4*)d_inc8, d_fe, stride, du, d_fext, d_minv, d_code, F.d, F.v);
+            CK(cudaEventRecord(ev1));
+            CK(cudaEventSynchronize(ev1));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, ev0, ev1));
+            printf("K5 %-28s %8.3f us\n", name, 1e3 * ms / steps);
+        };
+        t5(k_base_node<false, false, 256, 1>, 256, "256 thr, natural regs");
+        t5(k_base_node<false, false, 256, 4>, 256, "256 thr, 4 CTAs/SM");
+        t5(k_base_node<false, false, 256, 6>, 256, "256 thr, 6 CTAs/SM");
+        t5(k_base_node<false, false, 256, 8>, 256, "256 thr, 8 CTAs/SM");
+        t5(k_base_node<false, false, 128, 1>, 128, "128 thr, natural regs");
+        t5(k_base_node<false, false, 128, 12>, 128, "128 thr, 12 CTAs/SM");
+        t5(k_base_node<false, false, 512, 1>, 512, "512 thr, natural regs");
+        t5(k_base_node<false, false, 512, 3>, 512, "512 thr, 3 CTAs/SM");
+        t5(k_base_node<false, true, 256, 1>, 256, "256 thr, no fext");
+        return 0;
+    }
     if (getenv("LAB_SWEEPS_ONLY")) return 0;
     // ---- slab pipeline: K1 slabs on stream A, K5 slabs on stream B (co-resident when K1 leaves registers free)
     cudaStream_t sA, sB;

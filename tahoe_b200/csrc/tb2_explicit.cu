@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_cd_predictor(int64_t ndof, double dt, d
 // node kernel (see cd_node_update_one).  skip_slot (multi-GPU): nodes with skip_slot[n] >= 0 lie on the partition interface and
 // are updated by k_cd_interface_update once the summed force has arrived.
 template <bool GATHER, bool NEXT_PREDICTOR>
-__global__ void __launch_bounds__(256) k_cd_node_update(int64_t n_begin, int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+__global__ void __launch_bounds__(256, 6) k_cd_node_update(int64_t n_begin, int64_t nn, const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                                        const int4* __restrict__ inc8, const double* __restrict__ fe, int64_t stride,
                                                        const StepConsts sc, const NodeArrays na, const int* __restrict__ skip_slot)
 {
