@@ -37,6 +37,18 @@ MATERIAL = {"type": "Simo_isotropic", "density": 1.0, "kappa": 1000.0, "mu": 5.0
 REF_BIN = os.path.join(REPO, "oracle", "_ref", "tahoe")
 
 
+EXCHANGE = "peer"  # --exchange: interface sums over NVLink peer memory (tb2_comm_peer_*), or "nccl" = the packed ncclAllReduce
+
+
+def comm_init(m, dist, comm):
+    """tb2_comm_init on mesh m (+ the peer-window import when EXCHANGE is "peer": the 64-byte handles travel by all_gather_object)"""
+    def gather(b):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, b)
+        return out
+    m.comm_init(*comm, all_gather=gather if EXCHANGE == "peer" else None)
+
+
 def stable_dt(n):
     return 0.25 * (1.0 / n) / np.sqrt((MATERIAL["kappa"] + 4.0 * MATERIAL["mu"] / 3.0) / MATERIAL["density"])
 
@@ -377,7 +389,7 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
     if world > 1:
         uid = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        m.comm_init(rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
+        comm_init(m, dist, (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"]))
     g = capi.Group(m, capi.SMALL_STRAIN, capi.material({"type": "small_strain_StVenant", "E": 100.0, "nu": 0.25, "density": 1.0}))
     code = np.zeros(X.shape, np.uint8)
     code[ns[1]] = 1
@@ -648,7 +660,7 @@ def parity_check(torch, dist, capi, tmesh, rank, world, local):
     def explicit(X, conn, ns, comm, nsteps=8):
         m = capi.Mesh(X, conn, device=dev)
         if comm:
-            m.comm_init(*comm)
+            comm_init(m, dist, comm)
         g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MATERIAL))
         ex = capi.Explicit(g)
         code = np.zeros(X.shape, np.uint8)
@@ -799,7 +811,7 @@ def run_gpu_arm(args):
     if world > 1:
         uid = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        m.comm_init(rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
+        comm_init(m, dist, (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"]))
     g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MATERIAL))
     ex = capi.Explicit(g)
     code = np.zeros(X.shape, np.uint8)
@@ -960,8 +972,11 @@ def run_gpu_arm(args):
                                  algorithmic_flop_per_launch=k1_flops, hbm_frac=roof["frac"]),
                 "roofline_hbm": roof, "roofline_k5": roof_k5,
                 "schedule": ("K1 and K5 back to back on one stream (2 launches per step)" if world == 1 else
-                             "two lanes: boundary elements -> packed interface all-reduce -> interface nodes on the comm stream beside "
-                             "interior elements -> private nodes on the main stream"),
+                             "two lanes: boundary elements -> partial interface forces %s -> interface nodes on the comm stream beside "
+                             "interior elements -> private nodes on the main stream"
+                             % ("published to the rank's NVLink-mapped window, pulled and summed by the interface-node kernel of every sharer"
+                                if EXCHANGE == "peer" else "packed, ncclAllReduce")),
+                "exchange": EXCHANGE if world > 1 else None,
                 "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
                 "interface_exchange_ms": comm_ms if world > 1 else None,
                 "parity": parity,
@@ -1023,6 +1038,8 @@ def main():
     ap.add_argument("--nlpcg-n", type=int, default=48, help="cube edge of the J2 nonlinear-PCG leg (configs[3]; 159 -> 4M elements; 0 = skip)")
     ap.add_argument("--nlpcg-iters", type=int, default=20)
     ap.add_argument("--newton-j2-n", type=int, default=40, help="cube edge of the J2 Newton + BiCGStab leg (configs[3] as stated; 159 -> 4M elements; 0 = skip)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: interface sums pulled over NVLink peer memory inside the consuming kernels (default), or the packed ncclAllReduce")
     ap.add_argument("--no-parity", action="store_true", help="skip the partitioned-vs-single-GPU check that precedes the timing")
     ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-numbering leg")
     ap.add_argument("--no-plugin", action="store_true", help="skip the plugin-executable leg")
@@ -1034,6 +1051,8 @@ def main():
     ap.add_argument("--k1-fp64-inst-per-element", type=float, default=K1_FP64_INST_PER_ELEMENT)
     ap.add_argument("--k1-traffic-bytes-per-element", type=float, default=K1_TRAFFIC_BYTES_PER_ELEMENT)
     args = ap.parse_args()
+    global EXCHANGE
+    EXCHANGE = args.exchange
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly one JSON line: whatever a library prints to fd 1 meanwhile (e.g. NCCL's version banner) goes to stderr
     sys.stdout.flush()

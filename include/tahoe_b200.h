@@ -376,6 +376,18 @@ int tb2_comm_init(tb2_mesh* mesh, int rank, int nranks, const char h_id[128], in
                   const int32_t* h_interface_nodes, const int32_t* h_interface_slots, int64_t num_global_interface_nodes,
                   const uint8_t* h_node_owned /*[nn]: 1 if this rank owns the node (dot products count it once)*/);
 int tb2_comm_destroy(tb2_mesh* mesh);
+/* Interface exchange over NVLink peer memory, in place of the reference's point-to-point ghost-node messages and
+ * MPI_Allreduce (CommManagerT.cpp:424-436, SolverT.cpp:854-860): every rank exports the 64-byte IPC handle of its exchange
+ * window, the host program all-gathers the handles by its own means (MPI_Allgather where CommManagerT lives) and every rank
+ * imports the [nranks][64] table.  From then on the explicit step and the distributed PCG publish their partial interface
+ * values into their own window and pull the sharers' values inside the consuming kernel -- no collective library on the data
+ * path; without the import they run the packed ncclAllReduce.  One process per GPU, all GPUs in one NVLink domain (<= 16).
+ * Like a communicator, the windows are torn down collectively: the host program synchronises the ranks (a barrier after the
+ * last run has been waited for) before any rank calls tb2_comm_destroy / tb2_mesh_destroy.  A peer that never arrives at an
+ * exchange ends the waiting kernel after 300 s with a device trap (every later call on that rank fails). */
+int tb2_comm_peer_export(tb2_mesh* mesh, char h_handle[64]);
+int tb2_comm_peer_import(tb2_mesh* mesh, const char* h_handles /* [nranks][64], rank order */);
+int tb2_comm_peer_enabled(tb2_mesh* mesh); /* 1 after a successful import */
 /* d_nodal[nn][3] += contributions of the other sharers on interface nodes (ncclAllReduce on the packed vector) */
 int tb2_comm_sum_interface(tb2_mesh* mesh, double* d_nodal);
 

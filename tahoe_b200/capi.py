@@ -43,7 +43,8 @@ tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_s
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
-tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface""".split()
+tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
+tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled""".split()
 
 
 class Tb2Error(RuntimeError):
@@ -231,12 +232,26 @@ class Mesh(_Handle):
         return n.value, col
 
     # ---- multi-GPU
-    def comm_init(self, rank, nranks, uid, if_nodes, if_slots, n_global_interface, owned):
+    def comm_init(self, rank, nranks, uid, if_nodes, if_slots, n_global_interface, owned, all_gather=None):
+        """all_gather: callable bytes -> list of every rank's bytes in rank order (the host program's own all-gather); when
+        given, the exchange windows are mapped across the ranks and the hot loops exchange over NVLink peer memory
+        (tb2_comm_peer_export / _import) instead of the packed ncclAllReduce"""
         if_nodes = np.ascontiguousarray(if_nodes, np.int32)
         if_slots = np.ascontiguousarray(if_slots, np.int32)
         owned = np.ascontiguousarray(owned, np.uint8)
         _chk(lib().tb2_comm_init(self.h, rank, nranks, uid, C.c_int64(len(if_nodes)), _p(if_nodes), _p(if_slots),
                                  C.c_int64(n_global_interface), _p(owned)))
+        if all_gather is not None and nranks > 1:
+            self.comm_enable_peer(all_gather)
+
+    def comm_enable_peer(self, all_gather):
+        buf = C.create_string_buffer(64)
+        _chk(lib().tb2_comm_peer_export(self.h, buf))
+        handles = all_gather(buf.raw)
+        _chk(lib().tb2_comm_peer_import(self.h, b"".join(handles)))
+
+    def comm_peer_enabled(self):
+        return bool(lib().tb2_comm_peer_enabled(self.h))
 
     def sum_interface(self, d_nodal):
         _chk(lib().tb2_comm_sum_interface(self.h, _dp(d_nodal)))

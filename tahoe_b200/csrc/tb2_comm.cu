@@ -79,8 +79,21 @@ struct Comm {
     int64_t nb = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_packed = nullptr, ev_reduced = nullptr, ev_done = nullptr;
+    // peer-memory exchange (tb2_peer.cuh): this rank's window, the peers' windows as mapped here, the sharers of every
+    // interface node, last-CTA counters, the epochs of the two exchanges
+    char* win = nullptr;
+    size_t win_bytes = 0;
+    void* opened[kMaxPeers] = {};
+    PeerView pv{};
+    bool peer = false;
+    DevBuf<unsigned> share_mask; // [n_if] bit r: rank r touches the node
+    DevBuf<unsigned> counter;    // [2]
+    unsigned long long xe = 0, se = 0;
     ~Comm()
     {
+        for (void* q : opened)
+            if (q) cudaIpcCloseMemHandle(q);
+        if (win) cudaFree(win);
         if (ev_packed) cudaEventDestroy(ev_packed);
         if (ev_reduced) cudaEventDestroy(ev_reduced);
         if (ev_done) cudaEventDestroy(ev_done);
@@ -151,6 +164,64 @@ __global__ void k_unpack_eq(int64_t n_if, const int* __restrict__ nodes, const i
     if (eq > 0) v[eq - 1] = packed[3 * (int64_t)slots[k] + i];
 }
 
+// ---- peer-memory exchange -------------------------------------------------------------------------------------------------------
+__global__ void k_pack_rank_bit(int64_t n_if, const int* __restrict__ slots, double bit, double* __restrict__ packed)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_if) packed[3 * (int64_t)slots[k]] = bit;
+}
+__global__ void k_share_mask(int64_t n_if, const int* __restrict__ slots, const double* __restrict__ packed, unsigned* __restrict__ mask)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_if) mask[k] = (unsigned)packed[3 * (int64_t)slots[k]];
+}
+// publish the interface entries of an equation vector (prescribed dofs: 0) into this rank's window and raise the peers' flags
+__global__ void __launch_bounds__(256) k_peer_pack_eq(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
+                                                     const int* __restrict__ eqnos, const double* __restrict__ v, PeerView pv,
+                                                     unsigned long long epoch, unsigned* counter)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < 3 * n_if) {
+        const int64_t k = t / 3;
+        const int i = (int)(t % 3);
+        const int eq = eqnos[3 * (int64_t)nodes[k] + i];
+        peer_data(pv, pv.rank, epoch)[3 * (int64_t)slots[k] + i] = eq > 0 ? v[eq - 1] : 0.0;
+    }
+    peer_publish(pv, epoch, counter, kPeerFlagsOff);
+}
+// wait for the peers' flags, pull and sum the sharers' entries over NVLink, write them back into the equation vector
+__global__ void __launch_bounds__(256) k_peer_pull_eq(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
+                                                     const unsigned* __restrict__ share_mask, const int* __restrict__ eqnos,
+                                                     double* __restrict__ v, PeerView pv, unsigned long long epoch)
+{
+    peer_wait(pv, epoch, kPeerFlagsOff);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_if) return;
+    const int64_t k = t / 3;
+    const int i = (int)(t % 3);
+    const int eq = eqnos[3 * (int64_t)nodes[k] + i];
+    if (eq > 0) v[eq - 1] = peer_sum(pv, epoch, share_mask[k], 3 * (int64_t)slots[k] + i);
+}
+// all-reduce of n <= 4 scalars: every rank writes its values into every peer's mailbox, raises the flag, waits for the others
+// and sums the mailbox in rank order (identical bits on every rank).  One CTA.
+__global__ void k_peer_scalars(double* __restrict__ vals, int n, PeerView pv, unsigned long long epoch, unsigned timeout_s, bool trap)
+{
+    const int t = threadIdx.x;
+    if (t < pv.nranks) {
+        double* box = (double*)(pv.win[t] + kPeerMailOff) + ((epoch & 1ull) * kMaxPeers + pv.rank) * 4;
+        for (int i = 0; i < n; i++) box[i] = vals[i];
+        __threadfence_system();
+        if (t != pv.rank) peer_st_release((unsigned long long*)(pv.win[t] + kPeerSFlagsOff) + pv.rank, epoch);
+    }
+    peer_wait(pv, epoch, kPeerSFlagsOff, timeout_s, trap);
+    if (t < n) {
+        const double* box = (const double*)(pv.win[pv.rank] + kPeerMailOff) + (epoch & 1ull) * kMaxPeers * 4;
+        double s = 0.0;
+        for (int r = 0; r < pv.nranks; r++) s += peer_ld(box + r * 4 + t);
+        vals[t] = s;
+    }
+}
+
 bool comm_active(tb2_mesh* m) { return m->comm && m->comm->nranks > 1 && m->comm->n_glob > 0; }
 
 bool comm_plan(tb2_mesh* m, CommPlan* out)
@@ -170,6 +241,12 @@ bool comm_plan(tb2_mesh* m, CommPlan* out)
     out->ev_packed = c->ev_packed;
     out->ev_reduced = c->ev_reduced;
     out->ev_done = c->ev_done;
+    out->peer = c->peer;
+    out->pv = c->pv;
+    out->share_mask = c->share_mask.p;
+    out->counter = c->counter.p;
+    out->epoch = &c->xe;
+    out->sepoch = &c->se;
     return true;
 }
 
@@ -177,6 +254,7 @@ bool comm_plan(tb2_mesh* m, CommPlan* out)
 int comm_allreduce_packed(tb2_mesh* m)
 {
     Comm* c = m->comm;
+    if (c->peer) return TB2_OK; // the consumer pulls the peers' partials itself
     ProfScope ps(m, kProfComm, 1, c->stream);
     const int r = g_nccl.AllReduce(c->packed.p, c->packed.p, (size_t)(3 * c->n_glob), kNcclFloat64, kNcclSum, c->comm, c->stream);
     return r ? nccl_fail(r, "ncclAllReduce(interface, overlapped)") : TB2_OK;
@@ -188,9 +266,17 @@ const unsigned char* comm_owned_mask(tb2_mesh* m) { return m->comm ? m->comm->ow
 int comm_pack_eq(tb2_mesh* m, const int* d_eqnos, const double* d_eqvec, cudaStream_t st)
 {
     Comm* c = m->comm;
+    const int T = 256;
+    if (c->peer) {
+        ProfScope ps(m, kProfComm, 1, st);
+        c->xe++;
+        const int64_t nt = 3 * c->n_if > 0 ? 3 * c->n_if : 1;
+        k_peer_pack_eq<<<(unsigned)((nt + T - 1) / T), T, 0, st>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, d_eqvec, c->pv, c->xe, c->counter.p);
+        TB2_CUDA(cudaGetLastError());
+        return TB2_OK;
+    }
     ProfScope ps(m, kProfComm, 2, st);
     TB2_CUDA(cudaMemsetAsync(c->packed.p, 0, 3 * c->n_glob * sizeof(double), st));
-    const int T = 256;
     if (c->n_if) k_pack_eq<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, st>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, d_eqvec, c->packed.p);
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
@@ -200,6 +286,12 @@ int comm_unpack_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec, cudaStream_
     Comm* c = m->comm;
     ProfScope ps(m, kProfComm, 1, st);
     const int T = 256;
+    if (c->peer) {
+        const int64_t nt = 3 * c->n_if > 0 ? 3 * c->n_if : 1;
+        k_peer_pull_eq<<<(unsigned)((nt + T - 1) / T), T, 0, st>>>(c->n_if, c->nodes.p, c->slots.p, c->share_mask.p, d_eqnos, d_eqvec, c->pv, c->xe);
+        TB2_CUDA(cudaGetLastError());
+        return TB2_OK;
+    }
     if (c->n_if) k_unpack_eq<<<(unsigned)((3 * c->n_if + T - 1) / T), T, 0, st>>>(c->n_if, c->nodes.p, c->slots.p, d_eqnos, c->packed.p, d_eqvec);
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
@@ -209,6 +301,12 @@ int comm_unpack_eq(tb2_mesh* m, const int* d_eqnos, double* d_eqvec, cudaStream_
 int comm_allreduce_scalars(tb2_mesh* m, double* d_vals, int n)
 {
     if (!m->comm || m->comm->nranks == 1) return TB2_OK;
+    if (m->comm->peer && n <= 4) {
+        Comm* c = m->comm;
+        k_peer_scalars<<<1, 32, 0, m->stream>>>(d_vals, n, c->pv, ++c->se, 300, true);
+        TB2_CUDA(cudaGetLastError());
+        return TB2_OK;
+    }
     const int r = g_nccl.AllReduce(d_vals, d_vals, (size_t)n, kNcclFloat64, kNcclSum, m->comm->comm, m->stream);
     return r ? nccl_fail(r, "ncclAllReduce(scalars)") : TB2_OK;
 }
@@ -317,6 +415,87 @@ int tb2_comm_init(tb2_mesh* m, int rank, int nranks, const char h_id[128], int64
     m->comm = c;
     return TB2_OK;
 }
+
+int tb2_comm_peer_export(tb2_mesh* m, char h_handle[64])
+{
+    TB2_ARG(m && h_handle);
+    Comm* c = m->comm;
+    if (!c) {
+        set_error("tb2_comm_peer_export: no communicator on this mesh");
+        return TB2_ERR_ARG;
+    }
+    if (c->nranks > kMaxPeers) {
+        set_error("peer-memory exchange supports up to %d ranks (one NVSwitch domain), got %d", kMaxPeers, c->nranks);
+        return TB2_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard dg(m->device);
+    if (!c->win) {
+        c->win_bytes = (size_t)kPeerDataOff + 2 * 3 * (size_t)(c->n_glob > 0 ? c->n_glob : 1) * sizeof(double);
+        TB2_CUDA(cudaMalloc((void**)&c->win, c->win_bytes));
+    }
+    TB2_CUDA(cudaMemset(c->win, 0, c->win_bytes));
+    TB2_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    TB2_CUDA(cudaIpcGetMemHandle(&h, c->win));
+    memcpy(h_handle, &h, 64);
+    return TB2_OK;
+}
+
+int tb2_comm_peer_import(tb2_mesh* m, const char* h_handles)
+{
+    TB2_ARG(m && h_handles);
+    Comm* c = m->comm;
+    if (!c || !c->win) {
+        set_error("tb2_comm_peer_import: call tb2_comm_peer_export on every rank first");
+        return TB2_ERR_ARG;
+    }
+    DeviceGuard dg(m->device);
+    PeerView pv{};
+    pv.rank = c->rank;
+    pv.nranks = c->nranks;
+    pv.n3 = 3 * (c->n_glob > 0 ? c->n_glob : 1);
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) {
+            pv.win[r] = c->win;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_handles + 64 * (size_t)r, 64);
+        void* q = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (void*& o : c->opened)
+                if (o) {
+                    cudaIpcCloseMemHandle(o);
+                    o = nullptr;
+                }
+            return cuda_fail(e, "cudaIpcOpenMemHandle (peer window)", __FILE__, __LINE__);
+        }
+        c->opened[r] = q;
+        pv.win[r] = (char*)q;
+    }
+    // the sharers of every interface node: each rank adds its bit 2^rank on the slots it touches (exact in a double)
+    const int T = 256;
+    TB2_CUDA(c->share_mask.alloc(c->n_if > 0 ? c->n_if : 1));
+    TB2_CUDA(c->counter.alloc(2));
+    TB2_CUDA(cudaMemsetAsync(c->counter.p, 0, 2 * sizeof(unsigned), m->stream));
+    TB2_CUDA(cudaMemsetAsync(c->packed.p, 0, 3 * (c->n_glob > 0 ? c->n_glob : 1) * sizeof(double), m->stream));
+    if (c->n_if) k_pack_rank_bit<<<(unsigned)((c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->slots.p, (double)(1u << c->rank), c->packed.p);
+    if (c->n_glob > 0) {
+        const int r = g_nccl.AllReduce(c->packed.p, c->packed.p, (size_t)(3 * c->n_glob), kNcclFloat64, kNcclSum, c->comm, m->stream);
+        if (r) return nccl_fail(r, "ncclAllReduce(sharer masks)");
+    }
+    if (c->n_if) k_share_mask<<<(unsigned)((c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->slots.p, c->packed.p, c->share_mask.p);
+    TB2_CUDA(cudaGetLastError());
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    c->pv = pv;
+    c->xe = c->se = 0;
+    c->peer = true;
+    return TB2_OK;
+}
+
+int tb2_comm_peer_enabled(tb2_mesh* m) { return m && m->comm && m->comm->peer ? 1 : 0; }
 
 int tb2_comm_destroy(tb2_mesh* m)
 {

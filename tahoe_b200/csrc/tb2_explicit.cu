@@ -116,6 +116,66 @@ __global__ void __launch_bounds__(256) k_cd_interface_update(int64_t n_if, const
     }
 }
 
+// multi-GPU over peer memory (tb2_peer.cuh), step 1: the same partial forces, published into this rank's exchange window; the
+// last CTA raises the arrival flag in every peer's window
+__global__ void __launch_bounds__(256) k_peer_gather_publish(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
+                                                            const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                            const double* __restrict__ fe, int64_t stride, PeerView pv,
+                                                            unsigned long long epoch, unsigned* counter)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_if) {
+        const int64_t n = nodes[k];
+        const int k0 = inc_ptr[n], k1 = inc_ptr[n + 1];
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+        for (int q = k0; q < k1; q++) {
+            const int ent = __ldg(inc + q);
+            const int64_t e = ent >> 3;
+            const int a3 = 3 * (ent & 7);
+            f0 += __ldg(fe + (int64_t)(a3)*stride + e);
+            f1 += __ldg(fe + (int64_t)(a3 + 1) * stride + e);
+            f2 += __ldg(fe + (int64_t)(a3 + 2) * stride + e);
+        }
+        double* out = peer_data(pv, pv.rank, epoch) + 3 * (int64_t)slots[k];
+        out[0] = f0;
+        out[1] = f1;
+        out[2] = f2;
+    }
+    peer_publish(pv, epoch, counter, kPeerFlagsOff);
+}
+
+// step 2, exchange and node update in one kernel: wait for the peers' flags, pull the sharers' partial forces over NVLink, sum
+// them in rank order (bitwise the same on every sharer) and update the interface node
+template <bool NEXT_PREDICTOR>
+__global__ void __launch_bounds__(256) k_peer_interface_update(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
+                                                              const unsigned* __restrict__ share_mask, PeerView pv,
+                                                              unsigned long long epoch, const StepConsts sc, const NodeArrays na)
+{
+    peer_wait(pv, epoch, kPeerFlagsOff);
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_if) return;
+    const int64_t n = nodes[k];
+    const unsigned mask = share_mask[k];
+    const int64_t base = 3 * (int64_t)slots[k];
+    double f[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) f[i] = peer_sum(pv, epoch, mask, base + i);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int64_t q = 3 * n + i;
+        const unsigned char c = na.code[q];
+        double di = NEXT_PREDICTOR ? na.d[q] : 0.0, vi = na.v[q], ai;
+        const double bcv = (NEXT_PREDICTOR && c == TB2_BC_DSP) ? na.bcval[q] : 0.0;
+        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], na.fext ? na.fext[q] : 0.0, na.minv[q], bcv, di, vi, ai);
+        if (NEXT_PREDICTOR) na.d[q] = di;
+        else {
+            na.a[q] = ai;
+            na.fint[q] = f[i];
+        }
+        na.v[q] = vi;
+    }
+}
+
 // sparse refresh of the prescribed values (KBC controllers with a schedule): out[dof[k]] = value[k]
 __global__ void k_scatter_values(int64_t n, const int64_t* __restrict__ dof, const double* __restrict__ value, double* __restrict__ out)
 {
@@ -173,6 +233,50 @@ static void launch_node_update(tb2_explicit* ex, const StepConsts& sc, bool next
         k_cd_node_update<GATHER, false><<<nb, T, 0, st>>>(0, m->nn, m->inc_ptr.p, m->inc.p, (const int4*)m->inc8.p, m->fe.p, m->stride, sc, na, skip);
 }
 
+// the exchange lane of one multi-GPU step on the communicator's stream, after the boundary-element sweep: partial interface
+// forces -> sum over the sharers -> interface node update.  ev_packed marks the point where the scratch of the boundary
+// elements is complete (the private nodes of the main lane gather from it).
+static int interface_lane_peer(tb2_explicit* ex, const CommPlan& cp, const StepConsts& sc, bool next)
+{
+    tb2_mesh* m = ex->group->mesh;
+    const int T = 256;
+    const unsigned long long epoch = ++*cp.epoch;
+    const unsigned nb = (unsigned)(((cp.n_if > 0 ? cp.n_if : 1) + T - 1) / T); // a rank without interface nodes still raises its flag
+    const NodeArrays na = node_arrays(ex);
+    {
+        ProfScope ps(m, kProfComm, 1, cp.stream);
+        k_peer_gather_publish<<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, m->inc_ptr.p, m->inc.p, m->fe.p, m->stride, cp.pv, epoch,
+                                                      cp.counter);
+    }
+    TB2_CUDA(cudaEventRecord(cp.ev_packed, cp.stream));
+    ProfScope ps(m, kProfNodeUpdate, 1, cp.stream);
+    if (next) k_peer_interface_update<true><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.share_mask, cp.pv, epoch, sc, na);
+    else k_peer_interface_update<false><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.share_mask, cp.pv, epoch, sc, na);
+    return TB2_OK;
+}
+static int interface_lane_nccl(tb2_explicit* ex, const CommPlan& cp, const StepConsts& sc, bool next)
+{
+    tb2_mesh* m = ex->group->mesh;
+    const int T = 256;
+    {
+        ProfScope ps(m, kProfComm, 2, cp.stream);
+        TB2_CUDA(cudaMemsetAsync(cp.packed, 0, 3 * cp.n_glob * sizeof(double), cp.stream));
+        if (cp.n_if)
+            k_gather_pack<<<(unsigned)((cp.n_if + T - 1) / T), T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, m->inc_ptr.p, m->inc.p, m->fe.p,
+                                                                                m->stride, cp.packed);
+    }
+    TB2_CUDA(cudaEventRecord(cp.ev_packed, cp.stream));
+    TB2_CHECK(comm_allreduce_packed(m));
+    if (cp.n_if) {
+        ProfScope ps(m, kProfNodeUpdate, 1, cp.stream);
+        const unsigned nb = (unsigned)((cp.n_if + T - 1) / T);
+        const NodeArrays na = node_arrays(ex);
+        if (next) k_cd_interface_update<true><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.packed, sc, na);
+        else k_cd_interface_update<false><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.packed, sc, na);
+    }
+    return TB2_OK;
+}
+
 // nsteps explicit steps on the device-resident state; fs / vs: per-step scales of fext and of the prescribed displacements
 static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
 {
@@ -203,25 +307,10 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
             launch_node_update<true>(ex, sc, next, nullptr, m->stream);
             continue;
         }
-        // comm lane: boundary elements -> packed partial interface forces -> all-reduce -> interface nodes
+        // comm lane: boundary elements -> partial interface forces -> sum over the sharers (peer memory, else ncclAllReduce) -> interface nodes
         TB2_CUDA(cudaStreamWaitEvent(cp.stream, m->ev_k5, 0)); // the private nodes the boundary elements read are up to date
         TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, 0, cp.nb, cp.stream, cp.belems));
-        {
-            ProfScope ps(m, kProfComm, 2, cp.stream);
-            TB2_CUDA(cudaMemsetAsync(cp.packed, 0, 3 * cp.n_glob * sizeof(double), cp.stream));
-            if (cp.n_if)
-                k_gather_pack<<<(unsigned)((cp.n_if + T - 1) / T), T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, m->inc_ptr.p, m->inc.p, m->fe.p,
-                                                                                    m->stride, cp.packed);
-        }
-        TB2_CUDA(cudaEventRecord(cp.ev_packed, cp.stream));
-        TB2_CHECK(comm_allreduce_packed(m));
-        if (cp.n_if) {
-            ProfScope ps(m, kProfNodeUpdate, 1, cp.stream);
-            const unsigned nb = (unsigned)((cp.n_if + T - 1) / T);
-            const NodeArrays na = node_arrays(ex);
-            if (next) k_cd_interface_update<true><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.packed, sc, na);
-            else k_cd_interface_update<false><<<nb, T, 0, cp.stream>>>(cp.n_if, cp.nodes, cp.slots, cp.packed, sc, na);
-        }
+        TB2_CHECK(cp.peer ? interface_lane_peer(ex, cp, sc, next) : interface_lane_nccl(ex, cp, sc, next));
         TB2_CUDA(cudaEventRecord(cp.ev_done, cp.stream));
         // main lane: the other elements beside the all-reduce, then the private nodes (they gather boundary-element forces too)
         TB2_CHECK(launch_element_forces_range(g, ex->d.p, nullptr, 0, 0, m->ne, m->stream, nullptr, cp.belem_flag));

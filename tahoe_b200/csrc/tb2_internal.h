@@ -9,6 +9,7 @@
 
 #include "../../include/tahoe_b200.h"
 #include "tb2_materials.cuh"
+#include "tb2_peer.cuh"
 
 namespace tb2 {
 
@@ -82,6 +83,13 @@ struct CommPlan {
     double* packed = nullptr;       // [n_glob][3]
     cudaStream_t stream = nullptr;  // the collective runs here, beside the element sweep
     cudaEvent_t ev_packed = nullptr, ev_reduced = nullptr, ev_done = nullptr;
+    // peer-memory exchange (tb2_peer.cuh), when the windows have been imported: no collective library on the data path
+    bool peer = false;
+    PeerView pv{};
+    const unsigned* share_mask = nullptr; // [n_if] sharers of every interface node
+    unsigned* counter = nullptr;          // last-CTA counter of the publishing kernel
+    unsigned long long* epoch = nullptr;  // the communicator's interface-exchange epoch (host side, advanced per exchange)
+    unsigned long long* sepoch = nullptr; // ... and its scalar-exchange epoch
 };
 
 // per-kernel CUDA-event timing on the mesh stream (bench.py's roofline numbers are measured with these, live, inside the

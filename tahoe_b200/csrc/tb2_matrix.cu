@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(1024) k_cg_sum(int nvec, const double* __restr
     c = block_sum(c, sh);
     if (threadIdx.x == 0) { red[0] = a; red[1] = b; red[2] = c; }
 }
-__global__ void k_cg_scalars(const double* red, double* scal, PcgCtl* ctl, double rtol, double atol, int max_iter, int first)
+__device__ void cg_scalars(const double* red, double* scal, PcgCtl* ctl, double rtol, double atol, int max_iter, int first)
 {
     if (!first && ctl->done) return;
     const double gamma = red[0], rnorm = sqrt(red[1]), delta = red[2];
@@ -957,6 +957,45 @@ __global__ void k_cg_scalars(const double* red, double* scal, PcgCtl* ctl, doubl
     if (!ctl->done) {
         if (!(den > 0.0)) { ctl->breakdown = 1; ctl->done = 1; scal[kALPHA] = 0.0; }
         else scal[kALPHA] = gamma / den;
+    }
+}
+__global__ void k_cg_scalars(const double* red, double* scal, PcgCtl* ctl, double rtol, double atol, int max_iter, int first)
+{
+    cg_scalars(red, scal, ctl, rtol, atol, max_iter, first);
+}
+// the whole scalar step of one iteration in one CTA when the ranks exchange over peer memory (tb2_peer.cuh): this rank's three
+// partial sums -> every peer's mailbox -> flags -> wait -> sum over the ranks in rank order (identical bits everywhere) -> alpha, beta
+__global__ void __launch_bounds__(1024) k_cg_reduce_peer(int nvec, const double* __restrict__ pvec, int nif, const double* __restrict__ pif,
+                                                        int nint, const double* __restrict__ pint, double* __restrict__ scal, PcgCtl* ctl,
+                                                        double rtol, double atol, int max_iter, int first, PeerView pv, unsigned long long epoch)
+{
+    __shared__ double sh[32];
+    __shared__ double mine[3];
+    const int t = threadIdx.x;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = t; i < nvec; i += blockDim.x) { a += pvec[2 * i]; b += pvec[2 * i + 1]; }
+    for (int i = t; i < nif; i += blockDim.x) c += pif[i];
+    for (int i = t; i < nint; i += blockDim.x) c += pint[i];
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    c = block_sum(c, sh);
+    if (t == 0) { mine[0] = a; mine[1] = b; mine[2] = c; }
+    __syncthreads();
+    if (t < pv.nranks) {
+        double* box = (double*)(pv.win[t] + kPeerMailOff) + ((epoch & 1ull) * kMaxPeers + pv.rank) * 4;
+        box[0] = mine[0];
+        box[1] = mine[1];
+        box[2] = mine[2];
+        __threadfence_system();
+        if (t != pv.rank) peer_st_release((unsigned long long*)(pv.win[t] + kPeerSFlagsOff) + pv.rank, epoch);
+    }
+    peer_wait(pv, epoch, kPeerSFlagsOff);
+    if (t == 0) {
+        const double* box = (const double*)(pv.win[pv.rank] + kPeerMailOff) + (epoch & 1ull) * kMaxPeers * 4;
+        double red[3] = {0.0, 0.0, 0.0};
+        for (int r = 0; r < pv.nranks; r++)
+            for (int i = 0; i < 3; i++) red[i] += peer_ld(box + r * 4 + i);
+        cg_scalars(red, scal, ctl, rtol, atol, max_iter, first);
     }
 }
 
@@ -1027,6 +1066,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
             }
             TB2_CHECK(comm_pack_eq(m, eqnos, w, cp.stream));
             TB2_CHECK(comm_allreduce_packed(m));
+            if (cp.peer) TB2_CHECK(comm_unpack_eq(m, eqnos, w, cp.stream)); // the pull, beside the interior rows (they write other rows of w)
             TB2_CUDA(cudaEventRecord(cp.ev_reduced, cp.stream));
         }
         {
@@ -1037,7 +1077,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
         }
         if (ng_if > 0) {
             TB2_CUDA(cudaStreamWaitEvent(st, cp.ev_reduced, 0));
-            TB2_CHECK(comm_unpack_eq(m, eqnos, w, st));
+            if (!cp.peer) TB2_CHECK(comm_unpack_eq(m, eqnos, w, st));
         } else
             TB2_CHECK(comm_sum_interface_eq(m, eqnos, w));
         return TB2_OK;
@@ -1053,9 +1093,20 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     TB2_CUDA(cudaMemsetAsync(A->s.p, 0, n * sizeof(double), st));
     TB2_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PcgCtl), st));
     TB2_CHECK(multiply(A->z.p, A->q.p, true));
-    k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, red, nullptr);
-    TB2_CHECK(comm_allreduce_scalars(m, red, 3));
-    k_cg_scalars<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter, 1);
+    // (r,u), (r,r), (A u, u): this rank's partials, summed over the ranks, alpha and beta -- one CTA over peer memory, else
+    // sum + ncclAllReduce + scalar kernel
+    auto scalar_step = [&](int first) -> int {
+        if (overlap && cp.peer) {
+            k_cg_reduce_peer<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, scal, ctl, rtol, atol, max_iter,
+                                                first, cp.pv, ++*cp.sepoch);
+            return TB2_OK;
+        }
+        k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, red, first ? nullptr : ctl);
+        TB2_CHECK(comm_allreduce_scalars(m, red, 3));
+        k_cg_scalars<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter, first);
+        return TB2_OK;
+    };
+    TB2_CHECK(scalar_step(1));
     TB2_CUDA(cudaGetLastError());
     PcgCtl h{};
     const int check_every = 8;
@@ -1067,9 +1118,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
             }
             TB2_CHECK(multiply(A->z.p, A->q.p, true));
             ProfScope ps(m, kProfPcgVec, 2);
-            k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, red, ctl);
-            TB2_CHECK(comm_allreduce_scalars(m, red, 3));
-            k_cg_scalars<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter, 0);
+            TB2_CHECK(scalar_step(0));
         }
         TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
         TB2_CUDA(cudaStreamSynchronize(st));

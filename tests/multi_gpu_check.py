@@ -1,7 +1,8 @@
 """Multi-GPU parity script (run under torchrun, one rank per GPU; launched by tests/test_gpu_multi.py):
-explicit central difference on an element-partitioned cube with NCCL interface-node force sums must reproduce the
+explicit central difference on an element-partitioned cube with interface-node force sums over the sharers must reproduce the
 single-GPU run of the whole cube (rank 0 computes it on its own device) to 1e-12, and all sharers of an interface node
-must hold bitwise identical values."""
+must hold bitwise identical values.  argv[1] = "peer" (default: the exchange over NVLink peer memory, tb2_comm_peer_*) or
+"nccl" (the packed ncclAllReduce)."""
 import os
 import sys
 
@@ -21,10 +22,20 @@ def field(X):
     return 0.01 * X @ np.array([[0.3, -0.2, 0.1], [0.05, 0.4, -0.3], [0.2, 0.1, -0.25]]) + 1e-3 * np.sin(7.0 * X[:, ::-1])
 
 
+EXCHANGE = sys.argv[1] if len(sys.argv) > 1 else "peer"
+
+
+def gather_bytes(b):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, b)
+    return out
+
+
 def setup(X, conn, ns, device, comm=None):
     m = capi.Mesh(X, conn, device=device)
     if comm:
-        m.comm_init(*comm)
+        m.comm_init(*comm, all_gather=gather_bytes if EXCHANGE == "peer" else None)
+        assert m.comm_peer_enabled() == (EXCHANGE == "peer")
     g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MAT))
     ex = capi.Explicit(g)
     code = np.zeros(X.shape, np.uint8)
@@ -123,7 +134,7 @@ def general_mesh_phase(rank, world, local):
     ex.run(dt, nsteps)
     d, v, a = ex.get_state()
     out = [None] * world
-    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a})
+    dist.all_gather_object(out, {"gid": part["node_gid"], "d": d, "v": v, "a": a})  # also the barrier before the teardown
     ex.close(); g.close(); m.close()
     ok = True
     if rank == 0:
@@ -248,7 +259,8 @@ def main():
                     break
                 seen[gid] = row
         assert len(seen) == nn_glob
-        print("multi_gpu_check: world=%d %s" % (world, "OK" if ok else "FAILED"))
+        print("multi_gpu_check: world=%d exchange=%s %s" % (world, EXCHANGE, "OK" if ok else "FAILED"))
+    dist.barrier()  # no rank tears its exchange window down while a peer may still pull from it
     ex.close(); g.close(); m.close()
     ok = general_mesh_phase(rank, world, local) and ok
     ok = pipelined_phase(rank, world, local) and ok

@@ -18,11 +18,13 @@ def _ngpu():
         return 0
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_explicit_matches_single_gpu(world):
+def test_partitioned_explicit_matches_single_gpu(world, exchange):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-                        "--master-addr", "127.0.0.1", "--master-port", str(29530 + world), os.path.join(HERE, "multi_gpu_check.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", str(29530 + world + (10 if exchange == "nccl" else 0)),
+                        os.path.join(HERE, "multi_gpu_check.py"), exchange],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:]
