@@ -316,6 +316,11 @@ typedef struct {
 typedef struct tb2_nlpcg tb2_nlpcg;
 int tb2_nlpcg_create(tb2_group* group, tb2_equations* eqs, const tb2_nlpcg_params* params, tb2_nlpcg** solver);
 int tb2_nlpcg_destroy(tb2_nlpcg* solver);
+/* The solver's line search alone, on a host callback G(s) = R(u + s dir) . dir (PCGSolver_LS::Update's secant search with its
+ * bracketing, clamping at max_step, trial budget and best-step fallback, PCGSolver_LS.cpp:213-348): for host programs that own
+ * the residual evaluation, and for checking the decision logic without a device.  final_step is the step the callback saw last. */
+int tb2_secant_search_host(double (*slope)(double step, void* user), void* user, double slope_at_zero, double max_step,
+                           double abs_tolerance, double rel_tolerance, int max_trials, double* final_step, int* evaluations);
 /* SolverT::Solve(max_iterations) for one load step (SolverT::InitStep state: iteration number -1).  d_u[nn][3]: displacement
  * with the prescribed dofs already set, updated in place; d_u_last: last converged displacement (J2 only, else NULL);
  * d_fext[nn][3]: nodal forces of this step (FieldT::FormRHS).  solve_max_iterations = -1: no limit beyond params.

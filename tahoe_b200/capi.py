@@ -44,7 +44,7 @@ tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
-tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled""".split()
+tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_secant_search_host""".split()
 
 
 class Tb2Error(RuntimeError):

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "tb2_internal.h"
+#include "tb2_linesearch.h"
 
 namespace tb2 {
 
@@ -293,6 +294,29 @@ int tb2_nlpcg_counters(const tb2_nlpcg* s, int64_t* residual_sweeps, int64_t* pr
     return TB2_OK;
 }
 
+int tb2_secant_search_host(double (*slope)(double step, void* user), void* user, double slope_at_zero, double max_step, double abs_tolerance,
+                           double rel_tolerance, int max_trials, double* final_step, int* evaluations)
+{
+    TB2_ARG(slope && final_step && max_trials >= 0);
+    SecantSearch search(max_step, abs_tolerance, rel_tolerance, max_trials);
+    search.begin(slope_at_zero);
+    double step = 0.0, current = 0.0;
+    int count = 0;
+    while (search.propose(&step)) {
+        search.observe(slope(step, user));
+        current = step;
+        count++;
+    }
+    if (search.stalled() && search.best_step() != current) {
+        current = search.best_step();
+        slope(current, user); // the caller's state moves to the chosen step, as GValue's last call does
+        count++;
+    }
+    *final_step = current;
+    if (evaluations) *evaluations = count;
+    return TB2_OK;
+}
+
 int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const double* d_fext, int solve_max_iterations, int* status,
                     int* iterations, double* error_out, double* error0_out)
 {
@@ -323,7 +347,7 @@ int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const dou
     int rc = TB2_OK;
     double h[2], error = 0.0, error0 = 0.0;
     int num_iterations = 0, tan_iterations = 0, restart_count = -1;
-    std::vector<double> search(2 * (size_t)(prm.line_search_iterations > 2 ? prm.line_search_iterations + 1 : 3));
+    SecantSearch search(prm.max_step, prm.abs_tolerance, prm.line_search_tolerance, prm.line_search_iterations);
 
     // NLSolver::ExitIteration (NLSolver.cpp:675-756)
     auto exit_iteration = [&](int iter) {
@@ -368,7 +392,7 @@ int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const dou
                 k_nl_direction<<<c.vb, 256, 0, c.st>>>(c.n, s->red.p, s->R.p, s->minv.p, c.w, s->R_last.p, s->dir.p, s->partial.p);
             }
         }
-        // ---- Update: secant search for the step s with R(u + s dir) . dir = 0 (PCGSolver_LS.cpp:213-348)
+        // ---- Update: secant search for the step s with R(u + s dir) . dir = 0 (PCGSolver_LS.cpp:213-348; tb2_linesearch.h)
         double rr_last = 0.0;
         if (prm.line_search_iterations == 0) {
             k_nl_update<<<c.nb1, 256, 0, c.st>>>(c.n, s->eqs->eq_node.p, 1.0, s->dir.p, c.u); // NLSolver::Update: the full step
@@ -377,47 +401,14 @@ int tb2_nlpcg_solve(tb2_nlpcg* s, double* d_u, const double* d_u_last, const dou
             rr_last = h[0];
         } else {
             NL_TRY(read2(c, h));
-            double s_current = 0.0, s_a = 0.0, G_a = h[0], s_b = 1.0, G_b = 0.0, G_new = 0.0, rr = 0.0;
-            search[0] = s_a; search[1] = G_a;
-            NL_TRY(gvalue(c, s_b, s_current, G_b, rr));
-            search[2] = s_b; search[3] = G_b;
-            const double G_0 = std::fabs(G_a) > std::fabs(G_b) ? G_b : G_a;
-            int count = 2;
-            bool give_up = false;
-            do {
-                const double mm = (G_a - G_b) / (s_a - s_b);
-                const double bb = G_b - mm * s_b;
-                double s_new = -bb / mm;
-                if (s_new > prm.max_step || s_new < 0.0) {
-                    give_up = true;
-                    if (s_new > prm.max_step) {
-                        s_new = prm.max_step;
-                        NL_TRY(gvalue(c, s_new, s_current, G_new, rr));
-                        search[2 * count] = s_new; search[2 * count + 1] = G_new;
-                        count++;
-                    }
-                    break;
-                }
-                NL_TRY(gvalue(c, s_new, s_current, G_new, rr));
-                search[2 * count] = s_new; search[2 * count + 1] = G_new;
-                if (std::fabs(G_a) > std::fabs(G_new) && std::fabs(G_a) > std::fabs(G_b)) { G_a = G_new; s_a = s_new; give_up = false; }
-                else if (std::fabs(G_b) > std::fabs(G_new) && std::fabs(G_b) > std::fabs(G_a)) { G_b = G_new; s_b = s_new; give_up = false; }
-                else if (G_b * G_a > 0) {
-                    if (G_a * G_new < 0) { G_a = G_new; s_a = s_new; }
-                    else if (G_b * G_new < 0) { G_b = G_new; s_b = s_new; }
-                    else give_up = true;
-                } else give_up = true;
-                if (++count >= prm.line_search_iterations) give_up = true;
-            } while (std::fabs(G_new) > prm.abs_tolerance && std::fabs(G_new / G_0) > prm.line_search_tolerance && !give_up);
-            if (give_up) { // the best step tried
-                double s_best = std::fabs(search[0]), G_best = std::fabs(search[1]);
-                int best = 0;
-                for (int i = 1; i < count; i++) {
-                    const double s_test = std::fabs(search[2 * i]), G_test = std::fabs(search[2 * i + 1]);
-                    if (std::fabs(s_best) < 1.0e-12 || (s_test > 1.0e-12 && G_test < G_best)) { s_best = s_test; G_best = G_test; best = i; }
-                }
-                if (search[2 * best] != s_current) NL_TRY(gvalue(c, search[2 * best], s_current, G_new, rr));
+            double s_current = 0.0, G_trial = 0.0, rr = 0.0, step = 0.0;
+            search.begin(h[0]); // G(0) = direction . residual came with the direction update
+            while (search.propose(&step)) {
+                NL_TRY(gvalue(c, step, s_current, G_trial, rr));
+                search.observe(G_trial);
             }
+            if (search.stalled() && search.best_step() != s_current) // settle on the best step tried
+                NL_TRY(gvalue(c, search.best_step(), s_current, G_trial, rr));
             // The reference now forms the residual once more at the state GValue left (NLSolver.cpp:174-195): the same sweep on
             // the same displacements, bit for bit.  Only the solver's iteration number differs, which J2Simo3D reads
             // (J2Simo3D.cpp:83-84) -- so that case repeats the sweep and every other material reuses the last one.
