@@ -273,6 +273,7 @@ int tb2_matrix_multx(tb2_matrix* A, const double* d_x, double* d_y);
 int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y);
 /* GlobalMatrixT::CopyDiagonal */
 int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag);
+int tb2_matrix_copy_diagonal_host(tb2_matrix* A, double* h_diag); /* GlobalMatrixT::CopyDiagonal on host memory */
 /* GlobalMatrixT::Solve -> BackSubstitute (GlobalMatrixT.cpp:77-113): Jacobi-preconditioned CG
  * (preconditioner = DiagonalMatrixT::Factorize semantics, DiagonalMatrixT.cpp:267-310).
  * d_x: start guess in, solution out.  Stops when |r| <= atol or |r| <= rtol*|r0| or max_iter. */

@@ -42,7 +42,7 @@ tb2_equations_destroy tb2_equations_count tb2_equations_get tb2_equations_device
 tb2_matrix_nnz tb2_matrix_get_csr tb2_matrix_get_msr tb2_matrix_clear tb2_form_stiffness tb2_form_stiffness_host
 tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
-tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
+tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_copy_diagonal_host tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
 tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_secant_search_host""".split()
 

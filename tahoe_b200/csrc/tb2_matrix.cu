@@ -855,6 +855,16 @@ int tb2_matrix_multx_host(tb2_matrix* A, const double* h_x, double* h_y)
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     return TB2_OK;
 }
+int tb2_matrix_copy_diagonal_host(tb2_matrix* A, double* h_diag)
+{
+    TB2_ARG(A && h_diag);
+    tb2_mesh* m = A->ctx;
+    DeviceGuard dg(m->device);
+    TB2_CHECK(tb2_matrix_copy_diagonal(A, A->q.p));
+    TB2_CUDA(cudaMemcpyAsync(h_diag, A->q.p, A->neq * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    return TB2_OK;
+}
 int tb2_matrix_copy_diagonal(tb2_matrix* A, double* d_diag)
 {
     TB2_ARG(A && d_diag);

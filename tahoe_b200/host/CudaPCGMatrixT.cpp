@@ -2,6 +2,7 @@
 #include "CudaPCGMatrixT.h"
 
 #include "ExceptionT.h"
+#include "MSRBuilderT.h"
 #include "dArrayT.h"
 
 #include <vector>
@@ -17,7 +18,10 @@ CudaPCGMatrixT::CudaPCGMatrixT(ostream& out, int check_code, bool symmetric, con
 	fHostCSR(NULL),
 	fDeviceMatrix(NULL),
 	fLastIterations(0),
-	fLastResidual(0.0)
+	fLastResidual(0.0),
+	fHostStructure(false),
+	fHostAssembled(false),
+	fGroupsStale(false)
 {
 }
 
@@ -28,25 +32,98 @@ CudaPCGMatrixT::~CudaPCGMatrixT(void)
 
 GlobalMatrixT* CudaPCGMatrixT::Clone(void) const
 {
-	ExceptionT::GeneralFail("CudaPCGMatrixT::Clone", "not implemented");
+	/* the reference's MSR family cannot be cloned either: MSRMatrixT's copy constructor fails (MSRMatrixT.cpp:23-27) */
+	ExceptionT::GeneralFail("CudaPCGMatrixT::Clone", "MSRMatrixT-derived matrices cannot be copied (as SPOOLES_matrix)");
 	return NULL;
+}
+
+/* the equation sets go to the MSR builder as always (MSRMatrixT.cpp:50-60); sets left over from a system that was initialised
+ * without ever building its host structure are dropped first (MSRMatrixT::SetMSRData clears them only when it runs) */
+void CudaPCGMatrixT::AddEquationSet(const iArray2DT& eqnos)
+{
+	if (fGroupsStale) { fMSRBuilder->ClearGroups(); fGroupsStale = false; }
+	MSRMatrixT::AddEquationSet(eqnos);
+}
+
+void CudaPCGMatrixT::AddEquationSet(const RaggedArray2DT<int>& eqnos)
+{
+	if (fGroupsStale) { fMSRBuilder->ClearGroups(); fGroupsStale = false; }
+	MSRMatrixT::AddEquationSet(eqnos);
 }
 
 void CudaPCGMatrixT::Initialize(int tot_num_eq, int loc_num_eq, int start_eq)
 {
-	/* inherited: builds the MSR structure from the equation sets (MSRMatrixT.cpp:35-45) */
-	MSRMatrixT::Initialize(tot_num_eq, loc_num_eq, start_eq);
+	/* the dimensions only (GlobalMatrixT.cpp); MSRMatrixT::Initialize -- graph, fbindx, fval -- waits for the first host access */
+	GlobalMatrixT::Initialize(tot_num_eq, loc_num_eq, start_eq);
 	if (fTotNumEQ != fLocNumEQ || fStartEQ != 1)
 		ExceptionT::GeneralFail("CudaPCGMatrixT::Initialize", "one process owns all equations (multi-GPU runs are element-partitioned inside the library)");
 	if (fHostCSR) tb2_matrix_destroy(fHostCSR);
 	fHostCSR = NULL;
 	fDeviceMatrix = NULL;
+	fHostStructure = false;
+	fHostAssembled = false;
+	fGroupsStale = true;
+}
+
+void CudaPCGMatrixT::EnsureHostStructure(void)
+{
+	if (fHostStructure) return;
+	MSRMatrixT::Initialize(fTotNumEQ, fLocNumEQ, fStartEQ); /* consumes and clears the builder's equation sets */
+	MSRMatrixT::Clear();
+	fHostStructure = true;
+	fGroupsStale = false;
 }
 
 void CudaPCGMatrixT::Clear(void)
 {
-	MSRMatrixT::Clear();
+	if (fHostStructure) MSRMatrixT::Clear();
+	fHostAssembled = false;
 	fDeviceMatrix = NULL;
+}
+
+void CudaPCGMatrixT::Assemble(const ElementMatrixT& elMat, const ArrayT<int>& eqnos)
+{
+	EnsureHostStructure();
+	fHostAssembled = true;
+	MSRMatrixT::Assemble(elMat, eqnos);
+}
+
+void CudaPCGMatrixT::Assemble(const ElementMatrixT& elMat, const ArrayT<int>& row_eqnos, const ArrayT<int>& col_eqnos)
+{
+	EnsureHostStructure();
+	fHostAssembled = true;
+	MSRMatrixT::Assemble(elMat, row_eqnos, col_eqnos);
+}
+
+void CudaPCGMatrixT::Assemble(const nArrayT<double>& diagonal_elMat, const ArrayT<int>& eqnos)
+{
+	EnsureHostStructure();
+	fHostAssembled = true;
+	MSRMatrixT::Assemble(diagonal_elMat, eqnos);
+}
+
+/* host-side reads of a device-assembled matrix go to the device copy */
+bool CudaPCGMatrixT::CopyDiagonal(dArrayT& diags) const
+{
+	if (fDeviceMatrix && !fHostAssembled) {
+		diags.Dimension(fLocNumEQ);
+		if (tb2_matrix_copy_diagonal_host(fDeviceMatrix, diags.Pointer()) != TB2_OK)
+			ExceptionT::GeneralFail("CudaPCGMatrixT::CopyDiagonal", "%s", tb2_last_error());
+		return true;
+	}
+	const_cast<CudaPCGMatrixT*>(this)->EnsureHostStructure();
+	return MSRMatrixT::CopyDiagonal(diags);
+}
+
+void CudaPCGMatrixT::Multx(const dArrayT& x, dArrayT& b) const
+{
+	if (fDeviceMatrix && !fHostAssembled) {
+		if (tb2_matrix_multx_host(fDeviceMatrix, x.Pointer(), b.Pointer()) != TB2_OK)
+			ExceptionT::GeneralFail("CudaPCGMatrixT::Multx", "%s", tb2_last_error());
+		return;
+	}
+	const_cast<CudaPCGMatrixT*>(this)->EnsureHostStructure();
+	MSRMatrixT::Multx(x, b);
 }
 
 void CudaPCGMatrixT::AddDeviceMatrix(tb2_matrix* A, double scale)
@@ -55,14 +132,6 @@ void CudaPCGMatrixT::AddDeviceMatrix(tb2_matrix* A, double scale)
 	if (fDeviceMatrix && fDeviceMatrix != A) ExceptionT::GeneralFail(caller, "one device-assembling element group per solver group");
 	if (fabs(scale - 1.0) > 1.0e-14) ExceptionT::GeneralFail(caller, "tangent scale %g != 1 (static analyses only)", scale);
 	fDeviceMatrix = A;
-}
-
-bool CudaPCGMatrixT::HostValuesAreZero(void) const
-{
-	const double* v = fval.Pointer();
-	for (int i = 0; i < fval.Length(); i++)
-		if (v[i] != 0.0) return false;
-	return true;
 }
 
 /* MSR (MSRMatrixT.h:21-23: fval[0..n-1] diagonal, fbindx[0..n] row starts, then off-diagonal columns; upper triangle only
@@ -123,13 +192,16 @@ void CudaPCGMatrixT::BackSubstitute(dArrayT& result)
 	const char caller[] = "CudaPCGMatrixT::BackSubstitute";
 	tb2_matrix* A = NULL;
 	if (fDeviceMatrix) {
-		if (!HostValuesAreZero())
+		if (fHostAssembled)
 			ExceptionT::GeneralFail(caller, "mixed host- and device-assembled contributions are not supported yet");
 		A = fDeviceMatrix;
 	} else {
+		EnsureHostStructure(); /* nothing assembled at all: the zero matrix, as MSRMatrixT would hold it */
 		UploadHostMatrix();
 		A = fHostCSR;
 	}
+	fOut << " CudaPCGMatrixT: " << (fDeviceMatrix ? "device-assembled tangent" : "host-assembled MSR values")
+	     << ", host MSR structure " << (fHostStructure ? "built" : "not built") << '\n';
 	dArrayT x(result.Length());
 	x = 0.0;
 	int status = tb2_matrix_pcg_host(A, result.Pointer(), x.Pointer(), fRelTol, fAbsTol, fMaxIterations, &fLastIterations, &fLastResidual);

@@ -60,7 +60,8 @@ CudaSolidElementT<BaseT>::CudaSolidElementT(const ElementSupportT& support, cons
 	fMatrix(NULL),
 	fIsJ2(false),
 	fMuted(false),
-	fMaterialKind(-1)
+	fMaterialKind(-1),
+	fDevice(0)
 {
 	this->SetName(name);
 }
@@ -89,6 +90,17 @@ void CudaSolidElementT<BaseT>::Check(int status, const char* caller) const
 	}
 }
 
+/* everything the wrapped element class defines, plus the device the group lives on */
+template <class BaseT>
+void CudaSolidElementT<BaseT>::DefineParameters(ParameterListT& list) const
+{
+	BaseT::DefineParameters(list);
+	ParameterT device(ParameterT::Integer, "device");
+	device.SetDefault(0);
+	device.AddLimit(0, LimitT::LowerInclusive);
+	list.AddParameter(device, ParameterListT::ZeroOrOnce);
+}
+
 template <class BaseT>
 void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 {
@@ -96,6 +108,8 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 
 	/* inherited: connectivity, shape functions, materials, output -- all Tahoe's own */
 	BaseT::TakeParameterList(list);
+	const ParameterT* device = list.Parameter("device");
+	fDevice = device ? int(*device) : 0;
 
 	/* the device path covers exactly the reference's Hex8 / 8-point / standard-B case */
 	if (this->GeometryCode() != GeometryT::kHexahedron || this->NumElementNodes() != 8 || this->NumIP() != 8 || this->NumSD() != 3)
@@ -217,7 +231,7 @@ void CudaSolidElementT<BaseT>::TakeParameterList(const ParameterListT& list)
 		conn.insert(conn.end(), c.Pointer(), c.Pointer() + c.Length());
 	}
 	const dArray2DT& X = this->ElementSupport().InitialCoordinates();
-	Check(tb2_mesh_create(0, X.MajorDim(), (int64_t)(conn.size() / 8), &conn[0], X.Pointer(), &fMesh), caller);
+	Check(tb2_mesh_create(fDevice, X.MajorDim(), (int64_t)(conn.size() / 8), &conn[0], X.Pointer(), &fMesh), caller);
 	fGroups.resize(mats.size(), NULL);
 	fKinds.resize(mats.size());
 	for (size_t im = 0; im < mats.size(); im++) {

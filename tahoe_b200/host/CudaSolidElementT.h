@@ -63,6 +63,7 @@ public:
 	virtual ~CudaSolidElementT(void);
 
 	/** build the device mesh / element group after Tahoe has read connectivity and materials */
+	virtual void DefineParameters(ParameterListT& list) const;
 	virtual void TakeParameterList(const ParameterListT& list);
 
 	/** element status flags (ElementCardT::kOFF elements are skipped by the element loops, SolidElementT.cpp:1116,1177): mirrored
@@ -123,6 +124,7 @@ private:
 	dArray2DT fMa;         /**< [nn][3] inertia force of the whole group (implicit integrators) */
 	dArray2DT fBodyAcc;    /**< [nn][3] the constant nodal field -b * schedule of a body force */
 	int fMaterialKind;     /**< tb2_material_kind */
+	int fDevice;           /**< CUDA device ordinal of this group (attribute "device", default 0; one process per GPU sets its own) */
 };
 
 typedef CudaSolidElementT<SmallStrainT> CudaSmallStrainT;

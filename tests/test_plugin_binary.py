@@ -321,3 +321,84 @@ def test_plugin_restart_files_are_interchangeable_with_the_reference(writer):
         assert got.shape == want.shape and np.abs(got - want).max() < 1e-9 * np.abs(want).max()
     finally:
         shutil.rmtree(work, ignore_errors=True)
+
+
+@pytest.mark.skipif(not os.path.exists(PLUGIN_BIN), reason="the plugin executable is built in the authoring container (make -C tahoe_b200/host)")
+@pytest.mark.gpu
+def test_plugin_at_scale_50_cubed():
+    """The plugin executable on 50^3 = 125 k elements (384 k equations, 30 M non-zeros), where the reference's own SPOOLES LU is no
+    longer a practical comparison: (i) static small strain through <cuda_small_strain> + <CUDA_PCG_matrix> against the C oracle's
+    assembled K solved by SciPy's CG -- and the host MSR structure (MSRBuilderT graph, fbindx, fval) must never have been built;
+    (ii) 20 steps of the resident explicit pair (<CUDA_explicit_solver> + CUDA_central_difference) against the oracle's
+    predictor / force sweep / corrector."""
+    import sys
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import oracle_lib as oracle
+    oracle.build()
+    n = 50
+    X, conn, ns = ti.structured_cube(n, jitter=0.15)
+    kstv = {"type": "small_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25}
+    simo = {"type": "Simo_isotropic", "density": 1.0, "kappa": 1000.0, "mu": 5.0}
+    newton = {"type": "nonlinear_solver", "abs_tolerance": "1.0e-12", "rel_tolerance": "1.0e-9", "divergence_tolerance": "1.0e+03",
+              "max_iterations": "5", "matrix": "CUDA_PCG_matrix", "matrix_attrs": 'rel_tolerance="1.0e-12" max_iterations="20000"'}
+    work = tempfile.mkdtemp(prefix="tb2_plugin50_")
+    try:
+        # ---- (i) static
+        desc = {"time": {"num_steps": 1, "time_step": 1.0, "schedules": [RAMP]}, "integrator": "static", "kbc": CLAMP,
+                "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02 / n ** 2}, {"nodeset": 2, "dof": 2, "schedule": 1, "value": 0.005 / n ** 2}],
+                "element": {"type": "small_strain"}, "material": kstv, "solver": newton}
+        xml = _write(work, "static50", desc, True, newton, n=n)
+        r = _run(PLUGIN_BIN, xml)
+        assert r.returncode == 0 and "End Execution" in r.stdout and "ExceptionT::Throw" not in r.stdout, r.stdout[-3000:]
+        log = open(os.path.join(work, "static50.cuda.out")).read()
+        assert "device-assembled tangent, host MSR structure not built" in log
+        assert "host MSR structure built" not in log
+        got = _nodal_output(os.path.join(work, "static50.cuda.io0.run"))
+        assert got.shape[0] == (n + 1) ** 3
+        code = np.zeros(X.shape, np.uint8)
+        code[ns[1]] = 1
+        eq, neq = oracle.equation_numbers(code)
+        rp, ci = oracle.csr_structure(conn, eq, neq)
+        err, kv = oracle.assemble_stiffness(oracle.SMALL_STRAIN, oracle.material(kstv), conn, X, np.zeros_like(X), eq, neq, rp, ci)
+        assert err == 0
+        K = sp.csr_matrix((kv, ci, rp), shape=(neq, neq))
+        f = np.zeros_like(X)
+        f[ns[2], 0] = 0.02 / n ** 2
+        f[ns[2], 1] = 0.005 / n ** 2
+        act = eq.reshape(-1) > 0
+        dinv = 1.0 / K.diagonal()
+        x, info = spla.cg(K, f.reshape(-1)[act], rtol=1e-12, maxiter=20000, M=spla.LinearOperator((neq, neq), matvec=lambda v: dinv * v))
+        assert info == 0
+        want = np.zeros(3 * X.shape[0])
+        want[act] = x
+        want = want.reshape(-1, 3)
+        assert np.abs(got[:, :3] - want).max() < 1e-7 * np.abs(want).max()
+        # ---- (ii) resident explicit
+        dt = 0.25 * (1.0 / n) / np.sqrt(1000.0 + 4.0 * 5.0 / 3.0)
+        nsteps = 20
+        resident = {"type": "CUDA_explicit_solver", "matrix": "diagonal_matrix", "integrator": "CUDA_central_difference"}
+        desc = {"time": {"num_steps": nsteps, "time_step": dt, "schedules": [[(0.0, 1.0)]]}, "integrator": "central_difference",
+                "kbc": CLAMP, "fbc": [{"nodeset": 2, "dof": 1, "schedule": 1, "value": 0.02 / n ** 2}],
+                "element": {"type": "total_lagrangian", "mass_type": "lumped_mass"}, "material": simo,
+                "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}
+        xml = _write(work, "explicit50", desc, True, resident, n=n)
+        r = _run(PLUGIN_BIN, xml)
+        assert r.returncode == 0 and "End Execution" in r.stdout and "ExceptionT::Throw" not in r.stdout, r.stdout[-3000:]
+        got = _nodal_output(os.path.join(work, "explicit50.cuda.io0.run"))
+        omat = oracle.material(simo)
+        mass = oracle.lumped_mass(1.0, conn, X)
+        fext = np.zeros_like(X)
+        fext[ns[2], 0] = 0.02 / n ** 2
+        d, v = np.zeros_like(X), np.zeros_like(X)
+        # FEManagerT::InitialCondition: a0 = M^-1 (fext - fint(0)) on the free dofs
+        a = np.where(code > 0, 0.0, fext / mass)
+        for _ in range(nsteps):
+            oracle.cd_predictor(dt, d, v, a, code, np.zeros_like(X))
+            e, fi = oracle.internal_force(oracle.TOTAL_LAGRANGIAN, omat, conn, X, d)
+            assert e == 0
+            oracle.cd_corrector(dt, v, a, fext - fi, mass, code)
+        assert np.abs(got[:, :3] - d).max() < 1e-9 * np.abs(d).max()
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
