@@ -503,14 +503,12 @@ static unsigned spmv_grid()
 {
     static unsigned blocks = 0;
     if (!blocks) {
-        int dev = 0, sms = 148, occ = 6, occ_dot = 6, envb = 0;
+        int dev = 0, sms = 148, occ = 6, occ_dot = 6;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv<false>, 256, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dot, k_spmv<true>, 256, 0);
         if (occ_dot < occ) occ = occ_dot;
-        if (const char* e = getenv("TB2_SPMV_CTAS_PER_SM")) envb = atoi(e); // experiment knob
-        if (envb > 0) occ = envb;
         if (occ < 1) occ = 1;
         blocks = (unsigned)(sms * occ);
         if (blocks > (unsigned)kSpmvBlocks) blocks = kSpmvBlocks;
@@ -1009,6 +1007,20 @@ __global__ void __launch_bounds__(1024) k_cg_reduce_peer(int nvec, const double*
     }
 }
 
+#ifdef TB2_PCG_TIMELINE // lab builds only (profiles/tools/lab/pcg_timeline.sh): device-side event marks inside 8 iterations
+static cudaEvent_t g_tl[8][8];
+static int g_tl_it = -1;
+#define TL_MARK(k, stream)                                                                     \
+    do {                                                                                       \
+        if (g_tl_it >= 0 && g_tl_it < 8) {                                                     \
+            if (!g_tl[g_tl_it][k]) cudaEventCreate(&g_tl[g_tl_it][k]);                         \
+            cudaEventRecord(g_tl[g_tl_it][k], stream);                                         \
+        }                                                                                      \
+    } while (0)
+#else
+#define TL_MARK(k, stream) do { } while (0)
+#endif
+
 static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double rtol, double atol, int max_iter, int* iterations,
                            double* final_rnorm)
 {
@@ -1065,8 +1077,11 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     // w = A_loc u with the interface sum; leaves the (A_loc u, u) partials in pif / pint
     auto multiply = [&](const double* u, double* w, bool with_dot) -> int {
         if (ng_if > 0) {
-            // the whole interface lane -- rows of the interface nodes, pack, all-reduce -- on the communicator's (high-priority)
-            // stream, beside the interior rows on the mesh stream
+            // the whole interface lane -- rows of the interface nodes, pack, pull (or all-reduce) -- on the communicator's (high-priority)
+            // stream, beside the interior rows on the mesh stream.  Timeline (profiles/r02_summary.md, r02k): the persistent interior grid
+            // holds every CTA slot, so the lane's kernels mostly run in the ~35 us after it; an interior grid of short CTAs, one slot
+            // per SM left free, or lane kernels cut to the left-over registers hide the lane but cost the interior rows 5-10 %, more
+            // than the lane is worth -- the persistent grid stays
             TB2_CUDA(cudaEventRecord(cp.ev_packed, st)); // u is ready
             TB2_CUDA(cudaStreamWaitEvent(cp.stream, cp.ev_packed, 0));
             {
@@ -1074,9 +1089,12 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
                 if (with_dot) k_spmv<true><<<sg_if, 256, 0, cp.stream>>>(ng_if, A->grp_split.p, A->rowptr.p, A->colind.p, A->val.p, u, w, pif, &ctl->done);
                 else k_spmv<false><<<sg_if, 256, 0, cp.stream>>>(ng_if, A->grp_split.p, A->rowptr.p, A->colind.p, A->val.p, u, w, nullptr, nullptr);
             }
+            TL_MARK(2, cp.stream);
             TB2_CHECK(comm_pack_eq(m, eqnos, w, cp.stream));
+            TL_MARK(3, cp.stream);
             TB2_CHECK(comm_allreduce_packed(m));
             if (cp.peer) TB2_CHECK(comm_unpack_eq(m, eqnos, w, cp.stream)); // the pull, beside the interior rows (they write other rows of w)
+            TL_MARK(4, cp.stream);
             TB2_CUDA(cudaEventRecord(cp.ev_reduced, cp.stream));
         }
         {
@@ -1085,6 +1103,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
             if (with_dot) k_spmv<true><<<sg, 256, 0, st>>>(ng_int, g, A->rowptr.p, A->colind.p, A->val.p, u, w, pint, &ctl->done);
             else k_spmv<false><<<sg, 256, 0, st>>>(ng_int, g, A->rowptr.p, A->colind.p, A->val.p, u, w, nullptr, nullptr);
         }
+        TL_MARK(5, st);
         if (ng_if > 0) {
             TB2_CUDA(cudaStreamWaitEvent(st, cp.ev_reduced, 0));
             if (!cp.peer) TB2_CHECK(comm_unpack_eq(m, eqnos, w, st));
@@ -1122,13 +1141,22 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     const int check_every = 8;
     for (int it = 0; it < max_iter;) {
         for (int k = 0; k < check_every && it < max_iter; k++, it++) {
+#ifdef TB2_PCG_TIMELINE
+            g_tl_it = it - 16;
+#endif
+            TL_MARK(0, st);
             {
                 ProfScope ps(m, kProfPcgVec, 1);
                 k_cg_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->dinv.p, owned, A->q.p, A->z.p, A->p.p, A->s.p, d_x, A->r.p, pvec);
             }
+            TL_MARK(1, st);
             TB2_CHECK(multiply(A->z.p, A->q.p, true));
             ProfScope ps(m, kProfPcgVec, 2);
             TB2_CHECK(scalar_step(0));
+            TL_MARK(6, st);
+#ifdef TB2_PCG_TIMELINE
+            g_tl_it = -1;
+#endif
         }
         TB2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
         TB2_CUDA(cudaStreamSynchronize(st));
@@ -1138,6 +1166,23 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     double hs[kNumScal];
     TB2_CUDA(cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
     TB2_CUDA(cudaStreamSynchronize(st));
+#ifdef TB2_PCG_TIMELINE
+    if (g_tl[7][6]) {
+        const char* names[7] = {"start", "cg_update", "spmv_if", "pack", "pull", "spmv_int", "reduce"};
+        double sum[7] = {0};
+        for (int i = 0; i < 8; i++)
+            for (int k = 1; k < 7; k++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, g_tl[i][0], g_tl[i][k]);
+                sum[k] += ms;
+            }
+        float per = 0;
+        cudaEventElapsedTime(&per, g_tl[0][0], g_tl[7][0]);
+        fprintf(stderr, "pcg timeline (us from iteration start, mean of 8; iteration %.1f us):", per / 7 * 1e3);
+        for (int k = 1; k < 7; k++) fprintf(stderr, " %s %.1f", names[k], sum[k] / 8 * 1e3);
+        fprintf(stderr, "\n");
+    }
+#endif
     if (iterations) *iterations = h.iters;
     if (final_rnorm) *final_rnorm = hs[kRNORM];
     A->pcg_last_converged = !(hs[kRNORM] > atol) || !(hs[kRNORM] > rtol * hs[kR0]); // the device's own stop test
