@@ -448,7 +448,12 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
     it2, rn = A.pcg(b, x, rtol=0.0, atol=0.0, max_iter=min(iters, 48))
     ms_cat, cnt_cat, launches = m.profile_end()
     ms_profiled_iter = (float(ms_cat[3]) + float(ms_cat[4]) + float(ms_cat[6])) / max(it2, 1)
-    launches = 5 * iters + 4  # timed pass: 5 kernels per iteration + set-up (counted, not measured: the graph replays them)
+    if world == 1:
+        launches = 5 * iters + 4  # timed pass: 5 kernels per iteration + set-up (counted, not measured: the graph replays them)
+    else:
+        # distributed iteration: update, interface rows, pack, pull, interior rows, scalar step over peer memory (6 of ours); with the
+        # NCCL exchange: update, interface rows, pack, interior rows, unpack, partial sums, scalars (7 of ours + 2 NCCL kernels)
+        launches = (6 if EXCHANGE == "peer" else 7) * iters + 12
     # configs[2] as one call: NLSolver::Solve on the device (tb2_newton_solve: K1 residual, K3 tangent, Jacobi-PCG to 1e-8, update)
     newton = None
     if world == 1:
