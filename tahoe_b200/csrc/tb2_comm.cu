@@ -87,6 +87,7 @@ struct Comm {
     PeerView pv{};
     bool peer = false;
     DevBuf<unsigned> share_mask; // [n_if] bit r: rank r touches the node
+    DevBuf<unsigned> slot_mask;  // [n_glob] the same by slot of the packed interface vector (0 for slots this rank does not touch)
     DevBuf<unsigned> counter;    // [2]
     unsigned long long xe = 0, se = 0;
     ~Comm()
@@ -170,10 +171,14 @@ __global__ void k_pack_rank_bit(int64_t n_if, const int* __restrict__ slots, dou
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k < n_if) packed[3 * (int64_t)slots[k]] = bit;
 }
-__global__ void k_share_mask(int64_t n_if, const int* __restrict__ slots, const double* __restrict__ packed, unsigned* __restrict__ mask)
+__global__ void k_share_mask(int64_t n_if, const int* __restrict__ slots, const double* __restrict__ packed, unsigned* __restrict__ mask,
+                             unsigned* __restrict__ slot_mask)
 {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < n_if) mask[k] = (unsigned)packed[3 * (int64_t)slots[k]];
+    if (k >= n_if) return;
+    const unsigned mk = (unsigned)packed[3 * (int64_t)slots[k]];
+    mask[k] = mk;
+    slot_mask[slots[k]] = mk;
 }
 // publish the interface entries of an equation vector (prescribed dofs: 0) into this rank's window and raise the peers' flags
 __global__ void __launch_bounds__(256) k_peer_pack_eq(int64_t n_if, const int* __restrict__ nodes, const int* __restrict__ slots,
@@ -244,6 +249,7 @@ bool comm_plan(tb2_mesh* m, CommPlan* out)
     out->peer = c->peer;
     out->pv = c->pv;
     out->share_mask = c->share_mask.p;
+    out->slot_mask = c->slot_mask.p;
     out->counter = c->counter.p;
     out->epoch = &c->xe;
     out->sepoch = &c->se;
@@ -478,6 +484,8 @@ int tb2_comm_peer_import(tb2_mesh* m, const char* h_handles)
     // the sharers of every interface node: each rank adds its bit 2^rank on the slots it touches (exact in a double)
     const int T = 256;
     TB2_CUDA(c->share_mask.alloc(c->n_if > 0 ? c->n_if : 1));
+    TB2_CUDA(c->slot_mask.alloc(c->n_glob > 0 ? c->n_glob : 1));
+    TB2_CUDA(cudaMemsetAsync(c->slot_mask.p, 0, (c->n_glob > 0 ? c->n_glob : 1) * sizeof(unsigned), m->stream));
     TB2_CUDA(c->counter.alloc(2));
     TB2_CUDA(cudaMemsetAsync(c->counter.p, 0, 2 * sizeof(unsigned), m->stream));
     TB2_CUDA(cudaMemsetAsync(c->packed.p, 0, 3 * (c->n_glob > 0 ? c->n_glob : 1) * sizeof(double), m->stream));
@@ -486,7 +494,7 @@ int tb2_comm_peer_import(tb2_mesh* m, const char* h_handles)
         const int r = g_nccl.AllReduce(c->packed.p, c->packed.p, (size_t)(3 * c->n_glob), kNcclFloat64, kNcclSum, c->comm, m->stream);
         if (r) return nccl_fail(r, "ncclAllReduce(sharer masks)");
     }
-    if (c->n_if) k_share_mask<<<(unsigned)((c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->slots.p, c->packed.p, c->share_mask.p);
+    if (c->n_if) k_share_mask<<<(unsigned)((c->n_if + T - 1) / T), T, 0, m->stream>>>(c->n_if, c->slots.p, c->packed.p, c->share_mask.p, c->slot_mask.p);
     TB2_CUDA(cudaGetLastError());
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     c->pv = pv;

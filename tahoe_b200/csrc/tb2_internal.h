@@ -87,6 +87,7 @@ struct CommPlan {
     bool peer = false;
     PeerView pv{};
     const unsigned* share_mask = nullptr; // [n_if] sharers of every interface node
+    const unsigned* slot_mask = nullptr;  // [n_glob] the same by slot
     unsigned* counter = nullptr;          // last-CTA counter of the publishing kernel
     unsigned long long* epoch = nullptr;  // the communicator's interface-exchange epoch (host side, advanced per exchange)
     unsigned long long* sepoch = nullptr; // ... and its scalar-exchange epoch
@@ -200,6 +201,7 @@ struct tb2_matrix {
     tb2::DevBuf<double> scal;     // reduction scalars
     tb2::DevBuf<double> partial;  // per-block partial sums
     tb2::DevBuf<unsigned char> eq_owned; // multi-GPU: 1 if this rank owns the equation's node (dot products count it once)
+    tb2::DevBuf<int> eq_xidx;            // multi-GPU over peer memory: entry of the exchange buffer an interface equation maps to, -1 elsewhere
     tb2::DevBuf<double> s, partial_if;   // multi-GPU PCG: s = A p of the single-reduction recurrence; (A u, u) partials of the interface rows
     tb2::DevBuf<double> bi_rhat, bi_v, bi_s, bi_t; // BiCGStab work vectors (tb2_matrix_bicgstab), allocated on first use
     tb2::DevBuf<int> grp_split;          // row groups of interface nodes first, then the others

@@ -154,10 +154,12 @@ __global__ void k_elem_adjpos(int64_t ne, int64_t stride, const int* __restrict_
 // A matrix without node structure (tb2_matrix_create_csr) uses groups of one row.  Persistent grid: warp w of block b walks
 // groups b*W+w, +gridDim*W, ...; the p.Ap partial of a block is accumulated in that fixed order (deterministic).
 // grp[g] = first row | (rows-1) << 30.
-template <bool WITH_DOT>
-__global__ void __launch_bounds__(256, 6) k_spmv(int64_t ngroups, const int* __restrict__ grp, const long long* __restrict__ rowptr,
-                                                 const int* __restrict__ colind, const double* __restrict__ val, const double* __restrict__ x,
-                                                 double* __restrict__ y, double* __restrict__ partial, const int* __restrict__ done)
+template <bool WITH_DOT, bool PUBLISH>
+__device__ __forceinline__ void spmv_groups(int64_t ngroups, const int* __restrict__ grp, const long long* __restrict__ rowptr,
+                                            const int* __restrict__ colind, const double* __restrict__ val, const double* __restrict__ x,
+                                            double* __restrict__ y, double* __restrict__ partial, const int* __restrict__ done,
+                                            const int* __restrict__ xidx, double* __restrict__ xout, int64_t npublish,
+                                            const PeerView* pv, unsigned long long epoch, unsigned* counter)
 {
     if (WITH_DOT && done && *done) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -209,6 +211,20 @@ __global__ void __launch_bounds__(256, 6) k_spmv(int64_t ngroups, const int* __r
             y[r0] = s0;
             if (nr > 1) y[r0 + 1] = s1;
             if (nr > 2) y[r0 + 2] = s2;
+            if (PUBLISH && g < npublish) {
+                // a row group of an interface node (they come first in the group list): this rank's partial also goes into its exchange
+                // window; the warp that completes the last of them raises the arrival flag in every peer's window
+                xout[xidx[r0]] = s0;
+                if (nr > 1) xout[xidx[r0 + 1]] = s1;
+                if (nr > 2) xout[xidx[r0 + 2]] = s2;
+                __threadfence();
+                if (atomicAdd(counter, 1u) == (unsigned)(npublish - 1)) {
+                    *counter = 0;
+                    __threadfence_system();
+                    for (int r = 0; r < pv->nranks; r++)
+                        if (r != pv->rank) peer_st_release((unsigned long long*)(pv->win[r] + kPeerFlagsOff) + pv->rank, epoch);
+                }
+            }
             if (WITH_DOT) {
                 dot += s0 * x[r0];
                 if (nr > 1) dot += s1 * x[r0 + 1];
@@ -226,6 +242,34 @@ __global__ void __launch_bounds__(256, 6) k_spmv(int64_t ngroups, const int* __r
             partial[blockIdx.x] = t;
         }
     }
+}
+template <bool WITH_DOT>
+__global__ void __launch_bounds__(256, 6) k_spmv(int64_t ngroups, const int* __restrict__ grp, const long long* __restrict__ rowptr,
+                                                 const int* __restrict__ colind, const double* __restrict__ val, const double* __restrict__ x,
+                                                 double* __restrict__ y, double* __restrict__ partial, const int* __restrict__ done)
+{
+    spmv_groups<WITH_DOT, false>(ngroups, grp, rowptr, colind, val, x, y, partial, done, nullptr, nullptr, 0, nullptr, 0ull, nullptr);
+}
+// The SpMV of a distributed solve over peer memory (tb2_peer.cuh), multiply and exchange in one kernel: the group list holds the
+// rows of the interface nodes first; their partials A_loc u go to y AND into this rank's exchange window, and the warp that
+// completes the last of them raises the arrival flag in every peer's window while the grid goes on with the interior rows.
+// The sharers pull and sum the partials inside the next vector update (k_cg_update<true>), a whole SpMV later.
+__global__ void __launch_bounds__(256, 6) k_spmv_publish(int64_t ngroups, int64_t ngroups_if, const int* __restrict__ grp,
+                                                         const long long* __restrict__ rowptr, const int* __restrict__ colind,
+                                                         const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+                                                         double* __restrict__ partial, const int* __restrict__ done,
+                                                         const int* __restrict__ xidx, const PeerView pv, unsigned long long epoch,
+                                                         unsigned* counter)
+{
+    if (*done) { // uniform over the grid and over the ranks (it derives from all-reduced scalars): no rows, but the peers' pull of this
+                 // epoch still waits for the arrival flag
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (int r = 0; r < pv.nranks; r++)
+                if (r != pv.rank) peer_st_release((unsigned long long*)(pv.win[r] + kPeerFlagsOff) + pv.rank, epoch);
+        return;
+    }
+    spmv_groups<true, true>(ngroups, grp, rowptr, colind, val, x, y, partial, done, xidx, peer_data(pv, pv.rank, epoch), ngroups_if, &pv, epoch,
+                            counter);
 }
 // row groups of a mesh-derived matrix: one group per node with active dofs (flag/scan/compact); generic: one per row
 __global__ void k_group_flags(int64_t nn, const int* __restrict__ eqnos, int* __restrict__ flag)
@@ -894,6 +938,14 @@ __global__ void k_group_interface_flag(int64_t ng, const int* __restrict__ grp, 
     const int64_t r0 = (unsigned)grp[g] & 0x3fffffffu;
     flag[g] = node_slot[eq_node[r0] / 3] >= 0 ? 1 : 0;
 }
+// entry of the exchange buffer (3 slot + dof) of every equation of an interface node, -1 elsewhere
+__global__ void k_eq_exchange_index(int64_t neq, const int* __restrict__ eq_node, const int* __restrict__ node_slot, int* __restrict__ xidx)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= neq) return;
+    const int q = eq_node[i], slot = node_slot[q / 3];
+    xidx[i] = slot >= 0 ? 3 * slot + q % 3 : -1;
+}
 // p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = dinv r ; partials (r,u), (r,r) over owned equations
 __global__ void __launch_bounds__(256) k_cg_update(int64_t n, const double* __restrict__ scal, const PcgCtl* __restrict__ ctl,
                                                   const double* __restrict__ dinv, const unsigned char* __restrict__ owned,
@@ -1124,19 +1176,26 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
     TB2_CHECK(multiply(A->z.p, A->q.p, true));
     // (r,u), (r,r), (A u, u): this rank's partials, summed over the ranks, alpha and beta -- one CTA over peer memory, else
     // sum + ncclAllReduce + scalar kernel
-    auto scalar_step = [&](int first) -> int {
+    auto scalar_step = [&](int first, bool with_pif) -> int {
+        const int nif = (with_pif && ng_if > 0) ? (int)sg_if : 0; // partials of a separate interface-row launch
         if (overlap && cp.peer) {
-            k_cg_reduce_peer<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, scal, ctl, rtol, atol, max_iter,
+            k_cg_reduce_peer<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, nif, pif, (int)sg, pint, scal, ctl, rtol, atol, max_iter,
                                                 first, cp.pv, ++*cp.sepoch);
             return TB2_OK;
         }
-        k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, ng_if > 0 ? (int)sg_if : 0, pif, (int)sg, pint, red, first ? nullptr : ctl);
+        k_cg_sum<<<1, 1024, 0, st>>>((int)vec_blocks, pvec, nif, pif, (int)sg, pint, red, first ? nullptr : ctl);
         TB2_CHECK(comm_allreduce_scalars(m, red, 3));
         k_cg_scalars<<<1, 1, 0, st>>>(red, scal, ctl, rtol, atol, max_iter, first);
         return TB2_OK;
     };
-    TB2_CHECK(scalar_step(1));
+    TB2_CHECK(scalar_step(1, true));
     TB2_CUDA(cudaGetLastError());
+    // over peer memory the SpMV publishes the interface rows itself (k_spmv_publish) and the pull runs beside the scalar step
+    const bool fused = overlap && cp.peer && ng_if > 0;
+    if (fused && !A->eq_xidx.p) {
+        TB2_CUDA(A->eq_xidx.alloc(n));
+        k_eq_exchange_index<<<nb1, 256, 0, st>>>(n, A->eqs->eq_node.p, cp.node_slot, A->eq_xidx.p);
+    }
     PcgCtl h{};
     const int check_every = 8;
     for (int it = 0; it < max_iter;) {
@@ -1150,9 +1209,28 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
                 k_cg_update<<<vec_blocks, 256, 0, st>>>(n, scal, ctl, A->dinv.p, owned, A->q.p, A->z.p, A->p.p, A->s.p, d_x, A->r.p, pvec);
             }
             TL_MARK(1, st);
-            TB2_CHECK(multiply(A->z.p, A->q.p, true));
-            ProfScope ps(m, kProfPcgVec, 2);
-            TB2_CHECK(scalar_step(0));
+            if (fused) {
+                // one SpMV launch: the rows of the interface nodes come first in the group list and are published from inside the kernel
+                // (k_spmv_publish); once it is done the pull of the sharers' partials (communicator's stream) runs beside the scalar step
+                ++*cp.epoch;
+                {
+                    ProfScope ps(m, kProfSpmv, 1, st);
+                    k_spmv_publish<<<sg, 256, 0, st>>>(A->ngroups, ng_if, A->grp_split.p, A->rowptr.p, A->colind.p, A->val.p, A->z.p, A->q.p, pint,
+                                                      &ctl->done, A->eq_xidx.p, cp.pv, *cp.epoch, cp.counter);
+                }
+                TL_MARK(5, st);
+                TB2_CUDA(cudaEventRecord(cp.ev_packed, st));
+                TB2_CUDA(cudaStreamWaitEvent(cp.stream, cp.ev_packed, 0));
+                TB2_CHECK(comm_unpack_eq(m, eqnos, A->q.p, cp.stream));
+                TL_MARK(4, cp.stream);
+                TB2_CUDA(cudaEventRecord(cp.ev_reduced, cp.stream));
+            } else
+                TB2_CHECK(multiply(A->z.p, A->q.p, true));
+            {
+                ProfScope ps(m, kProfPcgVec, 2);
+                TB2_CHECK(scalar_step(0, !fused));
+            }
+            if (fused) TB2_CUDA(cudaStreamWaitEvent(st, cp.ev_reduced, 0)); // the next update reads the pulled rows of w
             TL_MARK(6, st);
 #ifdef TB2_PCG_TIMELINE
             g_tl_it = -1;
@@ -1173,7 +1251,7 @@ static int pcg_distributed(tb2_matrix* A, const double* d_b, double* d_x, double
         for (int i = 0; i < 8; i++)
             for (int k = 1; k < 7; k++) {
                 float ms = 0;
-                cudaEventElapsedTime(&ms, g_tl[i][0], g_tl[i][k]);
+                if (g_tl[i][k] && cudaEventQuery(g_tl[i][k]) == cudaSuccess) cudaEventElapsedTime(&ms, g_tl[i][0], g_tl[i][k]);
                 sum[k] += ms;
             }
         float per = 0;
