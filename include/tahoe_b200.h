@@ -73,7 +73,8 @@ typedef struct tb2_group     tb2_group;     /* one continuum-solid element group
 typedef struct tb2_equations tb2_equations; /* equation numbers + sparsity (FieldT::fEqnos, MSRBuilderT) */
 typedef struct tb2_matrix    tb2_matrix;    /* device CSR global matrix (GlobalMatrixT subclass; MSRMatrixT semantics) */
 typedef struct tb2_geom      tb2_geom;      /* a parsed TahoeII .geom file (host memory) */
-typedef struct tb2_traction  tb2_traction;  /* natural_bc traction cards of one element group (ContinuumElementT::fTractionList) */
+typedef struct tb2_traction  tb2_traction;
+typedef struct tb2_contact   tb2_contact;   /* contact_3D_penalty: active striker-facet pairs of one PenaltyContact3DT group */  /* natural_bc traction cards of one element group (ContinuumElementT::fTractionList) */
 typedef struct tb2_explicit  tb2_explicit;  /* d, v, a, lumped mass, BCs on device: FieldT + nExplicitCD + DiagonalMatrixT */
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -201,6 +202,26 @@ int tb2_traction_create(tb2_mesh* mesh, int64_t ncards, const int32_t* h_elem, c
 int tb2_traction_destroy(tb2_traction* traction);
 int tb2_traction_form(tb2_traction* traction, double scale, int accumulate, double* d_f);
 int tb2_traction_form_host(tb2_traction* traction, double scale, int accumulate, double* h_f);
+
+/* ---- contact_3D_penalty force: PenaltyContact3DT::RHSDriver (PenaltyContact3DT.cpp:262-500).
+ * The neighbour search stays host code (Contact3DT::SetActiveInteractions, Contact3DT.cpp:100-175; it runs at relaxation points, not
+ * per step); the host hands over its result with tb2_contact_set_pairs: h_pairs[npairs][4] = the three facet nodes and the striker
+ * (0-based; the rows of the group's connectivity), h_striker_area[npairs] = ContactT::fStrikerArea of each pair's striker.
+ * tb2_contact_form evaluates every pair on X + constKd u (constKd = eIntegratorT::FormKd): for a closed gap h = n . (x_s - centroid) < 0
+ * the penalty force -K h area dh/du, velocity-based regularised Coulomb friction (friction_coefficient > 0) and normal viscous damping
+ * (viscous_damping > 0), both from d_v[nn][3]; the pairs' 12-vectors are summed into d_f[nn][3] in pair order, the order of
+ * ElementSupportT::AssembleRHS in the reference's loop (accumulate != 0: added to d_f, else d_f is overwritten).  The sign is that of
+ * the residual the reference assembles.  tb2_contact_tracking returns what ContactT::SetTrackingData receives: the number of pairs in
+ * contact and the deepest penetration (<= 0) of the last evaluation.  The slip-based friction of static analyses (per-striker history,
+ * PenaltyContact3DT.cpp:427-447) and the contact tangent (LHSDriver) are not on the device. */
+int tb2_contact_create(tb2_mesh* mesh, double penalty_stiffness, double friction_coefficient, double friction_epsilon_velocity,
+                       double viscous_damping, tb2_contact** contact);
+int tb2_contact_destroy(tb2_contact* contact);
+int tb2_contact_set_pairs(tb2_contact* contact, int64_t npairs, const int32_t* h_pairs, const double* h_striker_area);
+int tb2_contact_form(tb2_contact* contact, double constKd, const double* d_u, const double* d_v /* NULL without friction / damping */,
+                     int accumulate, double* d_f);
+int tb2_contact_form_host(tb2_contact* contact, double constKd, const double* h_u, const double* h_v, int accumulate, double* h_f);
+int tb2_contact_tracking(tb2_contact* contact, int* num_contact, double* h_max);
 
 /* ---- explicit central difference (nExplicitCD.cpp:72-139, DiagonalMatrixT.cpp:267-323, FieldT.cpp:531-556) */
 int tb2_explicit_create(tb2_group* group, tb2_explicit** ex); /* forms and inverts the lumped mass */

@@ -19,6 +19,9 @@
  *   after the last CloseStep, before the extra evaluations above), iters (SolverT::IterationNumber per step), iters_ic
  *   (the same after FEManagerT::InitialCondition),
  *   timing (--time: wall seconds of the step loop, steps, elements)
+ *   --contact: for the first contact_3D_penalty group, at every dumped step k: cpairs_<k> (facet nodes 1-3 + striker, 0-based),
+ *   carea_<k> (the pair's striker area), crhs_<k> (that group's FormRHS alone, active equations) and once cparams
+ *   (penalty stiffness, friction coefficient, friction epsilon, viscous damping)
  */
 #include <sys/stat.h>
 #include <chrono>
@@ -37,6 +40,7 @@
 #include "MSRMatrixT.h"
 #include "NodeManagerT.h"
 #include "ParameterListT.h"
+#include "PenaltyContact3DT.h"
 #include "RaggedArray2DT.h"
 #include "SolverT.h"
 #include "TimeManagerT.h"
@@ -77,18 +81,48 @@ struct MSRPeek : public MSRMatrixT {
     }
 };
 
+/* exposes the protected contact data (ContactT.h:145-156, PenaltyContact3DT.h) */
+struct ContactPeek : public PenaltyContact3DT {
+    static void dump(PenaltyContact3DT& g, FEManagerT* tahoe, int solver_group, int k)
+    {
+        ContactPeek& p = static_cast<ContactPeek&>(g);
+        char buf[64];
+        const iArray2DT& pairs = *p.fConnectivities[0]; /* the active striker-facet pairs (Contact3DT::SetActiveInteractions, Contact3DT.cpp:100-175) */
+        snprintf(buf, sizeof buf, "cpairs_%d", k);
+        put(buf, "i4", pairs.Pointer(), 4, pairs.MajorDim(), pairs.MinorDim());
+        std::vector<double> area((size_t)pairs.MajorDim());
+        for (int i = 0; i < pairs.MajorDim(); i++) area[i] = p.fStrikerArea[p.fStrikerTags_map.Map(pairs(i, pairs.MinorDim() - 1))];
+        snprintf(buf, sizeof buf, "carea_%d", k);
+        put(buf, "f8", area.data(), 8, (long)area.size(), 0);
+        double prm[4] = {p.fK, p.fMu, p.fFrictionEps, p.fViscousDamping};
+        put("cparams", "f8", prm, 8, 4, 0);
+        /* the group's own residual contribution at the current state */
+        SolverT* solver = tahoe->Solver(solver_group);
+        dArrayT& rhs = const_cast<dArrayT&>(tahoe->RHS(solver_group));
+        dArrayT keep(rhs);
+        rhs = 0.0;
+        solver->UnlockRHS();
+        g.FormRHS();
+        solver->LockRHS();
+        snprintf(buf, sizeof buf, "crhs_%d", k);
+        put1(buf, rhs);
+        rhs = keep;
+    }
+};
+
 int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: tahoe_dump input.xml outdir [--every N] [--fint] [--lhs] [--time]\n"); return 2; }
     StringT input_file(argv[1]);
     g_out = argv[2];
     int every = 0;
-    bool want_fint = false, want_lhs = false, want_time = false;
+    bool want_fint = false, want_lhs = false, want_time = false, want_contact = false;
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--every") && i + 1 < argc) every = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--fint")) want_fint = true;
         else if (!strcmp(argv[i], "--lhs")) want_lhs = true;
         else if (!strcmp(argv[i], "--time")) want_time = true;
+        else if (!strcmp(argv[i], "--contact")) want_contact = true;
     }
     mkdir(g_out.c_str(), 0755);
     g_manifest = fopen((g_out + "/manifest.txt").c_str(), "w");
@@ -130,6 +164,9 @@ int main(int argc, char** argv)
             put("conn", "i4", all.data(), 4, nen ? (long)all.size() / nen : 0, nen);
         }
         put2("eqnos", field->Equations());
+        PenaltyContact3DT* contact = NULL;
+        if (want_contact)
+            for (int g = 0; g < tahoe->NumElementGroups() && !contact; g++) contact = dynamic_cast<PenaltyContact3DT*>(tahoe->ElementGroup(g));
 
         auto dump_fields = [&](int k) {
             char buf[64];
@@ -158,7 +195,10 @@ int main(int argc, char** argv)
             iters.push_back(tahoe->Solver(solver_group)->IterationNumber());
             if (error != ExceptionT::kNoError) break;
             int k = tm->StepNumber();
-            if ((every > 0 && k % every == 0) || k == tm->NumberOfSteps()) dump_fields(k);
+            if ((every > 0 && k % every == 0) || k == tm->NumberOfSteps()) {
+                dump_fields(k);
+                if (contact) ContactPeek::dump(*contact, tahoe, solver_group, k);
+            }
         }
         auto t1 = std::chrono::steady_clock::now();
         if (error != ExceptionT::kNoError) {

@@ -1550,6 +1550,99 @@ void orc_explicit_material_stress(const orc_material_t* m, const double* F, doub
     else xs_neo_hookean(m, F, sig);
 }
 
+/* ---- contact_3D_penalty ------------------------------------------------------------------------------------- */
+/* Contact3DT::Set_dn_du (Contact3DT.cpp:176-220): d(a x b)/du for a = x2 - x1, b = x3 - x1, as a 3 x 12 matrix stored by columns
+ * (dMatrixT is column-major); the striker's columns are zero */
+static void contact_dn_du(const double* x1, const double* x2, const double* x3, double dn[12][3])
+{
+    const double col[12][3] = {
+        {0, -x2[2] + x3[2], x2[1] - x3[1]}, {x2[2] - x3[2], 0, -x2[0] + x3[0]}, {-x2[1] + x3[1], x2[0] - x3[0], 0},
+        {0, x1[2] - x3[2], -x1[1] + x3[1]}, {-x1[2] + x3[2], 0, x1[0] - x3[0]}, {x1[1] - x3[1], -x1[0] + x3[0], 0},
+        {0, -x1[2] + x2[2], x1[1] - x2[1]}, {x1[2] - x2[2], 0, -x1[0] + x2[0]}, {-x1[1] + x2[1], x1[0] - x2[0], 0},
+        {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    memcpy(dn, col, sizeof col);
+}
+
+int orc_contact_force(int64_t npairs, const int32_t* pairs, const double* area, double K, double mu, double eps, double visc, double constKd,
+                      int64_t nn, const double* X, const double* u, const double* v, double* f, double* h_max_out)
+{
+    int num_contact = 0;
+    double h_max = 0.0;
+    (void)nn;
+    for (int64_t p = 0; p < npairs; p++) {
+        const int32_t* nd = pairs + 4 * p;
+        double x[4][3]; /* PenaltyContact3DT.cpp:297-311: X + constKd u of facet nodes 1-3 and the striker */
+        for (int a = 0; a < 4; a++)
+            for (int i = 0; i < 3; i++) x[a][i] = X[3 * (int64_t)nd[a] + i] + constKd * u[3 * (int64_t)nd[a] + i];
+        double a_[3], b_[3], n[3], c[3];
+        for (int i = 0; i < 3; i++) { a_[i] = x[1][i] - x[0][i]; b_[i] = x[2][i] - x[0][i]; }
+        n[0] = a_[1] * b_[2] - a_[2] * b_[1];
+        n[1] = a_[2] * b_[0] - a_[0] * b_[2];
+        n[2] = a_[0] * b_[1] - a_[1] * b_[0];
+        const double mag = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        for (int i = 0; i < 3; i++) n[i] /= mag;
+        for (int i = 0; i < 3; i++) c[i] = x[3][i] - (x[0][i] + x[1][i] + x[2][i]) / 3.0;
+        const double h = n[0] * c[0] + n[1] * c[1] + n[2] * c[2];
+        if (!(h < 0.0)) continue; /* :325 */
+        num_contact++;
+        if (h < h_max) h_max = h;
+        const double dphi = -K * h * area[p]; /* :332-333 */
+        double rhs[12];
+        /* fdc_du^T n (:136-172: -1/3 on the facet nodes, 1 on the striker), scaled by dphi */
+        for (int a = 0; a < 3; a++)
+            for (int i = 0; i < 3; i++) rhs[3 * a + i] = dphi * (-(1.0 / 3.0) * n[i]);
+        for (int i = 0; i < 3; i++) rhs[9 + i] = dphi * n[i];
+        /* d_normal (:339-344): V1_j = c . (n n^T - 1) dn_du[:, j]; RHS += -dphi / mag V1 */
+        double dn[12][3];
+        contact_dn_du(x[0], x[1], x[2], dn);
+        for (int j = 0; j < 12; j++) {
+            const double nd_ = n[0] * dn[j][0] + n[1] * dn[j][1] + n[2] * dn[j][2];
+            double v1 = 0.0;
+            for (int i = 0; i < 3; i++) v1 += (n[i] * nd_ - dn[j][i]) * c[i];
+            rhs[j] += -dphi / mag * v1;
+        }
+        if (v) {
+            double vs[3], vf[3];
+            for (int i = 0; i < 3; i++) {
+                vs[i] = v[3 * (int64_t)nd[3] + i];
+                vf[i] = (v[3 * (int64_t)nd[0] + i] + v[3 * (int64_t)nd[1] + i] + v[3 * (int64_t)nd[2] + i]) / 3.0;
+            }
+            if (mu > 0.0) { /* explicit branch, :375-426: f_t = -mu |f_n| v_t / sqrt(|v_t|^2 + eps^2) */
+                double vr[3], vt[3];
+                for (int i = 0; i < 3; i++) vr[i] = vs[i] - vf[i];
+                const double vrn = vr[0] * n[0] + vr[1] * n[1] + vr[2] * n[2];
+                for (int i = 0; i < 3; i++) vt[i] = vr[i] - vrn * n[i];
+                const double vt2 = vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2];
+                const double inv_smooth = 1.0 / sqrt(vt2 + eps * eps);
+                const double s = -mu * fabs(dphi) * inv_smooth;
+                const double third = 1.0 / 3.0;
+                for (int i = 0; i < 3; i++) {
+                    const double ft = s * vt[i];
+                    rhs[i] += -ft * third;
+                    rhs[3 + i] += -ft * third;
+                    rhs[6 + i] += -ft * third;
+                    rhs[9 + i] += ft;
+                }
+            }
+            if (visc > 0.0) { /* :463-488: f = -c v_n area along n */
+                const double vrn = (vs[0] - vf[0]) * n[0] + (vs[1] - vf[1]) * n[1] + (vs[2] - vf[2]) * n[2];
+                const double fv = -visc * vrn * area[p];
+                const double third = 1.0 / 3.0;
+                for (int i = 0; i < 3; i++) {
+                    rhs[i] += -fv * n[i] * third;
+                    rhs[3 + i] += -fv * n[i] * third;
+                    rhs[6 + i] += -fv * n[i] * third;
+                    rhs[9 + i] += fv * n[i];
+                }
+            }
+        }
+        for (int a = 0; a < 4; a++) /* SolverT::AssembleRHS, pair by pair */
+            for (int i = 0; i < 3; i++) f[3 * (int64_t)nd[a] + i] += rhs[3 * a + i];
+    }
+    if (h_max_out) *h_max_out = h_max;
+    return num_contact;
+}
+
 /* ---- natural_bc tractions: ContinuumElementT::ApplyTractionBC (ContinuumElementT.cpp:514-665) on Hex8 facets ------------------
  * facet nodes HexahedronT::NodesOnFacet (HexahedronT.cpp:1913-1918); 4-node quad facet shape with the 2x2 rule the hexahedron gets
  * (DomainIntegrationT.cpp:117-131; QuadT.cpp:75-81,379-389, weights 1); surface Jacobian |x,r x x,s| on the INITIAL coordinates

@@ -135,6 +135,16 @@ int orc_assemble_mass(double density, int mass_type, double constM, int64_t ne, 
 int orc_material_set_spline(orc_material_t* m, int n, const double* x, const double* y, int fixity);
 /* the hardening function and its derivative (known-answer checks) */
 void orc_hardening(const orc_material_t* m, double alpha, double* K, double* dK);
+/* SURVEY 8(f)-4, contact_3D_penalty: PenaltyContact3DT::RHSDriver (PenaltyContact3DT.cpp:262-500) over a given list of active
+ * striker-facet pairs (Contact3DT::SetActiveInteractions builds it: three facet nodes, then the striker; 0-based).  Per pair with
+ * penetration h = n . (x_s - centroid) < 0 on the configuration X + constKd u: the penalty force dphi dh/du with dphi = -K h area
+ * (Contact3DT::Set_dn_du for the normal's variation, Contact3DT.cpp:176-220), velocity-based regularised Coulomb friction
+ * (mu > 0 and v given) and normal viscous damping (visc > 0 and v given), each split -1/3 on the facet nodes and +1 on the striker.
+ * f[nn][3] receives the pairs' 12-vectors added in pair order (SolverT::AssembleRHS); returns the number of pairs in contact,
+ * *h_max the deepest penetration (<= 0). */
+int orc_contact_force(int64_t npairs, const int32_t* pairs /*[npairs][4]*/, const double* area /*[npairs]*/, double K, double mu, double eps,
+                      double visc, double constKd, int64_t nn, const double* X, const double* u, const double* v /* or NULL */, double* f,
+                      double* h_max);
 /* natural_bc tractions (ContinuumElementT::ApplyTractionBC, ContinuumElementT.cpp:514-665): f[nn][3] += consistent nodal forces of
  * ncards facet cards (elem, facet 0-based; tract[card][4][3] nodal traction vectors in facet-node order; coord_system 0 global, 1 local) */
 int orc_traction_force(int64_t ncards, const int32_t* elem, const int32_t* facet, const int32_t* conn, const double* X,

@@ -44,7 +44,8 @@ tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_copy_diagonal_host tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
-tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_secant_search_host""".split()
+tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_secant_search_host
+tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking""".split()
 
 
 class Tb2Error(RuntimeError):
@@ -400,6 +401,36 @@ class Traction(_Handle):
         f = np.zeros((self.mesh.nn, 3)) if out is None else _f64(out)
         _chk(lib().tb2_traction_form_host(self.h, C.c_double(scale), 0 if out is None else 1, _p(f)))
         return f
+
+
+class Contact(_Handle):
+    """contact_3D_penalty force of one PenaltyContact3DT group: parameters at construction, the active striker-facet pairs
+    (three facet nodes + striker, 0-based) and the strikers' areas from the host search with set_pairs"""
+    _destroy = "tb2_contact_destroy"
+
+    def __init__(self, mesh, penalty_stiffness, friction_coefficient=0.0, friction_epsilon=1.0e-6, viscous_damping=0.0):
+        self.mesh = mesh
+        self._init_handle(mesh)
+        _chk(lib().tb2_contact_create(mesh.h, C.c_double(penalty_stiffness), C.c_double(friction_coefficient), C.c_double(friction_epsilon),
+                                      C.c_double(viscous_damping), C.byref(self.h)))
+
+    def set_pairs(self, pairs, area):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 4)
+        area = _f64(area)
+        _chk(lib().tb2_contact_set_pairs(self.h, C.c_int64(pairs.shape[0]), _p(pairs), _p(area)))
+
+    def form_host(self, u, v=None, constKd=1.0, out=None):
+        """nodal forces [nn][3] (residual sign); added to `out` when given"""
+        f = np.zeros((self.mesh.nn, 3)) if out is None else _f64(out)
+        u = _f64(u)
+        vv = None if v is None else _f64(v)
+        _chk(lib().tb2_contact_form_host(self.h, C.c_double(constKd), _p(u), _p(vv) if vv is not None else None, 0 if out is None else 1, _p(f)))
+        return f
+
+    def tracking(self):
+        n, h = C.c_int(0), C.c_double(0.0)
+        _chk(lib().tb2_contact_tracking(self.h, C.byref(n), C.byref(h)))
+        return n.value, h.value
 
 
 class Explicit(_Handle):

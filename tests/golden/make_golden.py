@@ -127,6 +127,42 @@ def synthetic_case(name, n, desc, flags, jitter=0.1):
     shutil.rmtree(work)
 
 
+def contact_case(name, rel_xml, flags, edits=()):
+    """SURVEY 8(f)-4, contact_3D_penalty (PenaltyContact3DT): one of the reference's own contact inputs, optionally with text edits
+    (attributes added to the contact tag, fewer steps), run through tahoe_dump --contact.  The fixture holds what the force needs --
+    coordinates, equation numbers, d (and v) at the dumped steps, the active striker-facet pairs with the striker areas as the
+    reference's own search left them, the parameters -- and the contact group's own FormRHS at those states."""
+    src_dir = os.path.dirname(os.path.join(REF, rel_xml))
+    work = tempfile.mkdtemp(prefix="contact_")
+    shutil.copytree(os.path.dirname(src_dir), os.path.join(work, "lvl"), ignore=shutil.ignore_patterns("benchmark", "*.run", "*.out", "*.exo"))
+    xml = os.path.join(work, "lvl", os.path.basename(src_dir), os.path.basename(rel_xml))
+    text = open(xml).read()
+    for old, new in edits:
+        assert old in text, old
+        text = text.replace(old, new)
+    open(xml, "w").write(text)
+    out = tempfile.mkdtemp(prefix="dump_")
+    r = subprocess.run([DUMP, os.path.basename(xml), out] + flags + ["--contact"], cwd=os.path.dirname(xml), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-3000:])
+        raise RuntimeError("tahoe_dump failed for " + name)
+    dump = load_dump(out)
+    shutil.rmtree(out)
+    shutil.rmtree(work)
+    steps = sorted(int(k.split("_")[1]) for k in dump if k.startswith("cpairs_"))
+    payload = {"source": np.array("benchmark_XML/" + rel_xml + ("; edits: " + json.dumps(edits) if edits else "")),
+               "steps": np.asarray(steps, np.int32)}
+    keep = ("coords", "eqnos", "cparams") + tuple("%s_%d" % (a, k) for k in steps for a in ("d", "v", "cpairs", "carea", "crhs"))
+    for k in keep:
+        if k in dump:
+            payload["ref_" + k] = dump[k]
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **payload)
+    npairs = [int(dump["cpairs_%d" % k].shape[0]) for k in steps]
+    print("%-28s %7.1f kB  steps %s pairs %s" % (name, os.path.getsize(path) / 1024, steps, npairs))
+
+
 RAMP = [(0.0, 0.0), (1.0, 1.0)]
 RAMP_FAST = [(0.0, 0.0), (0.4, 1.0), (10.0, 1.0)]
 CLAMP_X0 = [{"nodeset": 1, "dof": d, "type": "fixed", "schedule": 0, "value": 0.0} for d in (1, 2, 3)]
@@ -168,6 +204,14 @@ def main():
             reference_case(name, rel, flags)
     if want("ref_beam_pcg"):
         pcg_history("ref_beam_pcg", "level.0/3D.elastostatic/beam.PCG.xml")
+    # contact_3D_penalty: the reference's static two-cube case as shipped, and its explicit sliding-friction case cut to 1200 steps with
+    # viscous damping switched on as well (all three force terms of PenaltyContact3DT::RHSDriver active, velocity-based friction)
+    if want("ref_contact_cubes_1"):
+        contact_case("ref_contact_cubes_1", "level.2/contact_simple/cubes.1.xml", ["--every", "1"])
+    if want("ref_contact_sliding_friction"):
+        contact_case("ref_contact_sliding_friction", "level.5/explicit_benchmark/vectorized_cubes_friction.xml", ["--every", "300"],
+                     edits=(('output_format="ExodusII"', ""), ('num_steps="5000"', 'num_steps="1200"'),
+                            ('friction_epsilon_velocity="0.001">', 'friction_epsilon_velocity="0.001" viscous_damping="20.0">')))
 
     # ---- synthetic jittered cubes ----
     kstv = {"type": "small_strain_StVenant", "density": 1.0, "E": 100.0, "nu": 0.25}

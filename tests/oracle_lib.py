@@ -307,6 +307,22 @@ def traction_force(conn, X, elem, facet, tract, coord_system="global", scale=1.0
     return f
 
 
+def contact_force(pairs, area, X, u, v=None, K=0.0, mu=0.0, eps=1e-6, visc=0.0, constKd=1.0):
+    """PenaltyContact3DT::RHSDriver over a list of active striker-facet pairs: (nodal forces [nn][3], pairs in contact, deepest penetration)"""
+    pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 4)
+    area = np.ascontiguousarray(area, np.float64)
+    X = np.ascontiguousarray(X)
+    u = np.ascontiguousarray(u)
+    f = np.zeros_like(X)
+    hmax = C.c_double(0.0)
+    L = lib()
+    L.orc_contact_force.restype = C.c_int
+    vv = None if v is None else np.ascontiguousarray(v)
+    n = L.orc_contact_force(C.c_int64(pairs.shape[0]), _p(pairs), _p(area), C.c_double(K), C.c_double(mu), C.c_double(eps), C.c_double(visc),
+                            C.c_double(constKd), C.c_int64(X.shape[0]), _p(X), _p(u), _p(vv) if vv is not None else None, _p(f), C.byref(hmax))
+    return f, n, hmax.value
+
+
 def inertial_force(density, mass_type, conn, X, acc, scale=1.0):
     """ContinuumElementT::FormMa summed over the mesh: M a [nn][3] (mass_type 1 consistent, 2 lumped)"""
     conn = np.ascontiguousarray(conn, np.int32)

@@ -1,0 +1,132 @@
+"""SURVEY 8(f)-4, contact_3D_penalty: the oracle's restatement of PenaltyContact3DT::RHSDriver against the reference's own runs
+(tests/golden/ref_contact_*.npz, written by tests/golden/make_golden.py with oracle/_ref/tahoe_dump --contact): the contact group's
+FormRHS on the active equations at every dumped state, for the reference's static two-cube case (penalty force only) and its explicit
+sliding case with velocity-based Coulomb friction and normal viscous damping."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["ref_contact_cubes_1", "ref_contact_sliding_friction"]
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def reference_states(g):
+    """(step, pairs, area, d, v or None, contact rhs on the active equations) of every dumped step"""
+    for k in g["steps"]:
+        v = g.get("ref_v_%d" % k)
+        yield int(k), g["ref_cpairs_%d" % k], g["ref_carea_%d" % k], g["ref_d_%d" % k], v, g["ref_crhs_%d" % k]
+
+
+def to_equations(f, eqnos):
+    out = np.zeros(int(eqnos.max()))
+    act = eqnos > 0
+    out[eqnos[act] - 1] = f[act]
+    return out
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    oracle_lib.build()
+    return oracle_lib
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_contact_force_matches_the_reference(oracle, name):
+    g = load(name)
+    K, mu, eps, visc = g["ref_cparams"]
+    X, eqnos = g["ref_coords"], g["ref_eqnos"]
+    seen_contact = 0
+    for k, pairs, area, d, v, want in reference_states(g):
+        f, n, hmax = oracle.contact_force(pairs, area, X, d, v, K=K, mu=mu, eps=eps, visc=visc)
+        got = to_equations(f, eqnos)
+        scale = max(np.abs(want).max(), 1e-300)
+        assert np.abs(got - want).max() < 1e-12 * scale, (name, k)
+        assert hmax <= 0.0 and n <= pairs.shape[0]
+        seen_contact += n
+    assert seen_contact > 0
+    if name == "ref_contact_sliding_friction":
+        assert mu > 0 and visc > 0  # the fixture exercises all three force terms
+        # ... and they matter: without friction / damping the force differs visibly
+        k, pairs, area, d, v, want = list(reference_states(g))[-1]
+        f0, _, _ = oracle.contact_force(pairs, area, X, d, None, K=K)
+        assert np.abs(to_equations(f0, eqnos) - want).max() > 1e-3 * np.abs(want).max()
+
+
+def test_contact_force_is_self_equilibrated(oracle):
+    """every pair's 12-vector sums to zero force (Newton's third law in all three terms)"""
+    g = load("ref_contact_sliding_friction")
+    K, mu, eps, visc = g["ref_cparams"]
+    k, pairs, area, d, v, _ = list(reference_states(g))[-1]
+    f, n, _ = oracle.contact_force(pairs, area, g["ref_coords"], d, v, K=K, mu=mu, eps=eps, visc=visc)
+    assert n > 0 and np.abs(f.sum(axis=0)).max() < 1e-12 * np.abs(f).sum()
+
+
+# ---- the device path (tb2_contact_*) against the same fixtures and against the oracle ---------------------------------------------
+
+@pytest.fixture(scope="module")
+def tb2():
+    from tahoe_b200 import capi
+    capi.lib()
+    assert capi.device_count() >= 1
+    return capi
+
+
+def _dummy_mesh(tb2, X):
+    """the contact force needs the coordinates only: a one-element connectivity over the first 8 nodes carries them to the device"""
+    return tb2.Mesh(X, np.arange(8, dtype=np.int32).reshape(1, 8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_device_contact_force_matches_the_reference(tb2, oracle, name):
+    g = load(name)
+    K, mu, eps, visc = g["ref_cparams"]
+    X, eqnos = g["ref_coords"], g["ref_eqnos"]
+    mesh = _dummy_mesh(tb2, X)
+    contact = tb2.Contact(mesh, K, mu, eps, visc)
+    for k, pairs, area, d, v, want in reference_states(g):
+        contact.set_pairs(pairs, area)
+        f = contact.form_host(d, v)
+        got = to_equations(f, eqnos)
+        assert np.abs(got - want).max() < 1e-10 * np.abs(want).max(), (name, k)  # BASELINE.json: forces to a relative 1e-10
+        f_o, n_o, h_o = oracle.contact_force(pairs, area, X, d, v, K=K, mu=mu, eps=eps, visc=visc)
+        assert np.abs(f - f_o).max() < 1e-12 * np.abs(f_o).max()
+        assert contact.tracking() == (n_o, h_o)  # pairs in contact and deepest penetration: exact
+        assert np.array_equal(f, contact.form_host(d, v))  # ordered sums, no float atomics
+        base = np.full_like(X, 0.25)
+        assert np.abs(contact.form_host(d, v, out=base.copy()) - (base + f)).max() < 1e-15 * max(np.abs(f).max(), 1.0)  # accumulate
+
+
+@pytest.mark.gpu
+def test_device_contact_force_on_a_large_random_pair_list(tb2, oracle):
+    """2 x 10^5 pairs over 10^5 nodes with many pairs per node (a striker in several pairs, facets shared): open and closed gaps,
+    friction and damping -- against the oracle entry by entry, tracking data exact, an empty list gives zero force"""
+    rng = np.random.default_rng(11)
+    nn, npairs = 100_000, 200_000
+    X = rng.random((nn, 3)) * 20.0
+    u = 0.01 * rng.standard_normal((nn, 3))
+    v = rng.standard_normal((nn, 3))
+    base = rng.integers(0, nn - 4, npairs)
+    pairs = np.stack([base, base + 1, base + 2, base + 3], axis=1).astype(np.int32)
+    area = rng.random(npairs) + 0.5
+    mesh = _dummy_mesh(tb2, X)
+    contact = tb2.Contact(mesh, 500.0, 0.3, 1e-3, 20.0)
+    contact.set_pairs(pairs, area)
+    f = contact.form_host(u, v, constKd=1.0)
+    f_o, n_o, h_o = oracle.contact_force(pairs, area, X, u, v, K=500.0, mu=0.3, eps=1e-3, visc=20.0)
+    assert 0.2 * npairs < n_o < 0.8 * npairs  # both branches are exercised
+    assert np.abs(f - f_o).max() < 1e-11 * np.abs(f_o).max()
+    assert contact.tracking() == (n_o, h_o)
+    contact.set_pairs(np.zeros((0, 4), np.int32), np.zeros(0))
+    assert not contact.form_host(u, v).any() and contact.tracking() == (0, 0.0)
+    with pytest.raises(tb2.Tb2Error):
+        contact.set_pairs(np.array([[0, 1, 2, nn]], np.int32), np.ones(1))  # node out of range
+    with pytest.raises(tb2.Tb2Error):
+        contact.form_host(u)  # friction without velocities
