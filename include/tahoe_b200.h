@@ -235,6 +235,11 @@ int tb2_explicit_set_bc(tb2_explicit* ex, const uint8_t* h_code, const double* h
  * nExplicitCD.cpp:20-69): value[h_dofs[k]] = h_values[k], h_dofs = nodal dof indices 3 n + i */
 int tb2_explicit_update_bc_values(tb2_explicit* ex, int64_t count, const int64_t* h_dofs, const double* h_values);
 /* FEManagerT::InitialCondition (FEManagerT.cpp:2034): a = M^-1 (fext - fint(d)) on free dofs */
+/* A contact_3D_penalty group in the resident step: before every element sweep the attached group's force is re-formed on the predicted
+ * d, v (what PenaltyContact3DT::RHSDriver sees inside FEManagerT::FormRHS) and enters the residual beside s fext - fint; also in
+ * tb2_explicit_initial_condition.  The pair list may be replaced between runs (tb2_contact_set_pairs, after the host's search at a
+ * relaxation point).  NULL detaches.  Single-GPU runs. */
+int tb2_explicit_attach_contact(tb2_explicit* ex, tb2_contact* contact);
 int tb2_explicit_initial_condition(tb2_explicit* ex);
 /* nsteps x { Predictor + ConsistentKBC ; fint ; a = M^-1 R ; Corrector }.  h_fext_scale / h_value_scale
  * (each nsteps long or NULL = 1.0) scale the stored fext / prescribed values at each step (ScheduleT). */

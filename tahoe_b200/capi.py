@@ -45,7 +45,7 @@ tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpc
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_copy_diagonal_host tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
 tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_secant_search_host
-tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking""".split()
+tb2_explicit_attach_contact tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking""".split()
 
 
 class Tb2Error(RuntimeError):
@@ -441,6 +441,11 @@ class Explicit(_Handle):
         self.nn = group.mesh.nn
         self._init_handle(group)
         _chk(lib().tb2_explicit_create(group.h, C.byref(self.h)))
+
+    def attach_contact(self, contact):
+        """a capi.Contact whose force joins the residual of every step (None detaches)"""
+        self._contact = contact
+        _chk(lib().tb2_explicit_attach_contact(self.h, contact.h if contact is not None else None))
 
     def set_state(self, d=None, v=None, a=None):
         _chk(lib().tb2_explicit_set_state(self.h, _p(_f64(d)), _p(_f64(v)), _p(_f64(a))))

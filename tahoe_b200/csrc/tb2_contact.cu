@@ -33,6 +33,7 @@ struct tb2_contact {
     tb2::DevBuf<int> track_n;     // [blocks] pairs in contact per CTA
     tb2::DevBuf<double> track_h;  // [blocks] deepest penetration per CTA
     int track_blocks = 0;
+    unsigned long long version = 0; // tb2_contact_set_pairs calls so far
 };
 
 namespace {
@@ -171,13 +172,19 @@ __global__ void __launch_bounds__(kContactThreads) k_contact_pairs(int64_t npair
     }
 }
 
+template <bool ACCUMULATE>
 __global__ void k_contact_nodes(int64_t ntouched, const int* __restrict__ node, const int* __restrict__ slot_ptr, const int* __restrict__ slot,
                                 const double* __restrict__ rec, double* __restrict__ f)
 {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= ntouched) return;
     const int64_t n = node[k];
-    double s0 = f[n * 3 + 0], s1 = f[n * 3 + 1], s2 = f[n * 3 + 2];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (ACCUMULATE) {
+        s0 = f[n * 3 + 0];
+        s1 = f[n * 3 + 1];
+        s2 = f[n * 3 + 2];
+    }
     for (int q = slot_ptr[k]; q < slot_ptr[k + 1]; q++) {
         const double* r = rec + (int64_t)slot[q] * 3;
         s0 += r[0];
@@ -189,7 +196,35 @@ __global__ void k_contact_nodes(int64_t ntouched, const int* __restrict__ node, 
     f[n * 3 + 2] = s2;
 }
 
+int contact_launch(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f, bool accumulate)
+{
+    tb2_mesh* m = c->mesh;
+    if ((c->mu > 0.0 || c->visc > 0.0) && !d_v) {
+        tb2::set_error("contact force: friction / viscous damping need the nodal velocities");
+        return TB2_ERR_ARG;
+    }
+    if (c->npairs == 0) return TB2_OK;
+    ProfScope ps(m, kProfOther, 2);
+    k_contact_pairs<<<(unsigned)c->track_blocks, kContactThreads, 0, m->stream>>>(c->npairs, c->pairs.p, c->area.p, c->K, c->mu, c->eps, c->visc, constKd,
+                                                                                 m->X.p, d_u, d_v, c->rec.p, c->track_n.p, c->track_h.p);
+    TB2_CUDA(cudaGetLastError());
+    const int T = 128;
+    const unsigned nb = (unsigned)((c->ntouched + T - 1) / T);
+    if (accumulate) k_contact_nodes<true><<<nb, T, 0, m->stream>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
+    else k_contact_nodes<false><<<nb, T, 0, m->stream>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
+    TB2_CUDA(cudaGetLastError());
+    return TB2_OK;
+}
+
 } // namespace
+
+namespace tb2 {
+int contact_form_touched(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f)
+{
+    return contact_launch(c, constKd, d_u, d_v, d_f, false);
+}
+unsigned long long contact_version(const tb2_contact* c) { return c->version; }
+} // namespace tb2
 
 extern "C" {
 
@@ -230,6 +265,7 @@ int tb2_contact_set_pairs(tb2_contact* c, int64_t npairs, const int32_t* h_pairs
     TB2_CUDA(cudaStreamSynchronize(m->stream)); // the previous list may still be in use
     c->npairs = npairs;
     c->ntouched = 0;
+    c->version++;
     if (npairs == 0) return TB2_OK;
     // node -> pair records, ascending pair order within a node (stable sort of the slots by node)
     std::vector<int> order((size_t)npairs * 4);
@@ -265,20 +301,8 @@ int tb2_contact_form(tb2_contact* c, double constKd, const double* d_u, const do
     TB2_ARG(c && d_u && d_f);
     tb2_mesh* m = c->mesh;
     DeviceGuard dg(m->device);
-    if ((c->mu > 0.0 || c->visc > 0.0) && !d_v) {
-        tb2::set_error("tb2_contact_form: friction / viscous damping need the nodal velocities");
-        return TB2_ERR_ARG;
-    }
     if (!accumulate) TB2_CUDA(cudaMemsetAsync(d_f, 0, (size_t)m->nn * 3 * sizeof(double), m->stream));
-    if (c->npairs == 0) return TB2_OK;
-    ProfScope ps(m, kProfOther, 2);
-    k_contact_pairs<<<(unsigned)c->track_blocks, kContactThreads, 0, m->stream>>>(c->npairs, c->pairs.p, c->area.p, c->K, c->mu, c->eps, c->visc, constKd,
-                                                                                 m->X.p, d_u, d_v, c->rec.p, c->track_n.p, c->track_h.p);
-    TB2_CUDA(cudaGetLastError());
-    const int T = 128;
-    k_contact_nodes<<<(unsigned)((c->ntouched + T - 1) / T), T, 0, m->stream>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
-    TB2_CUDA(cudaGetLastError());
-    return TB2_OK;
+    return contact_launch(c, constKd, d_u, d_v, d_f, true);
 }
 
 int tb2_contact_form_host(tb2_contact* c, double constKd, const double* h_u, const double* h_v, int accumulate, double* h_f)

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_cd_interface_update(int64_t n_if, const
         const unsigned char c = na.code[q];
         double di = NEXT_PREDICTOR ? na.d[q] : 0.0, vi = na.v[q], ai;
         const double bcv = (NEXT_PREDICTOR && c == TB2_BC_DSP) ? na.bcval[q] : 0.0;
-        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], na.fext ? na.fext[q] : 0.0, na.minv[q], bcv, di, vi, ai);
+        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], nodal_load(sc, na, q), na.minv[q], bcv, di, vi, ai);
         if (NEXT_PREDICTOR) na.d[q] = di;
         else {
             na.a[q] = ai;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) k_peer_interface_update(int64_t n_if, con
         const unsigned char c = na.code[q];
         double di = NEXT_PREDICTOR ? na.d[q] : 0.0, vi = na.v[q], ai;
         const double bcv = (NEXT_PREDICTOR && c == TB2_BC_DSP) ? na.bcval[q] : 0.0;
-        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], na.fext ? na.fext[q] : 0.0, na.minv[q], bcv, di, vi, ai);
+        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], nodal_load(sc, na, q), na.minv[q], bcv, di, vi, ai);
         if (NEXT_PREDICTOR) na.d[q] = di;
         else {
             na.a[q] = ai;
@@ -193,12 +193,13 @@ __global__ void k_invert_diagonal(int64_t n, const double* __restrict__ m, doubl
 }
 
 // FEManagerT::InitialCondition: a = minv (fext - fint) on free dofs, 0 elsewhere
-__global__ void k_initial_acceleration(int64_t n, const double* __restrict__ fext, const double* __restrict__ fint,
+__global__ void k_initial_acceleration(int64_t n, const double* __restrict__ fext, const double* __restrict__ fadd, const double* __restrict__ fint,
                                        const double* __restrict__ minv, const unsigned char* __restrict__ code, double* __restrict__ a)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    a[i] = code[i] ? 0.0 : (fext[i] - fint[i]) * minv[i];
+    const double load = fadd ? fext[i] + fadd[i] : fext[i];
+    a[i] = code[i] ? 0.0 : (load - fint[i]) * minv[i];
 }
 
 } // namespace tb2
@@ -209,6 +210,7 @@ static NodeArrays node_arrays(tb2_explicit* ex)
 {
     NodeArrays na;
     na.fext = ex->has_fext ? ex->fext.p : nullptr;
+    na.fadd = ex->contact ? ex->fadd.p : nullptr;
     na.minv = ex->minv.p;
     na.code = ex->bccode.p;
     na.bcval = ex->bcval.p;
@@ -277,6 +279,17 @@ static int interface_lane_nccl(tb2_explicit* ex, const CommPlan& cp, const StepC
     return TB2_OK;
 }
 
+// the attached contact group's force on the current (predicted) state -> fadd; fadd is cleared only when the pair list changed
+static int contact_loads(tb2_explicit* ex)
+{
+    tb2_mesh* m = ex->group->mesh;
+    if (ex->contact_version != contact_version(ex->contact)) {
+        TB2_CUDA(cudaMemsetAsync(ex->fadd.p, 0, (size_t)m->nn * 3 * sizeof(double), m->stream));
+        ex->contact_version = contact_version(ex->contact);
+    }
+    return contact_form_touched(ex->contact, 1.0 /* nExplicitCD: FormKd = 1 */, ex->d.p, ex->v.p, ex->fadd.p);
+}
+
 // nsteps explicit steps on the device-resident state; fs / vs: per-step scales of fext and of the prescribed displacements
 static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
 {
@@ -303,6 +316,7 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
         const bool next = s + 1 < nsteps;
         const StepConsts sc{dt, fs ? fs[s] : 1.0, (next && vs) ? vs[s + 1] : 1.0};
         if (!multi) {
+            if (ex->contact) TB2_CHECK(contact_loads(ex)); // on the predicted d, v -- what the group's RHSDriver sees in FEManagerT::FormRHS
             TB2_CHECK(launch_element_forces(g, ex->d.p, nullptr, 0));
             launch_node_update<true>(ex, sc, next, nullptr, m->stream);
             continue;
@@ -445,6 +459,22 @@ int tb2_explicit_update_bc_values(tb2_explicit* ex, int64_t count, const int64_t
     return TB2_OK;
 }
 
+int tb2_explicit_attach_contact(tb2_explicit* ex, tb2_contact* contact)
+{
+    TB2_ARG(ex);
+    tb2_mesh* m = ex->group->mesh;
+    DeviceGuard dg(m->device);
+    if (contact && comm_active(m)) {
+        set_error("tb2_explicit_attach_contact: contact pairs across ranks are not supported (single-GPU runs only)");
+        return TB2_ERR_ARG;
+    }
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    ex->contact = contact;
+    ex->contact_version = ~0ull;
+    if (contact && !ex->fadd.p) TB2_CUDA(ex->fadd.alloc((size_t)m->nn * 3));
+    return TB2_OK;
+}
+
 int tb2_explicit_initial_condition(tb2_explicit* ex)
 {
     TB2_ARG(ex);
@@ -454,7 +484,9 @@ int tb2_explicit_initial_condition(tb2_explicit* ex)
     TB2_CHECK(tb2_form_internal_force(g, ex->d.p, nullptr, 0, ex->fint.p));
     TB2_CHECK(tb2_comm_sum_interface(m, ex->fint.p));
     const int64_t n = 3 * m->nn;
-    k_initial_acceleration<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(n, ex->fext.p, ex->fint.p, ex->minv.p, ex->bccode.p, ex->a.p);
+    if (ex->contact) TB2_CHECK(contact_loads(ex));
+    k_initial_acceleration<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(n, ex->fext.p, ex->contact ? ex->fadd.p : nullptr, ex->fint.p, ex->minv.p,
+                                                                               ex->bccode.p, ex->a.p);
     TB2_CUDA(cudaGetLastError());
     return tb2_group_status(g, nullptr);
 }

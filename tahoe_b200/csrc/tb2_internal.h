@@ -223,12 +223,24 @@ struct tb2_matrix {
     std::vector<int> k3_nmin, k3_nmax;
 };
 
+struct tb2_contact;
+namespace tb2 {
+// tb2_contact.cu, for the resident explicit step: the pair forces of (u, v) summed into f for the nodes that appear in a pair only
+// (f is overwritten there and left alone elsewhere); the version counts tb2_contact_set_pairs calls
+int contact_form_touched(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f);
+unsigned long long contact_version(const tb2_contact* c);
+} // namespace tb2
+
 struct tb2_explicit {
     tb2_group* group = nullptr;
     int device = 0;                // copy for tb2_explicit_destroy (the group may be gone by then)
     tb2::DevBuf<double> d, v, a, mass, minv, fext, fint, bcval;
     tb2::DevBuf<unsigned char> bccode;
     bool has_fext = false; // fext holds a non-zero entry (an all-zero external force is not read by the node kernel)
+    // an attached contact_3D_penalty group (tb2_explicit_attach_contact): its force on the predicted state is re-formed before every sweep
+    tb2_contact* contact = nullptr;
+    tb2::DevBuf<double> fadd;                     // [nn][3] zero outside the nodes of the current pair list
+    unsigned long long contact_version = ~0ull;   // pair-list version fadd was last cleared for
     // tb2_explicit_run_async: displacement snapshots on their way to the host beside the next steps' kernels
     tb2::DevBuf<double> dsnap[2];
     cudaStream_t stream_copy = nullptr;

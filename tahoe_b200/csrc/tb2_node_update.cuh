@@ -31,7 +31,7 @@ template <bool NEXT_PREDICTOR>
 TB2_DEV void cd_update_dof(const StepConsts& u, const unsigned char c, const double f, const double fx, const double mi, const double bcv,
                            double& di, double& vi, double& ai)
 {
-    const double R = __dsub_rn(__dmul_rn(u.fext_scale, fx), f);
+    const double R = __dsub_rn(fx, f); // fx: the dof's external load of this step (nodal_load)
     const double upd = c ? 0.0 : __dmul_rn(R, mi);
     ai = 0.0;
     cd_correct(u.dt, vi, ai, upd);
@@ -45,6 +45,7 @@ TB2_DEV void cd_update_dof(const StepConsts& u, const unsigned char c, const dou
 
 struct NodeArrays {
     const double* fext; // null: no external force
+    const double* fadd; // null, or a second, unscaled load re-formed every step (contact forces: residual contributions of other groups)
     const double* minv;
     const unsigned char* code;
     const double* bcval;
@@ -53,6 +54,13 @@ struct NodeArrays {
     double* a;
     double* fint;
 };
+
+// the external load of dof q in this step: s fext (+ fadd).  Without the second array the expression is the one it always was.
+TB2_DEV double nodal_load(const StepConsts& sc, const NodeArrays& na, const int64_t q)
+{
+    const double fx = na.fext ? __dmul_rn(sc.fext_scale, na.fext[q]) : 0.0;
+    return na.fadd ? __dadd_rn(fx, na.fadd[q]) : fx;
+}
 
 // one node: gather fint (GATHER) or take it from fint[] (multi-GPU: the interface-summed force), then the update above.
 // GATHER reads the node's incidence from the fixed-width table inc8 (one 32-byte load).  Per node and step the steady state (NEXT_PREDICTOR) moves
@@ -101,7 +109,7 @@ TB2_DEV void cd_node_update_one(const int64_t n, const int* __restrict__ inc_ptr
         const unsigned char c = na.code[q];
         double di = NEXT_PREDICTOR ? na.d[q] : 0.0, vi = na.v[q], ai;
         const double bcv = (NEXT_PREDICTOR && c == TB2_BC_DSP) ? na.bcval[q] : 0.0;
-        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], na.fext ? na.fext[q] : 0.0, na.minv[q], bcv, di, vi, ai);
+        cd_update_dof<NEXT_PREDICTOR>(sc, c, f[i], nodal_load(sc, na, q), na.minv[q], bcv, di, vi, ai);
         if (NEXT_PREDICTOR) na.d[q] = di;
         else {
             na.a[q] = ai;

@@ -130,3 +130,69 @@ def test_device_contact_force_on_a_large_random_pair_list(tb2, oracle):
         contact.set_pairs(np.array([[0, 1, 2, nn]], np.int32), np.ones(1))  # node out of range
     with pytest.raises(tb2.Tb2Error):
         contact.form_host(u)  # friction without velocities
+
+
+@pytest.mark.gpu
+def test_resident_explicit_step_with_contact_matches_the_oracle_loop(tb2, oracle):
+    """Impact of two stacked cubes in the resident explicit step (tb2_explicit_attach_contact): the upper cube's bottom nodes strike
+    the triangulated top face of the clamped lower cube; 60 steps of predictor / element sweep / contact force on the predicted d, v /
+    corrector against the same loop written with the oracle's functions, friction and damping on."""
+    from tahoe_b200 import mesh as tmesh
+    n = 4
+    Xl, cl, nsl = tmesh.structured_cube(n, jitter=0.0)
+    Xu = Xl + np.array([0.0, 0.0, 1.0])  # zero initial gap
+    X = np.vstack([Xl, Xu])
+    conn = np.vstack([cl, cl + Xl.shape[0]]).astype(np.int32)
+    nn_l = Xl.shape[0]
+    px = n + 1
+    top = lambda i, j: n * px * px + j * px + i               # lower cube, z = 1 face
+    bot = lambda i, j: nn_l + j * px + i                      # upper cube, z = 1 face (its bottom)
+    pairs = []
+    for j in range(n):
+        for i in range(n):
+            pairs.append([top(i, j), top(i + 1, j), top(i + 1, j + 1), bot(i + 1, j)])      # normal (x2-x1) x (x3-x1) = +z
+            pairs.append([top(i, j), top(i + 1, j + 1), top(i, j + 1), bot(i, j + 1)])
+    pairs = np.asarray(pairs, np.int32)
+    area = np.full(len(pairs), 1.0 / n ** 2)
+    desc = {"type": "Simo_isotropic", "kappa": 1000.0, "mu": 400.0, "density": 1.0}
+    K, mu, eps, visc = 2000.0, 0.3, 1e-3, 20.0
+    code = np.zeros(X.shape, np.uint8)
+    code[nsl[5]] = 1  # bottom face of the lower cube clamped
+    v0 = np.zeros_like(X)
+    v0[nn_l:] = [0.4, 0.0, -5.0]  # the upper cube comes down sliding
+    dt, nsteps = 2.0e-4, 60
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.TOTAL_LAGRANGIAN, tb2.material(desc))
+    ex = tb2.Explicit(grp)
+    contact = tb2.Contact(mesh, K, mu, eps, visc)
+    contact.set_pairs(pairs, area)
+    ex.attach_contact(contact)
+    ex.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    ex.set_state(np.zeros_like(X), v0, np.zeros_like(X))
+    ex.run(dt, nsteps)
+    d, v, a = ex.get_state()
+    ncontact, hmax = contact.tracking()
+    # the same loop with the oracle
+    omat = oracle.material(desc)
+    mass = oracle.lumped_mass(1.0, conn, X)
+    d0, w0, a0 = np.zeros_like(X), v0.copy(), np.zeros_like(X)
+    seen = 0
+    for _ in range(nsteps):
+        oracle.cd_predictor(dt, d0, w0, a0, code, np.zeros_like(X))
+        err, fi = oracle.internal_force(oracle.TOTAL_LAGRANGIAN, omat, conn, X, d0)
+        assert err == 0
+        fc, nc, hm = oracle.contact_force(pairs, area, X, d0, w0, K=K, mu=mu, eps=eps, visc=visc)
+        seen += nc
+        oracle.cd_corrector(dt, w0, a0, fc - fi, mass, code)
+    assert seen > 10 * nsteps and nc > 0 and hm < 0.0  # the cubes are in contact through the run
+    assert (ncontact, hmax) == (nc, hm)  # the tracking data of the last step
+    for got, want in ((d, d0), (v, w0), (a, a0)):
+        assert np.abs(got - want).max() < TOL_FIELD * np.abs(want).max()
+    # the contact matters: without it the result differs at first order
+    ex.attach_contact(None)
+    ex.set_state(np.zeros_like(X), v0, np.zeros_like(X))
+    ex.run(dt, nsteps)
+    assert np.abs(ex.get_state()[0] - d0).max() > 1e-2 * np.abs(d0).max()
+
+
+TOL_FIELD = 1.0e-10  # BASELINE.json: fields to a relative 1e-10
