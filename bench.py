@@ -769,6 +769,62 @@ def run_shuffled(torch, capi, tmesh, local, n, steps, dt):
             "workload": "the same %d^3 cube with node and element numbers permuted at random (seed 7)" % n}
 
 
+def run_contact(torch, capi, tmesh, local, n, steps):
+    """two stacked n^3 cubes, the upper one coming down on the clamped lower one (the level.5 impact benchmark's shape),
+    contact_3D_penalty with friction and viscous damping inside the resident step: element-updates/s with the contact force re-formed
+    every step, the same run without it, and the two contact kernels' own time"""
+    Xl, cl, nsl = tmesh.structured_cube(n, jitter=0.0)
+    X = np.vstack([Xl, Xl + np.array([0.0, 0.0, 1.0])])
+    conn = np.vstack([cl, cl + Xl.shape[0]]).astype(np.int32)
+    nn_l, px = Xl.shape[0], n + 1
+    j, i = [a.ravel() for a in np.meshgrid(np.arange(n), np.arange(n), indexing="ij")]
+    top = lambda ii, jj: n * px * px + jj * px + ii
+    bot = lambda ii, jj: nn_l + jj * px + ii
+    pairs = np.concatenate([np.stack([top(i, j), top(i + 1, j), top(i + 1, j + 1), bot(i + 1, j)], axis=1),
+                            np.stack([top(i, j), top(i + 1, j + 1), top(i, j + 1), bot(i, j + 1)], axis=1)]).astype(np.int32)
+    area = np.full(pairs.shape[0], 1.0 / n ** 2)
+    mat = {"type": "Simo_isotropic", "density": 1.0, "kappa": 1000.0, "mu": 400.0}
+    dt = 0.25 / n / np.sqrt((1000.0 + 4.0 * 400.0 / 3.0) / 1.0)
+    code = np.zeros(X.shape, np.uint8)
+    code[nsl[5]] = 1
+    v0 = np.zeros_like(X)
+    v0[nn_l:] = [0.4, 0.0, -5.0]
+    m = capi.Mesh(X, conn, device=local)
+    g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(mat))
+    ex = capi.Explicit(g)
+    contact = capi.Contact(m, 2000.0, 0.3, 1e-3, 20.0)
+    contact.set_pairs(pairs, area)
+    ex.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
+    out = {}
+    for tag, att in (("without_contact", None), ("with_contact", contact)):
+        ex.attach_contact(att)
+        ex.set_state(np.zeros_like(X), v0, np.zeros_like(X))
+        ex.run(dt, 5)
+        m.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ex.run(dt, steps)
+        e1.record(stream)
+        m.synchronize()
+        torch.cuda.synchronize()
+        out[tag] = e0.elapsed_time(e1) / steps
+    ncontact, hmax = contact.tracking()
+    m.profile_begin()
+    ex.run(dt, 20)
+    ms_cat, cnt_cat, _ = m.profile_end()
+    d = ex.get_state()[0]
+    ok = bool(np.isfinite(d).all())
+    ex.close(); contact.close(); g.close(); m.close()
+    if not ok or ncontact == 0:
+        raise SystemExit("bench.py: contact leg: non-finite state or no pair in contact")
+    return {"value": conn.shape[0] / (out["with_contact"] * 1e-3), "unit": METRIC, "ms_per_step": out["with_contact"],
+            "ms_per_step_without_contact": out["without_contact"], "contact_kernels_ms_per_step": float(ms_cat[7]) / 20, "pairs": int(pairs.shape[0]),
+            "pairs_in_contact": int(ncontact), "deepest_penetration": float(hmax), "steps": steps,
+            "workload": "two stacked %d^3 cubes (%d elements), contact_3D_penalty K=2000 mu=0.3 c=20 on %d striker-facet pairs, force re-formed on the "
+                        "device before every sweep (tb2_explicit_attach_contact)" % (n, conn.shape[0], pairs.shape[0])}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -997,6 +1053,7 @@ def run_gpu_arm(args):
     if world == 1 and not args.no_explicit_solid:
         xs = run_explicit_solid(torch, capi, tmesh, local, n, min(args.steps, 200), args.warmup, hbm_peak_all, not args.no_cpu_baseline)
     shuffled = run_shuffled(torch, capi, tmesh, local, n, min(args.steps, 100), dt) if (world == 1 and not args.no_shuffled) else None
+    contact = run_contact(torch, capi, tmesh, local, 79, min(args.steps, 200)) if (world == 1 and not args.no_contact) else None
     j2 = None
     if world == 1 and args.nlpcg_n > 0:
         j2 = run_nlpcg_j2(torch, capi, tmesh, local, args.nlpcg_n, args.nlpcg_iters)
@@ -1014,6 +1071,8 @@ def run_gpu_arm(args):
                 line["plugin"] = {"error": str(e)[-400:]}
         if shuffled:
             line["shuffled_numbering"] = shuffled
+        if contact:
+            line["contact"] = contact
         if nj2:
             line["newton_j2"] = nj2
         if j2:
@@ -1047,6 +1106,7 @@ def main():
                     help="N > 1: interface sums pulled over NVLink peer memory inside the consuming kernels (default), or the packed ncclAllReduce")
     ap.add_argument("--no-parity", action="store_true", help="skip the partitioned-vs-single-GPU check that precedes the timing")
     ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-numbering leg")
+    ap.add_argument("--no-contact", action="store_true", help="skip the contact_3D_penalty leg (SURVEY.md 8f-4)")
     ap.add_argument("--no-plugin", action="store_true", help="skip the plugin-executable leg")
     ap.add_argument("--no-profile", action="store_true", help="experiments only: no per-launch CUDA events in the timed region")
     ap.add_argument("--pcg-n", type=int, default=100, help="cube edge of the implicit small-strain case (100 -> 3.06M equations, 245M nnz)")

@@ -196,7 +196,7 @@ __global__ void k_contact_nodes(int64_t ntouched, const int* __restrict__ node, 
     f[n * 3 + 2] = s2;
 }
 
-int contact_launch(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f, bool accumulate)
+int contact_launch(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f, bool accumulate, cudaStream_t st)
 {
     tb2_mesh* m = c->mesh;
     if ((c->mu > 0.0 || c->visc > 0.0) && !d_v) {
@@ -204,14 +204,14 @@ int contact_launch(tb2_contact* c, double constKd, const double* d_u, const doub
         return TB2_ERR_ARG;
     }
     if (c->npairs == 0) return TB2_OK;
-    ProfScope ps(m, kProfOther, 2);
-    k_contact_pairs<<<(unsigned)c->track_blocks, kContactThreads, 0, m->stream>>>(c->npairs, c->pairs.p, c->area.p, c->K, c->mu, c->eps, c->visc, constKd,
+    ProfScope ps(m, kProfOther, 2, st);
+    k_contact_pairs<<<(unsigned)c->track_blocks, kContactThreads, 0, st>>>(c->npairs, c->pairs.p, c->area.p, c->K, c->mu, c->eps, c->visc, constKd,
                                                                                  m->X.p, d_u, d_v, c->rec.p, c->track_n.p, c->track_h.p);
     TB2_CUDA(cudaGetLastError());
     const int T = 128;
     const unsigned nb = (unsigned)((c->ntouched + T - 1) / T);
-    if (accumulate) k_contact_nodes<true><<<nb, T, 0, m->stream>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
-    else k_contact_nodes<false><<<nb, T, 0, m->stream>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
+    if (accumulate) k_contact_nodes<true><<<nb, T, 0, st>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
+    else k_contact_nodes<false><<<nb, T, 0, st>>>(c->ntouched, c->node.p, c->slot_ptr.p, c->slot.p, c->rec.p, d_f);
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
 }
@@ -219,9 +219,9 @@ int contact_launch(tb2_contact* c, double constKd, const double* d_u, const doub
 } // namespace
 
 namespace tb2 {
-int contact_form_touched(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f)
+int contact_form_touched(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f, cudaStream_t st)
 {
-    return contact_launch(c, constKd, d_u, d_v, d_f, false);
+    return contact_launch(c, constKd, d_u, d_v, d_f, false, st);
 }
 unsigned long long contact_version(const tb2_contact* c) { return c->version; }
 } // namespace tb2
@@ -302,7 +302,7 @@ int tb2_contact_form(tb2_contact* c, double constKd, const double* d_u, const do
     tb2_mesh* m = c->mesh;
     DeviceGuard dg(m->device);
     if (!accumulate) TB2_CUDA(cudaMemsetAsync(d_f, 0, (size_t)m->nn * 3 * sizeof(double), m->stream));
-    return contact_launch(c, constKd, d_u, d_v, d_f, true);
+    return contact_launch(c, constKd, d_u, d_v, d_f, true, m->stream);
 }
 
 int tb2_contact_form_host(tb2_contact* c, double constKd, const double* h_u, const double* h_v, int accumulate, double* h_f)

@@ -279,15 +279,27 @@ static int interface_lane_nccl(tb2_explicit* ex, const CommPlan& cp, const StepC
     return TB2_OK;
 }
 
-// the attached contact group's force on the current (predicted) state -> fadd; fadd is cleared only when the pair list changed
+// the attached contact group's force on the current (predicted) state -> fadd; fadd is cleared only when the pair list changed.
+// The two small kernels run on their own (high-priority) stream beside the element sweep: ev_state = the state is ready, ev_loads = fadd is.
 static int contact_loads(tb2_explicit* ex)
 {
     tb2_mesh* m = ex->group->mesh;
+    if (!ex->stream_aux) {
+        int lo = 0, hi = 0;
+        TB2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        TB2_CUDA(cudaStreamCreateWithPriority(&ex->stream_aux, cudaStreamNonBlocking, hi));
+        TB2_CUDA(cudaEventCreateWithFlags(&ex->ev_state, cudaEventDisableTiming));
+        TB2_CUDA(cudaEventCreateWithFlags(&ex->ev_loads, cudaEventDisableTiming));
+    }
+    TB2_CUDA(cudaEventRecord(ex->ev_state, m->stream));
+    TB2_CUDA(cudaStreamWaitEvent(ex->stream_aux, ex->ev_state, 0));
     if (ex->contact_version != contact_version(ex->contact)) {
-        TB2_CUDA(cudaMemsetAsync(ex->fadd.p, 0, (size_t)m->nn * 3 * sizeof(double), m->stream));
+        TB2_CUDA(cudaMemsetAsync(ex->fadd.p, 0, (size_t)m->nn * 3 * sizeof(double), ex->stream_aux));
         ex->contact_version = contact_version(ex->contact);
     }
-    return contact_form_touched(ex->contact, 1.0 /* nExplicitCD: FormKd = 1 */, ex->d.p, ex->v.p, ex->fadd.p);
+    TB2_CHECK(contact_form_touched(ex->contact, 1.0 /* nExplicitCD: FormKd = 1 */, ex->d.p, ex->v.p, ex->fadd.p, ex->stream_aux));
+    TB2_CUDA(cudaEventRecord(ex->ev_loads, ex->stream_aux));
+    return TB2_OK;
 }
 
 // nsteps explicit steps on the device-resident state; fs / vs: per-step scales of fext and of the prescribed displacements
@@ -318,6 +330,7 @@ static int explicit_steps(tb2_explicit* ex, double dt, int nsteps, const double*
         if (!multi) {
             if (ex->contact) TB2_CHECK(contact_loads(ex)); // on the predicted d, v -- what the group's RHSDriver sees in FEManagerT::FormRHS
             TB2_CHECK(launch_element_forces(g, ex->d.p, nullptr, 0));
+            if (ex->contact) TB2_CUDA(cudaStreamWaitEvent(m->stream, ex->ev_loads, 0));
             launch_node_update<true>(ex, sc, next, nullptr, m->stream);
             continue;
         }
@@ -393,6 +406,11 @@ int tb2_explicit_destroy(tb2_explicit* ex)
             cudaEventDestroy(ex->ev_snap[b]);
             cudaEventDestroy(ex->ev_copied[b]);
         }
+    }
+    if (ex->stream_aux) {
+        cudaStreamDestroy(ex->stream_aux);
+        cudaEventDestroy(ex->ev_state);
+        cudaEventDestroy(ex->ev_loads);
     }
     delete ex;
     return TB2_OK;
@@ -484,7 +502,10 @@ int tb2_explicit_initial_condition(tb2_explicit* ex)
     TB2_CHECK(tb2_form_internal_force(g, ex->d.p, nullptr, 0, ex->fint.p));
     TB2_CHECK(tb2_comm_sum_interface(m, ex->fint.p));
     const int64_t n = 3 * m->nn;
-    if (ex->contact) TB2_CHECK(contact_loads(ex));
+    if (ex->contact) {
+        TB2_CHECK(contact_loads(ex));
+        TB2_CUDA(cudaStreamWaitEvent(m->stream, ex->ev_loads, 0));
+    }
     k_initial_acceleration<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(n, ex->fext.p, ex->contact ? ex->fadd.p : nullptr, ex->fint.p, ex->minv.p,
                                                                                ex->bccode.p, ex->a.p);
     TB2_CUDA(cudaGetLastError());

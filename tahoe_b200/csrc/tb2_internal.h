@@ -227,7 +227,7 @@ struct tb2_contact;
 namespace tb2 {
 // tb2_contact.cu, for the resident explicit step: the pair forces of (u, v) summed into f for the nodes that appear in a pair only
 // (f is overwritten there and left alone elsewhere); the version counts tb2_contact_set_pairs calls
-int contact_form_touched(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f);
+int contact_form_touched(tb2_contact* c, double constKd, const double* d_u, const double* d_v, double* d_f, cudaStream_t st);
 unsigned long long contact_version(const tb2_contact* c);
 } // namespace tb2
 
@@ -241,6 +241,8 @@ struct tb2_explicit {
     tb2_contact* contact = nullptr;
     tb2::DevBuf<double> fadd;                     // [nn][3] zero outside the nodes of the current pair list
     unsigned long long contact_version = ~0ull;   // pair-list version fadd was last cleared for
+    cudaStream_t stream_aux = nullptr;            // the contact kernels run here, beside the element sweep
+    cudaEvent_t ev_state = nullptr, ev_loads = nullptr;
     // tb2_explicit_run_async: displacement snapshots on their way to the host beside the next steps' kernels
     tb2::DevBuf<double> dsnap[2];
     cudaStream_t stream_copy = nullptr;
