@@ -47,6 +47,7 @@ def comm_init(m, dist, comm):
         dist.all_gather_object(out, b)
         return out
     m.comm_init(*comm, all_gather=gather if EXCHANGE == "peer" else None)
+    return m.comm_peer_enabled()
 
 
 def stable_dt(n):
@@ -451,9 +452,9 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
     if world == 1:
         launches = 5 * iters + 4  # timed pass: 5 kernels per iteration + set-up (counted, not measured: the graph replays them)
     else:
-        # distributed iteration: update, interface rows, pack, pull, interior rows, scalar step over peer memory (6 of ours); with the
+        # distributed iteration over peer memory: update, publishing SpMV, pull, scalar step (+ set-up); counted as 5 with the final check; with the
         # NCCL exchange: update, interface rows, pack, interior rows, unpack, partial sums, scalars (7 of ours + 2 NCCL kernels)
-        launches = (6 if EXCHANGE == "peer" else 7) * iters + 12
+        launches = (5 if m.comm_peer_enabled() else 7) * iters + 12
     # configs[2] as one call: NLSolver::Solve on the device (tb2_newton_solve: K1 residual, K3 tangent, Jacobi-PCG to 1e-8, update)
     newton = None
     if world == 1:
@@ -1036,8 +1037,8 @@ def run_gpu_arm(args):
                              "two lanes: boundary elements -> partial interface forces %s -> interface nodes on the comm stream beside "
                              "interior elements -> private nodes on the main stream"
                              % ("published to the rank's NVLink-mapped window, pulled and summed by the interface-node kernel of every sharer"
-                                if EXCHANGE == "peer" else "packed, ncclAllReduce")),
-                "exchange": EXCHANGE if world > 1 else None,
+                                if m.comm_peer_enabled() else "packed, ncclAllReduce")),
+                "exchange": ("peer" if m.comm_peer_enabled() else "nccl") if world > 1 else None,
                 "step_hbm_frac": step_bytes * args.steps / (ms * 1e-3) * 1e-9 / hbm_peak,
                 "interface_exchange_ms": comm_ms if world > 1 else None,
                 "parity": parity,

@@ -420,6 +420,9 @@ int tb2_comm_destroy(tb2_mesh* mesh);
 int tb2_comm_peer_export(tb2_mesh* mesh, char h_handle[64]);
 int tb2_comm_peer_import(tb2_mesh* mesh, const char* h_handles /* [nranks][64], rank order */);
 int tb2_comm_peer_enabled(tb2_mesh* mesh); /* 1 after a successful import */
+/* back to the packed ncclAllReduce; collective like the import: when the import failed on ANY rank (no IPC between the processes,
+ * GPUs outside one NVLink domain) the host program calls this on every rank */
+int tb2_comm_peer_disable(tb2_mesh* mesh);
 /* d_nodal[nn][3] += contributions of the other sharers on interface nodes (ncclAllReduce on the packed vector) */
 int tb2_comm_sum_interface(tb2_mesh* mesh, double* d_nodal);
 

@@ -44,7 +44,7 @@ tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_copy_diagonal_host tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
-tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_secant_search_host
+tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_comm_peer_disable tb2_secant_search_host
 tb2_explicit_attach_contact tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking""".split()
 
 
@@ -79,9 +79,13 @@ def lib():
     return _lib
 
 
+def last_error():
+    return lib().tb2_last_error().decode()
+
+
 def _chk(code):
     if code != 0:
-        raise Tb2Error(code, lib().tb2_last_error().decode())
+        raise Tb2Error(code, last_error())
 
 
 def _p(a):
@@ -246,10 +250,24 @@ class Mesh(_Handle):
             self.comm_enable_peer(all_gather)
 
     def comm_enable_peer(self, all_gather):
+        """export / all-gather / import; every step is collective, so a failure on one rank (no IPC between the processes, GPUs
+        outside one NVLink domain) is agreed on by all of them and the mesh stays on the packed ncclAllReduce.  Returns whether the
+        peer exchange is on."""
+        import sys
         buf = C.create_string_buffer(64)
-        _chk(lib().tb2_comm_peer_export(self.h, buf))
-        handles = all_gather(buf.raw)
-        _chk(lib().tb2_comm_peer_import(self.h, b"".join(handles)))
+        ok = lib().tb2_comm_peer_export(self.h, buf) == 0
+        err = "" if ok else last_error()
+        handles = all_gather(buf.raw if ok else b"\0" * 64)
+        if ok and all(h != b"\0" * 64 for h in handles):
+            ok = lib().tb2_comm_peer_import(self.h, b"".join(handles)) == 0
+            err = "" if ok else last_error()
+        else:
+            ok = False
+        if not all(f == b"1" for f in all_gather(b"1" if ok else b"0")):
+            _chk(lib().tb2_comm_peer_disable(self.h))
+            print("tahoe_b200: peer-memory exchange unavailable (%s); using the packed ncclAllReduce" % (err or "another rank failed"), file=sys.stderr)
+            return False
+        return True
 
     def comm_peer_enabled(self):
         return bool(lib().tb2_comm_peer_enabled(self.h))

@@ -505,6 +505,17 @@ int tb2_comm_peer_import(tb2_mesh* m, const char* h_handles)
 
 int tb2_comm_peer_enabled(tb2_mesh* m) { return m && m->comm && m->comm->peer ? 1 : 0; }
 
+int tb2_comm_peer_disable(tb2_mesh* m)
+{
+    TB2_ARG(m);
+    if (!m->comm) return TB2_OK;
+    DeviceGuard dg(m->device);
+    cudaStreamSynchronize(m->stream);
+    if (m->comm->stream) cudaStreamSynchronize(m->comm->stream);
+    m->comm->peer = false;
+    return TB2_OK;
+}
+
 int tb2_comm_destroy(tb2_mesh* m)
 {
     if (!m || !m->comm) return TB2_OK;

@@ -35,7 +35,7 @@ def setup(X, conn, ns, device, comm=None):
     m = capi.Mesh(X, conn, device=device)
     if comm:
         m.comm_init(*comm, all_gather=gather_bytes if EXCHANGE == "peer" else None)
-        assert m.comm_peer_enabled() == (EXCHANGE == "peer")
+        assert m.comm_peer_enabled() == (EXCHANGE == "peer"), "peer-memory exchange could not be set up on this box"
     g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MAT))
     ex = capi.Explicit(g)
     code = np.zeros(X.shape, np.uint8)
