@@ -452,9 +452,9 @@ def run_pcg(torch, dist, capi, tmesh, local, rank, world, n, iters, hbm_peak):
     if world == 1:
         launches = 5 * iters + 4  # timed pass: 5 kernels per iteration + set-up (counted, not measured: the graph replays them)
     else:
-        # distributed iteration over peer memory: update, publishing SpMV, pull, scalar step (+ set-up); counted as 5 with the final check; with the
+        # distributed iteration over peer memory: update, publishing SpMV, pull, scalar step (4 of ours); with the
         # NCCL exchange: update, interface rows, pack, interior rows, unpack, partial sums, scalars (7 of ours + 2 NCCL kernels)
-        launches = (5 if m.comm_peer_enabled() else 7) * iters + 12
+        launches = (4 if m.comm_peer_enabled() else 7) * iters + 12
     # configs[2] as one call: NLSolver::Solve on the device (tb2_newton_solve: K1 residual, K3 tangent, Jacobi-PCG to 1e-8, update)
     newton = None
     if world == 1:
