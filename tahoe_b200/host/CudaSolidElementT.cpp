@@ -2,6 +2,7 @@
 #include "CudaSolidElementT.h"
 
 #include "CudaPCGMatrixT.h"
+#include "CudaPenaltyContact3DT.h"
 #include "ElementSupportT.h"
 #include "ExceptionT.h"
 #include "FDKStV.h"
@@ -26,7 +27,7 @@ using namespace Tahoe;
 
 namespace Tahoe {
 const char* kCudaSolidElementNames[kNumCudaSolidElementNames] = {"cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian",
-	"cuda_explicit_solid"};
+	"cuda_explicit_solid", "cuda_contact_3D_penalty"};
 
 ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& support)
 {
@@ -34,6 +35,7 @@ ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& su
 	if (name == kCudaSolidElementNames[1]) return new CudaTotalLagrangianT(support, kCudaSolidElementNames[1], TB2_TOTAL_LAGRANGIAN);
 	if (name == kCudaSolidElementNames[2]) return new CudaUpdatedLagrangianT(support, kCudaSolidElementNames[2], TB2_UPDATED_LAGRANGIAN);
 	if (name == kCudaSolidElementNames[3]) return new CudaExplicitSolidT(support, kCudaSolidElementNames[3], TB2_UPDATED_LAGRANGIAN);
+	if (name == kCudaSolidElementNames[4]) return new CudaPenaltyContact3DT(support, kCudaSolidElementNames[4]);
 	return NULL;
 }
 } // namespace Tahoe

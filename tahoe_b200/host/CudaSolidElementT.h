@@ -136,7 +136,7 @@ typedef CudaSolidElementT<ExplicitElementT> CudaExplicitSolidT;
 /** factory used by the one-line registration in ElementListT::NewElement; returns NULL for other names */
 ElementBaseT* NewCudaSolidElement(const StringT& name, const ElementSupportT& support);
 /** the XML tags handled by NewCudaSolidElement */
-static const int kNumCudaSolidElementNames = 4;
+static const int kNumCudaSolidElementNames = 5; /* four continuum groups + cuda_contact_3D_penalty (CudaPenaltyContact3DT.h) */
 extern const char* kCudaSolidElementNames[kNumCudaSolidElementNames];
 
 } // namespace Tahoe

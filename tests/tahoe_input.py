@@ -87,9 +87,11 @@ def warp(coords):
 # ----------------------------------------------------------------------------
 # TahoeII .geom
 # ----------------------------------------------------------------------------
-def write_geom(path, coords, conn, nodesets, title="structured hex block", sidesets=None, block_sizes=None):
-    """block_sizes: element counts of consecutive element blocks (ids 1, 2, ...); default one block"""
+def write_geom(path, coords, conn, nodesets, title="structured hex block", sidesets=None, block_sizes=None, sideset_blocks=None):
+    """block_sizes: element counts of consecutive element blocks (ids 1, 2, ...); default one block.  sideset_blocks: {side set id:
+    element block id} (default block 1); a side set's element numbers count within its block"""
     sidesets = sidesets or {}
+    sideset_blocks = sideset_blocks or {}
     block_sizes = block_sizes or [conn.shape[0]]
     assert sum(block_sizes) == conn.shape[0]
     nn, ne = coords.shape[0], conn.shape[0]
@@ -104,7 +106,7 @@ def write_geom(path, coords, conn, nodesets, title="structured hex block", sides
         if sidesets:
             f.write("# [ID] [element set ID] [ns]\n")
         for sid in sorted(sidesets):
-            f.write("%d 1 %d\n" % (sid, len(sidesets[sid])))
+            f.write("%d %d %d\n" % (sid, sideset_blocks.get(sid, 1), len(sidesets[sid])))
         f.write("# end dimensions\n*nodesets\n")
         for sid in sorted(nodesets):
             ids = np.asarray(nodesets[sid]) + 1

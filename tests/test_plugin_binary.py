@@ -233,7 +233,7 @@ def test_plugin_schema_lists_the_cuda_tags():
         xsd = os.path.join(work, "tahoe.xsd")
         assert os.path.exists(xsd), r.stdout[-2000:]
         text = open(xsd).read()
-        for tag in ("cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian", "cuda_explicit_solid", "CUDA_PCG_matrix",
+        for tag in ("cuda_small_strain", "cuda_total_lagrangian", "cuda_updated_lagrangian", "cuda_explicit_solid", "cuda_contact_3D_penalty", "CUDA_PCG_matrix",
                     "CUDA_PCG_solver", "CUDA_explicit_solver", "CUDA_central_difference"):
             assert tag in text, tag
         # the matrix's attributes and the explicit solver's restart attribute are declared, not just the names
@@ -400,5 +400,101 @@ def test_plugin_at_scale_50_cubed():
             assert e == 0
             oracle.cd_corrector(dt, v, a, fext - fi, mass, code)
         assert np.abs(got[:, :3] - d).max() < 1e-9 * np.abs(d).max()
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+# ---- <cuda_contact_3D_penalty> (CudaPenaltyContact3DT) against the reference's <contact_3D_penalty> ---------------
+
+CONTACT_XML = """<?xml version="1.0"?>
+<tahoe geometry_file="mesh.geom" title="two stacked cubes, penalty contact">
+    <time num_steps="%(num_steps)d" output_inc="%(num_steps)d" time_step="%(dt).6e">
+        <schedule_function><piecewise_linear><OrderedPair x="0.0" y="0.0"/><OrderedPair x="1.0" y="1.0"/></piecewise_linear></schedule_function>
+    </time>
+    <nodes>
+        <field field_name="displacement"%(integrator)s>
+            <dof_labels><String value="D_X"/><String value="D_Y"/><String value="D_Z"/></dof_labels>
+%(conditions)s
+        </field>
+    </nodes>
+    <element_list>
+        <updated_lagrangian field_name="displacement"%(mass)s>
+            <hexahedron/>
+            <solid_element_nodal_output displacements="1"/>
+            <large_strain_element_block>
+                <block_ID_list><String value="1"/><String value="2"/></block_ID_list>
+                <large_strain_material_3D>
+                    <Simo_isotropic density="1.0"><E_and_nu Poisson_ratio="0.25" Young_modulus="100.0"/></Simo_isotropic>
+                </large_strain_material_3D>
+            </large_strain_element_block>
+        </updated_lagrangian>
+        <%(tag)s field_name="displacement" %(contact_attrs)s>
+            <contact_surface><surface_side_set side_set_ID="1"/></contact_surface>
+            <contact_surface><surface_side_set side_set_ID="2"/></contact_surface>
+            <contact_nodes><node_ID_list><String value="3"/><String value="4"/></node_ID_list></contact_nodes>
+        </%(tag)s>
+    </element_list>
+    %(solver)s
+</tahoe>
+"""
+
+
+def _two_cubes(work, n=3):
+    """two stacked n^3 cubes as element blocks 1 (lower) and 2 (upper, its own nodes, zero gap): node sets 1 bottom of the lower cube,
+    2 top of the upper, 3 / 4 the two faces that meet; side sets 1 (block 1, z = L facets) and 2 (block 2, z = 0 facets)"""
+    Xl, cl, nsl = ti.structured_cube(n, jitter=0.0)
+    X = np.vstack([Xl, Xl + np.array([0.0, 0.0, 1.0])])
+    conn = np.vstack([cl, cl + Xl.shape[0]]).astype(np.int32)
+    ns = {1: nsl[5], 2: nsl[6] + Xl.shape[0], 3: nsl[6], 4: nsl[5] + Xl.shape[0]}
+    ss = ti.cube_side_sets(n)
+    ti.write_geom(os.path.join(work, "mesh.geom"), X, conn, ns, sidesets={1: ss[6], 2: ss[5]}, block_sizes=[n ** 3, n ** 3],
+                  sideset_blocks={1: 1, 2: 2})
+    return X
+
+
+def _contact_cases():
+    clamp = "\n".join('            <kinematic_BC dof="%d" node_ID="1"/>' % d for d in (1, 2, 3))
+    return {
+        # the shape of the reference's level.5 impact benchmark: the upper cube comes down sliding; friction and damping on
+        "impact_friction_damping": dict(
+            num_steps=250, dt=2.0e-4, integrator=' integrator="central_difference"', mass=' mass_type="lumped_mass"',
+            conditions='            <initial_condition dof="3" node_ID="4" type="D_u" value="-5.0"/>\n'
+                       '            <initial_condition dof="3" node_ID="2" type="D_u" value="-5.0"/>\n'
+                       '            <initial_condition dof="1" node_ID="4" type="D_u" value="0.5"/>\n'
+                       '            <initial_condition dof="1" node_ID="2" type="D_u" value="0.5"/>\n' + clamp,
+            contact_attrs='penalty_stiffness="500.0" friction_coefficient="0.3" friction_epsilon_velocity="0.001" viscous_damping="20.0"',
+            solver="<linear_solver><diagonal_matrix/></linear_solver>"),
+        # the shape of level.2/contact_simple/cubes.1.xml: the top face pushed down quasi-statically, Newton with the inherited contact tangent
+        "static_push": dict(
+            num_steps=4, dt=0.25, integrator="", mass="",
+            conditions=clamp + '\n            <kinematic_BC dof="1" node_ID="2"/>\n            <kinematic_BC dof="2" node_ID="2"/>\n'
+                               '            <kinematic_BC dof="3" node_ID="2" schedule="1" type="u" value="-0.1"/>',
+            contact_attrs='penalty_stiffness="50.0"',
+            solver='<nonlinear_solver abs_tolerance="1.0e-10" divergence_tolerance="1.0e+03" max_iterations="10" rel_tolerance="1.0e-12">'
+                   '<profile_matrix/></nonlinear_solver>'),
+    }
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(_contact_cases()))
+def test_plugin_contact_reproduces_reference_output(name):
+    work = tempfile.mkdtemp(prefix="tb2_contact_")
+    try:
+        X = _two_cubes(work)
+        case = _contact_cases()[name]
+        for tag, suffix in (("contact_3D_penalty", "ref"), ("cuda_contact_3D_penalty", "cuda")):
+            open(os.path.join(work, "%s.%s.xml" % (name, suffix)), "w").write(CONTACT_XML % dict(case, tag=tag))
+        r0 = _run(REF_BIN, os.path.join(work, name + ".ref.xml"))
+        assert r0.returncode == 0 and "End Execution" in r0.stdout, r0.stdout[-3000:]
+        r1 = _run(PLUGIN_BIN, os.path.join(work, name + ".cuda.xml"))
+        assert r1.returncode == 0 and "End Execution" in r1.stdout and "ExceptionT::Throw" not in r1.stdout, r1.stdout[-3000:]
+        a = _nodal_output(os.path.join(work, name + ".ref.io0.run"))
+        b = _nodal_output(os.path.join(work, name + ".cuda.io0.run"))
+        assert a.shape == b.shape and a.shape[0] == X.shape[0]
+        assert np.abs(a).max() > 1e-3
+        assert np.abs(a - b).max() < 1e-9 * np.abs(a).max()
+        # contact did happen: the lower cube moved although nothing else loads it
+        assert np.abs(a[: X.shape[0] // 2, :3]).max() > 1e-4
     finally:
         shutil.rmtree(work, ignore_errors=True)
