@@ -201,6 +201,7 @@ struct tb2_matrix {
     tb2::DevBuf<double> scal;     // reduction scalars
     tb2::DevBuf<double> partial;  // per-block partial sums
     tb2::DevBuf<unsigned char> eq_owned; // multi-GPU: 1 if this rank owns the equation's node (dot products count it once)
+    bool values_zero = false;            // val is all zero: set by tb2_matrix_clear, dropped by every assembly / set_values
     tb2::DevBuf<int> eq_xidx;            // multi-GPU over peer memory: entry of the exchange buffer an interface equation maps to, -1 elsewhere
     tb2::DevBuf<double> s, partial_if;   // multi-GPU PCG: s = A p of the single-reduction recurrence; (A u, u) partials of the interface rows
     tb2::DevBuf<double> bi_rhat, bi_v, bi_s, bi_t; // BiCGStab work vectors (tb2_matrix_bicgstab), allocated on first use

@@ -805,6 +805,7 @@ int tb2_matrix_set_values(tb2_matrix* A, const double* h_val)
     DeviceGuard dg(A->ctx->device);
     TB2_CUDA(cudaMemcpyAsync(A->val.p, h_val, A->nnz * sizeof(double), cudaMemcpyHostToDevice, A->ctx->stream));
     TB2_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    A->values_zero = false;
     return TB2_OK;
 }
 int tb2_matrix_nnz(const tb2_matrix* A, int64_t* nnz)
@@ -856,6 +857,7 @@ int tb2_matrix_clear(tb2_matrix* A)
     tb2_mesh* m = A->ctx;
     DeviceGuard dg(m->device);
     TB2_CUDA(cudaMemsetAsync(A->val.p, 0, A->nnz * sizeof(double), m->stream));
+    A->values_zero = true;
     return TB2_OK;
 }
 

@@ -422,6 +422,7 @@ struct GatherArgs {
     int64_t n0, n1;        // row nodes of this launch
     int64_t e0, e1;        // element chunk held by the scratch ke[e - e0][rec]
     int sym;               // 1: records are packed upper triangles (300 entries), 0: full 24 x 24 (576)
+    int fresh;             // 1: val is known to be all zero (tb2_matrix_clear and nothing since): the running sums start from 0 unread
     const double* ke;
     const int* adj_ptr;
     const int* adj;
@@ -462,10 +463,12 @@ __global__ void __launch_bounds__(32 * kGatherWarps) k_assemble_gather(const Gat
         if ((j == 0 ? q0 : (j == 1 ? q1 : q2)) <= 0) continue; // inactive column
         const int col = __ldg(g.adj_coloff + blk) + (j > 0 && q0 > 0) + (j > 1 && q1 > 0);
         // the running sums start from the stored entries, so that chunking never changes the order of the additions:
-        // val + k_e1 + k_e2 + ... in ascending element order whatever the chunk boundaries are
+        // val + k_e1 + k_e2 + ... in ascending element order whatever the chunk boundaries are (a matrix known to be all zero is not read)
         double acc[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) acc[i] = row[i] >= 0 ? g.val[row[i] + col] : 0.0;
+        for (int i = 0; i < 3; i++) acc[i] = (row[i] >= 0 && !g.fresh) ? g.val[row[i] + col] : 0.0;
+        // (issuing a block's <= 8 contributions together -- codes first, then all 24 record loads -- was measured: 87 registers and
+        // predicated loads for the short blocks made the gather 2 ms slower, r02q)
         for (; c < c1; c++) {
             const unsigned code = __ldg(g.contrib + c);
             const int64_t e = code >> 6;
@@ -754,6 +757,7 @@ static int form_stiffness_coloured(tb2_group* g, tb2_matrix* A, const double* d_
     p.adj_coloff = A->adj_coloff.p;
     p.elem_adjpos = A->elem_adjpos.p;
     p.val = A->val.p;
+    A->values_zero = false;
     const size_t smem = (size_t)8 * kIpDoubles * kElemsPerBlock * sizeof(double);
     TB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int c = 0; c < m->ncolours; c++) {
@@ -807,10 +811,12 @@ int tb2_form_stiffness(tb2_group* g, tb2_matrix* A, const double* d_u, const dou
         ga.e1 = p.e1;
         ga.n0 = A->k3_nmin[c];
         ga.n1 = (int64_t)A->k3_nmax[c] + 1;
+        ga.fresh = (A->values_zero && c == 0) ? 1 : 0;
         ProfScope ps(m, kProfStiffness, 2);
         k<<<(unsigned)((p.e1 - p.e0 + kElemsPerBlock - 1) / kElemsPerBlock), 128, smem, m->stream>>>(p);
         k_assemble_gather<<<(unsigned)((ga.n1 - ga.n0 + kGatherWarps - 1) / kGatherWarps), 32 * kGatherWarps, 0, m->stream>>>(ga);
     }
+    A->values_zero = false;
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
 }
@@ -899,10 +905,12 @@ int tb2_form_mass(tb2_group* g, tb2_matrix* A, int mass_type, double constM)
         ga.e1 = ga.e0 + A->k3_chunk < m->ne ? ga.e0 + A->k3_chunk : m->ne;
         ga.n0 = A->k3_nmin[c];
         ga.n1 = (int64_t)A->k3_nmax[c] + 1;
+        ga.fresh = (A->values_zero && c == 0) ? 1 : 0;
         ProfScope ps(m, kProfStiffness, 2);
         TB2_CHECK(launch_element_mass(g, mass_type, constM, ga.e0, ga.e1, A->ke.p));
         k_assemble_gather<<<(unsigned)((ga.n1 - ga.n0 + kGatherWarps - 1) / kGatherWarps), 32 * kGatherWarps, 0, m->stream>>>(ga);
     }
+    A->values_zero = false;
     TB2_CUDA(cudaGetLastError());
     return TB2_OK;
 }
