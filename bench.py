@@ -818,7 +818,7 @@ def run_contact(torch, capi, tmesh, local, n, steps):
     ok = bool(np.isfinite(d).all())
     ex.close(); contact.close(); g.close(); m.close()
     if not ok or ncontact == 0:
-        raise SystemExit("bench.py: contact leg: non-finite state or no pair in contact")
+        raise RuntimeError("contact leg: non-finite state or no pair in contact")
     return {"value": conn.shape[0] / (out["with_contact"] * 1e-3), "unit": METRIC, "ms_per_step": out["with_contact"],
             "ms_per_step_without_contact": out["without_contact"], "contact_kernels_ms_per_step": float(ms_cat[7]) / 20, "pairs": int(pairs.shape[0]),
             "pairs_in_contact": int(ncontact), "deepest_penetration": float(hmax), "steps": steps,
@@ -1054,7 +1054,12 @@ def run_gpu_arm(args):
     if world == 1 and not args.no_explicit_solid:
         xs = run_explicit_solid(torch, capi, tmesh, local, n, min(args.steps, 200), args.warmup, hbm_peak_all, not args.no_cpu_baseline)
     shuffled = run_shuffled(torch, capi, tmesh, local, n, min(args.steps, 100), dt) if (world == 1 and not args.no_shuffled) else None
-    contact = run_contact(torch, capi, tmesh, local, 79, min(args.steps, 200)) if (world == 1 and not args.no_contact) else None
+    contact = None
+    if world == 1 and not args.no_contact:
+        try:
+            contact = run_contact(torch, capi, tmesh, local, 79, min(args.steps, 200))
+        except Exception as e:  # a side leg must not cost the line
+            contact = {"error": str(e)[-300:]}
     j2 = None
     if world == 1 and args.nlpcg_n > 0:
         j2 = run_nlpcg_j2(torch, capi, tmesh, local, args.nlpcg_n, args.nlpcg_iters)
