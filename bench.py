@@ -766,8 +766,39 @@ def run_shuffled(torch, capi, tmesh, local, n, steps, dt):
     ex.close(); g.close(); m.close()
     if not ok:
         raise SystemExit("bench.py: non-finite state on the shuffled mesh")
+    # the same shuffled mesh after the host-side locality renumbering a caller can apply before tb2_mesh_create (tahoe_b200.mesh.renumber)
+    t0 = time.perf_counter()
+    Xr, conn_r, ns_r, new_of_old = tmesh.renumber(Xs, conn_s, {1: nperm[ns[1]]})
+    t_renumber = time.perf_counter() - t0
+    m = capi.Mesh(Xr, conn_r, device=local)
+    g = capi.Group(m, capi.TOTAL_LAGRANGIAN, capi.material(MATERIAL))
+    ex = capi.Explicit(g)
+    code = np.zeros(Xr.shape, np.uint8)
+    code[ns_r[1]] = 1
+    ex.set_bc(code, np.zeros_like(Xr), np.zeros_like(Xr))
+    ex.set_state(initial_displacement(Xr), np.zeros_like(Xr), np.zeros_like(Xr))
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
+    ex.run(dt, 5)
+    m.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ex.run(dt, steps)
+    e1.record(stream)
+    m.synchronize()
+    torch.cuda.synchronize()
+    ms_r = e0.elapsed_time(e1)
+    dr = ex.get_state()[0]
+    ex.close(); g.close(); m.close()
+    # both runs took 5 + steps steps from the same physical state: the renumbered result, mapped back, is the shuffled one
+    same = float(np.abs(dr[new_of_old] - d).max() / max(np.abs(d).max(), 1e-300))
+    if not same < 1e-10:
+        raise SystemExit("bench.py: the renumbered mesh gives a different answer (%.3e)" % same)
     return {"value": conn.shape[0] * steps / (ms * 1e-3), "unit": METRIC, "ms_per_step": ms / steps, "steps": steps,
-            "workload": "the same %d^3 cube with node and element numbers permuted at random (seed 7)" % n}
+            "workload": "the same %d^3 cube with node and element numbers permuted at random (seed 7)" % n,
+            "after_locality_renumbering": {"value": conn.shape[0] * steps / (ms_r * 1e-3), "ms_per_step": ms_r / steps,
+                                           "host_seconds": t_renumber, "max_rel_difference_mapped_back": same,
+                                           "note": "tahoe_b200.mesh.renumber on the host before tb2_mesh_create: nodes by (z cell, y cell, x), "
+                                                   "elements by the same key of their centroid"}}
 
 
 def run_contact(torch, capi, tmesh, local, n, steps):

@@ -196,3 +196,38 @@ def partition_mesh(coords, conn, nranks, rank, nodesets=None, owner=None):
     part["n_global_interface"] = len(gi)
     part["owned"] = (lowest[node_gid] == rank).astype(np.uint8)
     return part
+
+
+def locality_order(coords, conn):
+    """A renumbering for meshes whose node / element numbers carry no locality (mesh generators, merged parts): the kernels gather
+    nodal data by element and element forces by node, so their memory traffic follows the numbering (bench.py `shuffled_numbering`:
+    a randomly numbered cube runs at 0.43 of the structured one).  The reference accepts any numbering and offers bandwidth
+    renumbering for its direct solvers; this is the analogue for the gathers: nodes sorted by (z cell, y cell, x) and elements by the
+    same key of their centroid, cells of one mean element edge -- on a grid-like mesh that restores rows of consecutive nodes.
+
+    Returns (new_of_old_node [nn], elem_order [ne]): new coordinates are coords[argsort(new_of_old_node)], new connectivity
+    new_of_old_node[conn[elem_order]]; a nodal result r_new maps back as r_old = r_new[new_of_old_node]."""
+    coords = np.asarray(coords, np.float64)
+    conn = np.asarray(conn)
+    lo, hi = coords.min(axis=0), coords.max(axis=0)
+    h = (np.prod(np.maximum(hi - lo, 1e-300)) / max(conn.shape[0], 1)) ** (1.0 / 3.0)
+
+    def key(p, shift):
+        cell = np.floor((p - lo) / h + shift).astype(np.int64)
+        return np.lexsort((p[:, 0], cell[:, 1], cell[:, 2]))  # last key is the primary one
+
+    node_sorted = key(coords, 0.5)  # old ids in their new order; nodes sit near cell corners, centroids near cell centres
+    new_of_old = np.empty(coords.shape[0], np.int64)
+    new_of_old[node_sorted] = np.arange(coords.shape[0])
+    elem_order = key(coords[conn].mean(axis=1), 0.0)
+    return new_of_old.astype(np.int32), elem_order.astype(np.int64)
+
+
+def renumber(coords, conn, nodesets=None):
+    """coords, conn (and node sets) in the numbering of locality_order, plus the map back: (X, conn, nodesets, new_of_old_node)"""
+    new_of_old, elem_order = locality_order(coords, conn)
+    X = np.empty_like(np.asarray(coords, np.float64))
+    X[new_of_old] = coords
+    c = np.ascontiguousarray(new_of_old[np.asarray(conn)[elem_order]].astype(np.int32))
+    ns = {k: np.sort(new_of_old[v]).astype(np.int32) for k, v in (nodesets or {}).items()}
+    return X, c, ns, new_of_old
