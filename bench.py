@@ -776,7 +776,9 @@ def run_shuffled(torch, capi, tmesh, local, n, steps, dt):
     code = np.zeros(Xr.shape, np.uint8)
     code[ns_r[1]] = 1
     ex.set_bc(code, np.zeros_like(Xr), np.zeros_like(Xr))
-    ex.set_state(initial_displacement(Xr), np.zeros_like(Xr), np.zeros_like(Xr))
+    u_r = np.empty_like(Xr)
+    u_r[new_of_old] = initial_displacement(Xs)  # the field of the shuffled run, node by node (its noise term goes by node number)
+    ex.set_state(u_r, np.zeros_like(Xr), np.zeros_like(Xr))
     stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local))
     ex.run(dt, 5)
     m.synchronize()
