@@ -321,28 +321,60 @@ int tb2_geom_open(const char* path, tb2_geom** out)
         g->sidesets[k].id = (int)id;
         g->sidesets[k].block = (int)blk;
     }
+    // a set's body is inline, or the name of a file (relative to the main file) that holds it -- as for element sets and nodes
+    // (ModelFileT::GetNodeSet / GetSideSet follow the same external-file convention, tri3.geom, quad4.*.geom)
+    auto set_body = [&](Cursor& cur, std::vector<char>& ext_buf, Cursor& body, std::string& where) -> bool {
+        Cursor look = cur;
+        const char *tb, *te;
+        int64_t tmp;
+        if (!next_token(look, tb, te)) return false;
+        if (to_i64(tb, te, tmp)) { // inline: the body starts here and the main cursor moves along with it
+            body = cur;
+            where = file;
+            return true;
+        }
+        cur = look;
+        where = dir + "/" + std::string(tb, te);
+        if (!read_file(where, ext_buf)) return false;
+        body = Cursor{ext_buf.data(), ext_buf.data() + ext_buf.size()};
+        return true;
+    };
     if (!expect(c, "*nodesets")) return fail("expected *nodesets", file);
     for (int64_t k = 0; k < nns; k++) {
-        if (!expect(c, "*set") || !next_int(c, v) || v != ns_len[k]) return fail("bad node set", file);
+        if (!expect(c, "*set")) return fail("bad node set", file);
+        std::vector<char> ext_buf;
+        Cursor body{nullptr, nullptr};
+        std::string where;
+        if (!set_body(c, ext_buf, body, where)) return fail("cannot read node set", where.empty() ? file : where);
+        const bool inline_body = where == file;
+        if (!next_int(body, v) || v != ns_len[k]) return fail("bad node set", where);
         auto& nodes = g->nodesets[k].nodes;
         nodes.resize((size_t)v);
         for (auto& n : nodes) {
             int64_t id;
-            if (!next_int(c, id) || id == 0 || id > g->nn) return fail("bad node set entry", file);
+            if (!next_int(body, id) || id == 0 || id > g->nn) return fail("bad node set entry", where);
             n = id < 0 ? -1 : (int32_t)(id - 1); // a negative entry is the reference's "all model nodes" marker (beam.1.geom): kept as -1
         }
+        if (inline_body) c = body;
     }
     if (!expect(c, "*sidesets")) return fail("expected *sidesets", file);
     for (int64_t k = 0; k < nss; k++) {
-        if (!expect(c, "*set") || !next_int(c, v) || v != ss_len[k]) return fail("bad side set", file);
+        if (!expect(c, "*set")) return fail("bad side set", file);
+        std::vector<char> ext_buf;
+        Cursor body{nullptr, nullptr};
+        std::string where;
+        if (!set_body(c, ext_buf, body, where)) return fail("cannot read side set", where.empty() ? file : where);
+        const bool inline_body = where == file;
+        if (!next_int(body, v) || v != ss_len[k]) return fail("bad side set", where);
         auto& sides = g->sidesets[k].sides;
         sides.resize((size_t)v * 2);
         for (int64_t s = 0; s < v; s++) {
             int64_t el, fc;
-            if (!next_int(c, el) || !next_int(c, fc) || el < 1 || fc < 1) return fail("bad side set entry", file);
+            if (!next_int(body, el) || !next_int(body, fc) || el < 1 || fc < 1) return fail("bad side set entry", where);
             sides[2 * s] = (int32_t)(el - 1);
             sides[2 * s + 1] = (int32_t)(fc - 1);
         }
+        if (inline_body) c = body;
     }
     timer.mark("dimensions, node/side sets");
     if (!expect(c, "*elements")) return fail("expected *elements", file);

@@ -158,3 +158,47 @@ def test_reference_geometry_files_as_the_reference_reads_them(capi, geom, fixtur
     assert np.array_equal(X, c.X) and np.array_equal(np.concatenate(blocks), c.conn)
     assert all(np.array_equal(ns[k], np.where(c.nodesets[k] < 0, -1, c.nodesets[k])) for k in c.nodesets)
     assert all(np.array_equal(ss[k], c.sidesets[k]) for k in c.sidesets)
+
+
+def test_node_sets_and_side_sets_in_external_files(capi):
+    """the bodies of node sets and side sets may live in files the main file names (tri3.geom, quad4.*.geom of the reference): the
+    same arrays as with the bodies inline, and side sets keep their element block"""
+    import re
+    work = tempfile.mkdtemp(prefix="tb2_geom_")
+    try:
+        n = 4
+        X, conn, ns = ti.structured_cube(n, jitter=0.1)
+        ss = ti.cube_side_sets(n)
+        inline = os.path.join(work, "inline.geom")
+        ti.write_geom(inline, X, conn, ns, sidesets={1: ss[6], 2: ss[5]}, block_sizes=[2 * n * n, 2 * n * n], sideset_blocks={1: 1, 2: 2})
+        text = open(inline).read()
+        head, rest = text.split("*nodesets\n", 1)
+        nodesets, rest = rest.split("# end node sets\n*sidesets\n", 1)
+        sidesets, rest = rest.split("*elements\n", 1)
+        out = head + "*nodesets\n"
+        for k, body in enumerate([b for b in nodesets.split("*set\n") if b.strip()]):
+            name = "split.geom.ns%d" % k
+            if k % 2 == 0:  # every other set goes to its own file
+                open(os.path.join(work, name), "w").write(body)
+                out += "*set\n%s\n" % name
+            else:
+                out += "*set\n" + body
+        out += "# end node sets\n*sidesets\n"
+        for k, body in enumerate([b for b in sidesets.split("*set\n") if b.strip()]):
+            name = "split.geom.ss%d" % k
+            open(os.path.join(work, name), "w").write(body)
+            out += "*set\n%s\n" % name
+        out += "*elements\n" + rest
+        split = os.path.join(work, "split.geom")
+        open(split, "w").write(out)
+        a, b = capi.read_geom(inline), capi.read_geom(split)
+        assert np.array_equal(a[0], b[0]) and all(np.array_equal(p, q) for p, q in zip(a[1], b[1]))
+        assert sorted(a[2]) == sorted(b[2]) == sorted(ns) and all(np.array_equal(a[2][k], b[2][k]) for k in a[2])
+        assert sorted(a[3]) == sorted(b[3]) == [1, 2] and all(np.array_equal(a[3][k], b[3][k]) for k in a[3])
+        assert all(np.array_equal(b[2][k], np.asarray(ns[k])) for k in ns)
+        assert np.array_equal(b[3][1], np.asarray(ss[6])) and np.array_equal(b[3][2], np.asarray(ss[5]))
+        os.remove(os.path.join(work, "split.geom.ss1"))
+        with pytest.raises(capi.Tb2Error):
+            capi.read_geom(split)  # a named file that does not exist
+    finally:
+        shutil.rmtree(work, ignore_errors=True)

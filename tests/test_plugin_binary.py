@@ -498,3 +498,41 @@ def test_plugin_contact_reproduces_reference_output(name):
         assert np.abs(a[: X.shape[0] // 2, :3]).max() > 1e-4
     finally:
         shutil.rmtree(work, ignore_errors=True)
+
+
+# ---- the threaded .geom reader behind ModelManagerT (FastGeomInputT) -- host-only analyses, no GPU needed ----------
+
+@needs_bins
+@pytest.mark.parametrize("case", ["static_one_block", "contact_two_blocks"])
+def test_plugin_reads_geometry_through_the_fast_reader(case):
+    """The plugin executable registers FastGeomInputT for TahoeII files (IOBaseT::NewInput): coordinates, connectivities, node sets and
+    side sets of every run come from tb2_geom_open.  Classic inputs (no cuda_* tag) therefore run entirely on the host through the new
+    reader and must reproduce the reference executable's output: a one-block static analysis with nodal loads on node sets, and the
+    two-block contact case whose surfaces are side sets of different element blocks."""
+    work = tempfile.mkdtemp(prefix="tb2_fastgeom_")
+    try:
+        if case == "static_one_block":
+            desc, _ = _cases()["static_ss_kstv_pcg"]
+            ref_xml = _write(work, case, desc, False, None)
+            cuda_xml = os.path.join(work, case + ".plugin.xml")
+            shutil.copy(ref_xml, cuda_xml)
+            nn = 6 ** 3
+        else:
+            X = _two_cubes(work)
+            nn = X.shape[0]
+            ref_xml, cuda_xml = os.path.join(work, case + ".ref.xml"), os.path.join(work, case + ".plugin.xml")
+            for path in (ref_xml, cuda_xml):
+                open(path, "w").write(CONTACT_XML % dict(_contact_cases()["static_push"], tag="contact_3D_penalty"))
+        r0 = _run(REF_BIN, ref_xml)
+        assert r0.returncode == 0 and "End Execution" in r0.stdout, r0.stdout[-2000:]
+        r1 = _run(PLUGIN_BIN, cuda_xml)
+        assert r1.returncode == 0 and "End Execution" in r1.stdout and "ExceptionT::Throw" not in r1.stdout, r1.stdout[-3000:]
+        log = open(os.path.splitext(cuda_xml)[0] + ".out").read()
+        assert "FastGeomInputT: %d nodes" % nn in log and "parsed by tb2_geom_open" in log
+        assert "reading through TahoeInputT" not in log
+        a = _nodal_output(os.path.splitext(ref_xml)[0] + ".io0.run")
+        b = _nodal_output(os.path.splitext(cuda_xml)[0] + ".io0.run")
+        assert a.shape == b.shape and a.shape[0] == nn and np.abs(a).max() > 1e-6
+        assert np.array_equal(a, b)  # the same host code on the same arrays: identical output
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
