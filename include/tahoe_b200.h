@@ -399,6 +399,19 @@ int tb2_newton_solve_dynamic_host(tb2_nlpcg* work, tb2_matrix* A, const tb2_newt
                                   int64_t* linear_iterations);
 
 /* ---- multi-GPU (replaces CommManagerT::AllGather / CommunicatorT::Sum) ------------ */
+/* ---- element partition for the one-process-per-GPU path (host code, no CUDA calls) -- DecomposeT / GraphBaseT::Partition's role
+ * (DecomposeT.cpp:362-592, GraphBaseT.cpp:185-270).  tb2_partition_rcb: owner rank of every element by recursive coordinate
+ * bisection of the element centroids (longest extent, weighted median: any rank count; deterministic).  tb2_partition_part: one
+ * rank's part from ANY element -> rank map (this one or a graph partitioner's): call it with the output arrays NULL for the sizes,
+ * then with arrays of those sizes.  Local nodes are numbered by ascending global id, elements keep their global order;
+ * h_if_nodes / h_if_slots / h_node_owned are what tb2_comm_init takes. */
+int tb2_partition_rcb(int64_t num_nodes, int64_t num_elements, const int32_t* h_conn /*[ne][8]*/, const double* h_coords /*[nn][3]*/,
+                      int nparts, int32_t* h_owner /*[ne]*/);
+int tb2_partition_part(int64_t num_nodes, int64_t num_elements, const int32_t* h_conn, const int32_t* h_owner, int nparts, int rank,
+                       int64_t* num_local_nodes, int64_t* num_local_elements, int64_t* num_interface_nodes,
+                       int64_t* num_global_interface_nodes, int64_t* h_node_gid /*[local nodes]*/, int64_t* h_elem_gid /*[local elements]*/,
+                       int32_t* h_local_conn /*[local elements][8]*/, int32_t* h_if_nodes, int32_t* h_if_slots, uint8_t* h_node_owned);
+
 /* One process per GPU.  The harness creates an NCCL unique id on rank 0, distributes it by its own
  * means, and every rank calls tb2_comm_init on its mesh.  h_interface_nodes are this rank's local node
  * ids of nodes shared with other ranks, h_interface_slots their positions in the packed global interface

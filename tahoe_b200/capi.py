@@ -44,7 +44,7 @@ tb2_form_stiffness_diagonal tb2_form_stiffness_diagonal_host
 tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpcg_counters tb2_newton_solve tb2_newton_solve_host
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_copy_diagonal_host tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
-tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_comm_peer_disable tb2_secant_search_host
+tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_comm_peer_disable tb2_partition_rcb tb2_partition_part tb2_secant_search_host
 tb2_explicit_attach_contact tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking""".split()
 
 
@@ -274,6 +274,28 @@ class Mesh(_Handle):
 
     def sum_interface(self, d_nodal):
         _chk(lib().tb2_comm_sum_interface(self.h, _dp(d_nodal)))
+
+
+def partition_rcb(coords, conn, nparts):
+    """tb2_partition_rcb: owner rank of every element"""
+    coords, conn = _f64(coords), np.ascontiguousarray(conn, np.int32)
+    owner = np.zeros(conn.shape[0], np.int32)
+    _chk(lib().tb2_partition_rcb(C.c_int64(coords.shape[0]), C.c_int64(conn.shape[0]), _p(conn), _p(coords), int(nparts), _p(owner)))
+    return owner
+
+
+def partition_part(nn, conn, owner, nparts, rank):
+    """tb2_partition_part: (node_gid, elem_gid, local_conn, if_nodes, if_slots, n_global_interface, owned) of one rank"""
+    conn, owner = np.ascontiguousarray(conn, np.int32), np.ascontiguousarray(owner, np.int32)
+    n = [C.c_int64(0) for _ in range(4)]
+    args = (C.c_int64(nn), C.c_int64(conn.shape[0]), _p(conn), _p(owner), int(nparts), int(rank))
+    _chk(lib().tb2_partition_part(*args, C.byref(n[0]), C.byref(n[1]), C.byref(n[2]), C.byref(n[3]), None, None, None, None, None, None))
+    nl, nel, nif, nglob = (v.value for v in n)
+    node_gid, elem_gid = np.zeros(nl, np.int64), np.zeros(nel, np.int64)
+    lconn, if_nodes, if_slots, owned = np.zeros((nel, 8), np.int32), np.zeros(nif, np.int32), np.zeros(nif, np.int32), np.zeros(nl, np.uint8)
+    _chk(lib().tb2_partition_part(*args, C.byref(n[0]), C.byref(n[1]), C.byref(n[2]), C.byref(n[3]), _p(node_gid), _p(elem_gid), _p(lconn),
+                                  _p(if_nodes), _p(if_slots), _p(owned)))
+    return node_gid, elem_gid, lconn, if_nodes, if_slots, nglob, owned
 
 
 def comm_unique_id():

@@ -124,7 +124,8 @@ def general_mesh_phase(rank, world, local):
     Xs[nperm] = X
     conn_s = np.ascontiguousarray(nperm[conn][rng.permutation(conn.shape[0])].astype(np.int32))
     ns_s = {k: np.sort(nperm[v]).astype(np.int32) for k, v in ns.items()}
-    part = tmesh.partition_mesh(Xs, conn_s, world, rank, ns_s)
+    # element owners from the library's own partitioner (tb2_partition_rcb), the rank's description from the harness
+    part = tmesh.partition_mesh(Xs, conn_s, world, rank, ns_s, owner=capi.partition_rcb(Xs, conn_s, world))
     uid = [capi.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     comm = (rank, world, uid[0], part["if_nodes"], part["if_slots"], part["n_global_interface"], part["owned"])
