@@ -1,11 +1,13 @@
 /* CudaExplicitSolverT.cpp -- see CudaExplicitSolverT.h */
 #include "CudaExplicitSolverT.h"
 
+#include "CudaPenaltyContact3DT.h"
 #include "CudaSolidElementT.h"
 #include "ElementBaseT.h"
 #include "ExceptionT.h"
 #include "FEManagerT.h"
 #include "FieldT.h"
+#include "NodeManagerT.h"
 #include "ParameterListT.h"
 #include "TimeManagerT.h"
 #include "iArray2DT.h"
@@ -36,6 +38,7 @@ CudaExplicitSolverT::CudaExplicitSolverT(FEManagerT& fe_manager, int group):
 	SolverT(fe_manager, group),
 	fEx(NULL),
 	fDev(NULL),
+	fContact(NULL),
 	fHasLoads(false),
 	fLoadsChecked(false),
 	fSteps(0),
@@ -76,16 +79,20 @@ CudaStiffnessSourceT* CudaExplicitSolverT::FindDeviceGroup(void) const
 {
 	const char caller[] = "CudaExplicitSolverT::FindDeviceGroup";
 	CudaStiffnessSourceT* found = NULL;
+	CudaPenaltyContact3DT* contact = NULL;
 	for (int i = 0; i < fFEManager.NumElementGroups(); i++) {
 		ElementBaseT* group = fFEManager.ElementGroup(i);
 		if (!group->InGroup(Group())) continue;
+		CudaPenaltyContact3DT* c = dynamic_cast<CudaPenaltyContact3DT*>(group);
+		if (c && !contact) { contact = c; continue; } /* one contact group rides along: its force is formed inside the device step */
 		CudaStiffnessSourceT* dev = dynamic_cast<CudaStiffnessSourceT*>(group);
 		if (!dev || found)
-			ExceptionT::BadInputValue(caller, "CUDA_explicit_solver needs exactly one cuda_* continuum element group in its solver group "
-				"(element group %d is %s)", i + 1, dev ? "a second one" : "a host group");
+			ExceptionT::BadInputValue(caller, "CUDA_explicit_solver needs exactly one cuda_* continuum element group (and at most one "
+				"cuda_contact_3D_penalty group) in its solver group (element group %d is %s)", i + 1, dev ? "a second one" : "a host group");
 		found = dev;
 	}
 	if (!found) ExceptionT::BadInputValue(caller, "no cuda_* element group in solver group %d", Group() + 1);
+	const_cast<CudaExplicitSolverT*>(this)->fContact = contact;
 	return found;
 }
 
@@ -121,6 +128,11 @@ void CudaExplicitSolverT::Setup(CudaStiffnessSourceT* dev)
 	fHasLoads = const_cast<FieldT&>(field).ForceBC().Length() > 0;
 	integrator->SetResident(true);
 	fDev = dev;
+	if (fContact) {
+		if (fContact->DeviceMesh() != dev->DeviceMesh())
+			ExceptionT::GeneralFail(caller, "the contact group and the continuum group do not share a device mesh");
+		Check(tb2_explicit_attach_contact(fEx, fContact->DeviceContact()), caller);
+	}
 }
 
 SolverT::SolutionStatusT CudaExplicitSolverT::Solve(int)
@@ -167,9 +179,11 @@ SolverT::SolutionStatusT CudaExplicitSolverT::Solve(int)
 			fLHS_lock = kIgnore;
 			fRHS = 0.0;
 			fDev->MuteInternalForce(true);
+			if (fContact) fContact->MuteForce(true);
 			try { fFEManager.FormRHS(Group()); }
-			catch (ExceptionT::CodeT code) { fDev->MuteInternalForce(false); throw code; }
+			catch (ExceptionT::CodeT code) { fDev->MuteInternalForce(false); if (fContact) fContact->MuteForce(false); throw code; }
 			fDev->MuteInternalForce(false);
+			if (fContact) fContact->MuteForce(false);
 			fRHS_lock = kLocked;
 			double biggest = 0.0;
 			for (int k = 0; k < ndof; k++) {
@@ -183,9 +197,22 @@ SolverT::SolutionStatusT CudaExplicitSolverT::Solve(int)
 			if (fHasLoads || biggest > 0.0) Check(tb2_explicit_set_bc(fEx, NULL, NULL, &fFext[0]), caller);
 		}
 
-		/* predictor + KBC values, internal force, a = M^-1 R, corrector: one call, nothing crosses the bus */
+		/* the pair list the last relaxation left (sent only when the search changed it) */
+		if (fContact) fContact->DeviceContact();
+
+		/* predictor + KBC values, internal force (+ contact force on the predicted state), a = M^-1 R, corrector: one call */
 		Check(tb2_explicit_run(fEx, fFEManager.TimeStep(), 1, NULL, NULL), caller);
 		fSteps++;
+
+		/* relaxation as LinearSolver::Solve does after its update (LinearSolver.cpp:76-90): the reference's contact search reads the
+		 * current coordinates on the host, so with a contact group the new displacements come down every step (d only; v, a stay) */
+		if (fContact) {
+			FieldT& host_field = const_cast<FieldT&>(field);
+			Check(tb2_explicit_get_state(fEx, host_field[0].Pointer(), NULL, NULL), caller);
+			fFEManager.NodeManager()->UpdateCurrentCoordinates();
+			GlobalT::RelaxCodeT relaxcode = fFEManager.RelaxSystem(Group());
+			if (relaxcode == GlobalT::kReEQ || relaxcode == GlobalT::kReEQRelax) fFEManager.SetEquationSystem(Group());
+		}
 		return kConverged;
 	}
 	catch (ExceptionT::CodeT code) {

@@ -28,6 +28,7 @@
 namespace Tahoe {
 
 class CudaStiffnessSourceT;
+class CudaPenaltyContact3DT;
 class FieldT;
 
 class CudaExplicitCDIntegrator: public ExplicitCDIntegrator
@@ -86,6 +87,7 @@ private:
 
 	tb2_explicit* fEx;
 	CudaStiffnessSourceT* fDev;
+	CudaPenaltyContact3DT* fContact;   /**< a cuda_contact_3D_penalty group of the solver group: its force is formed in the device step */
 	std::vector<int64_t> fPrescribed;  /**< nodal dof indices 3 n + i with a kinematic boundary condition */
 	std::vector<double> fPrescribedValue, fScratch;
 	std::vector<double> fFext;         /**< [nn][3] external load of the step */

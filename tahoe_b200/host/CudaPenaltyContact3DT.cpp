@@ -18,6 +18,7 @@ CudaPenaltyContact3DT::CudaPenaltyContact3DT(const ElementSupportT& support, con
 	PenaltyContact3DT(support),
 	fMesh(NULL),
 	fOwnMesh(false),
+	fMuted(false),
 	fContact(NULL)
 {
 	SetName(name);
@@ -94,7 +95,7 @@ void CudaPenaltyContact3DT::RHSDriver(void)
 	const char caller[] = "CudaPenaltyContact3DT::RHSDriver";
 	double constKd = 0.0;
 	int formKd = fIntegrator->FormKd(constKd);
-	if (!formKd) return;
+	if (!formKd || fMuted) return;
 	EnsureDevice();
 	SyncPairs();
 

@@ -32,8 +32,14 @@ public:
 
 	virtual void TakeParameterList(const ParameterListT& list);
 
-	/** the group's device object (a resident explicit step attaches it with tb2_explicit_attach_contact) */
+	/** the group's device object with the current pair list (a resident explicit step attaches it with tb2_explicit_attach_contact) */
 	tb2_contact* DeviceContact(void);
+
+	/** while set, RHSDriver() adds nothing: a resident solver that attached the group forms the contact force on the device itself */
+	void MuteForce(bool mute) { fMuted = mute; }
+
+	/** the mesh the device object lives on */
+	tb2_mesh* DeviceMesh(void) { EnsureDevice(); return fMesh; }
 
 protected:
 
@@ -47,6 +53,7 @@ private:
 
 	tb2_mesh* fMesh;        /**< shared with a cuda_* continuum group, or own (coordinates only) */
 	bool fOwnMesh;
+	bool fMuted;
 	tb2_contact* fContact;
 	dArray2DT fForce;       /**< nodal contact forces of the last evaluation */
 	std::vector<int> fPairsSent;   /**< the pair list the device holds */

@@ -418,7 +418,7 @@ CONTACT_XML = """<?xml version="1.0"?>
         </field>
     </nodes>
     <element_list>
-        <updated_lagrangian field_name="displacement"%(mass)s>
+        <%(solid_tag)s field_name="displacement"%(mass)s>
             <hexahedron/>
             <solid_element_nodal_output displacements="1"/>
             <large_strain_element_block>
@@ -427,7 +427,7 @@ CONTACT_XML = """<?xml version="1.0"?>
                     <Simo_isotropic density="1.0"><E_and_nu Poisson_ratio="0.25" Young_modulus="100.0"/></Simo_isotropic>
                 </large_strain_material_3D>
             </large_strain_element_block>
-        </updated_lagrangian>
+        </%(solid_tag)s>
         <%(tag)s field_name="displacement" %(contact_attrs)s>
             <contact_surface><surface_side_set side_set_ID="1"/></contact_surface>
             <contact_surface><surface_side_set side_set_ID="2"/></contact_surface>
@@ -484,7 +484,7 @@ def test_plugin_contact_reproduces_reference_output(name):
         X = _two_cubes(work)
         case = _contact_cases()[name]
         for tag, suffix in (("contact_3D_penalty", "ref"), ("cuda_contact_3D_penalty", "cuda")):
-            open(os.path.join(work, "%s.%s.xml" % (name, suffix)), "w").write(CONTACT_XML % dict(case, tag=tag))
+            open(os.path.join(work, "%s.%s.xml" % (name, suffix)), "w").write(CONTACT_XML % dict(case, tag=tag, solid_tag="updated_lagrangian"))
         r0 = _run(REF_BIN, os.path.join(work, name + ".ref.xml"))
         assert r0.returncode == 0 and "End Execution" in r0.stdout, r0.stdout[-3000:]
         r1 = _run(PLUGIN_BIN, os.path.join(work, name + ".cuda.xml"))
@@ -522,7 +522,7 @@ def test_plugin_reads_geometry_through_the_fast_reader(case):
             nn = X.shape[0]
             ref_xml, cuda_xml = os.path.join(work, case + ".ref.xml"), os.path.join(work, case + ".plugin.xml")
             for path in (ref_xml, cuda_xml):
-                open(path, "w").write(CONTACT_XML % dict(_contact_cases()["static_push"], tag="contact_3D_penalty"))
+                open(path, "w").write(CONTACT_XML % dict(_contact_cases()["static_push"], tag="contact_3D_penalty", solid_tag="updated_lagrangian"))
         r0 = _run(REF_BIN, ref_xml)
         assert r0.returncode == 0 and "End Execution" in r0.stdout, r0.stdout[-2000:]
         r1 = _run(PLUGIN_BIN, cuda_xml)
@@ -534,5 +534,35 @@ def test_plugin_reads_geometry_through_the_fast_reader(case):
         b = _nodal_output(os.path.splitext(cuda_xml)[0] + ".io0.run")
         assert a.shape == b.shape and a.shape[0] == nn and np.abs(a).max() > 1e-6
         assert np.array_equal(a, b)  # the same host code on the same arrays: identical output
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_plugin_resident_explicit_run_with_contact():
+    """The impact case with everything on the device: <cuda_updated_lagrangian> + <cuda_contact_3D_penalty> under
+    integrator="CUDA_central_difference" + <CUDA_explicit_solver>.  The step (predictor, element sweep, contact force on the predicted
+    state, update) runs resident; after every step the displacements come down for the reference's own contact search
+    (ContactT::RelaxSystem) and the pair list goes up when the search changed it.  Against the classic executable: 1e-9."""
+    work = tempfile.mkdtemp(prefix="tb2_contact_res_")
+    try:
+        X = _two_cubes(work)
+        case = _contact_cases()["impact_friction_damping"]
+        name = "impact_resident"
+        open(os.path.join(work, name + ".ref.xml"), "w").write(CONTACT_XML % dict(case, tag="contact_3D_penalty", solid_tag="updated_lagrangian"))
+        resident = dict(case, integrator=' integrator="CUDA_central_difference"',
+                        solver='<CUDA_explicit_solver restart_output_inc="0"><diagonal_matrix/></CUDA_explicit_solver>')
+        open(os.path.join(work, name + ".cuda.xml"), "w").write(CONTACT_XML % dict(resident, tag="cuda_contact_3D_penalty",
+                                                                                 solid_tag="cuda_updated_lagrangian"))
+        r0 = _run(REF_BIN, os.path.join(work, name + ".ref.xml"))
+        assert r0.returncode == 0 and "End Execution" in r0.stdout, r0.stdout[-3000:]
+        r1 = _run(PLUGIN_BIN, os.path.join(work, name + ".cuda.xml"))
+        assert r1.returncode == 0 and "End Execution" in r1.stdout and "ExceptionT::Throw" not in r1.stdout, r1.stdout[-3000:]
+        a = _nodal_output(os.path.join(work, name + ".ref.io0.run"))
+        b = _nodal_output(os.path.join(work, name + ".cuda.io0.run"))
+        assert a.shape == b.shape and a.shape[0] == X.shape[0] and np.abs(a).max() > 1e-3
+        assert np.abs(a - b).max() < 1e-9 * np.abs(a).max()
+        assert np.abs(a[: X.shape[0] // 2, :3]).max() > 1e-4  # the lower cube moved: contact happened
     finally:
         shutil.rmtree(work, ignore_errors=True)
