@@ -22,6 +22,7 @@ using namespace tb2;
 
 struct tb2_contact {
     tb2_mesh* mesh = nullptr;
+    int device = 0;               // copy for tb2_contact_destroy: a host may destroy the mesh (with its element group) first
     double K = 0.0, mu = 0.0, eps = 1.0e-6, visc = 0.0;
     int64_t npairs = 0, ntouched = 0;
     tb2::DevBuf<int> pairs;       // [npairs][4]
@@ -234,6 +235,7 @@ int tb2_contact_create(tb2_mesh* m, double penalty_stiffness, double friction_co
     TB2_ARG(m && out && penalty_stiffness >= 0.0 && friction_coefficient >= 0.0 && friction_epsilon > 0.0 && viscous_damping >= 0.0);
     tb2_contact* c = new tb2_contact;
     c->mesh = m;
+    c->device = m->device;
     c->K = penalty_stiffness;
     c->mu = friction_coefficient;
     c->eps = friction_epsilon;
@@ -245,8 +247,8 @@ int tb2_contact_create(tb2_mesh* m, double penalty_stiffness, double friction_co
 int tb2_contact_destroy(tb2_contact* c)
 {
     if (!c) return TB2_OK;
-    DeviceGuard dg(c->mesh->device);
-    cudaStreamSynchronize(c->mesh->stream);
+    DeviceGuard dg(c->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError(); // not the mesh stream: the mesh may be gone already
     delete c;
     return TB2_OK;
 }
