@@ -210,8 +210,10 @@ SolverT::SolutionStatusT CudaExplicitSolverT::Solve(int)
 			FieldT& host_field = const_cast<FieldT&>(field);
 			Check(tb2_explicit_get_state(fEx, host_field[0].Pointer(), NULL, NULL), caller);
 			fFEManager.NodeManager()->UpdateCurrentCoordinates();
-			GlobalT::RelaxCodeT relaxcode = fFEManager.RelaxSystem(Group());
-			if (relaxcode == GlobalT::kReEQ || relaxcode == GlobalT::kReEQRelax) fFEManager.SetEquationSystem(Group());
+			/* the search reports kReEQ whenever pairs are active (ContactT::RelaxSystem): LinearSolver re-numbers the equations for it
+			 * every step (the pair rows are connectivities of the group).  Nothing here depends on that: the dofs and their numbers
+			 * are the same, the diagonal matrix has no structure, and the attached group assembles by node, not by its fEqnos */
+			fFEManager.RelaxSystem(Group());
 		}
 		return kConverged;
 	}
