@@ -222,6 +222,18 @@ int tb2_contact_form(tb2_contact* contact, double constKd, const double* d_u, co
                      int accumulate, double* d_f);
 int tb2_contact_form_host(tb2_contact* contact, double constKd, const double* h_u, const double* h_v, int accumulate, double* h_f);
 int tb2_contact_tracking(tb2_contact* contact, int* num_contact, double* h_max);
+/* The search on the device, for hosts that keep the whole loop resident: Contact3DT::SetActiveStrikers with Contact3DT::Intersect
+ * (Contact3DT.cpp:226-391).  tb2_contact_set_surfaces hands over what the search works on -- the triangulated contact surfaces
+ * (h_facets[nfacets][3] node triples, h_facet_surface[nfacets] the surface each belongs to, at most 32 surfaces), the striker nodes
+ * and their tributary areas (ContactT::fStrikerTags / fStrikerArea).  tb2_contact_search looks, for every striker, on the configuration
+ * X + d_u for the accepted facet of smallest |h| among the surfaces the striker is not a node of (first facet on a tie) and makes the
+ * active pairs, in striker order, the group's pair list (the reference's row order follows its search-grid traversal; the set of pairs
+ * is the same).  With such a group attached, tb2_explicit_run searches once before its first step and after every step. */
+int tb2_contact_set_surfaces(tb2_contact* contact, int64_t nfacets, const int32_t* h_facets, const int32_t* h_facet_surface,
+                             int64_t nstrikers, const int32_t* h_strikers, const double* h_striker_area);
+int tb2_contact_search(tb2_contact* contact, const double* d_u, int64_t* npairs);
+int tb2_contact_get_pairs(tb2_contact* contact, int64_t* npairs, int32_t* h_pairs /*[npairs][4] or NULL*/, double* h_area /*or NULL*/);
+int tb2_contact_has_surfaces(const tb2_contact* contact);
 
 /* ---- explicit central difference (nExplicitCD.cpp:72-139, DiagonalMatrixT.cpp:267-323, FieldT.cpp:531-556) */
 int tb2_explicit_create(tb2_group* group, tb2_explicit** ex); /* forms and inverts the lumped mass */

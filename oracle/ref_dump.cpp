@@ -21,7 +21,8 @@
  *   timing (--time: wall seconds of the step loop, steps, elements)
  *   --contact: for the first contact_3D_penalty group, at every dumped step k: cpairs_<k> (facet nodes 1-3 + striker, 0-based),
  *   carea_<k> (the pair's striker area), crhs_<k> (that group's FormRHS alone, active equations) and once cparams
- *   (penalty stiffness, friction coefficient, friction epsilon, viscous damping)
+ *   (penalty stiffness, friction coefficient, friction epsilon, viscous damping), cfacets / cfacet_surface (the triangulated contact
+ *   surfaces), cstrikers / cstriker_area (striker nodes and their tributary areas)
  */
 #include <sys/stat.h>
 #include <chrono>
@@ -96,6 +97,19 @@ struct ContactPeek : public PenaltyContact3DT {
         put(buf, "f8", area.data(), 8, (long)area.size(), 0);
         double prm[4] = {p.fK, p.fMu, p.fFrictionEps, p.fViscousDamping};
         put("cparams", "f8", prm, 8, 4, 0);
+        /* what the search works on (ContactT.h:145-156): the triangulated surfaces, the striker nodes, their areas */
+        {
+            std::vector<int> facets, surf;
+            for (int sfc = 0; sfc < p.fSurfaces.Length(); sfc++)
+                for (int f = 0; f < p.fSurfaces[sfc].MajorDim(); f++) {
+                    for (int a = 0; a < 3; a++) facets.push_back(p.fSurfaces[sfc](f, a));
+                    surf.push_back(sfc);
+                }
+            put("cfacets", "i4", facets.data(), 4, (long)surf.size(), 3);
+            put("cfacet_surface", "i4", surf.data(), 4, (long)surf.size(), 0);
+            put1("cstrikers", p.fStrikerTags);
+            put1("cstriker_area", p.fStrikerArea);
+        }
         /* the group's own residual contribution at the current state */
         SolverT* solver = tahoe->Solver(solver_group);
         dArrayT& rhs = const_cast<dArrayT&>(tahoe->RHS(solver_group));

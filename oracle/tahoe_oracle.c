@@ -1563,6 +1563,67 @@ static void contact_dn_du(const double* x1, const double* x2, const double* x3, 
     memcpy(dn, col, sizeof col);
 }
 
+/* Contact3DT::Intersect (Contact3DT.cpp:336-391) */
+static int contact_intersect(const double* x1, const double* x2, const double* x3, const double* xs, double* h_out)
+{
+    double a[3], b[3], c[3], n[3], xsp[3];
+    for (int i = 0; i < 3; i++) { a[i] = x2[i] - x1[i]; b[i] = x3[i] - x1[i]; c[i] = xs[i] - x1[i]; }
+    n[0] = a[1] * b[2] - a[2] * b[1];
+    n[1] = a[2] * b[0] - a[0] * b[2];
+    n[2] = a[0] * b[1] - a[1] * b[0];
+    const double mag = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int i = 0; i < 3; i++) n[i] /= mag;
+    const double h = n[0] * c[0] + n[1] * c[1] + n[2] * c[2];
+    *h_out = h;
+    for (int i = 0; i < 3; i++) xsp[i] = 1.0 * xs[i] + (-h) * n[i];
+    const double dist_tol = sqrt(mag) / 2.0, area_tol = mag / 50.0;
+    if (fabs(h) > dist_tol) return 0;
+    const double* corner[3] = {x1, x2, x3};
+    const double* next[3] = {x2, x3, x1};
+    for (int e = 0; e < 3; e++) { /* edges 1-2, 2-3, 3-1: the projection must lie on the inner side of each */
+        double edge[3], xis[3], ni[3];
+        for (int i = 0; i < 3; i++) { edge[i] = next[e][i] - corner[e][i]; xis[i] = xsp[i] - corner[e][i]; }
+        ni[0] = edge[1] * xis[2] - edge[2] * xis[1];
+        ni[1] = edge[2] * xis[0] - edge[0] * xis[2];
+        ni[2] = edge[0] * xis[1] - edge[1] * xis[0];
+        if (n[0] * ni[0] + n[1] * ni[1] + n[2] * ni[2] < -area_tol) return 0;
+    }
+    return 1;
+}
+
+int orc_contact_search(int64_t nfacets, const int32_t* facets, const int32_t* facet_surface, int64_t nstrikers, const int32_t* strikers,
+                       int64_t nn, const double* x, int32_t* hit, double* gap)
+{
+    (void)nn;
+    int nsurf = 0;
+    for (int64_t f = 0; f < nfacets; f++) nsurf = facet_surface[f] + 1 > nsurf ? facet_surface[f] + 1 : nsurf;
+    int nactive = 0;
+    for (int64_t s = 0; s < nstrikers; s++) {
+        const int32_t tag = strikers[s];
+        hit[s] = -1;
+        double best = 0.0;
+        for (int64_t f = 0; f < nfacets; f++) { /* surfaces in order, facets in order: the reference's loops */
+            /* no self contact per surface: surface.HasValue(strikertag) */
+            int self = 0;
+            for (int64_t q = 0; q < nfacets && !self; q++)
+                if (facet_surface[q] == facet_surface[f] && (facets[3 * q] == tag || facets[3 * q + 1] == tag || facets[3 * q + 2] == tag)) self = 1;
+            if (self) continue;
+            double h;
+            if (!contact_intersect(x + 3 * (int64_t)facets[3 * f], x + 3 * (int64_t)facets[3 * f + 1], x + 3 * (int64_t)facets[3 * f + 2],
+                                   x + 3 * (int64_t)tag, &h))
+                continue;
+            if (hit[s] < 0 || fabs(h) < fabs(best)) { /* first time to a facet, or a closer projection (:300-318) */
+                hit[s] = (int32_t)f;
+                best = h;
+            }
+        }
+        if (gap) gap[s] = best;
+        nactive += hit[s] >= 0;
+    }
+    (void)nsurf;
+    return nactive;
+}
+
 int orc_contact_force(int64_t npairs, const int32_t* pairs, const double* area, double K, double mu, double eps, double visc, double constKd,
                       int64_t nn, const double* X, const double* u, const double* v, double* f, double* h_max_out)
 {

@@ -135,6 +135,13 @@ int orc_assemble_mass(double density, int mass_type, double constM, int64_t ne, 
 int orc_material_set_spline(orc_material_t* m, int n, const double* x, const double* y, int fixity);
 /* the hardening function and its derivative (known-answer checks) */
 void orc_hardening(const orc_material_t* m, double alpha, double* K, double* dK);
+/* The search that feeds it: Contact3DT::SetActiveStrikers (Contact3DT.cpp:226-334) on the configuration x[nn][3].  For every
+ * striker the facet of smallest |h| among the facets -- of surfaces the striker is not a node of -- that Contact3DT::Intersect
+ * (:336-391) accepts: |h| <= sqrt(|a x b|)/2 and the projection inside the triangle within |a x b|/50; the first facet in surface /
+ * facet order wins a tie.  (The reference looks for candidates through a search grid around the facet midpoint; every striker
+ * Intersect accepts lies inside that region, so the grid only prunes.)  hit[ns] = index into facets, -1 for a free striker. */
+int orc_contact_search(int64_t nfacets, const int32_t* facets /*[nf][3]*/, const int32_t* facet_surface /*[nf]*/, int64_t nstrikers,
+                       const int32_t* strikers /*[ns]*/, int64_t nn, const double* x, int32_t* hit, double* gap /*[ns] h of the hit, or NULL*/);
 /* SURVEY 8(f)-4, contact_3D_penalty: PenaltyContact3DT::RHSDriver (PenaltyContact3DT.cpp:262-500) over a given list of active
  * striker-facet pairs (Contact3DT::SetActiveInteractions builds it: three facet nodes, then the striker; 0-based).  Per pair with
  * penetration h = n . (x_s - centroid) < 0 on the configuration X + constKd u: the penalty force dphi dh/du with dphi = -K h area

@@ -45,7 +45,8 @@ tb2_nlpcg_create tb2_nlpcg_destroy tb2_nlpcg_solve tb2_nlpcg_solve_host tb2_nlpc
 tb2_matrix_multx tb2_matrix_multx_host tb2_matrix_copy_diagonal tb2_matrix_copy_diagonal_host tb2_matrix_pcg tb2_matrix_pcg_host tb2_equations_gather
 tb2_equations_scatter_add tb2_comm_unique_id tb2_comm_init tb2_comm_destroy tb2_comm_sum_interface
 tb2_comm_peer_export tb2_comm_peer_import tb2_comm_peer_enabled tb2_comm_peer_disable tb2_partition_rcb tb2_partition_part tb2_secant_search_host
-tb2_explicit_attach_contact tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking""".split()
+tb2_explicit_attach_contact tb2_contact_create tb2_contact_destroy tb2_contact_set_pairs tb2_contact_form tb2_contact_form_host tb2_contact_tracking
+tb2_contact_set_surfaces tb2_contact_search tb2_contact_get_pairs tb2_contact_has_surfaces""".split()
 
 
 class Tb2Error(RuntimeError):
@@ -466,6 +467,31 @@ class Contact(_Handle):
         vv = None if v is None else _f64(v)
         _chk(lib().tb2_contact_form_host(self.h, C.c_double(constKd), _p(u), _p(vv) if vv is not None else None, 0 if out is None else 1, _p(f)))
         return f
+
+    def set_surfaces(self, facets, facet_surface, strikers, striker_area):
+        """what the device search works on: triangulated surfaces (node triples + surface id), striker nodes and their areas"""
+        facets = np.ascontiguousarray(facets, np.int32).reshape(-1, 3)
+        facet_surface = np.ascontiguousarray(facet_surface, np.int32)
+        strikers = np.ascontiguousarray(strikers, np.int32)
+        striker_area = _f64(striker_area)
+        _chk(lib().tb2_contact_set_surfaces(self.h, C.c_int64(facets.shape[0]), _p(facets), _p(facet_surface), C.c_int64(strikers.shape[0]),
+                                            _p(strikers), _p(striker_area)))
+
+    def search_host(self, u):
+        """search on X + u (host array): the number of active pairs; they become the group's pair list"""
+        import torch
+        d = torch.from_numpy(_f64(u)).to(torch.device("cuda", self.mesh.device))
+        n = C.c_int64(0)
+        _chk(lib().tb2_contact_search(self.h, C.c_void_p(d.data_ptr()), C.byref(n)))
+        return n.value
+
+    def pairs(self):
+        n = C.c_int64(0)
+        _chk(lib().tb2_contact_get_pairs(self.h, C.byref(n), None, None))
+        pairs, area = np.zeros((n.value, 4), np.int32), np.zeros(n.value)
+        if n.value:
+            _chk(lib().tb2_contact_get_pairs(self.h, C.byref(n), _p(pairs), _p(area)))
+        return pairs, area
 
     def tracking(self):
         n, h = C.c_int(0), C.c_double(0.0)

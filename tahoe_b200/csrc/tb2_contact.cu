@@ -35,6 +35,13 @@ struct tb2_contact {
     tb2::DevBuf<double> track_h;  // [blocks] deepest penetration per CTA
     int track_blocks = 0;
     unsigned long long version = 0; // tb2_contact_set_pairs calls so far
+    // the search (tb2_contact_set_surfaces / tb2_contact_search): triangulated surfaces, strikers, per-node surface membership
+    int64_t nfacets = 0, nstrikers = 0;
+    tb2::DevBuf<int> facets, facet_surface, strikers, hit;
+    tb2::DevBuf<unsigned> node_surfaces; // [nn] bit s: the node belongs to surface s (no self contact per surface)
+    tb2::DevBuf<double> striker_area, gap;
+    std::vector<int> h_facets, h_strikers;
+    std::vector<double> h_striker_area;
 };
 
 namespace {
@@ -217,6 +224,113 @@ int contact_launch(tb2_contact* c, double constKd, const double* d_u, const doub
     return TB2_OK;
 }
 
+
+// Contact3DT::SetActiveStrikers (Contact3DT.cpp:226-334) with Contact3DT::Intersect (:336-391): one thread per striker walks the facets in
+// surface / facet order (tiles of them staged in shared memory by the CTA) and keeps the accepted facet of smallest |h|, the first one
+// on a tie.  The reference collects its candidates through a search grid around the facet midpoint (radius 1.65 |mid - x1|); a facet
+// is skipped here when the striker lies outside the sphere around that box, which never excludes a striker Intersect would accept.
+constexpr int kSearchThreads = 128;
+__global__ void __launch_bounds__(kSearchThreads) k_contact_search(int64_t nstrikers, const int* __restrict__ strikers, int64_t nfacets,
+                                                                  const int* __restrict__ facets, const int* __restrict__ facet_surface,
+                                                                  const unsigned* __restrict__ node_surfaces, const double* __restrict__ X,
+                                                                  const double* __restrict__ u, int* __restrict__ hit, double* __restrict__ gap)
+{
+    __shared__ double fx[kSearchThreads][9];
+    __shared__ double fmid[kSearchThreads][4]; // midpoint and squared reach
+    __shared__ int fsurf[kSearchThreads];
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool live = s < nstrikers;
+    const int tag = live ? strikers[s] : 0;
+    double xs[3] = {0.0, 0.0, 0.0};
+    unsigned mine = 0;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) xs[i] = X[3 * (int64_t)tag + i] + u[3 * (int64_t)tag + i];
+        mine = node_surfaces[tag];
+    }
+    int best_f = -1;
+    double best_h = 0.0;
+    for (int64_t f0 = 0; f0 < nfacets; f0 += kSearchThreads) {
+        const int64_t f = f0 + threadIdx.x;
+        __syncthreads();
+        if (f < nfacets) {
+            double m[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const int64_t n = facets[3 * f + a];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double c = X[3 * n + i] + u[3 * n + i];
+                    fx[threadIdx.x][3 * a + i] = c;
+                    m[i] += c;
+                }
+            }
+            double r2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                m[i] /= 3.0;
+                fmid[threadIdx.x][i] = m[i];
+                const double dd = m[i] - fx[threadIdx.x][i];
+                r2 += dd * dd;
+            }
+            fmid[threadIdx.x][3] = 3.0 * (1.1 * 1.5) * (1.1 * 1.5) * r2 * 1.0001; // (sqrt(3) * radius)^2, a hair wider
+            fsurf[threadIdx.x] = facet_surface[f];
+        }
+        __syncthreads();
+        const int nt = (int)(nfacets - f0 < kSearchThreads ? nfacets - f0 : kSearchThreads);
+        if (!live) continue;
+        for (int q = 0; q < nt; q++) {
+            if ((mine >> fsurf[q]) & 1u) continue; // no self contact (per surface)
+            const double dx = xs[0] - fmid[q][0], dy = xs[1] - fmid[q][1], dz = xs[2] - fmid[q][2];
+            if (dx * dx + dy * dy + dz * dz > fmid[q][3]) continue;
+            const double* x1 = fx[q];
+            const double* x2 = fx[q] + 3;
+            const double* x3 = fx[q] + 6;
+            double a[3], b[3], c[3], n[3], xsp[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                a[i] = x2[i] - x1[i];
+                b[i] = x3[i] - x1[i];
+                c[i] = xs[i] - x1[i];
+            }
+            n[0] = a[1] * b[2] - a[2] * b[1];
+            n[1] = a[2] * b[0] - a[0] * b[2];
+            n[2] = a[0] * b[1] - a[1] * b[0];
+            const double mag = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) n[i] /= mag;
+            const double h = n[0] * c[0] + n[1] * c[1] + n[2] * c[2];
+            if (fabs(h) > sqrt(mag) / 2.0) continue;
+#pragma unroll
+            for (int i = 0; i < 3; i++) xsp[i] = xs[i] + (-h) * n[i];
+            const double area_tol = mag / 50.0;
+            bool inside = true;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const double* p0 = fx[q] + 3 * e;
+                const double* p1 = fx[q] + 3 * ((e + 1) % 3);
+                double ed[3], xi[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    ed[i] = p1[i] - p0[i];
+                    xi[i] = xsp[i] - p0[i];
+                }
+                const double n0 = ed[1] * xi[2] - ed[2] * xi[1], n1 = ed[2] * xi[0] - ed[0] * xi[2], n2 = ed[0] * xi[1] - ed[1] * xi[0];
+                if (n[0] * n0 + n[1] * n1 + n[2] * n2 < -area_tol) inside = false;
+            }
+            if (!inside) continue;
+            if (best_f < 0 || fabs(h) < fabs(best_h)) {
+                best_f = (int)(f0 + q);
+                best_h = h;
+            }
+        }
+    }
+    if (live) {
+        hit[s] = best_f;
+        gap[s] = best_h;
+    }
+}
+
 } // namespace
 
 namespace tb2 {
@@ -306,6 +420,98 @@ int tb2_contact_form(tb2_contact* c, double constKd, const double* d_u, const do
     if (!accumulate) TB2_CUDA(cudaMemsetAsync(d_f, 0, (size_t)m->nn * 3 * sizeof(double), m->stream));
     return contact_launch(c, constKd, d_u, d_v, d_f, true, m->stream);
 }
+
+int tb2_contact_set_surfaces(tb2_contact* c, int64_t nfacets, const int32_t* h_facets, const int32_t* h_facet_surface, int64_t nstrikers,
+                             const int32_t* h_strikers, const double* h_striker_area)
+{
+    TB2_ARG(c && nfacets >= 0 && nstrikers >= 0 && (nfacets == 0 || (h_facets && h_facet_surface)) && (nstrikers == 0 || (h_strikers && h_striker_area)));
+    tb2_mesh* m = c->mesh;
+    std::vector<unsigned> mask((size_t)m->nn, 0u);
+    for (int64_t f = 0; f < nfacets; f++) {
+        if (h_facet_surface[f] < 0 || h_facet_surface[f] > 31) {
+            tb2::set_error("tb2_contact_set_surfaces: surface %d (at most 32 surfaces per group)", h_facet_surface[f]);
+            return TB2_ERR_ARG;
+        }
+        for (int a = 0; a < 3; a++) {
+            const int32_t n = h_facets[3 * f + a];
+            if (n < 0 || n >= m->nn) {
+                tb2::set_error("tb2_contact_set_surfaces: facet %lld has node %d out of range", (long long)f, n);
+                return TB2_ERR_SIZE;
+            }
+            mask[n] |= 1u << h_facet_surface[f];
+        }
+    }
+    for (int64_t s = 0; s < nstrikers; s++)
+        if (h_strikers[s] < 0 || h_strikers[s] >= m->nn) {
+            tb2::set_error("tb2_contact_set_surfaces: striker node %d out of range", h_strikers[s]);
+            return TB2_ERR_SIZE;
+        }
+    DeviceGuard dg(m->device);
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    c->nfacets = nfacets;
+    c->nstrikers = nstrikers;
+    c->h_facets.assign(h_facets, h_facets + 3 * nfacets);
+    c->h_strikers.assign(h_strikers, h_strikers + nstrikers);
+    c->h_striker_area.assign(h_striker_area, h_striker_area + nstrikers);
+    TB2_CUDA(c->facets.alloc(3 * (nfacets > 0 ? nfacets : 1)));
+    TB2_CUDA(c->facet_surface.alloc(nfacets > 0 ? nfacets : 1));
+    TB2_CUDA(c->strikers.alloc(nstrikers > 0 ? nstrikers : 1));
+    TB2_CUDA(c->striker_area.alloc(nstrikers > 0 ? nstrikers : 1));
+    TB2_CUDA(c->hit.alloc(nstrikers > 0 ? nstrikers : 1));
+    TB2_CUDA(c->gap.alloc(nstrikers > 0 ? nstrikers : 1));
+    TB2_CUDA(c->node_surfaces.alloc(m->nn));
+    if (nfacets) TB2_CUDA(cudaMemcpy(c->facets.p, h_facets, (size_t)nfacets * 3 * sizeof(int), cudaMemcpyHostToDevice));
+    if (nfacets) TB2_CUDA(cudaMemcpy(c->facet_surface.p, h_facet_surface, (size_t)nfacets * sizeof(int), cudaMemcpyHostToDevice));
+    if (nstrikers) TB2_CUDA(cudaMemcpy(c->strikers.p, h_strikers, (size_t)nstrikers * sizeof(int), cudaMemcpyHostToDevice));
+    if (nstrikers) TB2_CUDA(cudaMemcpy(c->striker_area.p, h_striker_area, (size_t)nstrikers * sizeof(double), cudaMemcpyHostToDevice));
+    TB2_CUDA(cudaMemcpy(c->node_surfaces.p, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    return TB2_OK;
+}
+
+// the search on X + u (device array), then the active pairs in striker order become the group's pair list.  The hits of the
+// strikers -- O(surface) integers -- pass through the host, which builds the per-node record lists as tb2_contact_set_pairs does.
+int tb2_contact_search(tb2_contact* c, const double* d_u, int64_t* npairs_out)
+{
+    TB2_ARG(c && d_u);
+    tb2_mesh* m = c->mesh;
+    DeviceGuard dg(m->device);
+    if (c->nstrikers == 0 || c->nfacets == 0) {
+        if (npairs_out) *npairs_out = 0;
+        return tb2_contact_set_pairs(c, 0, nullptr, nullptr);
+    }
+    {
+        ProfScope ps(m, kProfOther, 1);
+        k_contact_search<<<(unsigned)((c->nstrikers + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, m->stream>>>(
+            c->nstrikers, c->strikers.p, c->nfacets, c->facets.p, c->facet_surface.p, c->node_surfaces.p, m->X.p, d_u, c->hit.p, c->gap.p);
+    }
+    TB2_CUDA(cudaGetLastError());
+    std::vector<int> hit((size_t)c->nstrikers);
+    TB2_CUDA(cudaMemcpyAsync(hit.data(), c->hit.p, hit.size() * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream));
+    std::vector<int32_t> pairs;
+    std::vector<double> area;
+    for (int64_t s = 0; s < c->nstrikers; s++) {
+        if (hit[s] < 0) continue;
+        for (int a = 0; a < 3; a++) pairs.push_back(c->h_facets[3 * (size_t)hit[s] + a]);
+        pairs.push_back(c->h_strikers[s]);
+        area.push_back(c->h_striker_area[s]);
+    }
+    if (npairs_out) *npairs_out = (int64_t)area.size();
+    return tb2_contact_set_pairs(c, (int64_t)area.size(), pairs.data(), area.data());
+}
+
+int tb2_contact_get_pairs(tb2_contact* c, int64_t* npairs, int32_t* h_pairs, double* h_area)
+{
+    TB2_ARG(c);
+    DeviceGuard dg(c->device);
+    if (npairs) *npairs = c->npairs;
+    if (c->npairs == 0) return TB2_OK;
+    if (h_pairs) TB2_CUDA(cudaMemcpy(h_pairs, c->pairs.p, (size_t)c->npairs * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_area) TB2_CUDA(cudaMemcpy(h_area, c->area.p, (size_t)c->npairs * sizeof(double), cudaMemcpyDeviceToHost));
+    return TB2_OK;
+}
+
+int tb2_contact_has_surfaces(const tb2_contact* c) { return c && c->nfacets > 0 && c->nstrikers > 0 ? 1 : 0; }
 
 int tb2_contact_form_host(tb2_contact* c, double constKd, const double* h_u, const double* h_v, int accumulate, double* h_f)
 {

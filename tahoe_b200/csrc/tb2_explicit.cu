@@ -419,6 +419,7 @@ int tb2_explicit_destroy(tb2_explicit* ex)
 int tb2_explicit_set_state(tb2_explicit* ex, const double* h_d, const double* h_v, const double* h_a)
 {
     TB2_ARG(ex);
+    ex->contact_searched = false; // a new configuration: an attached group with surfaces is searched again before the next step
     tb2_mesh* m = ex->group->mesh;
     DeviceGuard dg(m->device);
     const size_t bytes = 3 * m->nn * sizeof(double);
@@ -489,6 +490,7 @@ int tb2_explicit_attach_contact(tb2_explicit* ex, tb2_contact* contact)
     TB2_CUDA(cudaStreamSynchronize(m->stream));
     ex->contact = contact;
     ex->contact_version = ~0ull;
+    ex->contact_searched = false;
     if (contact && !ex->fadd.p) TB2_CUDA(ex->fadd.alloc((size_t)m->nn * 3));
     return TB2_OK;
 }
@@ -512,11 +514,28 @@ int tb2_explicit_initial_condition(tb2_explicit* ex)
     return tb2_group_status(g, nullptr);
 }
 
+// An attached contact group that carries its surfaces (tb2_contact_set_surfaces) is searched on the device after every step, on the
+// corrected displacements, as LinearSolver::Solve relaxes the system after its update (LinearSolver.cpp:76-90 -> ContactT::RelaxSystem):
+// the steps then run one at a time (the next predictor cannot be fused into the node kernel), and once before the first step.
+static int explicit_steps_searching(tb2_explicit* ex, double dt, int nsteps, const double* fs, const double* vs)
+{
+    if (!ex->contact_searched) {
+        TB2_CHECK(tb2_contact_search(ex->contact, ex->d.p, nullptr));
+        ex->contact_searched = true;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        TB2_CHECK(explicit_steps(ex, dt, 1, fs ? fs + s : nullptr, vs ? vs + s : nullptr));
+        TB2_CHECK(tb2_contact_search(ex->contact, ex->d.p, nullptr));
+    }
+    return TB2_OK;
+}
+
 int tb2_explicit_run(tb2_explicit* ex, double dt, int nsteps, const double* h_fext_scale, const double* h_value_scale)
 {
     TB2_ARG(ex && nsteps >= 0);
     DeviceGuard dg(ex->group->mesh->device);
-    TB2_CHECK(explicit_steps(ex, dt, nsteps, h_fext_scale, h_value_scale));
+    if (ex->contact && tb2_contact_has_surfaces(ex->contact)) TB2_CHECK(explicit_steps_searching(ex, dt, nsteps, h_fext_scale, h_value_scale));
+    else TB2_CHECK(explicit_steps(ex, dt, nsteps, h_fext_scale, h_value_scale));
     return tb2_group_status(ex->group, nullptr);
 }
 
@@ -557,7 +576,8 @@ int tb2_explicit_run_async(tb2_explicit* ex, double dt, int nsteps, const double
     const int b = t & 1;
     // the snapshot buffer is free once the copy that last read it has finished
     TB2_CUDA(cudaStreamWaitEvent(m->stream, ex->ev_copied[b], 0));
-    TB2_CHECK(explicit_steps(ex, dt, nsteps, h_fext_scale, h_value_scale));
+    if (ex->contact && tb2_contact_has_surfaces(ex->contact)) TB2_CHECK(explicit_steps_searching(ex, dt, nsteps, h_fext_scale, h_value_scale));
+    else TB2_CHECK(explicit_steps(ex, dt, nsteps, h_fext_scale, h_value_scale));
     TB2_CUDA(cudaMemcpyAsync(ex->dsnap[b].p, ex->d.p, bytes, cudaMemcpyDeviceToDevice, m->stream));
     TB2_CUDA(cudaEventRecord(ex->ev_snap[b], m->stream));
     TB2_CUDA(cudaStreamWaitEvent(ex->stream_copy, ex->ev_snap[b], 0));

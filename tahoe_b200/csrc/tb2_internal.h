@@ -242,6 +242,7 @@ struct tb2_explicit {
     tb2_contact* contact = nullptr;
     tb2::DevBuf<double> fadd;                     // [nn][3] zero outside the nodes of the current pair list
     unsigned long long contact_version = ~0ull;   // pair-list version fadd was last cleared for
+    bool contact_searched = false;                // a group with surfaces: its pair list belongs to the current state
     cudaStream_t stream_aux = nullptr;            // the contact kernels run here, beside the element sweep
     cudaEvent_t ev_state = nullptr, ev_loads = nullptr;
     // tb2_explicit_run_async: displacement snapshots on their way to the host beside the next steps' kernels

@@ -153,7 +153,7 @@ def contact_case(name, rel_xml, flags, edits=()):
     steps = sorted(int(k.split("_")[1]) for k in dump if k.startswith("cpairs_"))
     payload = {"source": np.array("benchmark_XML/" + rel_xml + ("; edits: " + json.dumps(edits) if edits else "")),
                "steps": np.asarray(steps, np.int32)}
-    keep = ("coords", "eqnos", "cparams") + tuple("%s_%d" % (a, k) for k in steps for a in ("d", "v", "cpairs", "carea", "crhs"))
+    keep = ("coords", "eqnos", "cparams", "cfacets", "cfacet_surface", "cstrikers", "cstriker_area") + tuple("%s_%d" % (a, k) for k in steps for a in ("d", "v", "cpairs", "carea", "crhs"))
     for k in keep:
         if k in dump:
             payload["ref_" + k] = dump[k]

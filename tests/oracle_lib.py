@@ -307,6 +307,30 @@ def traction_force(conn, X, elem, facet, tract, coord_system="global", scale=1.0
     return f
 
 
+def contact_search(facets, facet_surface, strikers, x):
+    """Contact3DT::SetActiveStrikers on the configuration x: (hit facet per striker or -1, gap of the hit)"""
+    facets = np.ascontiguousarray(facets, np.int32).reshape(-1, 3)
+    facet_surface = np.ascontiguousarray(facet_surface, np.int32)
+    strikers = np.ascontiguousarray(strikers, np.int32)
+    x = np.ascontiguousarray(x, np.float64)
+    hit = np.zeros(strikers.shape[0], np.int32)
+    gap = np.zeros(strikers.shape[0])
+    L = lib()
+    L.orc_contact_search.restype = C.c_int
+    n = L.orc_contact_search(C.c_int64(facets.shape[0]), _p(facets), _p(facet_surface), C.c_int64(strikers.shape[0]), _p(strikers),
+                             C.c_int64(x.shape[0]), _p(x), _p(hit), _p(gap))
+    assert n == int((hit >= 0).sum())
+    return hit, gap
+
+
+def pairs_from_hits(facets, strikers, striker_area, hit):
+    """the pair rows (three facet nodes, striker) and areas of the active strikers, in striker order"""
+    act = np.nonzero(hit >= 0)[0]
+    facets = np.asarray(facets).reshape(-1, 3)
+    pairs = np.concatenate([facets[hit[act]], np.asarray(strikers)[act, None]], axis=1).astype(np.int32)
+    return pairs, np.asarray(striker_area)[act]
+
+
 def contact_force(pairs, area, X, u, v=None, K=0.0, mu=0.0, eps=1e-6, visc=0.0, constKd=1.0):
     """PenaltyContact3DT::RHSDriver over a list of active striker-facet pairs: (nodal forces [nn][3], pairs in contact, deepest penetration)"""
     pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 4)

@@ -196,3 +196,116 @@ def test_resident_explicit_step_with_contact_matches_the_oracle_loop(tb2, oracle
 
 
 TOL_FIELD = 1.0e-10  # BASELINE.json: fields to a relative 1e-10
+
+
+# ---- the search (Contact3DT::SetActiveStrikers) -------------------------------------------------------------------------------------
+
+def _pair_set(pairs):
+    return sorted(map(tuple, np.asarray(pairs).tolist()))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_contact_search_matches_the_reference_pair_lists(oracle, name):
+    """the reference's own search (grid + Intersect) left the pair list of every dumped step on the configuration X + d of that step:
+    the oracle's search finds the same striker-facet pairs (as a set: the reference's row order follows its grid traversal)"""
+    g = load(name)
+    X = g["ref_coords"]
+    for k, pairs, area, d, v, _ in reference_states(g):
+        hit, gap = oracle.contact_search(g["ref_cfacets"], g["ref_cfacet_surface"], g["ref_cstrikers"], X + d)
+        got, got_area = oracle.pairs_from_hits(g["ref_cfacets"], g["ref_cstrikers"], g["ref_cstriker_area"], hit)
+        assert _pair_set(got) == _pair_set(pairs), (name, k)
+        # the areas ride along with their strikers
+        want_area = dict(zip(pairs[:, 3].tolist(), area.tolist()))
+        assert all(want_area[s] == a for s, a in zip(got[:, 3].tolist(), got_area.tolist()))
+
+
+def _two_cube_surfaces(n):
+    """two stacked n^3 cubes (zero gap): mesh, triangulated contact surfaces (top of the lower cube = surface 0, bottom of the upper
+    cube = surface 1, both with outward normals), strikers = the nodes of both faces, tributary areas"""
+    from tahoe_b200 import mesh as tmesh
+    Xl, cl, nsl = tmesh.structured_cube(n, jitter=0.0)
+    X = np.vstack([Xl, Xl + np.array([0.0, 0.0, 1.0])])
+    conn = np.vstack([cl, cl + Xl.shape[0]]).astype(np.int32)
+    nn_l, px = Xl.shape[0], n + 1
+    top = lambda i, j: n * px * px + j * px + i
+    bot = lambda i, j: nn_l + j * px + i
+    facets, surf = [], []
+    for j in range(n):
+        for i in range(n):
+            facets += [[top(i, j), top(i + 1, j), top(i + 1, j + 1)], [top(i, j), top(i + 1, j + 1), top(i, j + 1)]]      # normal +z
+            surf += [0, 0]
+    for j in range(n):
+        for i in range(n):
+            facets += [[bot(i, j), bot(i + 1, j + 1), bot(i + 1, j)], [bot(i, j), bot(i, j + 1), bot(i + 1, j + 1)]]      # normal -z
+            surf += [1, 1]
+    strikers = np.array([top(i, j) for j in range(px) for i in range(px)] + [bot(i, j) for j in range(px) for i in range(px)], np.int32)
+    w = np.ones(px)
+    w[[0, -1]] = 0.5
+    area = np.concatenate([np.outer(w, w).ravel(), np.outer(w, w).ravel()]) / n ** 2
+    code = np.zeros(X.shape, np.uint8)
+    code[nsl[5]] = 1
+    return X, conn, np.asarray(facets, np.int32), np.asarray(surf, np.int32), strikers, area, code, nn_l
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_device_contact_search_matches_the_reference_pair_lists(tb2, oracle, name):
+    g = load(name)
+    X = g["ref_coords"]
+    mesh = _dummy_mesh(tb2, X)
+    K, mu, eps, visc = g["ref_cparams"]
+    contact = tb2.Contact(mesh, K, mu, eps, visc)
+    contact.set_surfaces(g["ref_cfacets"], g["ref_cfacet_surface"], g["ref_cstrikers"], g["ref_cstriker_area"])
+    for k, pairs, area, d, v, want in reference_states(g):
+        n = contact.search_host(d)
+        got, got_area = contact.pairs()
+        assert n == pairs.shape[0] and _pair_set(got) == _pair_set(pairs), (name, k)
+        hit, _ = oracle.contact_search(g["ref_cfacets"], g["ref_cfacet_surface"], g["ref_cstrikers"], X + d)
+        o_pairs, o_area = oracle.pairs_from_hits(g["ref_cfacets"], g["ref_cstrikers"], g["ref_cstriker_area"], hit)
+        assert np.array_equal(got, o_pairs) and np.array_equal(got_area, o_area)  # striker order: identical rows
+        # and the force on the searched list is the reference's
+        f = contact.form_host(d, v)
+        assert np.abs(to_equations(f, g["ref_eqnos"]) - want).max() < 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+def test_resident_impact_with_the_search_on_the_device(tb2, oracle):
+    """two cubes, both faces strikers of each other (two-sided contact as in the reference's impact benchmark): tb2_explicit_run searches
+    before the first step and after every step; the same loop with the oracle's search and force gives the same fields"""
+    n = 4
+    X, conn, facets, surf, strikers, area, code, nn_l = _two_cube_surfaces(n)
+    desc = {"type": "Simo_isotropic", "kappa": 1000.0, "mu": 400.0, "density": 1.0}
+    K, mu, eps, visc = 2000.0, 0.3, 1e-3, 20.0
+    v0 = np.zeros_like(X)
+    v0[nn_l:] = [0.4, 0.0, -5.0]
+    dt, nsteps = 2.0e-4, 50
+    mesh = tb2.Mesh(X, conn)
+    grp = tb2.Group(mesh, tb2.TOTAL_LAGRANGIAN, tb2.material(desc))
+    ex = tb2.Explicit(grp)
+    contact = tb2.Contact(mesh, K, mu, eps, visc)
+    contact.set_surfaces(facets, surf, strikers, area)
+    ex.attach_contact(contact)
+    ex.set_bc(code, np.zeros_like(X), np.zeros_like(X))
+    ex.set_state(np.zeros_like(X), v0, np.zeros_like(X))
+    ex.run(dt, nsteps)
+    d, v, a = ex.get_state()
+    omat = oracle.material(desc)
+    mass = oracle.lumped_mass(1.0, conn, X)
+    d0, w0, a0 = np.zeros_like(X), v0.copy(), np.zeros_like(X)
+    hit, _ = oracle.contact_search(facets, surf, strikers, X + d0)
+    npairs_seen = []
+    for _ in range(nsteps):
+        pairs, parea = oracle.pairs_from_hits(facets, strikers, area, hit)
+        oracle.cd_predictor(dt, d0, w0, a0, code, np.zeros_like(X))
+        err, fi = oracle.internal_force(oracle.TOTAL_LAGRANGIAN, omat, conn, X, d0)
+        assert err == 0
+        fc, nc, hm = oracle.contact_force(pairs, parea, X, d0, w0, K=K, mu=mu, eps=eps, visc=visc)
+        oracle.cd_corrector(dt, w0, a0, fc - fi, mass, code)
+        hit, _ = oracle.contact_search(facets, surf, strikers, X + d0)
+        npairs_seen.append(pairs.shape[0])
+    assert max(npairs_seen) > 10 and nc > 0
+    got_pairs, _ = contact.pairs()
+    want_pairs, _ = oracle.pairs_from_hits(facets, strikers, area, hit)
+    assert np.array_equal(got_pairs, want_pairs)  # the list after the last step
+    for got, want in ((d, d0), (v, w0), (a, a0)):
+        assert np.abs(got - want).max() < TOL_FIELD * np.abs(want).max()
