@@ -131,6 +131,9 @@ void CudaExplicitSolverT::Setup(CudaStiffnessSourceT* dev)
 	if (fContact) {
 		if (fContact->DeviceMesh() != dev->DeviceMesh())
 			ExceptionT::GeneralFail(caller, "the contact group and the continuum group do not share a device mesh");
+		/* the device object searches for itself from now on (tb2_contact_search after every step, as LinearSolver::Solve relaxes the
+		 * system after its update, LinearSolver.cpp:76-90): nothing of the contact crosses the bus per step */
+		fContact->SendSurfaces();
 		Check(tb2_explicit_attach_contact(fEx, fContact->DeviceContact()), caller);
 	}
 }
@@ -197,24 +200,10 @@ SolverT::SolutionStatusT CudaExplicitSolverT::Solve(int)
 			if (fHasLoads || biggest > 0.0) Check(tb2_explicit_set_bc(fEx, NULL, NULL, &fFext[0]), caller);
 		}
 
-		/* the pair list the last relaxation left (sent only when the search changed it) */
-		if (fContact) fContact->DeviceContact();
-
-		/* predictor + KBC values, internal force (+ contact force on the predicted state), a = M^-1 R, corrector: one call */
+		/* predictor + KBC values, internal force (+ contact force on the predicted state), a = M^-1 R, corrector; with a contact group
+		 * attached the run also searches for the striker-facet pairs of the corrected configuration, on the device */
 		Check(tb2_explicit_run(fEx, fFEManager.TimeStep(), 1, NULL, NULL), caller);
 		fSteps++;
-
-		/* relaxation as LinearSolver::Solve does after its update (LinearSolver.cpp:76-90): the reference's contact search reads the
-		 * current coordinates on the host, so with a contact group the new displacements come down every step (d only; v, a stay) */
-		if (fContact) {
-			FieldT& host_field = const_cast<FieldT&>(field);
-			Check(tb2_explicit_get_state(fEx, host_field[0].Pointer(), NULL, NULL), caller);
-			fFEManager.NodeManager()->UpdateCurrentCoordinates();
-			/* the search reports kReEQ whenever pairs are active (ContactT::RelaxSystem): LinearSolver re-numbers the equations for it
-			 * every step (the pair rows are connectivities of the group).  Nothing here depends on that: the dofs and their numbers
-			 * are the same, the diagonal matrix has no structure, and the attached group assembles by node, not by its fEqnos */
-			fFEManager.RelaxSystem(Group());
-		}
 		return kConverged;
 	}
 	catch (ExceptionT::CodeT code) {
@@ -238,6 +227,10 @@ void CudaExplicitSolverT::CloseStep(void)
 	FieldT& field = const_cast<FieldT&>(fDev->DeviceField());
 	Check(tb2_explicit_get_state(fEx, field[0].Pointer(), field[1].Pointer(), field[2].Pointer()), "CudaExplicitSolverT::CloseStep");
 	fDownloads++;
+	if (fContact) { /* Tahoe's own contact object catches up for its log and output (ContactT::RelaxSystem writes the contact info) */
+		fFEManager.NodeManager()->UpdateCurrentCoordinates();
+		fFEManager.RelaxSystem(Group());
+	}
 }
 
 void CudaExplicitSolverT::ResetStep(void)

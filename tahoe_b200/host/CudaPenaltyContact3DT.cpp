@@ -83,6 +83,23 @@ void CudaPenaltyContact3DT::SyncPairs(void)
 	Check(tb2_contact_set_pairs(fContact, np, np ? &fPairsSent[0] : NULL, np ? &fAreaSent[0] : NULL), "CudaPenaltyContact3DT::SyncPairs");
 }
 
+void CudaPenaltyContact3DT::SendSurfaces(void)
+{
+	const char caller[] = "CudaPenaltyContact3DT::SendSurfaces";
+	EnsureDevice();
+	std::vector<int32_t> facets, surface;
+	for (int s = 0; s < fSurfaces.Length(); s++) {
+		if (fSurfaces[s].MajorDim() > 0 && fSurfaces[s].MinorDim() != 3) ExceptionT::SizeMismatch(caller, "expecting triangular facets");
+		for (int f = 0; f < fSurfaces[s].MajorDim(); f++) {
+			for (int a = 0; a < 3; a++) facets.push_back(fSurfaces[s](f, a));
+			surface.push_back(s);
+		}
+	}
+	if (fStrikerTags.Length() == 0) ExceptionT::GeneralFail(caller, "the group has no striker list (all-nodes strikers are not supported on the device)");
+	Check(tb2_contact_set_surfaces(fContact, (int64_t)surface.size(), facets.empty() ? NULL : &facets[0], surface.empty() ? NULL : &surface[0],
+		fStrikerTags.Length(), fStrikerTags.Pointer(), fStrikerArea.Pointer()), caller);
+}
+
 tb2_contact* CudaPenaltyContact3DT::DeviceContact(void)
 {
 	EnsureDevice();

@@ -38,6 +38,10 @@ public:
 	/** while set, RHSDriver() adds nothing: a resident solver that attached the group forms the contact force on the device itself */
 	void MuteForce(bool mute) { fMuted = mute; }
 
+	/** hands the triangulated surfaces, the strikers and their areas to the device object, whose own search (tb2_contact_search:
+	 * Contact3DT::SetActiveStrikers on the device) then maintains the pair list of a resident run */
+	void SendSurfaces(void);
+
 	/** the mesh the device object lives on */
 	tb2_mesh* DeviceMesh(void) { EnsureDevice(); return fMesh; }
 
