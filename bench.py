@@ -849,12 +849,42 @@ def run_contact(torch, capi, tmesh, local, n, steps):
     ms_cat, cnt_cat, _ = m.profile_end()
     d = ex.get_state()[0]
     ok = bool(np.isfinite(d).all())
-    ex.close(); contact.close(); g.close(); m.close()
+    # the same impact with the pair list maintained by the search on the device (both faces strike each other, as in the reference's
+    # level.5 benchmark): tb2_explicit_run searches before the first step and after every step
+    px = n + 1
+    jj, ii = [a.ravel() for a in np.meshgrid(np.arange(px), np.arange(px), indexing="ij")]
+    lower = np.concatenate([np.stack([top(i, j), top(i + 1, j), top(i + 1, j + 1)], axis=1), np.stack([top(i, j), top(i + 1, j + 1), top(i, j + 1)], axis=1)])
+    upper = np.concatenate([np.stack([bot(i, j), bot(i + 1, j + 1), bot(i + 1, j)], axis=1), np.stack([bot(i, j), bot(i, j + 1), bot(i + 1, j + 1)], axis=1)])
+    facets = np.concatenate([lower, upper]).astype(np.int32)
+    surf = np.concatenate([np.zeros(len(lower), np.int32), np.ones(len(upper), np.int32)])
+    strikers = np.concatenate([top(ii, jj), bot(ii, jj)]).astype(np.int32)
+    w = np.ones(px)
+    w[[0, -1]] = 0.5
+    sarea = np.tile(np.outer(w, w).ravel() / n ** 2, 2)
+    searching = capi.Contact(m, 2000.0, 0.3, 1e-3, 20.0)
+    searching.set_surfaces(facets, surf, strikers, sarea)
+    ex.attach_contact(searching)
+    ex.set_state(np.zeros_like(X), v0, np.zeros_like(X))
+    ex.run(dt, 5)
+    m.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ex.run(dt, steps)
+    e1.record(stream)
+    m.synchronize()
+    torch.cuda.synchronize()
+    ms_search = e0.elapsed_time(e1) / steps
+    npairs_search = int(searching.pairs()[0].shape[0])
+    ok = ok and bool(np.isfinite(ex.get_state()[0]).all())
+    ex.close(); contact.close(); searching.close(); g.close(); m.close()
     if not ok or ncontact == 0:
         raise RuntimeError("contact leg: non-finite state or no pair in contact")
     return {"value": conn.shape[0] / (out["with_contact"] * 1e-3), "unit": METRIC, "ms_per_step": out["with_contact"],
             "ms_per_step_without_contact": out["without_contact"], "contact_kernels_ms_per_step": float(ms_cat[7]) / 20, "pairs": int(pairs.shape[0]),
             "pairs_in_contact": int(ncontact), "deepest_penetration": float(hmax), "steps": steps,
+            "with_device_search": {"ms_per_step": ms_search, "value": conn.shape[0] / (ms_search * 1e-3), "strikers": int(strikers.shape[0]),
+                                   "facets": int(facets.shape[0]), "pairs_after_last_step": npairs_search,
+                                   "note": "two-sided contact, pair list rebuilt by tb2_contact_search after every step (steps run one at a time)"},
             "workload": "two stacked %d^3 cubes (%d elements), contact_3D_penalty K=2000 mu=0.3 c=20 on %d striker-facet pairs, force re-formed on the "
                         "device before every sweep (tb2_explicit_attach_contact)" % (n, conn.shape[0], pairs.shape[0])}
 

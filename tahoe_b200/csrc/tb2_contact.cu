@@ -39,7 +39,7 @@ struct tb2_contact {
     int64_t nfacets = 0, nstrikers = 0;
     tb2::DevBuf<int> facets, facet_surface, strikers, hit;
     tb2::DevBuf<unsigned> node_surfaces; // [nn] bit s: the node belongs to surface s (no self contact per surface)
-    tb2::DevBuf<double> striker_area, gap;
+    tb2::DevBuf<double> striker_area, gap, tile_box;
     std::vector<int> h_facets, h_strikers;
     std::vector<double> h_striker_area;
 };
@@ -230,10 +230,67 @@ int contact_launch(tb2_contact* c, double constKd, const double* d_u, const doub
 // on a tie.  The reference collects its candidates through a search grid around the facet midpoint (radius 1.65 |mid - x1|); a facet
 // is skipped here when the striker lies outside the sphere around that box, which never excludes a striker Intersect would accept.
 constexpr int kSearchThreads = 128;
+// the box that holds every point a facet of tile t (kSearchThreads consecutive facets) can accept: midpoints +- their reach
+__global__ void __launch_bounds__(kSearchThreads) k_facet_tile_bounds(int64_t nfacets, const int* __restrict__ facets, const double* __restrict__ X,
+                                                                     const double* __restrict__ u, double* __restrict__ tile_box /*[ntiles][6]*/)
+{
+    __shared__ double lo[3][kSearchThreads / 32], hi[3][kSearchThreads / 32];
+    const int64_t f = blockIdx.x * (int64_t)kSearchThreads + threadIdx.x;
+    double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
+    if (f < nfacets) {
+        double x1[3], m[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int64_t n = facets[3 * f + a];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double c = X[3 * n + i] + u[3 * n + i];
+                if (a == 0) x1[i] = c;
+                m[i] += c;
+            }
+        }
+        double r2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            m[i] /= 3.0;
+            r2 += (m[i] - x1[i]) * (m[i] - x1[i]);
+        }
+        const double reach = sqrt(3.0 * (1.1 * 1.5) * (1.1 * 1.5) * r2 * 1.0001) * 1.0001;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            bl[i] = m[i] - reach;
+            bh[i] = m[i] + reach;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bl[i] = fmin(bl[i], __shfl_xor_sync(0xffffffffu, bl[i], o));
+            bh[i] = fmax(bh[i], __shfl_xor_sync(0xffffffffu, bh[i], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            lo[i][threadIdx.x >> 5] = bl[i];
+            hi[i][threadIdx.x >> 5] = bh[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = lo[threadIdx.x][0], b = hi[threadIdx.x][0];
+        for (int w = 1; w < kSearchThreads / 32; w++) {
+            a = fmin(a, lo[threadIdx.x][w]);
+            b = fmax(b, hi[threadIdx.x][w]);
+        }
+        tile_box[6 * blockIdx.x + threadIdx.x] = a;
+        tile_box[6 * blockIdx.x + 3 + threadIdx.x] = b;
+    }
+}
+
 __global__ void __launch_bounds__(kSearchThreads) k_contact_search(int64_t nstrikers, const int* __restrict__ strikers, int64_t nfacets,
                                                                   const int* __restrict__ facets, const int* __restrict__ facet_surface,
                                                                   const unsigned* __restrict__ node_surfaces, const double* __restrict__ X,
-                                                                  const double* __restrict__ u, int* __restrict__ hit, double* __restrict__ gap)
+                                                                  const double* __restrict__ u, const double* __restrict__ tile_box,
+                                                                  int* __restrict__ hit, double* __restrict__ gap)
 {
     __shared__ double fx[kSearchThreads][9];
     __shared__ double fmid[kSearchThreads][4]; // midpoint and squared reach
@@ -252,7 +309,11 @@ __global__ void __launch_bounds__(kSearchThreads) k_contact_search(int64_t nstri
     double best_h = 0.0;
     for (int64_t f0 = 0; f0 < nfacets; f0 += kSearchThreads) {
         const int64_t f = f0 + threadIdx.x;
-        __syncthreads();
+        {   // a tile none of this CTA's strikers can reach is not even staged (strikers and facets both come in spatial runs)
+            const double* box = tile_box + 6 * (f0 / kSearchThreads);
+            const int near_tile = live && xs[0] >= box[0] && xs[0] <= box[3] && xs[1] >= box[1] && xs[1] <= box[4] && xs[2] >= box[2] && xs[2] <= box[5];
+            if (!__syncthreads_or(near_tile)) continue;
+        }
         if (f < nfacets) {
             double m[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -460,6 +521,7 @@ int tb2_contact_set_surfaces(tb2_contact* c, int64_t nfacets, const int32_t* h_f
     TB2_CUDA(c->hit.alloc(nstrikers > 0 ? nstrikers : 1));
     TB2_CUDA(c->gap.alloc(nstrikers > 0 ? nstrikers : 1));
     TB2_CUDA(c->node_surfaces.alloc(m->nn));
+    TB2_CUDA(c->tile_box.alloc(6 * ((nfacets + kSearchThreads - 1) / kSearchThreads + 1)));
     if (nfacets) TB2_CUDA(cudaMemcpy(c->facets.p, h_facets, (size_t)nfacets * 3 * sizeof(int), cudaMemcpyHostToDevice));
     if (nfacets) TB2_CUDA(cudaMemcpy(c->facet_surface.p, h_facet_surface, (size_t)nfacets * sizeof(int), cudaMemcpyHostToDevice));
     if (nstrikers) TB2_CUDA(cudaMemcpy(c->strikers.p, h_strikers, (size_t)nstrikers * sizeof(int), cudaMemcpyHostToDevice));
@@ -481,8 +543,10 @@ int tb2_contact_search(tb2_contact* c, const double* d_u, int64_t* npairs_out)
     }
     {
         ProfScope ps(m, kProfOther, 1);
+        k_facet_tile_bounds<<<(unsigned)((c->nfacets + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, m->stream>>>(c->nfacets, c->facets.p, m->X.p,
+                                                                                                                            d_u, c->tile_box.p);
         k_contact_search<<<(unsigned)((c->nstrikers + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, m->stream>>>(
-            c->nstrikers, c->strikers.p, c->nfacets, c->facets.p, c->facet_surface.p, c->node_surfaces.p, m->X.p, d_u, c->hit.p, c->gap.p);
+            c->nstrikers, c->strikers.p, c->nfacets, c->facets.p, c->facet_surface.p, c->node_surfaces.p, m->X.p, d_u, c->tile_box.p, c->hit.p, c->gap.p);
     }
     TB2_CUDA(cudaGetLastError());
     std::vector<int> hit((size_t)c->nstrikers);
