@@ -457,19 +457,21 @@ int tb2_contact_set_pairs(tb2_contact* c, int64_t npairs, const int32_t* h_pairs
     ptr.push_back((int)order.size());
     c->ntouched = (int64_t)node.size();
     c->track_blocks = (int)((npairs + kContactThreads - 1) / kContactThreads);
-    TB2_CUDA(c->pairs.alloc(npairs * 4));
-    TB2_CUDA(c->area.alloc(npairs));
-    TB2_CUDA(c->rec.alloc(npairs * 12));
-    TB2_CUDA(c->node.alloc(node.size()));
-    TB2_CUDA(c->slot_ptr.alloc(ptr.size()));
-    TB2_CUDA(c->slot.alloc(order.size()));
-    TB2_CUDA(c->track_n.alloc(c->track_blocks));
-    TB2_CUDA(c->track_h.alloc(c->track_blocks));
-    TB2_CUDA(cudaMemcpy(c->pairs.p, h_pairs, (size_t)npairs * 4 * sizeof(int), cudaMemcpyHostToDevice));
-    TB2_CUDA(cudaMemcpy(c->area.p, h_area, (size_t)npairs * sizeof(double), cudaMemcpyHostToDevice));
-    TB2_CUDA(cudaMemcpy(c->node.p, node.data(), node.size() * sizeof(int), cudaMemcpyHostToDevice));
-    TB2_CUDA(cudaMemcpy(c->slot_ptr.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
-    TB2_CUDA(cudaMemcpy(c->slot.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // the list changes every time a resident run searches: the buffers keep their capacity and the five small arrays go up on the stream
+    TB2_CUDA(c->pairs.reserve(npairs * 4));
+    TB2_CUDA(c->area.reserve(npairs));
+    TB2_CUDA(c->rec.reserve(npairs * 12));
+    TB2_CUDA(c->node.reserve(node.size()));
+    TB2_CUDA(c->slot_ptr.reserve(ptr.size()));
+    TB2_CUDA(c->slot.reserve(order.size()));
+    TB2_CUDA(c->track_n.reserve(c->track_blocks));
+    TB2_CUDA(c->track_h.reserve(c->track_blocks));
+    TB2_CUDA(cudaMemcpyAsync(c->pairs.p, h_pairs, (size_t)npairs * 4 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(c->area.p, h_area, (size_t)npairs * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(c->node.p, node.data(), node.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(c->slot_ptr.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaMemcpyAsync(c->slot.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    TB2_CUDA(cudaStreamSynchronize(m->stream)); // the host vectors go out of scope
     return TB2_OK;
 }
 

@@ -59,8 +59,23 @@ struct DevBuf {
         if (count == 0) return cudaSuccess;
         return cudaMalloc((void**)&p, count * sizeof(T));
     }
+    // room for at least count elements, keeping the allocation when it is large enough (contents are not preserved when it grows)
+    cudaError_t reserve(size_t count)
+    {
+        if (p && count <= cap) {
+            n = count;
+            return cudaSuccess;
+        }
+        const size_t want = count + count / 2 + 64;
+        const cudaError_t e = alloc(want);
+        cap = e == cudaSuccess ? want : 0;
+        n = count;
+        return e;
+    }
+    size_t cap = 0;
     void release()
     {
+        cap = 0;
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
