@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 using namespace tb2;
 
 struct tb2_contact {
@@ -40,6 +42,9 @@ struct tb2_contact {
     tb2::DevBuf<int> facets, facet_surface, strikers, hit;
     tb2::DevBuf<unsigned> node_surfaces; // [nn] bit s: the node belongs to surface s (no self contact per surface)
     tb2::DevBuf<double> striker_area, gap, tile_box;
+    tb2::DevBuf<int> flag, pos, keys, keys_sorted, vals, run_len, counters; // the pair list built on the device after a search
+    tb2::DevBuf<unsigned char> cub_tmp;
+    size_t cub_bytes = 0;
     std::vector<int> h_facets, h_strikers;
     std::vector<double> h_striker_area;
 };
@@ -187,6 +192,7 @@ __global__ void k_contact_nodes(int64_t ntouched, const int* __restrict__ node, 
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= ntouched) return;
     const int64_t n = node[k];
+    if (n == 0x7fffffff) return; // the run of free strikers' keys at the end of a device-built list
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     if (ACCUMULATE) {
         s0 = f[n * 3 + 0];
@@ -392,6 +398,41 @@ __global__ void __launch_bounds__(kSearchThreads) k_contact_search(int64_t nstri
     }
 }
 
+
+// ---- the pair list of a search, built on the device: active strikers compacted in striker order, (node, record slot) keys sorted by
+// node (stable radix sort: ascending pair order within a node), run lengths -> the per-node record lists of k_contact_nodes
+__global__ void k_hit_flags(int64_t ns, const int* __restrict__ hit, int* __restrict__ flag)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s < ns) flag[s] = hit[s] >= 0 ? 1 : 0;
+}
+__global__ void k_build_pairs(int64_t ns, const int* __restrict__ hit, const int* __restrict__ flag, const int* __restrict__ pos,
+                              const int* __restrict__ facets, const int* __restrict__ strikers, const double* __restrict__ striker_area,
+                              int* __restrict__ pairs, double* __restrict__ area, int* __restrict__ keys, int* __restrict__ vals,
+                              int* __restrict__ counters)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    if (s == ns - 1) counters[0] = pos[s] + flag[s]; // number of pairs
+    if (!flag[s]) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) { // keys of free strikers sort to the end
+            keys[4 * s + a] = 0x7fffffff;
+            vals[4 * s + a] = 0;
+        }
+        return;
+    }
+    const int k = pos[s], f = hit[s];
+    const int nd[4] = {facets[3 * f], facets[3 * f + 1], facets[3 * f + 2], strikers[s]};
+    area[k] = striker_area[s];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        pairs[4 * k + a] = nd[a];
+        keys[4 * s + a] = nd[a];
+        vals[4 * s + a] = 4 * k + a;
+    }
+}
+
 } // namespace
 
 namespace tb2 {
@@ -543,27 +584,65 @@ int tb2_contact_search(tb2_contact* c, const double* d_u, int64_t* npairs_out)
         if (npairs_out) *npairs_out = 0;
         return tb2_contact_set_pairs(c, 0, nullptr, nullptr);
     }
+    cudaStream_t st = m->stream;
+    const int64_t ns = c->nstrikers, n4 = 4 * ns;
+    const int T = 128;
+    const unsigned nbs = (unsigned)((ns + T - 1) / T);
+    // buffers of the device-built list: sized by the striker count (every striker can be in one pair), allocated once
+    TB2_CUDA(c->flag.reserve(ns));
+    TB2_CUDA(c->pos.reserve(ns));
+    TB2_CUDA(c->keys.reserve(n4));
+    TB2_CUDA(c->keys_sorted.reserve(n4));
+    TB2_CUDA(c->vals.reserve(n4));
+    TB2_CUDA(c->run_len.reserve(n4 + 1));
+    TB2_CUDA(c->counters.reserve(2));
+    TB2_CUDA(c->pairs.reserve(n4));
+    TB2_CUDA(c->area.reserve(ns));
+    TB2_CUDA(c->rec.reserve(12 * ns));
+    TB2_CUDA(c->node.reserve(n4));
+    TB2_CUDA(c->slot_ptr.reserve(n4 + 1));
+    TB2_CUDA(c->slot.reserve(n4));
+    TB2_CUDA(c->track_n.reserve((ns + kContactThreads - 1) / kContactThreads));
+    TB2_CUDA(c->track_h.reserve((ns + kContactThreads - 1) / kContactThreads));
     {
-        ProfScope ps(m, kProfOther, 1);
-        k_facet_tile_bounds<<<(unsigned)((c->nfacets + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, m->stream>>>(c->nfacets, c->facets.p, m->X.p,
-                                                                                                                            d_u, c->tile_box.p);
-        k_contact_search<<<(unsigned)((c->nstrikers + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, m->stream>>>(
-            c->nstrikers, c->strikers.p, c->nfacets, c->facets.p, c->facet_surface.p, c->node_surfaces.p, m->X.p, d_u, c->tile_box.p, c->hit.p, c->gap.p);
+        size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, b1, c->flag.p, c->pos.p, (int)ns, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, b2, c->keys.p, c->keys_sorted.p, c->vals.p, c->slot.p, (int)n4, 0, 32, st);
+        cub::DeviceRunLengthEncode::Encode(nullptr, b3, c->keys_sorted.p, c->node.p, c->run_len.p, c->counters.p + 1, (int)n4, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, b4, c->run_len.p, c->slot_ptr.p, (int)(n4 + 1), st);
+        const size_t need = std::max(std::max(b1, b2), std::max(b3, b4));
+        if (need > c->cub_bytes) {
+            TB2_CUDA(c->cub_tmp.alloc(need));
+            c->cub_bytes = need;
+        }
     }
+    ProfScope ps(m, kProfOther, 8);
+    k_facet_tile_bounds<<<(unsigned)((c->nfacets + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, st>>>(c->nfacets, c->facets.p, m->X.p, d_u,
+                                                                                                                c->tile_box.p);
+    k_contact_search<<<(unsigned)((ns + kSearchThreads - 1) / kSearchThreads), kSearchThreads, 0, st>>>(
+        ns, c->strikers.p, c->nfacets, c->facets.p, c->facet_surface.p, c->node_surfaces.p, m->X.p, d_u, c->tile_box.p, c->hit.p, c->gap.p);
+    k_hit_flags<<<nbs, T, 0, st>>>(ns, c->hit.p, c->flag.p);
+    size_t bytes = c->cub_bytes;
+    TB2_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->flag.p, c->pos.p, (int)ns, st));
+    k_build_pairs<<<nbs, T, 0, st>>>(ns, c->hit.p, c->flag.p, c->pos.p, c->facets.p, c->strikers.p, c->striker_area.p, c->pairs.p, c->area.p, c->keys.p,
+                                    c->vals.p, c->counters.p);
+    bytes = c->cub_bytes;
+    TB2_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys.p, c->keys_sorted.p, c->vals.p, c->slot.p, (int)n4, 0, 32, st));
+    TB2_CUDA(cudaMemsetAsync(c->run_len.p, 0, (size_t)(n4 + 1) * sizeof(int), st)); // run lengths beyond the last run stay 0 for the scan
+    bytes = c->cub_bytes;
+    TB2_CUDA(cub::DeviceRunLengthEncode::Encode(c->cub_tmp.p, bytes, c->keys_sorted.p, c->node.p, c->run_len.p, c->counters.p + 1, (int)n4, st));
+    bytes = c->cub_bytes;
+    TB2_CUDA(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->run_len.p, c->slot_ptr.p, (int)(n4 + 1), st));
     TB2_CUDA(cudaGetLastError());
-    std::vector<int> hit((size_t)c->nstrikers);
-    TB2_CUDA(cudaMemcpyAsync(hit.data(), c->hit.p, hit.size() * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    TB2_CUDA(cudaStreamSynchronize(m->stream));
-    std::vector<int32_t> pairs;
-    std::vector<double> area;
-    for (int64_t s = 0; s < c->nstrikers; s++) {
-        if (hit[s] < 0) continue;
-        for (int a = 0; a < 3; a++) pairs.push_back(c->h_facets[3 * (size_t)hit[s] + a]);
-        pairs.push_back(c->h_strikers[s]);
-        area.push_back(c->h_striker_area[s]);
-    }
-    if (npairs_out) *npairs_out = (int64_t)area.size();
-    return tb2_contact_set_pairs(c, (int64_t)area.size(), pairs.data(), area.data());
+    int h[2] = {0, 0};
+    TB2_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    TB2_CUDA(cudaStreamSynchronize(st)); // the one host round trip of a search: two integers
+    c->npairs = h[0];
+    c->ntouched = h[1]; // includes the run of free strikers' keys (skipped by the node kernel)
+    c->track_blocks = (int)((c->npairs + kContactThreads - 1) / kContactThreads);
+    c->version++;
+    if (npairs_out) *npairs_out = c->npairs;
+    return TB2_OK;
 }
 
 int tb2_contact_get_pairs(tb2_contact* c, int64_t* npairs, int32_t* h_pairs, double* h_area)
