@@ -4,8 +4,10 @@
  * Tahoe has no FFI today: the boundary is three C++ abstract classes.  Every entry point
  * below names the reference member function (file:line under the Tahoe source tree) whose work it
  * performs, so that the C++ plugin classes in tahoe_b200/host/ (CudaSolidElementT : SolidElementT's
- * subclasses, CudaPCGMatrixT : GlobalMatrixT, CudaPCGSolverT : PCGSolver_LS, CudaExplicitSolverT : SolverT) are thin
+ * subclasses, CudaPCGMatrixT : MSRMatrixT, CudaPCGSolverT : PCGSolver_LS, CudaExplicitSolverT : SolverT with
+ * CudaExplicitCDIntegrator : ExplicitCDIntegrator, CudaPenaltyContact3DT : PenaltyContact3DT, FastGeomInputT : TahoeInputT) are thin
  * forwarding shells.  INTEGRATION.md shows the reference-side registration.
+ * The host-only entry points (tb2_geom_*, tb2_partition_*, tb2_secant_search_host) make no CUDA call and work without a device.
  *
  * Conventions (identical to the reference):
  *   - nodal arrays are [node][dof] doubles (dArray2DT), ndof = nsd = 3;
