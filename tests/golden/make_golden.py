@@ -208,6 +208,18 @@ def main():
     # viscous damping switched on as well (all three force terms of PenaltyContact3DT::RHSDriver active, velocity-based friction)
     if want("ref_contact_cubes_1"):
         contact_case("ref_contact_cubes_1", "level.2/contact_simple/cubes.1.xml", ["--every", "1"])
+    # more of the reference's own contact inputs, for the oracle's force and search (CPU tests): a second static two-cube case, the
+    # quasi-static sliding case (30 steps, pairs change from step to step), the damped impact and the Hertz sphere cut short
+    if want("ref_contact_cubes_2"):
+        contact_case("ref_contact_cubes_2", "level.2/contact_simple/cubes.2.xml", ["--every", "1"])
+    if want("ref_contact_sliding_3d"):
+        contact_case("ref_contact_sliding_3d", "level.2/contact_simple/sliding.3D.xml", ["--every", "5"])
+    if want("ref_contact_impact_damped"):
+        contact_case("ref_contact_impact_damped", "level.5/explicit_benchmark/vectorized_cubes_impact_damped.xml", ["--every", "250"],
+                     edits=(('output_format="ExodusII"', ""), ('num_steps="5000"', 'num_steps="1500"')))
+    if want("ref_contact_hertz_explicit"):
+        contact_case("ref_contact_hertz_explicit", "level.5/hertz/hertz_explicit.xml", ["--every", "400"],
+                     edits=(('output_format="ExodusII"', ""), ('num_steps="10000"', 'num_steps="1200"')))
     if want("ref_contact_sliding_friction"):
         contact_case("ref_contact_sliding_friction", "level.5/explicit_benchmark/vectorized_cubes_friction.xml", ["--every", "300"],
                      edits=(('output_format="ExodusII"', ""), ('num_steps="5000"', 'num_steps="1200"'),
