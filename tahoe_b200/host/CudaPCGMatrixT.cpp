@@ -204,9 +204,13 @@ void CudaPCGMatrixT::BackSubstitute(dArrayT& result)
 	     << ", host MSR structure " << (fHostStructure ? "built" : "not built") << '\n';
 	dArrayT x(result.Length());
 	x = 0.0;
-	int status = tb2_matrix_pcg_host(A, result.Pointer(), x.Pointer(), fRelTol, fAbsTol, fMaxIterations, &fLastIterations, &fLastResidual);
+	/* a non-symmetric system (J2Simo3D's consistent tangent: GlobalT::kNonSymmetric, which the reference hands to an LU, SolverT.cpp:1108-1109)
+	 * goes to the Jacobi-preconditioned BiCGStab, a symmetric one to the PCG */
+	int status = fSymmetric
+		? tb2_matrix_pcg_host(A, result.Pointer(), x.Pointer(), fRelTol, fAbsTol, fMaxIterations, &fLastIterations, &fLastResidual)
+		: tb2_matrix_bicgstab_host(A, result.Pointer(), x.Pointer(), fRelTol, fAbsTol, fMaxIterations, &fLastIterations, &fLastResidual);
 	if (status != TB2_OK) ExceptionT::GeneralFail(caller, "%s", tb2_last_error());
-	fOut << " CudaPCGMatrixT: " << fLastIterations << " PCG iterations, |r| = " << fLastResidual << '\n';
+	fOut << " CudaPCGMatrixT: " << fLastIterations << (fSymmetric ? " PCG" : " BiCGStab") << " iterations, |r| = " << fLastResidual << '\n';
 	/* an iterative solve that ran out of iterations is a failed solve: GlobalMatrixT::Solve catches the exception and returns
 	 * false (GlobalMatrixT.cpp:77-113), as it does for a zero pivot of a direct solver */
 	int converged = 1;

@@ -156,6 +156,11 @@ def _cases():
                                                            "body_force": {"schedule": 1, "vector": [0.0, 0.3, -9.81]}},
                                                "material": simo, "materials": [simo, dict(simo, density=3.0, mu=8.0)],
                                                "solver": {"type": "linear_solver", "matrix": "diagonal_matrix"}}, None),
+        # configs[3] through the executable: UL + Simo_J2 under Tahoe's Newton with the device-assembled non-symmetric tangent solved by the
+        # Jacobi-BiCGStab of <CUDA_PCG_matrix> (the reference: LU)
+        "static_ul_j2_bicgstab": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
+                                   "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton},
+                                  dict(newton, matrix="CUDA_PCG_matrix", matrix_attrs='rel_tolerance="1.0e-12" max_iterations="20000"')),
         # J2: device K1 with history, Tahoe's host tangent + SPOOLES (non-symmetric tangent)
         "static_ul_j2_lu": ({"time": {"num_steps": 3, "time_step": 1.0 / 3, "schedules": [RAMP]}, "integrator": "static", "kbc": pull, "fbc": [],
                              "element": {"type": "updated_lagrangian"}, "material": j2, "solver": newton}, None),
